@@ -1,0 +1,262 @@
+/*
+ * vag_nmt.h — C ABI of libvagnmt.so: the B200 (sm_100a) kernels behind the VAG-NMT
+ * per-timestep translation hot path.
+ *
+ * The reference (Eurus-Holmes/VAG-NMT) has no FFI: its boundary is the Python
+ * nn.Module API.  The Python package vag_nmt_b200 mirrors that
+ * API and binds this library with ctypes; every entry point below names the reference
+ * code (file:line, relative to the upstream repository root) whose arithmetic it
+ * replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - row-major, strides (ld*) in ELEMENTS; weights keep PyTorch's [out, in] layout;
+ *   - no allocation, no host synchronisation and no global state inside a call:
+ *     scratch is caller-owned (…_workspace_bytes() says how much);
+ *   - every call enqueues on `stream` (a cudaStream_t) and returns a vag_status;
+ *   - on failure vag_last_error() (thread-local) describes the reason.
+ */
+#ifndef VAG_NMT_H
+#define VAG_NMT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* vag_stream_t; /* cudaStream_t */
+
+typedef enum {
+    VAG_OK = 0,
+    VAG_ERR_INVALID = -1,     /* bad argument (null pointer, non-positive size, unsorted lengths …) */
+    VAG_ERR_CUDA = -2,        /* a CUDA runtime call / launch failed */
+    VAG_ERR_WORKSPACE = -3,   /* caller workspace too small */
+    VAG_ERR_UNSUPPORTED = -4  /* shape outside what the kernels implement */
+} vag_status;
+
+const char* vag_last_error(void);
+int vag_abi_version(void);
+/* 1 when the current device is sm_100 (B200); kernels are compiled for sm_100a only. */
+int vag_device_supported(void);
+/* Number of kernels this library has launched in the process so far (diagnostic; bench.py reports the delta). */
+long long vag_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * Dense contraction  y = act(x · Wᵀ + bias [+ y])
+ * Replaces every nn.Linear / F.linear on the path (layers/NMT_Decoder.py:38-40,127,137,143;
+ * layers/VSE_Imagine_Enc.py:57-58,123,138; decoderini V11:118) and the gate GEMMs inside
+ * nn.GRU (layers/Encoder.py:58, layers/NMT_Decoder.py:121,129).
+ * ---------------------------------------------------------------------------------- */
+enum {
+    VAG_LIN_TANH = 1,       /* y = tanh(...) */
+    VAG_LIN_ACCUMULATE = 2, /* add the previous content of y before the activation */
+    VAG_LIN_FORCE_SIMT = 4, /* never take the tensor-core path (used by parity tests) */
+    VAG_LIN_FORCE_TC = 8    /* fail with VAG_ERR_UNSUPPORTED instead of falling to SIMT FP32 */
+};
+/* x [rows, in_dim] (ld ldx), w [out_dim, in_dim] (ld ldw), bias [out_dim] or NULL,
+ * y [rows, out_dim] (ld ldy). */
+int vag_linear_f32(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw,
+                   const float* bias, int rows, int in_dim, int out_dim, int flags, vag_stream_t stream);
+
+/* out[r, :] = table[ids[r], :]   (nn.Embedding lookups: Encoder.py:50, NMT_Decoder.py:118) */
+int vag_embed_rows_f32(float* out, int64_t ldo, const float* table, int dim, const int64_t* ids, int rows,
+                       int64_t table_rows, vag_stream_t stream);
+
+/* PyTorch GRU cell gates (order r, z, n) given the two pre-activations
+ *   gi = W_ih x + b_ih   [rows, 3H]      gh = W_hh h + b_hh   [rows, 3H]
+ *   h' = (1-z) n + z h    with r = σ(gi_r+gh_r), z = σ(gi_z+gh_z), n = tanh(gi_n + r·gh_n)
+ * h_out2 (optional) receives a second copy of h' (the encoder writes its context rows with it).
+ * Replaces the cuDNN/ATen GRU cell behind Encoder.py:58 and NMT_Decoder.py:121,129. */
+int vag_gru_gates_f32(float* h_out, int64_t ld_ho, float* h_out2, int64_t ld_ho2, const float* gi, int64_t ld_gi,
+                      const float* gh, int64_t ld_gh, const float* h_prev, int64_t ld_hp, int rows, int H,
+                      vag_stream_t stream);
+
+/* Fused attention: score → masked softmax over T → context.
+ *   mode VAG_ATTN_MLP : s[n,t] = Σ_c v[c]·tanh(q[n,c] + keys[b,t,c])   BahdanauAttn, NMT_Decoder.py:27-51
+ *   mode VAG_ATTN_DOT : s[n,t] = Σ_c q[n,c]·keys[b,t,c]                 ImagineAttn.score_dot, VSE_Imagine_Enc.py:48-65
+ *   α[n,:] = softmax_t(s[n,t] where mask[b,t] != 0 else -inf);   c[n,:] = Σ_t α[n,t]·ctx[b,t,:]   (NMT_Decoder.py:126)
+ * Row n belongs to sentence b = n / rows_per_sent: the K beams of a sentence share keys/ctx, which are
+ * never tiled K times (the reference does, V11:253-254).  keys/ctx are SENTENCE-MAJOR [B, T, C].
+ * alpha may be NULL. */
+enum { VAG_ATTN_MLP = 0, VAG_ATTN_DOT = 1 };
+int vag_attention_f32(float* c_out, int64_t ld_c, float* alpha, const float* q, int64_t ld_q, const float* keys,
+                      const float* ctx, const float* v, const float* mask, int rows, int rows_per_sent, int T,
+                      int C, int mode, vag_stream_t stream);
+
+/* z[b,:] = split·ctx_vec[b,:] + (1-split)·Σ_t ctx[b,t,:] / Σ_t mask[b,t]     (V11:118,201; V2:85,142)
+ * ctx_vec may be NULL (text-only model: z = mean). */
+int vag_init_mix_f32(float* z, const float* ctx_vec, const float* ctx, const float* mask, float split, int B,
+                     int T, int C, vag_stream_t stream);
+
+/* x[r,:] /= max(‖x[r,:]‖₂, 1e-12)      utils/utils.py:6-10 */
+int vag_l2norm_rows_f32(float* x, int64_t ldx, int rows, int dim, vag_stream_t stream);
+
+/* logp = log_softmax(logits) row-wise (NMT_Decoder.py:143).  In place when logp == logits. */
+int vag_log_softmax_f32(float* logp, const float* logits, int rows, int V, vag_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Encoder  (LIUMCVC_Encoder.forward, layers/Encoder.py:36-65, eval-mode dropouts)
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+    int E, H;                 /* embedding size, hidden size per direction */
+    int64_t vocab;            /* rows of emb */
+    const float* emb;         /* encoder.embedding.weight [vocab, E] */
+    const float* w_ih[2];     /* encoder.gru.weight_ih_l0{,_reverse} [3H, E] */
+    const float* w_hh[2];     /* [3H, H] */
+    const float* b_ih[2];     /* [3H] */
+    const float* b_hh[2];     /* [3H] */
+} vag_encoder_weights;
+
+size_t vag_encoder_workspace_bytes(int B, int T, int E, int H);
+/* src int64 [B, T] 0-padded, rows sorted by length descending; lengths_host[B] (HOST, like the reference's
+ * python list).  ctx_out [B, T, 2H] sentence-major (exact zeros at pads), mask_out [B, T] (1.0 where src != 0). */
+int vag_encoder_fwd_f32(const vag_encoder_weights* w, const int64_t* src, const int32_t* lengths_host, int B, int T,
+                        float* ctx_out, float* mask_out, void* workspace, size_t workspace_bytes,
+                        vag_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Visual-attention text pooling  (VSE_Imagine_Enc.forward/get_emb_vec, layers/VSE_Imagine_Enc.py:110-172,
+ * ImagineAttn :29-79, l2norm utils/utils.py:6-10)
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+    int I, C, S;              /* image feature size, context size (2H), shared embedding size */
+    int method;               /* VAG_ATTN_DOT or VAG_ATTN_MLP (imagine_attn 'dot' / 'mlp') */
+    int activation;           /* activation_vse */
+    const float* im_w;        /* vse_imagine.im_embedding.weight [S, I] */
+    const float* im_b;        /* [S] */
+    const float* txt_w;       /* vse_imagine.text_embedding.weight [S, C] */
+    const float* txt_b;       /* [S] */
+    const float* ctx2ctx_w;   /* vse_imagine.imagine_attn.ctx2ctx.weight [C, C] */
+    const float* emb2ctx_w;   /* vse_imagine.imagine_attn.emb2ctx.weight [C, S] */
+    const float* mlp_w;       /* vse_imagine.imagine_attn.mlp.weight [C] (method mlp only) */
+} vag_vse_weights;
+
+size_t vag_vse_workspace_bytes(int B, int T, int I, int C, int S);
+/* im [B, I]; ctx [B, T, C]; mask [B, T] →
+ * im_emb [B, S], txt_emb [B, S], ctx_vec [B, C], beta [B, T] (beta may be NULL). */
+int vag_vse_pool_fwd_f32(const vag_vse_weights* w, const float* im, const float* ctx, const float* mask, int B, int T,
+                         float* im_emb, float* txt_emb, float* ctx_vec, float* beta, void* workspace,
+                         size_t workspace_bytes, vag_stream_t stream);
+
+/* Bidirectional hinge ranking loss, SUM over pairs (losses/PairwiseRankingLoss.py:9-24); with
+ * one_direction != 0 only cost_s (losses/ImageRetrievalRankingLoss.py:9-21).
+ * im [B, S], s [B, S] → loss_out[1]; grad_im/grad_s ([B, S], may both be NULL) receive dLoss/d·. */
+size_t vag_rank_loss_workspace_bytes(int B, int S);
+int vag_rank_loss_f32(const float* im, const float* s, int B, int S, float margin, int one_direction,
+                      float* loss_out, float* grad_im, float* grad_s, void* workspace, size_t workspace_bytes,
+                      vag_stream_t stream);
+
+/* ranks[i] = #{j : q_i·g_j > q_i·g_i} + #{j < i : q_i·g_j == q_i·g_i}   (utils/im_retrieval_eval.py:15-22) */
+size_t vag_recall_ranks_workspace_bytes(int n, int S);
+int vag_recall_ranks_f32(const float* queries, const float* gallery, int n, int S, int32_t* ranks, void* workspace,
+                         size_t workspace_bytes, vag_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Conditional-GRU attention decoder  (NMT_Decoder.forward, layers/NMT_Decoder.py:109-145)
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+    int E, H, C;              /* embedding, hidden, context (2·encoder H) */
+    int64_t V;                /* target vocabulary */
+    const float* emb;         /* decoder.embedding.weight [V, E] */
+    const float* gru1_w_ih;   /* [3H, E] */
+    const float* gru1_w_hh;   /* [3H, H] */
+    const float* gru1_b_ih;
+    const float* gru1_b_hh;
+    const float* attn_h_w;    /* decoder.attn.attn_h.weight [C, H] */
+    const float* attn_e_w;    /* decoder.attn.attn_e.weight [C, C] */
+    const float* attn_v;      /* decoder.attn.v [C] */
+    const float* c2h_w;       /* decoder.context2hid.weight [H, C] */
+    const float* gru2_w_ih;   /* [3H, H] */
+    const float* gru2_w_hh;   /* [3H, H] */
+    const float* gru2_b_ih;
+    const float* gru2_b_hh;
+    const float* w1_w;        /* [E, H] */
+    const float* w1_b;
+    const float* w2_w;        /* [E, C] */
+    const float* w2_b;
+    const float* w3_w;        /* [E, E] */
+    const float* w3_b;
+    const float* out_w;       /* decoder.out.weight [V, E] (== emb when tied, NMT_Decoder.py:105-106) */
+    const float* out_b;       /* [V] */
+    const float* ini_w;       /* decoderini.weight [H, C]  (V11:75) */
+    const float* ini_b;       /* [H] */
+} vag_decoder_weights;
+
+/* Hoisted step-invariant half of the attention MLP: keys[b,t,:] = attn_e(ctx[b,t,:])
+ * (the reference recomputes it on the K-times tiled context every step, NMT_Decoder.py:39-40,47). */
+int vag_attn_keys_f32(const vag_decoder_weights* w, const float* ctx, int B, int T, float* keys,
+                      vag_stream_t stream);
+
+/* h0 = tanh(decoderini(split·ctx_vec + (1-split)·mean_t ctx))  (V11:118,201; V2:85,142).
+ * workspace: B·C floats. */
+int vag_decoder_init_f32(const vag_decoder_weights* w, const float* ctx_vec, const float* ctx, const float* mask,
+                         float split, int B, int T, float* h0, void* workspace, size_t workspace_bytes,
+                         vag_stream_t stream);
+
+size_t vag_decoder_step_workspace_bytes(int rows, int E, int H, int C, int64_t V);
+/* One decoder step on `rows` rows (rows_per_sent consecutive rows share a sentence).
+ * tokens int64 [rows]; h_prev [rows, H]; keys/ctx [B, T, C]; mask [B, T] →
+ * h_out [rows, H]; logits_or_logp [rows, V] (log-softmax applied when want_logp != 0);
+ * alpha_out [rows, T] optional (NULL to skip). */
+int vag_decoder_step_f32(const vag_decoder_weights* w, const int64_t* tokens, const float* h_prev, const float* keys,
+                         const float* ctx, const float* mask, int rows, int rows_per_sent, int T, float* h_out,
+                         float* logits_or_logp, int want_logp, float* alpha_out, void* workspace,
+                         size_t workspace_bytes, vag_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Beam search  (V11.beamsearch, models/NMT_AttentionImagine_Seq2Seq_Beam_V11.py:233-337;
+ * identical text-only copy models/NMT_Seq2Seq_Beam_V2.py:173-276)
+ * ---------------------------------------------------------------------------------- */
+/* One selection step on materialised log-probabilities (the op the parity tests drive with
+ * hand-crafted logp): repeat suppression (V11:279-280), finished-hypothesis masking (:291-294),
+ * cand = nll + logp (:297), top-K per sentence (:300) in canonical order (score desc, flat index asc).
+ *   step == 0 : logp [B, V], picks top-K of each row;   step > 0 : logp [B·K, V].
+ *   prev_tokens int64 [B, K] (tokens chosen at step-1; ignored at step 0)
+ *   nll [B, K] in/out;  tokens_out int64 [B, K];  parents_out int32 [B, K] (index of the parent beam). */
+int vag_beam_select_f32(const float* logp, int64_t ld_logp, const int64_t* prev_tokens, float* nll,
+                        int64_t* tokens_out, int32_t* parents_out, int B, int K, int64_t V, int step,
+                        int avoid_double, vag_stream_t stream);
+
+size_t vag_beam_decode_workspace_bytes(int B, int K, int T, int L, int E, int H, int C, int64_t V);
+/* The whole loop: L decoder steps on B·K rows + selection + parent reorder, the all-finished early stop
+ * evaluated on the device (the reference synchronises with the host every step, V11:266-267), then the
+ * epilogue (:315-337): forced final EOS, length normalisation by #tokens>3, best hypothesis per sentence.
+ *   h0 [B, H]; ctx/keys [B, T, C]; mask [B, T]
+ *   hyp_out int64 [B, L]   tokens of the best hypothesis (full row of the beam, EOS/pad included)
+ *   hyp_len int32 [B]      number of tokens before the first EOS (what the reference returns)
+ *   beam_out int64 [L, B, K], nll_out [B, K] (un-normalised), steps_out int32[1]: optional (NULL to skip) */
+int vag_beam_decode_f32(const vag_decoder_weights* w, const float* h0, const float* keys, const float* ctx,
+                        const float* mask, int B, int K, int T, int L, int avoid_double, int64_t* hyp_out,
+                        int32_t* hyp_len, int64_t* beam_out, float* nll_out, int32_t* steps_out, void* workspace,
+                        size_t workspace_bytes, vag_stream_t stream);
+
+/* Greedy branch (beam_size == 1, V11:207-226): tokens_out int64 [B, L] = argmax at every step. */
+int vag_greedy_decode_f32(const vag_decoder_weights* w, const float* h0, const float* keys, const float* ctx,
+                          const float* mask, int B, int T, int L, int64_t* tokens_out, void* workspace,
+                          size_t workspace_bytes, vag_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Training-side forward pieces (V11.forward :136-164)
+ * ---------------------------------------------------------------------------------- */
+/* loss_rows[r] += -weight[tgt[r]] · logp[r, tgt[r]]  with logp = log_softmax(logits) computed on the fly
+ * (nn.NLLLoss(weight, reduce=False), nmt_multimodal_beam_DE.py:286-291).  weight may be NULL (all ones).
+ * lse_out [rows] optional: row log-sum-exp kept for the backward pass. */
+int vag_nll_rows_f32(const float* logits, int64_t ld, const int64_t* tgt, const float* weight, int rows, int64_t V,
+                     float* loss_rows, float* lse_out, vag_stream_t stream);
+
+/* out[r] = argmax_v logits[r, v] (ties → lowest index): the free-running branch of forward (V11:157-160)
+ * and greedy decoding (V11:211). */
+int vag_row_argmax_f32(const float* logits, int64_t ld, int rows, int64_t V, int64_t* out, vag_stream_t stream);
+
+/* Loss epilogue of forward (V11:164-166 ; NMT_Seq2Seq_Beam_V2.py:111):
+ *   loss_mt = mean_b( loss_rows[b] / #{t : tgt[b,t] != 0} ),   loss = loss_w·loss_mt + (1-loss_w)·loss_vse
+ * loss_vse is a device scalar or NULL (text-only model: loss = loss_mt).  out[3] = {loss, loss_mt, loss_vse}. */
+int vag_translation_loss_f32(const float* loss_rows, const int64_t* tgt, int B, int Tt, const float* loss_vse,
+                             float loss_w, float* out, vag_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VAG_NMT_H */

@@ -1,0 +1,132 @@
+"""ctypes binding of libvagnmt.so (the C ABI declared in include/vag_nmt.h).
+
+There is no fallback: if the library is missing, cannot be loaded, or the device is not a B200 (sm_100), every
+operator raises.  The library is loaded lazily so that the package itself can be imported on a CPU-only box
+(host logic, oracle tests, symbol checks).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+from typing import Optional
+
+import torch
+
+LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libvagnmt.so"
+
+c_f32p = C.c_void_p
+c_i64p = C.c_void_p
+c_i32p = C.c_void_p
+
+
+class EncoderWeights(C.Structure):
+    _fields_ = [("E", C.c_int), ("H", C.c_int), ("vocab", C.c_int64), ("emb", C.c_void_p),
+                ("w_ih", C.c_void_p * 2), ("w_hh", C.c_void_p * 2), ("b_ih", C.c_void_p * 2), ("b_hh", C.c_void_p * 2)]
+
+
+class VseWeights(C.Structure):
+    _fields_ = [("I", C.c_int), ("C", C.c_int), ("S", C.c_int), ("method", C.c_int), ("activation", C.c_int),
+                ("im_w", C.c_void_p), ("im_b", C.c_void_p), ("txt_w", C.c_void_p), ("txt_b", C.c_void_p),
+                ("ctx2ctx_w", C.c_void_p), ("emb2ctx_w", C.c_void_p), ("mlp_w", C.c_void_p)]
+
+
+class DecoderWeights(C.Structure):
+    _fields_ = [("E", C.c_int), ("H", C.c_int), ("C", C.c_int), ("V", C.c_int64), ("emb", C.c_void_p),
+                ("gru1_w_ih", C.c_void_p), ("gru1_w_hh", C.c_void_p), ("gru1_b_ih", C.c_void_p), ("gru1_b_hh", C.c_void_p),
+                ("attn_h_w", C.c_void_p), ("attn_e_w", C.c_void_p), ("attn_v", C.c_void_p), ("c2h_w", C.c_void_p),
+                ("gru2_w_ih", C.c_void_p), ("gru2_w_hh", C.c_void_p), ("gru2_b_ih", C.c_void_p), ("gru2_b_hh", C.c_void_p),
+                ("w1_w", C.c_void_p), ("w1_b", C.c_void_p), ("w2_w", C.c_void_p), ("w2_b", C.c_void_p),
+                ("w3_w", C.c_void_p), ("w3_b", C.c_void_p), ("out_w", C.c_void_p), ("out_b", C.c_void_p),
+                ("ini_w", C.c_void_p), ("ini_b", C.c_void_p)]
+
+
+I, I64, F, P, SZ = C.c_int, C.c_int64, C.c_float, C.c_void_p, C.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/vag_nmt.h declares (tests/test_cabi_symbols.py checks)
+SIGNATURES = {
+    "vag_last_error": (C.c_char_p, []),
+    "vag_abi_version": (I, []),
+    "vag_device_supported": (I, []),
+    "vag_launch_count": (C.c_longlong, []),
+    "vag_linear_f32": (I, [P, I64, P, I64, P, I64, P, I, I, I, I, P]),
+    "vag_embed_rows_f32": (I, [P, I64, P, I, P, I, I64, P]),
+    "vag_gru_gates_f32": (I, [P, I64, P, I64, P, I64, P, I64, P, I64, I, I, P]),
+    "vag_attention_f32": (I, [P, I64, P, P, I64, P, P, P, P, I, I, I, I, I, P]),
+    "vag_init_mix_f32": (I, [P, P, P, P, F, I, I, I, P]),
+    "vag_l2norm_rows_f32": (I, [P, I64, I, I, P]),
+    "vag_log_softmax_f32": (I, [P, P, I, I, P]),
+    "vag_encoder_workspace_bytes": (SZ, [I, I, I, I]),
+    "vag_encoder_fwd_f32": (I, [P, P, P, I, I, P, P, P, SZ, P]),
+    "vag_vse_workspace_bytes": (SZ, [I, I, I, I, I]),
+    "vag_vse_pool_fwd_f32": (I, [P, P, P, P, I, I, P, P, P, P, P, SZ, P]),
+    "vag_rank_loss_workspace_bytes": (SZ, [I, I]),
+    "vag_rank_loss_f32": (I, [P, P, I, I, F, I, P, P, P, P, SZ, P]),
+    "vag_recall_ranks_workspace_bytes": (SZ, [I, I]),
+    "vag_recall_ranks_f32": (I, [P, P, I, I, P, P, SZ, P]),
+    "vag_attn_keys_f32": (I, [P, P, I, I, P, P]),
+    "vag_decoder_init_f32": (I, [P, P, P, P, F, I, I, P, P, SZ, P]),
+    "vag_decoder_step_workspace_bytes": (SZ, [I, I, I, I, I64]),
+    "vag_decoder_step_f32": (I, [P, P, P, P, P, P, I, I, I, P, P, I, P, P, SZ, P]),
+    "vag_beam_select_f32": (I, [P, I64, P, P, P, P, I, I, I64, I, I, P]),
+    "vag_beam_decode_workspace_bytes": (SZ, [I, I, I, I, I, I, I, I64]),
+    "vag_beam_decode_f32": (I, [P, P, P, P, P, I, I, I, I, I, P, P, P, P, P, P, SZ, P]),
+    "vag_greedy_decode_f32": (I, [P, P, P, P, P, I, I, I, P, P, SZ, P]),
+    "vag_nll_rows_f32": (I, [P, I64, P, P, I, I64, P, P, P]),
+    "vag_row_argmax_f32": (I, [P, I64, I, I64, P, P]),
+    "vag_translation_loss_f32": (I, [P, P, I, I, P, F, P, P]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+class VagError(RuntimeError):
+    pass
+
+
+def load_library(path: Optional[os.PathLike] = None) -> C.CDLL:
+    """dlopen the library and attach the signatures.  Raises if it is missing — there is no CPU path."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = Path(path) if path is not None else LIB_PATH
+    if not p.exists():
+        raise VagError(f"{p} not found: build it with `python -m vag_nmt_b200.build` "
+                       "(the CUDA extension is the only implementation; there is no fallback)")
+    lib = C.CDLL(str(p))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def lib() -> C.CDLL:
+    """The library, checked against the current device."""
+    l = load_library()
+    if not torch.cuda.is_available():
+        raise VagError("vag_nmt_b200 needs a CUDA device (B200, sm_100a); none is visible and there is no CPU path")
+    return l
+
+
+def check(status: int) -> None:
+    if status != 0:
+        msg = load_library().vag_last_error().decode(errors="replace")
+        raise VagError(f"libvagnmt status {status}: {msg}")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def f32c(t: torch.Tensor, device=None) -> torch.Tensor:
+    """contiguous fp32 CUDA view/copy of t"""
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()

@@ -1,0 +1,71 @@
+"""In-tree build of libvagnmt.so (sm_100a only) with plain nvcc.
+
+``python -m vag_nmt_b200.build`` or ``__graft_entry__.build()``.  nvcc cross-compiles without a GPU; the
+resulting ``vag_nmt_b200/csrc/libvagnmt.so`` is git-ignored but travels to the GPU box with the snapshot.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+CSRC = Path(__file__).resolve().parent / "csrc"
+LIB = CSRC / "libvagnmt.so"
+OBJ_DIR = CSRC / "build"
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
+              "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _digest(paths) -> str:
+    h = hashlib.sha256()
+    for p in sorted(paths):
+        h.update(p.name.encode())
+        h.update(p.read_bytes())
+    h.update(" ".join(ARCH + NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build_library(force: bool = False, verbose: bool = False) -> Path:
+    sources = sorted(CSRC.glob("*.cu"))
+    headers = sorted(CSRC.glob("*.cuh")) + sorted((CSRC.parent.parent / "include").glob("*.h"))
+    stamp = OBJ_DIR / "stamp.txt"
+    digest = _digest(sources + headers)
+    if not force and LIB.exists() and stamp.exists() and stamp.read_text() == digest:
+        return LIB
+    OBJ_DIR.mkdir(exist_ok=True)
+    nvcc = _nvcc()
+
+    def compile_one(src: Path):
+        obj = OBJ_DIR / (src.stem + ".o")
+        cmd = [nvcc, *ARCH, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        (OBJ_DIR / (src.stem + ".ptxas.log")).write_text(res.stderr)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src.name}:\n{res.stdout}\n{res.stderr}")
+        if verbose:
+            sys.stderr.write(res.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, len(sources))) as ex:
+        objs = list(ex.map(compile_one, sources))
+    link = [nvcc, *ARCH, "-shared", "-o", str(LIB), *map(str, objs)]
+    res = subprocess.run(link, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    stamp.write_text(digest)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,75 @@
+// Library-level entry points: error string, ABI version, device probe, linear dispatch.
+#include "common.cuh"
+#include <string.h>
+#include <atomic>
+
+namespace vag {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int num_sms() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+int linear_simt(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias,
+                int rows, int K, int N, int flags, cudaStream_t st);
+int linear_tc(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias,
+              int rows, int K, int N, int flags, cudaStream_t st, bool* taken);
+
+int linear_dispatch(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias,
+                    int rows, int K, int N, int flags, cudaStream_t st) {
+    if (rows == 0 || N == 0) return VAG_OK;
+    if (!(flags & VAG_LIN_FORCE_SIMT)) {
+        bool taken = false;
+        int s = linear_tc(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags, st, &taken);
+        if (s != VAG_OK) return s;
+        if (taken) return VAG_OK;
+        if (flags & VAG_LIN_FORCE_TC) {
+            set_error("vag_linear_f32: shape rows=%d K=%d N=%d not eligible for the tensor-core path", rows, K, N);
+            return VAG_ERR_UNSUPPORTED;
+        }
+    }
+    return linear_simt(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags, st);
+}
+
+}  // namespace vag
+
+using namespace vag;
+
+extern "C" const char* vag_last_error(void) { return g_err; }
+extern "C" int vag_abi_version(void) { return 1; }
+extern "C" long long vag_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+extern "C" int vag_device_supported(void) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    int major = 0, minor = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+    return (major == 10 && minor == 0) ? 1 : 0;
+}
+
+extern "C" int vag_linear_f32(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw,
+                              const float* bias, int rows, int in_dim, int out_dim, int flags, vag_stream_t stream) {
+    VAG_REQUIRE(y && x && w, "vag_linear_f32: null pointer");
+    VAG_REQUIRE(rows >= 0 && in_dim > 0 && out_dim > 0, "vag_linear_f32: bad shape rows=%d in=%d out=%d", rows, in_dim, out_dim);
+    VAG_REQUIRE(ldx >= in_dim && ldw >= in_dim && ldy >= out_dim, "vag_linear_f32: leading dimension smaller than the row");
+    return linear_dispatch(y, ldy, x, ldx, w, ldw, bias, rows, in_dim, out_dim, flags, (cudaStream_t)stream);
+}

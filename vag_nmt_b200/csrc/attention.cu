@@ -1,0 +1,206 @@
+// Fused attention: score → masked softmax over the source positions → context vector.
+//
+// One CTA per (sentence, group of ≤16 rows).  The K beams of a sentence sit in consecutive rows and share
+// the sentence's keys/ctx [T, C], which are therefore read from HBM/L2 once per CTA instead of K times (the
+// reference tiles them K times, V11:253-254).  Three phases inside the CTA:
+//   1. scores: each warp owns source positions t = warp, warp+nw, …; a lane holds 4-channel slices of the key
+//      row in registers and loops over the rows (q staged in shared memory), warp-shuffle reducing over C;
+//   2. masked softmax over T, one warp per row;
+//   3. context: each thread owns 4 channels, streams ctx[t] once and accumulates all rows.
+// Bandwidth bound: algorithmic bytes per sentence = 2·T·C·4 (keys + ctx) + R·C·4·2 (q in, c out).
+#include "common.cuh"
+#include <math.h>
+
+namespace vag {
+
+constexpr int kMaxRowsPerCta = 16;
+
+template <int MODE, bool VEC>
+__global__ void __launch_bounds__(256)
+attention_kernel(float* __restrict__ c_out, int64_t ld_c, float* __restrict__ alpha_out, const float* __restrict__ q,
+                 int64_t ld_q, const float* __restrict__ keys, const float* __restrict__ ctx,
+                 const float* __restrict__ v, const float* __restrict__ mask, int rows, int rows_per_sent, int T, int C) {
+    extern __shared__ __align__(16) float smem[];
+    const int b = blockIdx.x;
+    const int r_base = blockIdx.y * kMaxRowsPerCta;  // first row of this group inside the sentence
+    const int R = min(kMaxRowsPerCta, rows_per_sent - r_base);
+    const int row0 = b * rows_per_sent + r_base;
+    if (row0 >= rows) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+
+    const int r_cap = min(kMaxRowsPerCta, rows_per_sent);
+    float* q_s = smem;                     // [r_cap][C]
+    float* v_s = q_s + (size_t)r_cap * C;  // [C]
+    float* sc_s = v_s + C;                 // [r_cap][T]  scores then α
+    const float* key_b = keys + (int64_t)b * T * C;
+    const float* ctx_b = ctx + (int64_t)b * T * C;
+    const float* mask_b = mask ? mask + (int64_t)b * T : nullptr;
+
+    for (int i = tid; i < R * C; i += blockDim.x) {
+        const int r = i / C, c = i % C;
+        q_s[r * C + c] = (row0 + r < rows) ? q[(int64_t)(row0 + r) * ld_q + c] : 0.f;
+    }
+    if (MODE == VAG_ATTN_MLP)
+        for (int i = tid; i < C; i += blockDim.x) v_s[i] = v[i];
+    __syncthreads();
+
+    // ---- phase 1: scores
+    for (int t = wid; t < T; t += nw) {
+        const bool live = mask_b ? (mask_b[t] != 0.f) : true;
+        float part[kMaxRowsPerCta];
+#pragma unroll
+        for (int r = 0; r < kMaxRowsPerCta; ++r) part[r] = 0.f;
+        if (live) {
+            const float* kr = key_b + (int64_t)t * C;
+            if (VEC) {
+                for (int c = lane * 4; c < C; c += 128) {
+                    const float4 kv = *reinterpret_cast<const float4*>(kr + c);
+                    float4 vv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (MODE == VAG_ATTN_MLP) vv = *reinterpret_cast<const float4*>(v_s + c);
+#pragma unroll
+                    for (int r = 0; r < kMaxRowsPerCta; ++r) {
+                        if (r < R) {
+                            const float4 qv = *reinterpret_cast<const float4*>(q_s + r * C + c);
+                            if (MODE == VAG_ATTN_MLP) {
+                                part[r] = fmaf(vv.x, tanhf(qv.x + kv.x), part[r]);
+                                part[r] = fmaf(vv.y, tanhf(qv.y + kv.y), part[r]);
+                                part[r] = fmaf(vv.z, tanhf(qv.z + kv.z), part[r]);
+                                part[r] = fmaf(vv.w, tanhf(qv.w + kv.w), part[r]);
+                            } else {
+                                part[r] = fmaf(qv.x, kv.x, part[r]);
+                                part[r] = fmaf(qv.y, kv.y, part[r]);
+                                part[r] = fmaf(qv.z, kv.z, part[r]);
+                                part[r] = fmaf(qv.w, kv.w, part[r]);
+                            }
+                        }
+                    }
+                }
+            } else {
+                for (int c = lane; c < C; c += 32) {
+                    const float kv = kr[c];
+#pragma unroll
+                    for (int r = 0; r < kMaxRowsPerCta; ++r) {
+                        if (r < R) {
+                            if (MODE == VAG_ATTN_MLP)
+                                part[r] = fmaf(v_s[c], tanhf(q_s[r * C + c] + kv), part[r]);
+                            else
+                                part[r] = fmaf(q_s[r * C + c], kv, part[r]);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kMaxRowsPerCta; ++r) {
+            if (r < R) {
+                const float s = warp_sum(part[r]);
+                if (lane == 0) sc_s[r * T + t] = live ? s : -INFINITY;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: softmax over T, one warp per row
+    for (int r = wid; r < R; r += nw) {
+        float* s = sc_s + r * T;
+        float m = -INFINITY;
+        for (int t = lane; t < T; t += 32) m = fmaxf(m, s[t]);
+        m = warp_max(m);
+        float sum = 0.f;
+        for (int t = lane; t < T; t += 32) {
+            const float e = expf(s[t] - m);
+            s[t] = e;
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        for (int t = lane; t < T; t += 32) {
+            const float a = s[t] / sum;
+            s[t] = a;
+            if (alpha_out && row0 + r < rows) alpha_out[(int64_t)(row0 + r) * T + t] = a;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 3: context
+    if (VEC) {
+        for (int c = tid * 4; c < C; c += blockDim.x * 4) {
+            float4 acc[kMaxRowsPerCta];
+#pragma unroll
+            for (int r = 0; r < kMaxRowsPerCta; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int t = 0; t < T; ++t) {
+                if (mask_b && mask_b[t] == 0.f) continue;  // α is exactly 0 there
+                const float4 x = *reinterpret_cast<const float4*>(ctx_b + (int64_t)t * C + c);
+#pragma unroll
+                for (int r = 0; r < kMaxRowsPerCta; ++r) {
+                    if (r < R) {
+                        const float a = sc_s[r * T + t];
+                        acc[r].x = fmaf(a, x.x, acc[r].x);
+                        acc[r].y = fmaf(a, x.y, acc[r].y);
+                        acc[r].z = fmaf(a, x.z, acc[r].z);
+                        acc[r].w = fmaf(a, x.w, acc[r].w);
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < kMaxRowsPerCta; ++r)
+                if (r < R && row0 + r < rows) *reinterpret_cast<float4*>(c_out + (int64_t)(row0 + r) * ld_c + c) = acc[r];
+        }
+    } else {
+        for (int c = tid; c < C; c += blockDim.x) {
+            float acc[kMaxRowsPerCta];
+#pragma unroll
+            for (int r = 0; r < kMaxRowsPerCta; ++r) acc[r] = 0.f;
+            for (int t = 0; t < T; ++t) {
+                if (mask_b && mask_b[t] == 0.f) continue;
+                const float x = ctx_b[(int64_t)t * C + c];
+#pragma unroll
+                for (int r = 0; r < kMaxRowsPerCta; ++r)
+                    if (r < R) acc[r] = fmaf(sc_s[r * T + t], x, acc[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < kMaxRowsPerCta; ++r)
+                if (r < R && row0 + r < rows) c_out[(int64_t)(row0 + r) * ld_c + c] = acc[r];
+        }
+    }
+}
+
+}  // namespace vag
+
+using namespace vag;
+
+extern "C" int vag_attention_f32(float* c_out, int64_t ld_c, float* alpha, const float* q, int64_t ld_q, const float* keys,
+                                 const float* ctx, const float* v, const float* mask, int rows, int rows_per_sent, int T,
+                                 int C, int mode, vag_stream_t stream) {
+    VAG_REQUIRE(c_out && q && keys && ctx, "vag_attention_f32: null pointer");
+    VAG_REQUIRE(mode == VAG_ATTN_MLP || mode == VAG_ATTN_DOT, "vag_attention_f32: bad mode %d", mode);
+    VAG_REQUIRE(mode == VAG_ATTN_DOT || v, "vag_attention_f32: MLP mode needs v");
+    VAG_REQUIRE(rows >= 0 && rows_per_sent > 0 && T > 0 && C > 0, "vag_attention_f32: bad shape");
+    VAG_REQUIRE(rows % rows_per_sent == 0, "vag_attention_f32: rows (%d) not a multiple of rows_per_sent (%d)", rows, rows_per_sent);
+    if (rows == 0) return VAG_OK;
+    const int B = rows / rows_per_sent;
+    const int r_cap = rows_per_sent < kMaxRowsPerCta ? rows_per_sent : kMaxRowsPerCta;
+    const size_t smem = ((size_t)r_cap * C + C + (size_t)r_cap * T) * sizeof(float);
+    if (smem > 227 * 1024) {
+        set_error("vag_attention_f32: C=%d T=%d needs %zu B of shared memory", C, T, smem);
+        return VAG_ERR_UNSUPPORTED;
+    }
+    auto al = [](const void* p) { return ((uintptr_t)p % 16) == 0; };
+    const bool vec = (C % 4 == 0) && (ld_c % 4 == 0) && al(keys) && al(ctx) && al(c_out);
+    dim3 grid(B, ceil_div(rows_per_sent, kMaxRowsPerCta));
+    cudaStream_t st = (cudaStream_t)stream;
+#define VAG_ATTN_LAUNCH(MODE, VEC)                                                                                  \
+    do {                                                                                                            \
+        VAG_CUDA(cudaFuncSetAttribute(attention_kernel<MODE, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                      (int)smem));                                                                  \
+        attention_kernel<MODE, VEC><<<grid, 256, smem, st>>>(c_out, ld_c, alpha, q, ld_q, keys, ctx, v, mask, rows, \
+                                                             rows_per_sent, T, C);                                  \
+    } while (0)
+    if (mode == VAG_ATTN_MLP) {
+        if (vec) VAG_ATTN_LAUNCH(VAG_ATTN_MLP, true); else VAG_ATTN_LAUNCH(VAG_ATTN_MLP, false);
+    } else {
+        if (vec) VAG_ATTN_LAUNCH(VAG_ATTN_DOT, true); else VAG_ATTN_LAUNCH(VAG_ATTN_DOT, false);
+    }
+#undef VAG_ATTN_LAUNCH
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}

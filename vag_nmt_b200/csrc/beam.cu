@@ -1,0 +1,313 @@
+// Beam-search kernels: candidate selection (masking + top-K per sentence), parent reorder, finalisation.
+// Reference: V11.beamsearch, models/NMT_AttentionImagine_Seq2Seq_Beam_V11.py:233-337.
+//
+// Selection = one CTA per sentence scanning its K·V candidates once, coalesced; every thread keeps a sorted
+// private top-K in registers (static indexing only), then K rounds of a block arg-max pop the winners in
+// canonical order (score descending, flat index k·V+v ascending on ties).  HBM bound: the logits are read once.
+#include "common.cuh"
+#include <math.h>
+
+namespace vag {
+
+constexpr int kMaxBeam = 16;
+constexpr int kEOS = 3;
+constexpr float kBeamInf = -1e5f;  // V11:257
+
+__device__ __forceinline__ bool cand_better(float av, int ai, float bv, int bi) {
+    return av > bv || (av == bv && ai < bi);
+}
+
+template <int KMAX>
+struct TopList {
+    float v[KMAX];
+    int i[KMAX];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) { v[j] = -INFINITY; i[j] = 0x7fffffff; }
+    }
+    // keep the best KMAX seen so far, sorted best-first (a superset of the top-K for any K <= KMAX; every
+    // index is static so the list stays in registers)
+    __device__ __forceinline__ void push(float c, int ci) {
+        if (!cand_better(c, ci, v[KMAX - 1], i[KMAX - 1])) return;  // quick reject against the current worst
+        bool prev_better = true;  // "old[j-1] is better than c"; true for j == 0 by convention
+        float carry_v = 0.f; int carry_i = 0;
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) {
+            const float ov = v[j]; const int oi = i[j];
+            const bool old_better = cand_better(ov, oi, c, ci);
+            if (!old_better) {
+                if (prev_better) { v[j] = c; i[j] = ci; }       // insertion point
+                else { v[j] = carry_v; i[j] = carry_i; }       // shifted down
+            }
+            carry_v = ov; carry_i = oi;
+            prev_better = old_better;
+        }
+    }
+    __device__ __forceinline__ void pop() {
+#pragma unroll
+        for (int j = 0; j + 1 < KMAX; ++j) { v[j] = v[j + 1]; i[j] = i[j + 1]; }
+        v[KMAX - 1] = -INFINITY; i[KMAX - 1] = 0x7fffffff;
+    }
+};
+
+// logits [rows, V] (ld), lse [rows] or NULL (then `logits` already holds log-probabilities).
+// done (optional): device flag; when *done != 0 the kernel leaves all state untouched.
+template <int KMAX>
+__global__ void __launch_bounds__(256)
+beam_select_kernel(const float* __restrict__ logits, int64_t ld, const float* __restrict__ lse,
+                   const int64_t* __restrict__ prev_tokens, float* __restrict__ nll, int64_t* __restrict__ tokens_out,
+                   int32_t* __restrict__ parents_out, int K, int64_t V, int step, int avoid_double,
+                   const int* __restrict__ done, int* __restrict__ fin_counter) {
+    if (done && *done) return;
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    __shared__ float nll_s[kMaxBeam];
+    __shared__ float lse_s[kMaxBeam];
+    __shared__ int64_t cur_s[kMaxBeam];
+    __shared__ float red_v[8];
+    __shared__ int red_i[8];
+    __shared__ int red_t[8];
+    __shared__ int win_t;
+
+    const int Kin = step == 0 ? 1 : K;  // rows of this sentence feeding the selection
+    if (tid < Kin) {
+        const int row = b * Kin + tid;
+        nll_s[tid] = step == 0 ? 0.f : nll[(int64_t)b * K + tid];
+        lse_s[tid] = lse ? lse[row] : 0.f;
+        cur_s[tid] = step == 0 ? -1 : prev_tokens[(int64_t)b * K + tid];
+    }
+    __syncthreads();
+
+    TopList<KMAX> top;
+    top.init();
+    const int64_t total = (int64_t)Kin * V;
+    for (int k = 0; k < Kin; ++k) {
+        const float* row = logits + (int64_t)(b * Kin + k) * ld;
+        const float base = nll_s[k];
+        const float l = lse_s[k];
+        const int64_t cur = cur_s[k];
+        const bool fin = (step > 0) && (cur == kEOS);
+        for (int64_t vtok = tid; vtok < V; vtok += blockDim.x) {
+            float lp;
+            if (fin) {
+                lp = (vtok == kEOS) ? 0.f : kBeamInf;  // V11:291-294
+            } else {
+                lp = row[vtok] - l;
+                if (avoid_double && step > 0 && vtok == cur) lp = kBeamInf;  // V11:279-280
+            }
+            const float c = step == 0 ? lp : base + lp;  // V11:297
+            top.push(c, (int)(k * V + vtok));
+        }
+    }
+    (void)total;
+
+    int n_eos = 0;
+    for (int round = 0; round < K; ++round) {
+        float bv = top.v[0];
+        int bi = top.i[0];
+        int bt = tid;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            const int ot = __shfl_xor_sync(0xffffffffu, bt, o);
+            if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; bt = ot; }
+        }
+        if (lane == 0) { red_v[wid] = bv; red_i[wid] = bi; red_t[wid] = bt; }
+        __syncthreads();
+        if (tid == 0) {
+            float fv = red_v[0]; int fi = red_i[0]; int ft = red_t[0];
+            for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+                if (cand_better(red_v[w], red_i[w], fv, fi)) { fv = red_v[w]; fi = red_i[w]; ft = red_t[w]; }
+            win_t = ft;
+            const int64_t tok = (int64_t)fi % V;
+            const int par = (int)((int64_t)fi / V);
+            nll[(int64_t)b * K + round] = fv;
+            tokens_out[(int64_t)b * K + round] = tok;
+            parents_out[(int64_t)b * K + round] = par;
+            n_eos += (tok == kEOS);
+        }
+        __syncthreads();
+        if (tid == win_t) top.pop();
+    }
+    if (tid == 0 && fin_counter) atomicAdd(fin_counter, n_eos);
+}
+
+// Row gather by parent + early-stop bookkeeping.
+//   h_next[b*K + k, :] = h_cur[b*Kin + parents[b,k], :]
+// Block (0,0) thread 0 also turns the per-step EOS counter into the `done` flag / steps_run the way the
+// reference's host-side test does (V11:265-269): all B·K tokens chosen at this step are EOS ⇒ stop.
+__global__ void __launch_bounds__(128)
+beam_advance_kernel(float* __restrict__ h_next, const float* __restrict__ h_cur, const int32_t* __restrict__ parents, int B,
+                    int K, int Kin, int H, int step, int* __restrict__ done, const int* __restrict__ fin_counter,
+                    int* __restrict__ steps_run) {
+    if (*done) return;
+    const int n = blockIdx.x;  // new row
+    const int b = n / K;
+    const int p = b * Kin + (Kin == 1 ? 0 : parents[n]);
+    const float4* src = reinterpret_cast<const float4*>(h_cur + (int64_t)p * H);
+    float4* dst = reinterpret_cast<float4*>(h_next + (int64_t)n * H);
+    if (H % 4 == 0) {
+        for (int c = threadIdx.x; c < H / 4; c += blockDim.x) dst[c] = src[c];
+    } else {
+        for (int c = threadIdx.x; c < H; c += blockDim.x) h_next[(int64_t)n * H + c] = h_cur[(int64_t)p * H + c];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) steps_run[0] = step + 1;
+}
+__global__ void beam_done_kernel(int* __restrict__ done, const int* __restrict__ fin_counter, int total) {
+    if (*fin_counter == total) *done = 1;
+}
+
+// Finalisation (V11:315-337): backtrace every final hypothesis through the parent pointers, force EOS in the
+// last row, normalise by #tokens>3 (clamped to 1), take the best hypothesis per sentence.
+// One warp per sentence, lane k = hypothesis k.
+__global__ void __launch_bounds__(32)
+beam_finalize_kernel(const int64_t* __restrict__ tok_hist /*[L,B,K]*/, const int32_t* __restrict__ par_hist /*[L,B,K]*/,
+                     const float* __restrict__ nll, const int* __restrict__ steps_run, int B, int K, int L,
+                     int64_t* __restrict__ hyp_out /*[B,L]*/, int32_t* __restrict__ hyp_len, int64_t* __restrict__ beam_out /*[L,B,K] or NULL*/) {
+    const int b = blockIdx.x;
+    const int k = threadIdx.x;
+    const int S = *steps_run;  // rows of the beam that were filled
+    int count = 0;
+    if (k < K) {
+        int p = k;
+        for (int di = L - 1; di >= 0; --di) {
+            int64_t tok;
+            if (di >= S) {
+                tok = 0;
+            } else {
+                tok = tok_hist[((int64_t)di * B + b) * K + p];
+                p = par_hist[((int64_t)di * B + b) * K + p];
+            }
+            if (di == L - 1) tok = kEOS;  // V11:315
+            if (beam_out) beam_out[((int64_t)di * B + b) * K + k] = tok;
+            count += (tok > 3);
+        }
+    }
+    float score = -INFINITY;
+    if (k < K) score = nll[(int64_t)b * K + k] / fmaxf((float)count, 1.0f);  // V11:318-321
+    float bv = score;
+    int bk = k;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+        if (ov > bv || (ov == bv && ok < bk)) { bv = ov; bk = ok; }
+    }
+    if (k == bk) {
+        int p = k;
+        int first_eos = L;
+        for (int di = L - 1; di >= 0; --di) {
+            int64_t tok;
+            if (di >= S) {
+                tok = 0;
+            } else {
+                tok = tok_hist[((int64_t)di * B + b) * K + p];
+                p = par_hist[((int64_t)di * B + b) * K + p];
+            }
+            if (di == L - 1) tok = kEOS;
+            hyp_out[(int64_t)b * L + di] = tok;
+            if (tok == kEOS) first_eos = di;
+        }
+        hyp_len[b] = first_eos;
+    }
+}
+
+// Row arg-max over V (greedy decoding, V11:207-216); ties → lowest index.  Writes the token twice:
+// into the [B, L] result (column `step`) and into the next-step input vector.
+__global__ void __launch_bounds__(256)
+row_argmax_kernel(const float* __restrict__ logits, int64_t ld, int64_t V, int64_t* __restrict__ out, int64_t out_stride,
+                  int64_t* __restrict__ next_in) {
+    const int r = blockIdx.x;
+    const float* row = logits + (int64_t)r * ld;
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int64_t i = threadIdx.x; i < V; i += blockDim.x) {
+        const float x = row[i];
+        if (cand_better(x, (int)i, bv, bi)) { bv = x; bi = (int)i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    __shared__ float sv[8];
+    __shared__ int si[8];
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+            if (cand_better(sv[w], si[w], bv, bi)) { bv = sv[w]; bi = si[w]; }
+        out[(int64_t)r * out_stride] = bi;
+        if (next_in) next_in[r] = bi;
+    }
+}
+
+int beam_select(const float* logits, int64_t ld, const float* lse, const int64_t* prev_tokens, float* nll,
+                int64_t* tokens_out, int32_t* parents_out, int B, int K, int64_t V, int step, int avoid_double,
+                const int* done, int* fin_counter, cudaStream_t st) {
+    if (K > kMaxBeam) {
+        set_error("beam size %d > %d is not supported", K, kMaxBeam);
+        return VAG_ERR_UNSUPPORTED;
+    }
+    if ((int64_t)K * V >= 0x7fffffff) {
+        set_error("K*V overflows the 31-bit candidate index");
+        return VAG_ERR_UNSUPPORTED;
+    }
+    if (K <= 4)
+        beam_select_kernel<4><<<B, 256, 0, st>>>(logits, ld, lse, prev_tokens, nll, tokens_out, parents_out, K, V, step, avoid_double, done, fin_counter);
+    else if (K <= 8)
+        beam_select_kernel<8><<<B, 256, 0, st>>>(logits, ld, lse, prev_tokens, nll, tokens_out, parents_out, K, V, step, avoid_double, done, fin_counter);
+    else if (K <= 12)
+        beam_select_kernel<12><<<B, 256, 0, st>>>(logits, ld, lse, prev_tokens, nll, tokens_out, parents_out, K, V, step, avoid_double, done, fin_counter);
+    else
+        beam_select_kernel<16><<<B, 256, 0, st>>>(logits, ld, lse, prev_tokens, nll, tokens_out, parents_out, K, V, step, avoid_double, done, fin_counter);
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
+int beam_advance(float* h_next, const float* h_cur, const int32_t* parents, int B, int K, int Kin, int H, int step,
+                 int* done, int* fin_counter, int* steps_run, cudaStream_t st) {
+    beam_advance_kernel<<<B * K, 128, 0, st>>>(h_next, h_cur, parents, B, K, Kin, H, step, done, fin_counter, steps_run);
+    VAG_LAUNCH_CHECK();
+    beam_done_kernel<<<1, 1, 0, st>>>(done, fin_counter, B * K);
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
+int beam_finalize(const int64_t* tok_hist, const int32_t* par_hist, const float* nll, const int* steps_run, int B, int K,
+                  int L, int64_t* hyp_out, int32_t* hyp_len, int64_t* beam_out, cudaStream_t st) {
+    beam_finalize_kernel<<<B, 32, 0, st>>>(tok_hist, par_hist, nll, steps_run, B, K, L, hyp_out, hyp_len, beam_out);
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
+int row_argmax(const float* logits, int64_t ld, int rows, int64_t V, int64_t* out, int64_t out_stride, int64_t* next_in,
+               cudaStream_t st) {
+    row_argmax_kernel<<<rows, 256, 0, st>>>(logits, ld, V, out, out_stride, next_in);
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
+}  // namespace vag
+
+using namespace vag;
+
+extern "C" int vag_beam_select_f32(const float* logp, int64_t ld_logp, const int64_t* prev_tokens, float* nll,
+                                   int64_t* tokens_out, int32_t* parents_out, int B, int K, int64_t V, int step,
+                                   int avoid_double, vag_stream_t stream) {
+    VAG_REQUIRE(logp && nll && tokens_out && parents_out, "vag_beam_select_f32: null pointer");
+    VAG_REQUIRE(step == 0 || prev_tokens, "vag_beam_select_f32: prev_tokens required for step > 0");
+    VAG_REQUIRE(B > 0 && K > 0 && V > 0 && ld_logp >= V && step >= 0, "vag_beam_select_f32: bad shape");
+    VAG_REQUIRE(K <= V, "vag_beam_select_f32: beam %d larger than the vocabulary %lld", K, (long long)V);
+    return beam_select(logp, ld_logp, nullptr, prev_tokens, nll, tokens_out, parents_out, B, K, V, step, avoid_double,
+                       nullptr, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int vag_row_argmax_f32(const float* logits, int64_t ld, int rows, int64_t V, int64_t* out, vag_stream_t stream) {
+    VAG_REQUIRE(logits && out, "vag_row_argmax_f32: null pointer");
+    VAG_REQUIRE(rows >= 0 && V > 0 && ld >= V, "vag_row_argmax_f32: bad shape");
+    if (rows == 0) return VAG_OK;
+    return row_argmax(logits, ld, rows, V, out, 1, nullptr, (cudaStream_t)stream);
+}

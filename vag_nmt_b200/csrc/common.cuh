@@ -1,0 +1,93 @@
+// Shared helpers for libvagnmt.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/vag_nmt.h"
+
+namespace vag {
+
+void set_error(const char* fmt, ...);
+
+#define VAG_REQUIRE(cond, ...)                 \
+    do {                                       \
+        if (!(cond)) {                         \
+            ::vag::set_error(__VA_ARGS__);     \
+            return VAG_ERR_INVALID;            \
+        }                                      \
+    } while (0)
+
+#define VAG_CUDA(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            ::vag::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return VAG_ERR_CUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+
+// every kernel launch of the library goes through this macro; the counter backs vag_launch_count()
+void count_launch();
+#define VAG_LAUNCH_CHECK()               \
+    do {                                 \
+        ::vag::count_launch();           \
+        VAG_CUDA(cudaGetLastError());    \
+    } while (0)
+
+#define VAG_TRY(call)              \
+    do {                           \
+        int s__ = (call);          \
+        if (s__ != VAG_OK) return s__; \
+    } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Bump allocator over the caller's workspace.
+struct Arena {
+    char* base;
+    size_t size;
+    size_t off;
+    bool overflow;
+    Arena(void* p, size_t n) : base((char*)p), size(n), off(0), overflow(false) {}
+    template <typename T>
+    T* take(size_t count) {
+        size_t start = align_up(off, 256);
+        size_t end = start + count * sizeof(T);
+        if (end > size || base == nullptr) {
+            overflow = true;
+            off = end;
+            return nullptr;
+        }
+        off = end;
+        return (T*)(base + start);
+    }
+};
+// Same arithmetic without memory: used by the *_workspace_bytes() functions.
+struct ArenaSizer {
+    size_t off = 0;
+    template <typename T>
+    void take(size_t count) {
+        off = align_up(off, 256) + count * sizeof(T);
+    }
+    size_t total() const { return align_up(off, 256) + 256; }
+};
+
+int num_sms();
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float sigmoidf_precise(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+}  // namespace vag

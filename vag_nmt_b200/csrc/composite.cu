@@ -1,0 +1,358 @@
+// Host-side composition of the kernels into the reference's operators: encoder, visual-attention pooling,
+// decoder step, beam / greedy decoding.  Everything is enqueued on the caller's stream; no allocation, no
+// host synchronisation.
+#include "common.cuh"
+#include <algorithm>
+#include <vector>
+
+namespace vag {
+
+int linear_dispatch(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias,
+                    int rows, int K, int N, int flags, cudaStream_t st);
+int row_lse(float* lse_out, const float* logits, int64_t ld, int rows, int64_t V, cudaStream_t st);
+int beam_select(const float* logits, int64_t ld, const float* lse, const int64_t* prev_tokens, float* nll,
+                int64_t* tokens_out, int32_t* parents_out, int B, int K, int64_t V, int step, int avoid_double,
+                const int* done, int* fin_counter, cudaStream_t st);
+int beam_advance(float* h_next, const float* h_cur, const int32_t* parents, int B, int K, int Kin, int H, int step,
+                 int* done, int* fin_counter, int* steps_run, cudaStream_t st);
+int beam_finalize(const int64_t* tok_hist, const int32_t* par_hist, const float* nll, const int* steps_run, int B, int K,
+                  int L, int64_t* hyp_out, int32_t* hyp_len, int64_t* beam_out, cudaStream_t st);
+int row_argmax(const float* logits, int64_t ld, int rows, int64_t V, int64_t* out, int64_t out_stride, int64_t* next_in,
+               cudaStream_t st);
+
+// ------------------------------------------------------------------ encoder
+// out[(t*B + b), :] = table[src[b, t], :]  (time-major rows so that a timestep is a contiguous row block),
+// mask[b, t] = src[b, t] != 0   (Encoder.py:47,50)
+__global__ void encoder_embed_kernel(float* __restrict__ out, float* __restrict__ mask, const float* __restrict__ table,
+                                     const int64_t* __restrict__ src, int B, int T, int E, int64_t vocab) {
+    const int row = blockIdx.x * blockDim.y + threadIdx.y;  // t*B + b
+    if (row >= B * T) return;
+    const int t = row / B, b = row % B;
+    int64_t id = src[(int64_t)b * T + t];
+    if (threadIdx.x == 0) mask[(int64_t)b * T + t] = id != 0 ? 1.0f : 0.0f;
+    if (id < 0 || id >= vocab) id = 0;
+    const float* s = table + id * E;
+    float* d = out + (int64_t)row * E;
+    for (int c = threadIdx.x; c < E; c += blockDim.x) d[c] = s[c];
+}
+
+__global__ void fill_i64_kernel(int64_t* p, int64_t v, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+struct EncoderWs {
+    float *x, *gi[2], *gh[2], *h[2];
+};
+template <typename A>
+static void encoder_layout(A& a, int B, int T, int E, int H, EncoderWs* ws) {
+    float* x = (float*)a.template take<float>((size_t)T * B * E);
+    float* gi0 = (float*)a.template take<float>((size_t)T * B * 3 * H);
+    float* gi1 = (float*)a.template take<float>((size_t)T * B * 3 * H);
+    float* gh0 = (float*)a.template take<float>((size_t)B * 3 * H);
+    float* gh1 = (float*)a.template take<float>((size_t)B * 3 * H);
+    float* h0 = (float*)a.template take<float>((size_t)B * H);
+    float* h1 = (float*)a.template take<float>((size_t)B * H);
+    if (ws) { ws->x = x; ws->gi[0] = gi0; ws->gi[1] = gi1; ws->gh[0] = gh0; ws->gh[1] = gh1; ws->h[0] = h0; ws->h[1] = h1; }
+}
+struct SizerAdapter {
+    ArenaSizer s;
+    template <typename T> void* take(size_t n) { s.take<T>(n); return nullptr; }
+};
+struct ArenaAdapter {
+    Arena a;
+    ArenaAdapter(void* p, size_t n) : a(p, n) {}
+    template <typename T> void* take(size_t n) { return a.take<T>(n); }
+};
+
+}  // namespace vag
+
+using namespace vag;
+
+extern "C" size_t vag_encoder_workspace_bytes(int B, int T, int E, int H) {
+    SizerAdapter s;
+    encoder_layout(s, B, T, E, H, nullptr);
+    return s.s.total();
+}
+
+extern "C" int vag_encoder_fwd_f32(const vag_encoder_weights* w, const int64_t* src, const int32_t* lengths_host, int B, int T,
+                                   float* ctx_out, float* mask_out, void* workspace, size_t workspace_bytes,
+                                   vag_stream_t stream) {
+    VAG_REQUIRE(w && src && lengths_host && ctx_out && mask_out, "vag_encoder_fwd_f32: null pointer");
+    VAG_REQUIRE(B > 0 && T > 0 && w->E > 0 && w->H > 0, "vag_encoder_fwd_f32: bad shape");
+    for (int b = 0; b < B; ++b) {
+        VAG_REQUIRE(lengths_host[b] >= 1 && lengths_host[b] <= T, "vag_encoder_fwd_f32: length[%d]=%d outside [1,%d]", b, lengths_host[b], T);
+        VAG_REQUIRE(b == 0 || lengths_host[b] <= lengths_host[b - 1],
+                    "vag_encoder_fwd_f32: lengths must be sorted in decreasing order (pack_padded_sequence, Encoder.py:55)");
+    }
+    VAG_REQUIRE(lengths_host[0] == T, "vag_encoder_fwd_f32: longest sentence (%d) must span the padded width (%d)", lengths_host[0], T);
+    const int E = w->E, H = w->H;
+    cudaStream_t st = (cudaStream_t)stream;
+    ArenaAdapter ar(workspace, workspace_bytes);
+    EncoderWs ws;
+    encoder_layout(ar, B, T, E, H, &ws);
+    if (ar.a.overflow) {
+        set_error("vag_encoder_fwd_f32: workspace %zu B too small", workspace_bytes);
+        return VAG_ERR_WORKSPACE;
+    }
+    {
+        dim3 block(64, 4);
+        encoder_embed_kernel<<<ceil_div(B * T, 4), block, 0, st>>>(ws.x, mask_out, w->emb, src, B, T, E, w->vocab);
+        VAG_LAUNCH_CHECK();
+    }
+    VAG_CUDA(cudaMemsetAsync(ctx_out, 0, (size_t)B * T * 2 * H * sizeof(float), st));
+    // active-row count per timestep (rows sorted by length ⇒ a prefix)
+    std::vector<int> n_act(T);
+    for (int t = 0; t < T; ++t) {
+        int n = 0;
+        while (n < B && lengths_host[n] > t) ++n;
+        n_act[t] = n;
+    }
+    for (int d = 0; d < 2; ++d) {
+        VAG_TRY(linear_dispatch(ws.gi[d], 3 * H, ws.x, E, w->w_ih[d], E, w->b_ih[d], T * B, E, 3 * H, 0, st));
+        VAG_CUDA(cudaMemsetAsync(ws.h[d], 0, (size_t)B * H * sizeof(float), st));
+    }
+    // the two directions are independent chains; interleave them so neighbouring launches can overlap their tails
+    for (int s = 0; s < T; ++s) {
+        for (int d = 0; d < 2; ++d) {
+            const int t = d == 0 ? s : T - 1 - s;
+            const int n = n_act[t];
+            if (n == 0) continue;
+            VAG_TRY(linear_dispatch(ws.gh[d], 3 * H, ws.h[d], H, w->w_hh[d], H, w->b_hh[d], n, H, 3 * H, 0, st));
+            VAG_TRY(vag_gru_gates_f32(ws.h[d], H, ctx_out + (int64_t)t * 2 * H + d * H, (int64_t)T * 2 * H,
+                                      ws.gi[d] + (int64_t)t * B * 3 * H, 3 * H, ws.gh[d], 3 * H, ws.h[d], H, n, H, stream));
+        }
+    }
+    return VAG_OK;
+}
+
+// ------------------------------------------------------------------ visual-attention pooling
+extern "C" size_t vag_vse_workspace_bytes(int B, int T, int I, int C, int S) {
+    ArenaSizer s;
+    s.take<float>((size_t)B * T * C);
+    s.take<float>((size_t)B * C);
+    (void)I; (void)S;
+    return s.total();
+}
+
+extern "C" int vag_vse_pool_fwd_f32(const vag_vse_weights* w, const float* im, const float* ctx, const float* mask, int B, int T,
+                                    float* im_emb, float* txt_emb, float* ctx_vec, float* beta, void* workspace,
+                                    size_t workspace_bytes, vag_stream_t stream) {
+    VAG_REQUIRE(w && im && ctx && im_emb && txt_emb && ctx_vec, "vag_vse_pool_fwd_f32: null pointer");
+    VAG_REQUIRE(B > 0 && T > 0, "vag_vse_pool_fwd_f32: bad shape");
+    VAG_REQUIRE(w->method == VAG_ATTN_DOT || (w->method == VAG_ATTN_MLP && w->mlp_w), "vag_vse_pool_fwd_f32: bad attention method");
+    const int I = w->I, C = w->C, S = w->S;
+    cudaStream_t st = (cudaStream_t)stream;
+    Arena ar(workspace, workspace_bytes);
+    float* pk = ar.take<float>((size_t)B * T * C);
+    float* iq = ar.take<float>((size_t)B * C);
+    if (ar.overflow) {
+        set_error("vag_vse_pool_fwd_f32: workspace %zu B too small", workspace_bytes);
+        return VAG_ERR_WORKSPACE;
+    }
+    const int act = w->activation ? VAG_LIN_TANH : 0;
+    VAG_TRY(linear_dispatch(im_emb, S, im, I, w->im_w, I, w->im_b, B, I, S, act, st));            // VSE_Imagine_Enc.py:123-127
+    VAG_TRY(vag_l2norm_rows_f32(im_emb, S, B, S, stream));                                        // :132
+    VAG_TRY(linear_dispatch(iq, C, im_emb, S, w->emb2ctx_w, S, nullptr, B, S, C, 0, st));         // :58
+    VAG_TRY(linear_dispatch(pk, C, ctx, C, w->ctx2ctx_w, C, nullptr, B * T, C, C, 0, st));        // :57
+    VAG_TRY(vag_attention_f32(ctx_vec, C, beta, iq, C, pk, ctx, w->mlp_w, mask, B, 1, T, C, w->method, stream));  // :135-137
+    VAG_TRY(linear_dispatch(txt_emb, S, ctx_vec, C, w->txt_w, C, w->txt_b, B, C, S, act, st));    // :138-140
+    VAG_TRY(vag_l2norm_rows_f32(txt_emb, S, B, S, stream));                                       // :145
+    return VAG_OK;
+}
+
+// ------------------------------------------------------------------ decoder
+extern "C" int vag_attn_keys_f32(const vag_decoder_weights* w, const float* ctx, int B, int T, float* keys, vag_stream_t stream) {
+    VAG_REQUIRE(w && ctx && keys && B > 0 && T > 0, "vag_attn_keys_f32: bad argument");
+    return linear_dispatch(keys, w->C, ctx, w->C, w->attn_e_w, w->C, nullptr, B * T, w->C, w->C, 0, (cudaStream_t)stream);
+}
+
+extern "C" int vag_decoder_init_f32(const vag_decoder_weights* w, const float* ctx_vec, const float* ctx, const float* mask,
+                                    float split, int B, int T, float* h0, void* workspace, size_t workspace_bytes,
+                                    vag_stream_t stream) {
+    VAG_REQUIRE(w && ctx && mask && h0 && B > 0 && T > 0, "vag_decoder_init_f32: bad argument");
+    VAG_REQUIRE(w->ini_w && w->ini_b, "vag_decoder_init_f32: decoderini weights missing");
+    Arena ar(workspace, workspace_bytes);
+    float* z = ar.take<float>((size_t)B * w->C);
+    if (ar.overflow) {
+        set_error("vag_decoder_init_f32: workspace %zu B too small (need B*C floats)", workspace_bytes);
+        return VAG_ERR_WORKSPACE;
+    }
+    VAG_TRY(vag_init_mix_f32(z, ctx_vec, ctx, mask, split, B, T, w->C, stream));
+    return linear_dispatch(h0, w->H, z, w->C, w->ini_w, w->C, w->ini_b, B, w->C, w->H, VAG_LIN_TANH, (cudaStream_t)stream);
+}
+
+namespace vag {
+struct StepWs {
+    float *e, *gi, *gh, *h1, *q, *c, *x2, *t;
+};
+template <typename A>
+static void step_layout(A& a, int rows, int E, int H, int C, StepWs* ws) {
+    float* e = (float*)a.template take<float>((size_t)rows * E);
+    float* gi = (float*)a.template take<float>((size_t)rows * 3 * H);
+    float* gh = (float*)a.template take<float>((size_t)rows * 3 * H);
+    float* h1 = (float*)a.template take<float>((size_t)rows * H);
+    float* q = (float*)a.template take<float>((size_t)rows * C);
+    float* c = (float*)a.template take<float>((size_t)rows * C);
+    float* x2 = (float*)a.template take<float>((size_t)rows * H);
+    float* t = (float*)a.template take<float>((size_t)rows * E);
+    if (ws) { ws->e = e; ws->gi = gi; ws->gh = gh; ws->h1 = h1; ws->q = q; ws->c = c; ws->x2 = x2; ws->t = t; }
+}
+
+// One conditional-GRU step up to (and including) the vocabulary logits.  NMT_Decoder.py:109-143.
+static int decoder_step_core(const vag_decoder_weights* w, const StepWs& ws, const int64_t* tokens, const float* h_prev,
+                             const float* keys, const float* ctx, const float* mask, int rows, int rows_per_sent, int T,
+                             float* h_out, float* logits, float* alpha_out, cudaStream_t st) {
+    const int E = w->E, H = w->H, C = w->C;
+    const int64_t V = w->V;
+    vag_stream_t vs = (vag_stream_t)st;
+    VAG_TRY(vag_embed_rows_f32(ws.e, E, w->emb, E, tokens, rows, V, vs));                                              // :118
+    VAG_TRY(linear_dispatch(ws.gi, 3 * H, ws.e, E, w->gru1_w_ih, E, w->gru1_b_ih, rows, E, 3 * H, 0, st));              // :121
+    VAG_TRY(linear_dispatch(ws.gh, 3 * H, h_prev, H, w->gru1_w_hh, H, w->gru1_b_hh, rows, H, 3 * H, 0, st));
+    VAG_TRY(vag_gru_gates_f32(ws.h1, H, nullptr, 0, ws.gi, 3 * H, ws.gh, 3 * H, h_prev, H, rows, H, vs));
+    VAG_TRY(linear_dispatch(ws.q, C, ws.h1, H, w->attn_h_w, H, nullptr, rows, H, C, 0, st));                            // :47
+    VAG_TRY(vag_attention_f32(ws.c, C, alpha_out, ws.q, C, keys, ctx, w->attn_v, mask, rows, rows_per_sent, T, C,
+                              VAG_ATTN_MLP, vs));                                                                       // :124-126
+    VAG_TRY(linear_dispatch(ws.x2, H, ws.c, C, w->c2h_w, C, nullptr, rows, C, H, 0, st));                               // :127
+    VAG_TRY(linear_dispatch(ws.gi, 3 * H, ws.x2, H, w->gru2_w_ih, H, w->gru2_b_ih, rows, H, 3 * H, 0, st));             // :129
+    VAG_TRY(linear_dispatch(ws.gh, 3 * H, ws.h1, H, w->gru2_w_hh, H, w->gru2_b_hh, rows, H, 3 * H, 0, st));
+    VAG_TRY(vag_gru_gates_f32(h_out, H, nullptr, 0, ws.gi, 3 * H, ws.gh, 3 * H, ws.h1, H, rows, H, vs));
+    // t = tanh((W1 h2 + b1) + (W3 e + b3) + (W2 c + b2)), summed left to right like :137
+    VAG_TRY(linear_dispatch(ws.t, E, h_out, H, w->w1_w, H, w->w1_b, rows, H, E, 0, st));
+    VAG_TRY(linear_dispatch(ws.t, E, ws.e, E, w->w3_w, E, w->w3_b, rows, E, E, VAG_LIN_ACCUMULATE, st));
+    VAG_TRY(linear_dispatch(ws.t, E, ws.c, C, w->w2_w, C, w->w2_b, rows, C, E, VAG_LIN_ACCUMULATE | VAG_LIN_TANH, st));
+    if (logits) VAG_TRY(linear_dispatch(logits, V, ws.t, E, w->out_w, E, w->out_b, rows, E, (int)V, 0, st));            // :143
+    return VAG_OK;
+}
+}  // namespace vag
+
+extern "C" size_t vag_decoder_step_workspace_bytes(int rows, int E, int H, int C, int64_t V) {
+    SizerAdapter s;
+    step_layout(s, rows, E, H, C, nullptr);
+    (void)V;
+    return s.s.total();
+}
+
+extern "C" int vag_decoder_step_f32(const vag_decoder_weights* w, const int64_t* tokens, const float* h_prev, const float* keys,
+                                    const float* ctx, const float* mask, int rows, int rows_per_sent, int T, float* h_out,
+                                    float* logits_or_logp, int want_logp, float* alpha_out, void* workspace,
+                                    size_t workspace_bytes, vag_stream_t stream) {
+    VAG_REQUIRE(w && tokens && h_prev && keys && ctx && h_out && logits_or_logp, "vag_decoder_step_f32: null pointer");
+    VAG_REQUIRE(rows > 0 && rows_per_sent > 0 && rows % rows_per_sent == 0 && T > 0, "vag_decoder_step_f32: bad shape");
+    VAG_REQUIRE(h_out != h_prev, "vag_decoder_step_f32: h_out must not alias h_prev");
+    ArenaAdapter ar(workspace, workspace_bytes);
+    StepWs ws;
+    step_layout(ar, rows, w->E, w->H, w->C, &ws);
+    if (ar.a.overflow) {
+        set_error("vag_decoder_step_f32: workspace %zu B too small", workspace_bytes);
+        return VAG_ERR_WORKSPACE;
+    }
+    VAG_TRY(decoder_step_core(w, ws, tokens, h_prev, keys, ctx, mask, rows, rows_per_sent, T, h_out, logits_or_logp, alpha_out,
+                              (cudaStream_t)stream));
+    if (want_logp) VAG_TRY(vag_log_softmax_f32(logits_or_logp, logits_or_logp, rows, (int)w->V, stream));
+    return VAG_OK;
+}
+
+// ------------------------------------------------------------------ beam search
+namespace vag {
+struct BeamWs {
+    StepWs step;
+    float *logits, *lse, *h_a, *h_b, *nll;
+    int64_t *tok_hist, *sos;
+    int32_t* par_hist;
+    int* flags;  // [0] done, [1] steps_run, [2..2+L) per-step EOS counters
+};
+template <typename A>
+static void beam_layout(A& a, int B, int K, int L, int E, int H, int C, int64_t V, BeamWs* ws) {
+    const int N = B * K;
+    StepWs sw;
+    step_layout(a, N, E, H, C, &sw);
+    float* logits = (float*)a.template take<float>((size_t)N * V);
+    float* lse = (float*)a.template take<float>((size_t)N);
+    float* h_a = (float*)a.template take<float>((size_t)N * H);
+    float* h_b = (float*)a.template take<float>((size_t)N * H);
+    float* nll = (float*)a.template take<float>((size_t)N);
+    int64_t* tok_hist = (int64_t*)a.template take<int64_t>((size_t)L * N);
+    int64_t* sos = (int64_t*)a.template take<int64_t>((size_t)B);
+    int32_t* par_hist = (int32_t*)a.template take<int32_t>((size_t)L * N);
+    int* flags = (int*)a.template take<int>((size_t)L + 2);
+    if (ws) {
+        ws->step = sw; ws->logits = logits; ws->lse = lse; ws->h_a = h_a; ws->h_b = h_b; ws->nll = nll;
+        ws->tok_hist = tok_hist; ws->sos = sos; ws->par_hist = par_hist; ws->flags = flags;
+    }
+}
+}  // namespace vag
+
+extern "C" size_t vag_beam_decode_workspace_bytes(int B, int K, int T, int L, int E, int H, int C, int64_t V) {
+    SizerAdapter s;
+    beam_layout(s, B, K, L, E, H, C, V, nullptr);
+    (void)T;
+    return s.s.total();
+}
+
+extern "C" int vag_beam_decode_f32(const vag_decoder_weights* w, const float* h0, const float* keys, const float* ctx,
+                                   const float* mask, int B, int K, int T, int L, int avoid_double, int64_t* hyp_out,
+                                   int32_t* hyp_len, int64_t* beam_out, float* nll_out, int32_t* steps_out, void* workspace,
+                                   size_t workspace_bytes, vag_stream_t stream) {
+    VAG_REQUIRE(w && h0 && keys && ctx && mask && hyp_out && hyp_len, "vag_beam_decode_f32: null pointer");
+    VAG_REQUIRE(B > 0 && K > 1 && T > 0 && L > 0, "vag_beam_decode_f32: bad shape B=%d K=%d T=%d L=%d", B, K, T, L);
+    VAG_REQUIRE(K <= w->V, "vag_beam_decode_f32: beam larger than the vocabulary");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int E = w->E, H = w->H, C = w->C;
+    const int64_t V = w->V;
+    const int N = B * K;
+    ArenaAdapter ar(workspace, workspace_bytes);
+    BeamWs ws;
+    beam_layout(ar, B, K, L, E, H, C, V, &ws);
+    if (ar.a.overflow) {
+        set_error("vag_beam_decode_f32: workspace %zu B too small", workspace_bytes);
+        return VAG_ERR_WORKSPACE;
+    }
+    int* done = ws.flags;
+    int* steps_run = ws.flags + 1;
+    int* fin = ws.flags + 2;
+    VAG_CUDA(cudaMemsetAsync(ws.flags, 0, sizeof(int) * (size_t)(L + 2), st));
+    fill_i64_kernel<<<ceil_div(B, 256), 256, 0, st>>>(ws.sos, 2 /*SOS*/, B);
+    VAG_LAUNCH_CHECK();
+    for (int di = 0; di < L; ++di) {
+        const int rows = di == 0 ? B : N;
+        const int rps = di == 0 ? 1 : K;
+        const int64_t* tokens = di == 0 ? ws.sos : ws.tok_hist + (size_t)(di - 1) * N;
+        const float* h_prev = di == 0 ? h0 : ws.h_a;
+        VAG_TRY(decoder_step_core(w, ws.step, tokens, h_prev, keys, ctx, mask, rows, rps, T, ws.h_b, ws.logits, nullptr, st));
+        VAG_TRY(row_lse(ws.lse, ws.logits, V, rows, V, st));
+        VAG_TRY(beam_select(ws.logits, V, ws.lse, di == 0 ? nullptr : tokens, ws.nll, ws.tok_hist + (size_t)di * N,
+                            ws.par_hist + (size_t)di * N, B, K, V, di, avoid_double, done, fin + di, st));
+        VAG_TRY(beam_advance(ws.h_a, ws.h_b, ws.par_hist + (size_t)di * N, B, K, rps, H, di, done, fin + di, steps_run, st));
+    }
+    VAG_TRY(beam_finalize(ws.tok_hist, ws.par_hist, ws.nll, steps_run, B, K, L, hyp_out, hyp_len, beam_out, st));
+    if (nll_out) VAG_CUDA(cudaMemcpyAsync(nll_out, ws.nll, sizeof(float) * (size_t)N, cudaMemcpyDeviceToDevice, st));
+    if (steps_out) VAG_CUDA(cudaMemcpyAsync(steps_out, steps_run, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    return VAG_OK;
+}
+
+extern "C" int vag_greedy_decode_f32(const vag_decoder_weights* w, const float* h0, const float* keys, const float* ctx,
+                                     const float* mask, int B, int T, int L, int64_t* tokens_out, void* workspace,
+                                     size_t workspace_bytes, vag_stream_t stream) {
+    VAG_REQUIRE(w && h0 && keys && ctx && mask && tokens_out, "vag_greedy_decode_f32: null pointer");
+    VAG_REQUIRE(B > 0 && T > 0 && L > 0, "vag_greedy_decode_f32: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    ArenaAdapter ar(workspace, workspace_bytes);
+    BeamWs ws;
+    beam_layout(ar, B, 1, L, w->E, w->H, w->C, w->V, &ws);
+    if (ar.a.overflow) {
+        set_error("vag_greedy_decode_f32: workspace %zu B too small (use vag_beam_decode_workspace_bytes with K=1)", workspace_bytes);
+        return VAG_ERR_WORKSPACE;
+    }
+    fill_i64_kernel<<<ceil_div(B, 256), 256, 0, st>>>(ws.sos, 2, B);
+    VAG_LAUNCH_CHECK();
+    VAG_CUDA(cudaMemcpyAsync(ws.h_a, h0, sizeof(float) * (size_t)B * w->H, cudaMemcpyDeviceToDevice, st));
+    float* h_cur = ws.h_a;
+    float* h_nxt = ws.h_b;
+    for (int di = 0; di < L; ++di) {
+        VAG_TRY(decoder_step_core(w, ws.step, ws.sos, h_cur, keys, ctx, mask, B, 1, T, h_nxt, ws.logits, nullptr, st));
+        VAG_TRY(row_argmax(ws.logits, w->V, B, w->V, tokens_out + di, L, ws.sos, st));
+        std::swap(h_cur, h_nxt);
+    }
+    return VAG_OK;
+}

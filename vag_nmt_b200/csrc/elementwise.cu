@@ -1,0 +1,258 @@
+// Bandwidth-bound fused element-wise / row-wise kernels: GRU gates, decoder-init mix, l2norm,
+// log-softmax, NLL rows.  All FP32, vectorised where the strides allow it.
+#include "common.cuh"
+#include <math.h>
+
+namespace vag {
+
+// ---------------------------------------------------------------- GRU gates
+// One thread per (row, 4 hidden units).  Reads gi/gh (3 gates each) + h_prev, writes h' (twice at most).
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+gru_gates_kernel(float* h_out, int64_t ld_ho, float* h_out2, int64_t ld_ho2,
+                 const float* __restrict__ gi, int64_t ld_gi, const float* __restrict__ gh, int64_t ld_gh,
+                 const float* h_prev /* may alias h_out */, int64_t ld_hp, int rows, int H) {
+    constexpr int W = VEC ? 4 : 1;
+    const int per_row = H / W;
+    const int64_t total = (int64_t)rows * per_row;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int row = (int)(idx / per_row);
+        const int j = (int)(idx % per_row) * W;
+        const float* gir = gi + (int64_t)row * ld_gi;
+        const float* ghr = gh + (int64_t)row * ld_gh;
+        float ir[W], iz[W], in_[W], hr[W], hz[W], hn[W], hp[W], out[W];
+        if (VEC) {
+            *reinterpret_cast<float4*>(ir) = *reinterpret_cast<const float4*>(gir + j);
+            *reinterpret_cast<float4*>(iz) = *reinterpret_cast<const float4*>(gir + H + j);
+            *reinterpret_cast<float4*>(in_) = *reinterpret_cast<const float4*>(gir + 2 * H + j);
+            *reinterpret_cast<float4*>(hr) = *reinterpret_cast<const float4*>(ghr + j);
+            *reinterpret_cast<float4*>(hz) = *reinterpret_cast<const float4*>(ghr + H + j);
+            *reinterpret_cast<float4*>(hn) = *reinterpret_cast<const float4*>(ghr + 2 * H + j);
+            *reinterpret_cast<float4*>(hp) = *reinterpret_cast<const float4*>(h_prev + (int64_t)row * ld_hp + j);
+        } else {
+            ir[0] = gir[j]; iz[0] = gir[H + j]; in_[0] = gir[2 * H + j];
+            hr[0] = ghr[j]; hz[0] = ghr[H + j]; hn[0] = ghr[2 * H + j];
+            hp[0] = h_prev[(int64_t)row * ld_hp + j];
+        }
+#pragma unroll
+        for (int u = 0; u < W; ++u) {
+            const float r = sigmoidf_precise(ir[u] + hr[u]);
+            const float z = sigmoidf_precise(iz[u] + hz[u]);
+            const float n = tanhf(in_[u] + r * hn[u]);
+            out[u] = (1.0f - z) * n + z * hp[u];
+        }
+        if (VEC) {
+            *reinterpret_cast<float4*>(h_out + (int64_t)row * ld_ho + j) = *reinterpret_cast<float4*>(out);
+            if (h_out2) *reinterpret_cast<float4*>(h_out2 + (int64_t)row * ld_ho2 + j) = *reinterpret_cast<float4*>(out);
+        } else {
+            h_out[(int64_t)row * ld_ho + j] = out[0];
+            if (h_out2) h_out2[(int64_t)row * ld_ho2 + j] = out[0];
+        }
+    }
+}
+
+// ---------------------------------------------------------------- decoder-init mix
+// z[b,c] = split*ctx_vec[b,c] + (1-split) * (Σ_t ctx[b,t,c]) / (Σ_t mask[b,t])
+__global__ void init_mix_kernel(float* __restrict__ z, const float* __restrict__ ctx_vec, const float* __restrict__ ctx,
+                                const float* __restrict__ mask, float split, int B, int T, int C) {
+    const int b = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float msum = 0.f;
+    for (int t = 0; t < T; ++t) msum += mask[(int64_t)b * T + t];
+    float s = 0.f;
+    for (int t = 0; t < T; ++t) s += ctx[((int64_t)b * T + t) * C + c];
+    const float mean = s / msum;
+    z[(int64_t)b * C + c] = ctx_vec ? split * ctx_vec[(int64_t)b * C + c] + (1.0f - split) * mean : mean;
+}
+
+// ---------------------------------------------------------------- l2norm rows (one warp per row)
+__global__ void l2norm_rows_kernel(float* __restrict__ x, int64_t ldx, int rows, int dim) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float* p = x + (int64_t)row * ldx;
+    float ss = 0.f;
+    for (int c = lane; c < dim; c += 32) ss = fmaf(p[c], p[c], ss);
+    ss = warp_sum(ss);
+    const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+    for (int c = lane; c < dim; c += 32) p[c] = p[c] / nrm;
+}
+
+// ---------------------------------------------------------------- row log-sum-exp helpers
+struct MaxSum {
+    float m, s;
+};
+__device__ __forceinline__ MaxSum ms_combine(MaxSum a, MaxSum b) {
+    MaxSum r;
+    r.m = fmaxf(a.m, b.m);
+    if (r.m == -INFINITY) { r.s = 0.f; return r; }
+    r.s = a.s * expf(a.m - r.m) + b.s * expf(b.m - r.m);
+    return r;
+}
+
+// Block-wide (max, Σexp(x-max)) of one row; two passes over the row (max first, then the sum) so that the
+// result follows log_softmax's own arithmetic: lse = max + log Σ exp(x - max).
+__device__ float block_row_lse(const float* __restrict__ row, int64_t V, float* red /* >= 33 floats */) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+    float m = -INFINITY;
+    for (int64_t i = tid; i < V; i += blockDim.x) m = fmaxf(m, row[i]);
+    m = warp_max(m);
+    if (lane == 0) red[wid] = m;
+    __syncthreads();
+    if (wid == 0) {
+        float v = lane < nw ? red[lane] : -INFINITY;
+        v = warp_max(v);
+        if (lane == 0) red[32] = v;
+    }
+    __syncthreads();
+    m = red[32];
+    __syncthreads();
+    float s = 0.f;
+    for (int64_t i = tid; i < V; i += blockDim.x) s += expf(row[i] - m);
+    s = warp_sum(s);
+    if (lane == 0) red[wid] = s;
+    __syncthreads();
+    if (wid == 0) {
+        float v = lane < nw ? red[lane] : 0.f;
+        v = warp_sum(v);
+        if (lane == 0) red[32] = v;
+    }
+    __syncthreads();
+    s = red[32];
+    __syncthreads();
+    return m + logf(s);
+}
+
+__global__ void __launch_bounds__(256) log_softmax_kernel(float* __restrict__ logp, const float* __restrict__ logits, int64_t V) {
+    __shared__ float red[33];
+    const float* src = logits + (int64_t)blockIdx.x * V;
+    float* dst = logp + (int64_t)blockIdx.x * V;
+    const float lse = block_row_lse(src, V, red);
+    for (int64_t i = threadIdx.x; i < V; i += blockDim.x) dst[i] = src[i] - lse;
+}
+
+__global__ void __launch_bounds__(256) row_lse_kernel(float* __restrict__ lse_out, const float* __restrict__ logits, int64_t ld, int64_t V) {
+    __shared__ float red[33];
+    const float lse = block_row_lse(logits + (int64_t)blockIdx.x * ld, V, red);
+    if (threadIdx.x == 0) lse_out[blockIdx.x] = lse;
+}
+
+__global__ void __launch_bounds__(256)
+nll_rows_kernel(const float* __restrict__ logits, int64_t ld, const int64_t* __restrict__ tgt, const float* __restrict__ weight,
+                int64_t V, float* __restrict__ loss_rows, float* __restrict__ lse_out) {
+    __shared__ float red[33];
+    const int r = blockIdx.x;
+    const float* row = logits + (int64_t)r * ld;
+    const float lse = block_row_lse(row, V, red);
+    if (threadIdx.x == 0) {
+        int64_t t = tgt[r];
+        if (t < 0 || t >= V) t = 0;
+        const float wgt = weight ? weight[t] : 1.0f;
+        loss_rows[r] += -(row[t] - lse) * wgt;
+        if (lse_out) lse_out[r] = lse;
+    }
+}
+
+// out = {loss, loss_mt, loss_vse};  one block, deterministic order
+__global__ void __launch_bounds__(256)
+translation_loss_kernel(const float* __restrict__ loss_rows, const int64_t* __restrict__ tgt, int B, int Tt,
+                        const float* __restrict__ loss_vse, float loss_w, float* __restrict__ out) {
+    __shared__ float red[8];
+    float a = 0.f;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        float cnt = 0.f;
+        for (int t = 0; t < Tt; ++t) cnt += (tgt[(int64_t)b * Tt + t] != 0) ? 1.f : 0.f;
+        a += loss_rows[b] / cnt;
+    }
+    a = warp_sum(a);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+        const float mt = t / (float)B;
+        const float vse = loss_vse ? loss_vse[0] : 0.f;
+        out[0] = loss_vse ? loss_w * mt + (1.0f - loss_w) * vse : mt;
+        out[1] = mt;
+        out[2] = vse;
+    }
+}
+
+int row_lse(float* lse_out, const float* logits, int64_t ld, int rows, int64_t V, cudaStream_t st) {
+    if (rows == 0) return VAG_OK;
+    row_lse_kernel<<<rows, 256, 0, st>>>(lse_out, logits, ld, V);
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
+}  // namespace vag
+
+using namespace vag;
+
+extern "C" int vag_gru_gates_f32(float* h_out, int64_t ld_ho, float* h_out2, int64_t ld_ho2, const float* gi, int64_t ld_gi,
+                                 const float* gh, int64_t ld_gh, const float* h_prev, int64_t ld_hp, int rows, int H,
+                                 vag_stream_t stream) {
+    VAG_REQUIRE(h_out && gi && gh && h_prev, "vag_gru_gates_f32: null pointer");
+    VAG_REQUIRE(rows >= 0 && H > 0, "vag_gru_gates_f32: bad shape rows=%d H=%d", rows, H);
+    if (rows == 0) return VAG_OK;
+    auto al = [](const void* p) { return ((uintptr_t)p % 16) == 0; };
+    const bool vec = (H % 4 == 0) && (ld_ho % 4 == 0) && (ld_gi % 4 == 0) && (ld_gh % 4 == 0) && (ld_hp % 4 == 0) &&
+                     (!h_out2 || ld_ho2 % 4 == 0) && al(h_out) && al(gi) && al(gh) && al(h_prev) && (!h_out2 || al(h_out2));
+    const int64_t total = (int64_t)rows * (vec ? H / 4 : H);
+    const int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)num_sms() * 16);
+    if (vec)
+        gru_gates_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(h_out, ld_ho, h_out2, ld_ho2, gi, ld_gi, gh, ld_gh, h_prev, ld_hp, rows, H);
+    else
+        gru_gates_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(h_out, ld_ho, h_out2, ld_ho2, gi, ld_gi, gh, ld_gh, h_prev, ld_hp, rows, H);
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
+extern "C" int vag_init_mix_f32(float* z, const float* ctx_vec, const float* ctx, const float* mask, float split, int B,
+                                int T, int C, vag_stream_t stream) {
+    VAG_REQUIRE(z && ctx && mask, "vag_init_mix_f32: null pointer");
+    VAG_REQUIRE(B > 0 && T > 0 && C > 0, "vag_init_mix_f32: bad shape");
+    dim3 grid(ceil_div(C, 128), B);
+    init_mix_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(z, ctx_vec, ctx, mask, split, B, T, C);
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
+extern "C" int vag_l2norm_rows_f32(float* x, int64_t ldx, int rows, int dim, vag_stream_t stream) {
+    VAG_REQUIRE(x, "vag_l2norm_rows_f32: null pointer");
+    VAG_REQUIRE(rows >= 0 && dim > 0, "vag_l2norm_rows_f32: bad shape");
+    if (rows == 0) return VAG_OK;
+    l2norm_rows_kernel<<<ceil_div(rows, 4), 128, 0, (cudaStream_t)stream>>>(x, ldx, rows, dim);
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
+extern "C" int vag_log_softmax_f32(float* logp, const float* logits, int rows, int V, vag_stream_t stream) {
+    VAG_REQUIRE(logp && logits, "vag_log_softmax_f32: null pointer");
+    VAG_REQUIRE(rows >= 0 && V > 0, "vag_log_softmax_f32: bad shape");
+    if (rows == 0) return VAG_OK;
+    log_softmax_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(logp, logits, V);
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
+extern "C" int vag_nll_rows_f32(const float* logits, int64_t ld, const int64_t* tgt, const float* weight, int rows,
+                                int64_t V, float* loss_rows, float* lse_out, vag_stream_t stream) {
+    VAG_REQUIRE(logits && tgt && loss_rows, "vag_nll_rows_f32: null pointer");
+    VAG_REQUIRE(rows >= 0 && V > 0 && ld >= V, "vag_nll_rows_f32: bad shape");
+    if (rows == 0) return VAG_OK;
+    nll_rows_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(logits, ld, tgt, weight, V, loss_rows, lse_out);
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
+extern "C" int vag_translation_loss_f32(const float* loss_rows, const int64_t* tgt, int B, int Tt, const float* loss_vse,
+                                        float loss_w, float* out, vag_stream_t stream) {
+    VAG_REQUIRE(loss_rows && tgt && out, "vag_translation_loss_f32: null pointer");
+    VAG_REQUIRE(B > 0 && Tt > 0, "vag_translation_loss_f32: bad shape");
+    translation_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(loss_rows, tgt, B, Tt, loss_vse, loss_w, out);
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}

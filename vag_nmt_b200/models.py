@@ -1,0 +1,260 @@
+"""Drop-in mirrors of the two model classes the reference's drivers instantiate.
+
+  NMT_AttentionImagine_Seq2Seq_Beam_V11   models/NMT_AttentionImagine_Seq2Seq_Beam_V11.py   (multimodal)
+  NMT_Seq2Seq_Beam_V2                     models/NMT_Seq2Seq_Beam_V2.py                     (text-only)
+
+Same constructors, methods, ``state_dict`` keys and return values.  The bodies enqueue
+sm_100a kernels through libvagnmt.so; the beam search runs entirely on the device (one C call for the L-step
+loop, no per-step host synchronisation) and never tiles the encoder context K times.
+"""
+from __future__ import annotations
+
+import random
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .layers import LIUMCVC_Encoder, NMT_Decoder, VSE_Imagine_Enc
+from .losses import ImageRetrievalRankingLoss, PairwiseRankingLoss
+
+SOS_token = 2
+EOS_token = 3
+UNK_token = 1
+
+
+def _nll_weight(criterion, device) -> Optional[torch.Tensor]:
+    """The caller passes nn.NLLLoss(weight=vocab_mask, reduce=False) (nmt_multimodal_beam_DE.py:286-291)."""
+    if criterion is None:
+        return None
+    if not isinstance(criterion, nn.NLLLoss):
+        raise TypeError("criterion_mt must be an nn.NLLLoss(weight=..., reduce=False) like the reference driver builds")
+    if getattr(criterion, "reduction", "none") != "none":
+        raise ValueError("criterion_mt must be built with reduce=False / reduction='none' (the model normalises per sentence)")
+    w = criterion.weight
+    return None if w is None else w.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+class _Seq2SeqBase(nn.Module):
+    """Pieces shared by the two models: encoder → h0 → decoder loop / beam search."""
+
+    def _reset_like_reference(self):
+        # V11:77-80 / V2:53-56: kaiming-normal on EVERY ≥2-D non-bias parameter (embeddings and GRU matrices too)
+        for name, param in self.named_parameters():
+            if param.requires_grad and 'bias' not in name and param.data.dim() > 1:
+                nn.init.kaiming_normal_(param.data)
+
+    # -- helpers ------------------------------------------------------------------------------------------
+    def _device(self) -> torch.device:
+        dev = self.decoderini.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("vag_nmt_b200 models run on a B200 only: call .cuda() first (there is no CPU path)")
+        return dev
+
+    def _encode(self, src_var, src_lengths):
+        return self.encoder.forward_sentence_major(src_var, src_lengths)
+
+    def _decode_tokens(self, w, h0, keys, ctx, mask, beam_size: int, tgt_l: int) -> List[List[int]]:
+        B = ctx.shape[0]
+        if beam_size == 1:
+            toks = ops.greedy_decode(w, h0, keys, ctx, mask, tgt_l).cpu().tolist()  # V11:207-226
+            out = []
+            for row in toks:
+                cut = []
+                for t in row:
+                    if t == EOS_token:
+                        break
+                    cut.append(t)
+                out.append(cut)
+            return out
+        hyp, hyp_len = ops.beam_decode(w, h0, keys, ctx, mask, beam_size, tgt_l)  # V11:229 → 233-337
+        hyp = hyp.cpu()
+        lens = hyp_len.cpu().tolist()
+        return [hyp[b, :lens[b]].tolist() for b in range(B)]
+
+    def decode_device(self, src_var, src_lengths, im_var=None, beam_size=12, max_length=80):
+        """Device-resident beam search: same work as ``beamsearch_decode`` but returns CUDA tensors
+        (hyp int64 [B, L], hyp_len int32 [B]) without the final device→host copy / list building."""
+        if isinstance(self, NMT_AttentionImagine_Seq2Seq_Beam_V11):
+            w, ctx, mask, keys, h0, _, _ = self._prepare(src_var, src_lengths, im_var)
+        else:
+            w, ctx, mask, keys, h0 = self._prepare(src_var, src_lengths)
+        if beam_size == 1:
+            return ops.greedy_decode(w, h0, keys, ctx, mask, max_length), None
+        return ops.beam_decode(w, h0, keys, ctx, mask, beam_size, max_length)
+
+    def _translation_loss_rows(self, w, h0, keys, ctx, mask, tgt, teacher_force_ratio, weight):
+        """The Tt-step loop of forward (V11:136-160): Σ_t NLL rows [B]."""
+        B, Tt = tgt.shape
+        dev = ctx.device
+        loss_rows = torch.zeros(B, dtype=torch.float32, device=dev)
+        inp = torch.full((B,), SOS_token, dtype=torch.int64, device=dev)
+        is_teacher = random.random() < teacher_force_ratio  # V11:136 (python RNG, once per batch)
+        h = h0
+        tgt_t = tgt.t().contiguous()  # [Tt, B] so that a step's targets are one contiguous row
+        for di in range(Tt):
+            logits, h, _ = ops.decoder_step(w, inp, h, keys, ctx, mask, 1, want_logp=False)
+            ops.nll_rows(logits, tgt_t[di], weight, loss_rows)
+            inp = tgt_t[di] if is_teacher else ops.row_argmax(logits)
+        return loss_rows
+
+
+class NMT_AttentionImagine_Seq2Seq_Beam_V11(_Seq2SeqBase):
+    def __init__(self, src_size, tgt_size, im_feats_size, src_embedding_size, tgt_embedding_size, hidden_size,
+                 shared_embedding_size, loss_w, beam_size=1, attn_model='dot', n_layers=1, dropout_ctx=0.0,
+                 dropout_emb=0.0, dropout_out=0.0, dropout_rnn_enc=0.0, dropout_rnn_dec=0.0, dropout_im_emb=0.0,
+                 dropout_txt_emb=0.0, activation_vse=True, tied_emb=False, init_split=0.5):
+        super().__init__()
+        self.src_size = src_size
+        self.tgt_size = tgt_size
+        self.im_feats_size = im_feats_size
+        self.src_embedding_size = src_embedding_size
+        self.tgt_embedding_size = tgt_embedding_size
+        self.hidden_size = hidden_size
+        self.n_layers = n_layers
+        self.shared_embedding_size = shared_embedding_size
+        self.beam_size = beam_size
+        self.loss_w = loss_w
+        self.tied_emb = tied_emb
+        self.dropout_im_emb = dropout_im_emb
+        self.dropout_txt_emb = dropout_txt_emb
+        self.activation_vse = activation_vse
+        self.attn_model = attn_model
+        self.init_split = init_split
+        self.encoder = LIUMCVC_Encoder(src_size, src_embedding_size, hidden_size, n_layers, dropout_rnn=dropout_rnn_enc,
+                                       dropout_ctx=dropout_ctx, dropout_emb=dropout_emb)
+        self.decoder = NMT_Decoder(tgt_size, tgt_embedding_size, hidden_size, 2 * hidden_size, n_layers,
+                                   dropout_rnn=dropout_rnn_dec, dropout_out=dropout_out, dropout_emb=0.0, tied_emb=tied_emb)
+        self.vse_imagine = VSE_Imagine_Enc(self.attn_model, self.im_feats_size, 2 * hidden_size, self.shared_embedding_size,
+                                           self.dropout_im_emb, self.dropout_txt_emb, self.activation_vse)
+        self.decoderini = nn.Linear(2 * hidden_size, hidden_size)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        self._reset_like_reference()
+
+    def _prepare(self, src_var, src_lengths, im_var, want_embeddings=False):
+        dev = self._device()
+        ctx, mask = self._encode(src_var, src_lengths)                                   # V11:111 / :193
+        im_emb, txt_emb, ctx_vec, _ = self.vse_imagine.pool_sentence_major(im_var.to(dev), ctx, mask)  # :114 / :196
+        w = ops.decoder_weights(self.decoder, self.decoderini)
+        h0 = ops.decoder_init(w, ctx_vec, ctx, mask, self.init_split)                    # :118 / :201
+        keys = ops.attn_keys(w, ctx)
+        return w, ctx, mask, keys, h0, im_emb, txt_emb
+
+    def forward(self, src_var, src_lengths, tgt_var, im_var, teacher_force_ratio=1.0, max_length=80, criterion_mt=None,
+                criterion_vse=None):
+        """→ (loss, loss_mt, loss_vse), V11:82-168."""
+        dev = self._device()
+        self.tgt_l = tgt_var.size()[1]
+        w, ctx, mask, keys, h0, im_emb, txt_emb = self._prepare(src_var, src_lengths, im_var)
+        loss_vse = None
+        if criterion_vse is not None:
+            loss_vse = criterion_vse(im_emb, txt_emb)                                    # VSE_Imagine_Enc.py:149-150
+        tgt = tgt_var.to(device=dev, dtype=torch.int64).contiguous()
+        weight = _nll_weight(criterion_mt, dev)
+        loss_rows = self._translation_loss_rows(w, h0, keys, ctx, mask, tgt, teacher_force_ratio, weight)
+        vse_dev = None
+        if loss_vse is not None:
+            vse_dev = loss_vse.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+        out = ops.translation_loss(loss_rows, tgt, vse_dev, self.loss_w if vse_dev is not None else 1.0)
+        if loss_vse is None:
+            # the reference mixes with the python int 0 (V11:91,166): loss = loss_w * loss_mt
+            return self.loss_w * out[1], out[1], 0
+        return out[0], out[1], out[2]
+
+    def beamsearch_decode(self, src_var, src_lengths, im_var, beam_size=1, max_length=80, tgt_var=None):
+        """→ list[B] of token-id lists (EOS excluded), V11:179-231."""
+        tgt_l = max_length if tgt_var is None else tgt_var.size()[1]
+        self.tgt_l = tgt_l
+        self.beam_size = beam_size
+        w, ctx, mask, keys, h0, _, _ = self._prepare(src_var, src_lengths, im_var)
+        self.final_sample = self._decode_tokens(w, h0, keys, ctx, mask, beam_size, tgt_l)
+        return self.final_sample
+
+    def embed_sent_im_eval(self, src_var, src_lengths, tgt_var, im_feats):
+        """→ (im_embedding, text_embedding), V11:341-368."""
+        self.tgt_l = tgt_var.size()[1]
+        return self._embed(src_var, src_lengths, im_feats)
+
+    def embed_sent_im_test(self, src_var, src_lengths, im_feats, max_length=80):
+        """→ (im_embedding, text_embedding), V11:370-397."""
+        self.tgt_l = max_length
+        return self._embed(src_var, src_lengths, im_feats)
+
+    def _embed(self, src_var, src_lengths, im_feats):
+        dev = self._device()
+        ctx, mask = self._encode(src_var, src_lengths)
+        im_emb, txt_emb, _, _ = self.vse_imagine.pool_sentence_major(im_feats.to(dev), ctx, mask)
+        return im_emb, txt_emb
+
+    def get_imagine_attention_eval(self, src_var, src_lengths, tgt_var, im_feats):
+        """→ attention weights [B, 1, T], V11:399-424."""
+        self.tgt_l = tgt_var.size()[1]
+        return self._imagine_attention(src_var, src_lengths, im_feats)
+
+    def get_imagine_attention_test(self, src_var, src_lengths, im_feats, max_length=80):
+        """→ attention weights [B, 1, T], V11:426-450."""
+        self.tgt_l = max_length
+        return self._imagine_attention(src_var, src_lengths, im_feats)
+
+    def _imagine_attention(self, src_var, src_lengths, im_feats):
+        dev = self._device()
+        ctx, mask = self._encode(src_var, src_lengths)
+        _, _, _, beta = self.vse_imagine.pool_sentence_major(im_feats.to(dev), ctx, mask, want_beta=True)
+        return beta.unsqueeze(1)
+
+
+class NMT_Seq2Seq_Beam_V2(_Seq2SeqBase):
+    def __init__(self, src_size, tgt_size, src_embedding_size, tgt_embedding_size, hidden_size, beam_size=1, n_layers=1,
+                 dropout_ctx=0.0, dropout_emb=0.0, dropout_out=0.0, dropout_rnn=0.0, tied_emb=False):
+        super().__init__()
+        self.src_size = src_size
+        self.tgt_size = tgt_size
+        self.src_embedding_size = src_embedding_size
+        self.tgt_embedding_size = tgt_embedding_size
+        self.hidden_size = hidden_size
+        self.n_layers = n_layers
+        self.beam_size = beam_size
+        self.tied_emb = tied_emb
+        self.encoder = LIUMCVC_Encoder(src_size, src_embedding_size, hidden_size, n_layers, dropout_rnn=dropout_rnn,
+                                       dropout_ctx=dropout_ctx, dropout_emb=dropout_emb)
+        self.decoder = NMT_Decoder(tgt_size, tgt_embedding_size, hidden_size, 2 * hidden_size, n_layers,
+                                   dropout_out=dropout_out, tied_emb=tied_emb)
+        self.decoderini = nn.Linear(2 * hidden_size, hidden_size)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        self._reset_like_reference()
+
+    def _prepare(self, src_var, src_lengths):
+        self._device()
+        ctx, mask = self._encode(src_var, src_lengths)
+        w = ops.decoder_weights(self.decoder, self.decoderini)
+        h0 = ops.decoder_init(w, None, ctx, mask, 0.0)                                   # V2:85,142
+        keys = ops.attn_keys(w, ctx)
+        return w, ctx, mask, keys, h0
+
+    def forward(self, src_var, src_lengths, tgt_var, teacher_force_ratio=1.0, max_length=80, criterion=None):
+        """→ loss, models/NMT_Seq2Seq_Beam_V2.py:58-113."""
+        dev = self._device()
+        self.tgt_l = tgt_var.size()[1]
+        w, ctx, mask, keys, h0 = self._prepare(src_var, src_lengths)
+        tgt = tgt_var.to(device=dev, dtype=torch.int64).contiguous()
+        weight = _nll_weight(criterion, dev)
+        loss_rows = self._translation_loss_rows(w, h0, keys, ctx, mask, tgt, teacher_force_ratio, weight)
+        return ops.translation_loss(loss_rows, tgt, None, 1.0)[1]
+
+    def beamsearch_decode(self, src_var, src_lengths, beam_size=1, max_length=80, tgt_var=None):
+        """→ list[B] of token-id lists, models/NMT_Seq2Seq_Beam_V2.py:124-171."""
+        tgt_l = max_length if tgt_var is None else tgt_var.size()[1]
+        self.tgt_l = tgt_l
+        self.beam_size = beam_size
+        w, ctx, mask, keys, h0 = self._prepare(src_var, src_lengths)
+        self.final_sample = self._decode_tokens(w, h0, keys, ctx, mask, beam_size, tgt_l)
+        return self.final_sample
+
+
+__all__ = ["NMT_AttentionImagine_Seq2Seq_Beam_V11", "NMT_Seq2Seq_Beam_V2", "PairwiseRankingLoss",
+           "ImageRetrievalRankingLoss", "SOS_token", "EOS_token", "UNK_token"]
