@@ -231,7 +231,9 @@ def main():
         cfg = dict(synthetic.TINY, attn_model=attn)
         print(f"tiny config ({attn})")
         mm, tm = build_models(ref, cfg, seed=11, mirror=(attn == "dot"))
-        batch = synthetic.make_batch(5, cfg["src_size"], cfg["tgt_size"], cfg["im_feats_size"], seed=3, max_len=9, min_len=2)
+        batch = synthetic.make_batch(6, cfg["src_size"], cfg["tgt_size"], cfg["im_feats_size"], seed=3, max_len=9, min_len=2,
+                                     mean=5.0, std=2.5, common_tgt_len=False)
+        assert len(set(batch.src_lengths)) > 2 and (batch.tgt == 0).any()   # ragged source AND padded targets
         fix = dict(cfg=cfg, seed=11, batch=dict(src=batch.src, src_lengths=batch.src_lengths, tgt=batch.tgt, im=batch.im),
                    params_mm={k: v.clone() for k, v in mm.state_dict().items()},
                    params_tm={k: v.clone() for k, v in tm.state_dict().items()}, beams=[1, 3, 4], max_length=12)
@@ -245,6 +247,8 @@ def main():
         fix["ref_fp32"], fix["ref_fp64"] = r32, r64
         torch.save(fix, GOLD / f"tiny_{attn}.pt")
 
+    if "--only-tiny" in sys.argv:
+        return
     # ---------------- full EN→DE shapes, B = 32: weights by seed, outputs (small) stored
     cfg = dict(synthetic.DE)
     print("full EN→DE config, B=32")

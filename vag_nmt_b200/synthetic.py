@@ -50,17 +50,18 @@ def _sentences(lengths: torch.Tensor, vocab: int, gen: torch.Generator, width: O
 
 
 def make_batch(batch_size: int, src_vocab: int, tgt_vocab: Optional[int] = None, im_size: Optional[int] = None,
-               seed: int = 7, common_tgt_len: bool = True, max_len: int = 40, min_len: int = 4) -> Batch:
+               seed: int = 7, common_tgt_len: bool = True, max_len: int = 40, min_len: int = 4, mean: float = 14.0,
+               std: float = 4.5) -> Batch:
     """One batch the way the reference's generators hand it to the model."""
     gen = torch.Generator().manual_seed(seed)
-    ls = draw_lengths(batch_size, gen, lo=min_len, hi=max_len)
+    ls = draw_lengths(batch_size, gen, lo=min_len, hi=max_len, mean=mean, std=std)
     src = _sentences(ls, src_vocab, gen)
     tgt = None
     if tgt_vocab is not None:
         if common_tgt_len:  # BucketBatchSampler: one target length per train batch (samplers/bucket.py:10-103)
-            lt = draw_lengths(1, gen, lo=min_len, hi=max_len).expand(batch_size).contiguous()
+            lt = draw_lengths(1, gen, lo=min_len, hi=max_len, mean=mean, std=std).expand(batch_size).contiguous()
         else:
-            lt = draw_lengths(batch_size, gen, lo=min_len, hi=max_len)
+            lt = draw_lengths(batch_size, gen, lo=min_len, hi=max_len, mean=mean, std=std)
         tgt = _sentences(lt, tgt_vocab, gen)
     im = torch.rand(batch_size, im_size, generator=gen) if im_size is not None else None
     order = torch.argsort(ls, descending=True, stable=True)
@@ -73,10 +74,10 @@ def make_batch(batch_size: int, src_vocab: int, tgt_vocab: Optional[int] = None,
 
 
 def make_corpus(n_sent: int, src_vocab: int, im_size: Optional[int], seed: int = 7, max_len: int = 40,
-                min_len: int = 4):
+                min_len: int = 4, mean: float = 14.0, std: float = 4.5):
     """An unsorted test-set-shaped corpus: list of token lists + image matrix."""
     gen = torch.Generator().manual_seed(seed)
-    ls = draw_lengths(n_sent, gen, lo=min_len, hi=max_len)
+    ls = draw_lengths(n_sent, gen, lo=min_len, hi=max_len, mean=mean, std=std)
     toks = _sentences(ls, src_vocab, gen)
     sents = [toks[i, :int(ls[i])].tolist() for i in range(n_sent)]
     im = torch.rand(n_sent, im_size, generator=gen) if im_size is not None else None
