@@ -52,13 +52,23 @@ long long vag_launch_count(void);
 enum {
     VAG_LIN_TANH = 1,       /* y = tanh(...) */
     VAG_LIN_ACCUMULATE = 2, /* add the previous content of y before the activation */
-    VAG_LIN_FORCE_SIMT = 4, /* never take the tensor-core path (used by parity tests) */
-    VAG_LIN_FORCE_TC = 8    /* fail with VAG_ERR_UNSUPPORTED instead of falling to SIMT FP32 */
+    VAG_LIN_FORCE_SIMT = 4, /* (internal) never take the tensor-core path */
+    VAG_LIN_FORCE_TC = 8    /* (internal) fail with VAG_ERR_UNSUPPORTED instead of falling to SIMT FP32 */
 };
 /* x [rows, in_dim] (ld ldx), w [out_dim, in_dim] (ld ldw), bias [out_dim] or NULL,
- * y [rows, out_dim] (ld ldy). */
+ * y [rows, out_dim] (ld ldy).  Any shape / alignment; FP32 FFMA kernel. */
 int vag_linear_f32(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw,
                    const float* bias, int rows, int in_dim, int out_dim, int flags, vag_stream_t stream);
+
+/* The same contraction on the 5th-generation tensor cores (tcgen05.mma kind::tf32, TMEM accumulators, TMA-fed):
+ * every operand is split into hi = rn_tf32(v) and lo = v - hi and hi·hi + hi·lo + lo·hi is accumulated in FP32
+ * (3xTF32), which keeps FP32-level accuracy so that decoded tokens stay exact.  Needs rows >= 64, out_dim >= 64,
+ * in_dim >= 32 and a multiple of 4, 16-byte aligned x / w (else VAG_ERR_UNSUPPORTED).  The composites below take
+ * this path automatically for eligible shapes; VAG_GEMM=simt in the environment forces the FFMA kernel. */
+size_t vag_linear_tc_workspace_bytes(int rows, int in_dim, int out_dim);
+int vag_linear_tc_f32(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw,
+                      const float* bias, int rows, int in_dim, int out_dim, int flags, void* workspace,
+                      size_t workspace_bytes, vag_stream_t stream);
 
 /* out[r, :] = table[ids[r], :]   (nn.Embedding lookups: Encoder.py:50, NMT_Decoder.py:118) */
 int vag_embed_rows_f32(float* out, int64_t ldo, const float* table, int dim, const int64_t* ids, int rows,
@@ -186,8 +196,9 @@ typedef struct {
 
 /* Hoisted step-invariant half of the attention MLP: keys[b,t,:] = attn_e(ctx[b,t,:])
  * (the reference recomputes it on the K-times tiled context every step, NMT_Decoder.py:39-40,47). */
-int vag_attn_keys_f32(const vag_decoder_weights* w, const float* ctx, int B, int T, float* keys,
-                      vag_stream_t stream);
+size_t vag_attn_keys_workspace_bytes(int B, int T, int C);
+int vag_attn_keys_f32(const vag_decoder_weights* w, const float* ctx, int B, int T, float* keys, void* workspace,
+                      size_t workspace_bytes, vag_stream_t stream);
 
 /* h0 = tanh(decoderini(split·ctx_vec + (1-split)·mean_t ctx))  (V11:118,201; V2:85,142).
  * workspace: B·C floats. */

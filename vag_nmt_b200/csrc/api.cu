@@ -1,6 +1,7 @@
 // Library-level entry points: error string, ABI version, device probe, linear dispatch.
 #include "common.cuh"
 #include <string.h>
+#include <stdlib.h>
 #include <atomic>
 
 namespace vag {
@@ -31,21 +32,30 @@ int num_sms() {
 
 int linear_simt(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias,
                 int rows, int K, int N, int flags, cudaStream_t st);
-int linear_tc(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias,
-              int rows, int K, int N, int flags, cudaStream_t st, bool* taken);
+int linear_tc(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, int rows,
+              int K, int N, int flags, void* scratch, size_t scratch_bytes, cudaStream_t st);
+size_t linear_tc_scratch_bytes(int64_t rows, int64_t K, int64_t N);
+bool linear_tc_eligible(const float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, int rows, int K, int N);
 
+// VAG_GEMM=simt forces the FP32 FFMA path everywhere (A/B runs); default = tcgen05 3xTF32 where eligible.
+bool tc_enabled() {
+    const char* e = getenv("VAG_GEMM");
+    return !(e && strcmp(e, "simt") == 0);
+}
+
+size_t gemm_scratch_bytes(int64_t rows, int64_t K, int64_t N) { return linear_tc_scratch_bytes(rows, K, N); }
+
+// The one contraction entry point of the composites.  With a scratch region (for the hi/lo operand splits) and an
+// eligible shape the tcgen05 kernel runs; otherwise the SIMT FP32 kernel.
 int linear_dispatch(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias,
-                    int rows, int K, int N, int flags, cudaStream_t st) {
+                    int rows, int K, int N, int flags, cudaStream_t st, void* scratch, size_t scratch_bytes) {
     if (rows == 0 || N == 0) return VAG_OK;
-    if (!(flags & VAG_LIN_FORCE_SIMT)) {
-        bool taken = false;
-        int s = linear_tc(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags, st, &taken);
-        if (s != VAG_OK) return s;
-        if (taken) return VAG_OK;
-        if (flags & VAG_LIN_FORCE_TC) {
-            set_error("vag_linear_f32: shape rows=%d K=%d N=%d not eligible for the tensor-core path", rows, K, N);
-            return VAG_ERR_UNSUPPORTED;
-        }
+    if (!(flags & VAG_LIN_FORCE_SIMT) && scratch && tc_enabled() && linear_tc_eligible(y, ldy, x, ldx, w, ldw, rows, K, N) &&
+        scratch_bytes >= linear_tc_scratch_bytes(rows, K, N))
+        return linear_tc(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags, scratch, scratch_bytes, st);
+    if (flags & VAG_LIN_FORCE_TC) {
+        set_error("linear: shape rows=%d K=%d N=%d (or its scratch) is not eligible for the tensor-core path", rows, K, N);
+        return VAG_ERR_UNSUPPORTED;
     }
     return linear_simt(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags, st);
 }
@@ -71,5 +81,23 @@ extern "C" int vag_linear_f32(float* y, int64_t ldy, const float* x, int64_t ldx
     VAG_REQUIRE(y && x && w, "vag_linear_f32: null pointer");
     VAG_REQUIRE(rows >= 0 && in_dim > 0 && out_dim > 0, "vag_linear_f32: bad shape rows=%d in=%d out=%d", rows, in_dim, out_dim);
     VAG_REQUIRE(ldx >= in_dim && ldw >= in_dim && ldy >= out_dim, "vag_linear_f32: leading dimension smaller than the row");
-    return linear_dispatch(y, ldy, x, ldx, w, ldw, bias, rows, in_dim, out_dim, flags, (cudaStream_t)stream);
+    return linear_dispatch(y, ldy, x, ldx, w, ldw, bias, rows, in_dim, out_dim, flags | VAG_LIN_FORCE_SIMT, (cudaStream_t)stream,
+                           nullptr, 0);
+}
+
+extern "C" size_t vag_linear_tc_workspace_bytes(int rows, int in_dim, int out_dim) {
+    return linear_tc_scratch_bytes(rows, in_dim, out_dim);
+}
+
+extern "C" int vag_linear_tc_f32(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw,
+                                 const float* bias, int rows, int in_dim, int out_dim, int flags, void* workspace,
+                                 size_t workspace_bytes, vag_stream_t stream) {
+    VAG_REQUIRE(y && x && w && workspace, "vag_linear_tc_f32: null pointer");
+    VAG_REQUIRE(rows > 0 && in_dim > 0 && out_dim > 0, "vag_linear_tc_f32: bad shape rows=%d in=%d out=%d", rows, in_dim, out_dim);
+    VAG_REQUIRE(ldx >= in_dim && ldw >= in_dim && ldy >= out_dim, "vag_linear_tc_f32: leading dimension smaller than the row");
+    if (!linear_tc_eligible(y, ldy, x, ldx, w, ldw, rows, in_dim, out_dim)) {
+        set_error("vag_linear_tc_f32: needs rows >= 64, out >= 64, in >= 32 and a multiple of 4, 16-byte aligned operands");
+        return VAG_ERR_UNSUPPORTED;
+    }
+    return linear_tc(y, ldy, x, ldx, w, ldw, bias, rows, in_dim, out_dim, flags, workspace, workspace_bytes, (cudaStream_t)stream);
 }

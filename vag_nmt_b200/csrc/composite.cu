@@ -8,7 +8,20 @@
 namespace vag {
 
 int linear_dispatch(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias,
-                    int rows, int K, int N, int flags, cudaStream_t st);
+                    int rows, int K, int N, int flags, cudaStream_t st, void* scratch, size_t scratch_bytes);
+size_t gemm_scratch_bytes(int64_t rows, int64_t K, int64_t N);
+
+// stream + scratch region (operand hi/lo splits of the tensor-core path) shared by all contractions of a composite
+struct Gemm {
+    cudaStream_t st;
+    void* scratch;
+    size_t bytes;
+    int operator()(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, int rows,
+                   int K, int N, int flags) const {
+        return linear_dispatch(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags, st, scratch, bytes);
+    }
+};
+static inline size_t max_sz(size_t a, size_t b) { return a > b ? a : b; }
 int row_lse(float* lse_out, const float* logits, int64_t ld, int rows, int64_t V, cudaStream_t st);
 int beam_select(const float* logits, int64_t ld, const float* lse, const int64_t* prev_tokens, float* nll,
                 int64_t* tokens_out, int32_t* parents_out, int B, int K, int64_t V, int step, int avoid_double,
@@ -43,6 +56,8 @@ __global__ void fill_i64_kernel(int64_t* p, int64_t v, int n) {
 
 struct EncoderWs {
     float *x, *gi[2], *gh[2], *h[2];
+    void* scratch;
+    size_t scratch_bytes;
 };
 template <typename A>
 static void encoder_layout(A& a, int B, int T, int E, int H, EncoderWs* ws) {
@@ -53,7 +68,12 @@ static void encoder_layout(A& a, int B, int T, int E, int H, EncoderWs* ws) {
     float* gh1 = (float*)a.template take<float>((size_t)B * 3 * H);
     float* h0 = (float*)a.template take<float>((size_t)B * H);
     float* h1 = (float*)a.template take<float>((size_t)B * H);
-    if (ws) { ws->x = x; ws->gi[0] = gi0; ws->gi[1] = gi1; ws->gh[0] = gh0; ws->gh[1] = gh1; ws->h[0] = h0; ws->h[1] = h1; }
+    const size_t sb = max_sz(gemm_scratch_bytes((int64_t)T * B, E, 3 * H), gemm_scratch_bytes(B, H, 3 * H));
+    void* sc = a.template take<char>(sb);
+    if (ws) {
+        ws->x = x; ws->gi[0] = gi0; ws->gi[1] = gi1; ws->gh[0] = gh0; ws->gh[1] = gh1; ws->h[0] = h0; ws->h[1] = h1;
+        ws->scratch = sc; ws->scratch_bytes = sb;
+    }
 }
 struct SizerAdapter {
     ArenaSizer s;
@@ -108,8 +128,9 @@ extern "C" int vag_encoder_fwd_f32(const vag_encoder_weights* w, const int64_t* 
         while (n < B && lengths_host[n] > t) ++n;
         n_act[t] = n;
     }
+    const Gemm gemm{st, ws.scratch, ws.scratch_bytes};
     for (int d = 0; d < 2; ++d) {
-        VAG_TRY(linear_dispatch(ws.gi[d], 3 * H, ws.x, E, w->w_ih[d], E, w->b_ih[d], T * B, E, 3 * H, 0, st));
+        VAG_TRY(gemm(ws.gi[d], 3 * H, ws.x, E, w->w_ih[d], E, w->b_ih[d], T * B, E, 3 * H, 0));
         VAG_CUDA(cudaMemsetAsync(ws.h[d], 0, (size_t)B * H * sizeof(float), st));
     }
     // the two directions are independent chains; interleave them so neighbouring launches can overlap their tails
@@ -118,7 +139,7 @@ extern "C" int vag_encoder_fwd_f32(const vag_encoder_weights* w, const int64_t* 
             const int t = d == 0 ? s : T - 1 - s;
             const int n = n_act[t];
             if (n == 0) continue;
-            VAG_TRY(linear_dispatch(ws.gh[d], 3 * H, ws.h[d], H, w->w_hh[d], H, w->b_hh[d], n, H, 3 * H, 0, st));
+            VAG_TRY(gemm(ws.gh[d], 3 * H, ws.h[d], H, w->w_hh[d], H, w->b_hh[d], n, H, 3 * H, 0));
             VAG_TRY(vag_gru_gates_f32(ws.h[d], H, ctx_out + (int64_t)t * 2 * H + d * H, (int64_t)T * 2 * H,
                                       ws.gi[d] + (int64_t)t * B * 3 * H, 3 * H, ws.gh[d], 3 * H, ws.h[d], H, n, H, stream));
         }
@@ -131,7 +152,8 @@ extern "C" size_t vag_vse_workspace_bytes(int B, int T, int I, int C, int S) {
     ArenaSizer s;
     s.take<float>((size_t)B * T * C);
     s.take<float>((size_t)B * C);
-    (void)I; (void)S;
+    s.take<char>(max_sz(max_sz(gemm_scratch_bytes(B, I, S), gemm_scratch_bytes(B, S, C)),
+                        max_sz(gemm_scratch_bytes((int64_t)B * T, C, C), gemm_scratch_bytes(B, C, S))));
     return s.total();
 }
 
@@ -146,25 +168,33 @@ extern "C" int vag_vse_pool_fwd_f32(const vag_vse_weights* w, const float* im, c
     Arena ar(workspace, workspace_bytes);
     float* pk = ar.take<float>((size_t)B * T * C);
     float* iq = ar.take<float>((size_t)B * C);
+    const size_t sb = max_sz(max_sz(gemm_scratch_bytes(B, I, S), gemm_scratch_bytes(B, S, C)),
+                             max_sz(gemm_scratch_bytes((int64_t)B * T, C, C), gemm_scratch_bytes(B, C, S)));
+    void* sc = ar.take<char>(sb);
     if (ar.overflow) {
         set_error("vag_vse_pool_fwd_f32: workspace %zu B too small", workspace_bytes);
         return VAG_ERR_WORKSPACE;
     }
+    const Gemm gemm{st, sc, sb};
     const int act = w->activation ? VAG_LIN_TANH : 0;
-    VAG_TRY(linear_dispatch(im_emb, S, im, I, w->im_w, I, w->im_b, B, I, S, act, st));            // VSE_Imagine_Enc.py:123-127
+    VAG_TRY(gemm(im_emb, S, im, I, w->im_w, I, w->im_b, B, I, S, act));            // VSE_Imagine_Enc.py:123-127
     VAG_TRY(vag_l2norm_rows_f32(im_emb, S, B, S, stream));                                        // :132
-    VAG_TRY(linear_dispatch(iq, C, im_emb, S, w->emb2ctx_w, S, nullptr, B, S, C, 0, st));         // :58
-    VAG_TRY(linear_dispatch(pk, C, ctx, C, w->ctx2ctx_w, C, nullptr, B * T, C, C, 0, st));        // :57
+    VAG_TRY(gemm(iq, C, im_emb, S, w->emb2ctx_w, S, nullptr, B, S, C, 0));         // :58
+    VAG_TRY(gemm(pk, C, ctx, C, w->ctx2ctx_w, C, nullptr, B * T, C, C, 0));        // :57
     VAG_TRY(vag_attention_f32(ctx_vec, C, beta, iq, C, pk, ctx, w->mlp_w, mask, B, 1, T, C, w->method, stream));  // :135-137
-    VAG_TRY(linear_dispatch(txt_emb, S, ctx_vec, C, w->txt_w, C, w->txt_b, B, C, S, act, st));    // :138-140
+    VAG_TRY(gemm(txt_emb, S, ctx_vec, C, w->txt_w, C, w->txt_b, B, C, S, act));    // :138-140
     VAG_TRY(vag_l2norm_rows_f32(txt_emb, S, B, S, stream));                                       // :145
     return VAG_OK;
 }
 
 // ------------------------------------------------------------------ decoder
-extern "C" int vag_attn_keys_f32(const vag_decoder_weights* w, const float* ctx, int B, int T, float* keys, vag_stream_t stream) {
+extern "C" size_t vag_attn_keys_workspace_bytes(int B, int T, int C) { return gemm_scratch_bytes((int64_t)B * T, C, C) + 256; }
+
+extern "C" int vag_attn_keys_f32(const vag_decoder_weights* w, const float* ctx, int B, int T, float* keys, void* workspace,
+                                 size_t workspace_bytes, vag_stream_t stream) {
     VAG_REQUIRE(w && ctx && keys && B > 0 && T > 0, "vag_attn_keys_f32: bad argument");
-    return linear_dispatch(keys, w->C, ctx, w->C, w->attn_e_w, w->C, nullptr, B * T, w->C, w->C, 0, (cudaStream_t)stream);
+    return linear_dispatch(keys, w->C, ctx, w->C, w->attn_e_w, w->C, nullptr, B * T, w->C, w->C, 0, (cudaStream_t)stream,
+                           workspace, workspace_bytes);
 }
 
 extern "C" int vag_decoder_init_f32(const vag_decoder_weights* w, const float* ctx_vec, const float* ctx, const float* mask,
@@ -179,15 +209,31 @@ extern "C" int vag_decoder_init_f32(const vag_decoder_weights* w, const float* c
         return VAG_ERR_WORKSPACE;
     }
     VAG_TRY(vag_init_mix_f32(z, ctx_vec, ctx, mask, split, B, T, w->C, stream));
-    return linear_dispatch(h0, w->H, z, w->C, w->ini_w, w->C, w->ini_b, B, w->C, w->H, VAG_LIN_TANH, (cudaStream_t)stream);
+    const size_t sb = gemm_scratch_bytes(B, w->C, w->H);
+    void* sc = ar.take<char>(sb);   // optional: without it the FP32 FFMA kernel runs
+    return linear_dispatch(h0, w->H, z, w->C, w->ini_w, w->C, w->ini_b, B, w->C, w->H, VAG_LIN_TANH, (cudaStream_t)stream,
+                           ar.overflow ? nullptr : sc, ar.overflow ? 0 : sb);
 }
 
 namespace vag {
 struct StepWs {
     float *e, *gi, *gh, *h1, *q, *c, *x2, *t;
+    void* scratch;
+    size_t scratch_bytes;
 };
+static size_t step_scratch_bytes(int rows, int E, int H, int C, int64_t V) {
+    size_t m = gemm_scratch_bytes(rows, E, 3 * H);
+    m = max_sz(m, gemm_scratch_bytes(rows, H, 3 * H));
+    m = max_sz(m, gemm_scratch_bytes(rows, H, C));
+    m = max_sz(m, gemm_scratch_bytes(rows, C, H));
+    m = max_sz(m, gemm_scratch_bytes(rows, H, E));
+    m = max_sz(m, gemm_scratch_bytes(rows, E, E));
+    m = max_sz(m, gemm_scratch_bytes(rows, C, E));
+    m = max_sz(m, gemm_scratch_bytes(rows, E, V));
+    return m;
+}
 template <typename A>
-static void step_layout(A& a, int rows, int E, int H, int C, StepWs* ws) {
+static void step_layout(A& a, int rows, int E, int H, int C, int64_t V, StepWs* ws) {
     float* e = (float*)a.template take<float>((size_t)rows * E);
     float* gi = (float*)a.template take<float>((size_t)rows * 3 * H);
     float* gh = (float*)a.template take<float>((size_t)rows * 3 * H);
@@ -196,7 +242,12 @@ static void step_layout(A& a, int rows, int E, int H, int C, StepWs* ws) {
     float* c = (float*)a.template take<float>((size_t)rows * C);
     float* x2 = (float*)a.template take<float>((size_t)rows * H);
     float* t = (float*)a.template take<float>((size_t)rows * E);
-    if (ws) { ws->e = e; ws->gi = gi; ws->gh = gh; ws->h1 = h1; ws->q = q; ws->c = c; ws->x2 = x2; ws->t = t; }
+    const size_t sb = step_scratch_bytes(rows, E, H, C, V);
+    void* sc = a.template take<char>(sb);
+    if (ws) {
+        ws->e = e; ws->gi = gi; ws->gh = gh; ws->h1 = h1; ws->q = q; ws->c = c; ws->x2 = x2; ws->t = t;
+        ws->scratch = sc; ws->scratch_bytes = sb;
+    }
 }
 
 // One conditional-GRU step up to (and including) the vocabulary logits.  NMT_Decoder.py:109-143.
@@ -206,30 +257,30 @@ static int decoder_step_core(const vag_decoder_weights* w, const StepWs& ws, con
     const int E = w->E, H = w->H, C = w->C;
     const int64_t V = w->V;
     vag_stream_t vs = (vag_stream_t)st;
+    const Gemm gemm{st, ws.scratch, ws.scratch_bytes};
     VAG_TRY(vag_embed_rows_f32(ws.e, E, w->emb, E, tokens, rows, V, vs));                                              // :118
-    VAG_TRY(linear_dispatch(ws.gi, 3 * H, ws.e, E, w->gru1_w_ih, E, w->gru1_b_ih, rows, E, 3 * H, 0, st));              // :121
-    VAG_TRY(linear_dispatch(ws.gh, 3 * H, h_prev, H, w->gru1_w_hh, H, w->gru1_b_hh, rows, H, 3 * H, 0, st));
+    VAG_TRY(gemm(ws.gi, 3 * H, ws.e, E, w->gru1_w_ih, E, w->gru1_b_ih, rows, E, 3 * H, 0));              // :121
+    VAG_TRY(gemm(ws.gh, 3 * H, h_prev, H, w->gru1_w_hh, H, w->gru1_b_hh, rows, H, 3 * H, 0));
     VAG_TRY(vag_gru_gates_f32(ws.h1, H, nullptr, 0, ws.gi, 3 * H, ws.gh, 3 * H, h_prev, H, rows, H, vs));
-    VAG_TRY(linear_dispatch(ws.q, C, ws.h1, H, w->attn_h_w, H, nullptr, rows, H, C, 0, st));                            // :47
+    VAG_TRY(gemm(ws.q, C, ws.h1, H, w->attn_h_w, H, nullptr, rows, H, C, 0));                            // :47
     VAG_TRY(vag_attention_f32(ws.c, C, alpha_out, ws.q, C, keys, ctx, w->attn_v, mask, rows, rows_per_sent, T, C,
                               VAG_ATTN_MLP, vs));                                                                       // :124-126
-    VAG_TRY(linear_dispatch(ws.x2, H, ws.c, C, w->c2h_w, C, nullptr, rows, C, H, 0, st));                               // :127
-    VAG_TRY(linear_dispatch(ws.gi, 3 * H, ws.x2, H, w->gru2_w_ih, H, w->gru2_b_ih, rows, H, 3 * H, 0, st));             // :129
-    VAG_TRY(linear_dispatch(ws.gh, 3 * H, ws.h1, H, w->gru2_w_hh, H, w->gru2_b_hh, rows, H, 3 * H, 0, st));
+    VAG_TRY(gemm(ws.x2, H, ws.c, C, w->c2h_w, C, nullptr, rows, C, H, 0));                               // :127
+    VAG_TRY(gemm(ws.gi, 3 * H, ws.x2, H, w->gru2_w_ih, H, w->gru2_b_ih, rows, H, 3 * H, 0));             // :129
+    VAG_TRY(gemm(ws.gh, 3 * H, ws.h1, H, w->gru2_w_hh, H, w->gru2_b_hh, rows, H, 3 * H, 0));
     VAG_TRY(vag_gru_gates_f32(h_out, H, nullptr, 0, ws.gi, 3 * H, ws.gh, 3 * H, ws.h1, H, rows, H, vs));
     // t = tanh((W1 h2 + b1) + (W3 e + b3) + (W2 c + b2)), summed left to right like :137
-    VAG_TRY(linear_dispatch(ws.t, E, h_out, H, w->w1_w, H, w->w1_b, rows, H, E, 0, st));
-    VAG_TRY(linear_dispatch(ws.t, E, ws.e, E, w->w3_w, E, w->w3_b, rows, E, E, VAG_LIN_ACCUMULATE, st));
-    VAG_TRY(linear_dispatch(ws.t, E, ws.c, C, w->w2_w, C, w->w2_b, rows, C, E, VAG_LIN_ACCUMULATE | VAG_LIN_TANH, st));
-    if (logits) VAG_TRY(linear_dispatch(logits, V, ws.t, E, w->out_w, E, w->out_b, rows, E, (int)V, 0, st));            // :143
+    VAG_TRY(gemm(ws.t, E, h_out, H, w->w1_w, H, w->w1_b, rows, H, E, 0));
+    VAG_TRY(gemm(ws.t, E, ws.e, E, w->w3_w, E, w->w3_b, rows, E, E, VAG_LIN_ACCUMULATE));
+    VAG_TRY(gemm(ws.t, E, ws.c, C, w->w2_w, C, w->w2_b, rows, C, E, VAG_LIN_ACCUMULATE | VAG_LIN_TANH));
+    if (logits) VAG_TRY(gemm(logits, V, ws.t, E, w->out_w, E, w->out_b, rows, E, (int)V, 0));            // :143
     return VAG_OK;
 }
 }  // namespace vag
 
 extern "C" size_t vag_decoder_step_workspace_bytes(int rows, int E, int H, int C, int64_t V) {
     SizerAdapter s;
-    step_layout(s, rows, E, H, C, nullptr);
-    (void)V;
+    step_layout(s, rows, E, H, C, V, nullptr);
     return s.s.total();
 }
 
@@ -242,7 +293,7 @@ extern "C" int vag_decoder_step_f32(const vag_decoder_weights* w, const int64_t*
     VAG_REQUIRE(h_out != h_prev, "vag_decoder_step_f32: h_out must not alias h_prev");
     ArenaAdapter ar(workspace, workspace_bytes);
     StepWs ws;
-    step_layout(ar, rows, w->E, w->H, w->C, &ws);
+    step_layout(ar, rows, w->E, w->H, w->C, w->V, &ws);
     if (ar.a.overflow) {
         set_error("vag_decoder_step_f32: workspace %zu B too small", workspace_bytes);
         return VAG_ERR_WORKSPACE;
@@ -266,7 +317,7 @@ template <typename A>
 static void beam_layout(A& a, int B, int K, int L, int E, int H, int C, int64_t V, BeamWs* ws) {
     const int N = B * K;
     StepWs sw;
-    step_layout(a, N, E, H, C, &sw);
+    step_layout(a, N, E, H, C, V, &sw);
     float* logits = (float*)a.template take<float>((size_t)N * V);
     float* lse = (float*)a.template take<float>((size_t)N);
     float* h_a = (float*)a.template take<float>((size_t)N * H);

@@ -1,10 +1,429 @@
-// Tensor-core (tcgen05 / TMEM / TMA) path of vag_linear_f32 — placeholder until the 3xTF32 kernel lands.
+// Tensor-core contraction for the FP32-exact mode:  y = act(x · Wᵀ + bias [+ y])  with 3xTF32 error compensation.
+//
+// tcgen05 has no FP32-input MMA, and plain TF32 (10-bit mantissa) flips beams (hard part 1).
+// Every operand is therefore split once into hi = rn_tf32(v) and lo = v - hi (exact in FP32) and the product is
+// accumulated in TMEM (FP32) as  hi·hi + (hi·lo + lo·hi) ; the dropped lo·lo term is ≤ 2^-24 relative.
+// The tensor core adds into its FP32 accumulator with truncation, a bias that grows with the number of
+// accumulating instructions, so the 2^-12-times-smaller cross terms get their OWN accumulator (second half of the
+// TMEM allocation): the main accumulator sees K/8 additions instead of 3K/8 and the two are summed once, in
+// round-to-nearest FP32, by the epilogue.
+//
+// Kernel anatomy (one 128 x BN output tile per CTA, 192 threads):
+//   warp 0   TMA producer: cp.async.bulk.tensor 2-D boxes {32 fp32 = 128 B, rows} of x_hi, x_lo, w_hi, w_lo
+//            into a STAGES-deep shared-memory ring (SWIZZLE_128B), completion on mbarriers (expect_tx)
+//   warp 1   TMEM allocation + MMA issuer: one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8)
+//            from shared-memory descriptors, 3 products per k-step; tcgen05.commit releases ring slots and
+//            finally signals the epilogue
+//   warps 2-5  epilogue: tcgen05.ld (32 lanes x 32 columns) → bias / accumulate / tanh → global stores
 #include "common.cuh"
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <stdlib.h>
+#include <string.h>
+#include <mutex>
+
 namespace vag {
-int linear_tc(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias,
-              int rows, int K, int N, int flags, cudaStream_t st, bool* taken) {
-    (void)y; (void)ldy; (void)x; (void)ldx; (void)w; (void)ldw; (void)bias; (void)rows; (void)K; (void)N; (void)flags; (void)st;
-    *taken = false;
+
+// ------------------------------------------------------------------------------------------ operand split
+// hi = round-to-nearest TF32 of v (low 13 mantissa bits zero), lo = v - hi.  Outputs are compact [rows, K].
+__global__ void __launch_bounds__(256)
+split_tf32_kernel(const float* __restrict__ x, int64_t ldx, int rows, int K, float* __restrict__ hi, float* __restrict__ lo) {
+    const int kq = K >> 2;
+    const int64_t total = (int64_t)rows * kq;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / kq), c = (int)(i % kq) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(x + (int64_t)r * ldx + c);
+        float4 h, l;
+        uint32_t t;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.x)); h.x = __uint_as_float(t); l.x = v.x - h.x;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y)); h.y = __uint_as_float(t); l.y = v.y - h.y;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z)); h.z = __uint_as_float(t); l.z = v.z - h.z;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w)); h.w = __uint_as_float(t); l.w = v.w - h.w;
+        *reinterpret_cast<float4*>(hi + (int64_t)r * K + c) = h;
+        *reinterpret_cast<float4*>(lo + (int64_t)r * K + c) = l;
+    }
+}
+
+// FP16 flavour of the split (default): hi = rn_f16(v), lo' = rn_f16((v - hi)·2^11).  v ≈ hi + lo'·2^-11 with a
+// residual ≤ 2^-22·|v|; the cross accumulator is scaled by 2^-11 in the epilogue.  Same 11-bit pieces as TF32 but
+// half the bytes per element and K = 16 per instruction: twice the tensor rate and half as many truncating
+// accumulator updates.  Valid for |v| < 65504 (activations here are bounded by tanh / GRU gates, weights are O(1));
+// larger magnitudes surface as inf/NaN in the output rather than as silently wrong numbers.
+__global__ void __launch_bounds__(256)
+split_f16_kernel(const float* __restrict__ x, int64_t ldx, int rows, int K, __half* __restrict__ hi, __half* __restrict__ lo) {
+    const int kq = K >> 2;
+    const int64_t total = (int64_t)rows * kq;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / kq), c = (int)(i % kq) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(x + (int64_t)r * ldx + c);
+        const float in[4] = {v.x, v.y, v.z, v.w};
+        __half h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            h[j] = __float2half_rn(in[j]);
+            l[j] = __float2half_rn((in[j] - __half2float(h[j])) * 2048.0f);
+        }
+        *reinterpret_cast<uint2*>(hi + (int64_t)r * K + c) = *reinterpret_cast<uint2*>(h);
+        *reinterpret_cast<uint2*>(lo + (int64_t)r * K + c) = *reinterpret_cast<uint2*>(l);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <bool F16>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (F16)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format, see cute/arch/mma_sm100_desc.hpp):
+//   [0,14) start address >> 4   [16,30) leading byte offset >> 4 (unused for swizzled K-major)
+//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B)   [46,48) version = 1   [61,64) layout = 2 (SW128)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+template <int BN, bool F16>
+struct TcCfg {
+    static constexpr int BM = 128;
+    static constexpr int ELT = F16 ? 2 : 4;
+    static constexpr int BK = 128 / ELT;   // elements per 128-byte swizzle row: 32 (tf32) / 64 (f16)
+    static constexpr int UK = 32 / ELT;    // K of one MMA instruction (32 bytes): 8 / 16
+    static constexpr int STAGES = BN == 256 ? 2 : 3;
+    static constexpr int A_BYTES = BM * 128;
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr uint32_t FMT = F16 ? 0u : 2u;  // F16F32Format: F16 = 0, TF32 = 2
+    static constexpr uint32_t IDESC = (1u << 4) /*D=F32*/ | (FMT << 7) /*A*/ | (FMT << 10) /*B*/ |
+                                      ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+};
+
+template <int BN, bool F16>
+__global__ void __launch_bounds__(192, 1)
+linear_split3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
+                     const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
+                     float* __restrict__ y, int64_t ldy, const float* __restrict__ bias, int rows, int K, int N, int flags) {
+    using Cfg = TcCfg<BN, F16>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + Cfg::STAGES;
+    uint64_t* tmem_full_bar = empty_bar + Cfg::STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * Cfg::BM;
+    const int n0 = blockIdx.x * BN;
+    const int n_kb = (K + Cfg::BK - 1) / Cfg::BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_xh) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_xl) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wh) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wl) : "memory");
+        for (int s = 0; s < Cfg::STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // TMEM: 2 x BN fp32 accumulator columns (main | cross), a power of two ≥ 32
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * BN)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < n_kb; ++kb) {
+                const int s = kb % Cfg::STAGES;
+                const uint32_t ph = (kb / Cfg::STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+                mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+                const int k0 = kb * Cfg::BK;
+                tma_load_2d(st, &map_xh, &full_bar[s], k0, m0);
+                tma_load_2d(st + Cfg::A_BYTES, &map_xl, &full_bar[s], k0, m0);
+                tma_load_2d(st + 2 * Cfg::A_BYTES, &map_wh, &full_bar[s], k0, n0);
+                tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &map_wl, &full_bar[s], k0, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int kb = 0; kb < n_kb; ++kb) {
+                const int s = kb % Cfg::STAGES;
+                const uint32_t ph = (kb / Cfg::STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tcgen05_fence_after();
+                const uint32_t st = smem_u32(smem + s * Cfg::STAGE_BYTES);
+                const uint64_t d_ah = make_smem_desc(st);
+                const uint64_t d_al = make_smem_desc(st + Cfg::A_BYTES);
+                const uint64_t d_bh = make_smem_desc(st + 2 * Cfg::A_BYTES);
+                const uint64_t d_bl = make_smem_desc(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+#pragma unroll
+                for (int j = 0; j < Cfg::BK / Cfg::UK; ++j) {
+                    const uint64_t adv = (uint64_t)((j * 32) >> 4);  // 32 B per k-step inside the 128 B swizzle row
+                    umma<F16>(tmem_base + BN, d_al + adv, d_bh + adv, Cfg::IDESC, (kb | j) != 0);  // cross terms
+                    umma<F16>(tmem_base + BN, d_ah + adv, d_bl + adv, Cfg::IDESC, 1);
+                    umma<F16>(tmem_base, d_ah + adv, d_bh + adv, Cfg::IDESC, (kb | j) != 0);       // main term
+                }
+                tcgen05_commit(&empty_bar[s]);  // frees the slot once the MMAs above have read it
+            }
+            tcgen05_commit(tmem_full_bar);      // accumulator complete
+        }
+    } else {
+        // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
+        const int lg = warp & 3;
+        const int row = m0 + lg * 32 + lane;
+        mbar_wait(tmem_full_bar, 0);
+        tcgen05_fence_after();
+        const bool do_tanh = flags & VAG_LIN_TANH, do_acc = flags & VAG_LIN_ACCUMULATE;
+        const bool vec_ok = ((ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            if (n0 + c0 >= N) break;  // warp-uniform
+            uint32_t r[32], q[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
+                  "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15]), "=r"(q[16]),
+                  "=r"(q[17]), "=r"(q[18]), "=r"(q[19]), "=r"(q[20]), "=r"(q[21]), "=r"(q[22]), "=r"(q[23]), "=r"(q[24]),
+                  "=r"(q[25]), "=r"(q[26]), "=r"(q[27]), "=r"(q[28]), "=r"(q[29]), "=r"(q[30]), "=r"(q[31])
+                : "r"(taddr + (uint32_t)BN)
+                : "memory");
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                  "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                  "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                r[j] = __float_as_uint(__uint_as_float(r[j]) + (F16 ? __uint_as_float(q[j]) * (1.0f / 2048.0f) : __uint_as_float(q[j])));
+            if (row < rows) {
+                float* dst = y + (int64_t)row * ldy + n0 + c0;
+                const float* bp = bias ? bias + n0 + c0 : nullptr;
+                if (vec_ok && n0 + c0 + 32 <= N) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                               __uint_as_float(r[j + 3]));
+                        if (bp) { v.x += bp[j]; v.y += bp[j + 1]; v.z += bp[j + 2]; v.w += bp[j + 3]; }
+                        if (do_acc) {
+                            const float4 o = *reinterpret_cast<const float4*>(dst + j);
+                            v.x = o.x + v.x; v.y = o.y + v.y; v.z = o.z + v.z; v.w = o.w + v.w;
+                        }
+                        if (do_tanh) { v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w); }
+                        *reinterpret_cast<float4*>(dst + j) = v;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (n0 + c0 + j < N) {
+                            float v = __uint_as_float(r[j]);
+                            if (bp) v += bp[j];
+                            if (do_acc) v = dst[j] + v;
+                            if (do_tanh) v = tanhf(v);
+                            dst[j] = v;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    });
+    return fn;
+}
+
+// 2-D tensor [rows, K] (K contiguous, row pitch ld elements), box {128 B, box_rows}, SWIZZLE_128B, zero OOB fill.
+static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t K, int64_t ld, int box_rows, bool f16) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled entry point not available");
+        return VAG_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * (f16 ? 2 : 4)};
+    cuuint32_t box[2] = {f16 ? 64u : 32u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with %d (rows=%lld K=%lld ld=%lld)", (int)r, (long long)rows, (long long)K, (long long)ld);
+        return VAG_ERR_CUDA;
+    }
     return VAG_OK;
 }
+
+size_t linear_tc_scratch_bytes(int64_t rows, int64_t K, int64_t N) {
+    return (size_t)(2 * rows * K + 2 * N * K) * sizeof(float) + 4 * 256;
+}
+
+bool linear_tc_eligible(const float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, int rows, int K, int N) {
+    auto al = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+    (void)y; (void)ldy;
+    return rows >= 64 && N >= 64 && K >= 32 && (K % 8 == 0) && (ldx % 4 == 0) && (ldw % 4 == 0) && al(x) && al(w);
+}
+
+template <int BN, bool F16>
+static int launch_tc(const CUtensorMap& xh, const CUtensorMap& xl, const CUtensorMap& wh, const CUtensorMap& wl, float* y,
+                     int64_t ldy, const float* bias, int rows, int K, int N, int flags, cudaStream_t st) {
+    using Cfg = TcCfg<BN, F16>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VAG_CUDA(cudaFuncSetAttribute(linear_split3_kernel<BN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    dim3 grid(ceil_div(N, BN), ceil_div(rows, Cfg::BM));
+    linear_split3_kernel<BN, F16><<<grid, 192, Cfg::SMEM_BYTES, st>>>(xh, xl, wh, wl, y, ldy, bias, rows, K, N, flags);
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
+// VAG_GEMM=tf32x3 selects the TF32 split (any FP32 range); default is the FP16 split (2x the tensor rate).
+static bool use_f16_split() {
+    const char* e = getenv("VAG_GEMM");
+    return !(e && strcmp(e, "tf32x3") == 0);
+}
+
+// scratch: ≥ linear_tc_scratch_bytes(rows, K, N).  Splits both operands, then runs the tcgen05 kernel.
+int linear_tc(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, int rows,
+              int K, int N, int flags, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+    if (scratch_bytes < linear_tc_scratch_bytes(rows, K, N) || !scratch) {
+        set_error("linear_tc: scratch %zu B too small", scratch_bytes);
+        return VAG_ERR_WORKSPACE;
+    }
+    Arena ar(scratch, scratch_bytes);
+    const bool f16 = use_f16_split();
+    const size_t esz = f16 ? 2 : 4;
+    void* xh = ar.take<char>((size_t)rows * K * esz);
+    void* xl = ar.take<char>((size_t)rows * K * esz);
+    void* wh = ar.take<char>((size_t)N * K * esz);
+    void* wl = ar.take<char>((size_t)N * K * esz);
+    if (ar.overflow) {
+        set_error("linear_tc: scratch overflow");
+        return VAG_ERR_WORKSPACE;
+    }
+    const int sms = num_sms();
+    {
+        const int64_t tot = (int64_t)rows * (K / 4);
+        const int gx = (int)std::min<int64_t>(ceil_div64(tot, 256), (int64_t)sms * 8);
+        const int64_t totw = (int64_t)N * (K / 4);
+        const int gw = (int)std::min<int64_t>(ceil_div64(totw, 256), (int64_t)sms * 8);
+        if (f16) {
+            split_f16_kernel<<<gx, 256, 0, st>>>(x, ldx, rows, K, (__half*)xh, (__half*)xl);
+            VAG_LAUNCH_CHECK();
+            split_f16_kernel<<<gw, 256, 0, st>>>(w, ldw, N, K, (__half*)wh, (__half*)wl);
+            VAG_LAUNCH_CHECK();
+        } else {
+            split_tf32_kernel<<<gx, 256, 0, st>>>(x, ldx, rows, K, (float*)xh, (float*)xl);
+            VAG_LAUNCH_CHECK();
+            split_tf32_kernel<<<gw, 256, 0, st>>>(w, ldw, N, K, (float*)wh, (float*)wl);
+            VAG_LAUNCH_CHECK();
+        }
+    }
+    const bool wide = (int64_t)ceil_div(N, 256) * ceil_div(rows, 128) >= sms;
+    const int bn = wide ? 256 : 128;
+    CUtensorMap mxh, mxl, mwh, mwl;
+    VAG_TRY(make_map(&mxh, xh, rows, K, K, 128, f16));
+    VAG_TRY(make_map(&mxl, xl, rows, K, K, 128, f16));
+    VAG_TRY(make_map(&mwh, wh, N, K, K, bn, f16));
+    VAG_TRY(make_map(&mwl, wl, N, K, K, bn, f16));
+    if (f16) {
+        if (wide) return launch_tc<256, true>(mxh, mxl, mwh, mwl, y, ldy, bias, rows, K, N, flags, st);
+        return launch_tc<128, true>(mxh, mxl, mwh, mwl, y, ldy, bias, rows, K, N, flags, st);
+    }
+    if (wide) return launch_tc<256, false>(mxh, mxl, mwh, mwl, y, ldy, bias, rows, K, N, flags, st);
+    return launch_tc<128, false>(mxh, mxl, mwh, mwl, y, ldy, bias, rows, K, N, flags, st);
+}
+
 }  // namespace vag

@@ -68,6 +68,24 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     return out2.reshape(*lead, out_dim)
 
 
+def linear_tc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, flags: int = 0,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Same contract as ``linear`` on the tcgen05 3xTF32 kernel (raises VagError for ineligible shapes)."""
+    _chk_f32(x, w, bias, out)
+    lib = _cabi.lib()
+    assert x.dim() == 2 and x.stride(1) == 1 and w.stride(1) == 1
+    rows, in_dim = x.shape
+    out_dim = w.shape[0]
+    if out is None:
+        assert not (flags & LIN_ACCUMULATE)
+        out = torch.empty(rows, out_dim, dtype=torch.float32, device=x.device)
+    ws = workspace(lib.vag_linear_tc_workspace_bytes(rows, in_dim, out_dim), x.device, slot="gemm")
+    with torch.cuda.device(x.device):
+        check(lib.vag_linear_tc_f32(out.data_ptr(), out.stride(0), x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0),
+                                    ptr(bias), rows, in_dim, out_dim, flags, ws.data_ptr(), ws.numel(), stream_ptr()))
+    return out
+
+
 def embed_rows(table: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
     _chk_f32(table)
     lib = _cabi.lib()
@@ -237,8 +255,10 @@ def attn_keys(w: DecoderWeights, ctx: torch.Tensor) -> torch.Tensor:
     ctx = ctx.contiguous()
     B, T, Cd = ctx.shape
     keys = torch.empty_like(ctx)
+    ws = workspace(lib.vag_attn_keys_workspace_bytes(B, T, Cd), ctx.device)
     with torch.cuda.device(ctx.device):
-        check(lib.vag_attn_keys_f32(C.byref(w), ctx.data_ptr(), B, T, keys.data_ptr(), stream_ptr()))
+        check(lib.vag_attn_keys_f32(C.byref(w), ctx.data_ptr(), B, T, keys.data_ptr(), ws.data_ptr(), ws.numel(),
+                                    stream_ptr()))
     return keys
 
 
@@ -247,7 +267,7 @@ def decoder_init(w: DecoderWeights, ctx_vec: Optional[torch.Tensor], ctx: torch.
     lib = _cabi.lib()
     B, T, Cd = ctx.shape
     h0 = torch.empty(B, w.H, dtype=torch.float32, device=ctx.device)
-    ws = workspace(B * Cd * 4 + 512, ctx.device)
+    ws = workspace(B * Cd * 4 + 1024 + lib.vag_linear_tc_workspace_bytes(B, Cd, w.H), ctx.device)
     with torch.cuda.device(ctx.device):
         check(lib.vag_decoder_init_f32(C.byref(w), ptr(ctx_vec), ctx.data_ptr(), mask.data_ptr(), float(split), B, T,
                                        h0.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr()))
