@@ -133,6 +133,162 @@ beam_select_kernel(const float* __restrict__ logits, int64_t ld, const float* __
     if (tid == 0 && fin_counter) atomicAdd(fin_counter, n_eos);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Fast selection for real vocabularies (V >= kFastMinV): one CTA per sentence, ONE pass over the logits.
+// Per row: every thread scans a strided slice keeping an online (max, Σexp) pair and a private top-3; the block
+// combines the log-sum-exp and then pops the row's K best in canonical order with a block arg-max.  A thread
+// whose private list runs dry refills it lazily by rescanning its own slice below the last key it gave away, so
+// the result is exact however the large logits are distributed.  The K·K row candidates (score = nll_k +
+// (logit − lse_k)) are merged by one warp.  The repeated token is skipped during the scan (V11:279-280) and a
+// finished hypothesis contributes exactly one candidate, <eos> at +0 (V11:291-294); their −1e5 siblings can never
+// be selected when V − 1 >= K, which holds for every vocabulary this kernel accepts.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kFastMinV = 512;
+
+struct Top3 {
+    float v0, v1, v2;
+    int i0, i1, i2;
+    __device__ __forceinline__ void init() { v0 = v1 = v2 = -INFINITY; i0 = i1 = i2 = 0x7fffffff; }
+    __device__ __forceinline__ void push(float c, int ci) {
+        if (!cand_better(c, ci, v2, i2)) return;
+        if (cand_better(c, ci, v0, i0)) { v2 = v1; i2 = i1; v1 = v0; i1 = i0; v0 = c; i0 = ci; }
+        else if (cand_better(c, ci, v1, i1)) { v2 = v1; i2 = i1; v1 = c; i1 = ci; }
+        else { v2 = c; i2 = ci; }
+    }
+    __device__ __forceinline__ void pop() { v0 = v1; i0 = i1; v1 = v2; i1 = i2; v2 = -INFINITY; i2 = 0x7fffffff; }
+    __device__ __forceinline__ bool empty() const { return i0 == 0x7fffffff; }
+};
+
+template <int KMAX>
+__global__ void __launch_bounds__(256)
+beam_select_fast_kernel(const float* __restrict__ logits, int64_t ld, int subtract_lse,
+                        const int64_t* __restrict__ prev_tokens, float* __restrict__ nll, int64_t* __restrict__ tokens_out,
+                        int32_t* __restrict__ parents_out, int K, int V, int step, int avoid_double,
+                        const int* __restrict__ done, int* __restrict__ fin_counter) {
+    if (done && *done) return;
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    __shared__ float pool_v[KMAX * KMAX];
+    __shared__ int pool_i[KMAX * KMAX];
+    __shared__ float nll_s[KMAX];
+    __shared__ int cur_s[KMAX];
+    __shared__ float red_a[8], red_b[8];
+    __shared__ int red_i[8], red_t[8];
+    __shared__ float bc_f[2];
+    __shared__ int bc_i[2];
+
+    const int Kin = step == 0 ? 1 : K;
+    if (tid < Kin) {
+        nll_s[tid] = step == 0 ? 0.f : nll[(int64_t)b * K + tid];
+        cur_s[tid] = step == 0 ? -1 : (int)prev_tokens[(int64_t)b * K + tid];
+    }
+    for (int i = tid; i < KMAX * KMAX; i += blockDim.x) { pool_v[i] = -INFINITY; pool_i[i] = 0x7fffffff; }
+    __syncthreads();
+
+    for (int k = 0; k < Kin; ++k) {
+        const float base = nll_s[k];
+        const int cur = cur_s[k];
+        if (step > 0 && cur == kEOS) {  // finished hypothesis: single candidate <eos> at +0
+            if (tid == 0) { pool_v[k * KMAX] = base + 0.f; pool_i[k * KMAX] = k * V + kEOS; }
+            continue;
+        }
+        const float* row = logits + (int64_t)(b * Kin + k) * ld;
+        const int skip = (avoid_double && step > 0) ? cur : -1;
+        // ---- single pass: online log-sum-exp + private top-3
+        Top3 top;
+        top.init();
+        float m = -INFINITY, s = 0.f;
+        int n_seen = 0;
+        for (int v = tid; v < V; v += 256) {
+            const float x = row[v];
+            if (x > m) { s = s * __expf(m - x) + 1.f; m = x; }
+            else s += __expf(x - m);
+            if (v != skip) { top.push(x, v); ++n_seen; }
+        }
+        // ---- block log-sum-exp (the skipped token still belongs to the softmax denominator)
+        float bm = warp_max(m);
+        float bs = warp_sum(m == -INFINITY ? 0.f : s * __expf(m - bm));
+        if (lane == 0) { red_a[wid] = bm; red_b[wid] = bs; }
+        __syncthreads();
+        if (tid == 0) {
+            float fm = red_a[0];
+            for (int w = 1; w < 8; ++w) fm = fmaxf(fm, red_a[w]);
+            float fs = 0.f;
+            for (int w = 0; w < 8; ++w) fs += red_b[w] * __expf(red_a[w] - fm);
+            bc_f[0] = subtract_lse ? fm + logf(fs) : 0.f;
+        }
+        __syncthreads();
+        const float lse = bc_f[0];
+        // ---- pop the row's K best
+        for (int round = 0; round < K; ++round) {
+            float bv = top.v0;
+            int bi = top.i0, bt = tid;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                const int ot = __shfl_xor_sync(0xffffffffu, bt, o);
+                if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; bt = ot; }
+            }
+            if (lane == 0) { red_a[wid] = bv; red_i[wid] = bi; red_t[wid] = bt; }
+            __syncthreads();
+            if (tid == 0) {
+                float fv = red_a[0];
+                int fi = red_i[0], ft = red_t[0];
+                for (int w = 1; w < 8; ++w)
+                    if (cand_better(red_a[w], red_i[w], fv, fi)) { fv = red_a[w]; fi = red_i[w]; ft = red_t[w]; }
+                bc_i[0] = ft;
+                if (fi != 0x7fffffff) {
+                    const float lp = fv - lse;
+                    pool_v[k * KMAX + round] = step == 0 ? lp : base + lp;
+                    pool_i[k * KMAX + round] = k * V + fi;
+                }
+            }
+            __syncthreads();
+            if (tid == bc_i[0] && !top.empty()) {
+                const float pv = top.v0;
+                const int pi = top.i0;
+                top.pop();
+                if (top.empty() && n_seen > 3) {  // refill: next best of my slice strictly after (pv, pi)
+                    for (int v = tid; v < V; v += 256) {
+                        const float x = row[v];
+                        if (v != skip && cand_better(pv, pi, x, v)) top.push(x, v);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- merge the Kin·K row candidates: warp 0, K rounds
+    if (wid == 0) {
+        int n_eos = 0;
+        for (int round = 0; round < K; ++round) {
+            float bv = -INFINITY;
+            int bi = 0x7fffffff, bs = -1;
+            for (int j = lane; j < KMAX * KMAX; j += 32)
+                if (cand_better(pool_v[j], pool_i[j], bv, bi)) { bv = pool_v[j]; bi = pool_i[j]; bs = j; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                const int os = __shfl_xor_sync(0xffffffffu, bs, o);
+                if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; bs = os; }
+            }
+            if (lane == 0) {
+                const int tok = bi % V, par = bi / V;
+                nll[(int64_t)b * K + round] = bv;
+                tokens_out[(int64_t)b * K + round] = tok;
+                parents_out[(int64_t)b * K + round] = par;
+                n_eos += (tok == kEOS);
+                pool_v[bs] = -INFINITY;
+                pool_i[bs] = 0x7fffffff;
+            }
+            __syncwarp();
+        }
+        if (lane == 0 && fin_counter) atomicAdd(fin_counter, n_eos);
+    }
+}
+
 // Row gather by parent + early-stop bookkeeping.
 //   h_next[b*K + k, :] = h_cur[b*Kin + parents[b,k], :]
 // Block (0,0) thread 0 also turns the per-step EOS counter into the `done` flag / steps_run the way the
@@ -255,14 +411,22 @@ int beam_select(const float* logits, int64_t ld, const float* lse, const int64_t
         set_error("K*V overflows the 31-bit candidate index");
         return VAG_ERR_UNSUPPORTED;
     }
-    if (K <= 4)
-        beam_select_kernel<4><<<B, 256, 0, st>>>(logits, ld, lse, prev_tokens, nll, tokens_out, parents_out, K, V, step, avoid_double, done, fin_counter);
-    else if (K <= 8)
-        beam_select_kernel<8><<<B, 256, 0, st>>>(logits, ld, lse, prev_tokens, nll, tokens_out, parents_out, K, V, step, avoid_double, done, fin_counter);
-    else if (K <= 12)
-        beam_select_kernel<12><<<B, 256, 0, st>>>(logits, ld, lse, prev_tokens, nll, tokens_out, parents_out, K, V, step, avoid_double, done, fin_counter);
-    else
-        beam_select_kernel<16><<<B, 256, 0, st>>>(logits, ld, lse, prev_tokens, nll, tokens_out, parents_out, K, V, step, avoid_double, done, fin_counter);
+    const bool fast = V >= kFastMinV && V > K + 1;
+    const int subtract = lse ? 1 : 0;  // the fast kernel computes the row log-sum-exp itself
+#define VAG_SELECT(KM)                                                                                                    \
+    do {                                                                                                                  \
+        if (fast)                                                                                                         \
+            beam_select_fast_kernel<KM><<<B, 256, 0, st>>>(logits, ld, subtract, prev_tokens, nll, tokens_out, parents_out, \
+                                                           K, (int)V, step, avoid_double, done, fin_counter);              \
+        else                                                                                                              \
+            beam_select_kernel<KM><<<B, 256, 0, st>>>(logits, ld, lse, prev_tokens, nll, tokens_out, parents_out, K, V, step, \
+                                                      avoid_double, done, fin_counter);                                   \
+    } while (0)
+    if (K <= 4) VAG_SELECT(4);
+    else if (K <= 8) VAG_SELECT(8);
+    else if (K <= 12) VAG_SELECT(12);
+    else VAG_SELECT(16);
+#undef VAG_SELECT
     VAG_LAUNCH_CHECK();
     return VAG_OK;
 }

@@ -253,7 +253,7 @@ static void step_layout(A& a, int rows, int E, int H, int C, int64_t V, StepWs* 
 // One conditional-GRU step up to (and including) the vocabulary logits.  NMT_Decoder.py:109-143.
 static int decoder_step_core(const vag_decoder_weights* w, const StepWs& ws, const int64_t* tokens, const float* h_prev,
                              const float* keys, const float* ctx, const float* mask, int rows, int rows_per_sent, int T,
-                             float* h_out, float* logits, float* alpha_out, cudaStream_t st) {
+                             float* h_out, float* logits, int64_t ld_logits, float* alpha_out, cudaStream_t st) {
     const int E = w->E, H = w->H, C = w->C;
     const int64_t V = w->V;
     vag_stream_t vs = (vag_stream_t)st;
@@ -273,7 +273,7 @@ static int decoder_step_core(const vag_decoder_weights* w, const StepWs& ws, con
     VAG_TRY(gemm(ws.t, E, h_out, H, w->w1_w, H, w->w1_b, rows, H, E, 0));
     VAG_TRY(gemm(ws.t, E, ws.e, E, w->w3_w, E, w->w3_b, rows, E, E, VAG_LIN_ACCUMULATE));
     VAG_TRY(gemm(ws.t, E, ws.c, C, w->w2_w, C, w->w2_b, rows, C, E, VAG_LIN_ACCUMULATE | VAG_LIN_TANH));
-    if (logits) VAG_TRY(gemm(logits, V, ws.t, E, w->out_w, E, w->out_b, rows, E, (int)V, 0));            // :143
+    if (logits) VAG_TRY(gemm(logits, ld_logits, ws.t, E, w->out_w, E, w->out_b, rows, E, (int)V, 0));            // :143
     return VAG_OK;
 }
 }  // namespace vag
@@ -298,7 +298,7 @@ extern "C" int vag_decoder_step_f32(const vag_decoder_weights* w, const int64_t*
         set_error("vag_decoder_step_f32: workspace %zu B too small", workspace_bytes);
         return VAG_ERR_WORKSPACE;
     }
-    VAG_TRY(decoder_step_core(w, ws, tokens, h_prev, keys, ctx, mask, rows, rows_per_sent, T, h_out, logits_or_logp, alpha_out,
+    VAG_TRY(decoder_step_core(w, ws, tokens, h_prev, keys, ctx, mask, rows, rows_per_sent, T, h_out, logits_or_logp, w->V, alpha_out,
                               (cudaStream_t)stream));
     if (want_logp) VAG_TRY(vag_log_softmax_f32(logits_or_logp, logits_or_logp, rows, (int)w->V, stream));
     return VAG_OK;
@@ -318,7 +318,7 @@ static void beam_layout(A& a, int B, int K, int L, int E, int H, int C, int64_t 
     const int N = B * K;
     StepWs sw;
     step_layout(a, N, E, H, C, V, &sw);
-    float* logits = (float*)a.template take<float>((size_t)N * V);
+    float* logits = (float*)a.template take<float>((size_t)N * ((V + 3) / 4 * 4));  // rows padded to 16 B
     float* lse = (float*)a.template take<float>((size_t)N);
     float* h_a = (float*)a.template take<float>((size_t)N * H);
     float* h_b = (float*)a.template take<float>((size_t)N * H);
@@ -365,14 +365,16 @@ extern "C" int vag_beam_decode_f32(const vag_decoder_weights* w, const float* h0
     VAG_CUDA(cudaMemsetAsync(ws.flags, 0, sizeof(int) * (size_t)(L + 2), st));
     fill_i64_kernel<<<ceil_div(B, 256), 256, 0, st>>>(ws.sos, 2 /*SOS*/, B);
     VAG_LAUNCH_CHECK();
+    const int64_t ldl = (V + 3) / 4 * 4;
     for (int di = 0; di < L; ++di) {
         const int rows = di == 0 ? B : N;
         const int rps = di == 0 ? 1 : K;
         const int64_t* tokens = di == 0 ? ws.sos : ws.tok_hist + (size_t)(di - 1) * N;
         const float* h_prev = di == 0 ? h0 : ws.h_a;
-        VAG_TRY(decoder_step_core(w, ws.step, tokens, h_prev, keys, ctx, mask, rows, rps, T, ws.h_b, ws.logits, nullptr, st));
-        VAG_TRY(row_lse(ws.lse, ws.logits, V, rows, V, st));
-        VAG_TRY(beam_select(ws.logits, V, ws.lse, di == 0 ? nullptr : tokens, ws.nll, ws.tok_hist + (size_t)di * N,
+        VAG_TRY(decoder_step_core(w, ws.step, tokens, h_prev, keys, ctx, mask, rows, rps, T, ws.h_b, ws.logits, ldl, nullptr, st));
+        const bool fused_lse = V >= 512;  // the fast selection kernel folds the log-sum-exp into its single pass
+        if (!fused_lse) VAG_TRY(row_lse(ws.lse, ws.logits, ldl, rows, V, st));
+        VAG_TRY(beam_select(ws.logits, ldl, ws.lse, di == 0 ? nullptr : tokens, ws.nll, ws.tok_hist + (size_t)di * N,
                             ws.par_hist + (size_t)di * N, B, K, V, di, avoid_double, done, fin + di, st));
         VAG_TRY(beam_advance(ws.h_a, ws.h_b, ws.par_hist + (size_t)di * N, B, K, rps, H, di, done, fin + di, steps_run, st));
     }
@@ -400,9 +402,10 @@ extern "C" int vag_greedy_decode_f32(const vag_decoder_weights* w, const float* 
     VAG_CUDA(cudaMemcpyAsync(ws.h_a, h0, sizeof(float) * (size_t)B * w->H, cudaMemcpyDeviceToDevice, st));
     float* h_cur = ws.h_a;
     float* h_nxt = ws.h_b;
+    const int64_t ldl = (w->V + 3) / 4 * 4;
     for (int di = 0; di < L; ++di) {
-        VAG_TRY(decoder_step_core(w, ws.step, ws.sos, h_cur, keys, ctx, mask, B, 1, T, h_nxt, ws.logits, nullptr, st));
-        VAG_TRY(row_argmax(ws.logits, w->V, B, w->V, tokens_out + di, L, ws.sos, st));
+        VAG_TRY(decoder_step_core(w, ws.step, ws.sos, h_cur, keys, ctx, mask, B, 1, T, h_nxt, ws.logits, ldl, nullptr, st));
+        VAG_TRY(row_argmax(ws.logits, ldl, B, w->V, tokens_out + di, L, ws.sos, st));
         std::swap(h_cur, h_nxt);
     }
     return VAG_OK;

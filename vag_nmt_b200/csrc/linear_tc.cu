@@ -233,11 +233,9 @@ linear_split3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_co
     } else {
         // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
         const int lg = warp & 3;
-        const int row = m0 + lg * 32 + lane;
         mbar_wait(tmem_full_bar, 0);
         tcgen05_fence_after();
         const bool do_tanh = flags & VAG_LIN_TANH, do_acc = flags & VAG_LIN_ACCUMULATE;
-        const bool vec_ok = ((ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             if (n0 + c0 >= N) break;  // warp-uniform
@@ -267,33 +265,24 @@ linear_split3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_co
 #pragma unroll
             for (int j = 0; j < 32; ++j)
                 r[j] = __float_as_uint(__uint_as_float(r[j]) + (F16 ? __uint_as_float(q[j]) * (1.0f / 2048.0f) : __uint_as_float(q[j])));
-            if (row < rows) {
-                float* dst = y + (int64_t)row * ldy + n0 + c0;
-                const float* bp = bias ? bias + n0 + c0 : nullptr;
-                if (vec_ok && n0 + c0 + 32 <= N) {
+            // transpose through shared memory (the pipeline stages are idle now) so that every store instruction
+            // writes 32 consecutive floats of ONE output row instead of one float in each of 32 rows
+            float* tile = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);
+            __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                               __uint_as_float(r[j + 3]));
-                        if (bp) { v.x += bp[j]; v.y += bp[j + 1]; v.z += bp[j + 2]; v.w += bp[j + 3]; }
-                        if (do_acc) {
-                            const float4 o = *reinterpret_cast<const float4*>(dst + j);
-                            v.x = o.x + v.x; v.y = o.y + v.y; v.z = o.z + v.z; v.w = o.w + v.w;
-                        }
-                        if (do_tanh) { v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w); }
-                        *reinterpret_cast<float4*>(dst + j) = v;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (n0 + c0 + j < N) {
-                            float v = __uint_as_float(r[j]);
-                            if (bp) v += bp[j];
-                            if (do_acc) v = dst[j] + v;
-                            if (do_tanh) v = tanhf(v);
-                            dst[j] = v;
-                        }
-                    }
+            for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = __uint_as_float(r[j]);
+            __syncwarp();
+            const int col = n0 + c0 + lane;
+            if (col < N) {
+                const float bv = bias ? bias[col] : 0.f;
+                const int r_lim = min(32, rows - (m0 + lg * 32));
+                float* dst = y + (int64_t)(m0 + lg * 32) * ldy + col;
+#pragma unroll 4
+                for (int rr = 0; rr < r_lim; ++rr) {
+                    float v = tile[rr * 33 + lane] + bv;
+                    if (do_acc) v = dst[(int64_t)rr * ldy] + v;
+                    if (do_tanh) v = tanhf(v);
+                    dst[(int64_t)rr * ldy] = v;
                 }
             }
         }
