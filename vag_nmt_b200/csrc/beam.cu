@@ -135,29 +135,42 @@ beam_select_kernel(const float* __restrict__ logits, int64_t ld, const float* __
 
 // ---------------------------------------------------------------------------------------------------------
 // Fast selection for real vocabularies (V >= kFastMinV): one CTA per sentence, ONE pass over the logits.
-// Per row: every thread scans a strided slice keeping an online (max, Σexp) pair and a private top-3; the block
-// combines the log-sum-exp and then pops the row's K best in canonical order with a block arg-max.  A thread
-// whose private list runs dry refills it lazily by rescanning its own slice below the last key it gave away, so
-// the result is exact however the large logits are distributed.  The K·K row candidates (score = nll_k +
-// (logit − lse_k)) are merged by one warp.  The repeated token is skipped during the scan (V11:279-280) and a
-// finished hypothesis contributes exactly one candidate, <eos> at +0 (V11:291-294); their −1e5 siblings can never
-// be selected when V − 1 >= K, which holds for every vocabulary this kernel accepts.
+//
+// Every thread owns a strided slice of each of the sentence's K rows.  During the single pass it keeps, per row,
+// an online (max, Σexp) pair and the BEST element of its slice (shared memory, [row][thread]).  After the rows'
+// log-sum-exps are combined, the best-of-slice values become scores  nll_k + (logit − lse_k)  and the block pops
+// the K winners in canonical order (score desc, flat index k·V+v asc) with K rounds of a block arg-max; only the
+// thread that owned a winner rescans that one slice (L2-resident) for its next-best element.  Exact for any data.
+// The repeated token is skipped (V11:279-280); a finished hypothesis offers exactly one candidate, <eos> at +0
+// (V11:291-294) — their −1e5 siblings can never be selected when V − 1 >= K, which every accepted V satisfies.
+// Instruction budget ≈ 6 per logit (ex2, max, compare) so the kernel is bound by the one read of the logits.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kFastMinV = 512;
+constexpr float kLog2e = 1.4426950408889634f;
 
-struct Top3 {
-    float v0, v1, v2;
-    int i0, i1, i2;
-    __device__ __forceinline__ void init() { v0 = v1 = v2 = -INFINITY; i0 = i1 = i2 = 0x7fffffff; }
-    __device__ __forceinline__ void push(float c, int ci) {
-        if (!cand_better(c, ci, v2, i2)) return;
-        if (cand_better(c, ci, v0, i0)) { v2 = v1; i2 = i1; v1 = v0; i1 = i0; v0 = c; i0 = ci; }
-        else if (cand_better(c, ci, v1, i1)) { v2 = v1; i2 = i1; v1 = c; i1 = ci; }
-        else { v2 = c; i2 = ci; }
+// best element of thread `tid`'s slice of `row` that is strictly worse than (pv, pi) in the canonical order
+__device__ __forceinline__ void slice_next_best(const float* __restrict__ row, int V, int tid, bool vec4, int skip, float pv,
+                                                int pi, float& bv, int& bi) {
+    bv = -INFINITY;
+    bi = 0x7fffffff;
+    if (vec4) {
+        for (int v0 = tid * 4; v0 < V; v0 += 1024) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int v = v0 + j;
+                if (v < V) {
+                    const float x = row[v];
+                    if (v != skip && cand_better(pv, pi, x, v) && cand_better(x, v, bv, bi)) { bv = x; bi = v; }
+                }
+            }
+        }
+    } else {
+        for (int v = tid; v < V; v += 256) {
+            const float x = row[v];
+            if (v != skip && cand_better(pv, pi, x, v) && cand_better(x, v, bv, bi)) { bv = x; bi = v; }
+        }
     }
-    __device__ __forceinline__ void pop() { v0 = v1; i0 = i1; v1 = v2; i1 = i2; v2 = -INFINITY; i2 = 0x7fffffff; }
-    __device__ __forceinline__ bool empty() const { return i0 == 0x7fffffff; }
-};
+}
 
 template <int KMAX>
 __global__ void __launch_bounds__(256)
@@ -168,125 +181,171 @@ beam_select_fast_kernel(const float* __restrict__ logits, int64_t ld, int subtra
     if (done && *done) return;
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    __shared__ float pool_v[KMAX * KMAX];
-    __shared__ int pool_i[KMAX * KMAX];
-    __shared__ float nll_s[KMAX];
+    __shared__ float best_v[KMAX][256];   // best remaining element of slice (row, thread): raw logit, later the score
+    __shared__ int best_i[KMAX][256];     // its token id (0x7fffffff: slice exhausted)
+    __shared__ float red_m[KMAX][8], red_s[KMAX][8];
+    __shared__ float nll_s[KMAX], lse_s[KMAX];
     __shared__ int cur_s[KMAX];
-    __shared__ float red_a[8], red_b[8];
+    __shared__ float red_a[8];
     __shared__ int red_i[8], red_t[8];
-    __shared__ float bc_f[2];
-    __shared__ int bc_i[2];
+    __shared__ int win_t, win_k, win_tok;
+    __shared__ float win_v;
 
     const int Kin = step == 0 ? 1 : K;
+    const bool vec4 = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);  // thread owns 4 consecutive tokens
     if (tid < Kin) {
         nll_s[tid] = step == 0 ? 0.f : nll[(int64_t)b * K + tid];
         cur_s[tid] = step == 0 ? -1 : (int)prev_tokens[(int64_t)b * K + tid];
     }
-    for (int i = tid; i < KMAX * KMAX; i += blockDim.x) { pool_v[i] = -INFINITY; pool_i[i] = 0x7fffffff; }
     __syncthreads();
 
+    // ---- single pass over the sentence's rows
     for (int k = 0; k < Kin; ++k) {
-        const float base = nll_s[k];
         const int cur = cur_s[k];
-        if (step > 0 && cur == kEOS) {  // finished hypothesis: single candidate <eos> at +0
-            if (tid == 0) { pool_v[k * KMAX] = base + 0.f; pool_i[k * KMAX] = k * V + kEOS; }
+        if (step > 0 && cur == kEOS) {  // finished hypothesis: the only candidate is <eos> at +0, parked in slice 0
+            best_v[k][tid] = tid == 0 ? 0.f : -INFINITY;
+            best_i[k][tid] = tid == 0 ? kEOS : 0x7fffffff;
+            if (lane == 0) { red_m[k][wid] = 0.f; red_s[k][wid] = wid == 0 ? 1.f : 0.f; }  // lse = 0 ⇒ score = nll_k + 0
             continue;
         }
         const float* row = logits + (int64_t)(b * Kin + k) * ld;
         const int skip = (avoid_double && step > 0) ? cur : -1;
-        // ---- single pass: online log-sum-exp + private top-3
-        Top3 top;
-        top.init();
-        float m = -INFINITY, s = 0.f;
-        int n_seen = 0;
-        for (int v = tid; v < V; v += 256) {
-            const float x = row[v];
-            if (x > m) { s = s * __expf(m - x) + 1.f; m = x; }
-            else s += __expf(x - m);
-            if (v != skip) { top.push(x, v); ++n_seen; }
-        }
-        // ---- block log-sum-exp (the skipped token still belongs to the softmax denominator)
-        float bm = warp_max(m);
-        float bs = warp_sum(m == -INFINITY ? 0.f : s * __expf(m - bm));
-        if (lane == 0) { red_a[wid] = bm; red_b[wid] = bs; }
-        __syncthreads();
-        if (tid == 0) {
-            float fm = red_a[0];
-            for (int w = 1; w < 8; ++w) fm = fmaxf(fm, red_a[w]);
-            float fs = 0.f;
-            for (int w = 0; w < 8; ++w) fs += red_b[w] * __expf(red_a[w] - fm);
-            bc_f[0] = subtract_lse ? fm + logf(fs) : 0.f;
-        }
-        __syncthreads();
-        const float lse = bc_f[0];
-        // ---- pop the row's K best
-        for (int round = 0; round < K; ++round) {
-            float bv = top.v0;
-            int bi = top.i0, bt = tid;
+        float m = -INFINITY, s = 0.f, bv = -INFINITY;
+        int bi = 0x7fffffff;
+        if (vec4) {
+            const int v_full = V & ~3;  // float4 groups entirely below V
+            for (int v0 = tid * 4; v0 < V; v0 += 2048) {
+                const int v1 = v0 + 1024;
+                float x[8];
+                const float4 a = *reinterpret_cast<const float4*>(row + v0);  // rows are padded to a multiple of 4
+                const float4 c = v1 < V ? *reinterpret_cast<const float4*>(row + v1) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+                x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = c.x; x[5] = c.y; x[6] = c.z; x[7] = c.w;
+                if (v0 >= v_full) {  // ragged tail group: mask the padding
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                const int ot = __shfl_xor_sync(0xffffffffu, bt, o);
-                if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; bt = ot; }
-            }
-            if (lane == 0) { red_a[wid] = bv; red_i[wid] = bi; red_t[wid] = bt; }
-            __syncthreads();
-            if (tid == 0) {
-                float fv = red_a[0];
-                int fi = red_i[0], ft = red_t[0];
-                for (int w = 1; w < 8; ++w)
-                    if (cand_better(red_a[w], red_i[w], fv, fi)) { fv = red_a[w]; fi = red_i[w]; ft = red_t[w]; }
-                bc_i[0] = ft;
-                if (fi != 0x7fffffff) {
-                    const float lp = fv - lse;
-                    pool_v[k * KMAX + round] = step == 0 ? lp : base + lp;
-                    pool_i[k * KMAX + round] = k * V + fi;
+                    for (int j = 0; j < 4; ++j) if (v0 + j >= V) x[j] = -INFINITY;
+                }
+                if (v1 < V && v1 >= v_full) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (v1 + j >= V) x[4 + j] = -INFINITY;
+                }
+                float cm = x[0];
+#pragma unroll
+                for (int j = 1; j < 8; ++j) cm = fmaxf(cm, x[j]);
+                if (cm > m) { s *= exp2f((m - cm) * kLog2e); m = cm; }
+                const float m2 = m * kLog2e;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s += exp2f(fmaf(x[j], kLog2e, -m2));
+                if (cm >= bv) {  // rare after the first groups: someone may beat the slice's best
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int v = (j < 4 ? v0 : v1 - 4) + j;
+                        if (x[j] != -INFINITY && v != skip && cand_better(x[j], v, bv, bi)) { bv = x[j]; bi = v; }
+                    }
                 }
             }
-            __syncthreads();
-            if (tid == bc_i[0] && !top.empty()) {
-                const float pv = top.v0;
-                const int pi = top.i0;
-                top.pop();
-                if (top.empty() && n_seen > 3) {  // refill: next best of my slice strictly after (pv, pi)
-                    for (int v = tid; v < V; v += 256) {
-                        const float x = row[v];
-                        if (v != skip && cand_better(pv, pi, x, v)) top.push(x, v);
+        } else {
+            for (int v0 = tid; v0 < V; v0 += 2048) {
+                float x[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = v0 + j * 256 < V ? row[v0 + j * 256] : -INFINITY;
+                float cm = x[0];
+#pragma unroll
+                for (int j = 1; j < 8; ++j) cm = fmaxf(cm, x[j]);
+                if (cm > m) { s *= exp2f((m - cm) * kLog2e); m = cm; }
+                const float m2 = m * kLog2e;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s += exp2f(fmaf(x[j], kLog2e, -m2));
+                if (cm >= bv) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int v = v0 + j * 256;
+                        if (x[j] != -INFINITY && v != skip && cand_better(x[j], v, bv, bi)) { bv = x[j]; bi = v; }
                     }
                 }
             }
         }
+        best_v[k][tid] = bv;
+        best_i[k][tid] = bi;
+        // warp-level (max, Σexp); the skipped token still belongs to the softmax denominator
+        const float wm = warp_max(m);
+        const float ws = warp_sum(m == -INFINITY ? 0.f : s * exp2f((m - wm) * kLog2e));
+        if (lane == 0) { red_m[k][wid] = wm; red_s[k][wid] = ws; }
     }
     __syncthreads();
-    // ---- merge the Kin·K row candidates: warp 0, K rounds
-    if (wid == 0) {
-        int n_eos = 0;
-        for (int round = 0; round < K; ++round) {
-            float bv = -INFINITY;
-            int bi = 0x7fffffff, bs = -1;
-            for (int j = lane; j < KMAX * KMAX; j += 32)
-                if (cand_better(pool_v[j], pool_i[j], bv, bi)) { bv = pool_v[j]; bi = pool_i[j]; bs = j; }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                const int os = __shfl_xor_sync(0xffffffffu, bs, o);
-                if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; bs = os; }
-            }
-            if (lane == 0) {
-                const int tok = bi % V, par = bi / V;
-                nll[(int64_t)b * K + round] = bv;
-                tokens_out[(int64_t)b * K + round] = tok;
-                parents_out[(int64_t)b * K + round] = par;
-                n_eos += (tok == kEOS);
-                pool_v[bs] = -INFINITY;
-                pool_i[bs] = 0x7fffffff;
-            }
-            __syncwarp();
-        }
-        if (lane == 0 && fin_counter) atomicAdd(fin_counter, n_eos);
+    if (tid < Kin) {
+        float fm = red_m[tid][0];
+        for (int w = 1; w < 8; ++w) fm = fmaxf(fm, red_m[tid][w]);
+        float fs = 0.f;
+        for (int w = 0; w < 8; ++w) fs += red_s[tid][w] * exp2f((red_m[tid][w] - fm) * kLog2e);
+        const bool fin = step > 0 && cur_s[tid] == kEOS;
+        lse_s[tid] = (subtract_lse && !fin) ? fm + logf(fs) : 0.f;
     }
+    __syncthreads();
+    // ---- raw logits → scores; every thread caches the head of its K slices
+    float hv = -INFINITY;
+    int hi = 0x7fffffff;  // flat index k·V + token
+    for (int k = 0; k < Kin; ++k) {
+        const int ti = best_i[k][tid];
+        if (ti != 0x7fffffff) {
+            const float lp = best_v[k][tid] - lse_s[k];
+            const float sc = step == 0 ? lp : nll_s[k] + lp;  // V11:297
+            best_v[k][tid] = sc;
+            if (cand_better(sc, k * V + ti, hv, hi)) { hv = sc; hi = k * V + ti; }
+        }
+    }
+    // ---- K rounds: block arg-max, then only the winner's owner refills that one slice
+    int n_eos = 0;
+    for (int round = 0; round < K; ++round) {
+        float bv = hv;
+        int bi = hi, bt = tid;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            const int ot = __shfl_xor_sync(0xffffffffu, bt, o);
+            if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; bt = ot; }
+        }
+        if (lane == 0) { red_a[wid] = bv; red_i[wid] = bi; red_t[wid] = bt; }
+        __syncthreads();
+        if (tid == 0) {
+            float fv = red_a[0];
+            int fi = red_i[0], ft = red_t[0];
+            for (int w = 1; w < 8; ++w)
+                if (cand_better(red_a[w], red_i[w], fv, fi)) { fv = red_a[w]; fi = red_i[w]; ft = red_t[w]; }
+            const int par = fi / V, tok = fi - par * V;
+            win_t = ft; win_k = par; win_tok = tok; win_v = fv;
+            nll[(int64_t)b * K + round] = fv;
+            tokens_out[(int64_t)b * K + round] = tok;
+            parents_out[(int64_t)b * K + round] = par;
+            n_eos += (tok == kEOS);
+        }
+        __syncthreads();
+        if (tid == win_t) {
+            const int k = win_k;
+            const int cur = cur_s[k];
+            float nv = -INFINITY;
+            int ni = 0x7fffffff;
+            if (!(step > 0 && cur == kEOS)) {
+                const float* row = logits + (int64_t)(b * Kin + k) * ld;
+                const int skip = (avoid_double && step > 0) ? cur : -1;
+                // the popped element's RAW logit is needed as the bound; recover it from the row itself
+                slice_next_best(row, V, tid, vec4, skip, row[win_tok], win_tok, nv, ni);
+                if (ni != 0x7fffffff) {
+                    const float lp = nv - lse_s[k];
+                    nv = step == 0 ? lp : nll_s[k] + lp;
+                }
+            }
+            best_v[k][tid] = nv;
+            best_i[k][tid] = ni;
+            hv = -INFINITY;
+            hi = 0x7fffffff;
+            for (int kk = 0; kk < Kin; ++kk) {
+                const int ti = best_i[kk][tid];
+                if (ti != 0x7fffffff && cand_better(best_v[kk][tid], kk * V + ti, hv, hi)) { hv = best_v[kk][tid]; hi = kk * V + ti; }
+            }
+        }
+    }
+    if (tid == 0 && fin_counter) atomicAdd(fin_counter, n_eos);
 }
 
 // Row gather by parent + early-stop bookkeeping.
