@@ -201,7 +201,8 @@ int vag_attn_keys_f32(const vag_decoder_weights* w, const float* ctx, int B, int
                       size_t workspace_bytes, vag_stream_t stream);
 
 /* h0 = tanh(decoderini(split·ctx_vec + (1-split)·mean_t ctx))  (V11:118,201; V2:85,142).
- * workspace: B·C floats. */
+ * workspace: vag_decoder_init_workspace_bytes(); B·C floats suffice for the FP32 FFMA path. */
+size_t vag_decoder_init_workspace_bytes(int B, int C, int H);
 int vag_decoder_init_f32(const vag_decoder_weights* w, const float* ctx_vec, const float* ctx, const float* mask,
                          float split, int B, int T, float* h0, void* workspace, size_t workspace_bytes,
                          vag_stream_t stream);

@@ -68,6 +68,7 @@ SIGNATURES = {
     "vag_attn_keys_f32": (I, [P, P, I, I, P, P, SZ, P]),
     "vag_linear_tc_workspace_bytes": (SZ, [I, I, I]),
     "vag_linear_tc_f32": (I, [P, I64, P, I64, P, I64, P, I, I, I, I, P, SZ, P]),
+    "vag_decoder_init_workspace_bytes": (SZ, [I, I, I]),
     "vag_decoder_init_f32": (I, [P, P, P, P, F, I, I, P, P, SZ, P]),
     "vag_decoder_step_workspace_bytes": (SZ, [I, I, I, I, I64]),
     "vag_decoder_step_f32": (I, [P, P, P, P, P, P, I, I, I, P, P, I, P, P, SZ, P]),

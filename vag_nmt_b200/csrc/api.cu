@@ -38,6 +38,7 @@ size_t linear_tc_scratch_bytes(int64_t rows, int64_t K, int64_t N);
 bool linear_tc_eligible(const float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, int rows, int K, int N);
 
 // VAG_GEMM=simt forces the FP32 FFMA path everywhere (A/B runs); default = tcgen05 3xTF32 where eligible.
+bool tc_enabled();
 bool tc_enabled() {
     const char* e = getenv("VAG_GEMM");
     return !(e && strcmp(e, "simt") == 0);

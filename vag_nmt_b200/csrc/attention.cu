@@ -172,6 +172,185 @@ attention_kernel(float* __restrict__ c_out, int64_t ld_c, float* __restrict__ al
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Tuned variant for C % 4 == 0 (every real configuration): rows-per-CTA is a template parameter so that the
+// accumulator arrays are exactly as large as the beam, a warp loads a whole key row (up to 1024 channels) with
+// independent 128-bit loads BEFORE the SFU-heavy row loop (memory-level parallelism), and the context phase
+// streams ctx with four positions in flight.  MLP-mode cost is 2 SFU ops per (row, position, channel).
+// ---------------------------------------------------------------------------------------------------------
+template <int MODE, int RCAP>
+__global__ void __launch_bounds__(256, RCAP <= 12 ? 3 : 2)
+attention_tuned_kernel(float* __restrict__ c_out, int64_t ld_c, float* __restrict__ alpha_out, const float* __restrict__ q,
+                       int64_t ld_q, const float* __restrict__ keys, const float* __restrict__ ctx,
+                       const float* __restrict__ v, const float* __restrict__ mask, int rows, int rows_per_sent, int T, int C) {
+    extern __shared__ __align__(16) float smem[];
+    const int b = blockIdx.x;
+    const int r_base = blockIdx.y * RCAP;
+    const int R = min(RCAP, rows_per_sent - r_base);
+    const int row0 = b * rows_per_sent + r_base;
+    if (row0 >= rows) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int NW = 8;
+    float* q_s = smem;                    // [RCAP][C]
+    float* v_s = q_s + (size_t)RCAP * C;  // [C]
+    float* sc_s = v_s + C;                // [RCAP][T]
+    const float* key_b = keys + (int64_t)b * T * C;
+    const float* ctx_b = ctx + (int64_t)b * T * C;
+    const float* mask_b = mask ? mask + (int64_t)b * T : nullptr;
+
+    for (int i = tid * 4; i < R * C; i += 1024) {
+        const int r = i / C, c = i - r * C;
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row0 + r < rows) val = *reinterpret_cast<const float4*>(q + (int64_t)(row0 + r) * ld_q + c);
+        *reinterpret_cast<float4*>(q_s + r * C + c) = val;
+    }
+    if (MODE == VAG_ATTN_MLP)
+        for (int i = tid; i < C; i += 256) v_s[i] = v[i];
+    __syncthreads();
+
+    // ---- phase 1: scores, one warp per source position
+    for (int t = wid; t < T; t += NW) {
+        const bool live = mask_b ? (mask_b[t] != 0.f) : true;
+        float part[RCAP];
+#pragma unroll
+        for (int r = 0; r < RCAP; ++r) part[r] = 0.f;
+        if (live) {
+            const float* kr = key_b + (int64_t)t * C;
+            for (int cb = 0; cb < C; cb += 1024) {
+                float4 kv[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = cb + j * 128 + lane * 4;
+                    kv[j] = c < C ? *reinterpret_cast<const float4*>(kr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int r = 0; r < RCAP; ++r) {
+                    if (r < R) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int c = cb + j * 128 + lane * 4;
+                            if (c < C) {
+                                const float4 qv = *reinterpret_cast<const float4*>(q_s + r * C + c);
+                                if (MODE == VAG_ATTN_MLP) {
+                                    const float4 vv = *reinterpret_cast<const float4*>(v_s + c);
+                                    part[r] = fmaf(vv.x, tanh_abs(qv.x + kv[j].x), part[r]);
+                                    part[r] = fmaf(vv.y, tanh_abs(qv.y + kv[j].y), part[r]);
+                                    part[r] = fmaf(vv.z, tanh_abs(qv.z + kv[j].z), part[r]);
+                                    part[r] = fmaf(vv.w, tanh_abs(qv.w + kv[j].w), part[r]);
+                                } else {
+                                    part[r] = fmaf(qv.x, kv[j].x, part[r]);
+                                    part[r] = fmaf(qv.y, kv[j].y, part[r]);
+                                    part[r] = fmaf(qv.z, kv[j].z, part[r]);
+                                    part[r] = fmaf(qv.w, kv[j].w, part[r]);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RCAP; ++r) {
+            if (r < R) {
+                const float s = warp_sum(part[r]);
+                if (lane == 0) sc_s[r * T + t] = live ? s : -INFINITY;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: masked softmax over T, one warp per row
+    for (int r = wid; r < R; r += NW) {
+        float* s = sc_s + r * T;
+        float m = -INFINITY;
+        for (int t = lane; t < T; t += 32) m = fmaxf(m, s[t]);
+        m = warp_max(m);
+        float sum = 0.f;
+        for (int t = lane; t < T; t += 32) {
+            const float e = expf(s[t] - m);
+            s[t] = e;
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        for (int t = lane; t < T; t += 32) {
+            const float a = s[t] / sum;
+            s[t] = a;
+            if (alpha_out && row0 + r < rows) alpha_out[(int64_t)(row0 + r) * T + t] = a;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 3: context, each thread owns 4 channels and keeps 4 positions in flight
+    for (int c = tid * 4; c < C; c += 1024) {
+        float4 acc[RCAP];
+#pragma unroll
+        for (int r = 0; r < RCAP; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int t0 = 0; t0 < T; t0 += 4) {
+            float4 x[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int t = t0 + u;
+                const bool on = t < T && !(mask_b && mask_b[t] == 0.f);  // α is exactly 0 at masked positions
+                x[u] = on ? *reinterpret_cast<const float4*>(ctx_b + (int64_t)t * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int t = t0 + u;
+                if (t < T) {
+#pragma unroll
+                    for (int r = 0; r < RCAP; ++r) {
+                        if (r < R) {
+                            const float a = sc_s[r * T + t];
+                            acc[r].x = fmaf(a, x[u].x, acc[r].x);
+                            acc[r].y = fmaf(a, x[u].y, acc[r].y);
+                            acc[r].z = fmaf(a, x[u].z, acc[r].z);
+                            acc[r].w = fmaf(a, x[u].w, acc[r].w);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RCAP; ++r)
+            if (r < R && row0 + r < rows) *reinterpret_cast<float4*>(c_out + (int64_t)(row0 + r) * ld_c + c) = acc[r];
+    }
+}
+
+template <int MODE, int RCAP>
+static int launch_attention_tuned(float* c_out, int64_t ld_c, float* alpha, const float* q, int64_t ld_q, const float* keys,
+                                  const float* ctx, const float* v, const float* mask, int rows, int rows_per_sent, int T, int C,
+                                  cudaStream_t st) {
+    const size_t smem = ((size_t)RCAP * C + C + (size_t)RCAP * T) * sizeof(float);
+    if (smem > 227 * 1024) {
+        set_error("vag_attention_f32: C=%d T=%d needs %zu B of shared memory", C, T, smem);
+        return VAG_ERR_UNSUPPORTED;
+    }
+    static size_t configured = 0;
+    if (smem > configured) {
+        VAG_CUDA(cudaFuncSetAttribute(attention_tuned_kernel<MODE, RCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    dim3 grid(rows / rows_per_sent, ceil_div(rows_per_sent, RCAP));
+    attention_tuned_kernel<MODE, RCAP><<<grid, 256, smem, st>>>(c_out, ld_c, alpha, q, ld_q, keys, ctx, v, mask, rows,
+                                                                 rows_per_sent, T, C);
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
+template <int MODE>
+static int dispatch_attention_tuned(float* c_out, int64_t ld_c, float* alpha, const float* q, int64_t ld_q, const float* keys,
+                                    const float* ctx, const float* v, const float* mask, int rows, int rows_per_sent, int T,
+                                    int C, cudaStream_t st) {
+#define VAG_ATT(RC) return launch_attention_tuned<MODE, RC>(c_out, ld_c, alpha, q, ld_q, keys, ctx, v, mask, rows, rows_per_sent, T, C, st)
+    if (rows_per_sent == 1) VAG_ATT(1);
+    if (rows_per_sent <= 4) VAG_ATT(4);
+    if (rows_per_sent <= 8) VAG_ATT(8);
+    if (rows_per_sent <= 12) VAG_ATT(12);
+    VAG_ATT(16);
+#undef VAG_ATT
+}
+
 }  // namespace vag
 
 using namespace vag;
@@ -194,6 +373,13 @@ extern "C" int vag_attention_f32(float* c_out, int64_t ld_c, float* alpha, const
     }
     auto al = [](const void* p) { return ((uintptr_t)p % 16) == 0; };
     const bool vec = (C % 4 == 0) && (ld_c % 4 == 0) && al(keys) && al(ctx) && al(c_out);
+    if (vec && (ld_q % 4 == 0) && al(q)) {
+        if (mode == VAG_ATTN_MLP)
+            return dispatch_attention_tuned<VAG_ATTN_MLP>(c_out, ld_c, alpha, q, ld_q, keys, ctx, v, mask, rows, rows_per_sent, T, C,
+                                                          (cudaStream_t)stream);
+        return dispatch_attention_tuned<VAG_ATTN_DOT>(c_out, ld_c, alpha, q, ld_q, keys, ctx, v, mask, rows, rows_per_sent, T, C,
+                                                      (cudaStream_t)stream);
+    }
     dim3 grid(B, ceil_div(rows_per_sent, kMaxRowsPerCta));
     cudaStream_t st = (cudaStream_t)stream;
 #define VAG_ATTN_LAUNCH(MODE, VEC)                                                                                  \

@@ -2,25 +2,12 @@
 // decoder step, beam / greedy decoding.  Everything is enqueued on the caller's stream; no allocation, no
 // host synchronisation.
 #include "common.cuh"
+#include "gemm_ctx.cuh"
 #include <algorithm>
 #include <vector>
 
 namespace vag {
 
-int linear_dispatch(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias,
-                    int rows, int K, int N, int flags, cudaStream_t st, void* scratch, size_t scratch_bytes);
-size_t gemm_scratch_bytes(int64_t rows, int64_t K, int64_t N);
-
-// stream + scratch region (operand hi/lo splits of the tensor-core path) shared by all contractions of a composite
-struct Gemm {
-    cudaStream_t st;
-    void* scratch;
-    size_t bytes;
-    int operator()(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, int rows,
-                   int K, int N, int flags) const {
-        return linear_dispatch(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags, st, scratch, bytes);
-    }
-};
 static inline size_t max_sz(size_t a, size_t b) { return a > b ? a : b; }
 int row_lse(float* lse_out, const float* logits, int64_t ld, int rows, int64_t V, cudaStream_t st);
 int beam_select(const float* logits, int64_t ld, const float* lse, const int64_t* prev_tokens, float* nll,
@@ -56,8 +43,8 @@ __global__ void fill_i64_kernel(int64_t* p, int64_t v, int n) {
 
 struct EncoderWs {
     float *x, *gi[2], *gh[2], *h[2];
-    void* scratch;
-    size_t scratch_bytes;
+    void *wreg, *areg;
+    size_t wbytes, abytes;
 };
 template <typename A>
 static void encoder_layout(A& a, int B, int T, int E, int H, EncoderWs* ws) {
@@ -68,11 +55,13 @@ static void encoder_layout(A& a, int B, int T, int E, int H, EncoderWs* ws) {
     float* gh1 = (float*)a.template take<float>((size_t)B * 3 * H);
     float* h0 = (float*)a.template take<float>((size_t)B * H);
     float* h1 = (float*)a.template take<float>((size_t)B * H);
-    const size_t sb = max_sz(gemm_scratch_bytes((int64_t)T * B, E, 3 * H), gemm_scratch_bytes(B, H, 3 * H));
-    void* sc = a.template take<char>(sb);
+    const size_t wb = 2 * (GemmCtx::split_bytes(3 * H, E) + GemmCtx::split_bytes(3 * H, H)) + 4096;
+    const size_t ab = max_sz(GemmCtx::split_bytes((int64_t)T * B, E), GemmCtx::split_bytes(B, H)) + 4096;
+    void* wr = a.template take<char>(wb);
+    void* ar = a.template take<char>(ab);
     if (ws) {
         ws->x = x; ws->gi[0] = gi0; ws->gi[1] = gi1; ws->gh[0] = gh0; ws->gh[1] = gh1; ws->h[0] = h0; ws->h[1] = h1;
-        ws->scratch = sc; ws->scratch_bytes = sb;
+        ws->wreg = wr; ws->wbytes = wb; ws->areg = ar; ws->abytes = ab;
     }
 }
 struct SizerAdapter {
@@ -128,9 +117,9 @@ extern "C" int vag_encoder_fwd_f32(const vag_encoder_weights* w, const int64_t* 
         while (n < B && lengths_host[n] > t) ++n;
         n_act[t] = n;
     }
-    const Gemm gemm{st, ws.scratch, ws.scratch_bytes};
+    GemmCtx gemm(st, ws.wreg, ws.wbytes, ws.areg, ws.abytes);
     for (int d = 0; d < 2; ++d) {
-        VAG_TRY(gemm(ws.gi[d], 3 * H, ws.x, E, w->w_ih[d], E, w->b_ih[d], T * B, E, 3 * H, 0));
+        VAG_TRY(gemm.linear(ws.gi[d], 3 * H, ws.x, E, w->w_ih[d], E, w->b_ih[d], T * B, E, 3 * H, 0));
         VAG_CUDA(cudaMemsetAsync(ws.h[d], 0, (size_t)B * H * sizeof(float), st));
     }
     // the two directions are independent chains; interleave them so neighbouring launches can overlap their tails
@@ -139,7 +128,8 @@ extern "C" int vag_encoder_fwd_f32(const vag_encoder_weights* w, const int64_t* 
             const int t = d == 0 ? s : T - 1 - s;
             const int n = n_act[t];
             if (n == 0) continue;
-            VAG_TRY(gemm(ws.gh[d], 3 * H, ws.h[d], H, w->w_hh[d], H, w->b_hh[d], n, H, 3 * H, 0));
+            gemm.new_step();  // h changed: its split is stale
+            VAG_TRY(gemm.linear(ws.gh[d], 3 * H, ws.h[d], H, w->w_hh[d], H, w->b_hh[d], n, H, 3 * H, 0));
             VAG_TRY(vag_gru_gates_f32(ws.h[d], H, ctx_out + (int64_t)t * 2 * H + d * H, (int64_t)T * 2 * H,
                                       ws.gi[d] + (int64_t)t * B * 3 * H, 3 * H, ws.gh[d], 3 * H, ws.h[d], H, n, H, stream));
         }
@@ -148,12 +138,18 @@ extern "C" int vag_encoder_fwd_f32(const vag_encoder_weights* w, const int64_t* 
 }
 
 // ------------------------------------------------------------------ visual-attention pooling
+static size_t vse_wbytes(int I, int C, int S) {
+    return GemmCtx::split_bytes(S, I) + GemmCtx::split_bytes(C, S) + GemmCtx::split_bytes(C, C) + GemmCtx::split_bytes(S, C) + 4096;
+}
+static size_t vse_abytes(int B, int T, int I, int C, int S) {
+    return GemmCtx::split_bytes(B, I) + GemmCtx::split_bytes(B, S) + GemmCtx::split_bytes((int64_t)B * T, C) + GemmCtx::split_bytes(B, C) + 4096;
+}
 extern "C" size_t vag_vse_workspace_bytes(int B, int T, int I, int C, int S) {
     ArenaSizer s;
     s.take<float>((size_t)B * T * C);
     s.take<float>((size_t)B * C);
-    s.take<char>(max_sz(max_sz(gemm_scratch_bytes(B, I, S), gemm_scratch_bytes(B, S, C)),
-                        max_sz(gemm_scratch_bytes((int64_t)B * T, C, C), gemm_scratch_bytes(B, C, S))));
+    s.take<char>(vse_wbytes(I, C, S));
+    s.take<char>(vse_abytes(B, T, I, C, S));
     return s.total();
 }
 
@@ -168,33 +164,44 @@ extern "C" int vag_vse_pool_fwd_f32(const vag_vse_weights* w, const float* im, c
     Arena ar(workspace, workspace_bytes);
     float* pk = ar.take<float>((size_t)B * T * C);
     float* iq = ar.take<float>((size_t)B * C);
-    const size_t sb = max_sz(max_sz(gemm_scratch_bytes(B, I, S), gemm_scratch_bytes(B, S, C)),
-                             max_sz(gemm_scratch_bytes((int64_t)B * T, C, C), gemm_scratch_bytes(B, C, S)));
-    void* sc = ar.take<char>(sb);
+    const size_t wb = vse_wbytes(I, C, S), ab = vse_abytes(B, T, I, C, S);
+    void* wr = ar.take<char>(wb);
+    void* areg = ar.take<char>(ab);
     if (ar.overflow) {
         set_error("vag_vse_pool_fwd_f32: workspace %zu B too small", workspace_bytes);
         return VAG_ERR_WORKSPACE;
     }
-    const Gemm gemm{st, sc, sb};
+    GemmCtx gemm(st, wr, wb, areg, ab);
     const int act = w->activation ? VAG_LIN_TANH : 0;
-    VAG_TRY(gemm(im_emb, S, im, I, w->im_w, I, w->im_b, B, I, S, act));            // VSE_Imagine_Enc.py:123-127
+    VAG_TRY(gemm.linear(im_emb, S, im, I, w->im_w, I, w->im_b, B, I, S, act));            // VSE_Imagine_Enc.py:123-127
     VAG_TRY(vag_l2norm_rows_f32(im_emb, S, B, S, stream));                                        // :132
-    VAG_TRY(gemm(iq, C, im_emb, S, w->emb2ctx_w, S, nullptr, B, S, C, 0));         // :58
-    VAG_TRY(gemm(pk, C, ctx, C, w->ctx2ctx_w, C, nullptr, B * T, C, C, 0));        // :57
+    VAG_TRY(gemm.linear(iq, C, im_emb, S, w->emb2ctx_w, S, nullptr, B, S, C, 0));         // :58
+    VAG_TRY(gemm.linear(pk, C, ctx, C, w->ctx2ctx_w, C, nullptr, B * T, C, C, 0));        // :57
     VAG_TRY(vag_attention_f32(ctx_vec, C, beta, iq, C, pk, ctx, w->mlp_w, mask, B, 1, T, C, w->method, stream));  // :135-137
-    VAG_TRY(gemm(txt_emb, S, ctx_vec, C, w->txt_w, C, w->txt_b, B, C, S, act));    // :138-140
+    VAG_TRY(gemm.linear(txt_emb, S, ctx_vec, C, w->txt_w, C, w->txt_b, B, C, S, act));    // :138-140
     VAG_TRY(vag_l2norm_rows_f32(txt_emb, S, B, S, stream));                                       // :145
     return VAG_OK;
 }
 
 // ------------------------------------------------------------------ decoder
-extern "C" size_t vag_attn_keys_workspace_bytes(int B, int T, int C) { return gemm_scratch_bytes((int64_t)B * T, C, C) + 256; }
+extern "C" size_t vag_attn_keys_workspace_bytes(int B, int T, int C) {
+    return GemmCtx::split_bytes(C, C) + GemmCtx::split_bytes((int64_t)B * T, C) + 8192;
+}
 
 extern "C" int vag_attn_keys_f32(const vag_decoder_weights* w, const float* ctx, int B, int T, float* keys, void* workspace,
                                  size_t workspace_bytes, vag_stream_t stream) {
     VAG_REQUIRE(w && ctx && keys && B > 0 && T > 0, "vag_attn_keys_f32: bad argument");
-    return linear_dispatch(keys, w->C, ctx, w->C, w->attn_e_w, w->C, nullptr, B * T, w->C, w->C, 0, (cudaStream_t)stream,
-                           workspace, workspace_bytes);
+    const size_t wb = GemmCtx::split_bytes(w->C, w->C) + 4096;
+    Arena ar(workspace, workspace_bytes);
+    void* wr = ar.take<char>(wb);
+    const size_t ab = ar.overflow || workspace_bytes < ar.off + 512 ? 0 : workspace_bytes - align_up(ar.off, 256) - 256;
+    void* areg = ab ? ar.take<char>(ab) : nullptr;
+    GemmCtx gemm((cudaStream_t)stream, ar.overflow ? nullptr : wr, wb, ar.overflow ? nullptr : areg, ab);
+    return gemm.linear(keys, w->C, ctx, w->C, w->attn_e_w, w->C, nullptr, B * T, w->C, w->C, 0);
+}
+
+extern "C" size_t vag_decoder_init_workspace_bytes(int B, int C, int H) {
+    return align_up((size_t)B * C * 4, 256) + GemmCtx::split_bytes(H, C) + GemmCtx::split_bytes(B, C) + 16384;
 }
 
 extern "C" int vag_decoder_init_f32(const vag_decoder_weights* w, const float* ctx_vec, const float* ctx, const float* mask,
@@ -209,28 +216,26 @@ extern "C" int vag_decoder_init_f32(const vag_decoder_weights* w, const float* c
         return VAG_ERR_WORKSPACE;
     }
     VAG_TRY(vag_init_mix_f32(z, ctx_vec, ctx, mask, split, B, T, w->C, stream));
-    const size_t sb = gemm_scratch_bytes(B, w->C, w->H);
-    void* sc = ar.take<char>(sb);   // optional: without it the FP32 FFMA kernel runs
-    return linear_dispatch(h0, w->H, z, w->C, w->ini_w, w->C, w->ini_b, B, w->C, w->H, VAG_LIN_TANH, (cudaStream_t)stream,
-                           ar.overflow ? nullptr : sc, ar.overflow ? 0 : sb);
+    const size_t wb = GemmCtx::split_bytes(w->H, w->C) + 4096, ab = GemmCtx::split_bytes(B, w->C) + 4096;
+    void* wr = ar.take<char>(wb);   // optional: without them the FP32 FFMA kernel runs
+    void* areg = ar.take<char>(ab);
+    GemmCtx gemm((cudaStream_t)stream, ar.overflow ? nullptr : wr, wb, ar.overflow ? nullptr : areg, ab);
+    return gemm.linear(h0, w->H, z, w->C, w->ini_w, w->C, w->ini_b, B, w->C, w->H, VAG_LIN_TANH);
 }
 
 namespace vag {
 struct StepWs {
     float *e, *gi, *gh, *h1, *q, *c, *x2, *t;
-    void* scratch;
-    size_t scratch_bytes;
+    void *wreg, *areg;
+    size_t wbytes, abytes;
 };
-static size_t step_scratch_bytes(int rows, int E, int H, int C, int64_t V) {
-    size_t m = gemm_scratch_bytes(rows, E, 3 * H);
-    m = max_sz(m, gemm_scratch_bytes(rows, H, 3 * H));
-    m = max_sz(m, gemm_scratch_bytes(rows, H, C));
-    m = max_sz(m, gemm_scratch_bytes(rows, C, H));
-    m = max_sz(m, gemm_scratch_bytes(rows, H, E));
-    m = max_sz(m, gemm_scratch_bytes(rows, E, E));
-    m = max_sz(m, gemm_scratch_bytes(rows, C, E));
-    m = max_sz(m, gemm_scratch_bytes(rows, E, V));
-    return m;
+static size_t step_wbytes(int E, int H, int C, int64_t V) {
+    return GemmCtx::split_bytes(3 * H, E) + 3 * GemmCtx::split_bytes(3 * H, H) + GemmCtx::split_bytes(C, H) +
+           GemmCtx::split_bytes(H, C) + GemmCtx::split_bytes(E, H + E + C) + GemmCtx::split_bytes(V, E) + 16384;
+}
+static size_t step_abytes(int rows, int E, int H, int C) {
+    return 2 * GemmCtx::split_bytes(rows, E) + 4 * GemmCtx::split_bytes(rows, H) + GemmCtx::split_bytes(rows, C) +
+           GemmCtx::split_bytes(rows, H + E + C) + 16384;
 }
 template <typename A>
 static void step_layout(A& a, int rows, int E, int H, int C, int64_t V, StepWs* ws) {
@@ -242,38 +247,44 @@ static void step_layout(A& a, int rows, int E, int H, int C, int64_t V, StepWs* 
     float* c = (float*)a.template take<float>((size_t)rows * C);
     float* x2 = (float*)a.template take<float>((size_t)rows * H);
     float* t = (float*)a.template take<float>((size_t)rows * E);
-    const size_t sb = step_scratch_bytes(rows, E, H, C, V);
-    void* sc = a.template take<char>(sb);
+    const size_t wb = step_wbytes(E, H, C, V), ab = step_abytes(rows, E, H, C);
+    void* wr = a.template take<char>(wb);
+    void* ar = a.template take<char>(ab);
     if (ws) {
         ws->e = e; ws->gi = gi; ws->gh = gh; ws->h1 = h1; ws->q = q; ws->c = c; ws->x2 = x2; ws->t = t;
-        ws->scratch = sc; ws->scratch_bytes = sb;
+        ws->wreg = wr; ws->wbytes = wb; ws->areg = ar; ws->abytes = ab;
     }
 }
 
 // One conditional-GRU step up to (and including) the vocabulary logits.  NMT_Decoder.py:109-143.
-static int decoder_step_core(const vag_decoder_weights* w, const StepWs& ws, const int64_t* tokens, const float* h_prev,
+static int decoder_step_core(GemmCtx& gemm, const vag_decoder_weights* w, const StepWs& ws, const int64_t* tokens, const float* h_prev,
                              const float* keys, const float* ctx, const float* mask, int rows, int rows_per_sent, int T,
                              float* h_out, float* logits, int64_t ld_logits, float* alpha_out, cudaStream_t st) {
     const int E = w->E, H = w->H, C = w->C;
     const int64_t V = w->V;
     vag_stream_t vs = (vag_stream_t)st;
-    const Gemm gemm{st, ws.scratch, ws.scratch_bytes};
+    gemm.new_step();
     VAG_TRY(vag_embed_rows_f32(ws.e, E, w->emb, E, tokens, rows, V, vs));                                              // :118
-    VAG_TRY(gemm(ws.gi, 3 * H, ws.e, E, w->gru1_w_ih, E, w->gru1_b_ih, rows, E, 3 * H, 0));              // :121
-    VAG_TRY(gemm(ws.gh, 3 * H, h_prev, H, w->gru1_w_hh, H, w->gru1_b_hh, rows, H, 3 * H, 0));
+    VAG_TRY(gemm.linear(ws.gi, 3 * H, ws.e, E, w->gru1_w_ih, E, w->gru1_b_ih, rows, E, 3 * H, 0));              // :121
+    VAG_TRY(gemm.linear(ws.gh, 3 * H, h_prev, H, w->gru1_w_hh, H, w->gru1_b_hh, rows, H, 3 * H, 0));
     VAG_TRY(vag_gru_gates_f32(ws.h1, H, nullptr, 0, ws.gi, 3 * H, ws.gh, 3 * H, h_prev, H, rows, H, vs));
-    VAG_TRY(gemm(ws.q, C, ws.h1, H, w->attn_h_w, H, nullptr, rows, H, C, 0));                            // :47
+    VAG_TRY(gemm.linear(ws.q, C, ws.h1, H, w->attn_h_w, H, nullptr, rows, H, C, 0));                            // :47
     VAG_TRY(vag_attention_f32(ws.c, C, alpha_out, ws.q, C, keys, ctx, w->attn_v, mask, rows, rows_per_sent, T, C,
                               VAG_ATTN_MLP, vs));                                                                       // :124-126
-    VAG_TRY(gemm(ws.x2, H, ws.c, C, w->c2h_w, C, nullptr, rows, C, H, 0));                               // :127
-    VAG_TRY(gemm(ws.gi, 3 * H, ws.x2, H, w->gru2_w_ih, H, w->gru2_b_ih, rows, H, 3 * H, 0));             // :129
-    VAG_TRY(gemm(ws.gh, 3 * H, ws.h1, H, w->gru2_w_hh, H, w->gru2_b_hh, rows, H, 3 * H, 0));
+    VAG_TRY(gemm.linear(ws.x2, H, ws.c, C, w->c2h_w, C, nullptr, rows, C, H, 0));                               // :127
+    VAG_TRY(gemm.linear(ws.gi, 3 * H, ws.x2, H, w->gru2_w_ih, H, w->gru2_b_ih, rows, H, 3 * H, 0));             // :129
+    VAG_TRY(gemm.linear(ws.gh, 3 * H, ws.h1, H, w->gru2_w_hh, H, w->gru2_b_hh, rows, H, 3 * H, 0));
     VAG_TRY(vag_gru_gates_f32(h_out, H, nullptr, 0, ws.gi, 3 * H, ws.gh, 3 * H, ws.h1, H, rows, H, vs));
     // t = tanh((W1 h2 + b1) + (W3 e + b3) + (W2 c + b2)), summed left to right like :137
-    VAG_TRY(gemm(ws.t, E, h_out, H, w->w1_w, H, w->w1_b, rows, H, E, 0));
-    VAG_TRY(gemm(ws.t, E, ws.e, E, w->w3_w, E, w->w3_b, rows, E, E, VAG_LIN_ACCUMULATE));
-    VAG_TRY(gemm(ws.t, E, ws.c, C, w->w2_w, C, w->w2_b, rows, C, E, VAG_LIN_ACCUMULATE | VAG_LIN_TANH));
-    if (logits) VAG_TRY(gemm(logits, ld_logits, ws.t, E, w->out_w, E, w->out_b, rows, E, (int)V, 0));            // :143
+    {
+        const float* const xs[3] = {h_out, ws.e, ws.c};
+        const int64_t lds[3] = {H, E, C};
+        const int Ks[3] = {H, E, C};
+        const float* const wts[3] = {w->w1_w, w->w3_w, w->w2_w};
+        const float* const bs[3] = {w->w1_b, w->w3_b, w->w2_b};
+        VAG_TRY(gemm.linear3(ws.t, E, xs, lds, Ks, wts, lds, bs, rows, E, VAG_LIN_TANH));
+    }
+    if (logits) VAG_TRY(gemm.linear(logits, ld_logits, ws.t, E, w->out_w, E, w->out_b, rows, E, (int)V, 0));            // :143
     return VAG_OK;
 }
 }  // namespace vag
@@ -298,8 +309,9 @@ extern "C" int vag_decoder_step_f32(const vag_decoder_weights* w, const int64_t*
         set_error("vag_decoder_step_f32: workspace %zu B too small", workspace_bytes);
         return VAG_ERR_WORKSPACE;
     }
-    VAG_TRY(decoder_step_core(w, ws, tokens, h_prev, keys, ctx, mask, rows, rows_per_sent, T, h_out, logits_or_logp, w->V, alpha_out,
-                              (cudaStream_t)stream));
+    GemmCtx gemm((cudaStream_t)stream, ws.wreg, ws.wbytes, ws.areg, ws.abytes);
+    VAG_TRY(decoder_step_core(gemm, w, ws, tokens, h_prev, keys, ctx, mask, rows, rows_per_sent, T, h_out, logits_or_logp, w->V,
+                              alpha_out, (cudaStream_t)stream));
     if (want_logp) VAG_TRY(vag_log_softmax_f32(logits_or_logp, logits_or_logp, rows, (int)w->V, stream));
     return VAG_OK;
 }
@@ -366,12 +378,13 @@ extern "C" int vag_beam_decode_f32(const vag_decoder_weights* w, const float* h0
     fill_i64_kernel<<<ceil_div(B, 256), 256, 0, st>>>(ws.sos, 2 /*SOS*/, B);
     VAG_LAUNCH_CHECK();
     const int64_t ldl = (V + 3) / 4 * 4;
+    GemmCtx gemm(st, ws.step.wreg, ws.step.wbytes, ws.step.areg, ws.step.abytes);
     for (int di = 0; di < L; ++di) {
         const int rows = di == 0 ? B : N;
         const int rps = di == 0 ? 1 : K;
         const int64_t* tokens = di == 0 ? ws.sos : ws.tok_hist + (size_t)(di - 1) * N;
         const float* h_prev = di == 0 ? h0 : ws.h_a;
-        VAG_TRY(decoder_step_core(w, ws.step, tokens, h_prev, keys, ctx, mask, rows, rps, T, ws.h_b, ws.logits, ldl, nullptr, st));
+        VAG_TRY(decoder_step_core(gemm, w, ws.step, tokens, h_prev, keys, ctx, mask, rows, rps, T, ws.h_b, ws.logits, ldl, nullptr, st));
         const bool fused_lse = V >= 512;  // the fast selection kernel folds the log-sum-exp into its single pass
         if (!fused_lse) VAG_TRY(row_lse(ws.lse, ws.logits, ldl, rows, V, st));
         VAG_TRY(beam_select(ws.logits, ldl, ws.lse, di == 0 ? nullptr : tokens, ws.nll, ws.tok_hist + (size_t)di * N,
@@ -403,8 +416,9 @@ extern "C" int vag_greedy_decode_f32(const vag_decoder_weights* w, const float* 
     float* h_cur = ws.h_a;
     float* h_nxt = ws.h_b;
     const int64_t ldl = (w->V + 3) / 4 * 4;
+    GemmCtx gemm(st, ws.step.wreg, ws.step.wbytes, ws.step.areg, ws.step.abytes);
     for (int di = 0; di < L; ++di) {
-        VAG_TRY(decoder_step_core(w, ws.step, ws.sos, h_cur, keys, ctx, mask, B, 1, T, h_nxt, ws.logits, ldl, nullptr, st));
+        VAG_TRY(decoder_step_core(gemm, w, ws.step, ws.sos, h_cur, keys, ctx, mask, B, 1, T, h_nxt, ws.logits, ldl, nullptr, st));
         VAG_TRY(row_argmax(ws.logits, ldl, B, w->V, tokens_out + di, L, ws.sos, st));
         std::swap(h_cur, h_nxt);
     }

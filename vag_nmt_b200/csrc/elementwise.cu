@@ -180,6 +180,17 @@ translation_loss_kernel(const float* __restrict__ loss_rows, const int64_t* __re
     }
 }
 
+__global__ void bias_sum3_kernel(float* __restrict__ out, const float* __restrict__ a, const float* __restrict__ b,
+                                 const float* __restrict__ c, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = ((a ? a[i] : 0.f) + (b ? b[i] : 0.f)) + (c ? c[i] : 0.f);
+}
+int bias_sum3(float* out, const float* a, const float* b, const float* c, int n, cudaStream_t st) {
+    bias_sum3_kernel<<<ceil_div(n, 256), 256, 0, st>>>(out, a, b, c, n);
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
 int row_lse(float* lse_out, const float* logits, int64_t ld, int rows, int64_t V, cudaStream_t st) {
     if (rows == 0) return VAG_OK;
     row_lse_kernel<<<rows, 256, 0, st>>>(lse_out, logits, ld, V);

@@ -27,7 +27,7 @@ namespace vag {
 // ------------------------------------------------------------------------------------------ operand split
 // hi = round-to-nearest TF32 of v (low 13 mantissa bits zero), lo = v - hi.  Outputs are compact [rows, K].
 __global__ void __launch_bounds__(256)
-split_tf32_kernel(const float* __restrict__ x, int64_t ldx, int rows, int K, float* __restrict__ hi, float* __restrict__ lo) {
+split_tf32_kernel(const float* __restrict__ x, int64_t ldx, int rows, int K, float* __restrict__ hi, float* __restrict__ lo, int64_t ldo) {
     const int kq = K >> 2;
     const int64_t total = (int64_t)rows * kq;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -39,8 +39,8 @@ split_tf32_kernel(const float* __restrict__ x, int64_t ldx, int rows, int K, flo
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y)); h.y = __uint_as_float(t); l.y = v.y - h.y;
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z)); h.z = __uint_as_float(t); l.z = v.z - h.z;
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w)); h.w = __uint_as_float(t); l.w = v.w - h.w;
-        *reinterpret_cast<float4*>(hi + (int64_t)r * K + c) = h;
-        *reinterpret_cast<float4*>(lo + (int64_t)r * K + c) = l;
+        *reinterpret_cast<float4*>(hi + (int64_t)r * ldo + c) = h;
+        *reinterpret_cast<float4*>(lo + (int64_t)r * ldo + c) = l;
     }
 }
 
@@ -50,7 +50,7 @@ split_tf32_kernel(const float* __restrict__ x, int64_t ldx, int rows, int K, flo
 // accumulator updates.  Valid for |v| < 65504 (activations here are bounded by tanh / GRU gates, weights are O(1));
 // larger magnitudes surface as inf/NaN in the output rather than as silently wrong numbers.
 __global__ void __launch_bounds__(256)
-split_f16_kernel(const float* __restrict__ x, int64_t ldx, int rows, int K, __half* __restrict__ hi, __half* __restrict__ lo) {
+split_f16_kernel(const float* __restrict__ x, int64_t ldx, int rows, int K, __half* __restrict__ hi, __half* __restrict__ lo, int64_t ldo) {
     const int kq = K >> 2;
     const int64_t total = (int64_t)rows * kq;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -63,8 +63,8 @@ split_f16_kernel(const float* __restrict__ x, int64_t ldx, int rows, int K, __ha
             h[j] = __float2half_rn(in[j]);
             l[j] = __float2half_rn((in[j] - __half2float(h[j])) * 2048.0f);
         }
-        *reinterpret_cast<uint2*>(hi + (int64_t)r * K + c) = *reinterpret_cast<uint2*>(h);
-        *reinterpret_cast<uint2*>(lo + (int64_t)r * K + c) = *reinterpret_cast<uint2*>(l);
+        *reinterpret_cast<uint2*>(hi + (int64_t)r * ldo + c) = *reinterpret_cast<uint2*>(h);
+        *reinterpret_cast<uint2*>(lo + (int64_t)r * ldo + c) = *reinterpret_cast<uint2*>(l);
     }
 }
 
@@ -364,6 +364,41 @@ static bool use_f16_split() {
     return !(e && strcmp(e, "tf32x3") == 0);
 }
 
+int tc_elem_bytes() { return use_f16_split() ? 2 : 4; }
+
+// Split x [rows, K] (pitch ldx) into hi / lo planes of pitch ld_out ELEMENTS, starting at column col_off
+// (so several sources can be laid side by side along K for a concatenated contraction).
+int tc_split(const float* x, int64_t ldx, int rows, int K, void* hi, void* lo, int64_t ld_out, int64_t col_off, cudaStream_t st) {
+    const int64_t tot = (int64_t)rows * (K / 4);
+    if (tot == 0) return VAG_OK;
+    const int g = (int)std::min<int64_t>(ceil_div64(tot, 256), (int64_t)num_sms() * 8);
+    if (use_f16_split())
+        split_f16_kernel<<<g, 256, 0, st>>>(x, ldx, rows, K, (__half*)hi + col_off, (__half*)lo + col_off, ld_out);
+    else
+        split_tf32_kernel<<<g, 256, 0, st>>>(x, ldx, rows, K, (float*)hi + col_off, (float*)lo + col_off, ld_out);
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
+// The tcgen05 contraction on pre-split operands: xh/xl [rows, K] pitch ldxs, wh/wl [N, K] pitch ldws (elements).
+int tc_gemm(float* y, int64_t ldy, const void* xh, const void* xl, int64_t ldxs, const void* wh, const void* wl, int64_t ldws,
+            const float* bias, int rows, int K, int N, int flags, cudaStream_t st) {
+    const bool f16 = use_f16_split();
+    const bool wide = (int64_t)ceil_div(N, 256) * ceil_div(rows, 128) >= num_sms();
+    const int bn = wide ? 256 : 128;
+    CUtensorMap mxh, mxl, mwh, mwl;
+    VAG_TRY(make_map(&mxh, xh, rows, K, ldxs, 128, f16));
+    VAG_TRY(make_map(&mxl, xl, rows, K, ldxs, 128, f16));
+    VAG_TRY(make_map(&mwh, wh, N, K, ldws, bn, f16));
+    VAG_TRY(make_map(&mwl, wl, N, K, ldws, bn, f16));
+    if (f16) {
+        if (wide) return launch_tc<256, true>(mxh, mxl, mwh, mwl, y, ldy, bias, rows, K, N, flags, st);
+        return launch_tc<128, true>(mxh, mxl, mwh, mwl, y, ldy, bias, rows, K, N, flags, st);
+    }
+    if (wide) return launch_tc<256, false>(mxh, mxl, mwh, mwl, y, ldy, bias, rows, K, N, flags, st);
+    return launch_tc<128, false>(mxh, mxl, mwh, mwl, y, ldy, bias, rows, K, N, flags, st);
+}
+
 // scratch: ≥ linear_tc_scratch_bytes(rows, K, N).  Splits both operands, then runs the tcgen05 kernel.
 int linear_tc(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, int rows,
               int K, int N, int flags, void* scratch, size_t scratch_bytes, cudaStream_t st) {
@@ -372,8 +407,7 @@ int linear_tc(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w
         return VAG_ERR_WORKSPACE;
     }
     Arena ar(scratch, scratch_bytes);
-    const bool f16 = use_f16_split();
-    const size_t esz = f16 ? 2 : 4;
+    const size_t esz = (size_t)tc_elem_bytes();
     void* xh = ar.take<char>((size_t)rows * K * esz);
     void* xl = ar.take<char>((size_t)rows * K * esz);
     void* wh = ar.take<char>((size_t)N * K * esz);
@@ -382,37 +416,9 @@ int linear_tc(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w
         set_error("linear_tc: scratch overflow");
         return VAG_ERR_WORKSPACE;
     }
-    const int sms = num_sms();
-    {
-        const int64_t tot = (int64_t)rows * (K / 4);
-        const int gx = (int)std::min<int64_t>(ceil_div64(tot, 256), (int64_t)sms * 8);
-        const int64_t totw = (int64_t)N * (K / 4);
-        const int gw = (int)std::min<int64_t>(ceil_div64(totw, 256), (int64_t)sms * 8);
-        if (f16) {
-            split_f16_kernel<<<gx, 256, 0, st>>>(x, ldx, rows, K, (__half*)xh, (__half*)xl);
-            VAG_LAUNCH_CHECK();
-            split_f16_kernel<<<gw, 256, 0, st>>>(w, ldw, N, K, (__half*)wh, (__half*)wl);
-            VAG_LAUNCH_CHECK();
-        } else {
-            split_tf32_kernel<<<gx, 256, 0, st>>>(x, ldx, rows, K, (float*)xh, (float*)xl);
-            VAG_LAUNCH_CHECK();
-            split_tf32_kernel<<<gw, 256, 0, st>>>(w, ldw, N, K, (float*)wh, (float*)wl);
-            VAG_LAUNCH_CHECK();
-        }
-    }
-    const bool wide = (int64_t)ceil_div(N, 256) * ceil_div(rows, 128) >= sms;
-    const int bn = wide ? 256 : 128;
-    CUtensorMap mxh, mxl, mwh, mwl;
-    VAG_TRY(make_map(&mxh, xh, rows, K, K, 128, f16));
-    VAG_TRY(make_map(&mxl, xl, rows, K, K, 128, f16));
-    VAG_TRY(make_map(&mwh, wh, N, K, K, bn, f16));
-    VAG_TRY(make_map(&mwl, wl, N, K, K, bn, f16));
-    if (f16) {
-        if (wide) return launch_tc<256, true>(mxh, mxl, mwh, mwl, y, ldy, bias, rows, K, N, flags, st);
-        return launch_tc<128, true>(mxh, mxl, mwh, mwl, y, ldy, bias, rows, K, N, flags, st);
-    }
-    if (wide) return launch_tc<256, false>(mxh, mxl, mwh, mwl, y, ldy, bias, rows, K, N, flags, st);
-    return launch_tc<128, false>(mxh, mxl, mwh, mwl, y, ldy, bias, rows, K, N, flags, st);
+    VAG_TRY(tc_split(x, ldx, rows, K, xh, xl, K, 0, st));
+    VAG_TRY(tc_split(w, ldw, N, K, wh, wl, K, 0, st));
+    return tc_gemm(y, ldy, xh, xl, K, wh, wl, K, bias, rows, K, N, flags, st);
 }
 
 }  // namespace vag

@@ -8,8 +8,8 @@
 
 namespace vag {
 
-int linear_dispatch(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias,
-                    int rows, int K, int N, int flags, cudaStream_t st, void* scratch, size_t scratch_bytes);
+int linear_simt(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias,
+                int rows, int K, int N, int flags, cudaStream_t st);
 
 // One CTA per row i of scores [B, B].  Writes G[i, j] (j != i) = dLoss/dscores[i,j] and the row's loss partial.
 __global__ void __launch_bounds__(256)
@@ -143,7 +143,7 @@ extern "C" int vag_rank_loss_f32(const float* im, const float* s, int B, int S, 
         set_error("vag_rank_loss_f32: workspace %zu B too small", workspace_bytes);
         return VAG_ERR_WORKSPACE;
     }
-    VAG_TRY(linear_dispatch(scores, B, im, S, s, S, nullptr, B, S, B, 0, st, nullptr, 0));  // scores = im · sᵀ   :12
+    VAG_TRY(linear_simt(scores, B, im, S, s, S, nullptr, B, S, B, 0, st));  // scores = im · sᵀ   :12
     rank_hinge_kernel<<<B, 256, 0, st>>>(scores, B, margin, one_direction, grad_im ? G : nullptr, row_loss);
     VAG_LAUNCH_CHECK();
     sum_to_scalar_kernel<<<1, 256, 0, st>>>(row_loss, B, loss_out);
@@ -178,7 +178,7 @@ extern "C" int vag_recall_ranks_f32(const float* queries, const float* gallery, 
         set_error("vag_recall_ranks_f32: workspace %zu B too small", workspace_bytes);
         return VAG_ERR_WORKSPACE;
     }
-    VAG_TRY(linear_dispatch(scores, n, queries, S, gallery, S, nullptr, n, S, n, 0, st, nullptr, 0));
+    VAG_TRY(linear_simt(scores, n, queries, S, gallery, S, nullptr, n, S, n, 0, st));
     recall_rank_kernel<<<n, 256, 0, st>>>(scores, n, ranks);
     VAG_LAUNCH_CHECK();
     return VAG_OK;

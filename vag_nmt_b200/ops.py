@@ -267,7 +267,7 @@ def decoder_init(w: DecoderWeights, ctx_vec: Optional[torch.Tensor], ctx: torch.
     lib = _cabi.lib()
     B, T, Cd = ctx.shape
     h0 = torch.empty(B, w.H, dtype=torch.float32, device=ctx.device)
-    ws = workspace(B * Cd * 4 + 1024 + lib.vag_linear_tc_workspace_bytes(B, Cd, w.H), ctx.device)
+    ws = workspace(lib.vag_decoder_init_workspace_bytes(B, Cd, w.H), ctx.device)
     with torch.cuda.device(ctx.device):
         check(lib.vag_decoder_init_f32(C.byref(w), ptr(ctx_vec), ctx.data_ptr(), mask.data_ptr(), float(split), B, T,
                                        h0.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr()))
