@@ -249,24 +249,35 @@ def run_ours(args):
     value = total_sent * args.steps / (ms / 1e3)
     e2e = total_sent * args.steps / (ms_e2e / 1e3)
 
-    # ---- roofline of the dominant kernel: the vocabulary projection [B*K, E] x [E, V] of one decoder step,
-    #      timed alone with CUDA events on the launching stream (burst peak applies).
+    # ---- roofline of the dominant kernel: the vocabulary projection [B*K, E] x [E, V] of one decoder step
+    #      (linear_split3_kernel, tcgen05 FP16-split contraction on pre-split operands, exactly the launch the
+    #      decode loop makes), timed alone with CUDA events on the launching stream (burst peak applies).
     pk = peaks()
     N = args.sentences * K
     E, V = cfg["tgt_embedding_size"], cfg["tgt_size"]
     x = torch.randn(N, E, device=dev)
-    y = torch.empty(N, V, device=dev)
-    wgt, bias = model.decoder.out.weight, model.decoder.out.bias
+    ldl = (V + 3) // 4 * 4
+    ybuf = torch.empty(N, ldl, device=dev)
+    wgt, bias = model.decoder.out.weight.detach(), model.decoder.out.bias.detach()
+    xs, wsplit = ops.tc_split(x), ops.tc_split(wgt)
+    y = ybuf[:, :V]
     for _ in range(3):
-        ops.linear(x, wgt, bias, out=y)
-    reps = 10
-    ms_k = timed(lambda: ops.linear(x, wgt, bias, out=y), reps) / reps
+        ops.tc_gemm(xs, wsplit, N, E, V, bias, out=y)
+    reps = 20
+    ms_k = timed(lambda: ops.tc_gemm(xs, wsplit, N, E, V, bias, out=y), reps) / reps
     flops = 2.0 * N * E * V
     achieved = flops / (ms_k / 1e3) / 1e12
-    peak_tf = pk["bf16"] / 6.0
-    roofline = {"bound": "tensor", "kernel": "vag_linear_f32 vocab projection rows=%d K=%d N=%d" % (N, E, V),
-                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
-                "peak_note": f"{pk['src']} bf16 burst {pk['bf16']} TF/s ÷ 6: FP32-exact mode = 3 TF32 products per MAC at half the bf16 rate",
+    split3 = lib.vag_tc_elem_bytes() == 2
+    peak_tf = pk["bf16"] / (3.0 if split3 else 6.0)
+    traffic = None
+    tpath = ROOT / "profiles" / "dominant_kernel_traffic.json"
+    if tpath.exists():
+        traffic = json.loads(tpath.read_text()).get("dram_bytes_per_launch")
+    roofline = {"bound": "tensor", "kernel": "linear_split3_kernel (vag_tc_gemm_f32) vocab projection rows=%d K=%d N=%d" % (N, E, V),
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
+                "peak_note": (f"{pk['src']} bf16 burst {pk['bf16']} TF/s ÷ 3: FP32-exact mode issues 3 FP16 tensor products "
+                              "(hi·hi, hi·lo, lo·hi) per algorithmic MAC" if split3 else
+                              f"{pk['src']} bf16 burst {pk['bf16']} TF/s ÷ 6: 3 TF32 products per MAC at half the bf16 rate"),
                 "ms_per_launch": ms_k, "flops_per_launch": flops}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

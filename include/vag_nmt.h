@@ -70,6 +70,17 @@ int vag_linear_tc_f32(float* y, int64_t ldy, const float* x, int64_t ldx, const 
                       const float* bias, int rows, int in_dim, int out_dim, int flags, void* workspace,
                       size_t workspace_bytes, vag_stream_t stream);
 
+/* The two halves of vag_linear_tc_f32 for callers that keep operands split across calls (weights are split once
+ * per decode; an activation read by several contractions is split once per step).
+ *   vag_tc_elem_bytes(): bytes per element of a split plane (2: FP16 split, the default; 4: VAG_GEMM=tf32x3).
+ *   vag_tc_split_f32 : x [rows, K] → hi / lo planes [rows, ld_out] (ld_out in elements, multiple of 8; planes 128-B aligned).
+ *   vag_tc_gemm_f32  : y = act(x·Wᵀ + bias [+ y]) from split operands (tcgen05.mma, TMEM accumulators, TMA loads). */
+int vag_tc_elem_bytes(void);
+int vag_tc_split_f32(const float* x, int64_t ldx, int rows, int K, void* hi, void* lo, int64_t ld_out, vag_stream_t stream);
+int vag_tc_gemm_f32(float* y, int64_t ldy, const void* x_hi, const void* x_lo, int64_t ldx, const void* w_hi,
+                    const void* w_lo, int64_t ldw, const float* bias, int rows, int in_dim, int out_dim, int flags,
+                    vag_stream_t stream);
+
 /* out[r, :] = table[ids[r], :]   (nn.Embedding lookups: Encoder.py:50, NMT_Decoder.py:118) */
 int vag_embed_rows_f32(float* out, int64_t ldo, const float* table, int dim, const int64_t* ids, int rows,
                        int64_t table_rows, vag_stream_t stream);

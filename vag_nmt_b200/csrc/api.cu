@@ -86,6 +86,33 @@ extern "C" int vag_linear_f32(float* y, int64_t ldy, const float* x, int64_t ldx
                            nullptr, 0);
 }
 
+namespace vag {
+int tc_elem_bytes();
+int tc_split(const float* x, int64_t ldx, int rows, int K, void* hi, void* lo, int64_t ld_out, int64_t col_off, cudaStream_t st);
+int tc_gemm(float* y, int64_t ldy, const void* xh, const void* xl, int64_t ldxs, const void* wh, const void* wl, int64_t ldws,
+            const float* bias, int rows, int K, int N, int flags, cudaStream_t st);
+}
+
+extern "C" int vag_tc_elem_bytes(void) { return tc_elem_bytes(); }
+
+extern "C" int vag_tc_split_f32(const float* x, int64_t ldx, int rows, int K, void* hi, void* lo, int64_t ld_out,
+                                vag_stream_t stream) {
+    VAG_REQUIRE(x && hi && lo, "vag_tc_split_f32: null pointer");
+    VAG_REQUIRE(rows > 0 && K > 0 && K % 8 == 0 && ldx % 4 == 0 && ld_out >= K && ld_out % 8 == 0,
+                "vag_tc_split_f32: K and ld_out must be multiples of 8, ldx a multiple of 4");
+    VAG_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)hi & 127) == 0 && ((uintptr_t)lo & 127) == 0, "vag_tc_split_f32: alignment");
+    return tc_split(x, ldx, rows, K, hi, lo, ld_out, 0, (cudaStream_t)stream);
+}
+
+extern "C" int vag_tc_gemm_f32(float* y, int64_t ldy, const void* x_hi, const void* x_lo, int64_t ldx, const void* w_hi,
+                               const void* w_lo, int64_t ldw, const float* bias, int rows, int in_dim, int out_dim, int flags,
+                               vag_stream_t stream) {
+    VAG_REQUIRE(y && x_hi && x_lo && w_hi && w_lo, "vag_tc_gemm_f32: null pointer");
+    VAG_REQUIRE(rows > 0 && in_dim >= 32 && in_dim % 8 == 0 && out_dim > 0 && ldx % 8 == 0 && ldw % 8 == 0 && ldy >= out_dim,
+                "vag_tc_gemm_f32: bad shape");
+    return tc_gemm(y, ldy, x_hi, x_lo, ldx, w_hi, w_lo, ldw, bias, rows, in_dim, out_dim, flags, (cudaStream_t)stream);
+}
+
 extern "C" size_t vag_linear_tc_workspace_bytes(int rows, int in_dim, int out_dim) {
     return linear_tc_scratch_bytes(rows, in_dim, out_dim);
 }

@@ -126,25 +126,33 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t b
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format, see cute/arch/mma_sm100_desc.hpp):
 //   [0,14) start address >> 4   [16,30) leading byte offset >> 4 (unused for swizzled K-major)
 //   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B)   [46,48) version = 1   [61,64) layout = 2 (SW128)
+// ROWB = bytes of one K-row in shared memory = the swizzle span: 128 (SWIZZLE_128B, layout 2) or 64 (SWIZZLE_64B,
+// layout 4); the stride between 8-row groups is 8·ROWB.
+template <int ROWB>
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
     d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)((8 * ROWB) >> 4) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)(ROWB == 128 ? 2 : 4) << 61;
     return d;
 }
 
-template <int BN, bool F16>
+// Two tile configurations:
+//   ROWB = 128 ("wide"): 128 x 256 tile, 128-byte K rows, 2 stages, one CTA per SM  — least L2 traffic per flop, for long K
+//   ROWB =  64 ("dual"): 128 x 128 tile,  64-byte K rows, 3 stages, TWO CTAs per SM — one CTA's epilogue overlaps the
+//                        other's main loop; for short-K / epilogue-heavy problems such as the vocabulary projection
+template <int BN, bool F16, int ROWB>
 struct TcCfg {
     static constexpr int BM = 128;
     static constexpr int ELT = F16 ? 2 : 4;
-    static constexpr int BK = 128 / ELT;   // elements per 128-byte swizzle row: 32 (tf32) / 64 (f16)
-    static constexpr int UK = 32 / ELT;    // K of one MMA instruction (32 bytes): 8 / 16
-    static constexpr int STAGES = BN == 256 ? 2 : 3;
-    static constexpr int A_BYTES = BM * 128;
-    static constexpr int B_BYTES = BN * 128;
+    static constexpr int BK = ROWB / ELT;  // elements per shared-memory K row
+    static constexpr int UK = 32 / ELT;    // K of one MMA instruction (32 bytes): 8 (tf32) / 16 (f16)
+    static constexpr int STAGES = ROWB == 64 ? 3 : (BN == 256 ? 2 : 3);
+    static constexpr int CTAS_PER_SM = ROWB == 64 ? 2 : 1;
+    static constexpr int A_BYTES = BM * ROWB;
+    static constexpr int B_BYTES = BN * ROWB;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
     static constexpr uint32_t FMT = F16 ? 0u : 2u;  // F16F32Format: F16 = 0, TF32 = 2
@@ -152,12 +160,12 @@ struct TcCfg {
                                       ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 };
 
-template <int BN, bool F16>
-__global__ void __launch_bounds__(192, 1)
+template <int BN, bool F16, int ROWB>
+__global__ void __launch_bounds__(192, (ROWB == 64 ? 2 : 1))
 linear_split3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                      const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
                      float* __restrict__ y, int64_t ldy, const float* __restrict__ bias, int rows, int K, int N, int flags) {
-    using Cfg = TcCfg<BN, F16>;
+    using Cfg = TcCfg<BN, F16, ROWB>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -215,10 +223,10 @@ linear_split3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_co
                 mbar_wait(&full_bar[s], ph);
                 tcgen05_fence_after();
                 const uint32_t st = smem_u32(smem + s * Cfg::STAGE_BYTES);
-                const uint64_t d_ah = make_smem_desc(st);
-                const uint64_t d_al = make_smem_desc(st + Cfg::A_BYTES);
-                const uint64_t d_bh = make_smem_desc(st + 2 * Cfg::A_BYTES);
-                const uint64_t d_bl = make_smem_desc(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+                const uint64_t d_ah = make_smem_desc<ROWB>(st);
+                const uint64_t d_al = make_smem_desc<ROWB>(st + Cfg::A_BYTES);
+                const uint64_t d_bh = make_smem_desc<ROWB>(st + 2 * Cfg::A_BYTES);
+                const uint64_t d_bl = make_smem_desc<ROWB>(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
 #pragma unroll
                 for (int j = 0; j < Cfg::BK / Cfg::UK; ++j) {
                     const uint64_t adv = (uint64_t)((j * 32) >> 4);  // 32 B per k-step inside the 128 B swizzle row
@@ -314,7 +322,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 // 2-D tensor [rows, K] (K contiguous, row pitch ld elements), box {128 B, box_rows}, SWIZZLE_128B, zero OOB fill.
-static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t K, int64_t ld, int box_rows, bool f16) {
+static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t K, int64_t ld, int box_rows, bool f16, int rowb) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled entry point not available");
@@ -322,10 +330,11 @@ static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t K, i
     }
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * (f16 ? 2 : 4)};
-    cuuint32_t box[2] = {f16 ? 64u : 32u, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)(rowb / (f16 ? 2 : 4)), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1u, 1u};
     CUresult r = fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with %d (rows=%lld K=%lld ld=%lld)", (int)r, (long long)rows, (long long)K, (long long)ld);
         return VAG_ERR_CUDA;
@@ -343,17 +352,17 @@ bool linear_tc_eligible(const float* y, int64_t ldy, const float* x, int64_t ldx
     return rows >= 64 && N >= 64 && K >= 32 && (K % 8 == 0) && (ldx % 4 == 0) && (ldw % 4 == 0) && al(x) && al(w);
 }
 
-template <int BN, bool F16>
+template <int BN, bool F16, int ROWB>
 static int launch_tc(const CUtensorMap& xh, const CUtensorMap& xl, const CUtensorMap& wh, const CUtensorMap& wl, float* y,
                      int64_t ldy, const float* bias, int rows, int K, int N, int flags, cudaStream_t st) {
-    using Cfg = TcCfg<BN, F16>;
+    using Cfg = TcCfg<BN, F16, ROWB>;
     static bool attr_set = false;
     if (!attr_set) {
-        VAG_CUDA(cudaFuncSetAttribute(linear_split3_kernel<BN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        VAG_CUDA(cudaFuncSetAttribute(linear_split3_kernel<BN, F16, ROWB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
     dim3 grid(ceil_div(N, BN), ceil_div(rows, Cfg::BM));
-    linear_split3_kernel<BN, F16><<<grid, 192, Cfg::SMEM_BYTES, st>>>(xh, xl, wh, wl, y, ldy, bias, rows, K, N, flags);
+    linear_split3_kernel<BN, F16, ROWB><<<grid, 192, Cfg::SMEM_BYTES, st>>>(xh, xl, wh, wl, y, ldy, bias, rows, K, N, flags);
     VAG_LAUNCH_CHECK();
     return VAG_OK;
 }
@@ -384,19 +393,34 @@ int tc_split(const float* x, int64_t ldx, int rows, int K, void* hi, void* lo, i
 int tc_gemm(float* y, int64_t ldy, const void* xh, const void* xl, int64_t ldxs, const void* wh, const void* wl, int64_t ldws,
             const float* bias, int rows, int K, int N, int flags, cudaStream_t st) {
     const bool f16 = use_f16_split();
-    const bool wide = (int64_t)ceil_div(N, 256) * ceil_div(rows, 128) >= num_sms();
-    const int bn = wide ? 256 : 128;
-    CUtensorMap mxh, mxl, mwh, mwl;
-    VAG_TRY(make_map(&mxh, xh, rows, K, ldxs, 128, f16));
-    VAG_TRY(make_map(&mxl, xl, rows, K, ldxs, 128, f16));
-    VAG_TRY(make_map(&mwh, wh, N, K, ldws, bn, f16));
-    VAG_TRY(make_map(&mwl, wl, N, K, ldws, bn, f16));
-    if (f16) {
-        if (wide) return launch_tc<256, true>(mxh, mxl, mwh, mwl, y, ldy, bias, rows, K, N, flags, st);
-        return launch_tc<128, true>(mxh, mxl, mwh, mwl, y, ldy, bias, rows, K, N, flags, st);
+    const int sms = num_sms();
+    // tile configuration: VAG_TC_CFG=wide|narrow|dual overrides the heuristic (tuning / A-B runs)
+    int cfg;  // 0 = 128x256 wide, 1 = 128x128 (128 B rows), 2 = 128x128 dual-CTA (64 B rows)
+    const char* e = getenv("VAG_TC_CFG");
+    if (e && strcmp(e, "wide") == 0) cfg = 0;
+    else if (e && strcmp(e, "narrow") == 0) cfg = 1;
+    else if (e && strcmp(e, "dual") == 0) cfg = 2;
+    else {
+        cfg = 2;  // measured on B200 (tools/tcbench.py): the dual-CTA tile wins or ties on every decode-step shape
+        (void)sms;
     }
-    if (wide) return launch_tc<256, false>(mxh, mxl, mwh, mwl, y, ldy, bias, rows, K, N, flags, st);
-    return launch_tc<128, false>(mxh, mxl, mwh, mwl, y, ldy, bias, rows, K, N, flags, st);
+    const int bn = cfg == 0 ? 256 : 128;
+    const int rowb = cfg == 2 ? 64 : 128;
+    CUtensorMap mxh, mxl, mwh, mwl;
+    VAG_TRY(make_map(&mxh, xh, rows, K, ldxs, 128, f16, rowb));
+    VAG_TRY(make_map(&mxl, xl, rows, K, ldxs, 128, f16, rowb));
+    VAG_TRY(make_map(&mwh, wh, N, K, ldws, bn, f16, rowb));
+    VAG_TRY(make_map(&mwl, wl, N, K, ldws, bn, f16, rowb));
+#define VAG_TC_GO(BN_, F16_, ROWB_) return launch_tc<BN_, F16_, ROWB_>(mxh, mxl, mwh, mwl, y, ldy, bias, rows, K, N, flags, st)
+    if (f16) {
+        if (cfg == 0) VAG_TC_GO(256, true, 128);
+        if (cfg == 1) VAG_TC_GO(128, true, 128);
+        VAG_TC_GO(128, true, 64);
+    }
+    if (cfg == 0) VAG_TC_GO(256, false, 128);
+    if (cfg == 1) VAG_TC_GO(128, false, 128);
+    VAG_TC_GO(128, false, 64);
+#undef VAG_TC_GO
 }
 
 // scratch: ≥ linear_tc_scratch_bytes(rows, K, N).  Splits both operands, then runs the tcgen05 kernel.

@@ -86,6 +86,33 @@ def linear_tc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = N
     return out
 
 
+def tc_split(x: torch.Tensor):
+    """x [rows, K] fp32 → (hi, lo) split planes (uint8 storage, [rows, K] elements of vag_tc_elem_bytes() each)."""
+    _chk_f32(x)
+    lib = _cabi.lib()
+    assert x.dim() == 2 and x.stride(1) == 1
+    rows, K = x.shape
+    esz = lib.vag_tc_elem_bytes()
+    hi = torch.empty(rows * K * esz, dtype=torch.uint8, device=x.device)
+    lo = torch.empty_like(hi)
+    with torch.cuda.device(x.device):
+        check(lib.vag_tc_split_f32(x.data_ptr(), x.stride(0), rows, K, hi.data_ptr(), lo.data_ptr(), K, stream_ptr()))
+    return hi, lo
+
+
+def tc_gemm(xs, ws, rows: int, in_dim: int, out_dim: int, bias: Optional[torch.Tensor] = None, flags: int = 0,
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = act(x·Wᵀ + bias) from operands split by ``tc_split`` (xs = (hi, lo), ws = (hi, lo))."""
+    lib = _cabi.lib()
+    dev = xs[0].device
+    if out is None:
+        out = torch.empty(rows, out_dim, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.vag_tc_gemm_f32(out.data_ptr(), out.stride(0), xs[0].data_ptr(), xs[1].data_ptr(), in_dim, ws[0].data_ptr(),
+                                  ws[1].data_ptr(), in_dim, ptr(bias), rows, in_dim, out_dim, flags, stream_ptr()))
+    return out
+
+
 def embed_rows(table: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
     _chk_f32(table)
     lib = _cabi.lib()
