@@ -279,6 +279,41 @@ int vag_row_argmax_f32(const float* logits, int64_t ld, int rows, int64_t V, int
 int vag_translation_loss_f32(const float* loss_rows, const int64_t* tgt, int B, int Tt, const float* loss_vse,
                              float loss_w, float* out, vag_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * Backward pieces of the training step (train.py:36-51: forward, loss.backward(), clip_grad_norm_, Adam.step()).
+ * The reference gets all of these from autograd + cuDNN; here each is one kernel and the Python autograd
+ * Functions of vag_nmt_b200/autograd.py sequence them (BPTT over the Tt decoder / Ts encoder steps).
+ * ---------------------------------------------------------------------------------- */
+/* C[m,n] = alpha·Σ_k A[m·sam + k·sak]·B[k·sbk + n·sbn] + beta·C[m,n]: dX = dY·W and dW = dYᵀ·X of every nn.Linear / GRU matrix. */
+int vag_gemm_f32(float* C, int64_t ldc, const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk,
+                 int64_t sbn, int M, int N, int K, float alpha, float beta, vag_stream_t stream);
+/* GRU cell backward from the saved pre-activations: dgi, dgh [rows,3H] and dh_prev [rows,H] = dh·z (the caller adds dgh·W_hh). */
+int vag_gru_gates_bwd_f32(float* dgi, float* dgh, float* dh_prev, const float* dh, int64_t ld_dh, const float* gi,
+                          const float* gh, const float* h_prev, int64_t ld_hp, int rows, int H, vag_stream_t stream);
+/* Backward of vag_attention_f32 with one row per sentence: dq [B,C]; dkeys, dctx [B,T,C] and dv [C] are ACCUMULATED
+ * (they collect contributions from every decoder step); dctx / dv may be NULL. */
+int vag_attention_bwd_f32(float* dq, int64_t ld_dq, float* dkeys, float* dctx, float* dv, const float* dc, int64_t ld_dc,
+                          const float* alpha, const float* q, int64_t ld_q, const float* keys, const float* ctx,
+                          const float* v, const float* mask, int B, int T, int C, int mode, vag_stream_t stream);
+/* dlogits[r,v] = grad_rows[r]·weight[tgt[r]]·(softmax(logits)[r,v] − [v == tgt[r]])   (backward of vag_nll_rows_f32) */
+int vag_nll_bwd_f32(float* dlogits, int64_t ldd, const float* logits, int64_t ld, const float* lse, const int64_t* tgt,
+                    const float* weight, const float* grad_rows, int rows, int64_t V, vag_stream_t stream);
+int vag_tanh_bwd_f32(float* dx, const float* dy, const float* y, int64_t n, vag_stream_t stream);          /* dx = dy·(1−y²) */
+int vag_axpby_f32(float* y, const float* x, float a, float b, int64_t n, vag_stream_t stream);             /* y = a·x + b·y */
+int vag_colsum_f32(float* out, const float* x, int64_t ldx, int rows, int cols, int accumulate, vag_stream_t stream); /* bias grads */
+int vag_embed_bwd_f32(float* table_grad, const float* g, int64_t ldg, const int64_t* ids, int rows, int dim,
+                      int64_t table_rows, vag_stream_t stream);                                             /* scatter-add */
+int vag_l2norm_bwd_f32(float* dx, const float* dy, const float* x, int rows, int dim, vag_stream_t stream);
+int vag_init_mix_bwd_f32(float* dctx_vec, float* dctx, const float* dz, const float* mask, float split, int B, int T,
+                         int C, vag_stream_t stream);
+/* Optimiser step of train.py:46-49 with the Adam of nmt_multimodal_beam_DE.py:303-332, fused per parameter tensor:
+ *   accum[0] += Σ grad²  (vag_sumsq_f32 over every tensor, after the gradient all-reduce when data-parallel), then
+ *   g ← grad·min(1, clip/(√accum + 1e-6)) [+ weight_decay·param];  Adam(m, v, step) update of param in place. */
+int vag_sumsq_f32(const float* g, int64_t n, float* accum, vag_stream_t stream);
+int vag_clip_adam_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                      const float* grad_sumsq, float clip, float lr, float beta1, float beta2, float eps,
+                      float weight_decay, int step, vag_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,6 +82,18 @@ SIGNATURES = {
     "vag_nll_rows_f32": (I, [P, I64, P, P, I, I64, P, P, P]),
     "vag_row_argmax_f32": (I, [P, I64, I, I64, P, P]),
     "vag_translation_loss_f32": (I, [P, P, I, I, P, F, P, P]),
+    "vag_gemm_f32": (I, [P, I64, P, I64, I64, P, I64, I64, I, I, I, F, F, P]),
+    "vag_gru_gates_bwd_f32": (I, [P, P, P, P, I64, P, P, P, I64, I, I, P]),
+    "vag_attention_bwd_f32": (I, [P, I64, P, P, P, P, I64, P, P, I64, P, P, P, P, I, I, I, I, P]),
+    "vag_nll_bwd_f32": (I, [P, I64, P, I64, P, P, P, P, I, I64, P]),
+    "vag_tanh_bwd_f32": (I, [P, P, P, I64, P]),
+    "vag_axpby_f32": (I, [P, P, F, F, I64, P]),
+    "vag_colsum_f32": (I, [P, P, I64, I, I, I, P]),
+    "vag_embed_bwd_f32": (I, [P, P, I64, P, I, I, I64, P]),
+    "vag_l2norm_bwd_f32": (I, [P, P, P, I, I, P]),
+    "vag_init_mix_bwd_f32": (I, [P, P, P, P, F, I, I, I, P]),
+    "vag_sumsq_f32": (I, [P, I64, P, P]),
+    "vag_clip_adam_f32": (I, [P, P, P, P, I64, P, F, F, F, F, F, F, I, P]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -36,6 +36,13 @@ def _nll_weight(criterion, device) -> Optional[torch.Tensor]:
     return None if w is None else w.detach().to(device=device, dtype=torch.float32).contiguous()
 
 
+def _no_dropout_in_training(model) -> None:
+    enc, dec = model.encoder, model.decoder
+    if model.training and any(r > 0 for r in (enc.dropout_emb, enc.dropout_ctx, dec.dropout_out, dec.dropout_emb)):
+        raise NotImplementedError("training-mode dropout is not part of the B200 path yet: build the model with zero dropout "
+                                  "rates (parity runs use p = 0, SURVEY.md section 7 hard part 7)")
+
+
 class _Seq2SeqBase(nn.Module):
     """Pieces shared by the two models: encoder → h0 → decoder loop / beam search."""
 
@@ -83,6 +90,38 @@ class _Seq2SeqBase(nn.Module):
         if beam_size == 1:
             return ops.greedy_decode(w, h0, keys, ctx, mask, max_length), None
         return ops.beam_decode(w, h0, keys, ctx, mask, beam_size, max_length)
+
+    # -- training path (autograd through hand-written backward kernels) ------------------------------------
+    def _wants_grad(self) -> bool:
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+
+    def _decoder_param_list(self):
+        d = self.decoder
+        return [d.embedding.weight, d.gru_1.weight_ih_l0, d.gru_1.weight_hh_l0, d.gru_1.bias_ih_l0, d.gru_1.bias_hh_l0,
+                d.attn.attn_h.weight, d.attn.attn_e.weight, d.attn.v, d.context2hid.weight, d.gru_2.weight_ih_l0,
+                d.gru_2.weight_hh_l0, d.gru_2.bias_ih_l0, d.gru_2.bias_hh_l0, d.W1.weight, d.W1.bias, d.W2.weight, d.W2.bias,
+                d.W3.weight, d.W3.bias, d.out.weight, d.out.bias]
+
+    def _encode_train(self, src_var, src_lengths):
+        from .autograd import EncoderFn
+        enc = self.encoder
+        dev = self._device()
+        src = src_var.to(device=dev, dtype=torch.int64).contiguous()
+        lengths = [int(x) for x in src_lengths]
+        if src.shape[1] != max(lengths):
+            raise ValueError("the padded width must equal the longest sentence (pad_packed_sequence, Encoder.py:60)")
+        if any(lengths[i] < lengths[i + 1] for i in range(len(lengths) - 1)):
+            raise RuntimeError("`lengths` array must be sorted in decreasing order (pack_padded_sequence, Encoder.py:55)")
+        g = enc.gru
+        ctx = EncoderFn.apply(src, lengths, enc.embedding.weight, g.weight_ih_l0, g.weight_hh_l0, g.bias_ih_l0, g.bias_hh_l0,
+                              g.weight_ih_l0_reverse, g.weight_hh_l0_reverse, g.bias_ih_l0_reverse, g.bias_hh_l0_reverse)
+        mask = (src != 0).to(torch.float32)                          # Encoder.py:47
+        return ctx, mask
+
+    def _decoder_loss_train(self, h0, ctx, mask, tgt, teacher_force_ratio, weight):
+        from .autograd import DecoderSeqFn
+        is_teacher = random.random() < teacher_force_ratio          # V11:136
+        return DecoderSeqFn.apply(h0, ctx, mask, tgt, weight, is_teacher, bool(self.decoder.tied_emb), *self._decoder_param_list())
 
     def _translation_loss_rows(self, w, h0, keys, ctx, mask, tgt, teacher_force_ratio, weight):
         """The Tt-step loop of forward (V11:136-160): Σ_t NLL rows [B]."""
@@ -148,6 +187,8 @@ class NMT_AttentionImagine_Seq2Seq_Beam_V11(_Seq2SeqBase):
         """→ (loss, loss_mt, loss_vse), V11:82-168."""
         dev = self._device()
         self.tgt_l = tgt_var.size()[1]
+        if self._wants_grad():
+            return self._forward_train(src_var, src_lengths, tgt_var, im_var, teacher_force_ratio, criterion_mt, criterion_vse)
         w, ctx, mask, keys, h0, im_emb, txt_emb = self._prepare(src_var, src_lengths, im_var)
         loss_vse = None
         if criterion_vse is not None:
@@ -161,6 +202,29 @@ class NMT_AttentionImagine_Seq2Seq_Beam_V11(_Seq2SeqBase):
         out = ops.translation_loss(loss_rows, tgt, vse_dev, self.loss_w if vse_dev is not None else 1.0)
         if loss_vse is None:
             # the reference mixes with the python int 0 (V11:91,166): loss = loss_w * loss_mt
+            return self.loss_w * out[1], out[1], 0
+        return out[0], out[1], out[2]
+
+    def _forward_train(self, src_var, src_lengths, tgt_var, im_var, teacher_force_ratio, criterion_mt, criterion_vse):
+        """Same values as the inference-mode forward, recorded for autograd (hand-written backward kernels)."""
+        from .autograd import DecoderInitFn, LossMixFn, VsePoolFn
+        _no_dropout_in_training(self)
+        dev = self._device()
+        ctx, mask = self._encode_train(src_var, src_lengths)
+        vse = self.vse_imagine
+        im = im_var.to(device=dev, dtype=torch.float32).contiguous()
+        mlp_w = vse.imagine_attn.mlp.weight if vse.attn_type == "mlp" else None
+        im_emb, txt_emb, ctx_vec = VsePoolFn.apply(im, ctx, mask, vse.attn_type, bool(vse.activation_vse), vse.im_embedding.weight,
+                                                   vse.im_embedding.bias, vse.text_embedding.weight, vse.text_embedding.bias,
+                                                   vse.imagine_attn.ctx2ctx.weight, vse.imagine_attn.emb2ctx.weight, mlp_w)
+        loss_vse = criterion_vse(im_emb, txt_emb) if criterion_vse is not None else None
+        h0 = DecoderInitFn.apply(ctx_vec, ctx, mask, float(self.init_split), self.decoderini.weight, self.decoderini.bias)
+        tgt = tgt_var.to(device=dev, dtype=torch.int64).contiguous()
+        weight = _nll_weight(criterion_mt, dev)
+        loss_rows = self._decoder_loss_train(h0, ctx, mask, tgt, teacher_force_ratio, weight)
+        vse_in = loss_vse.reshape(1) if loss_vse is not None else None
+        out = LossMixFn.apply(loss_rows, tgt, vse_in, float(self.loss_w))
+        if loss_vse is None:
             return self.loss_w * out[1], out[1], 0
         return out[0], out[1], out[2]
 
@@ -240,6 +304,14 @@ class NMT_Seq2Seq_Beam_V2(_Seq2SeqBase):
         """→ loss, models/NMT_Seq2Seq_Beam_V2.py:58-113."""
         dev = self._device()
         self.tgt_l = tgt_var.size()[1]
+        if self._wants_grad():
+            from .autograd import DecoderInitFn, LossMixFn
+            _no_dropout_in_training(self)
+            ctx, mask = self._encode_train(src_var, src_lengths)
+            h0 = DecoderInitFn.apply(None, ctx, mask, 0.0, self.decoderini.weight, self.decoderini.bias)
+            tgt = tgt_var.to(device=dev, dtype=torch.int64).contiguous()
+            loss_rows = self._decoder_loss_train(h0, ctx, mask, tgt, teacher_force_ratio, _nll_weight(criterion, dev))
+            return LossMixFn.apply(loss_rows, tgt, None, 1.0)[1]
         w, ctx, mask, keys, h0 = self._prepare(src_var, src_lengths)
         tgt = tgt_var.to(device=dev, dtype=torch.int64).contiguous()
         weight = _nll_weight(criterion, dev)

@@ -124,21 +124,27 @@ def embed_rows(table: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def gru_gates(gi: torch.Tensor, gh: torch.Tensor, h_prev: torch.Tensor) -> torch.Tensor:
-    _chk_f32(gi, gh, h_prev)
+def gru_gates(gi: torch.Tensor, gh: torch.Tensor, h_prev: torch.Tensor, out: Optional[torch.Tensor] = None,
+              out2: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """h' = GRU gates; all operands 2-D with unit inner stride; out2 optionally receives a second copy of h'."""
+    _chk_f32(gi, gh, h_prev, out, out2)
     lib = _cabi.lib()
     rows, H = h_prev.shape
-    gi, gh, h_prev = gi.contiguous(), gh.contiguous(), h_prev.contiguous()
-    out = torch.empty_like(h_prev)
+    for t in (gi, gh, h_prev):
+        assert t.stride(1) == 1
+    if out is None:
+        out = torch.empty(rows, H, dtype=torch.float32, device=h_prev.device)
     with torch.cuda.device(h_prev.device):
-        check(lib.vag_gru_gates_f32(out.data_ptr(), H, None, 0, gi.data_ptr(), 3 * H, gh.data_ptr(), 3 * H,
-                                    h_prev.data_ptr(), H, rows, H, stream_ptr()))
+        check(lib.vag_gru_gates_f32(out.data_ptr(), out.stride(0), ptr(out2), out2.stride(0) if out2 is not None else 0,
+                                    gi.data_ptr(), gi.stride(0), gh.data_ptr(), gh.stride(0), h_prev.data_ptr(),
+                                    h_prev.stride(0), rows, H, stream_ptr()))
     return out
 
 
 def attention(q: torch.Tensor, keys: torch.Tensor, ctx: torch.Tensor, v: Optional[torch.Tensor],
               mask: Optional[torch.Tensor], rows_per_sent: int = 1, mode: int = ATTN_MLP,
-              want_alpha: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+              want_alpha: bool = True, out_c: Optional[torch.Tensor] = None,
+              out_alpha: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """q [N, C]; keys/ctx [B, T, C] sentence-major; mask [B, T] → (c [N, C], α [N, T])."""
     _chk_f32(q, keys, ctx, v, mask)
     lib = _cabi.lib()
@@ -147,8 +153,9 @@ def attention(q: torch.Tensor, keys: torch.Tensor, ctx: torch.Tensor, v: Optiona
     N, Cdim = q.shape
     B, T, _ = ctx.shape
     assert N == B * rows_per_sent
-    c = torch.empty(N, Cdim, dtype=torch.float32, device=q.device)
-    alpha = torch.empty(N, T, dtype=torch.float32, device=q.device) if want_alpha else None
+    c = out_c if out_c is not None else torch.empty(N, Cdim, dtype=torch.float32, device=q.device)
+    alpha = out_alpha if out_alpha is not None else (torch.empty(N, T, dtype=torch.float32, device=q.device) if want_alpha else None)
+    assert c.is_contiguous() and (alpha is None or alpha.is_contiguous())
     with torch.cuda.device(q.device):
         check(lib.vag_attention_f32(c.data_ptr(), Cdim, ptr(alpha), q.data_ptr(), Cdim, keys.data_ptr(), ctx.data_ptr(),
                                     ptr(v), ptr(mask), N, rows_per_sent, T, Cdim, mode, stream_ptr()))
