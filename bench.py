@@ -183,6 +183,80 @@ def workload_config(args, per_step):
             "l2": "per-step working set (logits 451 MB + weights 64 MB) exceeds the 126 MB L2; no explicit flush"}
 
 
+# ------------------------------------------------------------------------------------------ training step (second metric)
+def oracle_train_step_time(model_cpu, batches, threads, lr=4e-4):
+    """One optimisation step the reference's way (train.py:36-51) through the CPU oracle + torch autograd."""
+    from oracle import vag_oracle as O
+    torch.set_num_threads(threads)
+    p = {k: v.detach().clone().requires_grad_(True) for k, v in model_cpu.state_dict().items()}
+    p["decoder.out.weight"] = p["decoder.embedding.weight"]
+    params = {k: v for k, v in p.items() if k != "decoder.out.weight"}
+    opt = torch.optim.Adam([{"params": [v for k, v in params.items() if "bias" not in k], "weight_decay": 1e-5},
+                            {"params": [v for k, v in params.items() if "bias" in k]}], lr=lr)
+    w = torch.ones(p["decoder.embedding.weight"].shape[0])
+    w[0] = 0
+    times, toks = [], 0
+    for i, bt in enumerate(batches):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        loss, _, _ = O.multimodal_forward(p, bt.src, bt.src_lengths, bt.tgt, bt.im, True, w, "pairwise", 0.1)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(list(params.values()), 1.0)
+        opt.step()
+        dt = time.perf_counter() - t0
+        if i > 0:           # first step warms the thread pool / allocator
+            times.append(dt)
+            toks += int((bt.tgt != 0).sum())
+    return toks / sum(times), len(times)
+
+
+def measure_train(args, dev, world, rank, timed):
+    """BASELINE configs[1]/[3] shape: EN->DE multimodal training step, batch 32 per GPU, teacher forced, FP32,
+    zero dropout (the drop-in does not implement training-mode dropout yet), gradients all-reduced over ranks."""
+    import vag_nmt_b200 as vag
+    from vag_nmt_b200 import synthetic
+    from vag_nmt_b200.optim import ClipAdam
+    from vag_nmt_b200.train import DistributedPairwiseRankingLoss, train_imagine_beam
+    cfg = synthetic.DE
+    model = build_cpu_params().to(dev)
+    opt = ClipAdam(model, lr=4e-4)
+    w = torch.ones(cfg["tgt_size"], device=dev)
+    w[0] = 0
+    crit_mt = torch.nn.NLLLoss(weight=w, reduction="none")
+    crit_vse = DistributedPairwiseRankingLoss(margin=0.1)
+    B = 32
+    batches = [synthetic.make_batch(B, cfg["src_size"], cfg["tgt_size"], cfg["im_feats_size"], seed=100 + 8 * i + rank) for i in range(8)]
+    pinned = [(bt.src.pin_memory(), bt.tgt.pin_memory(), bt.im.pin_memory(), bt.src_lengths) for bt in batches]
+    tokens = [int((bt.tgt != 0).sum()) for bt in batches]
+    state = {"i": 0, "loss": None}
+
+    def step():
+        src, tgt, im, lens = pinned[state["i"] % len(pinned)]
+        state["i"] += 1
+        out = train_imagine_beam(src.to(dev, non_blocking=True), tgt.to(dev, non_blocking=True), im.to(dev, non_blocking=True), lens,
+                                 model, opt, crit_mt, crit_vse, 0.99, 1.0, sync=False)
+        state["loss"] = out[0]
+
+    for _ in range(3):
+        step()
+    state["i"] = 0
+    steps = max(args.steps, 8)
+    ms = timed(step, steps)
+    final_loss = float(state["loss"])
+    tok = sum(tokens[i % len(tokens)] for i in range(steps)) * world
+    res = {"metric": "train tgt tokens/sec", "value": tok / (ms / 1e3), "unit": "tokens/s", "ms_per_step": ms / steps, "steps": steps,
+           "batch_per_gpu": B, "global_batch": B * world, "dtype": "f32", "loss_after": final_loss,
+           "note": "EN->DE multimodal, teacher forcing 1.0, dropout 0, pairwise ranking loss over the global batch, "
+                   "clip 1.0 + Adam(lr 4e-4, wd 1e-5 on non-bias); host batches (pinned) copied in the timed region"}
+    if rank == 0 and world == 1 and args.cpu_sample > 0:
+        threads = os.cpu_count() or 1
+        cpu_model = build_cpu_params()
+        v, n = oracle_train_step_time(cpu_model, batches[:4], threads)
+        res["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": threads, "kind": "port",
+                               "sample": f"{n} optimisation steps, batch {B}, oracle forward + torch autograd + clip + Adam on CPU fp32"}
+    return res
+
+
 # ------------------------------------------------------------------------------------------ B200 arm
 def run_ours(args):
     import torch.distributed as dist
@@ -301,6 +375,9 @@ def run_ours(args):
                                 "sample": f"first {n} sentences of the shard in reference eval batches of {REF_BATCH}, beam {K}, "
                                           f"max_length {L}, oracle/vag_oracle.py (torch CPU fp32)",
                                 "token_exact_sentences": f"{agree}/{n}"}
+    del model
+    torch.cuda.empty_cache()
+    line["train"] = measure_train(args, dev, world, rank, timed)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -1,0 +1,77 @@
+"""2 GPUs (skipped with fewer): sentence-sharded decoding and data-parallel training equal the single-GPU results."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import vag_nmt_b200 as vag
+    from conftest import build_mm
+    from vag_nmt_b200 import synthetic
+    from vag_nmt_b200.optim import ClipAdam
+    from vag_nmt_b200.train import DistributedPairwiseRankingLoss
+    from vag_nmt_b200.translate import decode_corpus, decode_corpus_sharded
+    cfg = dict(synthetic.TINY)
+    model = build_mm(cfg, 7).cuda()
+    # ---- decoding: every rank decodes its slice, all ranks end with the full list
+    sents, im = synthetic.make_corpus(13, cfg["src_size"], cfg["im_feats_size"], seed=4, max_len=9, min_len=1, mean=5, std=2)
+    fn = lambda s, l, i, K, L: model.beamsearch_decode(s, l, i, beam_size=K, max_length=L)
+    sharded = decode_corpus_sharded(fn, sents, im, 4, 10)
+    single = decode_corpus(fn, sents, im, 4, 10)
+    # ---- training: global batch 8 split 4 + 4 must give the single-process gradients
+    batch = synthetic.make_batch(8, cfg["src_size"], cfg["tgt_size"], cfg["im_feats_size"], seed=5, max_len=9, min_len=2, mean=5, std=2.5)
+    w = torch.ones(cfg["tgt_size"], device="cuda")
+    w[0] = 0
+    crit = torch.nn.NLLLoss(weight=w, reduction="none")
+    model.train()
+    loss, _, _ = model(batch.src, batch.src_lengths, batch.tgt, batch.im, 1.0, criterion_mt=crit, criterion_vse=vag.PairwiseRankingLoss(margin=0.1))
+    loss.backward()
+    ref = {n: p.grad.clone() for n, p in model.named_parameters()}
+    for p in model.parameters():
+        p.grad = None
+    sl = slice(rank * 4, rank * 4 + 4)
+    lens = batch.src_lengths[sl]
+    src = batch.src[sl][:, :max(lens)]
+    loss_l, _, _ = model(src, lens, batch.tgt[sl], batch.im[sl], 1.0, criterion_mt=crit, criterion_vse=DistributedPairwiseRankingLoss(margin=0.1))
+    loss_l.backward()
+    opt = ClipAdam(model, lr=0.0)
+    from vag_nmt_b200.optim import allreduce_gradients
+    allreduce_gradients(list(model.parameters()))
+    worst = 0.0
+    for n, p in model.named_parameters():
+        scale = float(ref[n].abs().max())
+        if scale > 0:
+            worst = max(worst, float((p.grad - ref[n]).abs().max()) / scale)
+    torch.save(dict(decode_ok=sharded == single, n=len(sharded), worst=worst), os.path.join(out_dir, f"m{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_decode_sharding_and_data_parallel_gradients(tmp_path):
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        res = torch.load(tmp_path / f"m{r}.pt")
+        assert res["decode_ok"] and res["n"] == 13
+        assert res["worst"] < 1e-4, res["worst"]       # DP gradients == single-process gradients of the global batch

@@ -41,3 +41,31 @@ def test_two_rank_sharded_decode_equals_single(tmp_path):
     for r in range(2):
         res = torch.load(tmp_path / f"r{r}.pt")
         assert res["ok"] and res["n"] == 9
+
+
+def _grad_worker(rank, world, port, out_dir):
+    sys.path.insert(0, str(ROOT))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vag_nmt_b200.optim import allreduce_gradients
+    torch.manual_seed(0)
+    net = torch.nn.Linear(5, 3)
+    x = torch.arange(20, dtype=torch.float32).reshape(4, 5) / 10 + rank     # a different shard per rank
+    net(x).pow(2).sum().backward()
+    local = [p.grad.clone() for p in net.parameters()]
+    allreduce_gradients(list(net.parameters()))
+    torch.save(dict(local=local, avg=[p.grad.clone() for p in net.parameters()]), os.path.join(out_dir, f"g{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce_is_the_mean(tmp_path):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_grad_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = torch.load(tmp_path / "g0.pt"), torch.load(tmp_path / "g1.pt")
+    for a0, a1, l0, l1 in zip(r0["avg"], r1["avg"], r0["local"], r1["local"]):
+        assert torch.equal(a0, a1)                                   # every rank ends with the same gradient
+        assert torch.allclose(a0, (l0 + l1) / 2, atol=1e-6)          # … the mean of the per-rank gradients
