@@ -90,7 +90,7 @@ namespace vag {
 int tc_elem_bytes();
 int tc_split(const float* x, int64_t ldx, int rows, int K, void* hi, void* lo, int64_t ld_out, int64_t col_off, cudaStream_t st);
 int tc_gemm(float* y, int64_t ldy, const void* xh, const void* xl, int64_t ldxs, const void* wh, const void* wl, int64_t ldws,
-            const float* bias, int rows, int K, int N, int flags, cudaStream_t st);
+            const float* bias, int rows, int K, int N, int flags, cudaStream_t st, float4* summ, int* summ_tile_w);
 }
 
 extern "C" int vag_tc_elem_bytes(void) { return tc_elem_bytes(); }
@@ -110,7 +110,7 @@ extern "C" int vag_tc_gemm_f32(float* y, int64_t ldy, const void* x_hi, const vo
     VAG_REQUIRE(y && x_hi && x_lo && w_hi && w_lo, "vag_tc_gemm_f32: null pointer");
     VAG_REQUIRE(rows > 0 && in_dim >= 32 && in_dim % 8 == 0 && out_dim > 0 && ldx % 8 == 0 && ldw % 8 == 0 && ldy >= out_dim,
                 "vag_tc_gemm_f32: bad shape");
-    return tc_gemm(y, ldy, x_hi, x_lo, ldx, w_hi, w_lo, ldw, bias, rows, in_dim, out_dim, flags, (cudaStream_t)stream);
+    return tc_gemm(y, ldy, x_hi, x_lo, ldx, w_hi, w_lo, ldw, bias, rows, in_dim, out_dim, flags, (cudaStream_t)stream, nullptr, nullptr);
 }
 
 extern "C" size_t vag_linear_tc_workspace_bytes(int rows, int in_dim, int out_dim) {

@@ -348,6 +348,160 @@ beam_select_fast_kernel(const float* __restrict__ logits, int64_t ld, int subtra
     if (tid == 0 && fin_counter) atomicAdd(fin_counter, n_eos);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Selection from the projection epilogue's summaries: the tensor-core kernel that produced the logits also left,
+// per (row, column tile of width tile_w), the tile's running max, Σexp(x − max) and arg-max (lowest column on
+// ties).  One CTA per sentence combines the tiles' (max, Σexp) into the row log-sum-exps, turns every tile's
+// arg-max into a score and pops the K winners with K block arg-max rounds; after each pop ONE warp rescans the
+// winner's tile in the logits (tile_w floats, L2-resident) for its next-best element, so the result is exactly
+// what a scan of all K·V logits gives while only ~K tiles per sentence are ever re-read.
+// ---------------------------------------------------------------------------------------------------------
+template <int KMAX>
+__global__ void __launch_bounds__(256)
+beam_select_summary_kernel(const float4* __restrict__ summ, int n_tiles, int tile_w, const float* __restrict__ logits, int64_t ld,
+                           const int64_t* __restrict__ prev_tokens, float* __restrict__ nll, int64_t* __restrict__ tokens_out,
+                           int32_t* __restrict__ parents_out, int K, int V, int step, int avoid_double,
+                           const int* __restrict__ done, int* __restrict__ fin_counter) {
+    if (done && *done) return;
+    extern __shared__ float dyn[];
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int Kin = step == 0 ? 1 : K;
+    const int n_sl = Kin * n_tiles;
+    float* sl_v = dyn;                                   // [Kin·n_tiles] score of the slice's best remaining element
+    int* sl_i = reinterpret_cast<int*>(dyn + n_sl);      // its token (0x7fffffff: exhausted)
+    __shared__ float nll_s[KMAX], lse_s[KMAX];
+    __shared__ int cur_s[KMAX];
+    __shared__ float red_a[8];
+    __shared__ int red_i[8], red_t[8];
+    __shared__ int win_sl, win_tok;
+    constexpr float kL2e = 1.4426950408889634f;
+
+    if (tid < Kin) {
+        nll_s[tid] = step == 0 ? 0.f : nll[(int64_t)b * K + tid];
+        cur_s[tid] = step == 0 ? -1 : (int)prev_tokens[(int64_t)b * K + tid];
+    }
+    __syncthreads();
+    // ---- row log-sum-exps from the tile summaries (one warp per row)
+    for (int k = wid; k < Kin; k += 8) {
+        const float4* sr = summ + (int64_t)(b * Kin + k) * n_tiles;
+        float m = -INFINITY;
+        for (int t = lane; t < n_tiles; t += 32) m = fmaxf(m, sr[t].x);
+        m = warp_max(m);
+        float s = 0.f;
+        for (int t = lane; t < n_tiles; t += 32) s += sr[t].y * exp2f((sr[t].x - m) * kL2e);
+        s = warp_sum(s);
+        if (lane == 0) lse_s[k] = (step > 0 && cur_s[k] == kEOS) ? 0.f : m + logf(s);
+    }
+    __syncthreads();
+
+    // best element of tile `tile` of row k strictly after (pv, pi) in canonical order, skipping `skip`; warp-cooperative
+    auto tile_next = [&](int k, int tile, int skip, float pv, int pi, float& bv, int& bi) {
+        const float* row = logits + (int64_t)(b * Kin + k) * ld;
+        const int c_lo = tile * tile_w, c_hi = min(V, c_lo + tile_w);
+        bv = -INFINITY;
+        bi = 0x7fffffff;
+        for (int c = c_lo + lane; c < c_hi; c += 32) {
+            const float x = row[c];
+            if (c != skip && cand_better(pv, pi, x, c) && cand_better(x, c, bv, bi)) { bv = x; bi = c; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+        }
+    };
+
+    // ---- slice scores
+    for (int idx = tid; idx < n_sl; idx += 256) {
+        const int k = idx / n_tiles, tile = idx - k * n_tiles;
+        float sc = -INFINITY;
+        int tok = 0x7fffffff;
+        if (step > 0 && cur_s[k] == kEOS) {              // finished hypothesis: one candidate, <eos> at +0 (V11:291-294)
+            if (tile == 0) { sc = nll_s[k] + 0.f; tok = kEOS; }
+        } else {
+            const float4 e = summ[(int64_t)(b * Kin + k) * n_tiles + tile];
+            tok = __float_as_int(e.w);
+            const float lp = e.z - lse_s[k];
+            sc = step == 0 ? lp : nll_s[k] + lp;        // V11:297
+        }
+        sl_v[idx] = sc;
+        sl_i[idx] = tok;
+    }
+    __syncthreads();
+    // the repeated token may not be chosen (V11:279-280): where it is a tile's arg-max, replace it by the runner-up
+    if (avoid_double && step > 0) {
+        for (int k = wid; k < Kin; k += 8) {
+            const int cur = cur_s[k];
+            if (cur == kEOS || cur < 0 || cur >= V) continue;
+            const int tile = cur / tile_w;
+            const int idx = k * n_tiles + tile;
+            if (sl_i[idx] == cur) {
+                float nv; int ni;
+                tile_next(k, tile, cur, INFINITY, -1, nv, ni);
+                if (lane == 0) {
+                    sl_i[idx] = ni;
+                    sl_v[idx] = ni == 0x7fffffff ? -INFINITY : nll_s[k] + (nv - lse_s[k]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- K rounds of block arg-max + one-tile refill
+    int n_eos = 0;
+    for (int round = 0; round < K; ++round) {
+        float bv = -INFINITY;
+        int bi = 0x7fffffff, bs = -1;                    // bi = flat index k·V + token
+        for (int idx = tid; idx < n_sl; idx += 256) {
+            const int tok = sl_i[idx];
+            if (tok != 0x7fffffff) {
+                const int flat = (idx / n_tiles) * V + tok;
+                if (cand_better(sl_v[idx], flat, bv, bi)) { bv = sl_v[idx]; bi = flat; bs = idx; }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            const int os = __shfl_xor_sync(0xffffffffu, bs, o);
+            if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; bs = os; }
+        }
+        if (lane == 0) { red_a[wid] = bv; red_i[wid] = bi; red_t[wid] = bs; }
+        __syncthreads();
+        if (tid == 0) {
+            float fv = red_a[0];
+            int fi = red_i[0], fs = red_t[0];
+            for (int w = 1; w < 8; ++w)
+                if (cand_better(red_a[w], red_i[w], fv, fi)) { fv = red_a[w]; fi = red_i[w]; fs = red_t[w]; }
+            const int par = fi / V, tok = fi - par * V;
+            win_sl = fs; win_tok = tok;
+            nll[(int64_t)b * K + round] = fv;
+            tokens_out[(int64_t)b * K + round] = tok;
+            parents_out[(int64_t)b * K + round] = par;
+            n_eos += (tok == kEOS);
+        }
+        __syncthreads();
+        if (wid == 0 && round + 1 < K) {                 // refill the winner's tile
+            const int idx = win_sl, k = idx / n_tiles, tile = idx - k * n_tiles;
+            const int cur = cur_s[k];
+            float nv = -INFINITY;
+            int ni = 0x7fffffff;
+            if (!(step > 0 && cur == kEOS)) {
+                const float* row = logits + (int64_t)(b * Kin + k) * ld;
+                tile_next(k, tile, (avoid_double && step > 0) ? cur : -1, row[win_tok], win_tok, nv, ni);
+            }
+            if (lane == 0) {
+                sl_i[idx] = ni;
+                sl_v[idx] = ni == 0x7fffffff ? -INFINITY : (step == 0 ? nv - lse_s[k] : nll_s[k] + (nv - lse_s[k]));
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && fin_counter) atomicAdd(fin_counter, n_eos);
+}
+
 // Row gather by parent + early-stop bookkeeping.
 //   h_next[b*K + k, :] = h_cur[b*Kin + parents[b,k], :]
 // Block (0,0) thread 0 also turns the per-step EOS counter into the `done` flag / steps_run the way the
@@ -486,6 +640,28 @@ int beam_select(const float* logits, int64_t ld, const float* lse, const int64_t
     else if (K <= 12) VAG_SELECT(12);
     else VAG_SELECT(16);
 #undef VAG_SELECT
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
+int beam_select_summary(const float4* summ, int tile_w, const float* logits, int64_t ld, const int64_t* prev_tokens, float* nll,
+                        int64_t* tokens_out, int32_t* parents_out, int B, int K, int64_t V, int step, int avoid_double,
+                        const int* done, int* fin_counter, cudaStream_t st) {
+    if (K > kMaxBeam || (int64_t)K * V >= 0x7fffffff || V <= K + 1) {
+        set_error("beam_select_summary: unsupported K=%d V=%lld", K, (long long)V);
+        return VAG_ERR_UNSUPPORTED;
+    }
+    const int n_tiles = (int)((V + tile_w - 1) / tile_w);
+    const int Kin = step == 0 ? 1 : K;
+    const size_t smem = (size_t)Kin * n_tiles * 8;
+#define VAG_SELS(KM)                                                                                                          \
+    beam_select_summary_kernel<KM><<<B, 256, smem, st>>>(summ, n_tiles, tile_w, logits, ld, prev_tokens, nll, tokens_out,      \
+                                                         parents_out, K, (int)V, step, avoid_double, done, fin_counter)
+    if (K <= 4) VAG_SELS(4);
+    else if (K <= 8) VAG_SELS(8);
+    else if (K <= 12) VAG_SELS(12);
+    else VAG_SELS(16);
+#undef VAG_SELS
     VAG_LAUNCH_CHECK();
     return VAG_OK;
 }

@@ -13,6 +13,9 @@ int row_lse(float* lse_out, const float* logits, int64_t ld, int rows, int64_t V
 int beam_select(const float* logits, int64_t ld, const float* lse, const int64_t* prev_tokens, float* nll,
                 int64_t* tokens_out, int32_t* parents_out, int B, int K, int64_t V, int step, int avoid_double,
                 const int* done, int* fin_counter, cudaStream_t st);
+int beam_select_summary(const float4* summ, int tile_w, const float* logits, int64_t ld, const int64_t* prev_tokens, float* nll,
+                        int64_t* tokens_out, int32_t* parents_out, int B, int K, int64_t V, int step, int avoid_double,
+                        const int* done, int* fin_counter, cudaStream_t st);
 int beam_advance(float* h_next, const float* h_cur, const int32_t* parents, int B, int K, int Kin, int H, int step,
                  int* done, int* fin_counter, int* steps_run, cudaStream_t st);
 int beam_finalize(const int64_t* tok_hist, const int32_t* par_hist, const float* nll, const int* steps_run, int B, int K,
@@ -259,7 +262,8 @@ static void step_layout(A& a, int rows, int E, int H, int C, int64_t V, StepWs* 
 // One conditional-GRU step up to (and including) the vocabulary logits.  NMT_Decoder.py:109-143.
 static int decoder_step_core(GemmCtx& gemm, const vag_decoder_weights* w, const StepWs& ws, const int64_t* tokens, const float* h_prev,
                              const float* keys, const float* ctx, const float* mask, int rows, int rows_per_sent, int T,
-                             float* h_out, float* logits, int64_t ld_logits, float* alpha_out, cudaStream_t st) {
+                             float* h_out, float* logits, int64_t ld_logits, float* alpha_out, cudaStream_t st,
+                             float4* summ = nullptr, int* summ_tile_w = nullptr) {
     const int E = w->E, H = w->H, C = w->C;
     const int64_t V = w->V;
     vag_stream_t vs = (vag_stream_t)st;
@@ -284,7 +288,7 @@ static int decoder_step_core(GemmCtx& gemm, const vag_decoder_weights* w, const 
         const float* const bs[3] = {w->w1_b, w->w3_b, w->w2_b};
         VAG_TRY(gemm.linear3(ws.t, E, xs, lds, Ks, wts, lds, bs, rows, E, VAG_LIN_TANH));
     }
-    if (logits) VAG_TRY(gemm.linear(logits, ld_logits, ws.t, E, w->out_w, E, w->out_b, rows, E, (int)V, 0));            // :143
+    if (logits) VAG_TRY(gemm.linear(logits, ld_logits, ws.t, E, w->out_w, E, w->out_b, rows, E, (int)V, 0, summ, summ_tile_w));            // :143
     return VAG_OK;
 }
 }  // namespace vag
@@ -321,6 +325,7 @@ namespace vag {
 struct BeamWs {
     StepWs step;
     float *logits, *lse, *h_a, *h_b, *nll;
+    float4* summ;
     int64_t *tok_hist, *sos;
     int32_t* par_hist;
     int* flags;  // [0] done, [1] steps_run, [2..2+L) per-step EOS counters
@@ -332,6 +337,7 @@ static void beam_layout(A& a, int B, int K, int L, int E, int H, int C, int64_t 
     step_layout(a, N, E, H, C, V, &sw);
     float* logits = (float*)a.template take<float>((size_t)N * ((V + 3) / 4 * 4));  // rows padded to 16 B
     float* lse = (float*)a.template take<float>((size_t)N);
+    float4* summ = (float4*)a.template take<float4>((size_t)N * ((V + 127) / 128));
     float* h_a = (float*)a.template take<float>((size_t)N * H);
     float* h_b = (float*)a.template take<float>((size_t)N * H);
     float* nll = (float*)a.template take<float>((size_t)N);
@@ -340,7 +346,7 @@ static void beam_layout(A& a, int B, int K, int L, int E, int H, int C, int64_t 
     int32_t* par_hist = (int32_t*)a.template take<int32_t>((size_t)L * N);
     int* flags = (int*)a.template take<int>((size_t)L + 2);
     if (ws) {
-        ws->step = sw; ws->logits = logits; ws->lse = lse; ws->h_a = h_a; ws->h_b = h_b; ws->nll = nll;
+        ws->step = sw; ws->logits = logits; ws->lse = lse; ws->summ = summ; ws->h_a = h_a; ws->h_b = h_b; ws->nll = nll;
         ws->tok_hist = tok_hist; ws->sos = sos; ws->par_hist = par_hist; ws->flags = flags;
     }
 }
@@ -384,11 +390,19 @@ extern "C" int vag_beam_decode_f32(const vag_decoder_weights* w, const float* h0
         const int rps = di == 0 ? 1 : K;
         const int64_t* tokens = di == 0 ? ws.sos : ws.tok_hist + (size_t)(di - 1) * N;
         const float* h_prev = di == 0 ? h0 : ws.h_a;
-        VAG_TRY(decoder_step_core(gemm, w, ws.step, tokens, h_prev, keys, ctx, mask, rows, rps, T, ws.h_b, ws.logits, ldl, nullptr, st));
-        const bool fused_lse = V >= 512;  // the fast selection kernel folds the log-sum-exp into its single pass
-        if (!fused_lse) VAG_TRY(row_lse(ws.lse, ws.logits, ldl, rows, V, st));
-        VAG_TRY(beam_select(ws.logits, ldl, ws.lse, di == 0 ? nullptr : tokens, ws.nll, ws.tok_hist + (size_t)di * N,
-                            ws.par_hist + (size_t)di * N, B, K, V, di, avoid_double, done, fin + di, st));
+        int tile_w = 0;  // > 0 when the tensor-core projection also produced the per-tile soft-max / arg-max summaries
+        VAG_TRY(decoder_step_core(gemm, w, ws.step, tokens, h_prev, keys, ctx, mask, rows, rps, T, ws.h_b, ws.logits, ldl, nullptr, st,
+                                  V >= 512 ? ws.summ : nullptr, &tile_w));
+        if (tile_w > 0) {
+            VAG_TRY(beam_select_summary(ws.summ, tile_w, ws.logits, ldl, di == 0 ? nullptr : tokens, ws.nll,
+                                        ws.tok_hist + (size_t)di * N, ws.par_hist + (size_t)di * N, B, K, V, di, avoid_double, done,
+                                        fin + di, st));
+        } else {
+            const bool fused_lse = V >= 512;  // the fast scan kernel folds the log-sum-exp into its single pass
+            if (!fused_lse) VAG_TRY(row_lse(ws.lse, ws.logits, ldl, rows, V, st));
+            VAG_TRY(beam_select(ws.logits, ldl, ws.lse, di == 0 ? nullptr : tokens, ws.nll, ws.tok_hist + (size_t)di * N,
+                                ws.par_hist + (size_t)di * N, B, K, V, di, avoid_double, done, fin + di, st));
+        }
         VAG_TRY(beam_advance(ws.h_a, ws.h_b, ws.par_hist + (size_t)di * N, B, K, rps, H, di, done, fin + di, steps_run, st));
     }
     VAG_TRY(beam_finalize(ws.tok_hist, ws.par_hist, ws.nll, steps_run, B, K, L, hyp_out, hyp_len, beam_out, st));

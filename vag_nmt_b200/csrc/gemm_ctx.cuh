@@ -15,7 +15,7 @@ int linear_simt(float* y, int64_t ldy, const float* x, int64_t ldx, const float*
 int tc_elem_bytes();
 int tc_split(const float* x, int64_t ldx, int rows, int K, void* hi, void* lo, int64_t ld_out, int64_t col_off, cudaStream_t st);
 int tc_gemm(float* y, int64_t ldy, const void* xh, const void* xl, int64_t ldxs, const void* wh, const void* wl, int64_t ldws,
-            const float* bias, int rows, int K, int N, int flags, cudaStream_t st);
+            const float* bias, int rows, int K, int N, int flags, cudaStream_t st, float4* summ, int* summ_tile_w);
 bool tc_enabled();
 int bias_sum3(float* out, const float* a, const float* b, const float* c, int n, cudaStream_t st);
 
@@ -72,15 +72,19 @@ struct GemmCtx {
         return &tab[n++];
     }
 
+    // summ / summ_tile_w: optional per-(row, column-tile) soft-max / arg-max summary written by the tensor-core
+    // epilogue (see tc_gemm); *summ_tile_w stays 0 when the FP32 FFMA kernel ran and no summary exists.
     int linear(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, int rows,
-               int K, int N, int flags) {
+               int K, int N, int flags, float4* summ = nullptr, int* summ_tile_w = nullptr) {
+        if (summ_tile_w) *summ_tile_w = 0;
         if (rows == 0 || N == 0) return VAG_OK;
         if (tc && shape_ok(rows, K, N) && ptr_ok(x, ldx) && ptr_ok(w, ldw)) {
             Ent* we = lookup(wc, nw, w, N, K);
             if (!we && (we = make(true, w, N, K))) VAG_TRY(tc_split(w, ldw, N, K, we->hi, we->lo, K, 0, st));
             Ent* xe = we ? lookup(ac, na, x, rows, K) : nullptr;
             if (we && !xe && (xe = make(false, x, rows, K))) VAG_TRY(tc_split(x, ldx, rows, K, xe->hi, xe->lo, K, 0, st));
-            if (we && xe) return tc_gemm(y, ldy, xe->hi, xe->lo, xe->ld, we->hi, we->lo, we->ld, bias, rows, K, N, flags, st);
+            if (we && xe)
+                return tc_gemm(y, ldy, xe->hi, xe->lo, xe->ld, we->hi, we->lo, we->ld, bias, rows, K, N, flags, st, summ, summ_tile_w);
         }
         return linear_simt(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags, st);
     }
@@ -121,7 +125,7 @@ struct GemmCtx {
                     VAG_TRY(tc_split(x[i], ldx[i], rows, K[i], xe->hi, xe->lo, Kt, off, st));
                     off += K[i];
                 }
-                return tc_gemm(y, ldy, xe->hi, xe->lo, Kt, we->hi, we->lo, Kt, bsum, rows, Kt, N, flags, st);
+                return tc_gemm(y, ldy, xe->hi, xe->lo, Kt, we->hi, we->lo, Kt, bsum, rows, Kt, N, flags, st, nullptr, nullptr);
             }
         }
         // FP32 FFMA path: three accumulating contractions, summed left to right like the reference

@@ -164,7 +164,8 @@ template <int BN, bool F16, int ROWB>
 __global__ void __launch_bounds__(192, (ROWB == 64 ? 2 : 1))
 linear_split3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                      const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
-                     float* __restrict__ y, int64_t ldy, const float* __restrict__ bias, int rows, int K, int N, int flags) {
+                     float* __restrict__ y, int64_t ldy, const float* __restrict__ bias, int rows, int K, int N, int flags,
+                     float4* __restrict__ summ) {
     using Cfg = TcCfg<BN, F16, ROWB>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -244,6 +245,13 @@ linear_split3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_co
         mbar_wait(tmem_full_bar, 0);
         tcgen05_fence_after();
         const bool do_tanh = flags & VAG_LIN_TANH, do_acc = flags & VAG_LIN_ACCUMULATE;
+        // the bias slice of this tile, staged once (the pipeline stages are idle now); epilogue warps only
+        float* bias_s = reinterpret_cast<float*>(smem) + 4 * (32 * 33);
+        for (int c = threadIdx.x - 64; c < BN; c += 128) bias_s[c] = (bias && n0 + c < N) ? bias[n0 + c] : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // optional per-(row, tile) summary for the fused beam selection: running max, Σexp(x - max), arg-max
+        float sm_m = -INFINITY, sm_s = 0.f, sm_bv = -INFINITY;
+        int sm_bi = 0x7fffffff;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             if (n0 + c0 >= N) break;  // warp-uniform
@@ -272,7 +280,26 @@ linear_split3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_co
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-                r[j] = __float_as_uint(__uint_as_float(r[j]) + (F16 ? __uint_as_float(q[j]) * (1.0f / 2048.0f) : __uint_as_float(q[j])));
+                r[j] = __float_as_uint((__uint_as_float(r[j]) + (F16 ? __uint_as_float(q[j]) * (1.0f / 2048.0f) : __uint_as_float(q[j]))) +
+                                       bias_s[c0 + j]);
+            if (summ) {
+                constexpr float kL2e = 1.4426950408889634f;
+                const int n_valid = min(32, N - (n0 + c0));   // ≥ 1 here
+                float cm = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) cm = fmaxf(cm, j < n_valid ? __uint_as_float(r[j]) : -INFINITY);
+                if (cm > sm_m) { sm_s *= exp2f((sm_m - cm) * kL2e); sm_m = cm; }
+                const float m2 = sm_m * kL2e;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sm_s += j < n_valid ? exp2f(fmaf(__uint_as_float(r[j]), kL2e, -m2)) : 0.f;
+                if (cm > sm_bv) {   // strictly greater: on ties the lower column (earlier chunk) wins
+                    sm_bv = cm;
+                    int first = 31;
+#pragma unroll
+                    for (int j = 31; j >= 0; --j) if (j < n_valid && __uint_as_float(r[j]) == cm) first = j;
+                    sm_bi = n0 + c0 + first;
+                }
+            }
             // transpose through shared memory (the pipeline stages are idle now) so that every store instruction
             // writes 32 consecutive floats of ONE output row instead of one float in each of 32 rows
             float* tile = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);
@@ -282,17 +309,20 @@ linear_split3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_co
             __syncwarp();
             const int col = n0 + c0 + lane;
             if (col < N) {
-                const float bv = bias ? bias[col] : 0.f;
                 const int r_lim = min(32, rows - (m0 + lg * 32));
                 float* dst = y + (int64_t)(m0 + lg * 32) * ldy + col;
 #pragma unroll 4
                 for (int rr = 0; rr < r_lim; ++rr) {
-                    float v = tile[rr * 33 + lane] + bv;
+                    float v = tile[rr * 33 + lane];
                     if (do_acc) v = dst[(int64_t)rr * ldy] + v;
                     if (do_tanh) v = tanhf(v);
                     dst[(int64_t)rr * ldy] = v;
                 }
             }
+        }
+        if (summ) {
+            const int row = m0 + lg * 32 + lane;
+            if (row < rows) summ[(int64_t)row * gridDim.x + blockIdx.x] = make_float4(sm_m, sm_s, sm_bv, __int_as_float(sm_bi));
         }
     }
     tcgen05_fence_before();
@@ -300,6 +330,239 @@ linear_split3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_co
     if (warp == 1) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------ persistent kernel
+// One CTA per SM walks a static round-robin list of 128 x 128 output tiles (column index fastest, so the CTAs that
+// run together share an A row block through L2).  Ten warps, three roles that never join until the end:
+//   warp 0      TMA producer — runs AHEAD across tile boundaries through a PSTAGES-deep ring (64-byte K rows);
+//   warp 1      MMA issuer — two TMEM accumulator buffers (main | cross each) alternate between tiles;
+//   warps 2-9   epilogue — drains buffer a while the MMA warp already fills buffer a^1: tcgen05.ld → (+bias, tanh,
+//               optional soft-max / arg-max summary) → 128-byte-swizzled shared tile → TMA store (no per-row stores).
+// Synchronisation is mbarrier-only: full/empty per ring slot, tmem_full/tmem_empty per accumulator buffer.
+constexpr int PSTAGES = 5;
+constexpr int P_STAGE_BYTES = 4 * 128 * 64;          // A_hi, A_lo, B_hi, B_lo: 128 rows x 64 B each = 32 KB
+constexpr int P_EPI_BYTES = 8 * 4096;                // one 32 x 32 fp32 staging tile per epilogue warp
+constexpr int P_SMEM_BYTES = PSTAGES * P_STAGE_BYTES + P_EPI_BYTES + 512 /*bias*/ + 2048 /*summary exchange*/ + 256 /*barriers*/ + 1024;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+
+template <bool F16>
+__global__ void __launch_bounds__(320, 1)
+linear_split3_persistent_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
+                                const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
+                                const __grid_constant__ CUtensorMap map_y, const float* __restrict__ bias, int rows, int K, int N,
+                                int flags, float4* __restrict__ summ) {
+    constexpr int BM = 128, BN = 128, ELT = F16 ? 2 : 4, BK = 64 / ELT, UK = 32 / ELT;
+    constexpr uint32_t FMT = F16 ? 0u : 2u;
+    constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    constexpr int T_BYTES = 128 * 64;  // one operand tile
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* epi = smem + PSTAGES * P_STAGE_BYTES;                       // 8 x 4 KB, 1024-B aligned
+    float* bias_s = reinterpret_cast<float*>(epi + P_EPI_BYTES);         // [128]
+    float4* xch = reinterpret_cast<float4*>(epi + P_EPI_BYTES + 512);    // [128] partial summaries of the right column half
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi + P_EPI_BYTES + 512 + 2048);
+    uint64_t* empty_bar = full_bar + PSTAGES;
+    uint64_t* tfull_bar = empty_bar + PSTAGES;   // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;        // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_n = (N + BN - 1) / BN, tiles_m = (rows + BM - 1) / BM;
+    const int n_tiles = tiles_n * tiles_m;
+    const int n_kb = (K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_xh) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_xl) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wh) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wl) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y) : "memory");
+        for (int s = 0; s < PSTAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t g = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+                for (int kb = 0; kb < n_kb; ++kb, ++g) {
+                    const int s = g % PSTAGES;
+                    mbar_wait(&empty_bar[s], ((g / PSTAGES) & 1) ^ 1);
+                    uint8_t* st = smem + s * P_STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[s], P_STAGE_BYTES);
+                    const int k0 = kb * BK;
+                    tma_load_2d(st, &map_xh, &full_bar[s], k0, m0);
+                    tma_load_2d(st + T_BYTES, &map_xl, &full_bar[s], k0, m0);
+                    tma_load_2d(st + 2 * T_BYTES, &map_wh, &full_bar[s], k0, n0);
+                    tma_load_2d(st + 3 * T_BYTES, &map_wl, &full_bar[s], k0, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t g = 0, it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const uint32_t a = it & 1;
+                mbar_wait(&tempty_bar[a], ((it >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator buffer
+                tcgen05_fence_after();
+                const uint32_t d_main = tmem_base + a * 256, d_cross = d_main + 128;
+                for (int kb = 0; kb < n_kb; ++kb, ++g) {
+                    const int s = g % PSTAGES;
+                    mbar_wait(&full_bar[s], (g / PSTAGES) & 1);
+                    tcgen05_fence_after();
+                    const uint32_t st = smem_u32(smem + s * P_STAGE_BYTES);
+                    const uint64_t d_ah = make_smem_desc<64>(st), d_al = make_smem_desc<64>(st + T_BYTES);
+                    const uint64_t d_bh = make_smem_desc<64>(st + 2 * T_BYTES), d_bl = make_smem_desc<64>(st + 3 * T_BYTES);
+#pragma unroll
+                    for (int j = 0; j < BK / UK; ++j) {
+                        const uint64_t adv = (uint64_t)((j * 32) >> 4);
+                        umma<F16>(d_cross, d_al + adv, d_bh + adv, IDESC, (kb | j) != 0);
+                        umma<F16>(d_cross, d_ah + adv, d_bl + adv, IDESC, 1);
+                        umma<F16>(d_main, d_ah + adv, d_bh + adv, IDESC, (kb | j) != 0);
+                    }
+                    tcgen05_commit(&empty_bar[s]);
+                }
+                tcgen05_commit(&tfull_bar[a]);
+            }
+        }
+    } else {
+        // ---- epilogue warps 2..9: TMEM lane group lg = warp % 4, column half ch (64 columns = two 32-wide chunks)
+        const int ew = warp - 2, lg = warp & 3, ch = ew >> 2;
+        uint8_t* my_tile = epi + ew * 4096;
+        const bool do_tanh = flags & VAG_LIN_TANH;
+        constexpr float kL2e = 1.4426950408889634f;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+            const int tn = tile % tiles_n;
+            const uint32_t a = it & 1;
+            // stage this tile's bias slice: first make sure every epilogue warp has finished reading the previous one
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (ew < 4) {
+                const int c = ew * 32 + lane;
+                bias_s[c] = (bias && n0 + c < N) ? bias[n0 + c] : 0.f;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            mbar_wait(&tfull_bar[a], (it >> 1) & 1);
+            tcgen05_fence_after();
+            float sm_m = -INFINITY, sm_s = 0.f, sm_bv = -INFINITY;
+            int sm_bi = 0x7fffffff;
+#pragma unroll 1
+            for (int cc = 0; cc < 2; ++cc) {
+                const int c0 = ch * 64 + cc * 32;
+                if (n0 + c0 >= N) break;  // warp-uniform: this chunk lies entirely outside the matrix
+                uint32_t r[32], q[32];
+                const uint32_t taddr = tmem_base + a * 256 + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
+                      "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15]), "=r"(q[16]),
+                      "=r"(q[17]), "=r"(q[18]), "=r"(q[19]), "=r"(q[20]), "=r"(q[21]), "=r"(q[22]), "=r"(q[23]), "=r"(q[24]),
+                      "=r"(q[25]), "=r"(q[26]), "=r"(q[27]), "=r"(q[28]), "=r"(q[29]), "=r"(q[30]), "=r"(q[31])
+                    : "r"(taddr + 128u)
+                    : "memory");
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                      "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                      "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr)
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (cc == 1 || n0 + c0 + 32 >= N) {
+                    // all TMEM reads of this warp for this tile are complete: hand the buffer back to the MMA warp early
+                    tcgen05_fence_before();
+                    if (lane == 0) mbar_arrive(&tempty_bar[a]);
+                }
+                float x[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    x[j] = (__uint_as_float(r[j]) + (F16 ? __uint_as_float(q[j]) * (1.0f / 2048.0f) : __uint_as_float(q[j]))) + bias_s[c0 + j];
+                    if (do_tanh) x[j] = tanhf(x[j]);
+                }
+                if (summ) {
+                    const int n_valid = min(32, N - (n0 + c0));
+                    float cm = -INFINITY;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) cm = fmaxf(cm, j < n_valid ? x[j] : -INFINITY);
+                    if (cm > sm_m) { sm_s *= exp2f((sm_m - cm) * kL2e); sm_m = cm; }
+                    const float m2 = sm_m * kL2e;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sm_s += j < n_valid ? exp2f(fmaf(x[j], kL2e, -m2)) : 0.f;
+                    if (cm > sm_bv) {
+                        sm_bv = cm;
+                        int first = 31;
+#pragma unroll
+                        for (int j = 31; j >= 0; --j) if (j < n_valid && x[j] == cm) first = j;
+                        sm_bi = n0 + c0 + first;
+                    }
+                }
+                // registers → 128-byte-swizzled staging tile (row = lane, 16-byte chunk index XOR row%8) → TMA store
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous store has finished reading the tile
+                __syncwarp();
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    float4 v = make_float4(x[4 * c4], x[4 * c4 + 1], x[4 * c4 + 2], x[4 * c4 + 3]);
+                    *reinterpret_cast<float4*>(my_tile + lane * 128 + ((c4 ^ (lane & 7)) << 4)) = v;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&map_y, my_tile, n0 + c0, m0 + lg * 32);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+            if (n0 + ch * 64 >= N) {   // this warp had no chunk at all in this tile: it still owes the arrival
+                tcgen05_fence_before();
+                if (lane == 0) mbar_arrive(&tempty_bar[a]);
+            }
+            if (summ) {   // combine the two column halves of every row and write the (row, tile) summary
+                const int rl = lg * 32 + lane;
+                if (ch == 1) xch[rl] = make_float4(sm_m, sm_s, sm_bv, __int_as_float(sm_bi));
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                if (ch == 0) {
+                    const float4 o = xch[rl];
+                    float m = sm_m, s_ = sm_s, bv = sm_bv;
+                    int bi = sm_bi;
+                    if (o.x > m) { s_ = s_ * exp2f((m - o.x) * kL2e) + o.y; m = o.x; }
+                    else if (o.x != -INFINITY) s_ += o.y * exp2f((o.x - m) * kL2e);
+                    if (o.z > bv) { bv = o.z; bi = __float_as_int(o.w); }   // strictly greater: the left half wins ties
+                    const int row = m0 + rl;
+                    if (row < rows) summ[(int64_t)row * tiles_n + tn] = make_float4(m, s_, bv, __int_as_float(bi));
+                }
+            }
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -342,6 +605,26 @@ static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t K, i
     return VAG_OK;
 }
 
+// fp32 output [rows, N] (pitch ldy), box {32, 32}, SWIZZLE_128B: the epilogue's staging tiles are stored with TMA
+static int make_out_map(CUtensorMap* m, float* y, int64_t rows, int64_t N, int64_t ldy) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled entry point not available");
+        return VAG_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ldy * sizeof(float)};
+    cuuint32_t box[2] = {32u, 32u};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (output) failed with %d (rows=%lld N=%lld ldy=%lld)", (int)r, (long long)rows, (long long)N, (long long)ldy);
+        return VAG_ERR_CUDA;
+    }
+    return VAG_OK;
+}
+
 size_t linear_tc_scratch_bytes(int64_t rows, int64_t K, int64_t N) {
     return (size_t)(2 * rows * K + 2 * N * K) * sizeof(float) + 4 * 256;
 }
@@ -354,7 +637,7 @@ bool linear_tc_eligible(const float* y, int64_t ldy, const float* x, int64_t ldx
 
 template <int BN, bool F16, int ROWB>
 static int launch_tc(const CUtensorMap& xh, const CUtensorMap& xl, const CUtensorMap& wh, const CUtensorMap& wl, float* y,
-                     int64_t ldy, const float* bias, int rows, int K, int N, int flags, cudaStream_t st) {
+                     int64_t ldy, const float* bias, int rows, int K, int N, int flags, float4* summ, cudaStream_t st) {
     using Cfg = TcCfg<BN, F16, ROWB>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -362,7 +645,7 @@ static int launch_tc(const CUtensorMap& xh, const CUtensorMap& xl, const CUtenso
         attr_set = true;
     }
     dim3 grid(ceil_div(N, BN), ceil_div(rows, Cfg::BM));
-    linear_split3_kernel<BN, F16, ROWB><<<grid, 192, Cfg::SMEM_BYTES, st>>>(xh, xl, wh, wl, y, ldy, bias, rows, K, N, flags);
+    linear_split3_kernel<BN, F16, ROWB><<<grid, 192, Cfg::SMEM_BYTES, st>>>(xh, xl, wh, wl, y, ldy, bias, rows, K, N, flags, summ);
     VAG_LAUNCH_CHECK();
     return VAG_OK;
 }
@@ -390,13 +673,44 @@ int tc_split(const float* x, int64_t ldx, int rows, int K, void* hi, void* lo, i
 }
 
 // The tcgen05 contraction on pre-split operands: xh/xl [rows, K] pitch ldxs, wh/wl [N, K] pitch ldws (elements).
+// summ (optional): [rows, ceil(N / tile_w)] float4 (max, Σexp(x-max), best value, best column as int bits) per
+// (row, column tile); *summ_tile_w receives the tile width the chosen configuration uses.
 int tc_gemm(float* y, int64_t ldy, const void* xh, const void* xl, int64_t ldxs, const void* wh, const void* wl, int64_t ldws,
-            const float* bias, int rows, int K, int N, int flags, cudaStream_t st) {
+            const float* bias, int rows, int K, int N, int flags, cudaStream_t st, float4* summ, int* summ_tile_w) {
     const bool f16 = use_f16_split();
     const int sms = num_sms();
-    // tile configuration: VAG_TC_CFG=wide|narrow|dual overrides the heuristic (tuning / A-B runs)
-    int cfg;  // 0 = 128x256 wide, 1 = 128x128 (128 B rows), 2 = 128x128 dual-CTA (64 B rows)
     const char* e = getenv("VAG_TC_CFG");
+    // Persistent kernel (default): needs a TMA-storable output (16-byte aligned rows) and no read-modify-write epilogue.
+    const bool y_tma = ((ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && !(flags & VAG_LIN_ACCUMULATE);
+    if (y_tma && (!e || strcmp(e, "persistent") == 0)) {
+        CUtensorMap mxh, mxl, mwh, mwl, my;
+        VAG_TRY(make_map(&mxh, xh, rows, K, ldxs, 128, f16, 64));
+        VAG_TRY(make_map(&mxl, xl, rows, K, ldxs, 128, f16, 64));
+        VAG_TRY(make_map(&mwh, wh, N, K, ldws, 128, f16, 64));
+        VAG_TRY(make_map(&mwl, wl, N, K, ldws, 128, f16, 64));
+        VAG_TRY(make_out_map(&my, y, rows, N, ldy));
+        if (summ_tile_w) *summ_tile_w = 128;
+        static bool attr_set[2] = {false, false};
+        const int n_tiles = ceil_div(N, 128) * ceil_div(rows, 128);
+        const int grid = n_tiles < sms ? n_tiles : sms;
+        if (f16) {
+            if (!attr_set[1]) {
+                VAG_CUDA(cudaFuncSetAttribute(linear_split3_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
+                attr_set[1] = true;
+            }
+            linear_split3_persistent_kernel<true><<<grid, 320, P_SMEM_BYTES, st>>>(mxh, mxl, mwh, mwl, my, bias, rows, K, N, flags, summ);
+        } else {
+            if (!attr_set[0]) {
+                VAG_CUDA(cudaFuncSetAttribute(linear_split3_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
+                attr_set[0] = true;
+            }
+            linear_split3_persistent_kernel<false><<<grid, 320, P_SMEM_BYTES, st>>>(mxh, mxl, mwh, mwl, my, bias, rows, K, N, flags, summ);
+        }
+        VAG_LAUNCH_CHECK();
+        return VAG_OK;
+    }
+    // tile configuration of the one-tile-per-CTA kernel: VAG_TC_CFG=wide|narrow|dual (tuning / A-B runs)
+    int cfg;  // 0 = 128x256 wide, 1 = 128x128 (128 B rows), 2 = 128x128 dual-CTA (64 B rows)
     if (e && strcmp(e, "wide") == 0) cfg = 0;
     else if (e && strcmp(e, "narrow") == 0) cfg = 1;
     else if (e && strcmp(e, "dual") == 0) cfg = 2;
@@ -406,12 +720,13 @@ int tc_gemm(float* y, int64_t ldy, const void* xh, const void* xl, int64_t ldxs,
     }
     const int bn = cfg == 0 ? 256 : 128;
     const int rowb = cfg == 2 ? 64 : 128;
+    if (summ_tile_w) *summ_tile_w = bn;
     CUtensorMap mxh, mxl, mwh, mwl;
     VAG_TRY(make_map(&mxh, xh, rows, K, ldxs, 128, f16, rowb));
     VAG_TRY(make_map(&mxl, xl, rows, K, ldxs, 128, f16, rowb));
     VAG_TRY(make_map(&mwh, wh, N, K, ldws, bn, f16, rowb));
     VAG_TRY(make_map(&mwl, wl, N, K, ldws, bn, f16, rowb));
-#define VAG_TC_GO(BN_, F16_, ROWB_) return launch_tc<BN_, F16_, ROWB_>(mxh, mxl, mwh, mwl, y, ldy, bias, rows, K, N, flags, st)
+#define VAG_TC_GO(BN_, F16_, ROWB_) return launch_tc<BN_, F16_, ROWB_>(mxh, mxl, mwh, mwl, y, ldy, bias, rows, K, N, flags, summ, st)
     if (f16) {
         if (cfg == 0) VAG_TC_GO(256, true, 128);
         if (cfg == 1) VAG_TC_GO(128, true, 128);
@@ -442,7 +757,7 @@ int linear_tc(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w
     }
     VAG_TRY(tc_split(x, ldx, rows, K, xh, xl, K, 0, st));
     VAG_TRY(tc_split(w, ldw, N, K, wh, wl, K, 0, st));
-    return tc_gemm(y, ldy, xh, xl, K, wh, wl, K, bias, rows, K, N, flags, st);
+    return tc_gemm(y, ldy, xh, xl, K, wh, wl, K, bias, rows, K, N, flags, st, nullptr, nullptr);
 }
 
 }  // namespace vag
