@@ -173,13 +173,25 @@ attention_kernel(float* __restrict__ c_out, int64_t ld_c, float* __restrict__ al
 }
 
 
+// 1 / (1 + exp(2x)) from a pre-scaled argument u = 2·log2(e)·x: two SFU ops (ex2, rcp) and one add.  tanh(x) = 1 − 2·this.
+// Saturates cleanly: u → +inf gives 0 (tanh = 1), u → −inf gives 1 (tanh = −1).
+__device__ __forceinline__ float inv_one_plus_exp2(float u) {
+    float t, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(u));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t + 1.0f));
+    return r;
+}
+constexpr float kTwoLog2e = 2.8853900817779268f;
+
 // ---------------------------------------------------------------------------------------------------------
 // Tuned variant for C % 4 == 0 (every real configuration): rows-per-CTA is a template parameter so that the
 // accumulator arrays are exactly as large as the beam, a warp loads a whole key row (up to 1024 channels) with
 // independent 128-bit loads BEFORE the SFU-heavy row loop (memory-level parallelism), and the context phase
 // streams ctx with four positions in flight.  MLP-mode cost is 2 SFU ops per (row, position, channel).
 // ---------------------------------------------------------------------------------------------------------
-template <int MODE, int RCAP>
+// FULLC: C is a multiple of 1024, so the per-chunk bounds checks (and the branches that fence the SFU chains apart)
+// disappear from the inner loops.
+template <int MODE, int RCAP, bool FULLC>
 __global__ void __launch_bounds__(256, RCAP <= 12 ? 3 : 2)
 attention_tuned_kernel(float* __restrict__ c_out, int64_t ld_c, float* __restrict__ alpha_out, const float* __restrict__ q,
                        int64_t ld_q, const float* __restrict__ keys, const float* __restrict__ ctx,
@@ -203,47 +215,78 @@ attention_tuned_kernel(float* __restrict__ c_out, int64_t ld_c, float* __restric
         const int r = i / C, c = i - r * C;
         float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
         if (row0 + r < rows) val = *reinterpret_cast<const float4*>(q + (int64_t)(row0 + r) * ld_q + c);
+        if (MODE == VAG_ATTN_MLP) { val.x *= kTwoLog2e; val.y *= kTwoLog2e; val.z *= kTwoLog2e; val.w *= kTwoLog2e; }
         *reinterpret_cast<float4*>(q_s + r * C + c) = val;
     }
-    if (MODE == VAG_ATTN_MLP)
-        for (int i = tid; i < C; i += 256) v_s[i] = v[i];
+    // MLP mode: Σ_c v_c·tanh(x_c) = Σ_c v_c − 2·Σ_c v_c / (1 + exp(2 x_c)); the first sum is a per-CTA constant
+    __shared__ float vsum_s[8];
+    float vsum = 0.f;
+    if (MODE == VAG_ATTN_MLP) {
+        float part_v = 0.f;
+        for (int i = tid; i < C; i += 256) { const float vv = v[i]; v_s[i] = vv; part_v += vv; }
+        part_v = warp_sum(part_v);
+        if (lane == 0) vsum_s[wid] = part_v;
+    }
     __syncthreads();
+    if (MODE == VAG_ATTN_MLP) {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) vsum += vsum_s[w];
+    }
 
-    // ---- phase 1: scores, one warp per source position
-    for (int t = wid; t < T; t += NW) {
-        const bool live = mask_b ? (mask_b[t] != 0.f) : true;
-        float part[RCAP];
+    // ---- phase 1: scores.  Work items = (live source position, group of RG rows), dealt round-robin to the 8 warps so
+    // that short sentences still keep every warp busy (a whole position per warp quantises badly when T_live ~ 8-16).
+    constexpr int RG = (RCAP + 3) / 4;
+    __shared__ int live_t[256];
+    __shared__ int n_live_s;
+    if (wid == 0) {  // compact the live positions (any mask pattern, not only prefixes)
+        int n = 0;
+        for (int t0 = 0; t0 < T; t0 += 32) {
+            const int t = t0 + lane;
+            const bool on = t < T && (mask_b ? mask_b[t] != 0.f : true);
+            const unsigned bal = __ballot_sync(0xffffffffu, on);
+            if (on && n + __popc(bal & ((1u << lane) - 1)) < 256) live_t[n + __popc(bal & ((1u << lane) - 1))] = t;
+            n += __popc(bal);
+        }
+        if (lane == 0) n_live_s = min(n, 256);
+    }
+    for (int i = tid; i < R * T; i += 256) sc_s[i] = -INFINITY;
+    __syncthreads();
+    const int n_live = n_live_s;
+    const int n_groups = (R + RG - 1) / RG;
+    for (int item = wid; item < n_live * n_groups; item += NW) {
+        const int t = live_t[item / n_groups];
+        const int r_lo = (item % n_groups) * RG;
+        float part[RG];
 #pragma unroll
-        for (int r = 0; r < RCAP; ++r) part[r] = 0.f;
-        if (live) {
-            const float* kr = key_b + (int64_t)t * C;
-            for (int cb = 0; cb < C; cb += 1024) {
-                float4 kv[8];
+        for (int g = 0; g < RG; ++g) part[g] = 0.f;
+        const float* kr = key_b + (int64_t)t * C;
+        for (int cb = 0; cb < C; cb += 1024) {
+            float4 kv[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int c = cb + j * 128 + lane * 4;
-                    kv[j] = c < C ? *reinterpret_cast<const float4*>(kr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+            for (int j = 0; j < 8; ++j) {
+                const int c = cb + j * 128 + lane * 4;
+                kv[j] = (FULLC || c < C) ? *reinterpret_cast<const float4*>(kr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
 #pragma unroll
-                for (int r = 0; r < RCAP; ++r) {
-                    if (r < R) {
+            for (int g = 0; g < RG; ++g) {
+                const int r = r_lo + g;
+                if (r < R) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int c = cb + j * 128 + lane * 4;
-                            if (c < C) {
-                                const float4 qv = *reinterpret_cast<const float4*>(q_s + r * C + c);
-                                if (MODE == VAG_ATTN_MLP) {
-                                    const float4 vv = *reinterpret_cast<const float4*>(v_s + c);
-                                    part[r] = fmaf(vv.x, tanh_abs(qv.x + kv[j].x), part[r]);
-                                    part[r] = fmaf(vv.y, tanh_abs(qv.y + kv[j].y), part[r]);
-                                    part[r] = fmaf(vv.z, tanh_abs(qv.z + kv[j].z), part[r]);
-                                    part[r] = fmaf(vv.w, tanh_abs(qv.w + kv[j].w), part[r]);
-                                } else {
-                                    part[r] = fmaf(qv.x, kv[j].x, part[r]);
-                                    part[r] = fmaf(qv.y, kv[j].y, part[r]);
-                                    part[r] = fmaf(qv.z, kv[j].z, part[r]);
-                                    part[r] = fmaf(qv.w, kv[j].w, part[r]);
-                                }
+                    for (int j = 0; j < 8; ++j) {
+                        const int c = cb + j * 128 + lane * 4;
+                        if (FULLC || c < C) {
+                            const float4 qv = *reinterpret_cast<const float4*>(q_s + r * C + c);
+                            if (MODE == VAG_ATTN_MLP) {
+                                const float4 vv = *reinterpret_cast<const float4*>(v_s + c);
+                                part[g] = fmaf(vv.x, inv_one_plus_exp2(fmaf(kv[j].x, kTwoLog2e, qv.x)), part[g]);
+                                part[g] = fmaf(vv.y, inv_one_plus_exp2(fmaf(kv[j].y, kTwoLog2e, qv.y)), part[g]);
+                                part[g] = fmaf(vv.z, inv_one_plus_exp2(fmaf(kv[j].z, kTwoLog2e, qv.z)), part[g]);
+                                part[g] = fmaf(vv.w, inv_one_plus_exp2(fmaf(kv[j].w, kTwoLog2e, qv.w)), part[g]);
+                            } else {
+                                part[g] = fmaf(qv.x, kv[j].x, part[g]);
+                                part[g] = fmaf(qv.y, kv[j].y, part[g]);
+                                part[g] = fmaf(qv.z, kv[j].z, part[g]);
+                                part[g] = fmaf(qv.w, kv[j].w, part[g]);
                             }
                         }
                     }
@@ -251,10 +294,12 @@ attention_tuned_kernel(float* __restrict__ c_out, int64_t ld_c, float* __restric
             }
         }
 #pragma unroll
-        for (int r = 0; r < RCAP; ++r) {
+        for (int g = 0; g < RG; ++g) {
+            const int r = r_lo + g;
             if (r < R) {
-                const float s = warp_sum(part[r]);
-                if (lane == 0) sc_s[r * T + t] = live ? s : -INFINITY;
+                float s = warp_sum(part[g]);
+                if (MODE == VAG_ATTN_MLP) s = fmaf(-2.0f, s, vsum);
+                if (lane == 0) sc_s[r * T + t] = s;
             }
         }
     }
@@ -317,7 +362,7 @@ attention_tuned_kernel(float* __restrict__ c_out, int64_t ld_c, float* __restric
     }
 }
 
-template <int MODE, int RCAP>
+template <int MODE, int RCAP, bool FULLC>
 static int launch_attention_tuned(float* c_out, int64_t ld_c, float* alpha, const float* q, int64_t ld_q, const float* keys,
                                   const float* ctx, const float* v, const float* mask, int rows, int rows_per_sent, int T, int C,
                                   cudaStream_t st) {
@@ -328,11 +373,11 @@ static int launch_attention_tuned(float* c_out, int64_t ld_c, float* alpha, cons
     }
     static size_t configured = 0;
     if (smem > configured) {
-        VAG_CUDA(cudaFuncSetAttribute(attention_tuned_kernel<MODE, RCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VAG_CUDA(cudaFuncSetAttribute(attention_tuned_kernel<MODE, RCAP, FULLC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     dim3 grid(rows / rows_per_sent, ceil_div(rows_per_sent, RCAP));
-    attention_tuned_kernel<MODE, RCAP><<<grid, 256, smem, st>>>(c_out, ld_c, alpha, q, ld_q, keys, ctx, v, mask, rows,
+    attention_tuned_kernel<MODE, RCAP, FULLC><<<grid, 256, smem, st>>>(c_out, ld_c, alpha, q, ld_q, keys, ctx, v, mask, rows,
                                                                  rows_per_sent, T, C);
     VAG_LAUNCH_CHECK();
     return VAG_OK;
@@ -342,7 +387,12 @@ template <int MODE>
 static int dispatch_attention_tuned(float* c_out, int64_t ld_c, float* alpha, const float* q, int64_t ld_q, const float* keys,
                                     const float* ctx, const float* v, const float* mask, int rows, int rows_per_sent, int T,
                                     int C, cudaStream_t st) {
-#define VAG_ATT(RC) return launch_attention_tuned<MODE, RC>(c_out, ld_c, alpha, q, ld_q, keys, ctx, v, mask, rows, rows_per_sent, T, C, st)
+#define VAG_ATT(RC)                                                                                                        \
+    do {                                                                                                                   \
+        if (C % 1024 == 0)                                                                                                 \
+            return launch_attention_tuned<MODE, RC, true>(c_out, ld_c, alpha, q, ld_q, keys, ctx, v, mask, rows, rows_per_sent, T, C, st); \
+        return launch_attention_tuned<MODE, RC, false>(c_out, ld_c, alpha, q, ld_q, keys, ctx, v, mask, rows, rows_per_sent, T, C, st);    \
+    } while (0)
     if (rows_per_sent == 1) VAG_ATT(1);
     if (rows_per_sent <= 4) VAG_ATT(4);
     if (rows_per_sent <= 8) VAG_ATT(8);
