@@ -140,6 +140,27 @@ def stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class _NullCtx:
+    __slots__ = ()
+
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+_NULL = _NullCtx()
+
+
+def on_device(device):
+    """Context manager making `device` current — free when it already is (the common single-GPU-per-process case)."""
+    idx = device.index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NULL
+    return torch.cuda.device(device)
+
+
 def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 

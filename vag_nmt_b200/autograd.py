@@ -19,6 +19,7 @@ from typing import List, Optional
 import torch
 
 from . import ops
+from ._cabi import on_device
 from . import train_ops as T
 
 SOS_token = 2
@@ -186,7 +187,7 @@ class DecoderInitFn(torch.autograd.Function):
         lib_mix = ops._cabi.lib()
         B, Tn, C = ctx.shape
         z = _empty(B, C, like=ctx)
-        with torch.cuda.device(ctx.device):
+        with on_device(ctx.device):
             ops.check(lib_mix.vag_init_mix_f32(z.data_ptr(), ops.ptr(ctx_vec), ctx.data_ptr(), mask.data_ptr(), float(split), B, Tn, C,
                                                ops.stream_ptr()))
         h0 = _lin(z, ini_w, ini_b, ops.LIN_TANH)

@@ -208,6 +208,12 @@ static int launch_simt(float* y, int64_t ldy, const float* x, int64_t ldx, const
 int linear_simt(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias,
                 int rows, int K, int N, int flags, cudaStream_t st) {
     const int sms = num_sms();
+    if (rows <= 32 && N >= 64 && K >= 64) {   // weight-streaming regime: one warp per output feature, K across the lanes
+        dim3 grid(ceil_div(N, 8), ceil_div(rows, 8));
+        linear_skinny_kernel<8><<<grid, 256, 0, st>>>(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags);
+        VAG_LAUNCH_CHECK();
+        return VAG_OK;
+    }
     const int64_t big_tiles = (int64_t)ceil_div(rows, 128) * ceil_div(N, 128);
     if (big_tiles >= sms) return launch_simt<128, 128, 16, 8, 8>(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags, st);
     const int64_t mid_tiles = (int64_t)ceil_div(rows, 64) * ceil_div(N, 64);

@@ -11,10 +11,13 @@ namespace vag {
 
 // ------------------------------------------------------------------------------------------ generic contraction
 // C[m, n] = alpha · Σ_k A(m, k)·B(k, n) + beta · C[m, n],   A(m,k) = A[m·sam + k·sak],  B(k,n) = B[k·sbk + n·sbn]
+// gridDim.z > 1: split-K — every z-slice handles k_chunk of the K range and atomically adds alpha·partial into C
+// (the host pre-scales C by beta); skinny problems (M = batch rows) would otherwise run on a handful of CTAs.
 template <int BM, int BN, int BK>
 __global__ void __launch_bounds__(256)
 gemm_generic_kernel(float* __restrict__ C, int64_t ldc, const float* __restrict__ A, int64_t sam, int64_t sak,
-                    const float* __restrict__ B, int64_t sbk, int64_t sbn, int M, int N, int K, float alpha, float beta) {
+                    const float* __restrict__ B, int64_t sbk, int64_t sbn, int M, int N, int K, float alpha, float beta,
+                    int k_chunk) {
     constexpr int TM = BM / 16, TN = BN / 16;
     __shared__ float As[BK][BM + 4];
     __shared__ float Bs[BK][BN + 4];
@@ -26,7 +29,11 @@ gemm_generic_kernel(float* __restrict__ C, int64_t ldc, const float* __restrict_
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
     const bool a_kfast = sak == 1, b_nfast = sbn == 1;
-    for (int k0 = 0; k0 < K; k0 += BK) {
+    const int k_begin = blockIdx.z * k_chunk;
+    const int k_end = min(K, k_begin + k_chunk);
+    const bool split = gridDim.z > 1;
+    K = k_end;
+    for (int k0 = k_begin; k0 < k_end; k0 += BK) {
         for (int idx = tid; idx < BM * BK; idx += 256) {
             const int m = a_kfast ? idx / BK : idx % BM;
             const int k = a_kfast ? idx % BK : idx / BM;
@@ -64,7 +71,8 @@ gemm_generic_kernel(float* __restrict__ C, int64_t ldc, const float* __restrict_
             if (gn >= N) continue;
             float* dst = C + (int64_t)gm * ldc + gn;
             const float v = alpha * acc[i][j];
-            *dst = beta == 0.f ? v : fmaf(beta, *dst, v);
+            if (split) atomicAdd(dst, v);
+            else *dst = beta == 0.f ? v : fmaf(beta, *dst, v);
         }
     }
 }
@@ -294,8 +302,33 @@ extern "C" int vag_gemm_f32(float* C, int64_t ldc, const float* A, int64_t sam, 
     VAG_REQUIRE(C && A && B, "vag_gemm_f32: null pointer");
     VAG_REQUIRE(M >= 0 && N >= 0 && K >= 0 && ldc >= N, "vag_gemm_f32: bad shape");
     if (M == 0 || N == 0) return VAG_OK;
-    dim3 grid(ceil_div(N, 64), ceil_div(M, 64));
-    gemm_generic_kernel<64, 64, 16><<<grid, 256, 0, (cudaStream_t)stream>>>(C, ldc, A, sam, sak, B, sbk, sbn, M, N, K, alpha, beta);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool small_m = M <= 32;
+    const int tiles = small_m ? ceil_div(N, 64) * ceil_div(M, 32) : ceil_div(N, 64) * ceil_div(M, 64);
+    int splits = 1;
+    const int target = 2 * num_sms();
+    if (tiles < target && K >= 256) splits = std::min(ceil_div(target, tiles), K / 64);
+    int k_chunk = K;
+    if (splits > 1) {
+        k_chunk = ceil_div(ceil_div(K, splits), 16) * 16;
+        splits = ceil_div(K, k_chunk);
+    }
+    if (splits > 1) {   // C ← beta·C first, then every slice adds its partial
+        if (beta == 0.f) {
+            if (ldc == N) VAG_CUDA(cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), st));
+            else VAG_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, st));
+        } else if (beta != 1.f) {
+            set_error("vag_gemm_f32: split-K path supports beta 0 or 1 only");
+            return VAG_ERR_UNSUPPORTED;
+        }
+    }
+    if (small_m) {
+        dim3 grid(ceil_div(N, 64), ceil_div(M, 32), splits);
+        gemm_generic_kernel<32, 64, 16><<<grid, 256, 0, st>>>(C, ldc, A, sam, sak, B, sbk, sbn, M, N, K, alpha, beta, k_chunk);
+    } else {
+        dim3 grid(ceil_div(N, 64), ceil_div(M, 64), splits);
+        gemm_generic_kernel<64, 64, 16><<<grid, 256, 0, st>>>(C, ldc, A, sam, sak, B, sbk, sbn, M, N, K, alpha, beta, k_chunk);
+    }
     VAG_LAUNCH_CHECK();
     return VAG_OK;
 }

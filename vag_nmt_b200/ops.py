@@ -11,7 +11,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _cabi
-from ._cabi import DecoderWeights, EncoderWeights, VseWeights, check, ptr, stream_ptr
+from ._cabi import DecoderWeights, EncoderWeights, VseWeights, check, on_device, ptr, stream_ptr
 
 ATTN_MLP, ATTN_DOT = 0, 1
 LIN_TANH, LIN_ACCUMULATE, LIN_FORCE_SIMT, LIN_FORCE_TC = 1, 2, 4, 8
@@ -61,7 +61,7 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
         out = torch.empty(rows, out_dim, dtype=torch.float32, device=x.device)
     out2 = out.reshape(-1, out_dim) if out.dim() != 2 else out
     assert out2.stride(-1) == 1 and out2.shape[0] == rows
-    with torch.cuda.device(x.device):
+    with on_device(x.device):
         check(lib.vag_linear_f32(out2.data_ptr(), out2.stride(0) if rows > 1 else out_dim, x2.data_ptr(),
                                  x2.stride(0) if rows > 1 else in_dim, w.data_ptr(), w.stride(0), ptr(bias), rows, in_dim,
                                  out_dim, flags, stream_ptr()))
@@ -80,7 +80,7 @@ def linear_tc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = N
         assert not (flags & LIN_ACCUMULATE)
         out = torch.empty(rows, out_dim, dtype=torch.float32, device=x.device)
     ws = workspace(lib.vag_linear_tc_workspace_bytes(rows, in_dim, out_dim), x.device, slot="gemm")
-    with torch.cuda.device(x.device):
+    with on_device(x.device):
         check(lib.vag_linear_tc_f32(out.data_ptr(), out.stride(0), x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0),
                                     ptr(bias), rows, in_dim, out_dim, flags, ws.data_ptr(), ws.numel(), stream_ptr()))
     return out
@@ -95,7 +95,7 @@ def tc_split(x: torch.Tensor):
     esz = lib.vag_tc_elem_bytes()
     hi = torch.empty(rows * K * esz, dtype=torch.uint8, device=x.device)
     lo = torch.empty_like(hi)
-    with torch.cuda.device(x.device):
+    with on_device(x.device):
         check(lib.vag_tc_split_f32(x.data_ptr(), x.stride(0), rows, K, hi.data_ptr(), lo.data_ptr(), K, stream_ptr()))
     return hi, lo
 
@@ -107,7 +107,7 @@ def tc_gemm(xs, ws, rows: int, in_dim: int, out_dim: int, bias: Optional[torch.T
     dev = xs[0].device
     if out is None:
         out = torch.empty(rows, out_dim, dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with on_device(dev):
         check(lib.vag_tc_gemm_f32(out.data_ptr(), out.stride(0), xs[0].data_ptr(), xs[1].data_ptr(), in_dim, ws[0].data_ptr(),
                                   ws[1].data_ptr(), in_dim, ptr(bias), rows, in_dim, out_dim, flags, stream_ptr()))
     return out
@@ -118,7 +118,7 @@ def embed_rows(table: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
     lib = _cabi.lib()
     ids = ids.reshape(-1).to(device=table.device, dtype=torch.int64).contiguous()
     out = torch.empty(ids.numel(), table.shape[1], dtype=torch.float32, device=table.device)
-    with torch.cuda.device(table.device):
+    with on_device(table.device):
         check(lib.vag_embed_rows_f32(out.data_ptr(), table.shape[1], table.data_ptr(), table.shape[1], ids.data_ptr(),
                                      ids.numel(), table.shape[0], stream_ptr()))
     return out
@@ -134,7 +134,7 @@ def gru_gates(gi: torch.Tensor, gh: torch.Tensor, h_prev: torch.Tensor, out: Opt
         assert t.stride(1) == 1
     if out is None:
         out = torch.empty(rows, H, dtype=torch.float32, device=h_prev.device)
-    with torch.cuda.device(h_prev.device):
+    with on_device(h_prev.device):
         check(lib.vag_gru_gates_f32(out.data_ptr(), out.stride(0), ptr(out2), out2.stride(0) if out2 is not None else 0,
                                     gi.data_ptr(), gi.stride(0), gh.data_ptr(), gh.stride(0), h_prev.data_ptr(),
                                     h_prev.stride(0), rows, H, stream_ptr()))
@@ -156,7 +156,7 @@ def attention(q: torch.Tensor, keys: torch.Tensor, ctx: torch.Tensor, v: Optiona
     c = out_c if out_c is not None else torch.empty(N, Cdim, dtype=torch.float32, device=q.device)
     alpha = out_alpha if out_alpha is not None else (torch.empty(N, T, dtype=torch.float32, device=q.device) if want_alpha else None)
     assert c.is_contiguous() and (alpha is None or alpha.is_contiguous())
-    with torch.cuda.device(q.device):
+    with on_device(q.device):
         check(lib.vag_attention_f32(c.data_ptr(), Cdim, ptr(alpha), q.data_ptr(), Cdim, keys.data_ptr(), ctx.data_ptr(),
                                     ptr(v), ptr(mask), N, rows_per_sent, T, Cdim, mode, stream_ptr()))
     return c, alpha
@@ -166,7 +166,7 @@ def l2norm_rows_(x: torch.Tensor) -> torch.Tensor:
     _chk_f32(x)
     lib = _cabi.lib()
     assert x.dim() == 2 and x.stride(1) == 1
-    with torch.cuda.device(x.device):
+    with on_device(x.device):
         check(lib.vag_l2norm_rows_f32(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], stream_ptr()))
     return x
 
@@ -176,7 +176,7 @@ def log_softmax(logits: torch.Tensor) -> torch.Tensor:
     lib = _cabi.lib()
     logits = logits.contiguous()
     out = torch.empty_like(logits)
-    with torch.cuda.device(logits.device):
+    with on_device(logits.device):
         check(lib.vag_log_softmax_f32(out.data_ptr(), logits.data_ptr(), logits.shape[0], logits.shape[1], stream_ptr()))
     return out
 
@@ -187,7 +187,7 @@ def nll_rows(logits: torch.Tensor, tgt: torch.Tensor, weight: Optional[torch.Ten
     _chk_f32(logits, weight, loss_rows, lse_out)
     lib = _cabi.lib()
     assert logits.stride(1) == 1 and tgt.dtype == torch.int64 and tgt.is_contiguous()
-    with torch.cuda.device(logits.device):
+    with on_device(logits.device):
         check(lib.vag_nll_rows_f32(logits.data_ptr(), logits.stride(0), tgt.data_ptr(), ptr(weight), logits.shape[0],
                                    logits.shape[1], loss_rows.data_ptr(), ptr(lse_out), stream_ptr()))
 
@@ -258,7 +258,7 @@ def encoder_fwd(w: EncoderWeights, src: torch.Tensor, lengths: Sequence[int]) ->
     mask = torch.empty(B, T, dtype=torch.float32, device=dev)
     nbytes = lib.vag_encoder_workspace_bytes(B, T, w.E, w.H)
     ws = workspace(nbytes, dev)
-    with torch.cuda.device(dev):
+    with on_device(dev):
         check(lib.vag_encoder_fwd_f32(C.byref(w), src.data_ptr(), lens, B, T, ctx.data_ptr(), mask.data_ptr(), ws.data_ptr(),
                                       ws.numel(), stream_ptr()))
     return ctx, mask
@@ -277,7 +277,7 @@ def vse_pool_fwd(w: VseWeights, im: torch.Tensor, ctx: torch.Tensor, mask: torch
     beta = torch.empty(B, T, dtype=torch.float32, device=dev) if want_beta else None
     nbytes = lib.vag_vse_workspace_bytes(B, T, w.I, w.C, w.S)
     ws = workspace(nbytes, dev)
-    with torch.cuda.device(dev):
+    with on_device(dev):
         check(lib.vag_vse_pool_fwd_f32(C.byref(w), im.data_ptr(), ctx.data_ptr(), mask.data_ptr(), B, T, im_emb.data_ptr(),
                                        txt_emb.data_ptr(), ctx_vec.data_ptr(), ptr(beta), ws.data_ptr(), ws.numel(),
                                        stream_ptr()))
@@ -290,7 +290,7 @@ def attn_keys(w: DecoderWeights, ctx: torch.Tensor) -> torch.Tensor:
     B, T, Cd = ctx.shape
     keys = torch.empty_like(ctx)
     ws = workspace(lib.vag_attn_keys_workspace_bytes(B, T, Cd), ctx.device)
-    with torch.cuda.device(ctx.device):
+    with on_device(ctx.device):
         check(lib.vag_attn_keys_f32(C.byref(w), ctx.data_ptr(), B, T, keys.data_ptr(), ws.data_ptr(), ws.numel(),
                                     stream_ptr()))
     return keys
@@ -302,7 +302,7 @@ def decoder_init(w: DecoderWeights, ctx_vec: Optional[torch.Tensor], ctx: torch.
     B, T, Cd = ctx.shape
     h0 = torch.empty(B, w.H, dtype=torch.float32, device=ctx.device)
     ws = workspace(lib.vag_decoder_init_workspace_bytes(B, Cd, w.H), ctx.device)
-    with torch.cuda.device(ctx.device):
+    with on_device(ctx.device):
         check(lib.vag_decoder_init_f32(C.byref(w), ptr(ctx_vec), ctx.data_ptr(), mask.data_ptr(), float(split), B, T,
                                        h0.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr()))
     return h0
@@ -323,7 +323,7 @@ def decoder_step(w: DecoderWeights, tokens: torch.Tensor, h_prev: torch.Tensor, 
     alpha = torch.empty(rows, T, dtype=torch.float32, device=dev) if want_alpha else None
     nbytes = lib.vag_decoder_step_workspace_bytes(rows, w.E, w.H, w.C, w.V)
     ws = workspace(nbytes, dev)
-    with torch.cuda.device(dev):
+    with on_device(dev):
         check(lib.vag_decoder_step_f32(C.byref(w), tokens.data_ptr(), h_prev.data_ptr(), keys.data_ptr(), ctx.data_ptr(),
                                        mask.data_ptr(), rows, rows_per_sent, T, h_out.data_ptr(), out.data_ptr(),
                                        1 if want_logp else 0, ptr(alpha), ws.data_ptr(), ws.numel(), stream_ptr()))
@@ -342,7 +342,7 @@ def beam_select(logp: torch.Tensor, prev_tokens: Optional[torch.Tensor], nll: to
     parents = torch.empty(B, K, dtype=torch.int32, device=dev)
     if prev_tokens is not None:
         prev_tokens = prev_tokens.to(torch.int64).contiguous()
-    with torch.cuda.device(dev):
+    with on_device(dev):
         check(lib.vag_beam_select_f32(logp.data_ptr(), V, ptr(prev_tokens), nll.data_ptr(), tokens.data_ptr(),
                                       parents.data_ptr(), B, K, V, step, 1 if avoid_double else 0, stream_ptr()))
     return tokens, parents
@@ -361,7 +361,7 @@ def beam_decode(w: DecoderWeights, h0: torch.Tensor, keys: torch.Tensor, ctx: to
     steps = torch.empty(1, dtype=torch.int32, device=dev) if debug else None
     nbytes = lib.vag_beam_decode_workspace_bytes(B, K, T, L, w.E, w.H, w.C, w.V)
     ws = workspace(nbytes, dev)
-    with torch.cuda.device(dev):
+    with on_device(dev):
         check(lib.vag_beam_decode_f32(C.byref(w), h0.data_ptr(), keys.data_ptr(), ctx.data_ptr(), mask.data_ptr(), B, K, T,
                                       L, 1 if avoid_double else 0, hyp.data_ptr(), hyp_len.data_ptr(), ptr(beam), ptr(nll),
                                       ptr(steps), ws.data_ptr(), ws.numel(), stream_ptr()))
@@ -378,7 +378,7 @@ def greedy_decode(w: DecoderWeights, h0: torch.Tensor, keys: torch.Tensor, ctx: 
     toks = torch.empty(B, L, dtype=torch.int64, device=dev)
     nbytes = lib.vag_beam_decode_workspace_bytes(B, 1, T, L, w.E, w.H, w.C, w.V)
     ws = workspace(nbytes, dev)
-    with torch.cuda.device(dev):
+    with on_device(dev):
         check(lib.vag_greedy_decode_f32(C.byref(w), h0.data_ptr(), keys.data_ptr(), ctx.data_ptr(), mask.data_ptr(), B, T, L,
                                         toks.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr()))
     return toks
@@ -394,7 +394,7 @@ def rank_loss(im: torch.Tensor, s: torch.Tensor, margin: float, one_direction: b
     g_im = torch.empty_like(im) if want_grad else None
     g_s = torch.empty_like(s) if want_grad else None
     ws = workspace(lib.vag_rank_loss_workspace_bytes(B, S), dev)
-    with torch.cuda.device(dev):
+    with on_device(dev):
         check(lib.vag_rank_loss_f32(im.data_ptr(), s.data_ptr(), B, S, float(margin), 1 if one_direction else 0,
                                     loss.data_ptr(), ptr(g_im), ptr(g_s), ws.data_ptr(), ws.numel(), stream_ptr()))
     return loss[0], g_im, g_s
@@ -408,7 +408,7 @@ def recall_ranks(queries: torch.Tensor, gallery: torch.Tensor) -> torch.Tensor:
     n, S = queries.shape
     ranks = torch.empty(n, dtype=torch.int32, device=dev)
     ws = workspace(lib.vag_recall_ranks_workspace_bytes(n, S), dev)
-    with torch.cuda.device(dev):
+    with on_device(dev):
         check(lib.vag_recall_ranks_f32(queries.data_ptr(), gallery.data_ptr(), n, S, ranks.data_ptr(), ws.data_ptr(),
                                        ws.numel(), stream_ptr()))
     return ranks
@@ -419,7 +419,7 @@ def row_argmax(logits: torch.Tensor) -> torch.Tensor:
     lib = _cabi.lib()
     assert logits.dim() == 2 and logits.stride(1) == 1
     out = torch.empty(logits.shape[0], dtype=torch.int64, device=logits.device)
-    with torch.cuda.device(logits.device):
+    with on_device(logits.device):
         check(lib.vag_row_argmax_f32(logits.data_ptr(), logits.stride(0), logits.shape[0], logits.shape[1], out.data_ptr(),
                                      stream_ptr()))
     return out
@@ -431,7 +431,7 @@ def translation_loss(loss_rows: torch.Tensor, tgt: torch.Tensor, loss_vse: Optio
     lib = _cabi.lib()
     B, Tt = tgt.shape
     out = torch.empty(3, dtype=torch.float32, device=loss_rows.device)
-    with torch.cuda.device(loss_rows.device):
+    with on_device(loss_rows.device):
         check(lib.vag_translation_loss_f32(loss_rows.data_ptr(), tgt.data_ptr(), B, Tt, ptr(loss_vse), float(loss_w),
                                            out.data_ptr(), stream_ptr()))
     return out

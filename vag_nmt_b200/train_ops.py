@@ -6,7 +6,7 @@ from typing import Optional
 import torch
 
 from . import _cabi
-from ._cabi import check, ptr, stream_ptr
+from ._cabi import check, on_device, ptr, stream_ptr
 
 
 def _f(n) -> float:
@@ -26,7 +26,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, trans_a: bool = False, trans_b: bool 
         assert beta == 0.0
         out = torch.empty(M, N, dtype=torch.float32, device=A.device)
     assert out.shape == (M, N) and out.stride(1) == 1
-    with torch.cuda.device(A.device):
+    with on_device(A.device):
         check(lib.vag_gemm_f32(out.data_ptr(), out.stride(0), A.data_ptr(), sam, sak, B.data_ptr(), sbk, sbn, M, N, K,
                                _f(alpha), _f(beta), stream_ptr()))
     return out
@@ -40,7 +40,7 @@ def gru_gates_bwd(dh: torch.Tensor, gi: torch.Tensor, gh: torch.Tensor, h_prev: 
     dgi = torch.empty(rows, 3 * H, dtype=torch.float32, device=dh.device)
     dgh = torch.empty_like(dgi)
     dhp = torch.empty(rows, H, dtype=torch.float32, device=dh.device)
-    with torch.cuda.device(dh.device):
+    with on_device(dh.device):
         check(lib.vag_gru_gates_bwd_f32(dgi.data_ptr(), dgh.data_ptr(), dhp.data_ptr(), dh.data_ptr(), dh.stride(0), gi.data_ptr(),
                                         gh.data_ptr(), h_prev.data_ptr(), h_prev.stride(0), rows, H, stream_ptr()))
     return dgi, dgh, dhp
@@ -52,7 +52,7 @@ def attention_bwd(dc, alpha, q, keys, ctx, v, mask, dkeys, dctx, dv, mode: int) 
     B, T, C = ctx.shape
     assert dc.stride(1) == 1 and q.stride(1) == 1 and alpha.is_contiguous() and keys.is_contiguous() and ctx.is_contiguous()
     dq = torch.empty(B, C, dtype=torch.float32, device=ctx.device)
-    with torch.cuda.device(ctx.device):
+    with on_device(ctx.device):
         check(lib.vag_attention_bwd_f32(dq.data_ptr(), C, dkeys.data_ptr(), ptr(dctx), ptr(dv), dc.data_ptr(), dc.stride(0),
                                         alpha.data_ptr(), q.data_ptr(), q.stride(0), keys.data_ptr(), ctx.data_ptr(), ptr(v),
                                         ptr(mask), B, T, C, mode, stream_ptr()))
@@ -63,7 +63,7 @@ def nll_bwd(logits, lse, tgt, weight, grad_rows) -> torch.Tensor:
     lib = _cabi.lib()
     rows, V = logits.shape
     d = torch.empty(rows, V, dtype=torch.float32, device=logits.device)
-    with torch.cuda.device(logits.device):
+    with on_device(logits.device):
         check(lib.vag_nll_bwd_f32(d.data_ptr(), V, logits.data_ptr(), logits.stride(0), lse.data_ptr(), tgt.data_ptr(), ptr(weight),
                                   grad_rows.data_ptr(), rows, V, stream_ptr()))
     return d
@@ -73,7 +73,7 @@ def tanh_bwd(dy: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     lib = _cabi.lib()
     dy, y = dy.contiguous(), y.contiguous()
     dx = torch.empty_like(y)
-    with torch.cuda.device(y.device):
+    with on_device(y.device):
         check(lib.vag_tanh_bwd_f32(dx.data_ptr(), dy.data_ptr(), y.data_ptr(), y.numel(), stream_ptr()))
     return dx
 
@@ -82,7 +82,7 @@ def axpby_(y: torch.Tensor, x: torch.Tensor, a: float = 1.0, b: float = 1.0) -> 
     """y = a·x + b·y in place (contiguous tensors of equal size)."""
     lib = _cabi.lib()
     assert y.is_contiguous() and x.is_contiguous() and y.numel() == x.numel()
-    with torch.cuda.device(y.device):
+    with on_device(y.device):
         check(lib.vag_axpby_f32(y.data_ptr(), x.data_ptr(), _f(a), _f(b), y.numel(), stream_ptr()))
     return y
 
@@ -94,7 +94,7 @@ def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool
     if out is None:
         out = torch.empty(cols, dtype=torch.float32, device=x.device)
         accumulate = False
-    with torch.cuda.device(x.device):
+    with on_device(x.device):
         check(lib.vag_colsum_f32(out.data_ptr(), x.data_ptr(), x.stride(0), rows, cols, 1 if accumulate else 0, stream_ptr()))
     return out
 
@@ -102,7 +102,7 @@ def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool
 def embed_bwd_(table_grad: torch.Tensor, g: torch.Tensor, ids: torch.Tensor) -> None:
     lib = _cabi.lib()
     assert table_grad.is_contiguous() and g.stride(1) == 1 and ids.is_contiguous() and ids.dtype == torch.int64
-    with torch.cuda.device(g.device):
+    with on_device(g.device):
         check(lib.vag_embed_bwd_f32(table_grad.data_ptr(), g.data_ptr(), g.stride(0), ids.data_ptr(), ids.numel(), g.shape[1],
                                     table_grad.shape[0], stream_ptr()))
 
@@ -111,7 +111,7 @@ def l2norm_bwd(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     lib = _cabi.lib()
     dy, x = dy.contiguous(), x.contiguous()
     dx = torch.empty_like(x)
-    with torch.cuda.device(x.device):
+    with on_device(x.device):
         check(lib.vag_l2norm_bwd_f32(dx.data_ptr(), dy.data_ptr(), x.data_ptr(), x.shape[0], x.shape[1], stream_ptr()))
     return dx
 
@@ -121,7 +121,7 @@ def init_mix_bwd(dz: torch.Tensor, mask: torch.Tensor, split: float, dctx: torch
     B, T, C = dctx.shape
     dz = dz.contiguous()
     dvec = torch.empty(B, C, dtype=torch.float32, device=dz.device) if want_ctx_vec else None
-    with torch.cuda.device(dz.device):
+    with on_device(dz.device):
         check(lib.vag_init_mix_bwd_f32(ptr(dvec), dctx.data_ptr(), dz.data_ptr(), mask.data_ptr(), _f(split), B, T, C, stream_ptr()))
     return dvec
 
@@ -129,14 +129,14 @@ def init_mix_bwd(dz: torch.Tensor, mask: torch.Tensor, split: float, dctx: torch
 def sumsq_(accum: torch.Tensor, g: torch.Tensor) -> None:
     lib = _cabi.lib()
     assert g.is_contiguous()
-    with torch.cuda.device(g.device):
+    with on_device(g.device):
         check(lib.vag_sumsq_f32(g.data_ptr(), g.numel(), accum.data_ptr(), stream_ptr()))
 
 
 def clip_adam_(param, grad, exp_avg, exp_avg_sq, sumsq, clip, lr, beta1, beta2, eps, weight_decay, step) -> None:
     lib = _cabi.lib()
     assert param.is_contiguous() and grad.is_contiguous()
-    with torch.cuda.device(param.device):
+    with on_device(param.device):
         check(lib.vag_clip_adam_f32(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), param.numel(),
                                     sumsq.data_ptr(), _f(clip), _f(lr), _f(beta1), _f(beta2), _f(eps), _f(weight_decay), int(step),
                                     stream_ptr()))
