@@ -306,6 +306,56 @@ int vag_embed_bwd_f32(float* table_grad, const float* g, int64_t ldg, const int6
 int vag_l2norm_bwd_f32(float* dx, const float* dy, const float* x, int rows, int dim, vag_stream_t stream);
 int vag_init_mix_bwd_f32(float* dctx_vec, float* dctx, const float* dz, const float* mask, float split, int B, int T,
                          int C, vag_stream_t stream);
+/* The whole teacher-forced / free-running decoder loop of V11.forward (:136-160) with the activations its backward
+ * needs, and the matching back-propagation through time — one call each.  All buffers are caller-owned. */
+typedef struct {
+    int64_t ld_logits;        /* row pitch of logits_all (>= V, multiple of 4) */
+    float* keys;              /* [B, T, C]   attn_e(ctx) */
+    float* e_all;             /* [Tt·B, E]   input embeddings            */
+    float* gi1_all;           /* [Tt, B, 3H] GRU1 input pre-activations  */
+    float* gh1_all;           /* [Tt, B, 3H] GRU1 hidden pre-activations */
+    float* h1_all;            /* [Tt, B, H]  */
+    float* q_all;             /* [Tt, B, C]  attn_h(h1) */
+    float* alpha_all;         /* [Tt, B, T]  attention weights */
+    float* c_all;             /* [Tt, B, C]  contexts */
+    float* x2_all;            /* [Tt, B, H]  context2hid(c) */
+    float* gi2_all;           /* [Tt, B, 3H] */
+    float* gh2_all;           /* [Tt, B, 3H] */
+    float* h2_all;            /* [Tt, B, H]  */
+    float* t_all;             /* [Tt·B, E]   tanh read-out */
+    float* logits_all;        /* [Tt·B, ld_logits] */
+    float* lse_all;           /* [Tt, B]     row log-sum-exp */
+} vag_decoder_seq_saved;
+
+typedef struct {              /* gradient outputs, same shapes as the weights (out_w unused when tied) */
+    float *emb, *gru1_w_ih, *gru1_w_hh, *gru1_b_ih, *gru1_b_hh, *attn_h_w, *attn_e_w, *attn_v, *c2h_w, *gru2_w_ih,
+          *gru2_w_hh, *gru2_b_ih, *gru2_b_hh, *w1_w, *w1_b, *w2_w, *w2_b, *w3_w, *w3_b, *out_w, *out_b;
+} vag_decoder_grads;
+
+size_t vag_decoder_seq_workspace_bytes(int B, int T, int Tt, int E, int H, int C, int64_t V);
+/* tok_in int64 [Tt, B]: row 0 = <sos>; teacher != 0: rows 1.. hold tgt[:, :-1] (caller fills); else the kernel's own
+ * arg-max feedback is written there.  tgt_t int64 [Tt, B].  loss_rows [B] = Σ_t NLL (nn.NLLLoss(weight, reduce=False)). */
+int vag_decoder_seq_fwd_f32(const vag_decoder_weights* w, const float* h0, const float* enc, const float* mask,
+                            int64_t* tok_in, const int64_t* tgt_t, const float* nll_weight, int B, int T, int Tt,
+                            int teacher, const vag_decoder_seq_saved* s, float* loss_rows, void* workspace,
+                            size_t workspace_bytes, vag_stream_t stream);
+int vag_decoder_seq_bwd_f32(const vag_decoder_weights* w, const float* h0, const float* enc, const float* mask,
+                            const int64_t* tok_in, const int64_t* tgt_t, const float* nll_weight, int B, int T, int Tt,
+                            int tied, const vag_decoder_seq_saved* s, const float* dloss_rows,
+                            const vag_decoder_grads* g, float* d_h0, float* d_enc, void* workspace,
+                            size_t workspace_bytes, vag_stream_t stream);
+
+/* Encoder training pair: forward that keeps what BPTT needs and the backward through both directions of the packed
+ * bi-GRU.  x [T·B, E] time-major embeddings, ids_tm int64 [T·B], gi / gh [2][T, B, 3H]; gradients like the weights. */
+size_t vag_encoder_train_workspace_bytes(int B, int T, int E, int H);
+int vag_encoder_train_fwd_f32(const vag_encoder_weights* w, const int64_t* src, const int32_t* lengths_host, int B, int T,
+                              float* ctx_out, float* x, int64_t* ids_tm, float* gi, float* gh, void* workspace,
+                              size_t workspace_bytes, vag_stream_t stream);
+int vag_encoder_bwd_f32(const vag_encoder_weights* w, const int32_t* lengths_host, int B, int T, const float* ctx,
+                        const float* dctx, const float* x, const int64_t* ids_tm, const float* gi, const float* gh,
+                        float* d_emb, float* const* d_w_ih, float* const* d_w_hh, float* const* d_b_ih,
+                        float* const* d_b_hh, void* workspace, size_t workspace_bytes, vag_stream_t stream);
+
 /* Optimiser step of train.py:46-49 with the Adam of nmt_multimodal_beam_DE.py:303-332, fused per parameter tensor:
  *   accum[0] += Σ grad²  (vag_sumsq_f32 over every tensor, after the gradient all-reduce when data-parallel), then
  *   g ← grad·min(1, clip/(√accum + 1e-6)) [+ weight_decay·param];  Adam(m, v, step) update of param in place. */

@@ -41,6 +41,18 @@ class DecoderWeights(C.Structure):
                 ("ini_w", C.c_void_p), ("ini_b", C.c_void_p)]
 
 
+class DecoderSeqSaved(C.Structure):
+    _fields_ = [("ld_logits", C.c_int64)] + [(n, C.c_void_p) for n in (
+        "keys", "e_all", "gi1_all", "gh1_all", "h1_all", "q_all", "alpha_all", "c_all", "x2_all", "gi2_all", "gh2_all", "h2_all",
+        "t_all", "logits_all", "lse_all")]
+
+
+class DecoderGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "emb", "gru1_w_ih", "gru1_w_hh", "gru1_b_ih", "gru1_b_hh", "attn_h_w", "attn_e_w", "attn_v", "c2h_w", "gru2_w_ih",
+        "gru2_w_hh", "gru2_b_ih", "gru2_b_hh", "w1_w", "w1_b", "w2_w", "w2_b", "w3_w", "w3_b", "out_w", "out_b")]
+
+
 I, I64, F, P, SZ = C.c_int, C.c_int64, C.c_float, C.c_void_p, C.c_size_t
 
 # name -> (restype, argtypes); must list every symbol include/vag_nmt.h declares (tests/test_cabi_symbols.py checks)
@@ -92,6 +104,12 @@ SIGNATURES = {
     "vag_embed_bwd_f32": (I, [P, P, I64, P, I, I, I64, P]),
     "vag_l2norm_bwd_f32": (I, [P, P, P, I, I, P]),
     "vag_init_mix_bwd_f32": (I, [P, P, P, P, F, I, I, I, P]),
+    "vag_decoder_seq_workspace_bytes": (SZ, [I, I, I, I, I, I, I64]),
+    "vag_decoder_seq_fwd_f32": (I, [P, P, P, P, P, P, P, I, I, I, I, P, P, P, SZ, P]),
+    "vag_decoder_seq_bwd_f32": (I, [P, P, P, P, P, P, P, I, I, I, I, P, P, P, P, P, P, SZ, P]),
+    "vag_encoder_train_workspace_bytes": (SZ, [I, I, I, I]),
+    "vag_encoder_train_fwd_f32": (I, [P, P, P, I, I, P, P, P, P, P, P, SZ, P]),
+    "vag_encoder_bwd_f32": (I, [P, P, I, I, P, P, P, P, P, P, P, P, P, P, P, P, SZ, P]),
     "vag_sumsq_f32": (I, [P, I64, P, P]),
     "vag_clip_adam_f32": (I, [P, P, P, P, I64, P, F, F, F, F, F, F, I, P]),
 }

@@ -45,81 +45,60 @@ def _empty(*shape, like):
 
 # ---------------------------------------------------------------------------------------------------- encoder
 class EncoderFn(torch.autograd.Function):
-    """src int64 [B, T] (sorted by length desc), lengths list → ctx [B, T, 2H] (sentence-major)."""
+    """src int64 [B, T] (sorted by length desc), lengths list → ctx [B, T, 2H] (sentence-major).
+    Forward (with saved pre-activations) and BPTT are one C call each."""
 
     @staticmethod
     def forward(fctx, src, lengths, emb, *gru):
         # gru = (w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r)
+        import ctypes as C
+        from ._cabi import EncoderWeights
+        lib = ops._cabi.lib()
         B, Tn = src.shape
-        E = emb.shape[1]
-        H = gru[1].shape[1]
-        lens = [int(x) for x in lengths]
-        n_act = [sum(1 for l in lens if l > t) for t in range(Tn)]
-        ids_tm = src.t().contiguous().reshape(-1)                      # time-major token ids [T·B]
-        x = ops.embed_rows(emb, ids_tm)                                # [T·B, E]
-        ctx = _zeros(B, Tn, 2 * H, like=emb)
-        gi, gh_all = [], []
+        E, H = emb.shape[1], gru[1].shape[1]
+        dev = emb.device
+        w = EncoderWeights()
+        w.E, w.H, w.vocab, w.emb = E, H, emb.shape[0], ops._p(emb.detach())
         for d in range(2):
-            w_ih, w_hh, b_ih, b_hh = gru[4 * d:4 * d + 4]
-            gi_d = _lin(x, w_ih, b_ih).view(Tn, B, 3 * H)
-            gh_d = _zeros(Tn, B, 3 * H, like=emb)
-            h = _zeros(B, H, like=emb)
-            steps = range(Tn) if d == 0 else range(Tn - 1, -1, -1)
-            for t in steps:
-                n = n_act[t]
-                if n == 0:
-                    continue
-                ops.linear(h[:n], w_hh, b_hh, out=gh_d[t, :n])
-                ops.gru_gates(gi_d[t, :n], gh_d[t, :n], h[:n], out=h[:n], out2=ctx[:n, t, d * H:(d + 1) * H])
-            gi.append(gi_d)
-            gh_all.append(gh_d)
-        fctx.save_for_backward(x, ctx, ids_tm, emb, gi[0], gi[1], gh_all[0], gh_all[1], *gru)
-        fctx.meta = (B, Tn, E, H, n_act)
+            w.w_ih[d], w.w_hh[d] = ops._p(gru[4 * d].detach()), ops._p(gru[4 * d + 1].detach())
+            w.b_ih[d], w.b_hh[d] = ops._p(gru[4 * d + 2].detach()), ops._p(gru[4 * d + 3].detach())
+        lens = (C.c_int32 * B)(*[int(x) for x in lengths])
+        ctx = torch.empty(B, Tn, 2 * H, dtype=torch.float32, device=dev)
+        x = torch.empty(Tn * B, E, dtype=torch.float32, device=dev)
+        ids_tm = torch.empty(Tn * B, dtype=torch.int64, device=dev)
+        gi = torch.empty(2, Tn, B, 3 * H, dtype=torch.float32, device=dev)
+        gh = torch.empty(2, Tn, B, 3 * H, dtype=torch.float32, device=dev)
+        ws = ops.workspace(lib.vag_encoder_train_workspace_bytes(B, Tn, E, H), dev)
+        with on_device(dev):
+            ops.check(lib.vag_encoder_train_fwd_f32(C.byref(w), src.data_ptr(), lens, B, Tn, ctx.data_ptr(), x.data_ptr(),
+                                                    ids_tm.data_ptr(), gi.data_ptr(), gh.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                    ops.stream_ptr()))
+        fctx.save_for_backward(x, ctx, ids_tm, gi, gh, emb, *gru)
+        fctx.meta = (B, Tn, E, H, [int(v) for v in lengths])
         return ctx
 
     @staticmethod
     def backward(fctx, dctx):
-        x, ctx, ids_tm, emb, gi0, gi1, gh0, gh1, *gru = fctx.saved_tensors
-        B, Tn, E, H, n_act = fctx.meta
-        dctx = dctx.contiguous()
-        grads: List[Optional[torch.Tensor]] = []
-        dx = _zeros(Tn * B, E, like=x)
-        zeros_h = _zeros(B, H, like=x)
+        import ctypes as C
+        from ._cabi import EncoderWeights
+        lib = ops._cabi.lib()
+        x, ctx, ids_tm, gi, gh, emb, *gru = fctx.saved_tensors
+        B, Tn, E, H, lengths = fctx.meta
+        dev = emb.device
+        w = EncoderWeights()
+        w.E, w.H, w.vocab, w.emb = E, H, emb.shape[0], ops._p(emb.detach())
         for d in range(2):
-            w_ih, w_hh, b_ih, b_hh = gru[4 * d:4 * d + 4]
-            gi_d, gh_d = (gi0, gh0) if d == 0 else (gi1, gh1)
-            dgi_all = _zeros(Tn, B, 3 * H, like=x)
-            dgh_all = _zeros(Tn, B, 3 * H, like=x)
-            hprev_all = _zeros(Tn, B, H, like=x)
-            carry = _zeros(B, H, like=x)
-            steps = range(Tn - 1, -1, -1) if d == 0 else range(Tn)    # reverse of the forward order
-            for t in steps:
-                n = n_act[t]
-                if n == 0:
-                    continue
-                tp = t - 1 if d == 0 else t + 1                        # where h_prev of this step was produced
-                if 0 <= tp < Tn and n_act[tp] > 0:
-                    # rows whose chain starts at this step (reverse direction) had h_prev = 0: ctx is 0 there already
-                    hp = ctx[:n, tp, d * H:(d + 1) * H]
-                else:
-                    hp = zeros_h[:n]
-                hprev_all[t, :n].copy_(hp)
-                dh = _empty(n, H, like=x)
-                dh.copy_(dctx[:n, t, d * H:(d + 1) * H])
-                T.axpby_(dh, carry[:n].contiguous(), 1.0, 1.0)
-                dgi, dgh, dhp = T.gru_gates_bwd(dh, gi_d[t, :n].contiguous(), gh_d[t, :n].contiguous(), hprev_all[t, :n])
-                dgi_all[t, :n].copy_(dgi)
-                dgh_all[t, :n].copy_(dgh)
-                T.gemm(dgh, w_hh, out=dhp, beta=1.0)                   # dh_prev = dh·z + dgh·W_hh
-                carry.zero_()
-                carry[:n].copy_(dhp)
-            dgi_f = dgi_all.view(Tn * B, 3 * H)
-            dgh_f = dgh_all.view(Tn * B, 3 * H)
-            T.gemm(dgi_f, w_ih, out=dx, beta=1.0)                       # dx += dgi·W_ih
-            grads += [T.gemm(dgi_f, x, trans_a=True), T.gemm(dgh_f, hprev_all.view(Tn * B, H), trans_a=True),
-                      T.colsum(dgi_f), T.colsum(dgh_f)]
-        demb = _zeros(*emb.shape, like=x)
-        T.embed_bwd_(demb, dx, ids_tm)
+            w.w_ih[d], w.w_hh[d] = ops._p(gru[4 * d].detach()), ops._p(gru[4 * d + 1].detach())
+            w.b_ih[d], w.b_hh[d] = ops._p(gru[4 * d + 2].detach()), ops._p(gru[4 * d + 3].detach())
+        lens = (C.c_int32 * B)(*lengths)
+        demb = torch.empty_like(emb)
+        grads = [torch.empty_like(p) for p in gru]
+        arr = lambda idx: (C.c_void_p * 2)(grads[idx].data_ptr(), grads[4 + idx].data_ptr())
+        ws = ops.workspace(lib.vag_encoder_train_workspace_bytes(B, Tn, E, H), dev)
+        with on_device(dev):
+            ops.check(lib.vag_encoder_bwd_f32(C.byref(w), lens, B, Tn, ctx.data_ptr(), dctx.contiguous().data_ptr(), x.data_ptr(),
+                                              ids_tm.data_ptr(), gi.data_ptr(), gh.data_ptr(), demb.data_ptr(), arr(0), arr(1), arr(2),
+                                              arr(3), ws.data_ptr(), ws.numel(), ops.stream_ptr()))
         return (None, None, demb, *grads)
 
 
@@ -209,148 +188,91 @@ class DecoderInitFn(torch.autograd.Function):
 
 
 # ---------------------------------------------------------------------------------------------------- decoder loop
+_PARAM_FIELDS = ("emb", "gru1_w_ih", "gru1_w_hh", "gru1_b_ih", "gru1_b_hh", "attn_h_w", "attn_e_w", "attn_v", "c2h_w", "gru2_w_ih",
+                 "gru2_w_hh", "gru2_b_ih", "gru2_b_hh", "w1_w", "w1_b", "w2_w", "w2_b", "w3_w", "w3_b", "out_w", "out_b")
+
+
 class DecoderSeqFn(torch.autograd.Function):
-    """(h0 [B,H], ctx [B,T,C], mask [B,T], tgt [B,Tt]) → Σ_t NLL rows [B]   (V11:136-160, NMT_Decoder.py:109-145)."""
+    """(h0 [B,H], ctx [B,T,C], mask [B,T], tgt [B,Tt]) → Σ_t NLL rows [B]   (V11:136-160, NMT_Decoder.py:109-145).
+
+    Forward and backward are ONE C call each (vag_decoder_seq_fwd_f32 / vag_decoder_seq_bwd_f32): the Tt-step loop,
+    the batched read-out / vocabulary projection / NLL and the whole BPTT run inside libvagnmt.so.
+    """
 
     @staticmethod
-    def forward(fctx, h0, enc, mask, tgt, weight, teacher, tied, emb, g1_wih, g1_whh, g1_bih, g1_bhh, attn_h, attn_e, v, c2h,
-                g2_wih, g2_whh, g2_bih, g2_bhh, w1, b1, w2, b2, w3, b3, out_w, out_b):
+    def forward(fctx, h0, enc, mask, tgt, weight, teacher, tied, *params):
+        import ctypes as C
+        from ._cabi import DecoderGrads, DecoderSeqSaved, DecoderWeights
+        lib = ops._cabi.lib()
         B, Tt = tgt.shape
-        _, Tn, C = enc.shape
+        _, Tn, Cd = enc.shape
+        emb, out_w = params[0], params[19]
         H, E, V = h0.shape[1], emb.shape[1], out_w.shape[0]
         dev = h0.device
-        tgt_t = tgt.t().contiguous()                                   # [Tt, B]
+        h0, enc, mask = h0.contiguous(), enc.contiguous(), mask.contiguous()
+        tgt_t = tgt.t().contiguous()
         tok_in = torch.empty(Tt, B, dtype=torch.int64, device=dev)
         tok_in[0].fill_(SOS_token)
-        keys = _lin(enc.view(B * Tn, C), attn_e).view(B, Tn, C)        # hoisted attn_e(ctx), NMT_Decoder.py:47
-        gh1_all, gi2_all, gh2_all = (_empty(Tt, B, 3 * H, like=h0) for _ in range(3))
-        h1_all, x2_all, h2_all = (_empty(Tt, B, H, like=h0) for _ in range(3))
-        q_all, c_all = _empty(Tt, B, C, like=h0), _empty(Tt, B, C, like=h0)
-        alpha_all = _empty(Tt, B, Tn, like=h0)
-        loss_rows = _zeros(B, like=h0)
-        lse_all = _empty(Tt, B, like=h0)
-        ldl = (V + 3) // 4 * 4
-        logits_all = _empty(Tt * B, ldl, like=h0)[:, :V]
-        if teacher:
+        if teacher and Tt > 1:
             tok_in[1:].copy_(tgt_t[:-1])
-            e_all = ops.embed_rows(emb, tok_in.reshape(-1))            # [Tt·B, E]
-            gi1_all = _lin(e_all, g1_wih, g1_bih).view(Tt, B, 3 * H)
-        else:
-            e_all = _empty(Tt * B, E, like=h0)
-            gi1_all = _empty(Tt, B, 3 * H, like=h0)
-            t_all = _empty(Tt * B, E, like=h0)
-        h = h0
-        for s in range(Tt):
-            if not teacher:
-                e_s = e_all[s * B:(s + 1) * B]
-                e_s.copy_(ops.embed_rows(emb, tok_in[s]))
-                ops.linear(e_s, g1_wih, g1_bih, out=gi1_all[s])
-            ops.linear(h, g1_whh, g1_bhh, out=gh1_all[s])
-            ops.gru_gates(gi1_all[s], gh1_all[s], h, out=h1_all[s])
-            ops.linear(h1_all[s], attn_h, out=q_all[s])
-            ops.attention(q_all[s], keys, enc, v, mask, 1, ops.ATTN_MLP, out_c=c_all[s], out_alpha=alpha_all[s])
-            ops.linear(c_all[s], c2h, out=x2_all[s])
-            ops.linear(x2_all[s], g2_wih, g2_bih, out=gi2_all[s])
-            ops.linear(h1_all[s], g2_whh, g2_bhh, out=gh2_all[s])
-            ops.gru_gates(gi2_all[s], gh2_all[s], h1_all[s], out=h2_all[s])
-            h = h2_all[s]
-            if not teacher:                                             # free running: the next input is this step's argmax
-                t_s = t_all[s * B:(s + 1) * B]
-                ops.linear(h, w1, b1, out=t_s)
-                ops.linear(e_all[s * B:(s + 1) * B], w3, b3, flags=ops.LIN_ACCUMULATE, out=t_s)
-                ops.linear(c_all[s], w2, b2, flags=ops.LIN_ACCUMULATE | ops.LIN_TANH, out=t_s)
-                lg = logits_all[s * B:(s + 1) * B]
-                ops.linear(t_s, out_w, out_b, out=lg)
-                if s + 1 < Tt:
-                    tok_in[s + 1].copy_(ops.row_argmax(lg))
-        if teacher:                                                     # read-out + vocabulary projection for all steps at once
-            t_all = _lin(h2_all.view(Tt * B, H), w1, b1)
-            _lin(e_all, w3, b3, flags=ops.LIN_ACCUMULATE, out=t_all)
-            _lin(c_all.view(Tt * B, C), w2, b2, flags=ops.LIN_ACCUMULATE | ops.LIN_TANH, out=t_all)
-            _lin(t_all, out_w, out_b, out=logits_all)
-        for s in range(Tt):
-            ops.nll_rows(logits_all[s * B:(s + 1) * B], tgt_t[s], weight, loss_rows, lse_all[s])
-        fctx.save_for_backward(h0, enc, mask, tgt_t, tok_in, keys, e_all, gi1_all, gh1_all, h1_all, q_all, alpha_all, c_all, x2_all,
-                               gi2_all, gh2_all, h2_all, t_all, logits_all, lse_all, emb, g1_wih, g1_whh, attn_h, attn_e, v, c2h,
-                               g2_wih, g2_whh, w1, w2, w3, out_w, weight if weight is not None else lse_all)
-        fctx.meta = (weight is not None, tied)
+        w = DecoderWeights()
+        w.E, w.H, w.C, w.V = E, H, Cd, V
+        for name, p in zip(_PARAM_FIELDS, params):
+            setattr(w, name, ops._p(p.detach()))
+        ldl = (V + 3) // 4 * 4
+        sizes = dict(keys=B * Tn * Cd, e_all=Tt * B * E, gi1_all=Tt * B * 3 * H, gh1_all=Tt * B * 3 * H, h1_all=Tt * B * H,
+                     q_all=Tt * B * Cd, alpha_all=Tt * B * Tn, c_all=Tt * B * Cd, x2_all=Tt * B * H, gi2_all=Tt * B * 3 * H,
+                     gh2_all=Tt * B * 3 * H, h2_all=Tt * B * H, t_all=Tt * B * E, logits_all=Tt * B * ldl, lse_all=Tt * B)
+        offs, total = {}, 0
+        for k, n in sizes.items():
+            offs[k] = total
+            total += (n + 63) // 64 * 64
+        store = torch.empty(total, dtype=torch.float32, device=dev)       # one allocation for every saved activation
+        saved = DecoderSeqSaved()
+        saved.ld_logits = ldl
+        for k in sizes:
+            setattr(saved, k, store.data_ptr() + 4 * offs[k])
+        loss_rows = torch.empty(B, dtype=torch.float32, device=dev)
+        ws = ops.workspace(lib.vag_decoder_seq_workspace_bytes(B, Tn, Tt, E, H, Cd, V), dev)
+        with on_device(dev):
+            ops.check(lib.vag_decoder_seq_fwd_f32(C.byref(w), h0.data_ptr(), enc.data_ptr(), mask.data_ptr(), tok_in.data_ptr(),
+                                                  tgt_t.data_ptr(), ops.ptr(weight), B, Tn, Tt, 1 if teacher else 0, C.byref(saved),
+                                                  loss_rows.data_ptr(), ws.data_ptr(), ws.numel(), ops.stream_ptr()))
+        fctx.save_for_backward(h0, enc, mask, tgt_t, tok_in, store, weight if weight is not None else loss_rows, *params)
+        fctx.meta = (weight is not None, bool(tied), offs, ldl, (B, Tn, Tt, E, H, Cd, V))
         return loss_rows
 
     @staticmethod
     def backward(fctx, dloss_rows):
-        (h0, enc, mask, tgt_t, tok_in, keys, e_all, gi1_all, gh1_all, h1_all, q_all, alpha_all, c_all, x2_all, gi2_all, gh2_all,
-         h2_all, t_all, logits_all, lse_all, emb, g1_wih, g1_whh, attn_h, attn_e, v, c2h, g2_wih, g2_whh, w1, w2, w3, out_w,
-         weight) = fctx.saved_tensors
-        has_weight, tied = fctx.meta
-        weight = weight if has_weight else None
-        Tt, B = tgt_t.shape
-        _, Tn, C = enc.shape
-        H, E, V = h0.shape[1], emb.shape[1], out_w.shape[0]
-        g_rows = dloss_rows.contiguous()
-        # ---- batched over all steps: vocabulary projection and read-out
-        dlogits = _empty(Tt * B, V, like=h0)
-        for s in range(Tt):
-            dlogits[s * B:(s + 1) * B].copy_(T.nll_bwd(logits_all[s * B:(s + 1) * B], lse_all[s], tgt_t[s], weight, g_rows))
-        d_t = T.gemm(dlogits, out_w)                                    # [Tt·B, E]
-        d_out_w = T.gemm(dlogits, t_all, trans_a=True)
-        d_out_b = T.colsum(dlogits)
-        du = T.tanh_bwd(d_t, t_all)
-        h2_f, c_f = h2_all.view(Tt * B, H), c_all.view(Tt * B, C)
-        d_h2_dir = T.gemm(du, w1).view(Tt, B, H)
-        d_e = T.gemm(du, w3)                                            # [Tt·B, E]
-        d_c_dir = T.gemm(du, w2).view(Tt, B, C)
-        d_w1, d_w3, d_w2 = T.gemm(du, h2_f, trans_a=True), T.gemm(du, e_all, trans_a=True), T.gemm(du, c_f, trans_a=True)
-        d_b = T.colsum(du)                                              # b1, b2, b3 all receive Σ du
-        # ---- recurrent part, reverse time
-        dgi2_all, dgh2_all, dgi1_all, dgh1_all = (_empty(Tt, B, 3 * H, like=h0) for _ in range(4))
-        dx2_all, dq_all = _empty(Tt, B, H, like=h0), _empty(Tt, B, C, like=h0)
-        dkeys, dctx, dv = _zeros(B, Tn, C, like=h0), _zeros(B, Tn, C, like=h0), _zeros(C, like=h0)
-        dh_next = _zeros(B, H, like=h0)
-        for s in range(Tt - 1, -1, -1):
-            dh2 = d_h2_dir[s]
-            T.axpby_(dh2, dh_next, 1.0, 1.0)
-            dgi2, dgh2, dh1 = T.gru_gates_bwd(dh2, gi2_all[s], gh2_all[s], h1_all[s])
-            dgi2_all[s].copy_(dgi2)
-            dgh2_all[s].copy_(dgh2)
-            T.gemm(dgi2, g2_wih, out=dx2_all[s])                         # dx2 = dgi2·W_ih2
-            dc = d_c_dir[s]
-            T.gemm(dx2_all[s], c2h, out=dc, beta=1.0)                    # dc += dx2·W_c2h
-            dq = T.attention_bwd(dc, alpha_all[s], q_all[s], keys, enc, v, mask, dkeys, dctx, dv, ops.ATTN_MLP)
-            dq_all[s].copy_(dq)
-            T.gemm(dgh2, g2_whh, out=dh1, beta=1.0)                      # dh1 += dgh2·W_hh2 + dq·W_attn_h
-            T.gemm(dq, attn_h, out=dh1, beta=1.0)
-            h_prev = h0 if s == 0 else h2_all[s - 1]
-            dgi1, dgh1, dhp = T.gru_gates_bwd(dh1, gi1_all[s], gh1_all[s], h_prev)
-            dgi1_all[s].copy_(dgi1)
-            dgh1_all[s].copy_(dgh1)
-            T.gemm(dgh1, g1_whh, out=dhp, beta=1.0)                      # dh_prev = dh1·z + dgh1·W_hh1
-            dh_next = dhp
-        d_h0 = dh_next
-        # ---- weight gradients, batched over steps
-        dgi2_f, dgh2_f = dgi2_all.view(Tt * B, 3 * H), dgh2_all.view(Tt * B, 3 * H)
-        dgi1_f, dgh1_f = dgi1_all.view(Tt * B, 3 * H), dgh1_all.view(Tt * B, 3 * H)
-        h1_f = h1_all.view(Tt * B, H)
-        d_g2_wih, d_g2_bih = T.gemm(dgi2_f, x2_all.view(Tt * B, H), trans_a=True), T.colsum(dgi2_f)
-        d_g2_whh, d_g2_bhh = T.gemm(dgh2_f, h1_f, trans_a=True), T.colsum(dgh2_f)
-        d_c2h = T.gemm(dx2_all.view(Tt * B, H), c_f, trans_a=True)
-        d_attn_h = T.gemm(dq_all.view(Tt * B, C), h1_f, trans_a=True)
-        d_g1_wih, d_g1_bih = T.gemm(dgi1_f, e_all, trans_a=True), T.colsum(dgi1_f)
-        d_g1_whh = T.gemm(dgh1_all[0], h0, trans_a=True)
-        if Tt > 1:
-            T.gemm(dgh1_all[1:].reshape((Tt - 1) * B, 3 * H), h2_all[:-1].reshape((Tt - 1) * B, H), trans_a=True, out=d_g1_whh, beta=1.0)
-        d_g1_bhh = T.colsum(dgh1_f)
-        T.gemm(dgi1_f, g1_wih, out=d_e, beta=1.0)                        # de += dgi1·W_ih1
-        d_emb = _zeros(*emb.shape, like=h0)
-        T.embed_bwd_(d_emb, d_e, tok_in.reshape(-1))
-        if tied:                                                         # out.weight IS the embedding (NMT_Decoder.py:105-106)
-            T.axpby_(d_emb, d_out_w, 1.0, 1.0)
-            d_out_w = None
-        # ---- hoisted keys: dW_attn_e and the path back into the encoder context
-        dk_f, enc_f = dkeys.view(B * Tn, C), enc.view(B * Tn, C)
-        d_attn_e = T.gemm(dk_f, enc_f, trans_a=True)
-        T.gemm(dk_f, attn_e, out=dctx.view(B * Tn, C), beta=1.0)
-        return (d_h0, dctx, None, None, None, None, None, d_emb, d_g1_wih, d_g1_whh, d_g1_bih, d_g1_bhh, d_attn_h, d_attn_e, dv,
-                d_c2h, d_g2_wih, d_g2_whh, d_g2_bih, d_g2_bhh, d_w1, d_b, d_w2, d_b.clone(), d_w3, d_b.clone(), d_out_w, d_out_b)
+        import ctypes as C
+        from ._cabi import DecoderGrads, DecoderSeqSaved, DecoderWeights
+        lib = ops._cabi.lib()
+        h0, enc, mask, tgt_t, tok_in, store, weight, *params = fctx.saved_tensors
+        has_weight, tied, offs, ldl, (B, Tn, Tt, E, H, Cd, V) = fctx.meta
+        dev = h0.device
+        w = DecoderWeights()
+        w.E, w.H, w.C, w.V = E, H, Cd, V
+        for name, p in zip(_PARAM_FIELDS, params):
+            setattr(w, name, ops._p(p.detach()))
+        saved = DecoderSeqSaved()
+        saved.ld_logits = ldl
+        for k, o in offs.items():
+            setattr(saved, k, store.data_ptr() + 4 * o)
+        grads = [torch.empty_like(p) for p in params]
+        g = DecoderGrads()
+        for name, t in zip(_PARAM_FIELDS, grads):
+            setattr(g, name, t.data_ptr())
+        d_h0 = torch.empty_like(h0)
+        d_enc = torch.empty_like(enc)
+        ws = ops.workspace(lib.vag_decoder_seq_workspace_bytes(B, Tn, Tt, E, H, Cd, V), dev)
+        with on_device(dev):
+            ops.check(lib.vag_decoder_seq_bwd_f32(C.byref(w), h0.data_ptr(), enc.data_ptr(), mask.data_ptr(), tok_in.data_ptr(),
+                                                  tgt_t.data_ptr(), weight.data_ptr() if has_weight else None, B, Tn, Tt,
+                                                  1 if tied else 0, C.byref(saved), dloss_rows.contiguous().data_ptr(), C.byref(g),
+                                                  d_h0.data_ptr(), d_enc.data_ptr(), ws.data_ptr(), ws.numel(), ops.stream_ptr()))
+        if tied:
+            grads[19] = None          # out.weight IS the embedding: its gradient was accumulated into grads[0]
+        return (d_h0, d_enc, None, None, None, None, None, *grads)
 
 
 # ---------------------------------------------------------------------------------------------------- loss epilogue

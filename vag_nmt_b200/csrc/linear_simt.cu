@@ -169,7 +169,21 @@ linear_skinny_kernel(float* __restrict__ y, int64_t ldy, const float* __restrict
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[r] = 0.f;
     const float* wr = w + (int64_t)warp * ldw;
-    for (int k = lane; k < K; k += 32) {
+    int k = lane;
+    for (; k + 96 < K; k += 128) {   // four independent K slices in flight per lane (memory-level parallelism)
+        float wv[4], xv[R][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) wv[u] = wr[k + 32 * u];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) xv[r][u] = (r0 + r < rows) ? x[(int64_t)(r0 + r) * ldx + k + 32 * u] : 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[r] = fmaf(xv[r][u], wv[u], acc[r]);
+    }
+    for (; k < K; k += 32) {
         float wv = wr[k];
 #pragma unroll
         for (int r = 0; r < R; ++r)

@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include <math.h>
 #include <algorithm>
+#include <vector>
 
 namespace vag {
 
@@ -119,6 +120,9 @@ attention_bwd_kernel(float* __restrict__ dq, int64_t ld_dq, float* __restrict__ 
     float* da = sm;          // [T]
     float* red = sm + T;     // [8]
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    // blockIdx.y selects a 256-channel slab: every CTA of a sentence recomputes the (cheap) softmax backward but only
+    // touches dctx / dkeys / dq / dv inside its own slab, so the expensive score backward spreads over B·C/256 CTAs
+    const int c_lo = blockIdx.y * 256, c_hi = min(C, c_lo + 256);
     const float* key_b = keys + (int64_t)b * T * C;
     const float* ctx_b = ctx + (int64_t)b * T * C;
     float* dkey_b = dkeys + (int64_t)b * T * C;
@@ -135,7 +139,7 @@ attention_bwd_kernel(float* __restrict__ dq, int64_t ld_dq, float* __restrict__ 
             for (int c = lane; c < C; c += 32) {
                 const float g = dcb[c];
                 p = fmaf(g, ctx_b[(int64_t)t * C + c], p);
-                if (dctx_b) dctx_b[(int64_t)t * C + c] += a * g;
+                if (dctx_b && c >= c_lo && c < c_hi) dctx_b[(int64_t)t * C + c] += a * g;
             }
         }
         p = warp_sum(p);
@@ -154,7 +158,7 @@ attention_bwd_kernel(float* __restrict__ dq, int64_t ld_dq, float* __restrict__ 
     for (int t = tid; t < T; t += 256) da[t] = al[t] * (da[t] - dot);
     __syncthreads();
     // through the score
-    for (int c = tid; c < C; c += 256) {
+    for (int c = c_lo + tid; c < c_hi; c += 256) {
         float dqc = 0.f, dvc = 0.f;
         const float qc = qb[c];
         const float vc = MODE == VAG_ATTN_MLP ? v[c] : 0.f;
@@ -350,9 +354,9 @@ extern "C" int vag_attention_bwd_f32(float* dq, int64_t ld_dq, float* dkeys, flo
     if (B == 0) return VAG_OK;
     const size_t smem = (size_t)(T + 8) * sizeof(float);
     if (mode == VAG_ATTN_MLP)
-        attention_bwd_kernel<VAG_ATTN_MLP><<<B, 256, smem, (cudaStream_t)stream>>>(dq, ld_dq, dkeys, dctx, dv, dc, ld_dc, alpha, q, ld_q, keys, ctx, v, mask, T, C);
+        attention_bwd_kernel<VAG_ATTN_MLP><<<dim3(B, ceil_div(C, 256)), 256, smem, (cudaStream_t)stream>>>(dq, ld_dq, dkeys, dctx, dv, dc, ld_dc, alpha, q, ld_q, keys, ctx, v, mask, T, C);
     else
-        attention_bwd_kernel<VAG_ATTN_DOT><<<B, 256, smem, (cudaStream_t)stream>>>(dq, ld_dq, dkeys, dctx, dv, dc, ld_dc, alpha, q, ld_q, keys, ctx, v, mask, T, C);
+        attention_bwd_kernel<VAG_ATTN_DOT><<<dim3(B, ceil_div(C, 256)), 256, smem, (cudaStream_t)stream>>>(dq, ld_dq, dkeys, dctx, dv, dc, ld_dc, alpha, q, ld_q, keys, ctx, v, mask, T, C);
     VAG_LAUNCH_CHECK();
     return VAG_OK;
 }
@@ -435,5 +439,365 @@ extern "C" int vag_clip_adam_f32(float* param, const float* grad, float* exp_avg
     clip_adam_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, grad_sumsq, clip, lr, beta1,
                                                                     beta2, eps, weight_decay, bc1, bc2_sqrt);
     VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
+// ==========================================================================================================
+// Sequence-level composites: the whole Tt-step decoder loop (forward with saved activations, and its BPTT) in
+// one C call each, so a training step costs a handful of host calls instead of one per kernel.
+// Reference: V11.forward :136-160 + autograd.  Buffers are caller-owned (vag_decoder_seq_saved).
+// ==========================================================================================================
+#include "gemm_ctx.cuh"
+
+namespace vag {
+int row_argmax(const float* logits, int64_t ld, int rows, int64_t V, int64_t* out, int64_t out_stride, int64_t* next_in,
+               cudaStream_t st);
+static int gemm_g(float* C, int64_t ldc, const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn, int M,
+                  int N, int K, float beta, cudaStream_t st) {
+    return vag_gemm_f32(C, ldc, A, sam, sak, B, sbk, sbn, M, N, K, 1.0f, beta, (vag_stream_t)st);
+}
+}  // namespace vag
+
+extern "C" size_t vag_decoder_seq_workspace_bytes(int B, int T, int Tt, int E, int H, int C, int64_t V) {
+    const int64_t R = (int64_t)B * Tt;
+    size_t fwd = GemmCtx::split_bytes(3 * H, E) + 3 * GemmCtx::split_bytes(3 * H, H) + GemmCtx::split_bytes(C, H) +
+                 GemmCtx::split_bytes(H, C) + GemmCtx::split_bytes(E, H) + GemmCtx::split_bytes(E, E) + GemmCtx::split_bytes(E, C) +
+                 GemmCtx::split_bytes(V, E) + GemmCtx::split_bytes(C, C) + 65536;
+    fwd += GemmCtx::split_bytes(R, E) * 2 + GemmCtx::split_bytes(R, H) + GemmCtx::split_bytes(R, C) + GemmCtx::split_bytes((int64_t)B * T, C) + 65536;
+    // backward scratch: dlogits [R, V], d_t / du [R, E] x2, dH2_dir [R, H], dE [R, E], dC_dir [R, C], per-step grads
+    size_t bwd = (size_t)R * V * 4 + (size_t)R * E * 4 * 3 + (size_t)R * H * 4 * 2 + (size_t)R * C * 4 * 2 + (size_t)R * 3 * H * 4 * 4 +
+                 (size_t)B * T * C * 4 + (size_t)B * H * 4 * 4 + (size_t)B * 3 * H * 4 * 4 + 65536;
+    return fwd > bwd ? fwd : bwd;
+}
+
+extern "C" int vag_decoder_seq_fwd_f32(const vag_decoder_weights* w, const float* h0, const float* enc, const float* mask,
+                                       int64_t* tok_in, const int64_t* tgt_t, const float* nll_weight, int B, int T, int Tt,
+                                       int teacher, const vag_decoder_seq_saved* s, float* loss_rows, void* workspace,
+                                       size_t workspace_bytes, vag_stream_t stream) {
+    VAG_REQUIRE(w && h0 && enc && mask && tok_in && tgt_t && s && loss_rows, "vag_decoder_seq_fwd_f32: null pointer");
+    VAG_REQUIRE(B > 0 && T > 0 && Tt > 0, "vag_decoder_seq_fwd_f32: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int E = w->E, H = w->H, C = w->C;
+    const int64_t V = w->V;
+    const int R = B * Tt;
+    const int64_t ldl = s->ld_logits;
+    Arena ar(workspace, workspace_bytes);
+    const size_t wb = GemmCtx::split_bytes(3 * H, E) + 3 * GemmCtx::split_bytes(3 * H, H) + GemmCtx::split_bytes(C, H) +
+                      GemmCtx::split_bytes(H, C) + GemmCtx::split_bytes(E, H) + GemmCtx::split_bytes(E, E) + GemmCtx::split_bytes(E, C) +
+                      GemmCtx::split_bytes(V, E) + GemmCtx::split_bytes(C, C) + 32768;
+    void* wr = ar.take<char>(wb);
+    const size_t ab = ar.overflow ? 0 : (workspace_bytes > align_up(ar.off, 256) + 1024 ? workspace_bytes - align_up(ar.off, 256) - 512 : 0);
+    void* areg = ab ? ar.take<char>(ab) : nullptr;
+    GemmCtx gemm(st, ar.overflow ? nullptr : wr, wb, ar.overflow ? nullptr : areg, ab);
+    vag_stream_t vs = stream;
+    // hoisted keys
+    VAG_TRY(gemm.linear(s->keys, C, enc, C, w->attn_e_w, C, nullptr, B * T, C, C, 0));
+    if (teacher) {   // all input embeddings and their W_ih projection at once
+        gemm.new_step();
+        VAG_TRY(vag_embed_rows_f32(s->e_all, E, w->emb, E, tok_in, R, V, vs));
+        VAG_TRY(gemm.linear(s->gi1_all, 3 * H, s->e_all, E, w->gru1_w_ih, E, w->gru1_b_ih, R, E, 3 * H, 0));
+    }
+    const float* h = h0;
+    for (int t = 0; t < Tt; ++t) {
+        gemm.new_step();
+        float* e_s = s->e_all + (size_t)t * B * E;
+        float* gi1 = s->gi1_all + (size_t)t * B * 3 * H;
+        float* gh1 = s->gh1_all + (size_t)t * B * 3 * H;
+        float* h1 = s->h1_all + (size_t)t * B * H;
+        float* q = s->q_all + (size_t)t * B * C;
+        float* c = s->c_all + (size_t)t * B * C;
+        float* x2 = s->x2_all + (size_t)t * B * H;
+        float* gi2 = s->gi2_all + (size_t)t * B * 3 * H;
+        float* gh2 = s->gh2_all + (size_t)t * B * 3 * H;
+        float* h2 = s->h2_all + (size_t)t * B * H;
+        if (!teacher) {
+            VAG_TRY(vag_embed_rows_f32(e_s, E, w->emb, E, tok_in + (size_t)t * B, B, V, vs));
+            VAG_TRY(gemm.linear(gi1, 3 * H, e_s, E, w->gru1_w_ih, E, w->gru1_b_ih, B, E, 3 * H, 0));
+        }
+        VAG_TRY(gemm.linear(gh1, 3 * H, h, H, w->gru1_w_hh, H, w->gru1_b_hh, B, H, 3 * H, 0));
+        VAG_TRY(vag_gru_gates_f32(h1, H, nullptr, 0, gi1, 3 * H, gh1, 3 * H, h, H, B, H, vs));
+        VAG_TRY(gemm.linear(q, C, h1, H, w->attn_h_w, H, nullptr, B, H, C, 0));
+        VAG_TRY(vag_attention_f32(c, C, s->alpha_all + (size_t)t * B * T, q, C, s->keys, enc, w->attn_v, mask, B, 1, T, C, VAG_ATTN_MLP, vs));
+        VAG_TRY(gemm.linear(x2, H, c, C, w->c2h_w, C, nullptr, B, C, H, 0));
+        VAG_TRY(gemm.linear(gi2, 3 * H, x2, H, w->gru2_w_ih, H, w->gru2_b_ih, B, H, 3 * H, 0));
+        VAG_TRY(gemm.linear(gh2, 3 * H, h1, H, w->gru2_w_hh, H, w->gru2_b_hh, B, H, 3 * H, 0));
+        VAG_TRY(vag_gru_gates_f32(h2, H, nullptr, 0, gi2, 3 * H, gh2, 3 * H, h1, H, B, H, vs));
+        h = h2;
+        if (!teacher) {   // free running (V11:149-160): this step's arg-max is the next input
+            float* t_s = s->t_all + (size_t)t * B * E;
+            float* lg = s->logits_all + (size_t)t * B * ldl;
+            VAG_TRY(gemm.linear(t_s, E, h2, H, w->w1_w, H, w->w1_b, B, H, E, 0));
+            VAG_TRY(gemm.linear(t_s, E, e_s, E, w->w3_w, E, w->w3_b, B, E, E, VAG_LIN_ACCUMULATE));
+            VAG_TRY(gemm.linear(t_s, E, c, C, w->w2_w, C, w->w2_b, B, C, E, VAG_LIN_ACCUMULATE | VAG_LIN_TANH));
+            VAG_TRY(gemm.linear(lg, ldl, t_s, E, w->out_w, E, w->out_b, B, E, (int)V, 0));
+            if (t + 1 < Tt) VAG_TRY(row_argmax(lg, ldl, B, V, tok_in + (size_t)(t + 1) * B, 1, nullptr, st));
+        }
+    }
+    if (teacher) {   // read-out and vocabulary projection for all steps at once
+        gemm.new_step();
+        VAG_TRY(gemm.linear(s->t_all, E, s->h2_all, H, w->w1_w, H, w->w1_b, R, H, E, 0));
+        VAG_TRY(gemm.linear(s->t_all, E, s->e_all, E, w->w3_w, E, w->w3_b, R, E, E, VAG_LIN_ACCUMULATE));
+        VAG_TRY(gemm.linear(s->t_all, E, s->c_all, C, w->w2_w, C, w->w2_b, R, C, E, VAG_LIN_ACCUMULATE | VAG_LIN_TANH));
+        gemm.new_step();
+        VAG_TRY(gemm.linear(s->logits_all, ldl, s->t_all, E, w->out_w, E, w->out_b, R, E, (int)V, 0));
+    }
+    VAG_CUDA(cudaMemsetAsync(loss_rows, 0, sizeof(float) * (size_t)B, st));
+    for (int t = 0; t < Tt; ++t)
+        VAG_TRY(vag_nll_rows_f32(s->logits_all + (size_t)t * B * ldl, ldl, tgt_t + (size_t)t * B, nll_weight, B, V, loss_rows,
+                                 s->lse_all + (size_t)t * B, vs));
+    return VAG_OK;
+}
+
+extern "C" int vag_decoder_seq_bwd_f32(const vag_decoder_weights* w, const float* h0, const float* enc, const float* mask,
+                                       const int64_t* tok_in, const int64_t* tgt_t, const float* nll_weight, int B, int T, int Tt,
+                                       int tied, const vag_decoder_seq_saved* s, const float* dloss_rows,
+                                       const vag_decoder_grads* g, float* d_h0, float* d_enc, void* workspace,
+                                       size_t workspace_bytes, vag_stream_t stream) {
+    VAG_REQUIRE(w && h0 && enc && mask && tok_in && tgt_t && s && dloss_rows && g && d_h0 && d_enc, "vag_decoder_seq_bwd_f32: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    vag_stream_t vs = stream;
+    const int E = w->E, H = w->H, C = w->C;
+    const int64_t V = w->V;
+    const int R = B * Tt;
+    const int64_t ldl = s->ld_logits;
+    Arena ar(workspace, workspace_bytes);
+    float* dlogits = ar.take<float>((size_t)R * V);
+    float* d_t = ar.take<float>((size_t)R * E);
+    float* du = ar.take<float>((size_t)R * E);
+    float* dh2_dir = ar.take<float>((size_t)R * H);
+    float* d_e = ar.take<float>((size_t)R * E);
+    float* dc_dir = ar.take<float>((size_t)R * C);
+    float* dgi2_all = ar.take<float>((size_t)R * 3 * H);
+    float* dgh2_all = ar.take<float>((size_t)R * 3 * H);
+    float* dgi1_all = ar.take<float>((size_t)R * 3 * H);
+    float* dgh1_all = ar.take<float>((size_t)R * 3 * H);
+    float* dx2_all = ar.take<float>((size_t)R * H);
+    float* dq_all = ar.take<float>((size_t)R * C);
+    float* dkeys = ar.take<float>((size_t)B * T * C);
+    float* dh1 = ar.take<float>((size_t)B * H);
+    float* dh_next = ar.take<float>((size_t)B * H);
+    if (ar.overflow) {
+        set_error("vag_decoder_seq_bwd_f32: workspace %zu B too small", workspace_bytes);
+        return VAG_ERR_WORKSPACE;
+    }
+    // ---- batched over all steps: vocabulary projection and read-out
+    for (int t = 0; t < Tt; ++t)
+        VAG_TRY(vag_nll_bwd_f32(dlogits + (size_t)t * B * V, V, s->logits_all + (size_t)t * B * ldl, ldl, s->lse_all + (size_t)t * B,
+                                tgt_t + (size_t)t * B, nll_weight, dloss_rows, B, V, vs));
+    VAG_TRY(gemm_g(d_t, E, dlogits, V, 1, w->out_w, E, 1, R, E, (int)V, 0.f, st));                 // d_t = dlogits · out_w
+    float* d_out_w = tied ? g->emb : g->out_w;                                                       // tied: accumulate into dEmb later
+    VAG_CUDA(cudaMemsetAsync(g->emb, 0, sizeof(float) * (size_t)V * E, st));
+    VAG_TRY(gemm_g(d_out_w, E, dlogits, 1, V, s->t_all, E, 1, (int)V, E, R, 0.f, st));              // dlogitsᵀ · t_all
+    VAG_TRY(vag_colsum_f32(g->out_b, dlogits, V, R, (int)V, 0, vs));
+    VAG_TRY(vag_tanh_bwd_f32(du, d_t, s->t_all, (int64_t)R * E, vs));
+    VAG_TRY(gemm_g(dh2_dir, H, du, E, 1, w->w1_w, H, 1, R, H, E, 0.f, st));
+    VAG_TRY(gemm_g(d_e, E, du, E, 1, w->w3_w, E, 1, R, E, E, 0.f, st));
+    VAG_TRY(gemm_g(dc_dir, C, du, E, 1, w->w2_w, C, 1, R, C, E, 0.f, st));
+    VAG_TRY(gemm_g(g->w1_w, H, du, 1, E, s->h2_all, H, 1, E, H, R, 0.f, st));
+    VAG_TRY(gemm_g(g->w3_w, E, du, 1, E, s->e_all, E, 1, E, E, R, 0.f, st));
+    VAG_TRY(gemm_g(g->w2_w, C, du, 1, E, s->c_all, C, 1, E, C, R, 0.f, st));
+    VAG_TRY(vag_colsum_f32(g->w1_b, du, E, R, E, 0, vs));
+    VAG_CUDA(cudaMemcpyAsync(g->w2_b, g->w1_b, sizeof(float) * E, cudaMemcpyDeviceToDevice, st));
+    VAG_CUDA(cudaMemcpyAsync(g->w3_b, g->w1_b, sizeof(float) * E, cudaMemcpyDeviceToDevice, st));
+    // ---- recurrent part, reverse time
+    VAG_CUDA(cudaMemsetAsync(dkeys, 0, sizeof(float) * (size_t)B * T * C, st));
+    VAG_CUDA(cudaMemsetAsync(d_enc, 0, sizeof(float) * (size_t)B * T * C, st));
+    VAG_CUDA(cudaMemsetAsync(g->attn_v, 0, sizeof(float) * C, st));
+    VAG_CUDA(cudaMemsetAsync(dh_next, 0, sizeof(float) * (size_t)B * H, st));
+    for (int t = Tt - 1; t >= 0; --t) {
+        float* dh2 = dh2_dir + (size_t)t * B * H;
+        VAG_TRY(vag_axpby_f32(dh2, dh_next, 1.f, 1.f, (int64_t)B * H, vs));
+        float* dgi2 = dgi2_all + (size_t)t * B * 3 * H;
+        float* dgh2 = dgh2_all + (size_t)t * B * 3 * H;
+        const float* h1 = s->h1_all + (size_t)t * B * H;
+        VAG_TRY(vag_gru_gates_bwd_f32(dgi2, dgh2, dh1, dh2, H, s->gi2_all + (size_t)t * B * 3 * H, s->gh2_all + (size_t)t * B * 3 * H, h1, H, B, H, vs));
+        float* dx2 = dx2_all + (size_t)t * B * H;
+        VAG_TRY(gemm_g(dx2, H, dgi2, 3 * H, 1, w->gru2_w_ih, H, 1, B, H, 3 * H, 0.f, st));             // dx2 = dgi2 · W_ih2
+        float* dc = dc_dir + (size_t)t * B * C;
+        VAG_TRY(gemm_g(dc, C, dx2, H, 1, w->c2h_w, C, 1, B, C, H, 1.f, st));                            // dc += dx2 · W_c2h
+        float* dq = dq_all + (size_t)t * B * C;
+        VAG_TRY(vag_attention_bwd_f32(dq, C, dkeys, d_enc, g->attn_v, dc, C, s->alpha_all + (size_t)t * B * T, s->q_all + (size_t)t * B * C,
+                                      C, s->keys, enc, w->attn_v, mask, B, T, C, VAG_ATTN_MLP, vs));
+        VAG_TRY(gemm_g(dh1, H, dgh2, 3 * H, 1, w->gru2_w_hh, H, 1, B, H, 3 * H, 1.f, st));              // dh1 += dgh2 · W_hh2
+        VAG_TRY(gemm_g(dh1, H, dq, C, 1, w->attn_h_w, H, 1, B, H, C, 1.f, st));                         //      + dq · W_attn_h
+        const float* h_prev = t == 0 ? h0 : s->h2_all + (size_t)(t - 1) * B * H;
+        float* dgi1 = dgi1_all + (size_t)t * B * 3 * H;
+        float* dgh1 = dgh1_all + (size_t)t * B * 3 * H;
+        VAG_TRY(vag_gru_gates_bwd_f32(dgi1, dgh1, dh_next, dh1, H, s->gi1_all + (size_t)t * B * 3 * H, s->gh1_all + (size_t)t * B * 3 * H, h_prev, H, B, H, vs));
+        VAG_TRY(gemm_g(dh_next, H, dgh1, 3 * H, 1, w->gru1_w_hh, H, 1, B, H, 3 * H, 1.f, st));          // dh_prev = dh1·z + dgh1 · W_hh1
+    }
+    VAG_CUDA(cudaMemcpyAsync(d_h0, dh_next, sizeof(float) * (size_t)B * H, cudaMemcpyDeviceToDevice, st));
+    // ---- weight gradients, batched over steps
+    VAG_TRY(gemm_g(g->gru2_w_ih, H, dgi2_all, 1, 3 * H, s->x2_all, H, 1, 3 * H, H, R, 0.f, st));
+    VAG_TRY(vag_colsum_f32(g->gru2_b_ih, dgi2_all, 3 * H, R, 3 * H, 0, vs));
+    VAG_TRY(gemm_g(g->gru2_w_hh, H, dgh2_all, 1, 3 * H, s->h1_all, H, 1, 3 * H, H, R, 0.f, st));
+    VAG_TRY(vag_colsum_f32(g->gru2_b_hh, dgh2_all, 3 * H, R, 3 * H, 0, vs));
+    VAG_TRY(gemm_g(g->c2h_w, C, dx2_all, 1, H, s->c_all, C, 1, H, C, R, 0.f, st));
+    VAG_TRY(gemm_g(g->attn_h_w, H, dq_all, 1, C, s->h1_all, H, 1, C, H, R, 0.f, st));
+    VAG_TRY(gemm_g(g->gru1_w_ih, E, dgi1_all, 1, 3 * H, s->e_all, E, 1, 3 * H, E, R, 0.f, st));
+    VAG_TRY(vag_colsum_f32(g->gru1_b_ih, dgi1_all, 3 * H, R, 3 * H, 0, vs));
+    VAG_TRY(gemm_g(g->gru1_w_hh, H, dgh1_all, 1, 3 * H, h0, H, 1, 3 * H, H, B, 0.f, st));
+    if (Tt > 1)
+        VAG_TRY(gemm_g(g->gru1_w_hh, H, dgh1_all + (size_t)B * 3 * H, 1, 3 * H, s->h2_all, H, 1, 3 * H, H, (Tt - 1) * B, 1.f, st));
+    VAG_TRY(vag_colsum_f32(g->gru1_b_hh, dgh1_all, 3 * H, R, 3 * H, 0, vs));
+    VAG_TRY(gemm_g(d_e, E, dgi1_all, 3 * H, 1, w->gru1_w_ih, E, 1, R, E, 3 * H, 1.f, st));              // de += dgi1 · W_ih1
+    VAG_TRY(vag_embed_bwd_f32(g->emb, d_e, E, tok_in, R, E, V, vs));                                     // (+ dOutW already inside when tied)
+    // ---- hoisted keys: dW_attn_e and the path back into the encoder context
+    VAG_TRY(gemm_g(g->attn_e_w, C, dkeys, 1, C, enc, C, 1, C, C, B * T, 0.f, st));
+    VAG_TRY(gemm_g(d_enc, C, dkeys, C, 1, w->attn_e_w, C, 1, B * T, C, C, 1.f, st));
+    return VAG_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// Encoder training pair: forward that keeps what BPTT needs (time-major embeddings, gi, per-step gh), and the
+// backward through both directions of the packed bi-GRU (layers/Encoder.py:36-65 under autograd).
+// ----------------------------------------------------------------------------------------------------------
+namespace vag {
+__global__ void encoder_embed_tm_kernel(float* __restrict__ out, const float* __restrict__ table, const int64_t* __restrict__ src,
+                                        int64_t* __restrict__ ids_tm, int B, int T, int E, int64_t vocab) {
+    const int row = blockIdx.x * blockDim.y + threadIdx.y;  // t*B + b
+    if (row >= B * T) return;
+    const int t = row / B, b = row % B;
+    int64_t id = src[(int64_t)b * T + t];
+    if (threadIdx.x == 0) ids_tm[row] = id;
+    if (id < 0 || id >= vocab) id = 0;
+    const float* s = table + id * E;
+    float* d = out + (int64_t)row * E;
+    for (int c = threadIdx.x; c < E; c += blockDim.x) d[c] = s[c];
+}
+// dst[r, :] = src[r*ld_src + :]  rows × cols copy with row pitches (strided slice → contiguous and back)
+__global__ void copy2d_kernel(float* __restrict__ dst, int64_t ld_dst, const float* __restrict__ src, int64_t ld_src, int rows, int cols) {
+    const int64_t total = (int64_t)rows * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / cols), c = (int)(i % cols);
+        dst[(int64_t)r * ld_dst + c] = src[(int64_t)r * ld_src + c];
+    }
+}
+static int copy2d(float* dst, int64_t ld_dst, const float* src, int64_t ld_src, int rows, int cols, cudaStream_t st) {
+    if (rows == 0) return VAG_OK;
+    copy2d_kernel<<<grid_for((int64_t)rows * cols), 256, 0, st>>>(dst, ld_dst, src, ld_src, rows, cols);
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+}  // namespace vag
+
+extern "C" size_t vag_encoder_train_workspace_bytes(int B, int T, int E, int H) {
+    return 2 * (GemmCtx::split_bytes(3 * H, E) + GemmCtx::split_bytes(3 * H, H)) + GemmCtx::split_bytes((int64_t)T * B, E) +
+           (size_t)T * B * 3 * H * 4 * 2 + (size_t)T * B * H * 4 + (size_t)B * H * 4 * 8 + (size_t)B * 3 * H * 4 * 4 + 131072;
+}
+
+/* saved: x [T·B, E] time-major embeddings, ids_tm int64 [T·B], gi [2][T, B, 3H], gh [2][T, B, 3H] (zero where inactive) */
+extern "C" int vag_encoder_train_fwd_f32(const vag_encoder_weights* w, const int64_t* src, const int32_t* lengths_host, int B, int T,
+                                         float* ctx_out, float* x, int64_t* ids_tm, float* gi, float* gh, void* workspace,
+                                         size_t workspace_bytes, vag_stream_t stream) {
+    VAG_REQUIRE(w && src && lengths_host && ctx_out && x && ids_tm && gi && gh, "vag_encoder_train_fwd_f32: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int E = w->E, H = w->H;
+    for (int b = 0; b < B; ++b) {
+        VAG_REQUIRE(lengths_host[b] >= 1 && lengths_host[b] <= T, "vag_encoder_train_fwd_f32: bad length");
+        VAG_REQUIRE(b == 0 || lengths_host[b] <= lengths_host[b - 1], "vag_encoder_train_fwd_f32: lengths must be sorted in decreasing order");
+    }
+    Arena ar(workspace, workspace_bytes);
+    const size_t wb = 2 * (GemmCtx::split_bytes(3 * H, E) + GemmCtx::split_bytes(3 * H, H)) + 8192;
+    const size_t ab = GemmCtx::split_bytes((int64_t)T * B, E) + 8192;
+    void* wr = ar.take<char>(wb);
+    void* areg = ar.take<char>(ab);
+    float* h = ar.take<float>((size_t)2 * B * H);
+    if (ar.overflow) {
+        set_error("vag_encoder_train_fwd_f32: workspace too small");
+        return VAG_ERR_WORKSPACE;
+    }
+    GemmCtx gemm(st, wr, wb, areg, ab);
+    {
+        dim3 block(64, 4);
+        encoder_embed_tm_kernel<<<ceil_div(B * T, 4), block, 0, st>>>(x, w->emb, src, ids_tm, B, T, E, w->vocab);
+        VAG_LAUNCH_CHECK();
+    }
+    VAG_CUDA(cudaMemsetAsync(ctx_out, 0, sizeof(float) * (size_t)B * T * 2 * H, st));
+    VAG_CUDA(cudaMemsetAsync(gh, 0, sizeof(float) * (size_t)2 * T * B * 3 * H, st));
+    VAG_CUDA(cudaMemsetAsync(h, 0, sizeof(float) * (size_t)2 * B * H, st));
+    std::vector<int> n_act(T);
+    for (int t = 0; t < T; ++t) {
+        int n = 0;
+        while (n < B && lengths_host[n] > t) ++n;
+        n_act[t] = n;
+    }
+    for (int d = 0; d < 2; ++d)
+        VAG_TRY(gemm.linear(gi + (size_t)d * T * B * 3 * H, 3 * H, x, E, w->w_ih[d], E, w->b_ih[d], T * B, E, 3 * H, 0));
+    for (int s_ = 0; s_ < T; ++s_) {
+        for (int d = 0; d < 2; ++d) {
+            const int t = d == 0 ? s_ : T - 1 - s_;
+            const int n = n_act[t];
+            if (n == 0) continue;
+            float* hd = h + (size_t)d * B * H;
+            float* gh_t = gh + ((size_t)d * T + t) * B * 3 * H;
+            gemm.new_step();
+            VAG_TRY(gemm.linear(gh_t, 3 * H, hd, H, w->w_hh[d], H, w->b_hh[d], n, H, 3 * H, 0));
+            VAG_TRY(vag_gru_gates_f32(hd, H, ctx_out + (int64_t)t * 2 * H + d * H, (int64_t)T * 2 * H,
+                                      gi + ((size_t)d * T + t) * B * 3 * H, 3 * H, gh_t, 3 * H, hd, H, n, H, stream));
+        }
+    }
+    return VAG_OK;
+}
+
+/* grads: d_emb [vocab, E] (zeroed here), d_w_ih[2] [3H,E], d_w_hh[2] [3H,H], d_b_ih[2], d_b_hh[2] [3H] */
+extern "C" int vag_encoder_bwd_f32(const vag_encoder_weights* w, const int32_t* lengths_host, int B, int T, const float* ctx,
+                                   const float* dctx, const float* x, const int64_t* ids_tm, const float* gi, const float* gh,
+                                   float* d_emb, float* const* d_w_ih, float* const* d_w_hh, float* const* d_b_ih,
+                                   float* const* d_b_hh, void* workspace, size_t workspace_bytes, vag_stream_t stream) {
+    VAG_REQUIRE(w && lengths_host && ctx && dctx && x && ids_tm && gi && gh && d_emb, "vag_encoder_bwd_f32: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    vag_stream_t vs = stream;
+    const int E = w->E, H = w->H;
+    Arena ar(workspace, workspace_bytes);
+    float* dgi_all = ar.take<float>((size_t)T * B * 3 * H);
+    float* dgh_all = ar.take<float>((size_t)T * B * 3 * H);
+    float* hprev_all = ar.take<float>((size_t)T * B * H);
+    float* dx = ar.take<float>((size_t)T * B * E);
+    float* carry = ar.take<float>((size_t)B * H);
+    float* dh = ar.take<float>((size_t)B * H);
+    float* dhp = ar.take<float>((size_t)B * H);
+    if (ar.overflow) {
+        set_error("vag_encoder_bwd_f32: workspace too small");
+        return VAG_ERR_WORKSPACE;
+    }
+    std::vector<int> n_act(T);
+    for (int t = 0; t < T; ++t) {
+        int n = 0;
+        while (n < B && lengths_host[n] > t) ++n;
+        n_act[t] = n;
+    }
+    VAG_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)T * B * E, st));
+    for (int d = 0; d < 2; ++d) {
+        VAG_CUDA(cudaMemsetAsync(dgi_all, 0, sizeof(float) * (size_t)T * B * 3 * H, st));
+        VAG_CUDA(cudaMemsetAsync(dgh_all, 0, sizeof(float) * (size_t)T * B * 3 * H, st));
+        VAG_CUDA(cudaMemsetAsync(hprev_all, 0, sizeof(float) * (size_t)T * B * H, st));
+        VAG_CUDA(cudaMemsetAsync(carry, 0, sizeof(float) * (size_t)B * H, st));
+        for (int s_ = 0; s_ < T; ++s_) {
+            const int t = d == 0 ? T - 1 - s_ : s_;           // reverse of the forward order of this direction
+            const int n = n_act[t];
+            if (n == 0) continue;
+            const int tp = d == 0 ? t - 1 : t + 1;            // where h_prev of this step was produced
+            float* hp = hprev_all + (size_t)t * B * H;
+            if (tp >= 0 && tp < T)   // rows whose chain starts here had h_prev = 0, and ctx is exactly 0 there (padding)
+                VAG_TRY(copy2d(hp, H, ctx + (int64_t)tp * 2 * H + d * H, (int64_t)T * 2 * H, n, H, st));
+            VAG_TRY(copy2d(dh, H, dctx + (int64_t)t * 2 * H + d * H, (int64_t)T * 2 * H, n, H, st));
+            VAG_TRY(vag_axpby_f32(dh, carry, 1.f, 1.f, (int64_t)n * H, vs));
+            float* dgi = dgi_all + (size_t)t * B * 3 * H;
+            float* dgh = dgh_all + (size_t)t * B * 3 * H;
+            VAG_TRY(vag_gru_gates_bwd_f32(dgi, dgh, dhp, dh, H, gi + ((size_t)d * T + t) * B * 3 * H, gh + ((size_t)d * T + t) * B * 3 * H,
+                                          hp, H, n, H, vs));
+            VAG_TRY(gemm_g(dhp, H, dgh, 3 * H, 1, w->w_hh[d], H, 1, n, H, 3 * H, 1.f, st));       // dh_prev = dh·z + dgh·W_hh
+            VAG_CUDA(cudaMemsetAsync(carry, 0, sizeof(float) * (size_t)B * H, st));
+            VAG_CUDA(cudaMemcpyAsync(carry, dhp, sizeof(float) * (size_t)n * H, cudaMemcpyDeviceToDevice, st));
+        }
+        VAG_TRY(gemm_g(dx, E, dgi_all, 3 * H, 1, w->w_ih[d], E, 1, T * B, E, 3 * H, 1.f, st));     // dx += dgi·W_ih
+        VAG_TRY(gemm_g(d_w_ih[d], E, dgi_all, 1, 3 * H, x, E, 1, 3 * H, E, T * B, 0.f, st));
+        VAG_TRY(gemm_g(d_w_hh[d], H, dgh_all, 1, 3 * H, hprev_all, H, 1, 3 * H, H, T * B, 0.f, st));
+        VAG_TRY(vag_colsum_f32(d_b_ih[d], dgi_all, 3 * H, T * B, 3 * H, 0, vs));
+        VAG_TRY(vag_colsum_f32(d_b_hh[d], dgh_all, 3 * H, T * B, 3 * H, 0, vs));
+    }
+    VAG_CUDA(cudaMemsetAsync(d_emb, 0, sizeof(float) * (size_t)w->vocab * E, st));
+    VAG_TRY(vag_embed_bwd_f32(d_emb, dx, E, ids_tm, T * B, E, w->vocab, vs));
     return VAG_OK;
 }
