@@ -300,6 +300,7 @@ int vag_nll_bwd_f32(float* dlogits, int64_t ldd, const float* logits, int64_t ld
                     const float* weight, const float* grad_rows, int rows, int64_t V, vag_stream_t stream);
 int vag_tanh_bwd_f32(float* dx, const float* dy, const float* y, int64_t n, vag_stream_t stream);          /* dx = dy·(1−y²) */
 int vag_axpby_f32(float* y, const float* x, float a, float b, int64_t n, vag_stream_t stream);             /* y = a·x + b·y */
+int vag_mul_f32(float* y, const float* m, int64_t n, vag_stream_t stream);                                /* y *= m (dropout masks) */
 int vag_colsum_f32(float* out, const float* x, int64_t ldx, int rows, int cols, int accumulate, vag_stream_t stream); /* bias grads */
 int vag_embed_bwd_f32(float* table_grad, const float* g, int64_t ldg, const int64_t* ids, int rows, int dim,
                       int64_t table_rows, vag_stream_t stream);                                             /* scatter-add */
@@ -334,27 +335,30 @@ typedef struct {              /* gradient outputs, same shapes as the weights (o
 
 size_t vag_decoder_seq_workspace_bytes(int B, int T, int Tt, int E, int H, int C, int64_t V);
 /* tok_in int64 [Tt, B]: row 0 = <sos>; teacher != 0: rows 1.. hold tgt[:, :-1] (caller fills); else the kernel's own
- * arg-max feedback is written there.  tgt_t int64 [Tt, B].  loss_rows [B] = Σ_t NLL (nn.NLLLoss(weight, reduce=False)). */
+ * arg-max feedback is written there.  tgt_t int64 [Tt, B].  loss_rows [B] = Σ_t NLL (nn.NLLLoss(weight, reduce=False)).
+ * out_mask (optional, [Tt·B, E], values 0 or 1/(1-p)): the output dropout of NMT_Decoder.py:140-141 with a caller-drawn mask. */
 int vag_decoder_seq_fwd_f32(const vag_decoder_weights* w, const float* h0, const float* enc, const float* mask,
                             int64_t* tok_in, const int64_t* tgt_t, const float* nll_weight, int B, int T, int Tt,
-                            int teacher, const vag_decoder_seq_saved* s, float* loss_rows, void* workspace,
-                            size_t workspace_bytes, vag_stream_t stream);
+                            int teacher, const vag_decoder_seq_saved* s, const float* out_mask, float* loss_rows,
+                            void* workspace, size_t workspace_bytes, vag_stream_t stream);
 int vag_decoder_seq_bwd_f32(const vag_decoder_weights* w, const float* h0, const float* enc, const float* mask,
                             const int64_t* tok_in, const int64_t* tgt_t, const float* nll_weight, int B, int T, int Tt,
-                            int tied, const vag_decoder_seq_saved* s, const float* dloss_rows,
+                            int tied, const vag_decoder_seq_saved* s, const float* out_mask, const float* dloss_rows,
                             const vag_decoder_grads* g, float* d_h0, float* d_enc, void* workspace,
                             size_t workspace_bytes, vag_stream_t stream);
 
 /* Encoder training pair: forward that keeps what BPTT needs and the backward through both directions of the packed
- * bi-GRU.  x [T·B, E] time-major embeddings, ids_tm int64 [T·B], gi / gh [2][T, B, 3H]; gradients like the weights. */
+ * bi-GRU.  x [T·B, E] time-major embeddings, ids_tm int64 [T·B], gi / gh [2][T, B, 3H]; gradients like the weights.
+ * emb_mask (optional, [T·B, E] time-major, 0 or 1/(1-p)): the embedding dropout of Encoder.py:51-52. */
 size_t vag_encoder_train_workspace_bytes(int B, int T, int E, int H);
 int vag_encoder_train_fwd_f32(const vag_encoder_weights* w, const int64_t* src, const int32_t* lengths_host, int B, int T,
-                              float* ctx_out, float* x, int64_t* ids_tm, float* gi, float* gh, void* workspace,
-                              size_t workspace_bytes, vag_stream_t stream);
+                              float* ctx_out, float* x, int64_t* ids_tm, float* gi, float* gh, const float* emb_mask,
+                              void* workspace, size_t workspace_bytes, vag_stream_t stream);
 int vag_encoder_bwd_f32(const vag_encoder_weights* w, const int32_t* lengths_host, int B, int T, const float* ctx,
                         const float* dctx, const float* x, const int64_t* ids_tm, const float* gi, const float* gh,
                         float* d_emb, float* const* d_w_ih, float* const* d_w_hh, float* const* d_b_ih,
-                        float* const* d_b_hh, void* workspace, size_t workspace_bytes, vag_stream_t stream);
+                        float* const* d_b_hh, const float* emb_mask, void* workspace, size_t workspace_bytes,
+                        vag_stream_t stream);
 
 /* Optimiser step of train.py:46-49 with the Adam of nmt_multimodal_beam_DE.py:303-332, fused per parameter tensor:
  *   accum[0] += Σ grad²  (vag_sumsq_f32 over every tensor, after the gradient all-reduce when data-parallel), then

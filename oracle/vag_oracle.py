@@ -74,8 +74,8 @@ def gru_cell(x: torch.Tensor, h: torch.Tensor, w_ih, w_hh, b_ih, b_hh) -> torch.
 # --------------------------------------------------------------------------
 # a1  encoder
 # --------------------------------------------------------------------------
-def encoder_forward(p: Params, src: torch.Tensor, lengths: Sequence[int],
-                    prefix: str = "encoder.") -> Tuple[torch.Tensor, torch.Tensor]:
+def encoder_forward(p: Params, src: torch.Tensor, lengths: Sequence[int], prefix: str = "encoder.",
+                    emb_mask: Optional[torch.Tensor] = None, ctx_mask: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """LIUMCVC_Encoder.forward in eval mode (no dropout).  layers/Encoder.py:36-65.
 
     src      int64 [B, T], 0-padded, rows sorted by length descending
@@ -93,6 +93,8 @@ def encoder_forward(p: Params, src: torch.Tensor, lengths: Sequence[int],
     emb = p[prefix + "embedding.weight"]
     dt = emb.dtype
     x = emb[src[:, :T]].transpose(0, 1)  # [T, B, E]   Encoder.py:50
+    if emb_mask is not None:  # training-mode embedding dropout with a given mask (0 or 1/(1-p)), Encoder.py:51-52
+        x = x * emb_mask.reshape(T, B, -1)
     H = p[prefix + "gru.weight_hh_l0"].shape[1]
     ctx = torch.zeros(T, B, 2 * H, dtype=dt)
     lens = torch.tensor(lengths)
@@ -110,6 +112,8 @@ def encoder_forward(p: Params, src: torch.Tensor, lengths: Sequence[int],
             h_new = gru_cell(x[t, :n_act], h[:n_act], w_ih, w_hh, b_ih, b_hh)
             h = torch.cat([h_new, h[n_act:]], 0)
             ctx[t, :n_act, direction * H:(direction + 1) * H] = h_new
+    if ctx_mask is not None:  # context dropout, Encoder.py:62-63; ctx_mask is sentence-major [B, T, 2H]
+        ctx = ctx * ctx_mask.transpose(0, 1)
     mask = (src[:, :T] != 0).long().transpose(0, 1).to(dt)  # Encoder.py:47,65
     return ctx, mask
 
@@ -138,7 +142,7 @@ def bahdanau_attention(p: Params, h1: torch.Tensor, ctx: torch.Tensor, mask: Opt
 
 def decoder_step(p: Params, tok: torch.Tensor, h: torch.Tensor, ctx: torch.Tensor,
                  mask: Optional[torch.Tensor], keys: Optional[torch.Tensor] = None,
-                 prefix: str = "decoder.", return_parts: bool = False):
+                 prefix: str = "decoder.", return_parts: bool = False, out_mask: Optional[torch.Tensor] = None):
     """NMT_Decoder.forward in eval mode.  layers/NMT_Decoder.py:109-145.
 
     tok int64 [N]; h [N, H]; ctx [T, N, C]; mask [T, N] → logp [N, V], h2 [N, H].
@@ -156,6 +160,8 @@ def decoder_step(p: Params, tok: torch.Tensor, h: torch.Tensor, ctx: torch.Tenso
     t = torch.tanh(linear(h2, p[prefix + "W1.weight"], p[prefix + "W1.bias"])
                    + linear(e, p[prefix + "W3.weight"], p[prefix + "W3.bias"])
                    + linear(c, p[prefix + "W2.weight"], p[prefix + "W2.bias"]))  # :137
+    if out_mask is not None:  # output dropout with a given mask, NMT_Decoder.py:140-141
+        t = t * out_mask
     out_w = p.get(prefix + "out.weight", emb_w)  # tied: NMT_Decoder.py:105-106
     logits = linear(t, out_w, p[prefix + "out.bias"])
     logp = torch.log_softmax(logits, dim=-1)  # :143
@@ -252,14 +258,14 @@ def _nll_rows(logp: torch.Tensor, tgt: torch.Tensor, weight: Optional[torch.Tens
 
 
 def translation_loss(p: Params, ctx, mask, h0, tgt: torch.Tensor, teacher_force: bool,
-                     nll_weight: Optional[torch.Tensor]) -> torch.Tensor:
+                     nll_weight: Optional[torch.Tensor], out_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
     """The Tt-step loop of forward.  V11:136-164 ; NMT_Seq2Seq_Beam_V2.py:91-111."""
     B, Tt = tgt.shape
     inp = torch.full((B,), SOS_token, dtype=torch.long)
     h = h0
     loss_rows = torch.zeros(B, dtype=h0.dtype)
     for di in range(Tt):
-        logp, h = decoder_step(p, inp, h, ctx, mask)
+        logp, h = decoder_step(p, inp, h, ctx, mask, out_mask=None if out_mask is None else out_mask.reshape(Tt, B, -1)[di])
         loss_rows = loss_rows + _nll_rows(logp, tgt[:, di], nll_weight)
         inp = tgt[:, di] if teacher_force else logp.argmax(1)
     tgt_mask = (tgt != 0).to(h0.dtype)
@@ -269,9 +275,11 @@ def translation_loss(p: Params, ctx, mask, h0, tgt: torch.Tensor, teacher_force:
 def multimodal_forward(p: Params, src, lengths, tgt, im, teacher_force: bool = True,
                        nll_weight: Optional[torch.Tensor] = None, vse_loss: Optional[str] = "pairwise",
                        margin: float = 0.1, loss_w: float = 0.99, init_split: float = 0.5,
-                       attn_model: str = "dot", activation_vse: bool = True):
-    """NMT_AttentionImagine_Seq2Seq_Beam_V11.forward (eval-mode dropouts).  V11:82-168."""
-    ctx, mask = encoder_forward(p, src, lengths)  # :111
+                       attn_model: str = "dot", activation_vse: bool = True, dropout_masks: Optional[dict] = None):
+    """NMT_AttentionImagine_Seq2Seq_Beam_V11.forward.  V11:82-168.  dropout_masks (optional) = {"emb": [T·B, E] time-major,
+    "ctx": [B, T, 2H], "out": [Tt·B, E]} with entries 0 or 1/(1-p): the training-mode dropouts with given masks."""
+    dm = dropout_masks or {}
+    ctx, mask = encoder_forward(p, src, lengths, emb_mask=dm.get("emb"), ctx_mask=dm.get("ctx"))  # :111
     im_emb, txt_emb, ctx_vec, _ = vse_pool(p, im, ctx, mask, attn_model, activation_vse)  # :114
     if vse_loss == "pairwise":
         loss_vse = pairwise_ranking_loss(im_emb, txt_emb, margin)
@@ -280,7 +288,7 @@ def multimodal_forward(p: Params, src, lengths, tgt, im, teacher_force: bool = T
     else:
         loss_vse = torch.zeros((), dtype=ctx.dtype)
     h0 = decoder_init(p, ctx, mask, ctx_vec, init_split)  # :118
-    loss_mt = translation_loss(p, ctx, mask, h0, tgt, teacher_force, nll_weight)
+    loss_mt = translation_loss(p, ctx, mask, h0, tgt, teacher_force, nll_weight, out_mask=dm.get("out"))
     loss = loss_w * loss_mt + (1 - loss_w) * loss_vse  # :166
     return loss, loss_mt, loss_vse
 

@@ -101,6 +101,44 @@ def test_full_shape_gradients_fp32_oracle():
     assert worst < 5e-3
 
 
+def test_training_mode_dropout_with_injected_masks():
+    """Embedding / context / output dropout (DE defaults 0.3 / 0.5 / 0.5) with the SAME masks on both sides."""
+    import vag_nmt_b200 as vag
+    from oracle import vag_oracle as O
+    from vag_nmt_b200 import synthetic
+    cfg = dict(synthetic.TINY)
+    torch.manual_seed(31)
+    model = vag.NMT_AttentionImagine_Seq2Seq_Beam_V11(
+        cfg["src_size"], cfg["tgt_size"], cfg["im_feats_size"], cfg["src_embedding_size"], cfg["tgt_embedding_size"],
+        cfg["hidden_size"], cfg["shared_embedding_size"], 0.99, dropout_ctx=0.5, dropout_emb=0.3, dropout_out=0.5, tied_emb=True).cuda().train()
+    batch = synthetic.make_batch(6, cfg["src_size"], cfg["tgt_size"], cfg["im_feats_size"], seed=5, max_len=9, min_len=2,
+                                 mean=5.0, std=2.5, common_tgt_len=False)
+    B, Ts = batch.src.shape
+    Tt = batch.tgt.shape[1]
+    gen = torch.Generator().manual_seed(3)
+    mk = lambda shape, p: torch.empty(shape).bernoulli_(1 - p, generator=gen) / (1 - p)
+    masks = {"emb": mk((Ts * B, cfg["src_embedding_size"]), 0.3), "ctx": mk((B, Ts, 2 * cfg["hidden_size"]), 0.5),
+             "out": mk((Tt * B, cfg["tgt_embedding_size"]), 0.5)}
+    model._dropout_masks = masks
+    p = {k: v.clone().double().requires_grad_(True) for k, v in cpu_params(model).items()}
+    p["decoder.out.weight"] = p["decoder.embedding.weight"]
+    w = torch.ones(cfg["tgt_size"], dtype=torch.float64)
+    w[0] = 0
+    ref, _, _ = O.multimodal_forward(p, batch.src, batch.src_lengths, batch.tgt, batch.im.double(), True, w, "pairwise", 0.1,
+                                     dropout_masks={k: v.double() for k, v in masks.items()})
+    ref.backward()
+    crit = torch.nn.NLLLoss(weight=w.float().cuda(), reduce=False)
+    loss, _, _ = model(batch.src, batch.src_lengths, batch.tgt, batch.im, 1.0, criterion_mt=crit, criterion_vse=vag.PairwiseRankingLoss(margin=0.1))
+    assert abs(float(loss) - float(ref)) < 1e-4 * abs(float(ref))
+    loss.backward()
+    _check_grads(model, {k: v.grad for k, v in p.items() if v.grad is not None})
+    # without injected masks the draw is random: two passes differ, eval mode is deterministic
+    model._dropout_masks = None
+    l1 = float(model(batch.src, batch.src_lengths, batch.tgt, batch.im, 1.0, criterion_mt=crit)[0])
+    l2 = float(model(batch.src, batch.src_lengths, batch.tgt, batch.im, 1.0, criterion_mt=crit)[0])
+    assert l1 != l2
+
+
 def test_clip_adam_matches_torch():
     from vag_nmt_b200.optim import ClipAdam, named_param_groups
     torch.manual_seed(0)

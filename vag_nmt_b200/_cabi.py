@@ -105,11 +105,12 @@ SIGNATURES = {
     "vag_l2norm_bwd_f32": (I, [P, P, P, I, I, P]),
     "vag_init_mix_bwd_f32": (I, [P, P, P, P, F, I, I, I, P]),
     "vag_decoder_seq_workspace_bytes": (SZ, [I, I, I, I, I, I, I64]),
-    "vag_decoder_seq_fwd_f32": (I, [P, P, P, P, P, P, P, I, I, I, I, P, P, P, SZ, P]),
-    "vag_decoder_seq_bwd_f32": (I, [P, P, P, P, P, P, P, I, I, I, I, P, P, P, P, P, P, SZ, P]),
+    "vag_decoder_seq_fwd_f32": (I, [P, P, P, P, P, P, P, I, I, I, I, P, P, P, P, SZ, P]),
+    "vag_decoder_seq_bwd_f32": (I, [P, P, P, P, P, P, P, I, I, I, I, P, P, P, P, P, P, P, SZ, P]),
+    "vag_mul_f32": (I, [P, P, I64, P]),
     "vag_encoder_train_workspace_bytes": (SZ, [I, I, I, I]),
-    "vag_encoder_train_fwd_f32": (I, [P, P, P, I, I, P, P, P, P, P, P, SZ, P]),
-    "vag_encoder_bwd_f32": (I, [P, P, I, I, P, P, P, P, P, P, P, P, P, P, P, P, SZ, P]),
+    "vag_encoder_train_fwd_f32": (I, [P, P, P, I, I, P, P, P, P, P, P, P, SZ, P]),
+    "vag_encoder_bwd_f32": (I, [P, P, I, I, P, P, P, P, P, P, P, P, P, P, P, P, P, SZ, P]),
     "vag_sumsq_f32": (I, [P, I64, P, P]),
     "vag_clip_adam_f32": (I, [P, P, P, P, I64, P, F, F, F, F, F, F, I, P]),
 }

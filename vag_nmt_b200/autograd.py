@@ -49,8 +49,8 @@ class EncoderFn(torch.autograd.Function):
     Forward (with saved pre-activations) and BPTT are one C call each."""
 
     @staticmethod
-    def forward(fctx, src, lengths, emb, *gru):
-        # gru = (w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r)
+    def forward(fctx, src, lengths, emb_mask, emb, *gru):
+        # gru = (w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r); emb_mask: [T·B, E] time-major dropout mask or None
         import ctypes as C
         from ._cabi import EncoderWeights
         lib = ops._cabi.lib()
@@ -71,10 +71,10 @@ class EncoderFn(torch.autograd.Function):
         ws = ops.workspace(lib.vag_encoder_train_workspace_bytes(B, Tn, E, H), dev)
         with on_device(dev):
             ops.check(lib.vag_encoder_train_fwd_f32(C.byref(w), src.data_ptr(), lens, B, Tn, ctx.data_ptr(), x.data_ptr(),
-                                                    ids_tm.data_ptr(), gi.data_ptr(), gh.data_ptr(), ws.data_ptr(), ws.numel(),
-                                                    ops.stream_ptr()))
-        fctx.save_for_backward(x, ctx, ids_tm, gi, gh, emb, *gru)
-        fctx.meta = (B, Tn, E, H, [int(v) for v in lengths])
+                                                    ids_tm.data_ptr(), gi.data_ptr(), gh.data_ptr(), ops.ptr(emb_mask), ws.data_ptr(),
+                                                    ws.numel(), ops.stream_ptr()))
+        fctx.save_for_backward(x, ctx, ids_tm, gi, gh, emb_mask if emb_mask is not None else ids_tm, emb, *gru)
+        fctx.meta = (B, Tn, E, H, [int(v) for v in lengths], emb_mask is not None)
         return ctx
 
     @staticmethod
@@ -82,8 +82,8 @@ class EncoderFn(torch.autograd.Function):
         import ctypes as C
         from ._cabi import EncoderWeights
         lib = ops._cabi.lib()
-        x, ctx, ids_tm, gi, gh, emb, *gru = fctx.saved_tensors
-        B, Tn, E, H, lengths = fctx.meta
+        x, ctx, ids_tm, gi, gh, emb_mask, emb, *gru = fctx.saved_tensors
+        B, Tn, E, H, lengths, has_mask = fctx.meta
         dev = emb.device
         w = EncoderWeights()
         w.E, w.H, w.vocab, w.emb = E, H, emb.shape[0], ops._p(emb.detach())
@@ -98,8 +98,31 @@ class EncoderFn(torch.autograd.Function):
         with on_device(dev):
             ops.check(lib.vag_encoder_bwd_f32(C.byref(w), lens, B, Tn, ctx.data_ptr(), dctx.contiguous().data_ptr(), x.data_ptr(),
                                               ids_tm.data_ptr(), gi.data_ptr(), gh.data_ptr(), demb.data_ptr(), arr(0), arr(1), arr(2),
-                                              arr(3), ws.data_ptr(), ws.numel(), ops.stream_ptr()))
-        return (None, None, demb, *grads)
+                                              arr(3), emb_mask.data_ptr() if has_mask else None, ws.data_ptr(), ws.numel(),
+                                              ops.stream_ptr()))
+        return (None, None, None, demb, *grads)
+
+
+class MaskMulFn(torch.autograd.Function):
+    """y = x ⊙ m with a fixed mask (dropout with a pre-drawn, pre-scaled mask): dx = dy ⊙ m."""
+
+    @staticmethod
+    def forward(fctx, x, m):
+        lib = ops._cabi.lib()
+        y = x.contiguous().clone()
+        with on_device(x.device):
+            ops.check(lib.vag_mul_f32(y.data_ptr(), m.data_ptr(), y.numel(), ops.stream_ptr()))
+        fctx.save_for_backward(m)
+        return y
+
+    @staticmethod
+    def backward(fctx, dy):
+        (m,) = fctx.saved_tensors
+        lib = ops._cabi.lib()
+        dx = dy.contiguous().clone()
+        with on_device(dx.device):
+            ops.check(lib.vag_mul_f32(dx.data_ptr(), m.data_ptr(), dx.numel(), ops.stream_ptr()))
+        return dx, None
 
 
 # ---------------------------------------------------------------------------------------------------- VSE pooling
@@ -200,7 +223,7 @@ class DecoderSeqFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(fctx, h0, enc, mask, tgt, weight, teacher, tied, *params):
+    def forward(fctx, h0, enc, mask, tgt, weight, teacher, tied, out_mask, *params):
         import ctypes as C
         from ._cabi import DecoderGrads, DecoderSeqSaved, DecoderWeights
         lib = ops._cabi.lib()
@@ -237,9 +260,10 @@ class DecoderSeqFn(torch.autograd.Function):
         with on_device(dev):
             ops.check(lib.vag_decoder_seq_fwd_f32(C.byref(w), h0.data_ptr(), enc.data_ptr(), mask.data_ptr(), tok_in.data_ptr(),
                                                   tgt_t.data_ptr(), ops.ptr(weight), B, Tn, Tt, 1 if teacher else 0, C.byref(saved),
-                                                  loss_rows.data_ptr(), ws.data_ptr(), ws.numel(), ops.stream_ptr()))
-        fctx.save_for_backward(h0, enc, mask, tgt_t, tok_in, store, weight if weight is not None else loss_rows, *params)
-        fctx.meta = (weight is not None, bool(tied), offs, ldl, (B, Tn, Tt, E, H, Cd, V))
+                                                  ops.ptr(out_mask), loss_rows.data_ptr(), ws.data_ptr(), ws.numel(), ops.stream_ptr()))
+        fctx.save_for_backward(h0, enc, mask, tgt_t, tok_in, store, weight if weight is not None else loss_rows,
+                               out_mask if out_mask is not None else loss_rows, *params)
+        fctx.meta = (weight is not None, bool(tied), offs, ldl, (B, Tn, Tt, E, H, Cd, V), out_mask is not None)
         return loss_rows
 
     @staticmethod
@@ -247,8 +271,8 @@ class DecoderSeqFn(torch.autograd.Function):
         import ctypes as C
         from ._cabi import DecoderGrads, DecoderSeqSaved, DecoderWeights
         lib = ops._cabi.lib()
-        h0, enc, mask, tgt_t, tok_in, store, weight, *params = fctx.saved_tensors
-        has_weight, tied, offs, ldl, (B, Tn, Tt, E, H, Cd, V) = fctx.meta
+        h0, enc, mask, tgt_t, tok_in, store, weight, out_mask, *params = fctx.saved_tensors
+        has_weight, tied, offs, ldl, (B, Tn, Tt, E, H, Cd, V), has_out_mask = fctx.meta
         dev = h0.device
         w = DecoderWeights()
         w.E, w.H, w.C, w.V = E, H, Cd, V
@@ -268,11 +292,12 @@ class DecoderSeqFn(torch.autograd.Function):
         with on_device(dev):
             ops.check(lib.vag_decoder_seq_bwd_f32(C.byref(w), h0.data_ptr(), enc.data_ptr(), mask.data_ptr(), tok_in.data_ptr(),
                                                   tgt_t.data_ptr(), weight.data_ptr() if has_weight else None, B, Tn, Tt,
-                                                  1 if tied else 0, C.byref(saved), dloss_rows.contiguous().data_ptr(), C.byref(g),
+                                                  1 if tied else 0, C.byref(saved), out_mask.data_ptr() if has_out_mask else None,
+                                                  dloss_rows.contiguous().data_ptr(), C.byref(g),
                                                   d_h0.data_ptr(), d_enc.data_ptr(), ws.data_ptr(), ws.numel(), ops.stream_ptr()))
         if tied:
             grads[19] = None          # out.weight IS the embedding: its gradient was accumulated into grads[0]
-        return (d_h0, d_enc, None, None, None, None, None, *grads)
+        return (d_h0, d_enc, None, None, None, None, None, None, *grads)
 
 
 # ---------------------------------------------------------------------------------------------------- loss epilogue

@@ -202,6 +202,19 @@ __global__ void tanh_bwd_kernel(float* __restrict__ dx, const float* __restrict_
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         dx[i] = dy[i] * (1.f - y[i] * y[i]);
 }
+// y *= m (dropout mask already scaled by 1/(1-p))
+__global__ void mul_kernel(float* __restrict__ y, const float* __restrict__ m, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] *= m[i];
+}
+// y = tanh(u)·m was stored; dx = dy·m·(1 − tanh(u)²) with tanh(u) = y/m where the unit was kept, 0 gradient elsewhere
+__global__ void tanh_dropout_bwd_kernel(float* __restrict__ dx, const float* __restrict__ dy, const float* __restrict__ y,
+                                        const float* __restrict__ m, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float mi = m[i];
+        const float th = mi != 0.f ? y[i] / mi : 0.f;
+        dx[i] = dy[i] * mi * (1.f - th * th);
+    }
+}
 __global__ void axpby_kernel(float* __restrict__ y, const float* __restrict__ x, float a, float b, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         y[i] = a * x[i] + (b == 0.f ? 0.f : b * y[i]);
@@ -386,6 +399,14 @@ extern "C" int vag_axpby_f32(float* y, const float* x, float a, float b, int64_t
     return VAG_OK;
 }
 
+extern "C" int vag_mul_f32(float* y, const float* m, int64_t n, vag_stream_t stream) {
+    VAG_REQUIRE(y && m, "vag_mul_f32: null pointer");
+    if (n == 0) return VAG_OK;
+    mul_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(y, m, n);
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
 extern "C" int vag_colsum_f32(float* out, const float* x, int64_t ldx, int rows, int cols, int accumulate, vag_stream_t stream) {
     VAG_REQUIRE(out && x, "vag_colsum_f32: null pointer");
     if (cols == 0) return VAG_OK;
@@ -472,8 +493,8 @@ extern "C" size_t vag_decoder_seq_workspace_bytes(int B, int T, int Tt, int E, i
 
 extern "C" int vag_decoder_seq_fwd_f32(const vag_decoder_weights* w, const float* h0, const float* enc, const float* mask,
                                        int64_t* tok_in, const int64_t* tgt_t, const float* nll_weight, int B, int T, int Tt,
-                                       int teacher, const vag_decoder_seq_saved* s, float* loss_rows, void* workspace,
-                                       size_t workspace_bytes, vag_stream_t stream) {
+                                       int teacher, const vag_decoder_seq_saved* s, const float* out_mask, float* loss_rows,
+                                       void* workspace, size_t workspace_bytes, vag_stream_t stream) {
     VAG_REQUIRE(w && h0 && enc && mask && tok_in && tgt_t && s && loss_rows, "vag_decoder_seq_fwd_f32: null pointer");
     VAG_REQUIRE(B > 0 && T > 0 && Tt > 0, "vag_decoder_seq_fwd_f32: bad shape");
     cudaStream_t st = (cudaStream_t)stream;
@@ -529,6 +550,7 @@ extern "C" int vag_decoder_seq_fwd_f32(const vag_decoder_weights* w, const float
             VAG_TRY(gemm.linear(t_s, E, h2, H, w->w1_w, H, w->w1_b, B, H, E, 0));
             VAG_TRY(gemm.linear(t_s, E, e_s, E, w->w3_w, E, w->w3_b, B, E, E, VAG_LIN_ACCUMULATE));
             VAG_TRY(gemm.linear(t_s, E, c, C, w->w2_w, C, w->w2_b, B, C, E, VAG_LIN_ACCUMULATE | VAG_LIN_TANH));
+            if (out_mask) VAG_TRY(vag_mul_f32(t_s, out_mask + (size_t)t * B * E, (int64_t)B * E, vs));   // output dropout, NMT_Decoder.py:140-141
             VAG_TRY(gemm.linear(lg, ldl, t_s, E, w->out_w, E, w->out_b, B, E, (int)V, 0));
             if (t + 1 < Tt) VAG_TRY(row_argmax(lg, ldl, B, V, tok_in + (size_t)(t + 1) * B, 1, nullptr, st));
         }
@@ -538,6 +560,7 @@ extern "C" int vag_decoder_seq_fwd_f32(const vag_decoder_weights* w, const float
         VAG_TRY(gemm.linear(s->t_all, E, s->h2_all, H, w->w1_w, H, w->w1_b, R, H, E, 0));
         VAG_TRY(gemm.linear(s->t_all, E, s->e_all, E, w->w3_w, E, w->w3_b, R, E, E, VAG_LIN_ACCUMULATE));
         VAG_TRY(gemm.linear(s->t_all, E, s->c_all, C, w->w2_w, C, w->w2_b, R, C, E, VAG_LIN_ACCUMULATE | VAG_LIN_TANH));
+        if (out_mask) VAG_TRY(vag_mul_f32(s->t_all, out_mask, (int64_t)R * E, vs));                       // output dropout
         gemm.new_step();
         VAG_TRY(gemm.linear(s->logits_all, ldl, s->t_all, E, w->out_w, E, w->out_b, R, E, (int)V, 0));
     }
@@ -550,7 +573,7 @@ extern "C" int vag_decoder_seq_fwd_f32(const vag_decoder_weights* w, const float
 
 extern "C" int vag_decoder_seq_bwd_f32(const vag_decoder_weights* w, const float* h0, const float* enc, const float* mask,
                                        const int64_t* tok_in, const int64_t* tgt_t, const float* nll_weight, int B, int T, int Tt,
-                                       int tied, const vag_decoder_seq_saved* s, const float* dloss_rows,
+                                       int tied, const vag_decoder_seq_saved* s, const float* out_mask, const float* dloss_rows,
                                        const vag_decoder_grads* g, float* d_h0, float* d_enc, void* workspace,
                                        size_t workspace_bytes, vag_stream_t stream) {
     VAG_REQUIRE(w && h0 && enc && mask && tok_in && tgt_t && s && dloss_rows && g && d_h0 && d_enc, "vag_decoder_seq_bwd_f32: null pointer");
@@ -589,7 +612,12 @@ extern "C" int vag_decoder_seq_bwd_f32(const vag_decoder_weights* w, const float
     VAG_CUDA(cudaMemsetAsync(g->emb, 0, sizeof(float) * (size_t)V * E, st));
     VAG_TRY(gemm_g(d_out_w, E, dlogits, 1, V, s->t_all, E, 1, (int)V, E, R, 0.f, st));              // dlogitsᵀ · t_all
     VAG_TRY(vag_colsum_f32(g->out_b, dlogits, V, R, (int)V, 0, vs));
-    VAG_TRY(vag_tanh_bwd_f32(du, d_t, s->t_all, (int64_t)R * E, vs));
+    if (out_mask) {
+        tanh_dropout_bwd_kernel<<<grid_for((int64_t)R * E), 256, 0, st>>>(du, d_t, s->t_all, out_mask, (int64_t)R * E);
+        VAG_LAUNCH_CHECK();
+    } else {
+        VAG_TRY(vag_tanh_bwd_f32(du, d_t, s->t_all, (int64_t)R * E, vs));
+    }
     VAG_TRY(gemm_g(dh2_dir, H, du, E, 1, w->w1_w, H, 1, R, H, E, 0.f, st));
     VAG_TRY(gemm_g(d_e, E, du, E, 1, w->w3_w, E, 1, R, E, E, 0.f, st));
     VAG_TRY(gemm_g(dc_dir, C, du, E, 1, w->w2_w, C, 1, R, C, E, 0.f, st));
@@ -688,8 +716,8 @@ extern "C" size_t vag_encoder_train_workspace_bytes(int B, int T, int E, int H) 
 
 /* saved: x [T·B, E] time-major embeddings, ids_tm int64 [T·B], gi [2][T, B, 3H], gh [2][T, B, 3H] (zero where inactive) */
 extern "C" int vag_encoder_train_fwd_f32(const vag_encoder_weights* w, const int64_t* src, const int32_t* lengths_host, int B, int T,
-                                         float* ctx_out, float* x, int64_t* ids_tm, float* gi, float* gh, void* workspace,
-                                         size_t workspace_bytes, vag_stream_t stream) {
+                                         float* ctx_out, float* x, int64_t* ids_tm, float* gi, float* gh, const float* emb_mask,
+                                         void* workspace, size_t workspace_bytes, vag_stream_t stream) {
     VAG_REQUIRE(w && src && lengths_host && ctx_out && x && ids_tm && gi && gh, "vag_encoder_train_fwd_f32: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const int E = w->E, H = w->H;
@@ -712,6 +740,7 @@ extern "C" int vag_encoder_train_fwd_f32(const vag_encoder_weights* w, const int
         dim3 block(64, 4);
         encoder_embed_tm_kernel<<<ceil_div(B * T, 4), block, 0, st>>>(x, w->emb, src, ids_tm, B, T, E, w->vocab);
         VAG_LAUNCH_CHECK();
+        if (emb_mask) VAG_TRY(vag_mul_f32(x, emb_mask, (int64_t)T * B * E, stream));   // embedding dropout, Encoder.py:51-52
     }
     VAG_CUDA(cudaMemsetAsync(ctx_out, 0, sizeof(float) * (size_t)B * T * 2 * H, st));
     VAG_CUDA(cudaMemsetAsync(gh, 0, sizeof(float) * (size_t)2 * T * B * 3 * H, st));
@@ -744,7 +773,8 @@ extern "C" int vag_encoder_train_fwd_f32(const vag_encoder_weights* w, const int
 extern "C" int vag_encoder_bwd_f32(const vag_encoder_weights* w, const int32_t* lengths_host, int B, int T, const float* ctx,
                                    const float* dctx, const float* x, const int64_t* ids_tm, const float* gi, const float* gh,
                                    float* d_emb, float* const* d_w_ih, float* const* d_w_hh, float* const* d_b_ih,
-                                   float* const* d_b_hh, void* workspace, size_t workspace_bytes, vag_stream_t stream) {
+                                   float* const* d_b_hh, const float* emb_mask, void* workspace, size_t workspace_bytes,
+                                   vag_stream_t stream) {
     VAG_REQUIRE(w && lengths_host && ctx && dctx && x && ids_tm && gi && gh && d_emb, "vag_encoder_bwd_f32: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     vag_stream_t vs = stream;
@@ -798,6 +828,7 @@ extern "C" int vag_encoder_bwd_f32(const vag_encoder_weights* w, const int32_t* 
         VAG_TRY(vag_colsum_f32(d_b_hh[d], dgh_all, 3 * H, T * B, 3 * H, 0, vs));
     }
     VAG_CUDA(cudaMemsetAsync(d_emb, 0, sizeof(float) * (size_t)w->vocab * E, st));
+    if (emb_mask) VAG_TRY(vag_mul_f32(dx, emb_mask, (int64_t)T * B * E, vs));
     VAG_TRY(vag_embed_bwd_f32(d_emb, dx, E, ids_tm, T * B, E, w->vocab, vs));
     return VAG_OK;
 }

@@ -17,9 +17,11 @@ from . import ops
 
 
 def _no_training_dropout(module: nn.Module, *rates: float) -> None:
-    if module.training and any(r > 0 for r in rates):
+    """The per-layer forward methods are the inference path (no autograd); dropout applies only in the models'
+    training path (models.py::_forward_train), so a layer called directly in train mode with p > 0 refuses."""
+    if module.training and torch.is_grad_enabled() and any(r > 0 for r in rates):
         raise NotImplementedError(
-            "training-mode dropout is not part of the B200 path yet; call .eval() or build the model with zero dropout")
+            "layer-level forward is inference-only; train through the model's forward (dropout + autograd live there)")
 
 
 class LIUMCVC_Encoder(nn.Module):

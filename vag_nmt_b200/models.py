@@ -37,10 +37,19 @@ def _nll_weight(criterion, device) -> Optional[torch.Tensor]:
 
 
 def _no_dropout_in_training(model) -> None:
-    enc, dec = model.encoder, model.decoder
-    if model.training and any(r > 0 for r in (enc.dropout_emb, enc.dropout_ctx, dec.dropout_out, dec.dropout_emb)):
-        raise NotImplementedError("training-mode dropout is not part of the B200 path yet: build the model with zero dropout "
-                                  "rates (parity runs use p = 0, SURVEY.md section 7 hard part 7)")
+    """Kept for callers of older versions: training-mode dropout is implemented (see _dropout_mask)."""
+    return None
+
+
+def _dropout_mask(model, name: str, p: float, shape, device) -> Optional[torch.Tensor]:
+    """Mask of nn.Dropout(p) in training mode: 0 with probability p, else 1/(1-p).  Drawn with torch's CUDA generator;
+    tests inject fixed masks through ``model._dropout_masks[name]`` to compare against a reference run."""
+    inject = getattr(model, "_dropout_masks", None)
+    if inject is not None and name in inject:
+        return inject[name].to(device=device, dtype=torch.float32).contiguous()
+    if not model.training or p <= 0.0:
+        return None
+    return torch.empty(shape, dtype=torch.float32, device=device).bernoulli_(1.0 - p).div_(1.0 - p)
 
 
 class _Seq2SeqBase(nn.Module):
@@ -113,15 +122,26 @@ class _Seq2SeqBase(nn.Module):
         if any(lengths[i] < lengths[i + 1] for i in range(len(lengths) - 1)):
             raise RuntimeError("`lengths` array must be sorted in decreasing order (pack_padded_sequence, Encoder.py:55)")
         g = enc.gru
-        ctx = EncoderFn.apply(src, lengths, enc.embedding.weight, g.weight_ih_l0, g.weight_hh_l0, g.bias_ih_l0, g.bias_hh_l0,
-                              g.weight_ih_l0_reverse, g.weight_hh_l0_reverse, g.bias_ih_l0_reverse, g.bias_hh_l0_reverse)
+        B, Tn = src.shape
+        E, H = enc.embedding.weight.shape[1], enc.hidden_size
+        emb_mask = _dropout_mask(self, "emb", enc.dropout_emb, (Tn * B, E), dev)        # time-major rows, Encoder.py:51-52
+        ctx = EncoderFn.apply(src, lengths, emb_mask, enc.embedding.weight, g.weight_ih_l0, g.weight_hh_l0, g.bias_ih_l0,
+                              g.bias_hh_l0, g.weight_ih_l0_reverse, g.weight_hh_l0_reverse, g.bias_ih_l0_reverse,
+                              g.bias_hh_l0_reverse)
+        ctx_mask = _dropout_mask(self, "ctx", enc.dropout_ctx, (B, Tn, 2 * H), dev)     # Encoder.py:62-63
+        if ctx_mask is not None:
+            from .autograd import MaskMulFn
+            ctx = MaskMulFn.apply(ctx, ctx_mask)
         mask = (src != 0).to(torch.float32)                          # Encoder.py:47
         return ctx, mask
 
     def _decoder_loss_train(self, h0, ctx, mask, tgt, teacher_force_ratio, weight):
         from .autograd import DecoderSeqFn
         is_teacher = random.random() < teacher_force_ratio          # V11:136
-        return DecoderSeqFn.apply(h0, ctx, mask, tgt, weight, is_teacher, bool(self.decoder.tied_emb), *self._decoder_param_list())
+        B, Tt = tgt.shape
+        out_mask = _dropout_mask(self, "out", self.decoder.dropout_out, (Tt * B, self.decoder.embedding_size), h0.device)
+        return DecoderSeqFn.apply(h0, ctx, mask, tgt, weight, is_teacher, bool(self.decoder.tied_emb), out_mask,
+                                  *self._decoder_param_list())
 
     def _translation_loss_rows(self, w, h0, keys, ctx, mask, tgt, teacher_force_ratio, weight):
         """The Tt-step loop of forward (V11:136-160): Σ_t NLL rows [B]."""
