@@ -76,6 +76,14 @@ int vag_linear_tc_f32(float* y, int64_t ldy, const float* x, int64_t ldx, const 
  *   vag_tc_split_f32 : x [rows, K] → hi / lo planes [rows, ld_out] (ld_out in elements, multiple of 8; planes 128-B aligned).
  *   vag_tc_gemm_f32  : y = act(x·Wᵀ + bias [+ y]) from split operands (tcgen05.mma, TMEM accumulators, TMA loads). */
 int vag_tc_elem_bytes(void);
+/* Arithmetic of every contraction issued by the calling thread from now on:
+ *   1  FP32-exact (default): FP16 hi/lo split, 3 tensor-core products, FP32-level accuracy (token-exact decoding)
+ *   0  FP32-exact, TF32 hi/lo split (any FP32 range, half the rate)
+ *   2  bf16 mode: operands rounded to bfloat16, ONE product, FP32 accumulation (north_star "bf16 mode"; the FFMA
+ *      fallback rounds its operands the same way)
+ *  -1  back to the default / the VAG_GEMM environment variable (tf32x3 | bf16 | simt). */
+int vag_set_gemm_mode(int mode);
+int vag_get_gemm_mode(void);
 int vag_tc_split_f32(const float* x, int64_t ldx, int rows, int K, void* hi, void* lo, int64_t ld_out, vag_stream_t stream);
 int vag_tc_gemm_f32(float* y, int64_t ldy, const void* x_hi, const void* x_lo, int64_t ldx, const void* w_hi,
                     const void* w_lo, int64_t ldw, const float* bias, int rows, int in_dim, int out_dim, int flags,

@@ -43,9 +43,25 @@ Params = Dict[str, torch.Tensor]
 # --------------------------------------------------------------------------
 # small helpers
 # --------------------------------------------------------------------------
+_OPERAND_ROUNDING = None
+
+
+def set_operand_rounding(kind: Optional[str]) -> None:
+    """None: plain arithmetic of the dtype.  "bf16": every contraction (nn.Linear / GRU matrix) sees its two operands
+    rounded to bfloat16 and accumulates in the working dtype — the reference run the bf16 mode is compared with
+    (SURVEY.md section 7 hard part 2: a reference that rounds at the same points)."""
+    global _OPERAND_ROUNDING
+    assert kind in (None, "bf16")
+    _OPERAND_ROUNDING = kind
+
+
+def _round_operand(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.bfloat16).to(t.dtype) if _OPERAND_ROUNDING == "bf16" else t
+
+
 def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor] = None) -> torch.Tensor:
     """y = x Wᵀ (+ b) — what every nn.Linear on the path computes."""
-    y = x.matmul(w.t())
+    y = _round_operand(x).matmul(_round_operand(w).t())
     if b is not None:
         y = y + b
     return y

@@ -1,0 +1,101 @@
+"""GPU: bf16 mode (model.precision = "bf16") against the oracle with bf16-rounded contraction operands.
+
+north_star bar: losses, logits and ranking-loss values within 1e-3 relative; recall@1/5/10 exact.  Both sides round
+the operands of every nn.Linear / GRU matrix to bfloat16 and accumulate in FP32/FP64; everything else stays FP32.
+Logits are compared norm-wise (max |Δ| / max |ref|), scalars by relative error.
+"""
+import pytest
+import torch
+
+from conftest import build_mm, cpu_params
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def bf16_oracle():
+    from oracle import vag_oracle as O
+    O.set_operand_rounding("bf16")
+    yield O
+    O.set_operand_rounding(None)
+
+
+def test_bf16_mode_losses_logits_and_recall(bf16_oracle):
+    O = bf16_oracle
+    import vag_nmt_b200 as vag
+    from vag_nmt_b200 import synthetic
+    cfg = dict(synthetic.DE)
+    model = build_mm(cfg, 1234).cuda().eval()
+    model.precision = "bf16"
+    batch = synthetic.make_batch(32, cfg["src_size"], cfg["tgt_size"], cfg["im_feats_size"], seed=7)
+    p = cpu_params(model)
+    w = torch.ones(cfg["tgt_size"])
+    w[0] = 0
+    with torch.no_grad():
+        ref = torch.stack(O.multimodal_forward(p, batch.src, batch.src_lengths, batch.tgt, batch.im, True, w, "pairwise", 0.1))
+        crit = torch.nn.NLLLoss(weight=w.cuda(), reduce=False)
+        got = model(batch.src, batch.src_lengths, batch.tgt, batch.im, 1.0, criterion_mt=crit, criterion_vse=vag.PairwiseRankingLoss(margin=0.1))
+        got = torch.stack([x.reshape(()) for x in got]).cpu()
+        assert float(((got - ref).abs() / ref.abs()).max()) < 1e-3, (got, ref)         # loss, loss_mt, loss_vse
+        # one decoder step on the reference layouts: logits / log-probabilities
+        ctx_o, mask_o = O.encoder_forward(p, batch.src, batch.src_lengths)
+        _, _, ctx_vec, _ = O.vse_pool(p, batch.im, ctx_o, mask_o)
+        h0 = O.decoder_init(p, ctx_o, mask_o, ctx_vec, 0.5)
+        tok = torch.full((32,), 2, dtype=torch.long)
+        logp_ref, h_ref = O.decoder_step(p, tok, h0, ctx_o, mask_o)
+        # direct layer calls are outside the model's precision scope: select the bf16 arithmetic by hand.  The encoder
+        # context (not a north_star quantity) is compared loosely: a recurrent state that rounds to a different bf16
+        # neighbour on the two sides moves an element by 2^-9 of its value.
+        _cabi_lib().vag_set_gemm_mode(2)
+        try:
+            ctx, mask = model.encoder(batch.src, batch.src_lengths)
+            # the step itself is fed the ORACLE's context so that the comparison isolates one decoder step
+            logp, h = model.decoder(tok.cuda(), h0.cuda().unsqueeze(0), ctx_o.cuda(), ctx_mask=mask_o.cuda())
+        finally:
+            _cabi_lib().vag_set_gemm_mode(-1)
+        assert float((ctx.cpu() - ctx_o).abs().max() / ctx_o.abs().max()) < 2e-3
+        assert float((logp.cpu() - logp_ref).abs().max() / logp_ref.abs().max()) < 1e-3
+        assert float((h.squeeze(0).cpu() - h_ref).abs().max() / h_ref.abs().max()) < 1e-3
+        # retrieval: recall@1/5/10 exact
+        e_im, e_txt = model.embed_sent_im_test(batch.src, batch.src_lengths, batch.im)
+        o_im, o_txt = O.embed_sent_im(p, batch.src, batch.src_lengths, batch.im)
+        assert vag.t2i(e_im, e_txt)[:3] == O.t2i(o_im, o_txt)[:3]
+        # the fp32 mode of the same model object is unaffected once the attribute is switched back
+        model.precision = "fp32"
+        assert _lib_mode() == 1
+
+
+def _cabi_lib():
+    from vag_nmt_b200 import _cabi
+    return _cabi.lib()
+
+
+def _lib_mode():
+    return _cabi_lib().vag_get_gemm_mode()
+
+
+def test_bf16_mode_is_actually_lower_precision_and_faster_path():
+    """Sanity: the bf16 contraction differs from FP32 at the 1e-3 level (so the mode really rounds) and decodes."""
+    import math
+    from vag_nmt_b200 import _cabi, ops, synthetic
+    lib = _cabi.lib()
+    x = torch.randn(512, 512, generator=torch.Generator().manual_seed(1)).cuda()
+    w = (torch.randn(1024, 512, generator=torch.Generator().manual_seed(2)) / math.sqrt(512)).cuda()
+    ref = x.double() @ w.double().t()
+    y32 = ops.linear_tc(x, w)
+    lib.vag_set_gemm_mode(2)
+    try:
+        y16 = ops.linear_tc(x, w)
+        ref16 = x.bfloat16().double() @ w.bfloat16().double().t()
+    finally:
+        lib.vag_set_gemm_mode(-1)
+    e32 = float((y32.double() - ref).abs().max() / ref.abs().max())
+    e16 = float((y16.double() - ref).abs().max() / ref.abs().max())
+    e16_vs_rounded = float((y16.double() - ref16).abs().max() / ref16.abs().max())
+    assert e32 < 3e-6 and 1e-4 < e16 < 2e-2 and e16_vs_rounded < 3e-6, (e32, e16, e16_vs_rounded)
+    cfg = dict(synthetic.DE)
+    model = build_mm(cfg, 1234).cuda().eval()
+    model.precision = "bf16"
+    batch = synthetic.make_batch(16, cfg["src_size"], cfg["tgt_size"], cfg["im_feats_size"], seed=9)
+    hyps = model.beamsearch_decode(batch.src, batch.src_lengths, batch.im, beam_size=12, max_length=20)
+    assert len(hyps) == 16 and all(len(h) <= 19 for h in hyps)

@@ -36,6 +36,7 @@ int linear_tc(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w
               int K, int N, int flags, void* scratch, size_t scratch_bytes, cudaStream_t st);
 size_t linear_tc_scratch_bytes(int64_t rows, int64_t K, int64_t N);
 bool linear_tc_eligible(const float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, int rows, int K, int N);
+bool tc_call_supported(const float* y, int64_t ldy, int flags);
 
 // VAG_GEMM=simt forces the FP32 FFMA path everywhere (A/B runs); default = tcgen05 3xTF32 where eligible.
 bool tc_enabled();
@@ -95,6 +96,17 @@ int tc_gemm(float* y, int64_t ldy, const void* xh, const void* xl, int64_t ldxs,
 
 extern "C" int vag_tc_elem_bytes(void) { return tc_elem_bytes(); }
 
+namespace vag {
+void set_gemm_mode(int m);
+int gemm_mode();
+}
+extern "C" int vag_set_gemm_mode(int mode) {
+    VAG_REQUIRE(mode >= -1 && mode <= 2, "vag_set_gemm_mode: mode must be -1 (environment default), 0 (tf32x3), 1 (f16x3) or 2 (bf16)");
+    set_gemm_mode(mode);
+    return VAG_OK;
+}
+extern "C" int vag_get_gemm_mode(void) { return gemm_mode(); }
+
 extern "C" int vag_tc_split_f32(const float* x, int64_t ldx, int rows, int K, void* hi, void* lo, int64_t ld_out,
                                 vag_stream_t stream) {
     VAG_REQUIRE(x && hi && lo, "vag_tc_split_f32: null pointer");
@@ -123,7 +135,7 @@ extern "C" int vag_linear_tc_f32(float* y, int64_t ldy, const float* x, int64_t 
     VAG_REQUIRE(y && x && w && workspace, "vag_linear_tc_f32: null pointer");
     VAG_REQUIRE(rows > 0 && in_dim > 0 && out_dim > 0, "vag_linear_tc_f32: bad shape rows=%d in=%d out=%d", rows, in_dim, out_dim);
     VAG_REQUIRE(ldx >= in_dim && ldw >= in_dim && ldy >= out_dim, "vag_linear_tc_f32: leading dimension smaller than the row");
-    if (!linear_tc_eligible(y, ldy, x, ldx, w, ldw, rows, in_dim, out_dim)) {
+    if (!linear_tc_eligible(y, ldy, x, ldx, w, ldw, rows, in_dim, out_dim) || !tc_call_supported(y, ldy, flags)) {
         set_error("vag_linear_tc_f32: needs rows >= 64, out >= 64, in >= 32 and a multiple of 4, 16-byte aligned operands");
         return VAG_ERR_UNSUPPORTED;
     }

@@ -17,6 +17,7 @@ int tc_split(const float* x, int64_t ldx, int rows, int K, void* hi, void* lo, i
 int tc_gemm(float* y, int64_t ldy, const void* xh, const void* xl, int64_t ldxs, const void* wh, const void* wl, int64_t ldws,
             const float* bias, int rows, int K, int N, int flags, cudaStream_t st, float4* summ, int* summ_tile_w);
 bool tc_enabled();
+bool tc_call_supported(const float* y, int64_t ldy, int flags);
 int bias_sum3(float* out, const float* a, const float* b, const float* c, int n, cudaStream_t st);
 
 struct GemmCtx {
@@ -78,7 +79,7 @@ struct GemmCtx {
                int K, int N, int flags, float4* summ = nullptr, int* summ_tile_w = nullptr) {
         if (summ_tile_w) *summ_tile_w = 0;
         if (rows == 0 || N == 0) return VAG_OK;
-        if (tc && shape_ok(rows, K, N) && ptr_ok(x, ldx) && ptr_ok(w, ldw)) {
+        if (tc && shape_ok(rows, K, N) && ptr_ok(x, ldx) && ptr_ok(w, ldw) && tc_call_supported(y, ldy, flags)) {
             Ent* we = lookup(wc, nw, w, N, K);
             if (!we && (we = make(true, w, N, K))) VAG_TRY(tc_split(w, ldw, N, K, we->hi, we->lo, K, 0, st));
             Ent* xe = we ? lookup(ac, na, x, rows, K) : nullptr;
@@ -93,7 +94,7 @@ struct GemmCtx {
     int linear3(float* y, int64_t ldy, const float* const x[3], const int64_t ldx[3], const int K[3], const float* const w[3],
                 const int64_t ldw[3], const float* const bias[3], int rows, int N, int flags) {
         const int Kt = K[0] + K[1] + K[2];
-        bool ok = tc && shape_ok(rows, Kt, N);
+        bool ok = tc && shape_ok(rows, Kt, N) && tc_call_supported(y, ldy, flags);
         for (int i = 0; i < 3; ++i) ok = ok && (K[i] % 8 == 0) && ptr_ok(x[i], ldx[i]) && ptr_ok(w[i], ldw[i]);
         if (ok) {
             Ent* we = lookup(wc, nw, w[0], N, Kt);

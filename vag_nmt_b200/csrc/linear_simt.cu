@@ -6,16 +6,22 @@
 // CTA stages BK-wide slabs of both through shared memory, transposed to [k][m] so that every
 // thread reads its 2×4 A and 2×4 B values with conflict-free 128-bit loads.
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace vag {
+
+int gemm_mode();
 
 template <int BM, int BN, int BK, int TM, int TN>
 struct SimtCfg {
     static constexpr int kThreads = (BM / TM) * (BN / TN);
 };
 
+// bf16 mode: operands are rounded to bfloat16 on load so that the FFMA path computes what the tensor-core path does
+__device__ __forceinline__ float rbf(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
 // Loads a [BROWS x BK] slab of a K-contiguous matrix into registers (float4 per thread-slot).
-template <int BROWS, int BK, int THREADS, bool VEC>
+template <int BROWS, int BK, int THREADS, bool VEC, bool RB>
 __device__ __forceinline__ void load_slab(float4 (&reg)[(BROWS * BK / 4 + THREADS - 1) / THREADS], const float* __restrict__ base,
                                           int64_t ld, int row0, int n_rows, int k0, int K, int tid) {
     constexpr int QPR = BK / 4;  // float4 per row
@@ -39,6 +45,7 @@ __device__ __forceinline__ void load_slab(float4 (&reg)[(BROWS * BK / 4 + THREAD
                     if (k + 2 < K) v.z = p[2];
                     if (k + 3 < K) v.w = p[3];
                 }
+                if (RB) { v.x = rbf(v.x); v.y = rbf(v.y); v.z = rbf(v.z); v.w = rbf(v.w); }
             }
         }
         reg[s] = v;
@@ -64,7 +71,7 @@ __device__ __forceinline__ void store_slab(float* __restrict__ sm, const float4 
     }
 }
 
-template <int BM, int BN, int BK, int TM, int TN, bool VEC>
+template <int BM, int BN, int BK, int TM, int TN, bool VEC, bool RB>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 linear_simt_kernel(float* __restrict__ y, int64_t ldy, const float* __restrict__ x, int64_t ldx,
                    const float* __restrict__ w, int64_t ldw, const float* __restrict__ bias, int rows, int K, int N,
@@ -95,8 +102,8 @@ linear_simt_kernel(float* __restrict__ y, int64_t ldy, const float* __restrict__
     float4 ra[ASLOTS], rb[BSLOTS];
 
     const int n_kt = (K + BK - 1) / BK;
-    load_slab<BM, BK, THREADS, VEC>(ra, x, ldx, m0, rows, 0, K, tid);
-    load_slab<BN, BK, THREADS, VEC>(rb, w, ldw, n0, N, 0, K, tid);
+    load_slab<BM, BK, THREADS, VEC, RB>(ra, x, ldx, m0, rows, 0, K, tid);
+    load_slab<BN, BK, THREADS, VEC, RB>(rb, w, ldw, n0, N, 0, K, tid);
     store_slab<BM, BK, THREADS, LDA>(As[0], ra, tid);
     store_slab<BN, BK, THREADS, LDB>(Bs[0], rb, tid);
     __syncthreads();
@@ -104,8 +111,8 @@ linear_simt_kernel(float* __restrict__ y, int64_t ldy, const float* __restrict__
     for (int kt = 0; kt < n_kt; ++kt) {
         const int cur = kt & 1;
         if (kt + 1 < n_kt) {
-            load_slab<BM, BK, THREADS, VEC>(ra, x, ldx, m0, rows, (kt + 1) * BK, K, tid);
-            load_slab<BN, BK, THREADS, VEC>(rb, w, ldw, n0, N, (kt + 1) * BK, K, tid);
+            load_slab<BM, BK, THREADS, VEC, RB>(ra, x, ldx, m0, rows, (kt + 1) * BK, K, tid);
+            load_slab<BN, BK, THREADS, VEC, RB>(rb, w, ldw, n0, N, (kt + 1) * BK, K, tid);
         }
         const float* a_s = As[cur];
         const float* b_s = Bs[cur];
@@ -156,7 +163,7 @@ linear_simt_kernel(float* __restrict__ y, int64_t ldy, const float* __restrict__
 
 // Skinny problem (few rows): one warp per (row-group, output) pair, K split across lanes.
 // Used when rows <= 8 so that the weight matrix is streamed exactly once.
-template <int R>
+template <int R, bool RB>
 __global__ void __launch_bounds__(256)
 linear_skinny_kernel(float* __restrict__ y, int64_t ldy, const float* __restrict__ x, int64_t ldx,
                      const float* __restrict__ w, int64_t ldw, const float* __restrict__ bias, int rows, int K, int N,
@@ -173,21 +180,27 @@ linear_skinny_kernel(float* __restrict__ y, int64_t ldy, const float* __restrict
     for (; k + 96 < K; k += 128) {   // four independent K slices in flight per lane (memory-level parallelism)
         float wv[4], xv[R][4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) wv[u] = wr[k + 32 * u];
+        for (int u = 0; u < 4; ++u) wv[u] = RB ? rbf(wr[k + 32 * u]) : wr[k + 32 * u];
 #pragma unroll
         for (int r = 0; r < R; ++r)
 #pragma unroll
-            for (int u = 0; u < 4; ++u) xv[r][u] = (r0 + r < rows) ? x[(int64_t)(r0 + r) * ldx + k + 32 * u] : 0.f;
+            for (int u = 0; u < 4; ++u) {
+                const float xx = (r0 + r < rows) ? x[(int64_t)(r0 + r) * ldx + k + 32 * u] : 0.f;
+                xv[r][u] = RB ? rbf(xx) : xx;
+            }
 #pragma unroll
         for (int r = 0; r < R; ++r)
 #pragma unroll
             for (int u = 0; u < 4; ++u) acc[r] = fmaf(xv[r][u], wv[u], acc[r]);
     }
     for (; k < K; k += 32) {
-        float wv = wr[k];
+        const float wv = RB ? rbf(wr[k]) : wr[k];
 #pragma unroll
         for (int r = 0; r < R; ++r)
-            if (r0 + r < rows) acc[r] = fmaf(x[(int64_t)(r0 + r) * ldx + k], wv, acc[r]);
+            if (r0 + r < rows) {
+                const float xx = x[(int64_t)(r0 + r) * ldx + k];
+                acc[r] = fmaf(RB ? rbf(xx) : xx, wv, acc[r]);
+            }
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[r] = warp_sum(acc[r]);
@@ -211,10 +224,13 @@ static int launch_simt(float* y, int64_t ldy, const float* x, int64_t ldx, const
     dim3 grid(ceil_div(N, BN), ceil_div(rows, BM));
     dim3 block((BM / TM) * (BN / TN));
     const bool vec = (ldx % 4 == 0) && (ldw % 4 == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)w % 16 == 0);
-    if (vec)
-        linear_simt_kernel<BM, BN, BK, TM, TN, true><<<grid, block, 0, st>>>(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags);
+    const bool rb = gemm_mode() == 2;
+    if (vec && !rb)
+        linear_simt_kernel<BM, BN, BK, TM, TN, true, false><<<grid, block, 0, st>>>(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags);
+    else if (!rb)
+        linear_simt_kernel<BM, BN, BK, TM, TN, false, false><<<grid, block, 0, st>>>(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags);
     else
-        linear_simt_kernel<BM, BN, BK, TM, TN, false><<<grid, block, 0, st>>>(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags);
+        linear_simt_kernel<BM, BN, BK, TM, TN, false, true><<<grid, block, 0, st>>>(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags);
     VAG_LAUNCH_CHECK();
     return VAG_OK;
 }
@@ -224,7 +240,8 @@ int linear_simt(float* y, int64_t ldy, const float* x, int64_t ldx, const float*
     const int sms = num_sms();
     if (rows <= 32 && N >= 64 && K >= 64) {   // weight-streaming regime: one warp per output feature, K across the lanes
         dim3 grid(ceil_div(N, 8), ceil_div(rows, 8));
-        linear_skinny_kernel<8><<<grid, 256, 0, st>>>(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags);
+        if (gemm_mode() == 2) linear_skinny_kernel<8, true><<<grid, 256, 0, st>>>(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags);
+        else linear_skinny_kernel<8, false><<<grid, 256, 0, st>>>(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags);
         VAG_LAUNCH_CHECK();
         return VAG_OK;
     }

@@ -18,11 +18,14 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <cuda_bf16.h>
 #include <stdlib.h>
 #include <string.h>
 #include <mutex>
 
 namespace vag {
+
+int gemm_mode();
 
 // ------------------------------------------------------------------------------------------ operand split
 // hi = round-to-nearest TF32 of v (low 13 mantissa bits zero), lo = v - hi.  Outputs are compact [rows, K].
@@ -65,6 +68,19 @@ split_f16_kernel(const float* __restrict__ x, int64_t ldx, int rows, int K, __ha
         }
         *reinterpret_cast<uint2*>(hi + (int64_t)r * ldo + c) = *reinterpret_cast<uint2*>(h);
         *reinterpret_cast<uint2*>(lo + (int64_t)r * ldo + c) = *reinterpret_cast<uint2*>(l);
+    }
+}
+
+// BF16 mode (north_star "bf16 mode": bf16 operands, FP32 accumulation): one plane, no error compensation.
+__global__ void __launch_bounds__(256)
+round_bf16_kernel(const float* __restrict__ x, int64_t ldx, int rows, int K, __nv_bfloat16* __restrict__ hi, int64_t ldo) {
+    const int kq = K >> 2;
+    const int64_t total = (int64_t)rows * kq;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / kq), c = (int)(i % kq) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(x + (int64_t)r * ldx + c);
+        __nv_bfloat16 h[4] = {__float2bfloat16_rn(v.x), __float2bfloat16_rn(v.y), __float2bfloat16_rn(v.z), __float2bfloat16_rn(v.w)};
+        *reinterpret_cast<uint2*>(hi + (int64_t)r * ldo + c) = *reinterpret_cast<uint2*>(h);
     }
 }
 
@@ -354,14 +370,17 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
                  ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
 }
 
-template <bool F16>
+// MODE: 0 = TF32 split (3 products), 1 = FP16 split (3 products), 2 = BF16 single product (bf16 mode)
+template <int MODE>
 __global__ void __launch_bounds__(320, 1)
 linear_split3_persistent_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                                 const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
                                 const __grid_constant__ CUtensorMap map_y, const float* __restrict__ bias, int rows, int K, int N,
                                 int flags, float4* __restrict__ summ) {
+    constexpr bool F16 = MODE != 0;              // 16-bit operands (kind::f16) vs TF32
+    constexpr bool SPLIT = MODE != 2;            // hi/lo error-compensated products
     constexpr int BM = 128, BN = 128, ELT = F16 ? 2 : 4, BK = 64 / ELT, UK = 32 / ELT;
-    constexpr uint32_t FMT = F16 ? 0u : 2u;
+    constexpr uint32_t FMT = MODE == 0 ? 2u : (MODE == 1 ? 0u : 1u);   // F16F32Format: F16 = 0, BF16 = 1, TF32 = 2
     constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     constexpr int T_BYTES = 128 * 64;  // one operand tile
     extern __shared__ uint8_t smem_raw[];
@@ -408,12 +427,12 @@ linear_split3_persistent_kernel(const __grid_constant__ CUtensorMap map_xh, cons
                     const int s = g % PSTAGES;
                     mbar_wait(&empty_bar[s], ((g / PSTAGES) & 1) ^ 1);
                     uint8_t* st = smem + s * P_STAGE_BYTES;
-                    mbar_expect_tx(&full_bar[s], P_STAGE_BYTES);
+                    mbar_expect_tx(&full_bar[s], SPLIT ? P_STAGE_BYTES : P_STAGE_BYTES / 2);
                     const int k0 = kb * BK;
                     tma_load_2d(st, &map_xh, &full_bar[s], k0, m0);
-                    tma_load_2d(st + T_BYTES, &map_xl, &full_bar[s], k0, m0);
+                    if (SPLIT) tma_load_2d(st + T_BYTES, &map_xl, &full_bar[s], k0, m0);
                     tma_load_2d(st + 2 * T_BYTES, &map_wh, &full_bar[s], k0, n0);
-                    tma_load_2d(st + 3 * T_BYTES, &map_wl, &full_bar[s], k0, n0);
+                    if (SPLIT) tma_load_2d(st + 3 * T_BYTES, &map_wl, &full_bar[s], k0, n0);
                 }
             }
         }
@@ -435,8 +454,10 @@ linear_split3_persistent_kernel(const __grid_constant__ CUtensorMap map_xh, cons
 #pragma unroll
                     for (int j = 0; j < BK / UK; ++j) {
                         const uint64_t adv = (uint64_t)((j * 32) >> 4);
-                        umma<F16>(d_cross, d_al + adv, d_bh + adv, IDESC, (kb | j) != 0);
-                        umma<F16>(d_cross, d_ah + adv, d_bl + adv, IDESC, 1);
+                        if (SPLIT) {
+                            umma<F16>(d_cross, d_al + adv, d_bh + adv, IDESC, (kb | j) != 0);
+                            umma<F16>(d_cross, d_ah + adv, d_bl + adv, IDESC, 1);
+                        }
                         umma<F16>(d_main, d_ah + adv, d_bh + adv, IDESC, (kb | j) != 0);
                     }
                     tcgen05_commit(&empty_bar[s]);
@@ -472,6 +493,7 @@ linear_split3_persistent_kernel(const __grid_constant__ CUtensorMap map_xh, cons
                 if (n0 + c0 >= N) break;  // warp-uniform: this chunk lies entirely outside the matrix
                 uint32_t r[32], q[32];
                 const uint32_t taddr = tmem_base + a * 256 + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0;
+                if (SPLIT)
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -501,7 +523,8 @@ linear_split3_persistent_kernel(const __grid_constant__ CUtensorMap map_xh, cons
                 float x[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    x[j] = (__uint_as_float(r[j]) + (F16 ? __uint_as_float(q[j]) * (1.0f / 2048.0f) : __uint_as_float(q[j]))) + bias_s[c0 + j];
+                    const float cross = !SPLIT ? 0.f : (F16 ? __uint_as_float(q[j]) * (1.0f / 2048.0f) : __uint_as_float(q[j]));
+                    x[j] = (__uint_as_float(r[j]) + cross) + bias_s[c0 + j];
                     if (do_tanh) x[j] = tanhf(x[j]);
                 }
                 if (summ) {
@@ -586,6 +609,7 @@ static EncodeTiledFn encode_fn() {
 
 // 2-D tensor [rows, K] (K contiguous, row pitch ld elements), box {128 B, box_rows}, SWIZZLE_128B, zero OOB fill.
 static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t K, int64_t ld, int box_rows, bool f16, int rowb) {
+    const bool bf16 = gemm_mode() == 2;
     EncodeTiledFn fn = encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled entry point not available");
@@ -595,7 +619,7 @@ static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t K, i
     cuuint64_t strides[1] = {(cuuint64_t)ld * (f16 ? 2 : 4)};
     cuuint32_t box[2] = {(cuuint32_t)(rowb / (f16 ? 2 : 4)), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1u, 1u};
-    CUresult r = fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = fn(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : (f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32), 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -651,12 +675,25 @@ static int launch_tc(const CUtensorMap& xh, const CUtensorMap& xl, const CUtenso
 }
 
 // VAG_GEMM=tf32x3 selects the TF32 split (any FP32 range); default is the FP16 split (2x the tensor rate).
-static bool use_f16_split() {
+// 0 = TF32 split, 1 = FP16 split (default), 2 = BF16 single product.  vag_set_gemm_mode() (thread-local) wins over VAG_GEMM.
+static thread_local int g_mode_override = -1;
+void set_gemm_mode(int m) { g_mode_override = m; }
+int gemm_mode() {
+    if (g_mode_override >= 0) return g_mode_override;
     const char* e = getenv("VAG_GEMM");
-    return !(e && strcmp(e, "tf32x3") == 0);
+    if (e && strcmp(e, "tf32x3") == 0) return 0;
+    if (e && strcmp(e, "bf16") == 0) return 2;
+    return 1;
 }
+static bool use_f16_split() { return gemm_mode() != 0; }   // 16-bit planes
 
 int tc_elem_bytes() { return use_f16_split() ? 2 : 4; }
+
+// Can tc_gemm take this call in the current mode?  (bf16 mode only has the persistent TMA-store kernel.)
+bool tc_call_supported(const float* y, int64_t ldy, int flags) {
+    if (gemm_mode() != 2) return true;
+    return ((ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && !(flags & VAG_LIN_ACCUMULATE);
+}
 
 // Split x [rows, K] (pitch ldx) into hi / lo planes of pitch ld_out ELEMENTS, starting at column col_off
 // (so several sources can be laid side by side along K for a concatenated contraction).
@@ -664,7 +701,9 @@ int tc_split(const float* x, int64_t ldx, int rows, int K, void* hi, void* lo, i
     const int64_t tot = (int64_t)rows * (K / 4);
     if (tot == 0) return VAG_OK;
     const int g = (int)std::min<int64_t>(ceil_div64(tot, 256), (int64_t)num_sms() * 8);
-    if (use_f16_split())
+    if (gemm_mode() == 2)
+        round_bf16_kernel<<<g, 256, 0, st>>>(x, ldx, rows, K, (__nv_bfloat16*)hi + col_off, ld_out);
+    else if (use_f16_split())
         split_f16_kernel<<<g, 256, 0, st>>>(x, ldx, rows, K, (__half*)hi + col_off, (__half*)lo + col_off, ld_out);
     else
         split_tf32_kernel<<<g, 256, 0, st>>>(x, ldx, rows, K, (float*)hi + col_off, (float*)lo + col_off, ld_out);
@@ -690,24 +729,28 @@ int tc_gemm(float* y, int64_t ldy, const void* xh, const void* xl, int64_t ldxs,
         VAG_TRY(make_map(&mwl, wl, N, K, ldws, 128, f16, 64));
         VAG_TRY(make_out_map(&my, y, rows, N, ldy));
         if (summ_tile_w) *summ_tile_w = 128;
-        static bool attr_set[2] = {false, false};
+        static bool attr_set[3] = {false, false, false};
         const int n_tiles = ceil_div(N, 128) * ceil_div(rows, 128);
         const int grid = n_tiles < sms ? n_tiles : sms;
-        if (f16) {
-            if (!attr_set[1]) {
-                VAG_CUDA(cudaFuncSetAttribute(linear_split3_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
-                attr_set[1] = true;
-            }
-            linear_split3_persistent_kernel<true><<<grid, 320, P_SMEM_BYTES, st>>>(mxh, mxl, mwh, mwl, my, bias, rows, K, N, flags, summ);
-        } else {
-            if (!attr_set[0]) {
-                VAG_CUDA(cudaFuncSetAttribute(linear_split3_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
-                attr_set[0] = true;
-            }
-            linear_split3_persistent_kernel<false><<<grid, 320, P_SMEM_BYTES, st>>>(mxh, mxl, mwh, mwl, my, bias, rows, K, N, flags, summ);
-        }
+        const int mode = gemm_mode();
+#define VAG_PERSIST(M)                                                                                                          \
+    do {                                                                                                                        \
+        if (!attr_set[M]) {                                                                                                     \
+            VAG_CUDA(cudaFuncSetAttribute(linear_split3_persistent_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES)); \
+            attr_set[M] = true;                                                                                                 \
+        }                                                                                                                       \
+        linear_split3_persistent_kernel<M><<<grid, 320, P_SMEM_BYTES, st>>>(mxh, mxl, mwh, mwl, my, bias, rows, K, N, flags, summ); \
+    } while (0)
+        if (mode == 0) VAG_PERSIST(0);
+        else if (mode == 1) VAG_PERSIST(1);
+        else VAG_PERSIST(2);
+#undef VAG_PERSIST
         VAG_LAUNCH_CHECK();
         return VAG_OK;
+    }
+    if (gemm_mode() == 2) {
+        set_error("tc_gemm: the bf16 mode needs a TMA-storable output and no accumulate flag");
+        return VAG_ERR_UNSUPPORTED;
     }
     // tile configuration of the one-tile-per-CTA kernel: VAG_TC_CFG=wide|narrow|dual (tuning / A-B runs)
     int cfg;  // 0 = 128x256 wide, 1 = 128x128 (128 B rows), 2 = 128x128 dual-CTA (64 B rows)

@@ -52,8 +52,33 @@ def _dropout_mask(model, name: str, p: float, shape, device) -> Optional[torch.T
     return torch.empty(shape, dtype=torch.float32, device=device).bernoulli_(1.0 - p).div_(1.0 - p)
 
 
+def _with_precision(fn):
+    """Run a public model method under the model's arithmetic mode (model.precision = "fp32" | "bf16")."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        mode = {"fp32": -1, "bf16": 2}[getattr(self, "precision", "fp32")]
+        if mode == -1:
+            return fn(self, *args, **kwargs)
+        from . import _cabi
+        lib = _cabi.lib()
+        lib.vag_set_gemm_mode(mode)
+        try:
+            return fn(self, *args, **kwargs)
+        finally:
+            lib.vag_set_gemm_mode(-1)
+    return wrapper
+
+
 class _Seq2SeqBase(nn.Module):
-    """Pieces shared by the two models: encoder → h0 → decoder loop / beam search."""
+    """Pieces shared by the two models: encoder → h0 → decoder loop / beam search.
+
+    ``precision``: "fp32" (default) keeps FP32-level accuracy on the tensor cores (error-compensated FP16 split,
+    token-exact decoding); "bf16" rounds every contraction operand to bfloat16 and issues a single product with
+    FP32 accumulation — state, soft-max, attention scores and losses stay FP32 (north_star "bf16 mode")."""
+
+    precision = "fp32"
 
     def _reset_like_reference(self):
         # V11:77-80 / V2:53-56: kaiming-normal on EVERY ≥2-D non-bias parameter (embeddings and GRU matrices too)
@@ -89,6 +114,7 @@ class _Seq2SeqBase(nn.Module):
         lens = hyp_len.cpu().tolist()
         return [hyp[b, :lens[b]].tolist() for b in range(B)]
 
+    @_with_precision
     def decode_device(self, src_var, src_lengths, im_var=None, beam_size=12, max_length=80):
         """Device-resident beam search: same work as ``beamsearch_decode`` but returns CUDA tensors
         (hyp int64 [B, L], hyp_len int32 [B]) without the final device→host copy / list building."""
@@ -202,6 +228,7 @@ class NMT_AttentionImagine_Seq2Seq_Beam_V11(_Seq2SeqBase):
         keys = ops.attn_keys(w, ctx)
         return w, ctx, mask, keys, h0, im_emb, txt_emb
 
+    @_with_precision
     def forward(self, src_var, src_lengths, tgt_var, im_var, teacher_force_ratio=1.0, max_length=80, criterion_mt=None,
                 criterion_vse=None):
         """→ (loss, loss_mt, loss_vse), V11:82-168."""
@@ -248,6 +275,7 @@ class NMT_AttentionImagine_Seq2Seq_Beam_V11(_Seq2SeqBase):
             return self.loss_w * out[1], out[1], 0
         return out[0], out[1], out[2]
 
+    @_with_precision
     def beamsearch_decode(self, src_var, src_lengths, im_var, beam_size=1, max_length=80, tgt_var=None):
         """→ list[B] of token-id lists (EOS excluded), V11:179-231."""
         tgt_l = max_length if tgt_var is None else tgt_var.size()[1]
@@ -257,11 +285,13 @@ class NMT_AttentionImagine_Seq2Seq_Beam_V11(_Seq2SeqBase):
         self.final_sample = self._decode_tokens(w, h0, keys, ctx, mask, beam_size, tgt_l)
         return self.final_sample
 
+    @_with_precision
     def embed_sent_im_eval(self, src_var, src_lengths, tgt_var, im_feats):
         """→ (im_embedding, text_embedding), V11:341-368."""
         self.tgt_l = tgt_var.size()[1]
         return self._embed(src_var, src_lengths, im_feats)
 
+    @_with_precision
     def embed_sent_im_test(self, src_var, src_lengths, im_feats, max_length=80):
         """→ (im_embedding, text_embedding), V11:370-397."""
         self.tgt_l = max_length
@@ -273,11 +303,13 @@ class NMT_AttentionImagine_Seq2Seq_Beam_V11(_Seq2SeqBase):
         im_emb, txt_emb, _, _ = self.vse_imagine.pool_sentence_major(im_feats.to(dev), ctx, mask)
         return im_emb, txt_emb
 
+    @_with_precision
     def get_imagine_attention_eval(self, src_var, src_lengths, tgt_var, im_feats):
         """→ attention weights [B, 1, T], V11:399-424."""
         self.tgt_l = tgt_var.size()[1]
         return self._imagine_attention(src_var, src_lengths, im_feats)
 
+    @_with_precision
     def get_imagine_attention_test(self, src_var, src_lengths, im_feats, max_length=80):
         """→ attention weights [B, 1, T], V11:426-450."""
         self.tgt_l = max_length
@@ -320,6 +352,7 @@ class NMT_Seq2Seq_Beam_V2(_Seq2SeqBase):
         keys = ops.attn_keys(w, ctx)
         return w, ctx, mask, keys, h0
 
+    @_with_precision
     def forward(self, src_var, src_lengths, tgt_var, teacher_force_ratio=1.0, max_length=80, criterion=None):
         """→ loss, models/NMT_Seq2Seq_Beam_V2.py:58-113."""
         dev = self._device()
@@ -338,6 +371,7 @@ class NMT_Seq2Seq_Beam_V2(_Seq2SeqBase):
         loss_rows = self._translation_loss_rows(w, h0, keys, ctx, mask, tgt, teacher_force_ratio, weight)
         return ops.translation_loss(loss_rows, tgt, None, 1.0)[1]
 
+    @_with_precision
     def beamsearch_decode(self, src_var, src_lengths, beam_size=1, max_length=80, tgt_var=None):
         """→ list[B] of token-id lists, models/NMT_Seq2Seq_Beam_V2.py:124-171."""
         tgt_l = max_length if tgt_var is None else tgt_var.size()[1]
