@@ -84,6 +84,8 @@ int vag_tc_elem_bytes(void);
  *  -1  back to the default / the VAG_GEMM environment variable (tf32x3 | bf16 | simt). */
 int vag_set_gemm_mode(int mode);
 int vag_get_gemm_mode(void);
+/* Tools only: device buffer of 32 int64 that the CTA-pair contraction fills with per-role cycle counters (NULL = off). */
+int vag_tc_set_debug(void* device_i64x32);
 int vag_tc_split_f32(const float* x, int64_t ldx, int rows, int K, void* hi, void* lo, int64_t ld_out, vag_stream_t stream);
 int vag_tc_gemm_f32(float* y, int64_t ldy, const void* x_hi, const void* x_lo, int64_t ldx, const void* w_hi,
                     const void* w_lo, int64_t ldw, const float* bias, int rows, int in_dim, int out_dim, int flags,

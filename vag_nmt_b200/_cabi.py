@@ -81,6 +81,7 @@ SIGNATURES = {
     "vag_tc_elem_bytes": (I, []),
     "vag_set_gemm_mode": (I, [I]),
     "vag_get_gemm_mode": (I, []),
+    "vag_tc_set_debug": (I, [P]),
     "vag_tc_split_f32": (I, [P, I64, I, I, P, P, I64, P]),
     "vag_tc_gemm_f32": (I, [P, I64, P, P, I64, P, P, I64, P, I, I, I, I, P]),
     "vag_linear_tc_workspace_bytes": (SZ, [I, I, I]),

@@ -106,6 +106,11 @@ extern "C" int vag_set_gemm_mode(int mode) {
     return VAG_OK;
 }
 extern "C" int vag_get_gemm_mode(void) { return gemm_mode(); }
+namespace vag { void set_tc_debug(long long* p); }
+extern "C" int vag_tc_set_debug(void* device_i64x32) {
+    set_tc_debug(reinterpret_cast<long long*>(device_i64x32));
+    return VAG_OK;
+}
 
 extern "C" int vag_tc_split_f32(const float* x, int64_t ldx, int rows, int K, void* hi, void* lo, int64_t ld_out,
                                 vag_stream_t stream) {

@@ -589,6 +589,335 @@ linear_split3_persistent_kernel(const __grid_constant__ CUtensorMap map_xh, cons
     }
 }
 
+// ------------------------------------------------------------------------------------------ CTA-pair kernel
+// The contractions of the decode step are bound by L2 → shared-memory traffic, not by the tensor pipe (ncu:
+// l1tex__m_xbar2l1tex_read_bytes ≈ 9 TB/s ≈ 85 % of the measured chip-wide cap while the tensor pipe idles half the
+// time): a 128 x 128 tile with split operands pulls 32 KB per 64-byte K block for six MMAs.  This kernel pairs the two
+// SMs of a TPC (cluster of 2, tcgen05 cta_group::2): the pair computes a 256 x 128 tile, every CTA loads its own 128
+// activation rows but only HALF of the weight tile (64 rows) — the MMA reads the other half from the peer's shared
+// memory — so the same six MMAs need 24 KB.  Roles per CTA as in the persistent kernel (warp 0 TMA producer, warp 1
+// MMA issuer — leader CTA only, warps 2-9 epilogue); barriers:
+//   full[s]    leader's shared memory, one arrival (leader's expect_tx of BOTH CTAs' bytes) — both producers' TMA loads
+//              complete on it (cp.async.bulk.tensor ... cta_group::2 may signal the peer's barrier)
+//   empty[s]   one per CTA, released by the leader's tcgen05.commit multicast to both CTAs
+//   tfull[a]   one per CTA, same multicast commit;  tempty[a]  leader's, 16 arrivals (8 epilogue warps x 2 CTAs)
+// The epilogue owns TWO staging tiles per warp so that a TMA store can drain while the next chunk is being written
+// (the single-buffer version was store-latency bound: 26 us for a K = 32 contraction with 73 MB of output).
+constexpr int Q_STAGES = 3;
+constexpr int Q_ROWB = 128;                                    // bytes of one K row in shared memory (SWIZZLE_128B)
+constexpr int Q_A_BYTES = 128 * Q_ROWB, Q_B_BYTES = 64 * Q_ROWB;
+constexpr int Q_STAGE_BYTES = 2 * Q_A_BYTES + 2 * Q_B_BYTES;   // A_hi, A_lo (128 rows), B_hi, B_lo (64 rows): 48 KB
+constexpr int Q_EPI_BYTES = 8 * 2 * 4096;                      // two 32 x 32 fp32 staging tiles per epilogue warp
+constexpr int Q_SMEM_BYTES = Q_STAGES * Q_STAGE_BYTES + Q_EPI_BYTES + 1024 /*bias per warp*/ + 4096 /*summary exchange x2*/ + 256 /*barriers*/ + 1024;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+template <bool F16>
+__device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (F16)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+}
+#define VAG_TMEM_LD32(v, addr)                                                                                                  \
+    asm volatile(                                                                                                               \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                               \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                               \
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                               \
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),           \
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),                \
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),               \
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                             \
+        : "r"(addr)                                                                                                             \
+        : "memory")
+
+// Role timers (tools/scratch/roles.py): compiled in with -DVAG_TC_TIMERS, otherwise every VAG_TCLK() folds to zero.
+#ifdef VAG_TC_TIMERS
+#define VAG_TCLK() clock64()
+#else
+#define VAG_TCLK() 0LL
+#endif
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
+linear_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
+                   const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
+                   const __grid_constant__ CUtensorMap map_y, const float* __restrict__ bias, int rows, int K, int N,
+                   int flags, float4* __restrict__ summ, long long* __restrict__ dbg) {
+    constexpr bool F16 = MODE != 0;
+    constexpr bool SPLIT = MODE != 2;
+    constexpr int BMP = 256, BM = 128, BN = 128, ELT = F16 ? 2 : 4, BK = Q_ROWB / ELT, UK = 32 / ELT;
+    constexpr uint32_t FMT = MODE == 0 ? 2u : (MODE == 1 ? 0u : 1u);
+    constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BMP >> 4) << 24);
+    constexpr uint32_t STAGE_TX = SPLIT ? Q_STAGE_BYTES : Q_STAGE_BYTES / 2;   // bytes ONE CTA's loads deliver per stage
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* epi = smem + Q_STAGES * Q_STAGE_BYTES;                      // 16 x 4 KB, 1024-B aligned
+    float* bias_w = reinterpret_cast<float*>(epi + Q_EPI_BYTES);         // [8 warps][32]
+    float4* xch2 = reinterpret_cast<float4*>(epi + Q_EPI_BYTES + 1024);  // [2][128], alternating between tiles
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi + Q_EPI_BYTES + 1024 + 4096);
+    uint64_t* empty_bar = full_bar + Q_STAGES;
+    uint64_t* tfull_bar = empty_bar + Q_STAGES;   // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;         // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int tiles_n = (N + BN - 1) / BN, tiles_m = (rows + BMP - 1) / BMP;
+    const int n_tiles = tiles_n * tiles_m;
+    const int n_kb = (K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_xh) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_xl) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wh) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wl) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y) : "memory");
+        for (int s = 0; s < Q_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], rank == 0 ? 9 : 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t g = 0;
+            long long t_wait = 0, t_begin = VAG_TCLK();
+            for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+                const int m0 = (tile / tiles_n) * BMP + (int)rank * BM, n0 = (tile % tiles_n) * BN + (int)rank * (BN / 2);
+                for (int kb = 0; kb < n_kb; ++kb, ++g) {
+                    const int s = g % Q_STAGES;
+                    const long long t0 = VAG_TCLK();
+                    mbar_wait(&empty_bar[s], ((g / Q_STAGES) & 1) ^ 1);
+                    t_wait += VAG_TCLK() - t0;
+                    uint8_t* st = smem + s * Q_STAGE_BYTES;
+                    if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * STAGE_TX);
+                    const uint32_t fb = mapa_u32(smem_u32(&full_bar[s]), 0);
+                    const int k0 = kb * BK;
+                    tma_load_2d_pair(st, &map_xh, fb, k0, m0);
+                    if (SPLIT) tma_load_2d_pair(st + Q_A_BYTES, &map_xl, fb, k0, m0);
+                    tma_load_2d_pair(st + 2 * Q_A_BYTES, &map_wh, fb, k0, n0);
+                    if (SPLIT) tma_load_2d_pair(st + 2 * Q_A_BYTES + Q_B_BYTES, &map_wl, fb, k0, n0);
+                }
+            }
+            if (dbg && pair == 0) { dbg[rank * 16 + 0] = VAG_TCLK() - t_begin; dbg[rank * 16 + 1] = t_wait; dbg[rank * 16 + 2] = g; }
+        }
+    } else if (warp == 1) {
+        if (rank == 0 && lane == 0) {
+            uint32_t g = 0, it = 0;
+            long long t_we = 0, t_wf = 0, t_begin = VAG_TCLK();
+            for (int tile = pair; tile < n_tiles; tile += n_pairs, ++it) {
+                const uint32_t a = it & 1;
+                long long t0 = VAG_TCLK();
+                mbar_wait(&tempty_bar[a], ((it >> 1) & 1) ^ 1);   // both CTAs' epilogues have drained this buffer
+                t_we += VAG_TCLK() - t0;
+                tcgen05_fence_after();
+                const uint32_t d_main = tmem_base + a * 256, d_cross = d_main + 128;
+                for (int kb = 0; kb < n_kb; ++kb, ++g) {
+                    const int s = g % Q_STAGES;
+                    t0 = VAG_TCLK();
+                    mbar_wait(&full_bar[s], (g / Q_STAGES) & 1);
+                    t_wf += VAG_TCLK() - t0;
+                    tcgen05_fence_after();
+                    const uint32_t st = smem_u32(smem + s * Q_STAGE_BYTES);
+                    const uint64_t d_ah = make_smem_desc<Q_ROWB>(st), d_al = make_smem_desc<Q_ROWB>(st + Q_A_BYTES);
+                    const uint64_t d_bh = make_smem_desc<Q_ROWB>(st + 2 * Q_A_BYTES), d_bl = make_smem_desc<Q_ROWB>(st + 2 * Q_A_BYTES + Q_B_BYTES);
+#pragma unroll
+                    for (int j = 0; j < BK / UK; ++j) {
+                        const uint64_t adv = (uint64_t)((j * 32) >> 4);
+                        if (SPLIT) {
+                            umma_pair<F16>(d_cross, d_al + adv, d_bh + adv, IDESC, (kb | j) != 0);
+                            umma_pair<F16>(d_cross, d_ah + adv, d_bl + adv, IDESC, 1);
+                        }
+                        umma_pair<F16>(d_main, d_ah + adv, d_bh + adv, IDESC, (kb | j) != 0);
+                    }
+                    tcgen05_commit_pair(&empty_bar[s]);
+                }
+                tcgen05_commit_pair(&tfull_bar[a]);
+            }
+            if (dbg && pair == 0) { dbg[4] = VAG_TCLK() - t_begin; dbg[5] = t_we; dbg[6] = t_wf; dbg[7] = it; }
+        } else if (rank == 1 && lane == 0) {
+            // the peer's MMA warp is idle: it forwards "my eight epilogue warps have drained buffer a" to the leader with
+            // ONE remote arrival per tile, keeping the cluster-scope release off the epilogue warps' critical path
+            uint32_t it = 0;
+            for (int tile = pair; tile < n_tiles; tile += n_pairs, ++it) {
+                const uint32_t a = it & 1;
+                mbar_wait(&tempty_bar[a], (it >> 1) & 1);
+                mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[a]), 0));
+            }
+        }
+    } else {
+        // ---- epilogue warps 2..9: TMEM lane group lg = warp % 4, column half ch (64 columns = two 32-wide chunks)
+        const int ew = warp - 2, lg = warp & 3, ch = ew >> 2;
+        uint8_t* my_tiles = epi + ew * 8192;
+        float* my_bias = bias_w + ew * 32;
+        const bool do_tanh = flags & VAG_LIN_TANH;
+        constexpr float kL2e = 1.4426950408889634f;
+        uint32_t it = 0, nst = 0;
+        long long t_wt = 0, t_ld = 0, t_ws = 0, t_math = 0, t_stage = 0, t_tma = 0, t_begin = VAG_TCLK();
+        for (int tile = pair; tile < n_tiles; tile += n_pairs, ++it) {
+            const int tn = tile % tiles_n;
+            const int m0 = (tile / tiles_n) * BMP + (int)rank * BM, n0 = tn * BN;
+            const uint32_t a = it & 1;
+            long long t0 = VAG_TCLK();
+            mbar_wait(&tfull_bar[a], (it >> 1) & 1);
+            t_wt += VAG_TCLK() - t0;
+            tcgen05_fence_after();
+            float sm_m = -INFINITY, sm_s = 0.f, sm_bv = -INFINITY;
+            int sm_bi = 0x7fffffff;
+            bool released = false;
+#pragma unroll 1
+            for (int cc = 0; cc < 2; ++cc) {
+                const int c0 = ch * 64 + cc * 32;
+                if (n0 + c0 >= N) break;  // warp-uniform: this chunk lies entirely outside the matrix
+                uint32_t r[32], q[32];
+                const uint32_t taddr = tmem_base + a * 256 + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0;
+                t0 = VAG_TCLK();
+                if (SPLIT) VAG_TMEM_LD32(q, taddr + 128u);
+                VAG_TMEM_LD32(r, taddr);
+                __syncwarp();
+                my_bias[lane] = (bias && n0 + c0 + lane < N) ? bias[n0 + c0 + lane] : 0.f;
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                t_ld += VAG_TCLK() - t0;
+                if (cc == 1 || n0 + c0 + 32 >= N) {
+                    // all TMEM reads of this warp for this tile are complete: hand the buffer back to the MMA warp early
+                    tcgen05_fence_before();
+                    if (lane == 0) mbar_arrive(&tempty_bar[a]);
+                    released = true;
+                }
+                __syncwarp();
+                t0 = VAG_TCLK();
+                float x[32];
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(my_bias + 4 * j4);
+                    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int j = 4 * j4 + u;
+                        const float cross = !SPLIT ? 0.f : (F16 ? __uint_as_float(q[j]) * (1.0f / 2048.0f) : __uint_as_float(q[j]));
+                        x[j] = (__uint_as_float(r[j]) + cross) + bb[u];
+                        if (do_tanh) x[j] = tanhf(x[j]);
+                    }
+                }
+                if (summ) {
+                    const int n_valid = min(32, N - (n0 + c0));
+                    float cm = -INFINITY;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) cm = fmaxf(cm, j < n_valid ? x[j] : -INFINITY);
+                    if (cm > sm_m) { sm_s *= exp2f((sm_m - cm) * kL2e); sm_m = cm; }
+                    const float m2 = sm_m * kL2e;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sm_s += j < n_valid ? exp2f(fmaf(x[j], kL2e, -m2)) : 0.f;
+                    if (cm > sm_bv) {
+                        sm_bv = cm;
+                        int first = 31;
+#pragma unroll
+                        for (int j = 31; j >= 0; --j) if (j < n_valid && x[j] == cm) first = j;
+                        sm_bi = n0 + c0 + first;
+                    }
+                }
+                // registers → 128-byte-swizzled staging tile (row = lane, 16-byte chunk index XOR row%8) → TMA store;
+                // two tiles alternate, so only the store issued TWO chunks ago has to have finished reading
+                uint8_t* my_tile = my_tiles + (nst & 1) * 4096;
+                ++nst;
+                t_math += VAG_TCLK() - t0;
+                t0 = VAG_TCLK();
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
+                t_ws += VAG_TCLK() - t0;
+                t0 = VAG_TCLK();
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    float4 v = make_float4(x[4 * c4], x[4 * c4 + 1], x[4 * c4 + 2], x[4 * c4 + 3]);
+                    *reinterpret_cast<float4*>(my_tile + lane * 128 + ((c4 ^ (lane & 7)) << 4)) = v;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                t_stage += VAG_TCLK() - t0;
+                t0 = VAG_TCLK();
+                if (lane == 0) {
+                    tma_store_2d(&map_y, my_tile, n0 + c0, m0 + lg * 32);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                __syncwarp();
+                t_tma += VAG_TCLK() - t0;
+            }
+            if (!released) {   // this warp had no chunk at all in this tile: it still owes the arrival
+                tcgen05_fence_before();
+                if (lane == 0) mbar_arrive(&tempty_bar[a]);
+            }
+            if (summ) {   // combine the two column halves of every row and write the (row, tile) summary
+                const int rl = lg * 32 + lane;
+                float4* xch = xch2 + (it & 1) * 128;   // the other copy may still be read by a slower warp
+                if (ch == 1) xch[rl] = make_float4(sm_m, sm_s, sm_bv, __int_as_float(sm_bi));
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                if (ch == 0) {
+                    const float4 o = xch[rl];
+                    float m = sm_m, s_ = sm_s, bv = sm_bv;
+                    int bi = sm_bi;
+                    if (o.x > m) { s_ = s_ * exp2f((m - o.x) * kL2e) + o.y; m = o.x; }
+                    else if (o.x != -INFINITY) s_ += o.y * exp2f((o.x - m) * kL2e);
+                    if (o.z > bv) { bv = o.z; bi = __float_as_int(o.w); }   // strictly greater: the left half wins ties
+                    const int row = m0 + rl;
+                    if (row < rows) summ[(int64_t)row * tiles_n + tn] = make_float4(m, s_, bv, __int_as_float(bi));
+                }
+            }
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (dbg && pair == 0 && ew == 0 && lane == 0) {
+            dbg[rank * 16 + 8] = VAG_TCLK() - t_begin; dbg[rank * 16 + 9] = t_wt; dbg[rank * 16 + 10] = t_ld; dbg[rank * 16 + 11] = t_ws; dbg[rank * 16 + 12] = t_math; dbg[rank * 16 + 13] = t_stage; dbg[rank * 16 + 14] = t_tma;
+        }
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();   // the peer's shared memory and the leader's barriers stay alive until both CTAs are done
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -677,6 +1006,8 @@ static int launch_tc(const CUtensorMap& xh, const CUtensorMap& xl, const CUtenso
 // VAG_GEMM=tf32x3 selects the TF32 split (any FP32 range); default is the FP16 split (2x the tensor rate).
 // 0 = TF32 split, 1 = FP16 split (default), 2 = BF16 single product.  vag_set_gemm_mode() (thread-local) wins over VAG_GEMM.
 static thread_local int g_mode_override = -1;
+static long long* g_tc_dbg = nullptr;   // optional device buffer [32] for the pair kernel's role timers (tools only)
+void set_tc_debug(long long* p) { g_tc_dbg = p; }
 void set_gemm_mode(int m) { g_mode_override = m; }
 int gemm_mode() {
     if (g_mode_override >= 0) return g_mode_override;
@@ -721,7 +1052,36 @@ int tc_gemm(float* y, int64_t ldy, const void* xh, const void* xl, int64_t ldxs,
     const char* e = getenv("VAG_TC_CFG");
     // Persistent kernel (default): needs a TMA-storable output (16-byte aligned rows) and no read-modify-write epilogue.
     const bool y_tma = ((ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && !(flags & VAG_LIN_ACCUMULATE);
-    if (y_tma && (!e || strcmp(e, "persistent") == 0)) {
+    if (y_tma && rows > 128 && (!e || strcmp(e, "pair") == 0)) {
+        // CTA-pair kernel: 256 x 128 tiles, half of the weight tile per CTA
+        CUtensorMap mxh, mxl, mwh, mwl, my;
+        VAG_TRY(make_map(&mxh, xh, rows, K, ldxs, 128, f16, Q_ROWB));
+        VAG_TRY(make_map(&mxl, xl, rows, K, ldxs, 128, f16, Q_ROWB));
+        VAG_TRY(make_map(&mwh, wh, N, K, ldws, 64, f16, Q_ROWB));
+        VAG_TRY(make_map(&mwl, wl, N, K, ldws, 64, f16, Q_ROWB));
+        VAG_TRY(make_out_map(&my, y, rows, N, ldy));
+        if (summ_tile_w) *summ_tile_w = 128;
+        static bool attr_set[3] = {false, false, false};
+        const int n_tiles = ceil_div(N, 128) * ceil_div(rows, 256);
+        const int max_pairs = sms / 2;
+        const int grid = 2 * (n_tiles < max_pairs ? n_tiles : max_pairs);
+        const int mode = gemm_mode();
+#define VAG_PAIR(M)                                                                                                             \
+    do {                                                                                                                        \
+        if (!attr_set[M]) {                                                                                                     \
+            VAG_CUDA(cudaFuncSetAttribute(linear_pair_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES));    \
+            attr_set[M] = true;                                                                                                 \
+        }                                                                                                                       \
+        linear_pair_kernel<M><<<grid, 320, Q_SMEM_BYTES, st>>>(mxh, mxl, mwh, mwl, my, bias, rows, K, N, flags, summ, g_tc_dbg);          \
+    } while (0)
+        if (mode == 0) VAG_PAIR(0);
+        else if (mode == 1) VAG_PAIR(1);
+        else VAG_PAIR(2);
+#undef VAG_PAIR
+        VAG_LAUNCH_CHECK();
+        return VAG_OK;
+    }
+    if (y_tma && (!e || strcmp(e, "persistent") == 0 || strcmp(e, "pair") == 0)) {
         CUtensorMap mxh, mxl, mwh, mwl, my;
         VAG_TRY(make_map(&mxh, xh, rows, K, ldxs, 128, f16, 64));
         VAG_TRY(make_map(&mxl, xl, rows, K, ldxs, 128, f16, 64));
