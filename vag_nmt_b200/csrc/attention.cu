@@ -9,6 +9,7 @@
 //   3. context: each thread owns 4 channels, streams ctx[t] once and accumulates all rows.
 // Bandwidth bound: algorithmic bytes per sentence = 2·T·C·4 (keys + ctx) + R·C·4·2 (q in, c out).
 #include "common.cuh"
+#include "split.cuh"
 #include <math.h>
 
 namespace vag {
@@ -195,7 +196,8 @@ template <int MODE, int RCAP, bool FULLC>
 __global__ void __launch_bounds__(256, RCAP <= 12 ? 3 : 2)
 attention_tuned_kernel(float* __restrict__ c_out, int64_t ld_c, float* __restrict__ alpha_out, const float* __restrict__ q,
                        int64_t ld_q, const float* __restrict__ keys, const float* __restrict__ ctx,
-                       const float* __restrict__ v, const float* __restrict__ mask, int rows, int rows_per_sent, int T, int C) {
+                       const float* __restrict__ v, const float* __restrict__ mask, int rows, int rows_per_sent, int T, int C,
+                       SplitDst sd) {
     extern __shared__ __align__(16) float smem[];
     const int b = blockIdx.x;
     const int r_base = blockIdx.y * RCAP;
@@ -358,14 +360,17 @@ attention_tuned_kernel(float* __restrict__ c_out, int64_t ld_c, float* __restric
         }
 #pragma unroll
         for (int r = 0; r < RCAP; ++r)
-            if (r < R && row0 + r < rows) *reinterpret_cast<float4*>(c_out + (int64_t)(row0 + r) * ld_c + c) = acc[r];
+            if (r < R && row0 + r < rows) {
+                if (c_out) *reinterpret_cast<float4*>(c_out + (int64_t)(row0 + r) * ld_c + c) = acc[r];
+                if (sd.hi) split_store4(sd, row0 + r, c, acc[r]);   // operand planes for context2hid / the read-out
+            }
     }
 }
 
 template <int MODE, int RCAP, bool FULLC>
 static int launch_attention_tuned(float* c_out, int64_t ld_c, float* alpha, const float* q, int64_t ld_q, const float* keys,
                                   const float* ctx, const float* v, const float* mask, int rows, int rows_per_sent, int T, int C,
-                                  cudaStream_t st) {
+                                  cudaStream_t st, SplitDst sd = SplitDst()) {
     const size_t smem = ((size_t)RCAP * C + C + (size_t)RCAP * T) * sizeof(float);
     if (smem > 227 * 1024) {
         set_error("vag_attention_f32: C=%d T=%d needs %zu B of shared memory", C, T, smem);
@@ -378,7 +383,7 @@ static int launch_attention_tuned(float* c_out, int64_t ld_c, float* alpha, cons
     }
     dim3 grid(rows / rows_per_sent, ceil_div(rows_per_sent, RCAP));
     attention_tuned_kernel<MODE, RCAP, FULLC><<<grid, 256, smem, st>>>(c_out, ld_c, alpha, q, ld_q, keys, ctx, v, mask, rows,
-                                                                 rows_per_sent, T, C);
+                                                                 rows_per_sent, T, C, sd);
     VAG_LAUNCH_CHECK();
     return VAG_OK;
 }
@@ -386,12 +391,12 @@ static int launch_attention_tuned(float* c_out, int64_t ld_c, float* alpha, cons
 template <int MODE>
 static int dispatch_attention_tuned(float* c_out, int64_t ld_c, float* alpha, const float* q, int64_t ld_q, const float* keys,
                                     const float* ctx, const float* v, const float* mask, int rows, int rows_per_sent, int T,
-                                    int C, cudaStream_t st) {
+                                    int C, cudaStream_t st, SplitDst sd = SplitDst()) {
 #define VAG_ATT(RC)                                                                                                        \
     do {                                                                                                                   \
         if (C % 1024 == 0)                                                                                                 \
-            return launch_attention_tuned<MODE, RC, true>(c_out, ld_c, alpha, q, ld_q, keys, ctx, v, mask, rows, rows_per_sent, T, C, st); \
-        return launch_attention_tuned<MODE, RC, false>(c_out, ld_c, alpha, q, ld_q, keys, ctx, v, mask, rows, rows_per_sent, T, C, st);    \
+            return launch_attention_tuned<MODE, RC, true>(c_out, ld_c, alpha, q, ld_q, keys, ctx, v, mask, rows, rows_per_sent, T, C, st, sd); \
+        return launch_attention_tuned<MODE, RC, false>(c_out, ld_c, alpha, q, ld_q, keys, ctx, v, mask, rows, rows_per_sent, T, C, st, sd); \
     } while (0)
     if (rows_per_sent == 1) VAG_ATT(1);
     if (rows_per_sent <= 4) VAG_ATT(4);
@@ -399,6 +404,13 @@ static int dispatch_attention_tuned(float* c_out, int64_t ld_c, float* alpha, co
     if (rows_per_sent <= 12) VAG_ATT(12);
     VAG_ATT(16);
 #undef VAG_ATT
+}
+
+// Decoder-step attention of the fused step: the context leaves the kernel only as tensor-core operand planes.
+// Requirements (the caller's workspace guarantees them): C % 4 == 0, 16-byte aligned q / keys / ctx, rows_per_sent <= 16.
+int attention_mlp_split(SplitDst sd, const float* q, int64_t ld_q, const float* keys, const float* ctx, const float* v,
+                        const float* mask, int rows, int rows_per_sent, int T, int C, cudaStream_t st) {
+    return dispatch_attention_tuned<VAG_ATTN_MLP>(nullptr, 0, nullptr, q, ld_q, keys, ctx, v, mask, rows, rows_per_sent, T, C, st, sd);
 }
 
 }  // namespace vag

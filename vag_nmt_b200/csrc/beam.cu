@@ -5,6 +5,7 @@
 // private top-K in registers (static indexing only), then K rounds of a block arg-max pop the winners in
 // canonical order (score descending, flat index k·V+v ascending on ties).  HBM bound: the logits are read once.
 #include "common.cuh"
+#include "split.cuh"
 #include <math.h>
 
 namespace vag {
@@ -523,6 +524,38 @@ beam_advance_kernel(float* __restrict__ h_next, const float* __restrict__ h_cur,
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) steps_run[0] = step + 1;
 }
+// Fused-step flavour: one launch reorders the hidden state by parent (fp32 + tensor-core operand planes), gathers the
+// operand planes of the next step's input embeddings from the pre-split table, and evaluates the stop test (the
+// separate one-thread kernel of the plain path).  A block that sees the flag flip mid-launch may skip its copy: the
+// state of a finished search is never read again.
+__global__ void __launch_bounds__(128)
+beam_advance_fused_kernel(float* __restrict__ h_next, const float* __restrict__ h_cur, const int32_t* __restrict__ parents,
+                          const int64_t* __restrict__ tokens, int B, int K, int Kin, int H, int step, int* __restrict__ done,
+                          const int* __restrict__ fin_counter, int* __restrict__ steps_run, SplitDst h_sd, SplitDst e_sd,
+                          const uint16_t* __restrict__ t_hi, const uint16_t* __restrict__ t_lo, int64_t ld_t, int E, int64_t V) {
+    if (*reinterpret_cast<volatile int*>(done)) return;
+    const int n = blockIdx.x;  // new row
+    const int b = n / K;
+    const int p = b * Kin + (Kin == 1 ? 0 : parents[n]);
+    const float4* src = reinterpret_cast<const float4*>(h_cur + (int64_t)p * H);
+    float4* dst = reinterpret_cast<float4*>(h_next + (int64_t)n * H);
+    for (int c = threadIdx.x; c < H / 4; c += blockDim.x) {
+        const float4 v = src[c];
+        dst[c] = v;
+        split_store4(h_sd, n, c * 4, v);
+    }
+    int64_t id = tokens[n];
+    if (id < 0 || id >= V) id = 0;
+    for (int c = threadIdx.x; c < E / 8; c += blockDim.x) {
+        *reinterpret_cast<uint4*>(e_sd.hi + (int64_t)n * e_sd.ld + c * 8) = *reinterpret_cast<const uint4*>(t_hi + id * ld_t + c * 8);
+        if (e_sd.mode != 2)
+            *reinterpret_cast<uint4*>(e_sd.lo + (int64_t)n * e_sd.ld + c * 8) = *reinterpret_cast<const uint4*>(t_lo + id * ld_t + c * 8);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        steps_run[0] = step + 1;
+        if (*fin_counter == B * K) *done = 1;
+    }
+}
 __global__ void beam_done_kernel(int* __restrict__ done, const int* __restrict__ fin_counter, int total) {
     if (*fin_counter == total) *done = 1;
 }
@@ -671,6 +704,15 @@ int beam_advance(float* h_next, const float* h_cur, const int32_t* parents, int 
     beam_advance_kernel<<<B * K, 128, 0, st>>>(h_next, h_cur, parents, B, K, Kin, H, step, done, fin_counter, steps_run);
     VAG_LAUNCH_CHECK();
     beam_done_kernel<<<1, 1, 0, st>>>(done, fin_counter, B * K);
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
+int beam_advance_fused(float* h_next, const float* h_cur, const int32_t* parents, const int64_t* tokens, int B, int K, int Kin,
+                       int H, int step, int* done, int* fin_counter, int* steps_run, SplitDst h_sd, SplitDst e_sd,
+                       const uint16_t* t_hi, const uint16_t* t_lo, int64_t ld_t, int E, int64_t V, cudaStream_t st) {
+    beam_advance_fused_kernel<<<B * K, 128, 0, st>>>(h_next, h_cur, parents, tokens, B, K, Kin, H, step, done, fin_counter, steps_run,
+                                                     h_sd, e_sd, t_hi, t_lo, ld_t, E, V);
     VAG_LAUNCH_CHECK();
     return VAG_OK;
 }

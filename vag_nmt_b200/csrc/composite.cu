@@ -291,6 +291,103 @@ static int decoder_step_core(GemmCtx& gemm, const vag_decoder_weights* w, const 
     if (logits) VAG_TRY(gemm.linear(logits, ld_logits, ws.t, E, w->out_w, E, w->out_b, rows, E, (int)V, 0, summ, summ_tile_w));            // :143
     return VAG_OK;
 }
+
+// ------------------------------------------------------------------ fused decode step (tensor-core path only)
+// Same arithmetic as decoder_step_core, but no activation ever takes the detour "fp32 in HBM → split kernel → planes":
+// every producer writes the operand planes of what it produced (split.cuh), and activations that only feed
+// contractions (embedding row, context, context2hid output, read-out) exist ONLY as planes.  Nine split launches, the
+// embedding gather and four fp32 round trips per step disappear.  The read-out input [h2 | e | c] is one plane pair of
+// pitch H+E+C; the embedding and the context are column windows of it (TMA takes any 16-byte aligned pitch).
+int gru_gates_split(float* h_out, int64_t ld_ho, const float* gi, int64_t ld_gi, const float* gh, int64_t ld_gh,
+                    const float* h_prev, int64_t ld_hp, int rows, int H, SplitDst sd, cudaStream_t st);
+int embed_split_rows(SplitDst dst, const uint16_t* t_hi, const uint16_t* t_lo, int64_t ld_t, int E, const int64_t* tokens, int rows,
+                     int64_t V, cudaStream_t st);
+int attention_mlp_split(SplitDst sd, const float* q, int64_t ld_q, const float* keys, const float* ctx, const float* v,
+                        const float* mask, int rows, int rows_per_sent, int T, int C, cudaStream_t st);
+int beam_advance_fused(float* h_next, const float* h_cur, const int32_t* parents, const int64_t* tokens, int B, int K, int Kin,
+                       int H, int step, int* done, int* fin_counter, int* steps_run, SplitDst h_sd, SplitDst e_sd,
+                       const uint16_t* t_hi, const uint16_t* t_lo, int64_t ld_t, int E, int64_t V, cudaStream_t st);
+
+struct FusedStep {
+    bool ok = false;
+    SplitDst hprev, h1, x2, t, cat;                 // cat = [h2 | e | c], pitch H + E + C
+    GemmCtx::Ent *w_g1i = nullptr, *w_g1h = nullptr, *w_ah = nullptr, *w_c2h = nullptr, *w_g2i = nullptr, *w_g2h = nullptr,
+                 *w_ro = nullptr, *w_out = nullptr, *w_emb = nullptr;
+    float* b_ro = nullptr;
+    SplitDst cat_e(int H) const { SplitDst d = cat; d.hi += H; if (d.lo) d.lo += H; return d; }
+    SplitDst cat_c(int H, int E) const { SplitDst d = cat; d.hi += H + E; if (d.lo) d.lo += H + E; return d; }
+};
+
+static int fused_setup(GemmCtx& gemm, const vag_decoder_weights* w, const StepWs& ws, int n_rows, int rows_per_sent, FusedStep* f) {
+    const int E = w->E, H = w->H, C = w->C, Kt = H + E + C;
+    const int64_t V = w->V;
+    const int mode = gemm_mode();
+    f->ok = false;
+    if (!gemm.tc || (mode != 1 && mode != 2) || n_rows <= 128 || rows_per_sent > 16 || V < 64) return VAG_OK;
+    if ((E % 8) || (H % 8) || (C % 8)) return VAG_OK;
+    const float* ws_[] = {w->gru1_w_ih, w->gru1_w_hh, w->attn_h_w, w->c2h_w, w->gru2_w_ih, w->gru2_w_hh, w->w1_w, w->w2_w, w->w3_w,
+                          w->out_w, w->emb};
+    for (const float* p : ws_)
+        if (!p || ((uintptr_t)p & 15)) return VAG_OK;
+    VAG_TRY(gemm.weight(&f->w_g1i, w->gru1_w_ih, E, 3 * H, E));
+    VAG_TRY(gemm.weight(&f->w_g1h, w->gru1_w_hh, H, 3 * H, H));
+    VAG_TRY(gemm.weight(&f->w_ah, w->attn_h_w, H, C, H));
+    VAG_TRY(gemm.weight(&f->w_c2h, w->c2h_w, C, H, C));
+    VAG_TRY(gemm.weight(&f->w_g2i, w->gru2_w_ih, H, 3 * H, H));
+    VAG_TRY(gemm.weight(&f->w_g2h, w->gru2_w_hh, H, 3 * H, H));
+    VAG_TRY(gemm.weight(&f->w_out, w->out_w, E, (int)V, E));
+    {
+        const float* const wts[3] = {w->w1_w, w->w3_w, w->w2_w};
+        const float* const bs[3] = {w->w1_b, w->w3_b, w->w2_b};
+        const int64_t lds[3] = {H, E, C};
+        const int Ks[3] = {H, E, C};
+        VAG_TRY(gemm.weight3(&f->w_ro, &f->b_ro, wts, lds, Ks, bs, E));
+    }
+    if (w->emb == w->out_w) f->w_emb = f->w_out;   // tied: the gather reads the projection's planes
+    else VAG_TRY(gemm.weight(&f->w_emb, w->emb, E, (int)V, E));
+    if (!f->w_g1i || !f->w_g1h || !f->w_ah || !f->w_c2h || !f->w_g2i || !f->w_g2h || !f->w_out || !f->w_ro || !f->b_ro || !f->w_emb)
+        return VAG_OK;
+    // activation planes, carved once from the step's activation region (the plain path's per-step splits are not used)
+    Arena ar(ws.areg, ws.abytes);
+    auto planes = [&](SplitDst* d, int K) {
+        d->hi = (uint16_t*)ar.take<uint16_t>((size_t)n_rows * K);
+        d->lo = (uint16_t*)ar.take<uint16_t>((size_t)n_rows * K);
+        d->ld = K;
+        d->mode = mode;
+    };
+    planes(&f->hprev, H);
+    planes(&f->h1, H);
+    planes(&f->x2, H);
+    planes(&f->t, E);
+    planes(&f->cat, Kt);
+    if (ar.overflow) return VAG_OK;
+    f->ok = true;
+    return VAG_OK;
+}
+
+// One fused step: the embedding planes (cat_e) and the previous state's planes (hprev) are already in place.
+static int decoder_step_fused(const FusedStep& f, const vag_decoder_weights* w, const StepWs& ws, const float* h_prev, const float* keys,
+                              const float* ctx, const float* mask, int rows, int rows_per_sent, int T, float* h_out, float* logits,
+                              int64_t ld_logits, cudaStream_t st, float4* summ, int* summ_tile_w) {
+    const int E = w->E, H = w->H, C = w->C, Kt = H + E + C;
+    const int64_t V = w->V;
+    const SplitDst ce = f.cat_e(H), cc = f.cat_c(H, E);
+    auto gemm = [&](float* y, int64_t ldy, const SplitDst& x, const GemmCtx::Ent* we, const float* bias, int K, int N, float4* sm,
+                    int* tw) {
+        return tc_gemm(y, ldy, x.hi, x.lo, x.ld, we->hi, we->lo, we->ld, bias, rows, K, N, 0, st, sm, tw);
+    };
+    VAG_TRY(gemm(ws.gi, 3 * H, ce, f.w_g1i, w->gru1_b_ih, E, 3 * H, nullptr, nullptr));                      // NMT_Decoder.py:121
+    VAG_TRY(gemm(ws.gh, 3 * H, f.hprev, f.w_g1h, w->gru1_b_hh, H, 3 * H, nullptr, nullptr));
+    VAG_TRY(gru_gates_split(ws.h1, H, ws.gi, 3 * H, ws.gh, 3 * H, h_prev, H, rows, H, f.h1, st));
+    VAG_TRY(gemm(ws.q, C, f.h1, f.w_ah, nullptr, H, C, nullptr, nullptr));                                    // :47
+    VAG_TRY(attention_mlp_split(cc, ws.q, C, keys, ctx, w->attn_v, mask, rows, rows_per_sent, T, C, st));     // :124-126
+    VAG_TRY(tc_gemm_split_out(f.x2, cc.hi, cc.lo, Kt, f.w_c2h->hi, f.w_c2h->lo, f.w_c2h->ld, nullptr, rows, C, H, 0, st));   // :127
+    VAG_TRY(gemm(ws.gi, 3 * H, f.x2, f.w_g2i, w->gru2_b_ih, H, 3 * H, nullptr, nullptr));                     // :129
+    VAG_TRY(gemm(ws.gh, 3 * H, f.h1, f.w_g2h, w->gru2_b_hh, H, 3 * H, nullptr, nullptr));
+    VAG_TRY(gru_gates_split(h_out, H, ws.gi, 3 * H, ws.gh, 3 * H, ws.h1, H, rows, H, f.cat, st));
+    VAG_TRY(tc_gemm_split_out(f.t, f.cat.hi, f.cat.lo, Kt, f.w_ro->hi, f.w_ro->lo, f.w_ro->ld, f.b_ro, rows, Kt, E, VAG_LIN_TANH, st));  // :137
+    return gemm(logits, ld_logits, f.t, f.w_out, w->out_b, E, (int)V, summ, summ_tile_w);                     // :143
+}
 }  // namespace vag
 
 extern "C" size_t vag_decoder_step_workspace_bytes(int rows, int E, int H, int C, int64_t V) {
@@ -385,12 +482,23 @@ extern "C" int vag_beam_decode_f32(const vag_decoder_weights* w, const float* h0
     VAG_LAUNCH_CHECK();
     const int64_t ldl = (V + 3) / 4 * 4;
     GemmCtx gemm(st, ws.step.wreg, ws.step.wbytes, ws.step.areg, ws.step.abytes);
+    FusedStep fused;
+    VAG_TRY(fused_setup(gemm, w, ws.step, N, K, &fused));
     for (int di = 0; di < L; ++di) {
         const int rows = di == 0 ? B : N;
         const int rps = di == 0 ? 1 : K;
         const int64_t* tokens = di == 0 ? ws.sos : ws.tok_hist + (size_t)(di - 1) * N;
         const float* h_prev = di == 0 ? h0 : ws.h_a;
         int tile_w = 0;  // > 0 when the tensor-core projection also produced the per-tile soft-max / arg-max summaries
+        if (fused.ok && rows > 128) {
+            if (di == 0) {   // planes of the initial state and of the <sos> embedding; later steps get them from the reorder
+                VAG_TRY(tc_split(h0, H, B, H, fused.hprev.hi, fused.hprev.lo, H, 0, st));
+                VAG_TRY(embed_split_rows(fused.cat_e(H), (const uint16_t*)fused.w_emb->hi, (const uint16_t*)fused.w_emb->lo,
+                                         fused.w_emb->ld, E, ws.sos, B, V, st));
+            }
+            VAG_TRY(decoder_step_fused(fused, w, ws.step, h_prev, keys, ctx, mask, rows, rps, T, ws.h_b, ws.logits, ldl, st,
+                                       V >= 512 ? ws.summ : nullptr, &tile_w));
+        } else
         VAG_TRY(decoder_step_core(gemm, w, ws.step, tokens, h_prev, keys, ctx, mask, rows, rps, T, ws.h_b, ws.logits, ldl, nullptr, st,
                                   V >= 512 ? ws.summ : nullptr, &tile_w));
         if (tile_w > 0) {
@@ -403,7 +511,12 @@ extern "C" int vag_beam_decode_f32(const vag_decoder_weights* w, const float* h0
             VAG_TRY(beam_select(ws.logits, ldl, ws.lse, di == 0 ? nullptr : tokens, ws.nll, ws.tok_hist + (size_t)di * N,
                                 ws.par_hist + (size_t)di * N, B, K, V, di, avoid_double, done, fin + di, st));
         }
-        VAG_TRY(beam_advance(ws.h_a, ws.h_b, ws.par_hist + (size_t)di * N, B, K, rps, H, di, done, fin + di, steps_run, st));
+        if (fused.ok)
+            VAG_TRY(beam_advance_fused(ws.h_a, ws.h_b, ws.par_hist + (size_t)di * N, ws.tok_hist + (size_t)di * N, B, K, rps, H, di, done,
+                                       fin + di, steps_run, fused.hprev, fused.cat_e(H), (const uint16_t*)fused.w_emb->hi,
+                                       (const uint16_t*)fused.w_emb->lo, fused.w_emb->ld, E, V, st));
+        else
+            VAG_TRY(beam_advance(ws.h_a, ws.h_b, ws.par_hist + (size_t)di * N, B, K, rps, H, di, done, fin + di, steps_run, st));
     }
     VAG_TRY(beam_finalize(ws.tok_hist, ws.par_hist, ws.nll, steps_run, B, K, L, hyp_out, hyp_len, beam_out, st));
     if (nll_out) VAG_CUDA(cudaMemcpyAsync(nll_out, ws.nll, sizeof(float) * (size_t)N, cudaMemcpyDeviceToDevice, st));

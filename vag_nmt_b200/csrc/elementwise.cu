@@ -1,6 +1,7 @@
 // Bandwidth-bound fused element-wise / row-wise kernels: GRU gates, decoder-init mix, l2norm,
 // log-softmax, NLL rows.  All FP32, vectorised where the strides allow it.
 #include "common.cuh"
+#include "split.cuh"
 #include <math.h>
 
 namespace vag {
@@ -11,7 +12,7 @@ template <bool VEC>
 __global__ void __launch_bounds__(256)
 gru_gates_kernel(float* h_out, int64_t ld_ho, float* h_out2, int64_t ld_ho2,
                  const float* __restrict__ gi, int64_t ld_gi, const float* __restrict__ gh, int64_t ld_gh,
-                 const float* h_prev /* may alias h_out */, int64_t ld_hp, int rows, int H) {
+                 const float* h_prev /* may alias h_out */, int64_t ld_hp, int rows, int H, SplitDst sd) {
     constexpr int W = VEC ? 4 : 1;
     const int per_row = H / W;
     const int64_t total = (int64_t)rows * per_row;
@@ -45,6 +46,7 @@ gru_gates_kernel(float* h_out, int64_t ld_ho, float* h_out2, int64_t ld_ho2,
         if (VEC) {
             *reinterpret_cast<float4*>(h_out + (int64_t)row * ld_ho + j) = *reinterpret_cast<float4*>(out);
             if (h_out2) *reinterpret_cast<float4*>(h_out2 + (int64_t)row * ld_ho2 + j) = *reinterpret_cast<float4*>(out);
+            if (sd.hi) split_store4(sd, row, j, *reinterpret_cast<float4*>(out));   // tensor-core operand planes of the new state
         } else {
             h_out[(int64_t)row * ld_ho + j] = out[0];
             if (h_out2) h_out2[(int64_t)row * ld_ho2 + j] = out[0];
@@ -198,9 +200,47 @@ int row_lse(float* lse_out, const float* logits, int64_t ld, int rows, int64_t V
     return VAG_OK;
 }
 
+// Fused-step flavour of the gates: also writes the operand planes of the new state (all pitches multiples of 4, 16-byte
+// aligned pointers — guaranteed by the caller's workspace layout).
+int gru_gates_split(float* h_out, int64_t ld_ho, const float* gi, int64_t ld_gi, const float* gh, int64_t ld_gh,
+                    const float* h_prev, int64_t ld_hp, int rows, int H, SplitDst sd, cudaStream_t st) {
+    if (rows == 0) return VAG_OK;
+    const int64_t total = (int64_t)rows * (H / 4);
+    const int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)num_sms() * 16);
+    gru_gates_kernel<true><<<blocks, 256, 0, st>>>(h_out, ld_ho, nullptr, 0, gi, ld_gi, gh, ld_gh, h_prev, ld_hp, rows, H, sd);
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
+// dst[row, 0:E) (both planes) = split planes of table[tokens[row], :] — the embedding gather reads the ALREADY SPLIT
+// table (the tied output projection keeps one for the vocabulary contraction), so no fp32 row is ever materialised.
+__global__ void __launch_bounds__(256)
+embed_split_rows_kernel(SplitDst dst, const uint16_t* __restrict__ t_hi, const uint16_t* __restrict__ t_lo, int64_t ld_t, int E,
+                        const int64_t* __restrict__ tokens, int rows, int64_t V) {
+    const int per_row = E / 8;   // 16-byte chunks per row and plane
+    const int64_t total = (int64_t)rows * per_row;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int row = (int)(i / per_row), c = (int)(i % per_row) * 8;
+        int64_t id = tokens[row];
+        if (id < 0 || id >= V) id = 0;
+        *reinterpret_cast<uint4*>(dst.hi + (int64_t)row * dst.ld + c) = *reinterpret_cast<const uint4*>(t_hi + id * ld_t + c);
+        if (dst.mode != 2) *reinterpret_cast<uint4*>(dst.lo + (int64_t)row * dst.ld + c) = *reinterpret_cast<const uint4*>(t_lo + id * ld_t + c);
+    }
+}
+int embed_split_rows(SplitDst dst, const uint16_t* t_hi, const uint16_t* t_lo, int64_t ld_t, int E, const int64_t* tokens, int rows,
+                     int64_t V, cudaStream_t st) {
+    if (rows == 0) return VAG_OK;
+    const int64_t total = (int64_t)rows * (E / 8);
+    const int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)num_sms() * 16);
+    embed_split_rows_kernel<<<blocks, 256, 0, st>>>(dst, t_hi, t_lo, ld_t, E, tokens, rows, V);
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
 }  // namespace vag
 
 using namespace vag;
+
 
 extern "C" int vag_gru_gates_f32(float* h_out, int64_t ld_ho, float* h_out2, int64_t ld_ho2, const float* gi, int64_t ld_gi,
                                  const float* gh, int64_t ld_gh, const float* h_prev, int64_t ld_hp, int rows, int H,
@@ -214,9 +254,9 @@ extern "C" int vag_gru_gates_f32(float* h_out, int64_t ld_ho, float* h_out2, int
     const int64_t total = (int64_t)rows * (vec ? H / 4 : H);
     const int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)num_sms() * 16);
     if (vec)
-        gru_gates_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(h_out, ld_ho, h_out2, ld_ho2, gi, ld_gi, gh, ld_gh, h_prev, ld_hp, rows, H);
+        gru_gates_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(h_out, ld_ho, h_out2, ld_ho2, gi, ld_gi, gh, ld_gh, h_prev, ld_hp, rows, H, SplitDst());
     else
-        gru_gates_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(h_out, ld_ho, h_out2, ld_ho2, gi, ld_gi, gh, ld_gh, h_prev, ld_hp, rows, H);
+        gru_gates_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(h_out, ld_ho, h_out2, ld_ho2, gi, ld_gi, gh, ld_gh, h_prev, ld_hp, rows, H, SplitDst());
     VAG_LAUNCH_CHECK();
     return VAG_OK;
 }

@@ -7,6 +7,7 @@
 //     (the three-matrix read-out  tanh(W1 h2 + W3 e + W2 c)  of NMT_Decoder.py:137).
 #pragma once
 #include "common.cuh"
+#include "split.cuh"
 
 namespace vag {
 
@@ -17,6 +18,9 @@ int tc_split(const float* x, int64_t ldx, int rows, int K, void* hi, void* lo, i
 int tc_gemm(float* y, int64_t ldy, const void* xh, const void* xl, int64_t ldxs, const void* wh, const void* wl, int64_t ldws,
             const float* bias, int rows, int K, int N, int flags, cudaStream_t st, float4* summ, int* summ_tile_w);
 bool tc_enabled();
+int gemm_mode();
+int tc_gemm_split_out(SplitDst out, const void* xh, const void* xl, int64_t ldxs, const void* wh, const void* wl, int64_t ldws,
+                      const float* bias, int rows, int K, int N, int flags, cudaStream_t st);
 bool tc_call_supported(const float* y, int64_t ldy, int flags);
 int bias_sum3(float* out, const float* a, const float* b, const float* c, int n, cudaStream_t st);
 
@@ -73,6 +77,38 @@ struct GemmCtx {
         return &tab[n++];
     }
 
+    // Split planes of a weight matrix, made once per composite call (nullptr: cache full / no region → FFMA path).
+    int weight(Ent** out, const float* w, int64_t ldw, int N, int K) {
+        Ent* we = lookup(wc, nw, w, N, K);
+        if (!we && (we = make(true, w, N, K))) VAG_TRY(tc_split(w, ldw, N, K, we->hi, we->lo, K, 0, st));
+        *out = we;
+        return VAG_OK;
+    }
+    // Three weight matrices laid side by side along K plus the sum of their biases (the read-out of NMT_Decoder.py:137).
+    int weight3(Ent** out, float** bsum_out, const float* const w[3], const int64_t ldw[3], const int K[3],
+                const float* const bias[3], int N) {
+        const int Kt = K[0] + K[1] + K[2];
+        *out = nullptr;
+        *bsum_out = nullptr;
+        Ent* we = lookup(wc, nw, w[0], N, Kt);
+        if (!we) {
+            we = make(true, w[0], N, Kt);
+            char* bp = we ? take(wbase, wcap, woff, align_up((size_t)N * 4, 256)) : nullptr;
+            if (!we || !bp) return VAG_OK;
+            int off = 0;
+            for (int i = 0; i < 3; ++i) {
+                VAG_TRY(tc_split(w[i], ldw[i], N, K[i], we->hi, we->lo, Kt, off, st));
+                off += K[i];
+            }
+            VAG_TRY(bias_sum3((float*)bp, bias[0], bias[1], bias[2], N, st));
+            // remember the bias vector right behind the entry (second cache slot keyed by the bias pointer)
+            if (nw < 32) wc[nw++] = Ent{(const void*)((uintptr_t)w[0] + 1), N, Kt, bp, nullptr, 0};
+        }
+        Ent* be = lookup(wc, nw, (const void*)((uintptr_t)w[0] + 1), N, Kt);
+        if (be) { *out = we; *bsum_out = (float*)be->hi; }
+        return VAG_OK;
+    }
+
     // summ / summ_tile_w: optional per-(row, column-tile) soft-max / arg-max summary written by the tensor-core
     // epilogue (see tc_gemm); *summ_tile_w stays 0 when the FP32 FFMA kernel ran and no summary exists.
     int linear(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, int rows,
@@ -80,8 +116,8 @@ struct GemmCtx {
         if (summ_tile_w) *summ_tile_w = 0;
         if (rows == 0 || N == 0) return VAG_OK;
         if (tc && shape_ok(rows, K, N) && ptr_ok(x, ldx) && ptr_ok(w, ldw) && tc_call_supported(y, ldy, flags)) {
-            Ent* we = lookup(wc, nw, w, N, K);
-            if (!we && (we = make(true, w, N, K))) VAG_TRY(tc_split(w, ldw, N, K, we->hi, we->lo, K, 0, st));
+            Ent* we = nullptr;
+            VAG_TRY(weight(&we, w, ldw, N, K));
             Ent* xe = we ? lookup(ac, na, x, rows, K) : nullptr;
             if (we && !xe && (xe = make(false, x, rows, K))) VAG_TRY(tc_split(x, ldx, rows, K, xe->hi, xe->lo, K, 0, st));
             if (we && xe)
@@ -97,28 +133,9 @@ struct GemmCtx {
         bool ok = tc && shape_ok(rows, Kt, N) && tc_call_supported(y, ldy, flags);
         for (int i = 0; i < 3; ++i) ok = ok && (K[i] % 8 == 0) && ptr_ok(x[i], ldx[i]) && ptr_ok(w[i], ldw[i]);
         if (ok) {
-            Ent* we = lookup(wc, nw, w[0], N, Kt);
+            Ent* we = nullptr;
             float* bsum = nullptr;
-            if (!we) {
-                we = make(true, w[0], N, Kt);
-                char* bp = we ? take(wbase, wcap, woff, align_up((size_t)N * 4, 256)) : nullptr;
-                if (we && bp) {
-                    int off = 0;
-                    for (int i = 0; i < 3; ++i) {
-                        VAG_TRY(tc_split(w[i], ldw[i], N, K[i], we->hi, we->lo, Kt, off, st));
-                        off += K[i];
-                    }
-                    VAG_TRY(bias_sum3((float*)bp, bias[0], bias[1], bias[2], N, st));
-                    // remember the bias vector right behind the entry (second cache slot keyed by the bias pointer)
-                    if (nw < 32) wc[nw++] = Ent{(const void*)((uintptr_t)w[0] + 1), N, Kt, bp, nullptr, 0};
-                } else {
-                    we = nullptr;
-                }
-            }
-            if (we) {
-                Ent* be = lookup(wc, nw, (const void*)((uintptr_t)w[0] + 1), N, Kt);
-                bsum = be ? (float*)be->hi : nullptr;
-            }
+            VAG_TRY(weight3(&we, &bsum, w, ldw, K, bias, N));
             Ent* xe = (we && bsum) ? make(false, x[0], rows, Kt) : nullptr;
             if (xe) {
                 int off = 0;

@@ -16,6 +16,7 @@
 //            finally signals the epilogue
 //   warps 2-5  epilogue: tcgen05.ld (32 lanes x 32 columns) → bias / accumulate / tanh → global stores
 #include "common.cuh"
+#include "split.cuh"
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
@@ -675,7 +676,8 @@ template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 linear_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                    const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
-                   const __grid_constant__ CUtensorMap map_y, const float* __restrict__ bias, int rows, int K, int N,
+                   const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_yh,
+                   const __grid_constant__ CUtensorMap map_yl, const float* __restrict__ bias, int rows, int K, int N,
                    int flags, float4* __restrict__ summ, long long* __restrict__ dbg) {
     constexpr bool F16 = MODE != 0;
     constexpr bool SPLIT = MODE != 2;
@@ -793,6 +795,7 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
         uint8_t* my_tiles = epi + ew * 8192;
         float* my_bias = bias_w + ew * 32;
         const bool do_tanh = flags & VAG_LIN_TANH;
+        const bool split_out = flags & VAG_LIN_SPLIT_OUT;   // the output leaves as tensor-core operand planes, not fp32
         constexpr float kL2e = 1.4426950408889634f;
         uint32_t it = 0, nst = 0;
         long long t_wt = 0, t_ld = 0, t_ws = 0, t_math = 0, t_stage = 0, t_tma = 0, t_begin = VAG_TCLK();
@@ -868,17 +871,41 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
                 __syncwarp();
                 t_ws += VAG_TCLK() - t0;
                 t0 = VAG_TCLK();
+                if (!split_out) {
 #pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) {
-                    float4 v = make_float4(x[4 * c4], x[4 * c4 + 1], x[4 * c4 + 2], x[4 * c4 + 3]);
-                    *reinterpret_cast<float4*>(my_tile + lane * 128 + ((c4 ^ (lane & 7)) << 4)) = v;
+                    for (int c4 = 0; c4 < 8; ++c4) {
+                        float4 v = make_float4(x[4 * c4], x[4 * c4 + 1], x[4 * c4 + 2], x[4 * c4 + 3]);
+                        *reinterpret_cast<float4*>(my_tile + lane * 128 + ((c4 ^ (lane & 7)) << 4)) = v;
+                    }
+                } else {
+                    // hi plane tile at +0, lo plane tile at +2048: 32 rows x 64 B, SWIZZLE_64B (chunk ^= (row >> 1) & 3)
+#pragma unroll
+                    for (int c8 = 0; c8 < 4; ++c8) {
+                        uint32_t hw[4], lw[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            uint16_t h0, l0, h1, l1;
+                            split_one(MODE, x[8 * c8 + 2 * u], h0, l0);
+                            split_one(MODE, x[8 * c8 + 2 * u + 1], h1, l1);
+                            hw[u] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                            lw[u] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                        }
+                        const int off = lane * 64 + ((c8 ^ ((lane >> 1) & 3)) << 4);
+                        *reinterpret_cast<uint4*>(my_tile + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                        if (SPLIT) *reinterpret_cast<uint4*>(my_tile + 2048 + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                    }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 t_stage += VAG_TCLK() - t0;
                 t0 = VAG_TCLK();
                 if (lane == 0) {
-                    tma_store_2d(&map_y, my_tile, n0 + c0, m0 + lg * 32);
+                    if (!split_out) {
+                        tma_store_2d(&map_y, my_tile, n0 + c0, m0 + lg * 32);
+                    } else {
+                        tma_store_2d(&map_yh, my_tile, n0 + c0, m0 + lg * 32);
+                        if (SPLIT) tma_store_2d(&map_yl, my_tile + 2048, n0 + c0, m0 + lg * 32);
+                    }
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
                 __syncwarp();
@@ -978,6 +1005,27 @@ static int make_out_map(CUtensorMap* m, float* y, int64_t rows, int64_t N, int64
     return VAG_OK;
 }
 
+// 16-bit operand plane [rows, N] (pitch ld elements) written by the split-output epilogue: box {32, 32}, SWIZZLE_64B
+static int make_plane_out_map(CUtensorMap* m, void* base, int64_t rows, int64_t N, int64_t ld, bool bf16) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled entry point not available");
+        return VAG_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {32u, 32u};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = fn(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (operand-plane output) failed with %d (rows=%lld N=%lld ld=%lld)", (int)r, (long long)rows, (long long)N, (long long)ld);
+        return VAG_ERR_CUDA;
+    }
+    return VAG_OK;
+}
+
 size_t linear_tc_scratch_bytes(int64_t rows, int64_t K, int64_t N) {
     return (size_t)(2 * rows * K + 2 * N * K) * sizeof(float) + 4 * 256;
 }
@@ -1045,6 +1093,38 @@ int tc_split(const float* x, int64_t ldx, int rows, int K, void* hi, void* lo, i
 // The tcgen05 contraction on pre-split operands: xh/xl [rows, K] pitch ldxs, wh/wl [N, K] pitch ldws (elements).
 // summ (optional): [rows, ceil(N / tile_w)] float4 (max, Σexp(x-max), best value, best column as int bits) per
 // (row, column tile); *summ_tile_w receives the tile width the chosen configuration uses.
+// Split-output flavour (fused decode step): y = act(x·Wᵀ + bias) leaves the kernel as operand planes `out` (no fp32
+// copy).  CTA-pair kernel only: rows > 128, 16-bit modes, out.ld % 8 == 0, 16-byte aligned planes.
+int tc_gemm_split_out(SplitDst out, const void* xh, const void* xl, int64_t ldxs, const void* wh, const void* wl, int64_t ldws,
+                      const float* bias, int rows, int K, int N, int flags, cudaStream_t st) {
+    const int mode = gemm_mode();
+    if (mode == 0 || rows <= 128 || !out.hi || (out.ld & 7) || (reinterpret_cast<uintptr_t>(out.hi) & 15) ||
+        (mode == 1 && (!out.lo || (reinterpret_cast<uintptr_t>(out.lo) & 15)))) {
+        set_error("tc_gemm_split_out: needs a 16-bit mode, rows > 128 and 16-byte aligned output planes");
+        return VAG_ERR_UNSUPPORTED;
+    }
+    CUtensorMap mxh, mxl, mwh, mwl, myh, myl;
+    VAG_TRY(make_map(&mxh, xh, rows, K, ldxs, 128, true, Q_ROWB));
+    VAG_TRY(make_map(&mxl, xl, rows, K, ldxs, 128, true, Q_ROWB));
+    VAG_TRY(make_map(&mwh, wh, N, K, ldws, 64, true, Q_ROWB));
+    VAG_TRY(make_map(&mwl, wl, N, K, ldws, 64, true, Q_ROWB));
+    VAG_TRY(make_plane_out_map(&myh, out.hi, rows, N, out.ld, mode == 2));
+    VAG_TRY(make_plane_out_map(&myl, mode == 2 ? out.hi : out.lo, rows, N, out.ld, mode == 2));
+    const int n_tiles = ceil_div(N, 128) * ceil_div(rows, 256);
+    const int max_pairs = num_sms() / 2;
+    const int grid = 2 * (n_tiles < max_pairs ? n_tiles : max_pairs);
+    static bool attr_set[3] = {false, false, false};
+    if (mode == 1) {
+        if (!attr_set[1]) { VAG_CUDA(cudaFuncSetAttribute(linear_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES)); attr_set[1] = true; }
+        linear_pair_kernel<1><<<grid, 320, Q_SMEM_BYTES, st>>>(mxh, mxl, mwh, mwl, myh, myh, myl, bias, rows, K, N, flags | VAG_LIN_SPLIT_OUT, nullptr, g_tc_dbg);
+    } else {
+        if (!attr_set[2]) { VAG_CUDA(cudaFuncSetAttribute(linear_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES)); attr_set[2] = true; }
+        linear_pair_kernel<2><<<grid, 320, Q_SMEM_BYTES, st>>>(mxh, mxl, mwh, mwl, myh, myh, myl, bias, rows, K, N, flags | VAG_LIN_SPLIT_OUT, nullptr, g_tc_dbg);
+    }
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
 int tc_gemm(float* y, int64_t ldy, const void* xh, const void* xl, int64_t ldxs, const void* wh, const void* wl, int64_t ldws,
             const float* bias, int rows, int K, int N, int flags, cudaStream_t st, float4* summ, int* summ_tile_w) {
     const bool f16 = use_f16_split();
@@ -1072,7 +1152,7 @@ int tc_gemm(float* y, int64_t ldy, const void* xh, const void* xl, int64_t ldxs,
             VAG_CUDA(cudaFuncSetAttribute(linear_pair_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES));    \
             attr_set[M] = true;                                                                                                 \
         }                                                                                                                       \
-        linear_pair_kernel<M><<<grid, 320, Q_SMEM_BYTES, st>>>(mxh, mxl, mwh, mwl, my, bias, rows, K, N, flags, summ, g_tc_dbg);          \
+        linear_pair_kernel<M><<<grid, 320, Q_SMEM_BYTES, st>>>(mxh, mxl, mwh, mwl, my, my, my, bias, rows, K, N, flags & ~VAG_LIN_SPLIT_OUT, summ, g_tc_dbg);          \
     } while (0)
         if (mode == 0) VAG_PAIR(0);
         else if (mode == 1) VAG_PAIR(1);
