@@ -65,6 +65,12 @@ int vag_linear_f32(float* y, int64_t ldy, const float* x, int64_t ldx, const flo
  * (3xTF32), which keeps FP32-level accuracy so that decoded tokens stay exact.  Needs rows >= 64, out_dim >= 64,
  * in_dim >= 32 and a multiple of 4, 16-byte aligned x / w (else VAG_ERR_UNSUPPORTED).  The composites below take
  * this path automatically for eligible shapes; VAG_GEMM=simt in the environment forces the FFMA kernel. */
+/* Vocabulary projection of the beam loop WITHOUT an output matrix (replaces NMT_Decoder.py:143 `out` + log_softmax + the
+ * topk of V11:300 for the tensor-core path): summ [ceil(out_dim / 32), rows] x 4 floats =
+ *   (best logit of the 32-column slice, sum of exp(logit - best), second-best logit, best column | second column << 16)
+ * in canonical order (value descending, column ascending; 0xFFFF = none).  Needs rows > 128 and a 16-bit gemm mode. */
+int vag_tc_gemm_top2_f32(float* summ, const void* x_hi, const void* x_lo, int64_t ldx, const void* w_hi, const void* w_lo,
+                         int64_t ldw, const float* bias, int rows, int in_dim, int out_dim, vag_stream_t stream);
 size_t vag_linear_tc_workspace_bytes(int rows, int in_dim, int out_dim);
 int vag_linear_tc_f32(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw,
                       const float* bias, int rows, int in_dim, int out_dim, int flags, void* workspace,

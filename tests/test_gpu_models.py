@@ -191,3 +191,27 @@ def test_error_behaviour():
     cpu_model = build_mm(cfg, 1)
     with pytest.raises(RuntimeError):            # no CPU path
         cpu_model.beamsearch_decode(src.flip(0), [4, 3], torch.rand(2, cfg["im_feats_size"]), beam_size=2, max_length=4)
+
+
+@pytest.mark.parametrize("env", [{}, {"VAG_SELECT_RECOMPUTE": "1"}, {"VAG_KEEP_LOGITS": "1"}])
+def test_fused_step_selection_variants_token_exact(env, monkeypatch, full_de):
+    """The fused beam loop selects from per-tile top-2 summaries without logits; VAG_SELECT_RECOMPUTE=1 forces the rare
+    'third candidate of a tile' path (tile recomputed from the operand planes) on every refill, VAG_KEEP_LOGITS=1 keeps
+    the logits + rescan selection.  All three must reproduce the reference's tokens (golden fixture, beams 5 and 12)
+    and, at a batch large enough for step 0 to run fused as well (B = 160 > 128), the CPU oracle's."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    from oracle import vag_oracle as O
+    from vag_nmt_b200 import synthetic
+    fix = full_de
+    cfg = fix["cfg"]
+    mm = build_mm(cfg, fix["seed"]).cuda().eval()
+    batch = synthetic.make_batch(fix["batch_size"], cfg["src_size"], cfg["tgt_size"], cfg["im_feats_size"], seed=fix["data_seed"])
+    for K in (5, 12):
+        got = mm.beamsearch_decode(batch.src, batch.src_lengths, batch.im, beam_size=K, max_length=fix["max_length"])
+        assert got == fix["ref_fp32"][f"decode_k{K}"], f"beam {K} differs under {env}"
+    big = synthetic.make_batch(160, cfg["src_size"], cfg["tgt_size"], cfg["im_feats_size"], seed=21)
+    got = mm.beamsearch_decode(big.src, big.src_lengths, big.im, beam_size=12, max_length=12)
+    with torch.no_grad():
+        want = O.multimodal_beamsearch_decode(cpu_params(mm), big.src, big.src_lengths, big.im, 12, 12)
+    assert got == want

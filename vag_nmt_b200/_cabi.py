@@ -84,6 +84,7 @@ SIGNATURES = {
     "vag_tc_set_debug": (I, [P]),
     "vag_tc_split_f32": (I, [P, I64, I, I, P, P, I64, P]),
     "vag_tc_gemm_f32": (I, [P, I64, P, P, I64, P, P, I64, P, I, I, I, I, P]),
+    "vag_tc_gemm_top2_f32": (I, [P, P, P, I64, P, P, I64, P, I, I, I, P]),
     "vag_linear_tc_workspace_bytes": (SZ, [I, I, I]),
     "vag_linear_tc_f32": (I, [P, I64, P, I64, P, I64, P, I, I, I, I, P, SZ, P]),
     "vag_decoder_init_workspace_bytes": (SZ, [I, I, I]),

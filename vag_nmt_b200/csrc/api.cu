@@ -130,6 +130,20 @@ extern "C" int vag_tc_gemm_f32(float* y, int64_t ldy, const void* x_hi, const vo
     return tc_gemm(y, ldy, x_hi, x_lo, ldx, w_hi, w_lo, ldw, bias, rows, in_dim, out_dim, flags, (cudaStream_t)stream, nullptr, nullptr);
 }
 
+namespace vag {
+int tc_gemm_top2(float4* summ, const void* xh, const void* xl, int64_t ldxs, const void* wh, const void* wl, int64_t ldws,
+                 const float* bias, int rows, int K, int N, cudaStream_t st);
+}
+extern "C" int vag_tc_gemm_top2_f32(float* summ, const void* x_hi, const void* x_lo, int64_t ldx, const void* w_hi,
+                                    const void* w_lo, int64_t ldw, const float* bias, int rows, int in_dim, int out_dim,
+                                    vag_stream_t stream) {
+    VAG_REQUIRE(summ && x_hi && x_lo && w_hi && w_lo, "vag_tc_gemm_top2_f32: null pointer");
+    VAG_REQUIRE(rows > 128 && in_dim >= 32 && in_dim % 8 == 0 && out_dim > 0 && out_dim < 65535 && ldx % 8 == 0 && ldw % 8 == 0,
+                "vag_tc_gemm_top2_f32: bad shape (rows > 128, in %% 8 == 0, out < 65535)");
+    VAG_REQUIRE(((uintptr_t)summ & 15) == 0, "vag_tc_gemm_top2_f32: summ must be 16-byte aligned");
+    return tc_gemm_top2(reinterpret_cast<float4*>(summ), x_hi, x_lo, ldx, w_hi, w_lo, ldw, bias, rows, in_dim, out_dim, (cudaStream_t)stream);
+}
+
 extern "C" size_t vag_linear_tc_workspace_bytes(int rows, int in_dim, int out_dim) {
     return linear_tc_scratch_bytes(rows, in_dim, out_dim);
 }

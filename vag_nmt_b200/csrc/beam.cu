@@ -6,6 +6,9 @@
 // canonical order (score descending, flat index k·V+v ascending on ties).  HBM bound: the logits are read once.
 #include "common.cuh"
 #include "split.cuh"
+#include <stdlib.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <math.h>
 
 namespace vag {
@@ -503,6 +506,200 @@ beam_select_summary_kernel(const float4* __restrict__ summ, int n_tiles, int til
     if (tid == 0 && fin_counter) atomicAdd(fin_counter, n_eos);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Selection WITHOUT logits (fused decode step): the vocabulary contraction leaves only, per (row, 128-column tile),
+// the best two elements in canonical order and Σexp relative to the best (tc_gemm_top2).  The K winners are popped as
+// in the kernel above; a tile that has to supply a THIRD candidate (rare: ≈ C(K,3)/tiles² of the step-0 rows) has its
+// 128 logits recomputed by one warp from the operand planes of the read-out and of the projection matrix with the
+// tensor core's own three-product arithmetic, excluding the columns already taken.  451 MB of logits per step (1000
+// sentences, beam 12) are neither written nor read.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float plane_f(int mode, uint16_t u) {
+    return mode == 2 ? __bfloat162float(__ushort_as_bfloat16(u)) : __half2float(__ushort_as_half(u));
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(256)
+beam_select_top2_kernel(const float4* __restrict__ summ /*[n_slices][n_rows]*/, int n_slices, int slice_w, int n_rows,
+                        const uint16_t* __restrict__ t_hi, const uint16_t* __restrict__ t_lo, int64_t ld_t,
+                        const uint16_t* __restrict__ w_hi, const uint16_t* __restrict__ w_lo, int64_t ld_w,
+                        const float* __restrict__ bias, int E, int mode, const int64_t* __restrict__ prev_tokens,
+                        float* __restrict__ nll, int64_t* __restrict__ tokens_out, int32_t* __restrict__ parents_out, int K,
+                        int V, int step, int avoid_double, const int* __restrict__ done, int* __restrict__ fin_counter,
+                        int force_recompute, long long* __restrict__ dbg) {
+    if (done && *done) return;
+    extern __shared__ float dyn[];
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int Kin = step == 0 ? 1 : K;
+    const int n_sl = Kin * n_slices;                         // entry idx = slice·Kin + k (k fastest: coalesced summary reads)
+    float* sl_v = dyn;                                       // best logit of the slice, later: score of its next candidate
+    int* sl_i = reinterpret_cast<int*>(dyn + n_sl);          // column bits, later: token of the next candidate (0x7fffffff: none)
+    float* sl_s = dyn + 2 * n_sl;                            // Σexp, later (as int): 0 = candidate is the slice's best, 1 = its second, 2 = recomputed
+    int* sl_d = reinterpret_cast<int*>(sl_s);
+    __shared__ float nll_s[KMAX], lse_s[KMAX];
+    __shared__ int cur_s[KMAX];
+    __shared__ float red_a[8];
+    __shared__ int red_i[8], red_t[8];
+    __shared__ int win_sl;
+    __shared__ int win_par[KMAX], win_tok[KMAX];
+    constexpr float kL2e = 1.4426950408889634f;
+    const int64_t row0 = (int64_t)b * Kin;
+
+    if (tid < Kin) {
+        nll_s[tid] = step == 0 ? 0.f : nll[(int64_t)b * K + tid];
+        cur_s[tid] = step == 0 ? -1 : (int)prev_tokens[(int64_t)b * K + tid];
+    }
+    for (int idx = tid; idx < n_sl; idx += 256) {
+        const int sl = idx / Kin, k = idx - sl * Kin;
+        const float4 e = summ[(int64_t)sl * n_rows + row0 + k];
+        sl_v[idx] = e.x;
+        sl_s[idx] = e.y;
+        sl_i[idx] = __float_as_int(e.w);
+    }
+    __syncthreads();
+    for (int k = wid; k < Kin; k += 8) {   // row log-sum-exps from the slice summaries (one warp per row)
+        float m = -INFINITY;
+        for (int sl = lane; sl < n_slices; sl += 32) m = fmaxf(m, sl_v[sl * Kin + k]);
+        m = warp_max(m);
+        float sum = 0.f;
+        for (int sl = lane; sl < n_slices; sl += 32) sum += sl_s[sl * Kin + k] * exp2f((sl_v[sl * Kin + k] - m) * kL2e);
+        sum = warp_sum(sum);
+        if (lane == 0) lse_s[k] = (step > 0 && cur_s[k] == kEOS) ? 0.f : m + logf(sum);
+    }
+    __syncthreads();
+    auto score_of = [&](int k, float logit) { const float lp = logit - lse_s[k]; return step == 0 ? lp : nll_s[k] + lp; };
+
+    for (int idx = tid; idx < n_sl; idx += 256) {
+        const int sl = idx / Kin, k = idx - sl * Kin;
+        float sc = -INFINITY;
+        int tok = 0x7fffffff, d = 2;
+        if (step > 0 && cur_s[k] == kEOS) {              // finished hypothesis: one candidate, <eos> at +0 (V11:291-294)
+            if (sl == 0) { sc = nll_s[k] + 0.f; tok = kEOS; }
+        } else {
+            const int bits = sl_i[idx], i1 = bits & 0xFFFF, i2 = (bits >> 16) & 0xFFFF;
+            const int skip = (avoid_double && step > 0) ? cur_s[k] : -1;   // the repeated token may not be chosen (V11:279-280)
+            if (i1 != 0xFFFF && i1 != skip) { sc = score_of(k, sl_v[idx]); tok = i1; d = 0; }
+            else if (i1 != 0xFFFF && i2 != 0xFFFF) {     // i1 == skip ⇒ i2 != skip: the slice starts at its second element
+                sc = score_of(k, summ[(int64_t)sl * n_rows + row0 + k].z); tok = i2; d = 1;
+            }
+        }
+        sl_v[idx] = sc;
+        sl_i[idx] = tok;
+        sl_d[idx] = d;
+    }
+    __syncthreads();
+
+    int n_eos = 0;
+    for (int round = 0; round < K; ++round) {
+        float bv = -INFINITY;
+        int bi = 0x7fffffff, bs = -1;                    // bi = flat index k·V + token
+        for (int idx = tid; idx < n_sl; idx += 256) {
+            const int tok = sl_i[idx];
+            if (tok != 0x7fffffff) {
+                const int flat = (idx % Kin) * V + tok;
+                if (cand_better(sl_v[idx], flat, bv, bi)) { bv = sl_v[idx]; bi = flat; bs = idx; }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            const int os = __shfl_xor_sync(0xffffffffu, bs, o);
+            if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; bs = os; }
+        }
+        if (lane == 0) { red_a[wid] = bv; red_i[wid] = bi; red_t[wid] = bs; }
+        __syncthreads();
+        if (tid == 0) {
+            float fv = red_a[0];
+            int fi = red_i[0], fs = red_t[0];
+            for (int w = 1; w < 8; ++w)
+                if (cand_better(red_a[w], red_i[w], fv, fi)) { fv = red_a[w]; fi = red_i[w]; fs = red_t[w]; }
+            const int par = fi / V, tok = fi - par * V;
+            win_sl = fs;
+            win_par[round] = par;
+            win_tok[round] = tok;
+            nll[(int64_t)b * K + round] = fv;
+            tokens_out[(int64_t)b * K + round] = tok;
+            parents_out[(int64_t)b * K + round] = par;
+            n_eos += (tok == kEOS);
+        }
+        __syncthreads();
+        if (round + 1 < K) {                             // next candidate of the winner's slice (every thread decides alike)
+            const int idx = win_sl, sl = idx / Kin, k = idx - sl * Kin;
+            const int cur = cur_s[k];
+            const int skip = (avoid_double && step > 0) ? cur : -1;
+            float nv = -INFINITY;
+            int ni = 0x7fffffff, nd = 2;
+            bool recompute = false;
+            if (!(step > 0 && cur == kEOS)) {
+                if (sl_d[idx] == 0 && force_recompute != 1) {
+                    const float4 e = summ[(int64_t)sl * n_rows + row0 + k];
+                    const int i2 = (__float_as_int(e.w) >> 16) & 0xFFFF;
+                    if (i2 == 0xFFFF) { /* single-column slice: exhausted */ }
+                    else if (i2 != skip) { nv = e.z; ni = i2; nd = 1; }
+                    else recompute = true;
+                } else {
+                    recompute = true;
+                }
+            }
+            if (dbg && tid == 0) { atomicAdd((unsigned long long*)dbg + 20, (unsigned long long)recompute); atomicAdd((unsigned long long*)dbg + 21, 1ull); }
+            if (recompute && force_recompute != 2) {
+                // block-uniform: the CTA recomputes the slice's logits from the operand planes with the tensor core's own
+                // three products (hi·hi + (lo·hi + hi·lo)·2^-11); warp = every 8th column, lane = 8 consecutive k
+                const uint16_t* th = t_hi + (row0 + k) * ld_t;
+                const uint16_t* tl = t_lo + (row0 + k) * ld_t;
+                const int c_lo = sl * slice_w, c_hi = min(V, c_lo + slice_w);
+                for (int c = c_lo + wid; c < c_hi; c += 8) {
+                    bool taken = c == skip;
+                    for (int w = 0; w <= round; ++w) taken |= (win_par[w] == k && win_tok[w] == c);
+                    if (taken) continue;   // warp-uniform
+                    const uint16_t* wh = w_hi + (int64_t)c * ld_w;
+                    const uint16_t* wl = w_lo + (int64_t)c * ld_w;
+                    float main_acc = 0.f, cross_acc = 0.f;
+                    for (int e0 = lane * 8; e0 < E; e0 += 256) {
+                        const uint4 a_h = *reinterpret_cast<const uint4*>(th + e0), b_h = *reinterpret_cast<const uint4*>(wh + e0);
+                        const uint32_t ah[4] = {a_h.x, a_h.y, a_h.z, a_h.w}, bh[4] = {b_h.x, b_h.y, b_h.z, b_h.w};
+                        uint32_t al[4] = {0u, 0u, 0u, 0u}, bl[4] = {0u, 0u, 0u, 0u};
+                        if (mode != 2) {
+                            const uint4 a_l = *reinterpret_cast<const uint4*>(tl + e0), b_l = *reinterpret_cast<const uint4*>(wl + e0);
+                            al[0] = a_l.x; al[1] = a_l.y; al[2] = a_l.z; al[3] = a_l.w;
+                            bl[0] = b_l.x; bl[1] = b_l.y; bl[2] = b_l.z; bl[3] = b_l.w;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int sh = (u & 1) * 16;
+                            const float xh = plane_f(mode, (uint16_t)(ah[u >> 1] >> sh)), yh = plane_f(mode, (uint16_t)(bh[u >> 1] >> sh));
+                            main_acc = fmaf(xh, yh, main_acc);
+                            if (mode != 2) {
+                                const float xl = plane_f(mode, (uint16_t)(al[u >> 1] >> sh)), yl = plane_f(mode, (uint16_t)(bl[u >> 1] >> sh));
+                                cross_acc = fmaf(xl, yh, cross_acc);
+                                cross_acc = fmaf(xh, yl, cross_acc);
+                            }
+                        }
+                    }
+                    main_acc = warp_sum(main_acc);
+                    cross_acc = warp_sum(cross_acc);
+                    const float x = (main_acc + cross_acc * (1.0f / 2048.0f)) + (bias ? bias[c] : 0.f);
+                    if (cand_better(x, c, nv, ni)) { nv = x; ni = c; }
+                }
+                if (lane == 0) { red_a[wid] = nv; red_i[wid] = ni; }
+                __syncthreads();
+                nv = red_a[0]; ni = red_i[0];
+                for (int w = 1; w < 8; ++w)
+                    if (cand_better(red_a[w], red_i[w], nv, ni)) { nv = red_a[w]; ni = red_i[w]; }
+            }
+            if (tid == 0) {
+                sl_i[idx] = ni;
+                sl_v[idx] = ni == 0x7fffffff ? -INFINITY : score_of(k, nv);
+                sl_d[idx] = nd;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && fin_counter) atomicAdd(fin_counter, n_eos);
+}
+
 // Row gather by parent + early-stop bookkeeping.
 //   h_next[b*K + k, :] = h_cur[b*Kin + parents[b,k], :]
 // Block (0,0) thread 0 also turns the per-step EOS counter into the `done` flag / steps_run the way the
@@ -695,6 +892,45 @@ int beam_select_summary(const float4* summ, int tile_w, const float* logits, int
     else if (K <= 12) VAG_SELS(12);
     else VAG_SELS(16);
 #undef VAG_SELS
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
+long long* tc_debug();
+// summ: [ceil(V / slice_w)][n_rows] (tc_gemm_top2), n_rows = B (step 0) or B·K
+int beam_select_top2(const float4* summ, int slice_w, SplitDst t, const uint16_t* w_hi, const uint16_t* w_lo, int64_t ld_w,
+                     const float* bias, int E, const int64_t* prev_tokens, float* nll, int64_t* tokens_out, int32_t* parents_out,
+                     int B, int K, int64_t V, int step, int avoid_double, const int* done, int* fin_counter, cudaStream_t st) {
+    if (K > kMaxBeam || (int64_t)K * V >= 0x7fffffff || V <= K + 1 || V >= 0xFFFF || (E % 8)) {
+        set_error("beam_select_top2: unsupported K=%d V=%lld E=%d", K, (long long)V, E);
+        return VAG_ERR_UNSUPPORTED;
+    }
+    const int n_slices = (int)((V + slice_w - 1) / slice_w);
+    const int Kin = step == 0 ? 1 : K;
+    const size_t smem = (size_t)Kin * n_slices * 12 + 16;
+    if (smem > 200 * 1024) {
+        set_error("beam_select_top2: K=%d V=%lld needs %zu B of shared memory", K, (long long)V, smem);
+        return VAG_ERR_UNSUPPORTED;
+    }
+    // VAG_SELECT_RECOMPUTE=1 (tests): never use a slice's stored runner-up, always recompute — exercises the rare path
+    const char* fe = getenv("VAG_SELECT_RECOMPUTE");
+    const int force = fe ? (fe[0] == '1' ? 1 : (fe[0] == '2' ? 2 : 0)) : 0;   // 2: timing experiments only (never recompute)
+#define VAG_SEL2(KM)                                                                                                          \
+    do {                                                                                                                      \
+        static size_t configured = 0;                                                                                         \
+        if (smem > 48 * 1024 && smem > configured) {                                                                          \
+            VAG_CUDA(cudaFuncSetAttribute(beam_select_top2_kernel<KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            configured = smem;                                                                                                \
+        }                                                                                                                     \
+        beam_select_top2_kernel<KM><<<B, 256, smem, st>>>(summ, n_slices, slice_w, B * Kin, t.hi, t.lo, t.ld, w_hi, w_lo, ld_w, bias, E, \
+                                                          t.mode, prev_tokens, nll, tokens_out, parents_out, K, (int)V, step,  \
+                                                          avoid_double, done, fin_counter, force, tc_debug());                 \
+    } while (0)
+    if (K <= 4) VAG_SEL2(4);
+    else if (K <= 8) VAG_SEL2(8);
+    else if (K <= 12) VAG_SEL2(12);
+    else VAG_SEL2(16);
+#undef VAG_SEL2
     VAG_LAUNCH_CHECK();
     return VAG_OK;
 }

@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "gemm_ctx.cuh"
 #include <algorithm>
+#include <stdlib.h>
 #include <vector>
 
 namespace vag {
@@ -304,6 +305,9 @@ int embed_split_rows(SplitDst dst, const uint16_t* t_hi, const uint16_t* t_lo, i
                      int64_t V, cudaStream_t st);
 int attention_mlp_split(SplitDst sd, const float* q, int64_t ld_q, const float* keys, const float* ctx, const float* v,
                         const float* mask, int rows, int rows_per_sent, int T, int C, cudaStream_t st);
+int beam_select_top2(const float4* summ, int tile_w, SplitDst t, const uint16_t* w_hi, const uint16_t* w_lo, int64_t ld_w,
+                     const float* bias, int E, const int64_t* prev_tokens, float* nll, int64_t* tokens_out, int32_t* parents_out,
+                     int B, int K, int64_t V, int step, int avoid_double, const int* done, int* fin_counter, cudaStream_t st);
 int beam_advance_fused(float* h_next, const float* h_cur, const int32_t* parents, const int64_t* tokens, int B, int K, int Kin,
                        int H, int step, int* done, int* fin_counter, int* steps_run, SplitDst h_sd, SplitDst e_sd,
                        const uint16_t* t_hi, const uint16_t* t_lo, int64_t ld_t, int E, int64_t V, cudaStream_t st);
@@ -386,6 +390,10 @@ static int decoder_step_fused(const FusedStep& f, const vag_decoder_weights* w, 
     VAG_TRY(gemm(ws.gh, 3 * H, f.h1, f.w_g2h, w->gru2_b_hh, H, 3 * H, nullptr, nullptr));
     VAG_TRY(gru_gates_split(h_out, H, ws.gi, 3 * H, ws.gh, 3 * H, ws.h1, H, rows, H, f.cat, st));
     VAG_TRY(tc_gemm_split_out(f.t, f.cat.hi, f.cat.lo, Kt, f.w_ro->hi, f.w_ro->lo, f.w_ro->ld, f.b_ro, rows, Kt, E, VAG_LIN_TANH, st));  // :137
+    if (!logits) {   // beam loop: only the top-2 / Σexp summaries of every 128-column tile leave the projection
+        if (summ_tile_w) *summ_tile_w = 128;
+        return tc_gemm_top2(summ, f.t.hi, f.t.lo, f.t.ld, f.w_out->hi, f.w_out->lo, f.w_out->ld, w->out_b, rows, E, (int)V, st);
+    }
     return gemm(logits, ld_logits, f.t, f.w_out, w->out_b, E, (int)V, summ, summ_tile_w);                     // :143
 }
 }  // namespace vag
@@ -434,7 +442,7 @@ static void beam_layout(A& a, int B, int K, int L, int E, int H, int C, int64_t 
     step_layout(a, N, E, H, C, V, &sw);
     float* logits = (float*)a.template take<float>((size_t)N * ((V + 3) / 4 * 4));  // rows padded to 16 B
     float* lse = (float*)a.template take<float>((size_t)N);
-    float4* summ = (float4*)a.template take<float4>((size_t)N * ((V + 127) / 128));
+    float4* summ = (float4*)a.template take<float4>((size_t)N * ((V + 31) / 32));   // per 32-column slice (top-2 kernel); the per-128 summaries need a quarter
     float* h_a = (float*)a.template take<float>((size_t)N * H);
     float* h_b = (float*)a.template take<float>((size_t)N * H);
     float* nll = (float*)a.template take<float>((size_t)N);
@@ -496,12 +504,20 @@ extern "C" int vag_beam_decode_f32(const vag_decoder_weights* w, const float* h0
                 VAG_TRY(embed_split_rows(fused.cat_e(H), (const uint16_t*)fused.w_emb->hi, (const uint16_t*)fused.w_emb->lo,
                                          fused.w_emb->ld, E, ws.sos, B, V, st));
             }
-            VAG_TRY(decoder_step_fused(fused, w, ws.step, h_prev, keys, ctx, mask, rows, rps, T, ws.h_b, ws.logits, ldl, st,
-                                       V >= 512 ? ws.summ : nullptr, &tile_w));
+            const bool no_logits = V >= 512 && V < 0xFFFF && !getenv("VAG_KEEP_LOGITS");
+            VAG_TRY(decoder_step_fused(fused, w, ws.step, h_prev, keys, ctx, mask, rows, rps, T, ws.h_b, no_logits ? nullptr : ws.logits,
+                                       ldl, st, V >= 512 ? ws.summ : nullptr, &tile_w));
+            if (no_logits) {
+                VAG_TRY(beam_select_top2(ws.summ, 32, fused.t, (const uint16_t*)fused.w_out->hi, (const uint16_t*)fused.w_out->lo,
+                                         fused.w_out->ld, w->out_b, E, di == 0 ? nullptr : tokens, ws.nll, ws.tok_hist + (size_t)di * N,
+                                         ws.par_hist + (size_t)di * N, B, K, V, di, avoid_double, done, fin + di, st));
+                tile_w = -1;   // selection done
+            }
         } else
         VAG_TRY(decoder_step_core(gemm, w, ws.step, tokens, h_prev, keys, ctx, mask, rows, rps, T, ws.h_b, ws.logits, ldl, nullptr, st,
                                   V >= 512 ? ws.summ : nullptr, &tile_w));
-        if (tile_w > 0) {
+        if (tile_w < 0) {
+        } else if (tile_w > 0) {
             VAG_TRY(beam_select_summary(ws.summ, tile_w, ws.logits, ldl, di == 0 ? nullptr : tokens, ws.nll,
                                         ws.tok_hist + (size_t)di * N, ws.par_hist + (size_t)di * N, B, K, V, di, avoid_double, done,
                                         fin + di, st));

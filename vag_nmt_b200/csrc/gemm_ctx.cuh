@@ -19,6 +19,8 @@ int tc_gemm(float* y, int64_t ldy, const void* xh, const void* xl, int64_t ldxs,
             const float* bias, int rows, int K, int N, int flags, cudaStream_t st, float4* summ, int* summ_tile_w);
 bool tc_enabled();
 int gemm_mode();
+int tc_gemm_top2(float4* summ, const void* xh, const void* xl, int64_t ldxs, const void* wh, const void* wl, int64_t ldws,
+                 const float* bias, int rows, int K, int N, cudaStream_t st);
 int tc_gemm_split_out(SplitDst out, const void* xh, const void* xl, int64_t ldxs, const void* wh, const void* wl, int64_t ldws,
                       const float* bias, int rows, int K, int N, int flags, cudaStream_t st);
 bool tc_call_supported(const float* y, int64_t ldy, int flags);

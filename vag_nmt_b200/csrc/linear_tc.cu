@@ -666,6 +666,15 @@ __device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t adesc, uint6
         : "r"(addr)                                                                                                             \
         : "memory")
 
+#define VAG_TMEM_LD16(v, addr)                                                                                                  \
+    asm volatile(                                                                                                               \
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                                               \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"                                        \
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),           \
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])                              \
+        : "r"(addr)                                                                                                             \
+        : "memory")
+
 // Role timers (tools/scratch/roles.py): compiled in with -DVAG_TC_TIMERS, otherwise every VAG_TCLK() folds to zero.
 #ifdef VAG_TC_TIMERS
 #define VAG_TCLK() clock64()
@@ -863,9 +872,9 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
                 }
                 // registers → 128-byte-swizzled staging tile (row = lane, 16-byte chunk index XOR row%8) → TMA store;
                 // two tiles alternate, so only the store issued TWO chunks ago has to have finished reading
+                t_math += VAG_TCLK() - t0;
                 uint8_t* my_tile = my_tiles + (nst & 1) * 4096;
                 ++nst;
-                t_math += VAG_TCLK() - t0;
                 t0 = VAG_TCLK();
                 asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                 __syncwarp();
@@ -939,6 +948,242 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
     }
     tcgen05_fence_before();
     cluster_sync_all();   // the peer's shared memory and the leader's barriers stay alive until both CTAs are done
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------ vocabulary top-2 kernel
+// The vocabulary projection of the beam loop.  Same CTA-pair main loop, but NO output matrix: each of SIXTEEN epilogue
+// warps owns one 32-column chunk of the CTA's 128 x 128 accumulator and reduces it, per row, to
+//     (best logit, Σ exp(logit − best), second-best logit, best column | second column << 16)       [canonical order]
+// written to summ[slice][row] (slice = 32-column chunk of the vocabulary, row fastest ⇒ coalesced 512-byte stores).
+// beam_select_top2_kernel picks the K winners from these 294 x 16 B per row instead of 9391 x 4 B of logits.
+// Why 16 warps: with K = 256 the three-product main loop lasts only ≈ 3 k cycles per tile, and the reduction (≈ 17
+// instructions per element, serial insertion chains) is latency-bound with two warps per scheduler; four per scheduler
+// hide it.  No staging tiles ⇒ room for a fourth pipeline stage.
+constexpr int V_STAGES = 4;
+constexpr int V_SMEM_BYTES = V_STAGES * Q_STAGE_BYTES + 2048 /*bias per warp*/ + 256 /*barriers*/ + 1024;
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(576, 1)
+vocab_top2_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
+                       const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
+                       const float* __restrict__ bias, int rows, int K, int N, float4* __restrict__ summ,
+                       long long* __restrict__ dbg) {
+    constexpr bool F16 = MODE != 0;
+    constexpr bool SPLIT = MODE != 2;
+    constexpr int BMP = 256, BM = 128, BN = 128, ELT = F16 ? 2 : 4, BK = Q_ROWB / ELT, UK = 32 / ELT;
+    constexpr uint32_t FMT = MODE == 0 ? 2u : (MODE == 1 ? 0u : 1u);
+    constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BMP >> 4) << 24);
+    constexpr uint32_t STAGE_TX = SPLIT ? Q_STAGE_BYTES : Q_STAGE_BYTES / 2;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float* bias_w = reinterpret_cast<float*>(smem + V_STAGES * Q_STAGE_BYTES);   // [16 warps][32]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + V_STAGES * Q_STAGE_BYTES + 2048);
+    uint64_t* empty_bar = full_bar + V_STAGES;
+    uint64_t* tfull_bar = empty_bar + V_STAGES;   // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;         // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int tiles_n = (N + BN - 1) / BN, tiles_m = (rows + BMP - 1) / BMP;
+    const int n_tiles = tiles_n * tiles_m;
+    const int n_kb = (K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_xh) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_xl) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wh) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wl) : "memory");
+        for (int s = 0; s < V_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], rank == 0 ? 17 : 16); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t g = 0;
+            long long t_wait = 0, t_begin = VAG_TCLK();
+            for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+                const int m0 = (tile / tiles_n) * BMP + (int)rank * BM, n0 = (tile % tiles_n) * BN + (int)rank * (BN / 2);
+                for (int kb = 0; kb < n_kb; ++kb, ++g) {
+                    const int s = g % V_STAGES;
+                    const long long t0 = VAG_TCLK();
+                    mbar_wait(&empty_bar[s], ((g / V_STAGES) & 1) ^ 1);
+                    t_wait += VAG_TCLK() - t0;
+                    uint8_t* st = smem + s * Q_STAGE_BYTES;
+                    if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * STAGE_TX);
+                    const uint32_t fb = mapa_u32(smem_u32(&full_bar[s]), 0);
+                    const int k0 = kb * BK;
+                    tma_load_2d_pair(st, &map_xh, fb, k0, m0);
+                    if (SPLIT) tma_load_2d_pair(st + Q_A_BYTES, &map_xl, fb, k0, m0);
+                    tma_load_2d_pair(st + 2 * Q_A_BYTES, &map_wh, fb, k0, n0);
+                    if (SPLIT) tma_load_2d_pair(st + 2 * Q_A_BYTES + Q_B_BYTES, &map_wl, fb, k0, n0);
+                }
+            }
+            if (dbg && pair == 0) { dbg[rank * 16 + 0] = VAG_TCLK() - t_begin; dbg[rank * 16 + 1] = t_wait; dbg[rank * 16 + 2] = g; }
+        }
+    } else if (warp == 1) {
+        if (rank == 0 && lane == 0) {
+            uint32_t g = 0, it = 0;
+            long long t_we = 0, t_wf = 0, t_begin = VAG_TCLK();
+            for (int tile = pair; tile < n_tiles; tile += n_pairs, ++it) {
+                const uint32_t a = it & 1;
+                long long t0 = VAG_TCLK();
+                mbar_wait(&tempty_bar[a], ((it >> 1) & 1) ^ 1);
+                t_we += VAG_TCLK() - t0;
+                tcgen05_fence_after();
+                const uint32_t d_main = tmem_base + a * 256, d_cross = d_main + 128;
+                for (int kb = 0; kb < n_kb; ++kb, ++g) {
+                    const int s = g % V_STAGES;
+                    t0 = VAG_TCLK();
+                    mbar_wait(&full_bar[s], (g / V_STAGES) & 1);
+                    t_wf += VAG_TCLK() - t0;
+                    tcgen05_fence_after();
+                    const uint32_t st = smem_u32(smem + s * Q_STAGE_BYTES);
+                    const uint64_t d_ah = make_smem_desc<Q_ROWB>(st), d_al = make_smem_desc<Q_ROWB>(st + Q_A_BYTES);
+                    const uint64_t d_bh = make_smem_desc<Q_ROWB>(st + 2 * Q_A_BYTES), d_bl = make_smem_desc<Q_ROWB>(st + 2 * Q_A_BYTES + Q_B_BYTES);
+#pragma unroll
+                    for (int j = 0; j < BK / UK; ++j) {
+                        const uint64_t adv = (uint64_t)((j * 32) >> 4);
+                        if (SPLIT) {
+                            umma_pair<F16>(d_cross, d_al + adv, d_bh + adv, IDESC, (kb | j) != 0);
+                            umma_pair<F16>(d_cross, d_ah + adv, d_bl + adv, IDESC, 1);
+                        }
+                        umma_pair<F16>(d_main, d_ah + adv, d_bh + adv, IDESC, (kb | j) != 0);
+                    }
+                    tcgen05_commit_pair(&empty_bar[s]);
+                }
+                tcgen05_commit_pair(&tfull_bar[a]);
+            }
+            if (dbg && pair == 0) { dbg[4] = VAG_TCLK() - t_begin; dbg[5] = t_we; dbg[6] = t_wf; dbg[7] = it; }
+        } else if (rank == 1 && lane == 0) {
+            uint32_t it = 0;   // forward "my sixteen epilogue warps have drained buffer a" to the leader
+            for (int tile = pair; tile < n_tiles; tile += n_pairs, ++it) {
+                const uint32_t a = it & 1;
+                mbar_wait(&tempty_bar[a], (it >> 1) & 1);
+                mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[a]), 0));
+            }
+        }
+    } else {
+        // ---- epilogue warps 2..17: TMEM lane group lg = warp % 4, column quarter cq: ONE 32-column chunk per tile
+        const int ew = warp - 2, lg = warp & 3, cq = ew >> 2;
+        float* my_bias = bias_w + ew * 32;
+        constexpr float kL2e = 1.4426950408889634f;
+        const int n_slices = tiles_n * 4;
+        uint32_t it = 0;
+        long long t_wt = 0, t_ld = 0, t_math = 0, t_begin = VAG_TCLK();
+        for (int tile = pair; tile < n_tiles; tile += n_pairs, ++it) {
+            const int tn = tile % tiles_n;
+            const int m0 = (tile / tiles_n) * BMP + (int)rank * BM, n0 = tn * BN, c0 = cq * 32;
+            const uint32_t a = it & 1;
+            long long t0 = VAG_TCLK();
+            mbar_wait(&tfull_bar[a], (it >> 1) & 1);
+            t_wt += VAG_TCLK() - t0;
+            tcgen05_fence_after();
+            const int n_valid = min(32, N - (n0 + c0));   // ≤ 0: the chunk lies outside the matrix (warp-uniform)
+            float x[32];
+            t0 = VAG_TCLK();
+            if (n_valid > 0) {
+                __syncwarp();
+                my_bias[lane] = (bias && lane < n_valid) ? bias[n0 + c0 + lane] : 0.f;
+                __syncwarp();
+                // two 16-column halves keep the live registers at x[32] + 2 x 16 (the kernel runs 18 warps per SM)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t r[16], q[16];
+                    const uint32_t taddr = tmem_base + a * 256 + ((uint32_t)(lg * 32) << 16) + (uint32_t)(c0 + 16 * h);
+                    if (SPLIT) VAG_TMEM_LD16(q, taddr + 128u);
+                    VAG_TMEM_LD16(r, taddr);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(my_bias + 16 * h + 4 * j4);
+                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int j = 4 * j4 + u;
+                            const float cross = !SPLIT ? 0.f : (F16 ? __uint_as_float(q[j]) * (1.0f / 2048.0f) : __uint_as_float(q[j]));
+                            x[16 * h + j] = (__uint_as_float(r[j]) + cross) + bb[u];
+                        }
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            if (lane == 0) mbar_arrive(&tempty_bar[a]);   // this warp's share of the accumulator is in registers
+            __syncwarp();
+            t_ld += VAG_TCLK() - t0;
+            t0 = VAG_TCLK();
+            float4 out = make_float4(-INFINITY, 0.f, -INFINITY, __int_as_float((int)0xFFFFFFFFu));
+            if (n_valid > 0) {
+                if (n_valid < 32) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] = j < n_valid ? x[j] : -INFINITY;
+                }
+                // best two of the chunk: four independent insertion chains (j mod 4) merged at the end; compares are strict,
+                // so inside a chain the lower column wins ties; the merges order equal values by column explicitly
+                float c1[4], c2[4];
+                int k1[4], k2[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { c1[u] = -INFINITY; c2[u] = -INFINITY; k1[u] = 0xFFFF; k2[u] = 0xFFFF; }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int u = j & 3;
+                    const float xv = x[j];
+                    const bool g1 = xv > c1[u], g2 = xv > c2[u];
+                    c2[u] = g1 ? c1[u] : (g2 ? xv : c2[u]);
+                    k2[u] = g1 ? k1[u] : (g2 ? j : k2[u]);
+                    c1[u] = g1 ? xv : c1[u];
+                    k1[u] = g1 ? j : k1[u];
+                }
+                auto better = [](float av, int ai, float bv, int bi) { return av > bv || (av == bv && ai < bi); };
+                auto merge2 = [&](float& p1, int& i1, float& p2, int& i2, float q1, int j1_, float q2, int j2_) {
+                    const bool qf = better(q1, j1_, p1, i1);
+                    const float r1 = qf ? q1 : p1; const int ri1 = qf ? j1_ : i1;
+                    const float s1 = qf ? p1 : p2; const int si1 = qf ? i1 : i2;     // runner-up candidates: the loser's head ...
+                    const float s2 = qf ? q2 : q1; const int si2 = qf ? j2_ : j1_;   // ... and the winner's next
+                    const bool sf = better(s2, si2, s1, si1);
+                    p1 = r1; i1 = ri1;
+                    p2 = sf ? s2 : s1; i2 = sf ? si2 : si1;
+                };
+                merge2(c1[0], k1[0], c2[0], k2[0], c1[1], k1[1], c2[1], k2[1]);
+                merge2(c1[2], k1[2], c2[2], k2[2], c1[3], k1[3], c2[3], k2[3]);
+                merge2(c1[0], k1[0], c2[0], k2[0], c1[2], k1[2], c2[2], k2[2]);
+                const float m2 = c1[0] * kL2e;
+                float ps[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float ev;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ev) : "f"(fmaf(x[j], kL2e, -m2)));   // exp(-inf) = 0 for padded columns
+                    ps[j & 3] += ev;
+                }
+                const int j1 = n0 + c0 + k1[0], j2 = k2[0] == 0xFFFF ? 0xFFFF : n0 + c0 + k2[0];
+                out = make_float4(c1[0], (ps[0] + ps[1]) + (ps[2] + ps[3]), c2[0], __int_as_float(j1 | (j2 << 16)));
+            }
+            const int row = m0 + lg * 32 + lane;
+            if (row < rows && n_valid > 0) summ[(int64_t)(tn * 4 + cq) * rows + row] = out;   // slices past ceil(N / 32) do not exist
+            t_math += VAG_TCLK() - t0;
+        }
+        (void)n_slices;
+        if (dbg && pair == 0 && ew == 0 && lane == 0) {
+            dbg[rank * 16 + 8] = VAG_TCLK() - t_begin; dbg[rank * 16 + 9] = t_wt; dbg[rank * 16 + 10] = t_ld; dbg[rank * 16 + 12] = t_math;
+        }
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();
     if (warp == 1) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -1056,6 +1301,7 @@ static int launch_tc(const CUtensorMap& xh, const CUtensorMap& xl, const CUtenso
 static thread_local int g_mode_override = -1;
 static long long* g_tc_dbg = nullptr;   // optional device buffer [32] for the pair kernel's role timers (tools only)
 void set_tc_debug(long long* p) { g_tc_dbg = p; }
+long long* tc_debug() { return g_tc_dbg; }
 void set_gemm_mode(int m) { g_mode_override = m; }
 int gemm_mode() {
     if (g_mode_override >= 0) return g_mode_override;
@@ -1120,6 +1366,36 @@ int tc_gemm_split_out(SplitDst out, const void* xh, const void* xl, int64_t ldxs
     } else {
         if (!attr_set[2]) { VAG_CUDA(cudaFuncSetAttribute(linear_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES)); attr_set[2] = true; }
         linear_pair_kernel<2><<<grid, 320, Q_SMEM_BYTES, st>>>(mxh, mxl, mwh, mwl, myh, myh, myl, bias, rows, K, N, flags | VAG_LIN_SPLIT_OUT, nullptr, g_tc_dbg);
+    }
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
+// Summary-only vocabulary projection (fused decode step): NO output matrix.  summ [ceil(N / 32), rows] float4 =
+// (best value, Σexp(x − best), second-best value, best column | second column << 16 — 0xFFFF: none) per (32-column slice,
+// row), canonical order (value descending, column ascending).  CTA-pair kernel: rows > 128, 16-bit modes, N < 65535.
+int tc_gemm_top2(float4* summ, const void* xh, const void* xl, int64_t ldxs, const void* wh, const void* wl, int64_t ldws,
+                 const float* bias, int rows, int K, int N, cudaStream_t st) {
+    const int mode = gemm_mode();
+    if (mode == 0 || rows <= 128 || !summ || N >= 0xFFFF) {
+        set_error("tc_gemm_top2: needs a 16-bit mode, rows > 128 and fewer than 65535 columns");
+        return VAG_ERR_UNSUPPORTED;
+    }
+    CUtensorMap mxh, mxl, mwh, mwl;
+    VAG_TRY(make_map(&mxh, xh, rows, K, ldxs, 128, true, Q_ROWB));
+    VAG_TRY(make_map(&mxl, xl, rows, K, ldxs, 128, true, Q_ROWB));
+    VAG_TRY(make_map(&mwh, wh, N, K, ldws, 64, true, Q_ROWB));
+    VAG_TRY(make_map(&mwl, wl, N, K, ldws, 64, true, Q_ROWB));
+    const int n_tiles = ceil_div(N, 128) * ceil_div(rows, 256);
+    const int max_pairs = num_sms() / 2;
+    const int grid = 2 * (n_tiles < max_pairs ? n_tiles : max_pairs);
+    static bool attr_set[3] = {false, false, false};
+    if (mode == 1) {
+        if (!attr_set[1]) { VAG_CUDA(cudaFuncSetAttribute(vocab_top2_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, V_SMEM_BYTES)); attr_set[1] = true; }
+        vocab_top2_pair_kernel<1><<<grid, 576, V_SMEM_BYTES, st>>>(mxh, mxl, mwh, mwl, bias, rows, K, N, summ, g_tc_dbg);
+    } else {
+        if (!attr_set[2]) { VAG_CUDA(cudaFuncSetAttribute(vocab_top2_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, V_SMEM_BYTES)); attr_set[2] = true; }
+        vocab_top2_pair_kernel<2><<<grid, 576, V_SMEM_BYTES, st>>>(mxh, mxl, mwh, mwl, bias, rows, K, N, summ, g_tc_dbg);
     }
     VAG_LAUNCH_CHECK();
     return VAG_OK;

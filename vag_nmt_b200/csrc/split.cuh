@@ -11,6 +11,8 @@ namespace vag {
 
 // internal epilogue flag (never part of the C ABI): write the output as tensor-core operand planes instead of fp32
 constexpr int VAG_LIN_SPLIT_OUT = 0x100;
+// internal: no output matrix, only the per-(row, tile) top-2 / Σexp summaries (vocabulary projection of the beam loop)
+constexpr int VAG_LIN_TOP2 = 0x200;
 
 struct SplitDst {
     uint16_t* hi = nullptr;   // nullptr: disabled

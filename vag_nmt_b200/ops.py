@@ -113,6 +113,17 @@ def tc_gemm(xs, ws, rows: int, in_dim: int, out_dim: int, bias: Optional[torch.T
     return out
 
 
+def tc_gemm_top2(xs, ws, rows: int, in_dim: int, out_dim: int, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Summary-only vocabulary projection → [ceil(out_dim/32), rows, 4] (best, Σexp, second, columns as int bits)."""
+    lib = _cabi.lib()
+    dev = xs[0].device
+    summ = torch.empty((out_dim + 31) // 32, rows, 4, dtype=torch.float32, device=dev)
+    with on_device(dev):
+        check(lib.vag_tc_gemm_top2_f32(summ.data_ptr(), xs[0].data_ptr(), xs[1].data_ptr(), in_dim, ws[0].data_ptr(), ws[1].data_ptr(),
+                                       in_dim, ptr(bias), rows, in_dim, out_dim, stream_ptr()))
+    return summ
+
+
 def embed_rows(table: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
     _chk_f32(table)
     lib = _cabi.lib()
