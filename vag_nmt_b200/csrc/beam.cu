@@ -518,8 +518,20 @@ __device__ __forceinline__ float plane_f(int mode, uint16_t u) {
     return mode == 2 ? __bfloat162float(__ushort_as_bfloat16(u)) : __half2float(__ushort_as_half(u));
 }
 
+constexpr int kSel2Threads = 128;   // 4 warps per sentence; 28 KB of entries ⇒ 7 CTAs per SM (1000 sentences in one wave)
+
+// Candidate of one slice held in registers by the thread that owns the slice's entry.
+struct SelCand {
+    float sc;      // score (V11:297) of the slice's next candidate
+    int flat;      // k·V + token  (0x7fffffff: empty list slot)
+    int idx;       // entry index = slice·Kin + k
+    int depth;     // 0: the slice's best, 1: its second, 2: recomputed
+    float sc2;     // depth 0 only: score of the slice's second element ...
+    int tok2;      // ... and its column (0xFFFF: the slice has no second; -2: not loaded, read the summary again)
+};
+
 template <int KMAX>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kSel2Threads)
 beam_select_top2_kernel(const float4* __restrict__ summ /*[n_slices][n_rows]*/, int n_slices, int slice_w, int n_rows,
                         const uint16_t* __restrict__ t_hi, const uint16_t* __restrict__ t_lo, int64_t ld_t,
                         const uint16_t* __restrict__ w_hi, const uint16_t* __restrict__ w_lo, int64_t ld_w,
@@ -530,19 +542,28 @@ beam_select_top2_kernel(const float4* __restrict__ summ /*[n_slices][n_rows]*/, 
     if (done && *done) return;
     extern __shared__ float dyn[];
     const int b = blockIdx.x;
+    constexpr int NT = kSel2Threads, NW = NT / 32;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int Kin = step == 0 ? 1 : K;
-    const int n_sl = Kin * n_slices;                         // entry idx = slice·Kin + k (k fastest: coalesced summary reads)
-    float* sl_v = dyn;                                       // best logit of the slice, later: score of its next candidate
-    int* sl_i = reinterpret_cast<int*>(dyn + n_sl);          // column bits, later: token of the next candidate (0x7fffffff: none)
-    float* sl_s = dyn + 2 * n_sl;                            // Σexp, later (as int): 0 = candidate is the slice's best, 1 = its second, 2 = recomputed
-    int* sl_d = reinterpret_cast<int*>(sl_s);
+    const int n_sl = Kin * n_slices;                     // entry idx = slice·Kin + k (k fastest: coalesced summary reads)
+    // Thread t works for ONE row: k = t mod Kin, as worker j = t / Kin of the row's J = NT / Kin workers (slices j, j+J, …;
+    // threads ≥ J·Kin idle).  One pass over the summaries then yields, in registers, the row's soft-max partials AND the
+    // thread's three best candidates (ordering inside a row does not depend on the row's log-sum-exp).
+    const int J = NT / Kin, my_k = tid % Kin, my_j = tid / Kin;
+    const bool worker = my_j < J;
+    // 8 bytes per entry, only read again when a thread's list runs empty: (raw logit of the entry's next candidate — or its
+    // SCORE once it has been advanced, flagged by bit 20 —, token | depth << 16), 0x7fffffff = exhausted
+    float* sl_v = dyn;
+    int* sl_i = reinterpret_cast<int*>(dyn + n_sl);
     __shared__ float nll_s[KMAX], lse_s[KMAX];
     __shared__ int cur_s[KMAX];
-    __shared__ float red_a[8];
-    __shared__ int red_i[8], red_t[8];
+    __shared__ float part_m[NT], part_s[NT];
+    __shared__ float red_a[NW];
+    __shared__ int red_i[NW], red_t[NW];
     __shared__ int win_sl;
     __shared__ int win_par[KMAX], win_tok[KMAX];
+    __shared__ float win_v[KMAX];
+    __shared__ int req_flag, req_idx;                    // pending block-wide recomputation of one slice
     constexpr float kL2e = 1.4426950408889634f;
     const int64_t row0 = (int64_t)b * Kin;
 
@@ -550,57 +571,123 @@ beam_select_top2_kernel(const float4* __restrict__ summ /*[n_slices][n_rows]*/, 
         nll_s[tid] = step == 0 ? 0.f : nll[(int64_t)b * K + tid];
         cur_s[tid] = step == 0 ? -1 : (int)prev_tokens[(int64_t)b * K + tid];
     }
-    for (int idx = tid; idx < n_sl; idx += 256) {
-        const int sl = idx / Kin, k = idx - sl * Kin;
-        const float4 e = summ[(int64_t)sl * n_rows + row0 + k];
-        sl_v[idx] = e.x;
-        sl_s[idx] = e.y;
-        sl_i[idx] = __float_as_int(e.w);
-    }
+    if (tid == 0) req_flag = 0;
     __syncthreads();
-    for (int k = wid; k < Kin; k += 8) {   // row log-sum-exps from the slice summaries (one warp per row)
+
+    // ---- the thread's sorted list of its three best entries (sc = RAW logit until the log-sum-exps are known)
+    SelCand L0, L1, L2;
+    L0.flat = L1.flat = L2.flat = 0x7fffffff;
+    L0.sc = L1.sc = L2.sc = -INFINITY;
+    int n_l = 0;
+    auto insert = [&](const SelCand& c) {   // keeps the best three; the caller guarantees c may legally enter (see apply_next)
+        if (!cand_better(c.sc, c.flat, L2.sc, L2.flat)) return;
+        if (cand_better(c.sc, c.flat, L0.sc, L0.flat)) { L2 = L1; L1 = L0; L0 = c; }
+        else if (cand_better(c.sc, c.flat, L1.sc, L1.flat)) { L2 = L1; L1 = c; }
+        else { L2 = c; }
+        n_l = min(n_l + 1, 3);
+    };
+    const int my_cur = cur_s[my_k];
+    const bool row_done = step > 0 && my_cur == kEOS;
+    const int my_skip = (avoid_double && step > 0) ? my_cur : -1;   // the repeated token may not be chosen (V11:279-280)
+    float pm = -INFINITY, ps = 0.f;
+    if (worker) {
+        if (row_done) {                                  // finished hypothesis: one candidate, <eos> at +0 (V11:291-294)
+            for (int sl = my_j; sl < n_slices; sl += J) sl_i[sl * Kin + my_k] = 0x7fffffff;
+            if (my_j == 0) {
+                SelCand c;
+                c.sc = 0.f; c.flat = my_k * V + kEOS; c.idx = my_k; c.depth = 2; c.sc2 = -INFINITY; c.tok2 = 0xFFFF;
+                sl_v[my_k] = 0.f;
+                sl_i[my_k] = kEOS | (2 << 16);
+                insert(c);
+            }
+        } else {
+            const float4* sp = summ + row0 + my_k;
+            for (int sl0 = my_j; sl0 < n_slices; sl0 += 4 * J) {
+                float4 e[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {            // four independent loads in flight
+                    const int sl = sl0 + u * J;
+                    e[u] = sl < n_slices ? sp[(int64_t)sl * n_rows] : make_float4(-INFINITY, 0.f, -INFINITY, __int_as_float((int)0xFFFFFFFFu));
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int sl = sl0 + u * J;
+                    if (sl >= n_slices) break;
+                    const int idx = sl * Kin + my_k;
+                    if (e[u].x > pm) { ps = ps * exp2f((pm - e[u].x) * kL2e) + e[u].y; pm = e[u].x; }
+                    else if (e[u].x != -INFINITY) ps += e[u].y * exp2f((e[u].x - pm) * kL2e);
+                    const int bits = __float_as_int(e[u].w), i1 = bits & 0xFFFF, i2 = (bits >> 16) & 0xFFFF;
+                    SelCand c;
+                    c.idx = idx; c.sc2 = -INFINITY; c.tok2 = 0xFFFF; c.depth = 2; c.sc = -INFINITY;
+                    int tok = 0x7fffffff;
+                    if (i1 != 0xFFFF && i1 != my_skip) { c.sc = e[u].x; tok = i1; c.depth = 0; c.tok2 = i2; c.sc2 = e[u].z; }
+                    else if (i1 != 0xFFFF && i2 != 0xFFFF) { c.sc = e[u].z; tok = i2; c.depth = 1; }   // i1 == skip ⇒ i2 != skip
+                    sl_v[idx] = c.sc;
+                    sl_i[idx] = tok == 0x7fffffff ? tok : (tok | (c.depth << 16));
+                    if (tok != 0x7fffffff) { c.flat = my_k * V + tok; insert(c); }
+                }
+            }
+        }
+    }
+    part_m[tid] = pm;
+    part_s[tid] = ps;
+    __syncthreads();
+    if (tid < Kin) {                                     // row log-sum-exp from its J workers' partials
         float m = -INFINITY;
-        for (int sl = lane; sl < n_slices; sl += 32) m = fmaxf(m, sl_v[sl * Kin + k]);
-        m = warp_max(m);
+        for (int j = 0; j < J; ++j) m = fmaxf(m, part_m[j * Kin + tid]);
         float sum = 0.f;
-        for (int sl = lane; sl < n_slices; sl += 32) sum += sl_s[sl * Kin + k] * exp2f((sl_v[sl * Kin + k] - m) * kL2e);
-        sum = warp_sum(sum);
-        if (lane == 0) lse_s[k] = (step > 0 && cur_s[k] == kEOS) ? 0.f : m + logf(sum);
+        for (int j = 0; j < J; ++j) {
+            const float pmj = part_m[j * Kin + tid];
+            if (pmj != -INFINITY) sum += part_s[j * Kin + tid] * exp2f((pmj - m) * kL2e);
+        }
+        lse_s[tid] = (step > 0 && cur_s[tid] == kEOS) ? 0.f : m + logf(sum);
     }
     __syncthreads();
     auto score_of = [&](int k, float logit) { const float lp = logit - lse_s[k]; return step == 0 ? lp : nll_s[k] + lp; };
-
-    for (int idx = tid; idx < n_sl; idx += 256) {
-        const int sl = idx / Kin, k = idx - sl * Kin;
-        float sc = -INFINITY;
-        int tok = 0x7fffffff, d = 2;
-        if (step > 0 && cur_s[k] == kEOS) {              // finished hypothesis: one candidate, <eos> at +0 (V11:291-294)
-            if (sl == 0) { sc = nll_s[k] + 0.f; tok = kEOS; }
-        } else {
-            const int bits = sl_i[idx], i1 = bits & 0xFFFF, i2 = (bits >> 16) & 0xFFFF;
-            const int skip = (avoid_double && step > 0) ? cur_s[k] : -1;   // the repeated token may not be chosen (V11:279-280)
-            if (i1 != 0xFFFF && i1 != skip) { sc = score_of(k, sl_v[idx]); tok = i1; d = 0; }
-            else if (i1 != 0xFFFF && i2 != 0xFFFF) {     // i1 == skip ⇒ i2 != skip: the slice starts at its second element
-                sc = score_of(k, summ[(int64_t)sl * n_rows + row0 + k].z); tok = i2; d = 1;
+    // raw logits → scores (a finished row's <eos> candidate is nll + 0)
+    if (L0.flat != 0x7fffffff) { L0.sc = score_of(my_k, L0.sc); L0.sc2 = score_of(my_k, L0.sc2); }
+    if (L1.flat != 0x7fffffff) { L1.sc = score_of(my_k, L1.sc); L1.sc2 = score_of(my_k, L1.sc2); }
+    if (L2.flat != 0x7fffffff) { L2.sc = score_of(my_k, L2.sc); L2.sc2 = score_of(my_k, L2.sc2); }
+    // rebuild the list from the entry arrays (only when it ran empty: the thread took three winners in a row); depth-0
+    // entries still hold raw logits, advanced entries hold scores
+    auto rescan = [&]() {
+        L0.flat = L1.flat = L2.flat = 0x7fffffff;
+        L0.sc = L1.sc = L2.sc = -INFINITY;
+        n_l = 0;
+        if (!worker) return;
+        for (int sl = my_j; sl < n_slices; sl += J) {
+            const int idx = sl * Kin + my_k;
+            const int pk = sl_i[idx];
+            if (pk != 0x7fffffff) {
+                SelCand c;
+                c.depth = (pk >> 16) & 0xF;
+                c.sc = (pk & (1 << 20)) ? sl_v[idx] : score_of(my_k, sl_v[idx]);   // bit 20: the value is already a score
+                c.flat = my_k * V + (pk & 0xFFFF); c.idx = idx; c.sc2 = -INFINITY; c.tok2 = -2;
+                insert(c);
             }
         }
-        sl_v[idx] = sc;
-        sl_i[idx] = tok;
-        sl_d[idx] = d;
-    }
+    };
+    // the owner replaces the popped head by the slice's next candidate (nt == 0x7fffffff: the slice is exhausted)
+    auto apply_next = [&](int idx, int k, float nsc, int nt, int nd) {
+        sl_i[idx] = nt == 0x7fffffff ? nt : (nt | (nd << 16) | (1 << 20));
+        sl_v[idx] = nsc;
+        L0 = L1; L1 = L2; L2.flat = 0x7fffffff; L2.sc = -INFINITY;   // pop the head
+        --n_l;
+        if (n_l == 0) { rescan(); return; }                          // includes the entry just written
+        if (nt == 0x7fffffff) return;
+        SelCand c;
+        c.sc = nsc; c.flat = k * V + nt; c.idx = idx; c.depth = nd; c.sc2 = -INFINITY; c.tok2 = 0xFFFF;
+        // the list holds the TRUE best n_l entries of this thread; a candidate below its tail may be beaten by entries the
+        // list never saw, so it only enters when it beats the tail (or fills a slot the pop just freed AND beats the tail)
+        const SelCand& tail = n_l == 2 ? L1 : L0;
+        if (cand_better(c.sc, c.flat, tail.sc, tail.flat)) insert(c);
+    };
     __syncthreads();
 
     int n_eos = 0;
-    for (int round = 0; round < K; ++round) {
-        float bv = -INFINITY;
-        int bi = 0x7fffffff, bs = -1;                    // bi = flat index k·V + token
-        for (int idx = tid; idx < n_sl; idx += 256) {
-            const int tok = sl_i[idx];
-            if (tok != 0x7fffffff) {
-                const int flat = (idx % Kin) * V + tok;
-                if (cand_better(sl_v[idx], flat, bv, bi)) { bv = sl_v[idx]; bi = flat; bs = idx; }
-            }
-        }
+    for (int round = 0; round < K;) {
+        float bv = L0.sc;
+        int bi = L0.flat, bs = L0.idx;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
@@ -610,49 +697,21 @@ beam_select_top2_kernel(const float4* __restrict__ summ /*[n_slices][n_rows]*/, 
         }
         if (lane == 0) { red_a[wid] = bv; red_i[wid] = bi; red_t[wid] = bs; }
         __syncthreads();
-        if (tid == 0) {
-            float fv = red_a[0];
-            int fi = red_i[0], fs = red_t[0];
-            for (int w = 1; w < 8; ++w)
-                if (cand_better(red_a[w], red_i[w], fv, fi)) { fv = red_a[w]; fi = red_i[w]; fs = red_t[w]; }
-            const int par = fi / V, tok = fi - par * V;
-            win_sl = fs;
-            win_par[round] = par;
-            win_tok[round] = tok;
-            nll[(int64_t)b * K + round] = fv;
-            tokens_out[(int64_t)b * K + round] = tok;
-            parents_out[(int64_t)b * K + round] = par;
-            n_eos += (tok == kEOS);
-        }
-        __syncthreads();
-        if (round + 1 < K) {                             // next candidate of the winner's slice (every thread decides alike)
-            const int idx = win_sl, sl = idx / Kin, k = idx - sl * Kin;
-            const int cur = cur_s[k];
-            const int skip = (avoid_double && step > 0) ? cur : -1;
+        if (req_flag) {
+            // block-uniform: the previous winner's slice needs a third (or later) candidate.  The CTA recomputes the slice's
+            // logits from the operand planes with the tensor core's own three products (hi·hi + (lo·hi + hi·lo)·2^-11);
+            // warp = every NW-th column, lane = 8 consecutive k; columns already taken are excluded.
+            const int idx = req_idx, sl = idx / Kin, k = idx - sl * Kin;
+            const int skip = (avoid_double && step > 0) ? cur_s[k] : -1;
             float nv = -INFINITY;
-            int ni = 0x7fffffff, nd = 2;
-            bool recompute = false;
-            if (!(step > 0 && cur == kEOS)) {
-                if (sl_d[idx] == 0 && force_recompute != 1) {
-                    const float4 e = summ[(int64_t)sl * n_rows + row0 + k];
-                    const int i2 = (__float_as_int(e.w) >> 16) & 0xFFFF;
-                    if (i2 == 0xFFFF) { /* single-column slice: exhausted */ }
-                    else if (i2 != skip) { nv = e.z; ni = i2; nd = 1; }
-                    else recompute = true;
-                } else {
-                    recompute = true;
-                }
-            }
-            if (dbg && tid == 0) { atomicAdd((unsigned long long*)dbg + 20, (unsigned long long)recompute); atomicAdd((unsigned long long*)dbg + 21, 1ull); }
-            if (recompute && force_recompute != 2) {
-                // block-uniform: the CTA recomputes the slice's logits from the operand planes with the tensor core's own
-                // three products (hi·hi + (lo·hi + hi·lo)·2^-11); warp = every 8th column, lane = 8 consecutive k
+            int ni = 0x7fffffff;
+            if (force_recompute != 2) {
                 const uint16_t* th = t_hi + (row0 + k) * ld_t;
                 const uint16_t* tl = t_lo + (row0 + k) * ld_t;
                 const int c_lo = sl * slice_w, c_hi = min(V, c_lo + slice_w);
-                for (int c = c_lo + wid; c < c_hi; c += 8) {
+                for (int c = c_lo + wid; c < c_hi; c += NW) {
                     bool taken = c == skip;
-                    for (int w = 0; w <= round; ++w) taken |= (win_par[w] == k && win_tok[w] == c);
+                    for (int w = 0; w < round; ++w) taken |= (win_par[w] == k && win_tok[w] == c);
                     if (taken) continue;   // warp-uniform
                     const uint16_t* wh = w_hi + (int64_t)c * ld_w;
                     const uint16_t* wl = w_lo + (int64_t)c * ld_w;
@@ -683,19 +742,68 @@ beam_select_top2_kernel(const float4* __restrict__ summ /*[n_slices][n_rows]*/, 
                     const float x = (main_acc + cross_acc * (1.0f / 2048.0f)) + (bias ? bias[c] : 0.f);
                     if (cand_better(x, c, nv, ni)) { nv = x; ni = c; }
                 }
-                if (lane == 0) { red_a[wid] = nv; red_i[wid] = ni; }
-                __syncthreads();
+            }
+            __syncthreads();                              // red_* of the aborted arg-max are no longer needed
+            if (lane == 0) { red_a[wid] = nv; red_i[wid] = ni; }
+            __syncthreads();
+            if (((sl % J) * Kin + k) == tid) {            // the owner installs the recomputed candidate
                 nv = red_a[0]; ni = red_i[0];
-                for (int w = 1; w < 8; ++w)
+                for (int w = 1; w < NW; ++w)
                     if (cand_better(red_a[w], red_i[w], nv, ni)) { nv = red_a[w]; ni = red_i[w]; }
+                apply_next(idx, k, ni == 0x7fffffff ? -INFINITY : score_of(k, nv), ni, 2);
+                req_flag = 0;
             }
-            if (tid == 0) {
-                sl_i[idx] = ni;
-                sl_v[idx] = ni == 0x7fffffff ? -INFINITY : score_of(k, nv);
-                sl_d[idx] = nd;
-            }
+            __syncthreads();
+            continue;                                     // redo the arg-max of this round with the owner's updated list
+        }
+        if (tid == 0) {
+            float fv = red_a[0];
+            int fi = red_i[0], fs = red_t[0];
+            for (int w = 1; w < NW; ++w)
+                if (cand_better(red_a[w], red_i[w], fv, fi)) { fv = red_a[w]; fi = red_i[w]; fs = red_t[w]; }
+            const int par = fi / V, tok = fi - par * V;
+            win_sl = fs;
+            win_par[round] = par;
+            win_tok[round] = tok;
+            win_v[round] = fv;
+            n_eos += (tok == kEOS);
         }
         __syncthreads();
+        ++round;
+        const int w_idx = win_sl, w_sl = w_idx / Kin, w_k = w_idx - w_sl * Kin;
+        if (round < K && ((w_sl % J) * Kin + w_k) == tid) {   // owner: next candidate of the winner's slice
+            const int idx = w_idx, sl = w_sl, k = w_k;
+            const int cur = cur_s[k];
+            const int skip = (avoid_double && step > 0) ? cur : -1;
+            bool recompute = false;
+            float nsc = -INFINITY;
+            int nt = 0x7fffffff;
+            if (!(step > 0 && cur == kEOS)) {
+                if (L0.depth == 0 && force_recompute != 1) {
+                    int tok2 = L0.tok2;
+                    float sc2 = L0.sc2;
+                    if (tok2 == -2) {                     // list entry rebuilt by a rescan: fetch the slice's second again
+                        const float4 e = summ[(int64_t)sl * n_rows + row0 + k];
+                        tok2 = (__float_as_int(e.w) >> 16) & 0xFFFF;
+                        sc2 = tok2 == 0xFFFF ? -INFINITY : score_of(k, e.z);
+                    }
+                    if (tok2 == 0xFFFF) { /* single-column slice: exhausted */ }
+                    else if (tok2 != skip) { nsc = sc2; nt = tok2; }
+                    else recompute = true;
+                } else {
+                    recompute = true;
+                }
+            }
+            if (dbg) { atomicAdd((unsigned long long*)dbg + 20, (unsigned long long)recompute); atomicAdd((unsigned long long*)dbg + 21, 1ull); }
+            if (recompute) { req_idx = idx; req_flag = 1; }   // seen by everybody after the next round's first barrier
+            else apply_next(idx, k, nsc, nt, 1);
+        }
+    }
+    __syncthreads();
+    if (tid < K) {
+        nll[(int64_t)b * K + tid] = win_v[tid];
+        tokens_out[(int64_t)b * K + tid] = win_tok[tid];
+        parents_out[(int64_t)b * K + tid] = win_par[tid];
     }
     if (tid == 0 && fin_counter) atomicAdd(fin_counter, n_eos);
 }
@@ -907,7 +1015,7 @@ int beam_select_top2(const float4* summ, int slice_w, SplitDst t, const uint16_t
     }
     const int n_slices = (int)((V + slice_w - 1) / slice_w);
     const int Kin = step == 0 ? 1 : K;
-    const size_t smem = (size_t)Kin * n_slices * 12 + 16;
+    const size_t smem = (size_t)Kin * n_slices * 8 + 16;
     if (smem > 200 * 1024) {
         set_error("beam_select_top2: K=%d V=%lld needs %zu B of shared memory", K, (long long)V, smem);
         return VAG_ERR_UNSUPPORTED;
@@ -922,7 +1030,7 @@ int beam_select_top2(const float4* summ, int slice_w, SplitDst t, const uint16_t
             VAG_CUDA(cudaFuncSetAttribute(beam_select_top2_kernel<KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             configured = smem;                                                                                                \
         }                                                                                                                     \
-        beam_select_top2_kernel<KM><<<B, 256, smem, st>>>(summ, n_slices, slice_w, B * Kin, t.hi, t.lo, t.ld, w_hi, w_lo, ld_w, bias, E, \
+        beam_select_top2_kernel<KM><<<B, kSel2Threads, smem, st>>>(summ, n_slices, slice_w, B * Kin, t.hi, t.lo, t.ld, w_hi, w_lo, ld_w, bias, E, \
                                                           t.mode, prev_tokens, nll, tokens_out, parents_out, K, (int)V, step,  \
                                                           avoid_double, done, fin_counter, force, tc_debug());                 \
     } while (0)

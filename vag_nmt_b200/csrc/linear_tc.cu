@@ -1090,16 +1090,17 @@ vocab_top2_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_
             const int tn = tile % tiles_n;
             const int m0 = (tile / tiles_n) * BMP + (int)rank * BM, n0 = tn * BN, c0 = cq * 32;
             const uint32_t a = it & 1;
+            const int n_valid = min(32, N - (n0 + c0));   // ≤ 0: the chunk lies outside the matrix (warp-uniform)
+            const float bias_l = (bias && lane < n_valid) ? bias[n0 + c0 + lane] : 0.f;   // in flight while the tile is still being accumulated
             long long t0 = VAG_TCLK();
             mbar_wait(&tfull_bar[a], (it >> 1) & 1);
             t_wt += VAG_TCLK() - t0;
             tcgen05_fence_after();
-            const int n_valid = min(32, N - (n0 + c0));   // ≤ 0: the chunk lies outside the matrix (warp-uniform)
             float x[32];
             t0 = VAG_TCLK();
             if (n_valid > 0) {
                 __syncwarp();
-                my_bias[lane] = (bias && lane < n_valid) ? bias[n0 + c0 + lane] : 0.f;
+                my_bias[lane] = bias_l;
                 __syncwarp();
                 // two 16-column halves keep the live registers at x[32] + 2 x 16 (the kernel runs 18 warps per SM)
 #pragma unroll
@@ -1128,7 +1129,15 @@ vocab_top2_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_
             t_ld += VAG_TCLK() - t0;
             t0 = VAG_TCLK();
             float4 out = make_float4(-INFINITY, 0.f, -INFINITY, __int_as_float((int)0xFFFFFFFFu));
+#ifdef VAG_EXP_NOMATH
+            if (n_valid > 0) { float acc = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc += x[j];
+                out.x = acc; }
+            if (false) {
+#else
             if (n_valid > 0) {
+#endif
                 if (n_valid < 32) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) x[j] = j < n_valid ? x[j] : -INFINITY;
