@@ -180,7 +180,7 @@ def workload_config(args, per_step):
             "model": "NMT_AttentionImagine_Seq2Seq_Beam_V11 E256 H512 S512 I2048 V9391 random-init (seed 1234)",
             "sentences_per_rank_per_step": per_step, "beam": args.beam, "max_length": args.max_length,
             "src_len": "clip(round(N(14,4.5)),4,40)", "parallelism": f"dp{args.gpus} (sentence-sharded, no collective)",
-            "l2": "per-step working set (logits 451 MB + weights 64 MB) exceeds the 126 MB L2; no explicit flush"}
+            "l2": "one bench step = 80 decoder steps over 12000 rows; the activations + summaries + weights each decoder step touches (~0.5 GB) exceed the 126 MB L2; no explicit flush"}
 
 
 # ------------------------------------------------------------------------------------------ training step (second metric)
@@ -210,15 +210,17 @@ def oracle_train_step_time(model_cpu, batches, threads, lr=4e-4):
     return toks / sum(times), len(times)
 
 
-def measure_train(args, dev, world, rank, timed):
-    """BASELINE configs[1]/[3] shape: EN->DE multimodal training step, batch 32 per GPU, teacher forced, FP32,
-    zero dropout (the drop-in does not implement training-mode dropout yet), gradients all-reduced over ranks."""
+def measure_train(args, dev, world, rank, timed, precision="bf16"):
+    """BASELINE configs[1]/[3] shape: EN->DE multimodal training step, batch 32 per GPU, teacher forced, dropout 0
+    (parity configuration), gradients all-reduced over ranks.  precision "bf16": every tensor-core / FFMA contraction of the
+    forward AND backward pass rounds its operands to bfloat16 and accumulates in FP32; state, soft-max, losses, Adam FP32."""
     import vag_nmt_b200 as vag
     from vag_nmt_b200 import synthetic
     from vag_nmt_b200.optim import ClipAdam
     from vag_nmt_b200.train import DistributedPairwiseRankingLoss, train_imagine_beam
     cfg = synthetic.DE
     model = build_cpu_params().to(dev)
+    model.precision = precision
     opt = ClipAdam(model, lr=4e-4)
     w = torch.ones(cfg["tgt_size"], device=dev)
     w[0] = 0
@@ -245,10 +247,10 @@ def measure_train(args, dev, world, rank, timed):
     final_loss = float(state["loss"])
     tok = sum(tokens[i % len(tokens)] for i in range(steps)) * world
     res = {"metric": "train tgt tokens/sec", "value": tok / (ms / 1e3), "unit": "tokens/s", "ms_per_step": ms / steps, "steps": steps,
-           "batch_per_gpu": B, "global_batch": B * world, "dtype": "f32", "loss_after": final_loss,
+           "batch_per_gpu": B, "global_batch": B * world, "dtype": "bf16" if precision == "bf16" else "f32", "loss_after": final_loss,
            "note": "EN->DE multimodal, teacher forcing 1.0, dropout 0, pairwise ranking loss over the global batch, "
                    "clip 1.0 + Adam(lr 4e-4, wd 1e-5 on non-bias); host batches (pinned) copied in the timed region"}
-    if rank == 0 and world == 1 and args.cpu_sample > 0:
+    if rank == 0 and world == 1 and args.cpu_sample > 0 and precision == "bf16":
         threads = os.cpu_count() or 1
         cpu_model = build_cpu_params()
         v, n = oracle_train_step_time(cpu_model, batches[:4], threads)
@@ -323,35 +325,31 @@ def run_ours(args):
     value = total_sent * args.steps / (ms / 1e3)
     e2e = total_sent * args.steps / (ms_e2e / 1e3)
 
-    # ---- roofline of the dominant kernel: the vocabulary projection [B*K, E] x [E, V] of one decoder step
-    #      (linear_split3_kernel, tcgen05 FP16-split contraction on pre-split operands, exactly the launch the
-    #      decode loop makes), timed alone with CUDA events on the launching stream (burst peak applies).
+    # ---- roofline of the dominant kernel: the vocabulary projection of one decoder step, [B*K, E] x [E, V] reduced in its
+    #      epilogue to per-slice top-2 / soft-max summaries (vocab_top2_pair_kernel — tcgen05 cta_group::2, FP16-split
+    #      operands, exactly the launch the beam loop makes), timed alone with CUDA events on the launching stream.
     pk = peaks()
     N = args.sentences * K
     E, V = cfg["tgt_embedding_size"], cfg["tgt_size"]
-    x = torch.randn(N, E, device=dev)
-    ldl = (V + 3) // 4 * 4
-    ybuf = torch.empty(N, ldl, device=dev)
+    x = torch.tanh(torch.randn(N, E, device=dev))
     wgt, bias = model.decoder.out.weight.detach(), model.decoder.out.bias.detach()
     xs, wsplit = ops.tc_split(x), ops.tc_split(wgt)
-    y = ybuf[:, :V]
     for _ in range(3):
-        ops.tc_gemm(xs, wsplit, N, E, V, bias, out=y)
+        ops.tc_gemm_top2(xs, wsplit, N, E, V, bias)
     reps = 20
-    ms_k = timed(lambda: ops.tc_gemm(xs, wsplit, N, E, V, bias, out=y), reps) / reps
+    ms_k = timed(lambda: ops.tc_gemm_top2(xs, wsplit, N, E, V, bias), reps) / reps
     flops = 2.0 * N * E * V
     achieved = flops / (ms_k / 1e3) / 1e12
-    split3 = lib.vag_tc_elem_bytes() == 2
-    peak_tf = pk["bf16"] / (3.0 if split3 else 6.0)
+    peak_tf = pk["bf16"] / 3.0
     traffic = None
     tpath = ROOT / "profiles" / "dominant_kernel_traffic.json"
     if tpath.exists():
         traffic = json.loads(tpath.read_text()).get("dram_bytes_per_launch")
-    roofline = {"bound": "tensor", "kernel": "linear_split3_kernel (vag_tc_gemm_f32) vocab projection rows=%d K=%d N=%d" % (N, E, V),
+    roofline = {"bound": "tensor", "kernel": "vocab_top2_pair_kernel (vag_tc_gemm_top2_f32) vocabulary projection + top-2/soft-max "
+                                             "summaries, rows=%d K=%d N=%d" % (N, E, V),
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
-                "peak_note": (f"{pk['src']} bf16 burst {pk['bf16']} TF/s ÷ 3: FP32-exact mode issues 3 FP16 tensor products "
-                              "(hi·hi, hi·lo, lo·hi) per algorithmic MAC" if split3 else
-                              f"{pk['src']} bf16 burst {pk['bf16']} TF/s ÷ 6: 3 TF32 products per MAC at half the bf16 rate"),
+                "peak_note": f"{pk['src']} bf16 burst {pk['bf16']} TF/s ÷ 3: FP32-exact mode issues 3 FP16 tensor products "
+                             "(hi·hi, hi·lo, lo·hi) per algorithmic MAC; algorithmic FLOPs = 2·rows·K·N",
                 "ms_per_launch": ms_k, "flops_per_launch": flops}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -377,7 +375,8 @@ def run_ours(args):
                                 "token_exact_sentences": f"{agree}/{n}"}
     del model
     torch.cuda.empty_cache()
-    line["train"] = measure_train(args, dev, world, rank, timed)
+    line["train"] = measure_train(args, dev, world, rank, timed, "bf16")       # BASELINE configs[1]: training step bf16
+    line["train_f32"] = measure_train(args, dev, world, rank, timed, "fp32")
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -80,6 +80,25 @@ class _Seq2SeqBase(nn.Module):
 
     precision = "fp32"
 
+    def precision_scope(self):
+        """Context manager: run the enclosed calls (e.g. ``loss.backward()``) under the model's arithmetic mode."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def scope():
+            mode = {"fp32": -1, "bf16": 2}[getattr(self, "precision", "fp32")]
+            if mode == -1:
+                yield
+                return
+            from . import _cabi
+            lib = _cabi.lib()
+            lib.vag_set_gemm_mode(mode)
+            try:
+                yield
+            finally:
+                lib.vag_set_gemm_mode(-1)
+        return scope()
+
     def _reset_like_reference(self):
         # V11:77-80 / V2:53-56: kaiming-normal on EVERY ≥2-D non-bias parameter (embeddings and GRU matrices too)
         for name, param in self.named_parameters():
@@ -110,9 +129,9 @@ class _Seq2SeqBase(nn.Module):
                 out.append(cut)
             return out
         hyp, hyp_len = ops.beam_decode(w, h0, keys, ctx, mask, beam_size, tgt_l)  # V11:229 → 233-337
-        hyp = hyp.cpu()
+        rows = hyp.cpu().tolist()            # one device→host copy, one conversion; per-row tensor slicing costs ~4 µs a row
         lens = hyp_len.cpu().tolist()
-        return [hyp[b, :lens[b]].tolist() for b in range(B)]
+        return [rows[b][:lens[b]] for b in range(B)]
 
     @_with_precision
     def decode_device(self, src_var, src_lengths, im_var=None, beam_size=12, max_length=80):

@@ -19,7 +19,8 @@ def train_nmt(input_variable, target_variable, input_lengths, model, criterion, 
     model.train()
     optimizer.zero_grad()
     loss = model(input_variable, input_lengths, target_variable, teacher_force_ratio, criterion=criterion)
-    loss.backward()
+    with model.precision_scope():   # the backward contractions run in the same arithmetic mode as the forward ones
+        loss.backward()
     optimizer.step(clip=CLIP)
     return loss.item()
 
@@ -31,7 +32,8 @@ def train_imagine_beam(input_variable, target_variable, im_variable, input_lengt
     optimizer.zero_grad()
     loss, loss_mt, loss_vse = model(input_variable, input_lengths, target_variable, im_variable, teacher_force_ratio,
                                     criterion_mt=criterion_mt, criterion_vse=criterion_vse)
-    loss.backward()
+    with model.precision_scope():   # the backward contractions run in the same arithmetic mode as the forward ones
+        loss.backward()
     optimizer.step(clip=clip)
     if not sync:
         return loss.detach(), loss_mt.detach(), loss_vse.detach() if torch.is_tensor(loss_vse) else loss_vse
