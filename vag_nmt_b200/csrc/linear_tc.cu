@@ -965,7 +965,7 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
 // instructions per element, serial insertion chains) is latency-bound with two warps per scheduler; four per scheduler
 // hide it.  No staging tiles ⇒ room for a fourth pipeline stage.
 constexpr int V_STAGES = 4;
-constexpr int V_SMEM_BYTES = V_STAGES * Q_STAGE_BYTES + 2048 /*bias per warp*/ + 256 /*barriers*/ + 1024;
+constexpr int V_SMEM_BYTES = V_STAGES * Q_STAGE_BYTES + 2048 /*bias per warp*/ + 256 /*barriers*/ + 1024;   // stationary mode: 64 KB resident weights + 4 x 32 KB
 
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(576, 1)
@@ -986,7 +986,9 @@ vocab_top2_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_
     uint64_t* empty_bar = full_bar + V_STAGES;
     uint64_t* tfull_bar = empty_bar + V_STAGES;   // [2]
     uint64_t* tempty_bar = tfull_bar + 2;         // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* bfull_bar = tempty_bar + 2;         // weight tile resident (leader's; both CTAs' loads complete on it)
+    uint64_t* bempty_bar = bfull_bar + 1;         // every MMA that reads the resident weight tile has finished
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bempty_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -994,12 +996,25 @@ vocab_top2_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_
     const int tiles_n = (N + BN - 1) / BN, tiles_m = (rows + BMP - 1) / BMP;
     const int n_tiles = tiles_n * tiles_m;
     const int n_kb = (K + BK - 1) / BK;
+    // Every CTA pair walks a CONTIGUOUS range of tiles, row blocks fastest, so that consecutive tiles share their 128-column
+    // weight tile.  Weight-stationary mode (K ≤ 4 K-blocks, i.e. the whole [64 rows x K] half tile fits in 64 KB): the weight
+    // tile is loaded ONCE per column tile into a resident region and only the activations stream through the ring — a third
+    // less L2 → shared-memory traffic (the kernel is L2-fed-bound: 48 KB per K block for 12 MMAs).
+    const int t_begin = (int)((int64_t)pair * n_tiles / n_pairs), t_end = (int)((int64_t)(pair + 1) * n_tiles / n_pairs);
+    const bool stationary = n_kb <= 4;
+    constexpr int B_KB_BYTES = 2 * Q_B_BYTES;                       // B_hi + B_lo of one K block: 16 KB
+    const int stage_bytes = stationary ? 2 * Q_A_BYTES : Q_STAGE_BYTES;
+    uint8_t* bres = smem;                                           // resident weight tile (stationary mode): 4 x 16 KB
+    uint8_t* ring = stationary ? smem + 4 * B_KB_BYTES : smem;      // 4 stages of 32 KB (A only) or 48 KB (A + B)
+    constexpr uint32_t A_TX = SPLIT ? 2 * Q_A_BYTES : Q_A_BYTES, B_TX = SPLIT ? 2 * Q_B_BYTES : Q_B_BYTES;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_xh) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_xl) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wh) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wl) : "memory");
+        mbar_init(bfull_bar, 1);
+        mbar_init(bempty_bar, 1);
         for (int s = 0; s < V_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], rank == 0 ? 17 : 16); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1015,36 +1030,58 @@ vocab_top2_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_
 
     if (warp == 0) {
         if (lane == 0) {
-            uint32_t g = 0;
-            long long t_wait = 0, t_begin = VAG_TCLK();
-            for (int tile = pair; tile < n_tiles; tile += n_pairs) {
-                const int m0 = (tile / tiles_n) * BMP + (int)rank * BM, n0 = (tile % tiles_n) * BN + (int)rank * (BN / 2);
+            uint32_t g = 0, nb = 0;
+            int cur_tn = -1;
+            long long t_wait = 0, t_start = VAG_TCLK();
+            for (int tile = t_begin; tile < t_end; ++tile) {
+                const int tn = tile / tiles_m, tm = tile - tn * tiles_m;
+                const int m0 = tm * BMP + (int)rank * BM, n0 = tn * BN + (int)rank * (BN / 2);
+                if (stationary && tn != cur_tn) {
+                    if (nb > 0) mbar_wait(bempty_bar, (nb - 1) & 1);   // the previous column tile's MMAs are done with the region
+                    if (rank == 0) mbar_expect_tx(bfull_bar, 2 * n_kb * B_TX);
+                    const uint32_t bb = mapa_u32(smem_u32(bfull_bar), 0);
+                    for (int kb = 0; kb < n_kb; ++kb) {
+                        tma_load_2d_pair(bres + kb * B_KB_BYTES, &map_wh, bb, kb * BK, n0);
+                        if (SPLIT) tma_load_2d_pair(bres + kb * B_KB_BYTES + Q_B_BYTES, &map_wl, bb, kb * BK, n0);
+                    }
+                    cur_tn = tn;
+                    ++nb;
+                }
                 for (int kb = 0; kb < n_kb; ++kb, ++g) {
                     const int s = g % V_STAGES;
                     const long long t0 = VAG_TCLK();
                     mbar_wait(&empty_bar[s], ((g / V_STAGES) & 1) ^ 1);
                     t_wait += VAG_TCLK() - t0;
-                    uint8_t* st = smem + s * Q_STAGE_BYTES;
-                    if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * STAGE_TX);
+                    uint8_t* st = ring + s * stage_bytes;
+                    if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * (A_TX + (stationary ? 0u : B_TX)));
                     const uint32_t fb = mapa_u32(smem_u32(&full_bar[s]), 0);
                     const int k0 = kb * BK;
                     tma_load_2d_pair(st, &map_xh, fb, k0, m0);
                     if (SPLIT) tma_load_2d_pair(st + Q_A_BYTES, &map_xl, fb, k0, m0);
-                    tma_load_2d_pair(st + 2 * Q_A_BYTES, &map_wh, fb, k0, n0);
-                    if (SPLIT) tma_load_2d_pair(st + 2 * Q_A_BYTES + Q_B_BYTES, &map_wl, fb, k0, n0);
+                    if (!stationary) {
+                        tma_load_2d_pair(st + 2 * Q_A_BYTES, &map_wh, fb, k0, n0);
+                        if (SPLIT) tma_load_2d_pair(st + 2 * Q_A_BYTES + Q_B_BYTES, &map_wl, fb, k0, n0);
+                    }
                 }
             }
-            if (dbg && pair == 0) { dbg[rank * 16 + 0] = VAG_TCLK() - t_begin; dbg[rank * 16 + 1] = t_wait; dbg[rank * 16 + 2] = g; }
+            if (dbg && pair == 0) { dbg[rank * 16 + 0] = VAG_TCLK() - t_start; dbg[rank * 16 + 1] = t_wait; dbg[rank * 16 + 2] = g; }
         }
     } else if (warp == 1) {
         if (rank == 0 && lane == 0) {
-            uint32_t g = 0, it = 0;
-            long long t_we = 0, t_wf = 0, t_begin = VAG_TCLK();
-            for (int tile = pair; tile < n_tiles; tile += n_pairs, ++it) {
+            uint32_t g = 0, it = 0, nb = 0;
+            int cur_tn = -1;
+            long long t_we = 0, t_wf = 0, t_start = VAG_TCLK();
+            for (int tile = t_begin; tile < t_end; ++tile, ++it) {
+                const int tn = tile / tiles_m;
                 const uint32_t a = it & 1;
                 long long t0 = VAG_TCLK();
                 mbar_wait(&tempty_bar[a], ((it >> 1) & 1) ^ 1);
                 t_we += VAG_TCLK() - t0;
+                if (stationary && tn != cur_tn) {
+                    mbar_wait(bfull_bar, nb & 1);
+                    ++nb;
+                    cur_tn = tn;
+                }
                 tcgen05_fence_after();
                 const uint32_t d_main = tmem_base + a * 256, d_cross = d_main + 128;
                 for (int kb = 0; kb < n_kb; ++kb, ++g) {
@@ -1053,9 +1090,10 @@ vocab_top2_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_
                     mbar_wait(&full_bar[s], (g / V_STAGES) & 1);
                     t_wf += VAG_TCLK() - t0;
                     tcgen05_fence_after();
-                    const uint32_t st = smem_u32(smem + s * Q_STAGE_BYTES);
+                    const uint32_t st = smem_u32(ring + s * stage_bytes);
+                    const uint32_t sb = stationary ? smem_u32(bres + kb * B_KB_BYTES) : st + 2 * Q_A_BYTES;
                     const uint64_t d_ah = make_smem_desc<Q_ROWB>(st), d_al = make_smem_desc<Q_ROWB>(st + Q_A_BYTES);
-                    const uint64_t d_bh = make_smem_desc<Q_ROWB>(st + 2 * Q_A_BYTES), d_bl = make_smem_desc<Q_ROWB>(st + 2 * Q_A_BYTES + Q_B_BYTES);
+                    const uint64_t d_bh = make_smem_desc<Q_ROWB>(sb), d_bl = make_smem_desc<Q_ROWB>(sb + Q_B_BYTES);
 #pragma unroll
                     for (int j = 0; j < BK / UK; ++j) {
                         const uint64_t adv = (uint64_t)((j * 32) >> 4);
@@ -1068,11 +1106,12 @@ vocab_top2_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_
                     tcgen05_commit_pair(&empty_bar[s]);
                 }
                 tcgen05_commit_pair(&tfull_bar[a]);
+                if (stationary && (tile + 1 == t_end || (tile + 1) / tiles_m != tn)) tcgen05_commit_pair(bempty_bar);
             }
-            if (dbg && pair == 0) { dbg[4] = VAG_TCLK() - t_begin; dbg[5] = t_we; dbg[6] = t_wf; dbg[7] = it; }
+            if (dbg && pair == 0) { dbg[4] = VAG_TCLK() - t_start; dbg[5] = t_we; dbg[6] = t_wf; dbg[7] = it; }
         } else if (rank == 1 && lane == 0) {
             uint32_t it = 0;   // forward "my sixteen epilogue warps have drained buffer a" to the leader
-            for (int tile = pair; tile < n_tiles; tile += n_pairs, ++it) {
+            for (int tile = t_begin; tile < t_end; ++tile, ++it) {
                 const uint32_t a = it & 1;
                 mbar_wait(&tempty_bar[a], (it >> 1) & 1);
                 mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[a]), 0));
@@ -1085,10 +1124,10 @@ vocab_top2_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_
         constexpr float kL2e = 1.4426950408889634f;
         const int n_slices = tiles_n * 4;
         uint32_t it = 0;
-        long long t_wt = 0, t_ld = 0, t_math = 0, t_begin = VAG_TCLK();
-        for (int tile = pair; tile < n_tiles; tile += n_pairs, ++it) {
-            const int tn = tile % tiles_n;
-            const int m0 = (tile / tiles_n) * BMP + (int)rank * BM, n0 = tn * BN, c0 = cq * 32;
+        long long t_wt = 0, t_ld = 0, t_math = 0, t_start = VAG_TCLK();
+        for (int tile = t_begin; tile < t_end; ++tile, ++it) {
+            const int tn = tile / tiles_m;
+            const int m0 = (tile - tn * tiles_m) * BMP + (int)rank * BM, n0 = tn * BN, c0 = cq * 32;
             const uint32_t a = it & 1;
             const int n_valid = min(32, N - (n0 + c0));   // ≤ 0: the chunk lies outside the matrix (warp-uniform)
             const float bias_l = (bias && lane < n_valid) ? bias[n0 + c0 + lane] : 0.f;   // in flight while the tile is still being accumulated
@@ -1188,7 +1227,7 @@ vocab_top2_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_
         }
         (void)n_slices;
         if (dbg && pair == 0 && ew == 0 && lane == 0) {
-            dbg[rank * 16 + 8] = VAG_TCLK() - t_begin; dbg[rank * 16 + 9] = t_wt; dbg[rank * 16 + 10] = t_ld; dbg[rank * 16 + 12] = t_math;
+            dbg[rank * 16 + 8] = VAG_TCLK() - t_start; dbg[rank * 16 + 9] = t_wt; dbg[rank * 16 + 10] = t_ld; dbg[rank * 16 + 12] = t_math;
         }
     }
     tcgen05_fence_before();
