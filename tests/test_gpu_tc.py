@@ -49,3 +49,40 @@ def test_linear_tc_strided_and_rejects():
         ops.linear_tc(torch.randn(8, 64).cuda(), torch.randn(64, 64).cuda())       # too few rows
     with pytest.raises(_cabi.VagError):
         ops.linear_tc(torch.randn(128, 36).cuda(), torch.randn(64, 36).cuda())     # K not a multiple of 8
+
+
+@pytest.mark.parametrize("rows,K,N", [(300, 256, 9391), (1000, 128, 777), (12000, 256, 9391)])
+def test_vocab_top2_summaries_match_fp64(rows, K, N):
+    """vag_tc_gemm_top2_f32 (the dominant kernel of the beam loop): per (32-column slice, row) the best two logits with
+    their columns in canonical order and Σexp relative to the best — against a float64 contraction.  Columns must match
+    wherever the float64 margin exceeds the FP32-level tolerance; values and the row log-sum-exp to 3e-6 of max|logit|.
+    Ragged last slice (N % 32 != 0), a weight-stationary (K <= 256) and a streaming (K = 128 here is stationary too;
+    the 1000 x 128 x 777 case has partial row blocks and 25 slices with a 9-column tail) case are covered."""
+    from vag_nmt_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(rows + N)
+    x = torch.tanh(torch.randn(rows, K, device="cuda", generator=g))
+    w = torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)
+    b = torch.randn(N, device="cuda", generator=g)
+    summ = ops.tc_gemm_top2(ops.tc_split(x), ops.tc_split(w), rows, K, N, b).permute(1, 0, 2).contiguous()   # [rows, slices, 4]
+    ref = x.double() @ w.double().t() + b.double()
+    slices = (N + 31) // 32
+    pad = torch.full((rows, slices * 32 - N), -float("inf"), device="cuda", dtype=torch.float64)
+    rt = torch.cat([ref, pad], 1).view(rows, slices, 32)
+    top = rt.topk(3, dim=2)
+    base = (torch.arange(slices, device="cuda") * 32).view(1, slices, 1)
+    gi = top.indices + base
+    bits = summ[..., 3].contiguous().view(torch.int32)
+    i1, i2 = (bits & 0xFFFF).long(), ((bits >> 16) & 0xFFFF).long()
+    scale = float(ref.abs().max())
+    tol = 4e-6 * scale
+    assert float((summ[..., 0].double() - top.values[..., 0]).abs().max()) < tol
+    v2_ok = torch.isfinite(top.values[..., 1])
+    assert float(((summ[..., 2].double() - top.values[..., 1]).abs() * v2_ok).nan_to_num(0).max()) < tol
+    clear1 = (top.values[..., 0] - top.values[..., 1]) > 2 * tol          # unambiguous best
+    clear2 = clear1 & ((top.values[..., 1] - top.values[..., 2]) > 2 * tol)   # unambiguous second
+    assert bool((i1 == gi[..., 0])[clear1].all())
+    assert bool((i2 == gi[..., 1])[clear2 & v2_ok].all())
+    assert bool((i2[~v2_ok] == 0xFFFF).all())                              # single-column slices have no second
+    m = summ[..., 0].max(1).values
+    lse = m + torch.log((summ[..., 1] * torch.exp(summ[..., 0] - m[:, None])).sum(1))
+    assert float((lse.double() - torch.logsumexp(ref, 1)).abs().max()) < tol

@@ -300,7 +300,8 @@ static int decoder_step_core(GemmCtx& gemm, const vag_decoder_weights* w, const 
 // embedding gather and four fp32 round trips per step disappear.  The read-out input [h2 | e | c] is one plane pair of
 // pitch H+E+C; the embedding and the context are column windows of it (TMA takes any 16-byte aligned pitch).
 int gru_gates_split(float* h_out, int64_t ld_ho, const float* gi, int64_t ld_gi, const float* gh, int64_t ld_gh,
-                    const float* h_prev, int64_t ld_hp, int rows, int H, SplitDst sd, cudaStream_t st);
+                    const float* h_prev, int64_t ld_hp, int rows, int H, SplitDst sd, cudaStream_t st,
+                    const int64_t* gi_rows = nullptr, int64_t gi_n_rows = 0);
 int embed_split_rows(SplitDst dst, const uint16_t* t_hi, const uint16_t* t_lo, int64_t ld_t, int E, const int64_t* tokens, int rows,
                      int64_t V, cudaStream_t st);
 int attention_mlp_split(SplitDst sd, const float* q, int64_t ld_q, const float* keys, const float* ctx, const float* v,
@@ -318,11 +319,13 @@ struct FusedStep {
     GemmCtx::Ent *w_g1i = nullptr, *w_g1h = nullptr, *w_ah = nullptr, *w_c2h = nullptr, *w_g2i = nullptr, *w_g2h = nullptr,
                  *w_ro = nullptr, *w_out = nullptr, *w_emb = nullptr;
     float* b_ro = nullptr;
+    float* g1 = nullptr;   // [V, 3H] table  Emb·W_ihᵀ + b_ih  of gru_1: its input pre-activations depend on the token only
     SplitDst cat_e(int H) const { SplitDst d = cat; d.hi += H; if (d.lo) d.lo += H; return d; }
     SplitDst cat_c(int H, int E) const { SplitDst d = cat; d.hi += H + E; if (d.lo) d.lo += H + E; return d; }
 };
 
-static int fused_setup(GemmCtx& gemm, const vag_decoder_weights* w, const StepWs& ws, int n_rows, int rows_per_sent, FusedStep* f) {
+static int fused_setup(GemmCtx& gemm, const vag_decoder_weights* w, const StepWs& ws, int n_rows, int rows_per_sent, float* g1,
+                       FusedStep* f) {
     const int E = w->E, H = w->H, C = w->C, Kt = H + E + C;
     const int64_t V = w->V;
     const int mode = gemm_mode();
@@ -365,12 +368,19 @@ static int fused_setup(GemmCtx& gemm, const vag_decoder_weights* w, const StepWs
     planes(&f->t, E);
     planes(&f->cat, Kt);
     if (ar.overflow) return VAG_OK;
+    // gru_1's input contraction once per call for EVERY token instead of once per step for every row: the same kernel on
+    // the same operand rows, so each table row is bit-identical to what the per-step contraction produced
+    if (g1 && V > 128) {
+        VAG_TRY(tc_gemm(g1, 3 * H, f->w_emb->hi, f->w_emb->lo, f->w_emb->ld, f->w_g1i->hi, f->w_g1i->lo, f->w_g1i->ld, w->gru1_b_ih,
+                        (int)V, E, 3 * H, 0, gemm.st, nullptr, nullptr));
+        f->g1 = g1;
+    }
     f->ok = true;
     return VAG_OK;
 }
 
 // One fused step: the embedding planes (cat_e) and the previous state's planes (hprev) are already in place.
-static int decoder_step_fused(const FusedStep& f, const vag_decoder_weights* w, const StepWs& ws, const float* h_prev, const float* keys,
+static int decoder_step_fused(const FusedStep& f, const vag_decoder_weights* w, const StepWs& ws, const int64_t* tokens, const float* h_prev, const float* keys,
                               const float* ctx, const float* mask, int rows, int rows_per_sent, int T, float* h_out, float* logits,
                               int64_t ld_logits, cudaStream_t st, float4* summ, int* summ_tile_w) {
     const int E = w->E, H = w->H, C = w->C, Kt = H + E + C;
@@ -380,9 +390,10 @@ static int decoder_step_fused(const FusedStep& f, const vag_decoder_weights* w, 
                     int* tw) {
         return tc_gemm(y, ldy, x.hi, x.lo, x.ld, we->hi, we->lo, we->ld, bias, rows, K, N, 0, st, sm, tw);
     };
-    VAG_TRY(gemm(ws.gi, 3 * H, ce, f.w_g1i, w->gru1_b_ih, E, 3 * H, nullptr, nullptr));                      // NMT_Decoder.py:121
+    if (!f.g1) VAG_TRY(gemm(ws.gi, 3 * H, ce, f.w_g1i, w->gru1_b_ih, E, 3 * H, nullptr, nullptr));           // NMT_Decoder.py:121
     VAG_TRY(gemm(ws.gh, 3 * H, f.hprev, f.w_g1h, w->gru1_b_hh, H, 3 * H, nullptr, nullptr));
-    VAG_TRY(gru_gates_split(ws.h1, H, ws.gi, 3 * H, ws.gh, 3 * H, h_prev, H, rows, H, f.h1, st));
+    if (f.g1) VAG_TRY(gru_gates_split(ws.h1, H, f.g1, 3 * H, ws.gh, 3 * H, h_prev, H, rows, H, f.h1, st, tokens, V));
+    else VAG_TRY(gru_gates_split(ws.h1, H, ws.gi, 3 * H, ws.gh, 3 * H, h_prev, H, rows, H, f.h1, st));
     VAG_TRY(gemm(ws.q, C, f.h1, f.w_ah, nullptr, H, C, nullptr, nullptr));                                    // :47
     VAG_TRY(attention_mlp_split(cc, ws.q, C, keys, ctx, w->attn_v, mask, rows, rows_per_sent, T, C, st));     // :124-126
     VAG_TRY(tc_gemm_split_out(f.x2, cc.hi, cc.lo, Kt, f.w_c2h->hi, f.w_c2h->lo, f.w_c2h->ld, nullptr, rows, C, H, 0, st));   // :127
@@ -429,7 +440,7 @@ extern "C" int vag_decoder_step_f32(const vag_decoder_weights* w, const int64_t*
 namespace vag {
 struct BeamWs {
     StepWs step;
-    float *logits, *lse, *h_a, *h_b, *nll;
+    float *logits, *lse, *h_a, *h_b, *nll, *g1;
     float4* summ;
     int64_t *tok_hist, *sos;
     int32_t* par_hist;
@@ -442,6 +453,7 @@ static void beam_layout(A& a, int B, int K, int L, int E, int H, int C, int64_t 
     step_layout(a, N, E, H, C, V, &sw);
     float* logits = (float*)a.template take<float>((size_t)N * ((V + 3) / 4 * 4));  // rows padded to 16 B
     float* lse = (float*)a.template take<float>((size_t)N);
+    float* g1 = (float*)a.template take<float>((size_t)V * 3 * H);   // per-token input pre-activations of gru_1 (fused path)
     float4* summ = (float4*)a.template take<float4>((size_t)N * ((V + 31) / 32));   // per 32-column slice (top-2 kernel); the per-128 summaries need a quarter
     float* h_a = (float*)a.template take<float>((size_t)N * H);
     float* h_b = (float*)a.template take<float>((size_t)N * H);
@@ -451,7 +463,7 @@ static void beam_layout(A& a, int B, int K, int L, int E, int H, int C, int64_t 
     int32_t* par_hist = (int32_t*)a.template take<int32_t>((size_t)L * N);
     int* flags = (int*)a.template take<int>((size_t)L + 2);
     if (ws) {
-        ws->step = sw; ws->logits = logits; ws->lse = lse; ws->summ = summ; ws->h_a = h_a; ws->h_b = h_b; ws->nll = nll;
+        ws->step = sw; ws->logits = logits; ws->lse = lse; ws->g1 = g1; ws->summ = summ; ws->h_a = h_a; ws->h_b = h_b; ws->nll = nll;
         ws->tok_hist = tok_hist; ws->sos = sos; ws->par_hist = par_hist; ws->flags = flags;
     }
 }
@@ -491,7 +503,7 @@ extern "C" int vag_beam_decode_f32(const vag_decoder_weights* w, const float* h0
     const int64_t ldl = (V + 3) / 4 * 4;
     GemmCtx gemm(st, ws.step.wreg, ws.step.wbytes, ws.step.areg, ws.step.abytes);
     FusedStep fused;
-    VAG_TRY(fused_setup(gemm, w, ws.step, N, K, &fused));
+    VAG_TRY(fused_setup(gemm, w, ws.step, N, K, ws.g1, &fused));
     for (int di = 0; di < L; ++di) {
         const int rows = di == 0 ? B : N;
         const int rps = di == 0 ? 1 : K;
@@ -505,7 +517,7 @@ extern "C" int vag_beam_decode_f32(const vag_decoder_weights* w, const float* h0
                                          fused.w_emb->ld, E, ws.sos, B, V, st));
             }
             const bool no_logits = V >= 512 && V < 0xFFFF && !getenv("VAG_KEEP_LOGITS");
-            VAG_TRY(decoder_step_fused(fused, w, ws.step, h_prev, keys, ctx, mask, rows, rps, T, ws.h_b, no_logits ? nullptr : ws.logits,
+            VAG_TRY(decoder_step_fused(fused, w, ws.step, tokens, h_prev, keys, ctx, mask, rows, rps, T, ws.h_b, no_logits ? nullptr : ws.logits,
                                        ldl, st, V >= 512 ? ws.summ : nullptr, &tile_w));
             if (no_logits) {
                 VAG_TRY(beam_select_top2(ws.summ, 32, fused.t, (const uint16_t*)fused.w_out->hi, (const uint16_t*)fused.w_out->lo,

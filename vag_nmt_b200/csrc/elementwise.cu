@@ -12,7 +12,8 @@ template <bool VEC>
 __global__ void __launch_bounds__(256)
 gru_gates_kernel(float* h_out, int64_t ld_ho, float* h_out2, int64_t ld_ho2,
                  const float* __restrict__ gi, int64_t ld_gi, const float* __restrict__ gh, int64_t ld_gh,
-                 const float* h_prev /* may alias h_out */, int64_t ld_hp, int rows, int H, SplitDst sd) {
+                 const float* h_prev /* may alias h_out */, int64_t ld_hp, int rows, int H, SplitDst sd,
+                 const int64_t* __restrict__ gi_rows = nullptr, int64_t gi_n_rows = 0) {
     constexpr int W = VEC ? 4 : 1;
     const int per_row = H / W;
     const int64_t total = (int64_t)rows * per_row;
@@ -20,7 +21,12 @@ gru_gates_kernel(float* h_out, int64_t ld_ho, float* h_out2, int64_t ld_ho2,
          idx += (int64_t)gridDim.x * blockDim.x) {
         const int row = (int)(idx / per_row);
         const int j = (int)(idx % per_row) * W;
-        const float* gir = gi + (int64_t)row * ld_gi;
+        int64_t gi_row = row;
+        if (gi_rows) {   // input pre-activations looked up in a per-token table (the row's token id; out of range → 0 like the embedding)
+            gi_row = gi_rows[row];
+            if (gi_row < 0 || gi_row >= gi_n_rows) gi_row = 0;
+        }
+        const float* gir = gi + gi_row * ld_gi;
         const float* ghr = gh + (int64_t)row * ld_gh;
         float ir[W], iz[W], in_[W], hr[W], hz[W], hn[W], hp[W], out[W];
         if (VEC) {
@@ -203,11 +209,12 @@ int row_lse(float* lse_out, const float* logits, int64_t ld, int rows, int64_t V
 // Fused-step flavour of the gates: also writes the operand planes of the new state (all pitches multiples of 4, 16-byte
 // aligned pointers — guaranteed by the caller's workspace layout).
 int gru_gates_split(float* h_out, int64_t ld_ho, const float* gi, int64_t ld_gi, const float* gh, int64_t ld_gh,
-                    const float* h_prev, int64_t ld_hp, int rows, int H, SplitDst sd, cudaStream_t st) {
+                    const float* h_prev, int64_t ld_hp, int rows, int H, SplitDst sd, cudaStream_t st, const int64_t* gi_rows,
+                    int64_t gi_n_rows) {
     if (rows == 0) return VAG_OK;
     const int64_t total = (int64_t)rows * (H / 4);
     const int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)num_sms() * 16);
-    gru_gates_kernel<true><<<blocks, 256, 0, st>>>(h_out, ld_ho, nullptr, 0, gi, ld_gi, gh, ld_gh, h_prev, ld_hp, rows, H, sd);
+    gru_gates_kernel<true><<<blocks, 256, 0, st>>>(h_out, ld_ho, nullptr, 0, gi, ld_gi, gh, ld_gh, h_prev, ld_hp, rows, H, sd, gi_rows, gi_n_rows);
     VAG_LAUNCH_CHECK();
     return VAG_OK;
 }

@@ -740,6 +740,9 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
                 for (int kb = 0; kb < n_kb; ++kb, ++g) {
                     const int s = g % Q_STAGES;
                     const long long t0 = VAG_TCLK();
+#ifdef VAG_EXP_NOLOAD
+                    if (g >= Q_STAGES) continue;
+#endif
                     mbar_wait(&empty_bar[s], ((g / Q_STAGES) & 1) ^ 1);
                     t_wait += VAG_TCLK() - t0;
                     uint8_t* st = smem + s * Q_STAGE_BYTES;
@@ -768,6 +771,9 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
                 for (int kb = 0; kb < n_kb; ++kb, ++g) {
                     const int s = g % Q_STAGES;
                     t0 = VAG_TCLK();
+#ifdef VAG_EXP_NOLOAD
+                    if (g < Q_STAGES)
+#endif
                     mbar_wait(&full_bar[s], (g / Q_STAGES) & 1);
                     t_wf += VAG_TCLK() - t0;
                     tcgen05_fence_after();
