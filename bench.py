@@ -321,6 +321,13 @@ def run_ours(args):
     step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
 
+    # bf16 mode of the same workload (north_star's second arithmetic mode; not token-exact, see tests/test_gpu_bf16.py)
+    model.precision = "bf16"
+    for _ in range(2):
+        step_device()
+    ms_bf16 = timed(step_device, args.steps)
+    model.precision = "fp32"
+
     total_sent = args.sentences * world
     value = total_sent * args.steps / (ms / 1e3)
     e2e = total_sent * args.steps / (ms_e2e / 1e3)
@@ -358,6 +365,8 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(src_pin.numel() * 8 + im_pin.numel() * 4),
                     "d2h_bytes_per_step": int(args.sentences * (L * 8 + 4)), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "decode_bf16": {"value": total_sent * args.steps / (ms_bf16 / 1e3), "unit": UNIT, "ms_per_step": ms_bf16 / args.steps,
+                            "note": "same workload with model.precision = 'bf16' (bfloat16 operands, one tensor product, FP32 accumulation)"},
             "algorithmic": {"gflop_per_sentence": 2.0 * (1 + (L - 1) * K) * P_STEP_DE / 1e9,
                             "achieved_tflops_whole_job": value * 2.0 * (1 + (L - 1) * K) * P_STEP_DE / 1e12 / world}}
 

@@ -693,15 +693,20 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
     constexpr int BMP = 256, BM = 128, BN = 128, ELT = F16 ? 2 : 4, BK = Q_ROWB / ELT, UK = 32 / ELT;
     constexpr uint32_t FMT = MODE == 0 ? 2u : (MODE == 1 ? 0u : 1u);
     constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BMP >> 4) << 24);
-    constexpr uint32_t STAGE_TX = SPLIT ? Q_STAGE_BYTES : Q_STAGE_BYTES / 2;   // bytes ONE CTA's loads deliver per stage
+    // bf16 mode has no lo planes: its stages are half as large, so twice as many fit (it needs the depth: one product per
+    // K step means a stage is consumed three times faster)
+    constexpr int NST = SPLIT ? Q_STAGES : 2 * Q_STAGES;
+    constexpr int A_USED = SPLIT ? 2 * Q_A_BYTES : Q_A_BYTES, B_USED = SPLIT ? 2 * Q_B_BYTES : Q_B_BYTES;
+    constexpr int STG = A_USED + B_USED;
+    constexpr uint32_t STAGE_TX = STG;   // bytes ONE CTA's loads deliver per stage
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* epi = smem + Q_STAGES * Q_STAGE_BYTES;                      // 16 x 4 KB, 1024-B aligned
     float* bias_w = reinterpret_cast<float*>(epi + Q_EPI_BYTES);         // [8 warps][32]
     float4* xch2 = reinterpret_cast<float4*>(epi + Q_EPI_BYTES + 1024);  // [2][128], alternating between tiles
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi + Q_EPI_BYTES + 1024 + 4096);
-    uint64_t* empty_bar = full_bar + Q_STAGES;
-    uint64_t* tfull_bar = empty_bar + Q_STAGES;   // [2]
+    uint64_t* empty_bar = full_bar + NST;
+    uint64_t* tfull_bar = empty_bar + NST;   // [2]
     uint64_t* tempty_bar = tfull_bar + 2;         // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
@@ -718,7 +723,7 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wh) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wl) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y) : "memory");
-        for (int s = 0; s < Q_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], rank == 0 ? 9 : 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -738,21 +743,21 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
             for (int tile = pair; tile < n_tiles; tile += n_pairs) {
                 const int m0 = (tile / tiles_n) * BMP + (int)rank * BM, n0 = (tile % tiles_n) * BN + (int)rank * (BN / 2);
                 for (int kb = 0; kb < n_kb; ++kb, ++g) {
-                    const int s = g % Q_STAGES;
+                    const int s = g % NST;
                     const long long t0 = VAG_TCLK();
 #ifdef VAG_EXP_NOLOAD
-                    if (g >= Q_STAGES) continue;
+                    if (g >= NST) continue;
 #endif
-                    mbar_wait(&empty_bar[s], ((g / Q_STAGES) & 1) ^ 1);
+                    mbar_wait(&empty_bar[s], ((g / NST) & 1) ^ 1);
                     t_wait += VAG_TCLK() - t0;
-                    uint8_t* st = smem + s * Q_STAGE_BYTES;
+                    uint8_t* st = smem + s * STG;
                     if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * STAGE_TX);
                     const uint32_t fb = mapa_u32(smem_u32(&full_bar[s]), 0);
                     const int k0 = kb * BK;
                     tma_load_2d_pair(st, &map_xh, fb, k0, m0);
                     if (SPLIT) tma_load_2d_pair(st + Q_A_BYTES, &map_xl, fb, k0, m0);
-                    tma_load_2d_pair(st + 2 * Q_A_BYTES, &map_wh, fb, k0, n0);
-                    if (SPLIT) tma_load_2d_pair(st + 2 * Q_A_BYTES + Q_B_BYTES, &map_wl, fb, k0, n0);
+                    tma_load_2d_pair(st + A_USED, &map_wh, fb, k0, n0);
+                    if (SPLIT) tma_load_2d_pair(st + A_USED + Q_B_BYTES, &map_wl, fb, k0, n0);
                 }
             }
             if (dbg && pair == 0) { dbg[rank * 16 + 0] = VAG_TCLK() - t_begin; dbg[rank * 16 + 1] = t_wait; dbg[rank * 16 + 2] = g; }
@@ -769,17 +774,17 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
                 tcgen05_fence_after();
                 const uint32_t d_main = tmem_base + a * 256, d_cross = d_main + 128;
                 for (int kb = 0; kb < n_kb; ++kb, ++g) {
-                    const int s = g % Q_STAGES;
+                    const int s = g % NST;
                     t0 = VAG_TCLK();
 #ifdef VAG_EXP_NOLOAD
-                    if (g < Q_STAGES)
+                    if (g < NST)
 #endif
-                    mbar_wait(&full_bar[s], (g / Q_STAGES) & 1);
+                    mbar_wait(&full_bar[s], (g / NST) & 1);
                     t_wf += VAG_TCLK() - t0;
                     tcgen05_fence_after();
-                    const uint32_t st = smem_u32(smem + s * Q_STAGE_BYTES);
+                    const uint32_t st = smem_u32(smem + s * STG);
                     const uint64_t d_ah = make_smem_desc<Q_ROWB>(st), d_al = make_smem_desc<Q_ROWB>(st + Q_A_BYTES);
-                    const uint64_t d_bh = make_smem_desc<Q_ROWB>(st + 2 * Q_A_BYTES), d_bl = make_smem_desc<Q_ROWB>(st + 2 * Q_A_BYTES + Q_B_BYTES);
+                    const uint64_t d_bh = make_smem_desc<Q_ROWB>(st + A_USED), d_bl = make_smem_desc<Q_ROWB>(st + A_USED + Q_B_BYTES);
 #pragma unroll
                     for (int j = 0; j < BK / UK; ++j) {
                         const uint64_t adv = (uint64_t)((j * 32) >> 4);
@@ -984,13 +989,14 @@ vocab_top2_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_
     constexpr int BMP = 256, BM = 128, BN = 128, ELT = F16 ? 2 : 4, BK = Q_ROWB / ELT, UK = 32 / ELT;
     constexpr uint32_t FMT = MODE == 0 ? 2u : (MODE == 1 ? 0u : 1u);
     constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BMP >> 4) << 24);
-    constexpr uint32_t STAGE_TX = SPLIT ? Q_STAGE_BYTES : Q_STAGE_BYTES / 2;
+    constexpr int NST = SPLIT ? V_STAGES : 2 * V_STAGES;           // bf16 mode: half-size stages, twice as many
+    constexpr int A_USED = SPLIT ? 2 * Q_A_BYTES : Q_A_BYTES, B_USED = SPLIT ? 2 * Q_B_BYTES : Q_B_BYTES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     float* bias_w = reinterpret_cast<float*>(smem + V_STAGES * Q_STAGE_BYTES);   // [16 warps][32]
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + V_STAGES * Q_STAGE_BYTES + 2048);
-    uint64_t* empty_bar = full_bar + V_STAGES;
-    uint64_t* tfull_bar = empty_bar + V_STAGES;   // [2]
+    uint64_t* empty_bar = full_bar + NST;
+    uint64_t* tfull_bar = empty_bar + NST;   // [2]
     uint64_t* tempty_bar = tfull_bar + 2;         // [2]
     uint64_t* bfull_bar = tempty_bar + 2;         // weight tile resident (leader's; both CTAs' loads complete on it)
     uint64_t* bempty_bar = bfull_bar + 1;         // every MMA that reads the resident weight tile has finished
@@ -1008,11 +1014,11 @@ vocab_top2_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_
     // less L2 → shared-memory traffic (the kernel is L2-fed-bound: 48 KB per K block for 12 MMAs).
     const int t_begin = (int)((int64_t)pair * n_tiles / n_pairs), t_end = (int)((int64_t)(pair + 1) * n_tiles / n_pairs);
     const bool stationary = n_kb <= 4;
-    constexpr int B_KB_BYTES = 2 * Q_B_BYTES;                       // B_hi + B_lo of one K block: 16 KB
-    const int stage_bytes = stationary ? 2 * Q_A_BYTES : Q_STAGE_BYTES;
+    constexpr int B_KB_BYTES = B_USED;                              // B_hi (+ B_lo) of one K block: 16 KB (8 KB in bf16 mode)
+    const int stage_bytes = stationary ? A_USED : A_USED + B_USED;
     uint8_t* bres = smem;                                           // resident weight tile (stationary mode): 4 x 16 KB
-    uint8_t* ring = stationary ? smem + 4 * B_KB_BYTES : smem;      // 4 stages of 32 KB (A only) or 48 KB (A + B)
-    constexpr uint32_t A_TX = SPLIT ? 2 * Q_A_BYTES : Q_A_BYTES, B_TX = SPLIT ? 2 * Q_B_BYTES : Q_B_BYTES;
+    uint8_t* ring = stationary ? smem + 4 * B_KB_BYTES : smem;      // NST stages of A only or A + B
+    constexpr uint32_t A_TX = A_USED, B_TX = B_USED;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_xh) : "memory");
@@ -1021,7 +1027,7 @@ vocab_top2_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wl) : "memory");
         mbar_init(bfull_bar, 1);
         mbar_init(bempty_bar, 1);
-        for (int s = 0; s < V_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], rank == 0 ? 17 : 16); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -1054,9 +1060,9 @@ vocab_top2_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_
                     ++nb;
                 }
                 for (int kb = 0; kb < n_kb; ++kb, ++g) {
-                    const int s = g % V_STAGES;
+                    const int s = g % NST;
                     const long long t0 = VAG_TCLK();
-                    mbar_wait(&empty_bar[s], ((g / V_STAGES) & 1) ^ 1);
+                    mbar_wait(&empty_bar[s], ((g / NST) & 1) ^ 1);
                     t_wait += VAG_TCLK() - t0;
                     uint8_t* st = ring + s * stage_bytes;
                     if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * (A_TX + (stationary ? 0u : B_TX)));
@@ -1065,8 +1071,8 @@ vocab_top2_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_
                     tma_load_2d_pair(st, &map_xh, fb, k0, m0);
                     if (SPLIT) tma_load_2d_pair(st + Q_A_BYTES, &map_xl, fb, k0, m0);
                     if (!stationary) {
-                        tma_load_2d_pair(st + 2 * Q_A_BYTES, &map_wh, fb, k0, n0);
-                        if (SPLIT) tma_load_2d_pair(st + 2 * Q_A_BYTES + Q_B_BYTES, &map_wl, fb, k0, n0);
+                        tma_load_2d_pair(st + A_USED, &map_wh, fb, k0, n0);
+                        if (SPLIT) tma_load_2d_pair(st + A_USED + Q_B_BYTES, &map_wl, fb, k0, n0);
                     }
                 }
             }
@@ -1091,13 +1097,13 @@ vocab_top2_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_
                 tcgen05_fence_after();
                 const uint32_t d_main = tmem_base + a * 256, d_cross = d_main + 128;
                 for (int kb = 0; kb < n_kb; ++kb, ++g) {
-                    const int s = g % V_STAGES;
+                    const int s = g % NST;
                     t0 = VAG_TCLK();
-                    mbar_wait(&full_bar[s], (g / V_STAGES) & 1);
+                    mbar_wait(&full_bar[s], (g / NST) & 1);
                     t_wf += VAG_TCLK() - t0;
                     tcgen05_fence_after();
                     const uint32_t st = smem_u32(ring + s * stage_bytes);
-                    const uint32_t sb = stationary ? smem_u32(bres + kb * B_KB_BYTES) : st + 2 * Q_A_BYTES;
+                    const uint32_t sb = stationary ? smem_u32(bres + kb * B_KB_BYTES) : st + A_USED;
                     const uint64_t d_ah = make_smem_desc<Q_ROWB>(st), d_al = make_smem_desc<Q_ROWB>(st + Q_A_BYTES);
                     const uint64_t d_bh = make_smem_desc<Q_ROWB>(sb), d_bl = make_smem_desc<Q_ROWB>(sb + Q_B_BYTES);
 #pragma unroll
