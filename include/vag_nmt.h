@@ -380,6 +380,20 @@ int vag_encoder_bwd_f32(const vag_encoder_weights* w, const int32_t* lengths_hos
  *   accum[0] += Σ grad²  (vag_sumsq_f32 over every tensor, after the gradient all-reduce when data-parallel), then
  *   g ← grad·min(1, clip/(√accum + 1e-6)) [+ weight_decay·param];  Adam(m, v, step) update of param in place. */
 int vag_sumsq_f32(const float* g, int64_t n, float* accum, vag_stream_t stream);
+/* Multi-tensor flavours: ONE launch each over all parameter tensors (a device array of descriptors, 48 bytes each);
+ * max_n = the largest tensor's element count (sizes the grid).  Same arithmetic as the per-tensor entry points. */
+typedef struct vag_optim_tensor {
+    float* param;
+    const float* grad;
+    float* exp_avg;
+    float* exp_avg_sq;
+    int64_t n;
+    float weight_decay; /* added to the gradient (torch.optim.Adam), 0 for biases (nmt_multimodal_beam_DE.py:303-312) */
+    float lr;
+} vag_optim_tensor;
+int vag_sumsq_multi_f32(const vag_optim_tensor* tensors_device, int n_tensors, int64_t max_n, float* accum, vag_stream_t stream);
+int vag_clip_adam_multi_f32(const vag_optim_tensor* tensors_device, int n_tensors, int64_t max_n, const float* grad_sumsq,
+                            float clip, float beta1, float beta2, float eps, int step, vag_stream_t stream);
 int vag_clip_adam_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                       const float* grad_sumsq, float clip, float lr, float beta1, float beta2, float eps,
                       float weight_decay, int step, vag_stream_t stream);

@@ -229,6 +229,8 @@ static int launch_simt(float* y, int64_t ldy, const float* x, int64_t ldx, const
         linear_simt_kernel<BM, BN, BK, TM, TN, true, false><<<grid, block, 0, st>>>(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags);
     else if (!rb)
         linear_simt_kernel<BM, BN, BK, TM, TN, false, false><<<grid, block, 0, st>>>(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags);
+    else if (vec)
+        linear_simt_kernel<BM, BN, BK, TM, TN, true, true><<<grid, block, 0, st>>>(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags);
     else
         linear_simt_kernel<BM, BN, BK, TM, TN, false, true><<<grid, block, 0, st>>>(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags);
     VAG_LAUNCH_CHECK();

@@ -310,6 +310,41 @@ clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
 
 static inline int grid_for(int64_t n) { return (int)std::min<int64_t>((n + 255) / 256, (int64_t)num_sms() * 8); }
 
+// Multi-tensor flavours: ONE launch covers every parameter tensor (blockIdx.y = tensor, blockIdx.x strides over its
+// elements) instead of two launches per tensor — the ~37 tensors of the model cost 74 host calls per step otherwise.
+__global__ void __launch_bounds__(256) sumsq_multi_kernel(const vag_optim_tensor* __restrict__ t, float* __restrict__ out) {
+    const vag_optim_tensor e = t[blockIdx.y];
+    float a = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < e.n; i += (int64_t)gridDim.x * blockDim.x) a = fmaf(e.grad[i], e.grad[i], a);
+    a = warp_sum(a);
+    __shared__ float red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int w = 0; w < 8; ++w) s += red[w];
+        if (s != 0.f) atomicAdd(out, s);
+    }
+}
+__global__ void __launch_bounds__(256)
+clip_adam_multi_kernel(const vag_optim_tensor* __restrict__ t, const float* __restrict__ sumsq, float clip, float beta1, float beta2,
+                       float eps, float bc1, float bc2_sqrt) {
+    const vag_optim_tensor e = t[blockIdx.y];
+    const float norm = sqrtf(sumsq[0]);
+    const float coef = fminf(1.f, clip / (norm + 1e-6f));
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < e.n; i += (int64_t)gridDim.x * blockDim.x) {
+        float gi = e.grad[i] * coef;
+        const float w = e.param[i];
+        if (e.weight_decay != 0.f) gi = fmaf(e.weight_decay, w, gi);
+        const float mi = beta1 * e.exp_avg[i] + (1.f - beta1) * gi;
+        const float vi = beta2 * e.exp_avg_sq[i] + (1.f - beta2) * gi * gi;
+        e.exp_avg[i] = mi;
+        e.exp_avg_sq[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        e.param[i] = w - (e.lr / bc1) * (mi / denom);
+    }
+}
+
 }  // namespace vag
 
 using namespace vag;
@@ -459,6 +494,29 @@ extern "C" int vag_clip_adam_f32(float* param, const float* grad, float* exp_avg
     const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
     clip_adam_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, grad_sumsq, clip, lr, beta1,
                                                                     beta2, eps, weight_decay, bc1, bc2_sqrt);
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
+extern "C" int vag_sumsq_multi_f32(const vag_optim_tensor* tensors_device, int n_tensors, int64_t max_n, float* accum,
+                                   vag_stream_t stream) {
+    VAG_REQUIRE(tensors_device && accum && n_tensors >= 0 && max_n >= 0, "vag_sumsq_multi_f32: bad argument");
+    if (n_tensors == 0 || max_n == 0) return VAG_OK;
+    dim3 grid((unsigned)std::min<int64_t>((max_n + 255) / 256, 128), (unsigned)n_tensors);
+    sumsq_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tensors_device, accum);
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
+extern "C" int vag_clip_adam_multi_f32(const vag_optim_tensor* tensors_device, int n_tensors, int64_t max_n, const float* grad_sumsq,
+                                       float clip, float beta1, float beta2, float eps, int step, vag_stream_t stream) {
+    VAG_REQUIRE(tensors_device && grad_sumsq && n_tensors >= 0 && max_n >= 0, "vag_clip_adam_multi_f32: bad argument");
+    VAG_REQUIRE(step >= 1, "vag_clip_adam_multi_f32: step counts from 1");
+    if (n_tensors == 0 || max_n == 0) return VAG_OK;
+    const float bc1 = 1.f - powf(beta1, (float)step);
+    const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+    dim3 grid((unsigned)std::min<int64_t>((max_n + 255) / 256, 128), (unsigned)n_tensors);
+    clip_adam_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tensors_device, grad_sumsq, clip, beta1, beta2, eps, bc1, bc2_sqrt);
     VAG_LAUNCH_CHECK();
     return VAG_OK;
 }

@@ -2,8 +2,9 @@
 
 Mirrors ``torch.nn.utils.clip_grad_norm_(model.parameters(), clip)`` followed by ``optim.Adam(param_groups).step()``
 with the parameter groups of nmt_multimodal_beam_DE.py:303-332 (weight decay — added to the gradient, not
-decoupled — on every parameter whose name lacks 'bias').  All arithmetic runs in two kernels per parameter tensor
-(vag_sumsq_f32, vag_clip_adam_f32); the clip coefficient is read on the device, so a step never synchronises.
+decoupled — on every parameter whose name lacks 'bias').  All arithmetic runs in TWO launches for all parameter tensors
+(vag_sumsq_multi_f32, vag_clip_adam_multi_f32 over a descriptor table); the clip coefficient is read on the device, so a
+step never synchronises.
 """
 from __future__ import annotations
 
@@ -71,19 +72,24 @@ class ClipAdam:
         if self._sumsq is None or self._sumsq.device != dev:
             self._sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
         self._sumsq.zero_()
-        for p in params:
-            if not p.grad.is_contiguous():
-                p.grad = p.grad.contiguous()
-            T.sumsq_(self._sumsq, p.grad)
         self.step_count += 1
         b1, b2 = self.betas
+        # ONE descriptor table (48 B per tensor) and two launches for all tensors: Σ‖g‖², then clip + Adam
+        entries, max_n = [], 0
         for g in self.param_groups:
             for p in g["params"]:
                 if p.grad is None:
                     continue
+                if not p.grad.is_contiguous():
+                    p.grad = p.grad.contiguous()
                 st = self.state.get(p)
                 if st is None:
                     st = self.state[p] = (torch.zeros_like(p), torch.zeros_like(p))
-                T.clip_adam_(p.data, p.grad, st[0], st[1], self._sumsq, clip if clip is not None else float("inf"), g["lr"], b1, b2,
-                             self.eps, g["weight_decay"], self.step_count)
+                entries.append((p.data, p.grad, st[0], st[1], float(g["weight_decay"]), float(g["lr"])))
+                max_n = max(max_n, p.numel())
+        table = T.optim_table(entries).to(dev, non_blocking=True)
+        T.sumsq_multi_(self._sumsq, table, len(entries), max_n)
+        T.clip_adam_multi_(table, len(entries), max_n, self._sumsq, clip if clip is not None else float("inf"), b1, b2, self.eps,
+                           self.step_count)
+        self._table = table   # keep the descriptors alive until the kernels have run
         return self._sumsq

@@ -140,3 +140,28 @@ def clip_adam_(param, grad, exp_avg, exp_avg_sq, sumsq, clip, lr, beta1, beta2, 
         check(lib.vag_clip_adam_f32(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), param.numel(),
                                     sumsq.data_ptr(), _f(clip), _f(lr), _f(beta1), _f(beta2), _f(eps), _f(weight_decay), int(step),
                                     stream_ptr()))
+
+
+def optim_table(entries) -> torch.Tensor:
+    """Descriptor table for the multi-tensor optimiser kernels: entries = [(param, grad, exp_avg, exp_avg_sq, wd, lr), …]
+    → uint8 host tensor laid out as ``vag_optim_tensor[n]`` (include/vag_nmt.h: 4 pointers, int64 n, 2 floats = 48 B)."""
+    import numpy as np
+    dt = np.dtype([("param", "<u8"), ("grad", "<u8"), ("m", "<u8"), ("v", "<u8"), ("n", "<i8"), ("wd", "<f4"), ("lr", "<f4")])
+    assert dt.itemsize == 48
+    arr = np.zeros(len(entries), dtype=dt)
+    for i, (p, g, m, v, wd, lr) in enumerate(entries):
+        arr[i] = (p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), wd, lr)
+    return torch.from_numpy(arr.view(np.uint8).reshape(-1))
+
+
+def sumsq_multi_(accum: torch.Tensor, table_dev: torch.Tensor, n_tensors: int, max_n: int) -> None:
+    lib = _cabi.lib()
+    with on_device(accum.device):
+        check(lib.vag_sumsq_multi_f32(table_dev.data_ptr(), int(n_tensors), int(max_n), accum.data_ptr(), stream_ptr()))
+
+
+def clip_adam_multi_(table_dev: torch.Tensor, n_tensors: int, max_n: int, sumsq, clip, beta1, beta2, eps, step) -> None:
+    lib = _cabi.lib()
+    with on_device(sumsq.device):
+        check(lib.vag_clip_adam_multi_f32(table_dev.data_ptr(), int(n_tensors), int(max_n), sumsq.data_ptr(), _f(clip), _f(beta1),
+                                          _f(beta2), _f(eps), int(step), stream_ptr()))
