@@ -30,11 +30,15 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], group=None) -> Non
     grads = [p.grad for p in params if p.grad is not None]
     if not grads:
         return
-    flat = torch._utils._flatten_dense_tensors(grads)
+    world = dist.get_world_size(group)
+    flat = torch.cat([g.reshape(-1) for g in grads])              # one launch
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    flat /= dist.get_world_size(group)
-    for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
-        g.copy_(f)
+    flat.mul_(1.0 / world)
+    views, off = [], 0
+    for g in grads:
+        views.append(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()
+    torch._foreach_copy_(grads, views)                            # multi-tensor copy back: a couple of launches, not one per tensor
 
 
 class ClipAdam:
