@@ -1200,14 +1200,17 @@ vocab_top2_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_
 #pragma unroll
                 for (int u = 0; u < 4; ++u) { c1[u] = -INFINITY; c2[u] = -INFINITY; k1[u] = 0xFFFF; k2[u] = 0xFFFF; }
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
+                for (int j = 0; j < 32; ++j) {   // values through min/max (no predicates), columns through two selects each
                     const int u = j & 3;
                     const float xv = x[j];
-                    const bool g1 = xv > c1[u], g2 = xv > c2[u];
-                    c2[u] = g1 ? c1[u] : (g2 ? xv : c2[u]);
-                    k2[u] = g1 ? k1[u] : (g2 ? j : k2[u]);
-                    c1[u] = g1 ? xv : c1[u];
+                    const bool g1 = xv > c1[u];
+                    const float loser = fminf(c1[u], xv);          // the one of (old best, new) that is not the new best
+                    const int kl = g1 ? k1[u] : j;
+                    c1[u] = fmaxf(c1[u], xv);
                     k1[u] = g1 ? j : k1[u];
+                    const bool g2 = loser > c2[u];
+                    c2[u] = fmaxf(c2[u], loser);
+                    k2[u] = g2 ? kl : k2[u];
                 }
                 auto better = [](float av, int ai, float bv, int bi) { return av > bv || (av == bv && ai < bi); };
                 auto merge2 = [&](float& p1, int& i1, float& p2, int& i2, float q1, int j1_, float q2, int j2_) {
