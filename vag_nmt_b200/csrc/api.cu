@@ -94,6 +94,13 @@ int tc_gemm(float* y, int64_t ldy, const void* xh, const void* xl, int64_t ldxs,
             const float* bias, int rows, int K, int N, int flags, cudaStream_t st, float4* summ, int* summ_tile_w);
 }
 
+namespace vag {
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("VAG_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+}
 extern "C" int vag_tc_elem_bytes(void) { return tc_elem_bytes(); }
 
 namespace vag {

@@ -216,6 +216,7 @@ attention_tuned_kernel(float* __restrict__ c_out, int64_t ld_c, float* __restric
                        int64_t ld_q, const float* __restrict__ keys, const float* __restrict__ ctx,
                        const float* __restrict__ v, const float* __restrict__ mask, int rows, int rows_per_sent, int T, int C,
                        SplitDst sd) {
+    pdl_trigger();   // the contraction that follows may start its prologue while this kernel drains
     extern __shared__ __align__(16) float smem[];
     const int b = blockIdx.x;
     const int r_base = blockIdx.y * RCAP;

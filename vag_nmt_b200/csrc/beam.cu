@@ -838,6 +838,7 @@ beam_advance_fused_kernel(float* __restrict__ h_next, const float* __restrict__ 
                           const int64_t* __restrict__ tokens, int B, int K, int Kin, int H, int step, int* __restrict__ done,
                           const int* __restrict__ fin_counter, int* __restrict__ steps_run, SplitDst h_sd, SplitDst e_sd,
                           const uint16_t* __restrict__ t_hi, const uint16_t* __restrict__ t_lo, int64_t ld_t, int E, int64_t V) {
+    pdl_trigger();   // the contraction that follows may start its prologue while this kernel drains
     if (*reinterpret_cast<volatile int*>(done)) return;
     const int n = blockIdx.x;  // new row
     const int b = n / K;

@@ -14,6 +14,7 @@ gru_gates_kernel(float* h_out, int64_t ld_ho, float* h_out2, int64_t ld_ho2,
                  const float* __restrict__ gi, int64_t ld_gi, const float* __restrict__ gh, int64_t ld_gh,
                  const float* h_prev /* may alias h_out */, int64_t ld_hp, int rows, int H, SplitDst sd,
                  const int64_t* __restrict__ gi_rows = nullptr, int64_t gi_n_rows = 0) {
+    pdl_trigger();   // the contraction that follows may start its prologue while this kernel drains
     constexpr int W = VEC ? 4 : 1;
     const int per_row = H / W;
     const int64_t total = (int64_t)rows * per_row;

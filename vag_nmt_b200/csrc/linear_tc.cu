@@ -735,6 +735,8 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
     cluster_sync_all();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();   // the next kernel on the stream may start its own prologue as SMs drain
+    pdl_wait();      // everything above touched no global memory; from here on the predecessor's results are needed
 
     if (warp == 0) {
         if (lane == 0) {
@@ -1039,6 +1041,8 @@ vocab_top2_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_
     cluster_sync_all();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();   // the next kernel on the stream may start its own prologue as SMs drain
+    pdl_wait();      // everything above touched no global memory; from here on the predecessor's results are needed
 
     if (warp == 0) {
         if (lane == 0) {
@@ -1425,10 +1429,10 @@ int tc_gemm_split_out(SplitDst out, const void* xh, const void* xl, int64_t ldxs
     static bool attr_set[3] = {false, false, false};
     if (mode == 1) {
         if (!attr_set[1]) { VAG_CUDA(cudaFuncSetAttribute(linear_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES)); attr_set[1] = true; }
-        linear_pair_kernel<1><<<grid, 320, Q_SMEM_BYTES, st>>>(mxh, mxl, mwh, mwl, myh, myh, myl, bias, rows, K, N, flags | VAG_LIN_SPLIT_OUT, nullptr, g_tc_dbg);
+        VAG_CUDA(launch_pdl(linear_pair_kernel<1>, dim3(grid), dim3(320), Q_SMEM_BYTES, st, mxh, mxl, mwh, mwl, myh, myh, myl, bias, rows, K, N, flags | VAG_LIN_SPLIT_OUT, (float4*)nullptr, g_tc_dbg));
     } else {
         if (!attr_set[2]) { VAG_CUDA(cudaFuncSetAttribute(linear_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES)); attr_set[2] = true; }
-        linear_pair_kernel<2><<<grid, 320, Q_SMEM_BYTES, st>>>(mxh, mxl, mwh, mwl, myh, myh, myl, bias, rows, K, N, flags | VAG_LIN_SPLIT_OUT, nullptr, g_tc_dbg);
+        VAG_CUDA(launch_pdl(linear_pair_kernel<2>, dim3(grid), dim3(320), Q_SMEM_BYTES, st, mxh, mxl, mwh, mwl, myh, myh, myl, bias, rows, K, N, flags | VAG_LIN_SPLIT_OUT, (float4*)nullptr, g_tc_dbg));
     }
     VAG_LAUNCH_CHECK();
     return VAG_OK;
@@ -1455,10 +1459,10 @@ int tc_gemm_top2(float4* summ, const void* xh, const void* xl, int64_t ldxs, con
     static bool attr_set[3] = {false, false, false};
     if (mode == 1) {
         if (!attr_set[1]) { VAG_CUDA(cudaFuncSetAttribute(vocab_top2_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, V_SMEM_BYTES)); attr_set[1] = true; }
-        vocab_top2_pair_kernel<1><<<grid, 576, V_SMEM_BYTES, st>>>(mxh, mxl, mwh, mwl, bias, rows, K, N, summ, g_tc_dbg);
+        VAG_CUDA(launch_pdl(vocab_top2_pair_kernel<1>, dim3(grid), dim3(576), V_SMEM_BYTES, st, mxh, mxl, mwh, mwl, bias, rows, K, N, summ, g_tc_dbg));
     } else {
         if (!attr_set[2]) { VAG_CUDA(cudaFuncSetAttribute(vocab_top2_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, V_SMEM_BYTES)); attr_set[2] = true; }
-        vocab_top2_pair_kernel<2><<<grid, 576, V_SMEM_BYTES, st>>>(mxh, mxl, mwh, mwl, bias, rows, K, N, summ, g_tc_dbg);
+        VAG_CUDA(launch_pdl(vocab_top2_pair_kernel<2>, dim3(grid), dim3(576), V_SMEM_BYTES, st, mxh, mxl, mwh, mwl, bias, rows, K, N, summ, g_tc_dbg));
     }
     VAG_LAUNCH_CHECK();
     return VAG_OK;
@@ -1491,7 +1495,7 @@ int tc_gemm(float* y, int64_t ldy, const void* xh, const void* xl, int64_t ldxs,
             VAG_CUDA(cudaFuncSetAttribute(linear_pair_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES));    \
             attr_set[M] = true;                                                                                                 \
         }                                                                                                                       \
-        linear_pair_kernel<M><<<grid, 320, Q_SMEM_BYTES, st>>>(mxh, mxl, mwh, mwl, my, my, my, bias, rows, K, N, flags & ~VAG_LIN_SPLIT_OUT, summ, g_tc_dbg);          \
+        VAG_CUDA(launch_pdl(linear_pair_kernel<M>, dim3(grid), dim3(320), Q_SMEM_BYTES, st, mxh, mxl, mwh, mwl, my, my, my, bias, rows, K, N, flags & ~VAG_LIN_SPLIT_OUT, summ, g_tc_dbg));          \
     } while (0)
         if (mode == 0) VAG_PAIR(0);
         else if (mode == 1) VAG_PAIR(1);
