@@ -228,6 +228,8 @@ attention_tuned_kernel(float* __restrict__ c_out, int64_t ld_c, float* __restric
     float* q_s = smem;                    // [RCAP][C]
     float* v_s = q_s + (size_t)RCAP * C;  // [C]
     float* sc_s = v_s + C;                // [RCAP][T]
+    constexpr int RPAD = (RCAP + 3) / 4 * 4;
+    float* al_s = sc_s + (((size_t)RCAP * T + 3) & ~(size_t)3);  // [T][RPAD], 16-byte aligned: α transposed, so the context phase reads a position's weights as float4
     const float* key_b = keys + (int64_t)b * T * C;
     const float* ctx_b = ctx + (int64_t)b * T * C;
     const float* mask_b = mask ? mask + (int64_t)b * T : nullptr;
@@ -271,6 +273,7 @@ attention_tuned_kernel(float* __restrict__ c_out, int64_t ld_c, float* __restric
         if (lane == 0) n_live_s = min(n, 256);
     }
     for (int i = tid; i < R * T; i += 256) sc_s[i] = -INFINITY;
+    for (int i = tid; i < T * RPAD; i += 256) al_s[i] = 0.f;
     __syncthreads();
     const int n_live = n_live_s;
     const int n_groups = (R + RG - 1) / RG;
@@ -340,6 +343,7 @@ attention_tuned_kernel(float* __restrict__ c_out, int64_t ld_c, float* __restric
         for (int t = lane; t < T; t += 32) {
             const float a = s[t] / sum;
             s[t] = a;
+            al_s[t * RPAD + r] = a;
             if (alpha_out && row0 + r < rows) alpha_out[(int64_t)(row0 + r) * T + t] = a;
         }
     }
@@ -362,15 +366,16 @@ attention_tuned_kernel(float* __restrict__ c_out, int64_t ld_c, float* __restric
             for (int u = 0; u < 4; ++u) {
                 const int t = t0 + u;
                 if (t < T) {
+                    float al[RPAD];
+#pragma unroll
+                    for (int r4 = 0; r4 < RPAD / 4; ++r4)   // rows ≥ R hold zeros (cleared below): no per-row guard in the FMA loop
+                        *reinterpret_cast<float4*>(al + 4 * r4) = *reinterpret_cast<const float4*>(al_s + t * RPAD + 4 * r4);
 #pragma unroll
                     for (int r = 0; r < RCAP; ++r) {
-                        if (r < R) {
-                            const float a = sc_s[r * T + t];
-                            acc[r].x = fmaf(a, x[u].x, acc[r].x);
-                            acc[r].y = fmaf(a, x[u].y, acc[r].y);
-                            acc[r].z = fmaf(a, x[u].z, acc[r].z);
-                            acc[r].w = fmaf(a, x[u].w, acc[r].w);
-                        }
+                        acc[r].x = fmaf(al[r], x[u].x, acc[r].x);
+                        acc[r].y = fmaf(al[r], x[u].y, acc[r].y);
+                        acc[r].z = fmaf(al[r], x[u].z, acc[r].z);
+                        acc[r].w = fmaf(al[r], x[u].w, acc[r].w);
                     }
                 }
             }
@@ -388,7 +393,7 @@ template <int MODE, int RCAP, bool FULLC>
 static int launch_attention_tuned(float* c_out, int64_t ld_c, float* alpha, const float* q, int64_t ld_q, const float* keys,
                                   const float* ctx, const float* v, const float* mask, int rows, int rows_per_sent, int T, int C,
                                   cudaStream_t st, SplitDst sd = SplitDst()) {
-    const size_t smem = ((size_t)RCAP * C + C + (size_t)RCAP * T) * sizeof(float);
+    const size_t smem = ((size_t)RCAP * C + C + (size_t)RCAP * T + 4 + (size_t)T * ((RCAP + 3) / 4 * 4)) * sizeof(float);
     if (smem > 227 * 1024) {
         set_error("vag_attention_f32: C=%d T=%d needs %zu B of shared memory", C, T, smem);
         return VAG_ERR_UNSUPPORTED;
