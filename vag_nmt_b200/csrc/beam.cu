@@ -840,22 +840,24 @@ beam_advance_fused_kernel(float* __restrict__ h_next, const float* __restrict__ 
                           const uint16_t* __restrict__ t_hi, const uint16_t* __restrict__ t_lo, int64_t ld_t, int E, int64_t V) {
     pdl_trigger();   // the contraction that follows may start its prologue while this kernel drains
     if (*reinterpret_cast<volatile int*>(done)) return;
-    const int n = blockIdx.x;  // new row
-    const int b = n / K;
-    const int p = b * Kin + (Kin == 1 ? 0 : parents[n]);
-    const float4* src = reinterpret_cast<const float4*>(h_cur + (int64_t)p * H);
-    float4* dst = reinterpret_cast<float4*>(h_next + (int64_t)n * H);
-    for (int c = threadIdx.x; c < H / 4; c += blockDim.x) {
-        const float4 v = src[c];
-        dst[c] = v;
-        split_store4(h_sd, n, c * 4, v);
-    }
-    int64_t id = tokens[n];
-    if (id < 0 || id >= V) id = 0;
-    for (int c = threadIdx.x; c < E / 8; c += blockDim.x) {
-        *reinterpret_cast<uint4*>(e_sd.hi + (int64_t)n * e_sd.ld + c * 8) = *reinterpret_cast<const uint4*>(t_hi + id * ld_t + c * 8);
-        if (e_sd.mode != 2)
-            *reinterpret_cast<uint4*>(e_sd.lo + (int64_t)n * e_sd.ld + c * 8) = *reinterpret_cast<const uint4*>(t_lo + id * ld_t + c * 8);
+    constexpr int RPB = 4;   // rows per block: 12000 one-row blocks were launch-overhead bound
+    for (int n = blockIdx.x * RPB; n < min((int)(blockIdx.x + 1) * RPB, B * K); ++n) {   // new row
+        const int b = n / K;
+        const int p = b * Kin + (Kin == 1 ? 0 : parents[n]);
+        const float4* src = reinterpret_cast<const float4*>(h_cur + (int64_t)p * H);
+        float4* dst = reinterpret_cast<float4*>(h_next + (int64_t)n * H);
+        for (int c = threadIdx.x; c < H / 4; c += blockDim.x) {
+            const float4 v = src[c];
+            dst[c] = v;
+            split_store4(h_sd, n, c * 4, v);
+        }
+        int64_t id = e_sd.hi ? tokens[n] : 0;
+        if (id < 0 || id >= V) id = 0;
+        for (int c = threadIdx.x; e_sd.hi && c < E / 8; c += blockDim.x) {
+            *reinterpret_cast<uint4*>(e_sd.hi + (int64_t)n * e_sd.ld + c * 8) = *reinterpret_cast<const uint4*>(t_hi + id * ld_t + c * 8);
+            if (e_sd.mode != 2)
+                *reinterpret_cast<uint4*>(e_sd.lo + (int64_t)n * e_sd.ld + c * 8) = *reinterpret_cast<const uint4*>(t_lo + id * ld_t + c * 8);
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         steps_run[0] = step + 1;
@@ -1056,7 +1058,7 @@ int beam_advance(float* h_next, const float* h_cur, const int32_t* parents, int 
 int beam_advance_fused(float* h_next, const float* h_cur, const int32_t* parents, const int64_t* tokens, int B, int K, int Kin,
                        int H, int step, int* done, int* fin_counter, int* steps_run, SplitDst h_sd, SplitDst e_sd,
                        const uint16_t* t_hi, const uint16_t* t_lo, int64_t ld_t, int E, int64_t V, cudaStream_t st) {
-    beam_advance_fused_kernel<<<B * K, 128, 0, st>>>(h_next, h_cur, parents, tokens, B, K, Kin, H, step, done, fin_counter, steps_run,
+    beam_advance_fused_kernel<<<(B * K + 3) / 4, 128, 0, st>>>(h_next, h_cur, parents, tokens, B, K, Kin, H, step, done, fin_counter, steps_run,
                                                      h_sd, e_sd, t_hi, t_lo, ld_t, E, V);
     VAG_LAUNCH_CHECK();
     return VAG_OK;
