@@ -637,6 +637,14 @@ __device__ __forceinline__ void tcgen05_commit_pair(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// One elected lane of a fully converged warp (the MMA-issuing warp runs its loops warp-uniformly so that descriptors and
+// barrier addresses stay in uniform registers; only the tcgen05 instructions themselves are predicated on this lane —
+// issuing from inside an `if (lane == 0)` region makes the compiler wrap EVERY MMA in an elect / R2UR broadcast loop).
+__device__ __forceinline__ bool elect_one_lane() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 template <bool F16>
 __device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     if (F16)
@@ -765,7 +773,7 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
             if (dbg && pair == 0) { dbg[rank * 16 + 0] = VAG_TCLK() - t_begin; dbg[rank * 16 + 1] = t_wait; dbg[rank * 16 + 2] = g; }
         }
     } else if (warp == 1) {
-        if (rank == 0 && lane == 0) {
+        if (rank == 0) {   // the whole warp walks the loops (uniform values); one elected lane issues the tcgen05 instructions
             uint32_t g = 0, it = 0;
             long long t_we = 0, t_wf = 0, t_begin = VAG_TCLK();
             for (int tile = pair; tile < n_tiles; tile += n_pairs, ++it) {
@@ -787,20 +795,23 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
                     const uint32_t st = smem_u32(smem + s * STG);
                     const uint64_t d_ah = make_smem_desc<Q_ROWB>(st), d_al = make_smem_desc<Q_ROWB>(st + Q_A_BYTES);
                     const uint64_t d_bh = make_smem_desc<Q_ROWB>(st + A_USED), d_bl = make_smem_desc<Q_ROWB>(st + A_USED + Q_B_BYTES);
+                    if (elect_one_lane()) {
 #pragma unroll
-                    for (int j = 0; j < BK / UK; ++j) {
-                        const uint64_t adv = (uint64_t)((j * 32) >> 4);
-                        if (SPLIT) {
-                            umma_pair<F16>(d_cross, d_al + adv, d_bh + adv, IDESC, (kb | j) != 0);
-                            umma_pair<F16>(d_cross, d_ah + adv, d_bl + adv, IDESC, 1);
+                        for (int j = 0; j < BK / UK; ++j) {
+                            const uint64_t adv = (uint64_t)((j * 32) >> 4);
+                            if (SPLIT) {
+                                umma_pair<F16>(d_cross, d_al + adv, d_bh + adv, IDESC, (kb | j) != 0);
+                                umma_pair<F16>(d_cross, d_ah + adv, d_bl + adv, IDESC, 1);
+                            }
+                            umma_pair<F16>(d_main, d_ah + adv, d_bh + adv, IDESC, (kb | j) != 0);
                         }
-                        umma_pair<F16>(d_main, d_ah + adv, d_bh + adv, IDESC, (kb | j) != 0);
+                        tcgen05_commit_pair(&empty_bar[s]);
+                        if (kb == n_kb - 1) tcgen05_commit_pair(&tfull_bar[a]);
                     }
-                    tcgen05_commit_pair(&empty_bar[s]);
+                    __syncwarp();
                 }
-                tcgen05_commit_pair(&tfull_bar[a]);
             }
-            if (dbg && pair == 0) { dbg[4] = VAG_TCLK() - t_begin; dbg[5] = t_we; dbg[6] = t_wf; dbg[7] = it; }
+            if (dbg && pair == 0 && lane == 0) { dbg[4] = VAG_TCLK() - t_begin; dbg[5] = t_we; dbg[6] = t_wf; dbg[7] = it; }
         } else if (rank == 1 && lane == 0) {
             // the peer's MMA warp is idle: it forwards "my eight epilogue warps have drained buffer a" to the leader with
             // ONE remote arrival per tile, keeping the cluster-scope release off the epilogue warps' critical path
@@ -1083,7 +1094,7 @@ vocab_top2_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_
             if (dbg && pair == 0) { dbg[rank * 16 + 0] = VAG_TCLK() - t_start; dbg[rank * 16 + 1] = t_wait; dbg[rank * 16 + 2] = g; }
         }
     } else if (warp == 1) {
-        if (rank == 0 && lane == 0) {
+        if (rank == 0) {   // the whole warp walks the loops (uniform values); one elected lane issues the tcgen05 instructions
             uint32_t g = 0, it = 0, nb = 0;
             int cur_tn = -1;
             long long t_we = 0, t_wf = 0, t_start = VAG_TCLK();
@@ -1110,21 +1121,26 @@ vocab_top2_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_
                     const uint32_t sb = stationary ? smem_u32(bres + kb * B_KB_BYTES) : st + A_USED;
                     const uint64_t d_ah = make_smem_desc<Q_ROWB>(st), d_al = make_smem_desc<Q_ROWB>(st + Q_A_BYTES);
                     const uint64_t d_bh = make_smem_desc<Q_ROWB>(sb), d_bl = make_smem_desc<Q_ROWB>(sb + Q_B_BYTES);
+                    if (elect_one_lane()) {
 #pragma unroll
-                    for (int j = 0; j < BK / UK; ++j) {
-                        const uint64_t adv = (uint64_t)((j * 32) >> 4);
-                        if (SPLIT) {
-                            umma_pair<F16>(d_cross, d_al + adv, d_bh + adv, IDESC, (kb | j) != 0);
-                            umma_pair<F16>(d_cross, d_ah + adv, d_bl + adv, IDESC, 1);
+                        for (int j = 0; j < BK / UK; ++j) {
+                            const uint64_t adv = (uint64_t)((j * 32) >> 4);
+                            if (SPLIT) {
+                                umma_pair<F16>(d_cross, d_al + adv, d_bh + adv, IDESC, (kb | j) != 0);
+                                umma_pair<F16>(d_cross, d_ah + adv, d_bl + adv, IDESC, 1);
+                            }
+                            umma_pair<F16>(d_main, d_ah + adv, d_bh + adv, IDESC, (kb | j) != 0);
                         }
-                        umma_pair<F16>(d_main, d_ah + adv, d_bh + adv, IDESC, (kb | j) != 0);
+                        tcgen05_commit_pair(&empty_bar[s]);
+                        if (kb == n_kb - 1) {
+                            tcgen05_commit_pair(&tfull_bar[a]);
+                            if (stationary && (tile + 1 == t_end || (tile + 1) / tiles_m != tn)) tcgen05_commit_pair(bempty_bar);
+                        }
                     }
-                    tcgen05_commit_pair(&empty_bar[s]);
+                    __syncwarp();
                 }
-                tcgen05_commit_pair(&tfull_bar[a]);
-                if (stationary && (tile + 1 == t_end || (tile + 1) / tiles_m != tn)) tcgen05_commit_pair(bempty_bar);
             }
-            if (dbg && pair == 0) { dbg[4] = VAG_TCLK() - t_start; dbg[5] = t_we; dbg[6] = t_wf; dbg[7] = it; }
+            if (dbg && pair == 0 && lane == 0) { dbg[4] = VAG_TCLK() - t_start; dbg[5] = t_we; dbg[6] = t_wf; dbg[7] = it; }
         } else if (rank == 1 && lane == 0) {
             uint32_t it = 0;   // forward "my sixteen epilogue warps have drained buffer a" to the leader
             for (int tile = t_begin; tile < t_end; ++tile, ++it) {
@@ -1184,7 +1200,13 @@ vocab_top2_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_
             t_ld += VAG_TCLK() - t0;
             t0 = VAG_TCLK();
             float4 out = make_float4(-INFINITY, 0.f, -INFINITY, __int_as_float((int)0xFFFFFFFFu));
-#ifdef VAG_EXP_NOMATH
+#ifdef VAG_EXP_NOMATH1
+            if (n_valid > 0 && lg == 1) { float acc = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc += x[j];
+                out.x = acc; }
+            if (n_valid > 0 && lg != 1) {
+#elif defined(VAG_EXP_NOMATH)
             if (n_valid > 0) { float acc = 0.f;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) acc += x[j];
