@@ -122,6 +122,14 @@ __device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// One elected lane of a fully converged warp (the MMA-issuing warp runs its loops warp-uniformly so that descriptors and
+// barrier addresses stay in uniform registers; only the tcgen05 instructions themselves are predicated on this lane —
+// issuing from inside an `if (lane == 0)` region makes the compiler wrap EVERY MMA in an elect / R2UR broadcast loop).
+__device__ __forceinline__ bool elect_one_lane() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 template <bool F16>
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     if (F16)
@@ -234,7 +242,7 @@ linear_split3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_co
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // warp-uniform loop, one elected lane issues (see elect_one_lane)
             for (int kb = 0; kb < n_kb; ++kb) {
                 const int s = kb % Cfg::STAGES;
                 const uint32_t ph = (kb / Cfg::STAGES) & 1;
@@ -245,16 +253,19 @@ linear_split3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_co
                 const uint64_t d_al = make_smem_desc<ROWB>(st + Cfg::A_BYTES);
                 const uint64_t d_bh = make_smem_desc<ROWB>(st + 2 * Cfg::A_BYTES);
                 const uint64_t d_bl = make_smem_desc<ROWB>(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+                if (elect_one_lane()) {
 #pragma unroll
-                for (int j = 0; j < Cfg::BK / Cfg::UK; ++j) {
-                    const uint64_t adv = (uint64_t)((j * 32) >> 4);  // 32 B per k-step inside the 128 B swizzle row
-                    umma<F16>(tmem_base + BN, d_al + adv, d_bh + adv, Cfg::IDESC, (kb | j) != 0);  // cross terms
-                    umma<F16>(tmem_base + BN, d_ah + adv, d_bl + adv, Cfg::IDESC, 1);
-                    umma<F16>(tmem_base, d_ah + adv, d_bh + adv, Cfg::IDESC, (kb | j) != 0);       // main term
+                    for (int j = 0; j < Cfg::BK / Cfg::UK; ++j) {
+                        const uint64_t adv = (uint64_t)((j * 32) >> 4);  // 32 B per k-step inside the 128 B swizzle row
+                        umma<F16>(tmem_base + BN, d_al + adv, d_bh + adv, Cfg::IDESC, (kb | j) != 0);  // cross terms
+                        umma<F16>(tmem_base + BN, d_ah + adv, d_bl + adv, Cfg::IDESC, 1);
+                        umma<F16>(tmem_base, d_ah + adv, d_bh + adv, Cfg::IDESC, (kb | j) != 0);       // main term
+                    }
+                    tcgen05_commit(&empty_bar[s]);  // frees the slot once the MMAs above have read it
+                    if (kb == n_kb - 1) tcgen05_commit(tmem_full_bar);      // accumulator complete
                 }
-                tcgen05_commit(&empty_bar[s]);  // frees the slot once the MMAs above have read it
+                __syncwarp();
             }
-            tcgen05_commit(tmem_full_bar);      // accumulator complete
         }
     } else {
         // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
@@ -438,7 +449,7 @@ linear_split3_persistent_kernel(const __grid_constant__ CUtensorMap map_xh, cons
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // warp-uniform loops, one elected lane issues (see elect_one_lane)
             uint32_t g = 0, it = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
                 const uint32_t a = it & 1;
@@ -452,18 +463,21 @@ linear_split3_persistent_kernel(const __grid_constant__ CUtensorMap map_xh, cons
                     const uint32_t st = smem_u32(smem + s * P_STAGE_BYTES);
                     const uint64_t d_ah = make_smem_desc<64>(st), d_al = make_smem_desc<64>(st + T_BYTES);
                     const uint64_t d_bh = make_smem_desc<64>(st + 2 * T_BYTES), d_bl = make_smem_desc<64>(st + 3 * T_BYTES);
+                    if (elect_one_lane()) {
 #pragma unroll
-                    for (int j = 0; j < BK / UK; ++j) {
-                        const uint64_t adv = (uint64_t)((j * 32) >> 4);
-                        if (SPLIT) {
-                            umma<F16>(d_cross, d_al + adv, d_bh + adv, IDESC, (kb | j) != 0);
-                            umma<F16>(d_cross, d_ah + adv, d_bl + adv, IDESC, 1);
+                        for (int j = 0; j < BK / UK; ++j) {
+                            const uint64_t adv = (uint64_t)((j * 32) >> 4);
+                            if (SPLIT) {
+                                umma<F16>(d_cross, d_al + adv, d_bh + adv, IDESC, (kb | j) != 0);
+                                umma<F16>(d_cross, d_ah + adv, d_bl + adv, IDESC, 1);
+                            }
+                            umma<F16>(d_main, d_ah + adv, d_bh + adv, IDESC, (kb | j) != 0);
                         }
-                        umma<F16>(d_main, d_ah + adv, d_bh + adv, IDESC, (kb | j) != 0);
+                        tcgen05_commit(&empty_bar[s]);
+                        if (kb == n_kb - 1) tcgen05_commit(&tfull_bar[a]);
                     }
-                    tcgen05_commit(&empty_bar[s]);
+                    __syncwarp();
                 }
-                tcgen05_commit(&tfull_bar[a]);
             }
         }
     } else {
@@ -636,14 +650,6 @@ __device__ __forceinline__ void tcgen05_commit_pair(uint64_t* bar) {
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// One elected lane of a fully converged warp (the MMA-issuing warp runs its loops warp-uniformly so that descriptors and
-// barrier addresses stay in uniform registers; only the tcgen05 instructions themselves are predicated on this lane —
-// issuing from inside an `if (lane == 0)` region makes the compiler wrap EVERY MMA in an elect / R2UR broadcast loop).
-__device__ __forceinline__ bool elect_one_lane() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-    return pred != 0;
 }
 template <bool F16>
 __device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
