@@ -303,6 +303,15 @@ int vag_translation_loss_f32(const float* loss_rows, const int64_t* tgt, int B, 
 /* C[m,n] = alpha·Σ_k A[m·sam + k·sak]·B[k·sbk + n·sbn] + beta·C[m,n]: dX = dY·W and dW = dYᵀ·X of every nn.Linear / GRU matrix. */
 int vag_gemm_f32(float* C, int64_t ldc, const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk,
                  int64_t sbn, int M, int N, int K, float alpha, float beta, vag_stream_t stream);
+
+/* vag_gemm_f32 with a caller-owned workspace (vag_gemm_tc_workspace_bytes): contractions with M, N >= 64 run on the tcgen05
+   path — operands are split into tensor-core planes inside the workspace, transposing those that are not contraction-
+   contiguous — everything else falls through to vag_gemm_f32.  Replaces the torch.mm calls autograd issues for the
+   weight / input gradients of every nn.Linear and nn.GRU on the path (layers/NMT_Decoder.py:121-143 under backward()). */
+size_t vag_gemm_tc_workspace_bytes(int M, int N, int K);
+int vag_gemm_tc_f32(float* C, int64_t ldc, const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk,
+                    int64_t sbn, int M, int N, int K, float alpha, float beta, void* workspace, size_t workspace_bytes,
+                    vag_stream_t stream);
 /* GRU cell backward from the saved pre-activations: dgi, dgh [rows,3H] and dh_prev [rows,H] = dh·z (the caller adds dgh·W_hh). */
 int vag_gru_gates_bwd_f32(float* dgi, float* dgh, float* dh_prev, const float* dh, int64_t ld_dh, const float* gi,
                           const float* gh, const float* h_prev, int64_t ld_hp, int rows, int H, vag_stream_t stream);

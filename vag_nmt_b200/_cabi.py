@@ -99,6 +99,8 @@ SIGNATURES = {
     "vag_row_argmax_f32": (I, [P, I64, I, I64, P, P]),
     "vag_translation_loss_f32": (I, [P, P, I, I, P, F, P, P]),
     "vag_gemm_f32": (I, [P, I64, P, I64, I64, P, I64, I64, I, I, I, F, F, P]),
+    "vag_gemm_tc_workspace_bytes": (SZ, [I, I, I]),
+    "vag_gemm_tc_f32": (I, [P, I64, P, I64, I64, P, I64, I64, I, I, I, F, F, P, SZ, P]),
     "vag_gru_gates_bwd_f32": (I, [P, P, P, P, I64, P, P, P, I64, I, I, P]),
     "vag_attention_bwd_f32": (I, [P, I64, P, P, P, P, I64, P, P, I64, P, P, P, P, I, I, I, I, P]),
     "vag_nll_bwd_f32": (I, [P, I64, P, I64, P, P, P, P, I, I64, P]),

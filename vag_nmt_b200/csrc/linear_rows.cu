@@ -1,0 +1,156 @@
+// Contractions with at most 32 rows (one training batch per GPU: the recurrent steps of the encoder / decoder loops,
+// forward and backward).  These are weight-streaming problems — 32 x K x N with K, N in 256..1536: 1-6 MB of weights,
+// 25-100 MFLOP — whose cost is latency, not bytes or FLOPs, so the kernel is shaped for one short wave of CTAs with
+// every load in flight early:
+//   * lane = row (32 rows = one warp), so a weight element is a warp-uniform (broadcast) load and is read exactly
+//     once per CTA;
+//   * a CTA owns BN = 8 (or 4) output columns and its 16 warps split the contraction range; partial sums meet in
+//     shared memory, the epilogue (bias, accumulate, tanh) runs on the first BN·32 threads;
+//   * WK = true : W(c, k) = w[c·ldw + k]   (y = x·Wᵀ, the forward layout,  layers/NMT_Decoder.py:121-137)
+//     WK = false: W(c, k) = w[k·ldw + c]   (dx = dy·W, the same weight read for back-propagation through time).
+#include "common.cuh"
+#include <cuda_bf16.h>
+
+namespace vag {
+
+int gemm_mode();
+
+namespace {
+
+__device__ __forceinline__ float rbf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+template <bool RB>
+__device__ __forceinline__ float4 rnd4(float4 v) {
+    if (RB) { v.x = rbf16(v.x); v.y = rbf16(v.y); v.z = rbf16(v.z); v.w = rbf16(v.w); }
+    return v;
+}
+
+constexpr int ROWS32_WARPS = 16;
+constexpr int ROWS32_KC = 32;   // contraction indices per warp per pass
+
+// One pass of a warp = a [BN columns] x [32 contraction indices] weight sub-tile: every lane fetches BN/4 DIFFERENT 16-byte
+// pieces of it (coalesced; together with the lane's eight x quads that is the whole pass in flight at once), the tile
+// goes through a per-warp shared-memory slot, and the FMAs read it back as broadcast LDS.128.
+template <int BN, bool WK, bool RB>
+__global__ void __launch_bounds__(ROWS32_WARPS * 32, 2)
+linear_rows32_kernel(float* __restrict__ y, int64_t ldy, const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
+                     int64_t ldw, const float* __restrict__ bias, int rows, int K, int N, int flags) {
+    __shared__ float red[ROWS32_WARPS][32][BN + 1];
+    __shared__ __align__(16) float wtile[ROWS32_WARPS][BN * ROWS32_KC];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int n0 = blockIdx.x * BN;
+    const bool row_ok = lane < rows;
+    const float* xr = x + (int64_t)(row_ok ? lane : 0) * ldx;
+    float* wt = wtile[wid];
+    float acc[BN];
+#pragma unroll
+    for (int c = 0; c < BN; ++c) acc[c] = 0.f;
+    for (int k0 = wid * ROWS32_KC; k0 < K; k0 += ROWS32_WARPS * ROWS32_KC) {
+        // ---- issue every load of the pass
+        float4 wv[BN / 4];
+#pragma unroll
+        for (int i = 0; i < BN / 4; ++i) {
+            if (WK) {   // piece = (column c, quad q) of the [BN][32] tile
+                const int piece = i * 32 + lane, c = piece >> 3, q = piece & 7;
+                const int col = min(n0 + c, N - 1), k = min(k0 + 4 * q, K - 4);
+                wv[i] = __ldg(reinterpret_cast<const float4*>(w + (int64_t)col * ldw + k));
+            } else {    // lane = contraction index, piece i = columns 4i..4i+3 of the [32][BN] tile
+                const int k = min(k0 + lane, K - 1), col = min(n0 + 4 * i, N - 4);
+                wv[i] = __ldg(reinterpret_cast<const float4*>(w + (int64_t)k * ldw + col));
+            }
+        }
+        float4 xv[ROWS32_KC / 4];
+#pragma unroll
+        for (int q = 0; q < ROWS32_KC / 4; ++q) {
+            const int k = k0 + 4 * q;
+            xv[q] = (row_ok && k < K) ? __ldg(reinterpret_cast<const float4*>(xr + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        // ---- weight tile through shared memory (same layout for both weight orientations: [piece] of float4)
+#pragma unroll
+        for (int i = 0; i < BN / 4; ++i) reinterpret_cast<float4*>(wt)[i * 32 + lane] = rnd4<RB>(wv[i]);
+        __syncwarp();
+        if (WK) {
+#pragma unroll
+            for (int c = 0; c < BN; ++c)
+#pragma unroll
+                for (int q = 0; q < ROWS32_KC / 4; ++q) {
+                    const float4 wq = reinterpret_cast<const float4*>(wt)[c * 8 + q];
+                    const float4 xq = rnd4<RB>(xv[q]);
+                    acc[c] = fmaf(xq.x, wq.x, acc[c]);
+                    acc[c] = fmaf(xq.y, wq.y, acc[c]);
+                    acc[c] = fmaf(xq.z, wq.z, acc[c]);
+                    acc[c] = fmaf(xq.w, wq.w, acc[c]);
+                }
+        } else {
+#pragma unroll
+            for (int q = 0; q < ROWS32_KC / 4; ++q) {
+                const float4 xq = rnd4<RB>(xv[q]);
+                const float xs[4] = {xq.x, xq.y, xq.z, xq.w};
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                    for (int i = 0; i < BN / 4; ++i) {
+                        const float4 wq = reinterpret_cast<const float4*>(wt)[i * 32 + 4 * q + kk];
+                        acc[4 * i + 0] = fmaf(xs[kk], wq.x, acc[4 * i + 0]);
+                        acc[4 * i + 1] = fmaf(xs[kk], wq.y, acc[4 * i + 1]);
+                        acc[4 * i + 2] = fmaf(xs[kk], wq.z, acc[4 * i + 2]);
+                        acc[4 * i + 3] = fmaf(xs[kk], wq.w, acc[4 * i + 3]);
+                    }
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int c = 0; c < BN; ++c) red[wid][lane][c] = acc[c];
+    __syncthreads();
+    if (threadIdx.x < 32 * BN) {
+        const int row = threadIdx.x / BN, c = threadIdx.x % BN;
+        const int col = n0 + c;
+        if (row < rows && col < N) {
+            float v = 0.f;
+#pragma unroll
+            for (int q = 0; q < ROWS32_WARPS; ++q) v += red[q][row][c];
+            if (bias) v += bias[col];
+            float* dst = y + (int64_t)row * ldy + col;
+            if (flags & VAG_LIN_ACCUMULATE) v = *dst + v;
+            if (flags & VAG_LIN_TANH) v = tanhf(v);
+            *dst = v;
+        }
+    }
+}
+
+template <bool WK, bool RB>
+int launch_rows32(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, int rows,
+                  int K, int N, int flags, cudaStream_t st) {
+    // enough CTAs for one wave on 148 SMs: 8 columns per CTA for wide outputs, 4 otherwise
+    if (N >= 960) {
+        linear_rows32_kernel<8, WK, RB><<<ceil_div(N, 8), ROWS32_WARPS * 32, 0, st>>>(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags);
+    } else {
+        linear_rows32_kernel<4, WK, RB><<<ceil_div(N, 4), ROWS32_WARPS * 32, 0, st>>>(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags);
+    }
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
+}  // namespace
+
+// Eligibility: rows <= 32, 16-byte aligned operands with pitches that keep float4 loads aligned, K a multiple of 4
+// (and, for the transposed weight read, N a multiple of 4).
+bool rows32_ok(const float* x, int64_t ldx, const float* w, int64_t ldw, int rows, int K, int N, bool wk) {
+    if (rows < 1 || rows > 32 || K < 64 || N < 32 || (K & 3)) return false;
+    if (((uintptr_t)x & 15) || ((uintptr_t)w & 15) || (ldx & 3) || (ldw & 3)) return false;
+    if (!wk && (N & 3)) return false;
+    return true;
+}
+
+// y[rows, N] (+)= x[rows, K] · W(c, k)  (+ bias) (tanh);  round_bf16: operands rounded to bfloat16 first (bf16 mode)
+int linear_rows32(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, int rows,
+                  int K, int N, int flags, bool wk, bool round_bf16, cudaStream_t st) {
+    if (wk) {
+        if (round_bf16) return launch_rows32<true, true>(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags, st);
+        return launch_rows32<true, false>(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags, st);
+    }
+    if (round_bf16) return launch_rows32<false, true>(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags, st);
+    return launch_rows32<false, false>(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags, st);
+}
+
+}  // namespace vag

@@ -11,6 +11,9 @@
 namespace vag {
 
 int gemm_mode();
+bool rows32_ok(const float* x, int64_t ldx, const float* w, int64_t ldw, int rows, int K, int N, bool wk);
+int linear_rows32(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, int rows,
+                  int K, int N, int flags, bool wk, bool round_bf16, cudaStream_t st);
 
 template <int BM, int BN, int BK, int TM, int TN>
 struct SimtCfg {
@@ -240,6 +243,7 @@ static int launch_simt(float* y, int64_t ldy, const float* x, int64_t ldx, const
 int linear_simt(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias,
                 int rows, int K, int N, int flags, cudaStream_t st) {
     const int sms = num_sms();
+    if (rows32_ok(x, ldx, w, ldw, rows, K, N, true)) return linear_rows32(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags, true, gemm_mode() == 2, st);
     if (rows <= 32 && N >= 64 && K >= 64) {   // weight-streaming regime: one warp per output feature, K across the lanes
         dim3 grid(ceil_div(N, 8), ceil_div(rows, 8));
         if (gemm_mode() == 2) linear_skinny_kernel<8, true><<<grid, 256, 0, st>>>(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags);

@@ -9,6 +9,9 @@
 #include <vector>
 
 namespace vag {
+bool rows32_ok(const float* x, int64_t ldx, const float* w, int64_t ldw, int rows, int K, int N, bool wk);
+int linear_rows32(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, int rows,
+                  int K, int N, int flags, bool wk, bool round_bf16, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------ generic contraction
 // C[m, n] = alpha · Σ_k A(m, k)·B(k, n) + beta · C[m, n],   A(m,k) = A[m·sam + k·sak],  B(k,n) = B[k·sbk + n·sbn]
@@ -355,6 +358,13 @@ extern "C" int vag_gemm_f32(float* C, int64_t ldc, const float* A, int64_t sam, 
     VAG_REQUIRE(M >= 0 && N >= 0 && K >= 0 && ldc >= N, "vag_gemm_f32: bad shape");
     if (M == 0 || N == 0) return VAG_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    if (alpha == 1.f && (beta == 0.f || beta == 1.f) && sak == 1 && (sbk == 1 || sbn == 1) && M <= 32) {
+        // batch-sized row count: the weight-streaming kernel (linear_rows.cu); B(k, n) is the weight read k-fast or n-fast
+        const bool wk = sbk == 1;
+        const int64_t ldw = wk ? sbn : sbk;
+        if (rows32_ok(A, sam, B, ldw, M, K, N, wk))
+            return linear_rows32(C, ldc, A, sam, B, ldw, nullptr, M, K, N, beta == 1.f ? VAG_LIN_ACCUMULATE : 0, wk, false, st);
+    }
     const bool small_m = M <= 32;
     const int tiles = small_m ? ceil_div(N, 64) * ceil_div(M, 32) : ceil_div(N, 64) * ceil_div(M, 64);
     int splits = 1;
@@ -531,11 +541,105 @@ extern "C" int vag_clip_adam_multi_f32(const vag_optim_tensor* tensors_device, i
 namespace vag {
 int row_argmax(const float* logits, int64_t ld, int rows, int64_t V, int64_t* out, int64_t out_stride, int64_t* next_in,
                cudaStream_t st);
+// ---- tensor-core route of the batched backward contractions (dW = dyᵀ·x over all batch·time rows, dx = dy·W) --------------
+// tc_gemm wants both operands contraction-contiguous ([M, Kc] and [N, Kc]); an operand stored the other way round goes
+// through the transposing split (tc_split_t).  Scratch for the operand planes comes from the composite's workspace.
+struct TcScratch {
+    char* base = nullptr;
+    size_t cap = 0;
+};
+static thread_local TcScratch g_tc_scratch;
+struct TcScratchScope {
+    TcScratch prev;
+    TcScratchScope(void* p, size_t n) : prev(g_tc_scratch) { g_tc_scratch = TcScratch{(char*)p, n}; }
+    ~TcScratchScope() { g_tc_scratch = prev; }
+};
+__global__ void add2d_kernel(float* __restrict__ C, int64_t ldc, const float* __restrict__ T, int M, int N) {
+    const int64_t total = (int64_t)M * (N >> 2);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int m = (int)(i / (N >> 2)), n = (int)(i % (N >> 2)) * 4;
+        float4 c = *reinterpret_cast<float4*>(C + (int64_t)m * ldc + n);
+        const float4 t = *reinterpret_cast<const float4*>(T + (int64_t)m * N + n);
+        c.x += t.x; c.y += t.y; c.z += t.z; c.w += t.w;
+        *reinterpret_cast<float4*>(C + (int64_t)m * ldc + n) = c;
+    }
+}
+// → 1: ran on the tensor cores, 0: not eligible (caller falls back to the FFMA kernel), < 0: error
+static int gemm_tc_try(float* C, int64_t ldc, const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn,
+                       int M, int N, int K, float beta, char* scratch, size_t cap, cudaStream_t st, bool a_padded = false) {
+    // a_padded: A is stored [M, K] with rows zero-padded up to the next multiple of 4 past K (K itself need not be one)
+    if (!scratch || !tc_enabled() || M < 64 || N < 64 || K < 32 || (N & 3)) return 0;
+    if (!(beta == 0.f || beta == 1.f)) return 0;
+    const bool xt = sak != 1, wt = sbk != 1;     // operand stored [Kc, rows] instead of [rows, Kc]
+    if ((xt && sam != 1) || (wt && sbn != 1)) return 0;
+    const int64_t ldx = xt ? sak : sam, ldw = wt ? sbk : sbn;
+    if (!xt && (!GemmCtx::ptr_ok(A, ldx) || ((K & 3) && !a_padded))) return 0;
+    if (a_padded && xt) return 0;
+    if (!wt && (!GemmCtx::ptr_ok(B, ldw) || (K & 3))) return 0;
+    if (!GemmCtx::ptr_ok(C, ldc)) return 0;
+    const int Kp = (K + 7) / 8 * 8;
+    const size_t esz = (size_t)tc_elem_bytes();
+    Arena ar(scratch, cap);
+    char* xh = ar.take<char>((size_t)M * Kp * esz);
+    char* xl = ar.take<char>((size_t)M * Kp * esz);
+    char* wh = ar.take<char>((size_t)N * Kp * esz);
+    char* wl = ar.take<char>((size_t)N * Kp * esz);
+    float* tmp = beta == 1.f ? ar.take<float>((size_t)M * N) : nullptr;
+    if (ar.overflow) return 0;
+    if (xt) {
+        VAG_TRY(tc_split_t(A, ldx, K, M, xh, xl, Kp, Kp, st));
+    } else {
+        if (Kp != (K + 3) / 4 * 4) {
+            VAG_CUDA(cudaMemsetAsync(xh, 0, (size_t)M * Kp * esz, st));
+            VAG_CUDA(cudaMemsetAsync(xl, 0, (size_t)M * Kp * esz, st));
+        }
+        VAG_TRY(tc_split(A, ldx, M, (K + 3) / 4 * 4, xh, xl, Kp, 0, st));
+    }
+    if (wt) {
+        VAG_TRY(tc_split_t(B, ldw, K, N, wh, wl, Kp, Kp, st));
+    } else {
+        if (Kp != K) {
+            VAG_CUDA(cudaMemsetAsync(wh, 0, (size_t)N * Kp * esz, st));
+            VAG_CUDA(cudaMemsetAsync(wl, 0, (size_t)N * Kp * esz, st));
+        }
+        VAG_TRY(tc_split(B, ldw, N, K, wh, wl, Kp, 0, st));
+    }
+    VAG_TRY(tc_gemm(tmp ? tmp : C, tmp ? N : ldc, xh, xl, Kp, wh, wl, Kp, nullptr, M, Kp, N, 0, st, nullptr, nullptr));
+    if (tmp) {
+        add2d_kernel<<<grid_for((int64_t)M * N / 4), 256, 0, st>>>(C, ldc, tmp, M, N);
+        VAG_LAUNCH_CHECK();
+    }
+    return 1;
+}
 static int gemm_g(float* C, int64_t ldc, const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn, int M,
                   int N, int K, float beta, cudaStream_t st) {
+    const int r = gemm_tc_try(C, ldc, A, sam, sak, B, sbk, sbn, M, N, K, beta, g_tc_scratch.base, g_tc_scratch.cap, st);
+    if (r != 0) return r < 0 ? r : VAG_OK;
     return vag_gemm_f32(C, ldc, A, sam, sak, B, sbk, sbn, M, N, K, 1.0f, beta, (vag_stream_t)st);
 }
+// scratch the tensor-core route may need for one contraction of the given logical shape
+static size_t gemm_tc_scratch_bytes(int64_t M, int64_t N, int64_t K) {
+    const int64_t Kp = (K + 7) / 8 * 8;
+    return 2 * align_up((size_t)M * Kp * 4, 256) + 2 * align_up((size_t)N * Kp * 4, 256) + align_up((size_t)M * N * 4, 256) + 4096;
+}
 }  // namespace vag
+
+extern "C" size_t vag_gemm_tc_workspace_bytes(int M, int N, int K) { return gemm_tc_scratch_bytes(M, N, K); }
+
+/* vag_gemm_f32 with a caller-owned workspace: large contractions run on the tcgen05 path (operands are split, and
+   transposed where they are not contraction-contiguous, into the workspace); everything else takes the FFMA kernels. */
+extern "C" int vag_gemm_tc_f32(float* C, int64_t ldc, const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk,
+                               int64_t sbn, int M, int N, int K, float alpha, float beta, void* workspace, size_t workspace_bytes,
+                               vag_stream_t stream) {
+    VAG_REQUIRE(C && A && B, "vag_gemm_tc_f32: null pointer");
+    VAG_REQUIRE(M >= 0 && N >= 0 && K >= 0 && ldc >= N, "vag_gemm_tc_f32: bad shape");
+    if (M == 0 || N == 0) return VAG_OK;
+    if (alpha == 1.f) {
+        const int r = gemm_tc_try(C, ldc, A, sam, sak, B, sbk, sbn, M, N, K, beta, (char*)workspace, workspace_bytes, (cudaStream_t)stream);
+        if (r != 0) return r < 0 ? r : VAG_OK;
+    }
+    return vag_gemm_f32(C, ldc, A, sam, sak, B, sbk, sbn, M, N, K, alpha, beta, stream);
+}
 
 extern "C" size_t vag_decoder_seq_workspace_bytes(int B, int T, int Tt, int E, int H, int C, int64_t V) {
     const int64_t R = (int64_t)B * Tt;
@@ -544,7 +648,8 @@ extern "C" size_t vag_decoder_seq_workspace_bytes(int B, int T, int Tt, int E, i
                  GemmCtx::split_bytes(V, E) + GemmCtx::split_bytes(C, C) + 65536;
     fwd += GemmCtx::split_bytes(R, E) * 2 + GemmCtx::split_bytes(R, H) + GemmCtx::split_bytes(R, C) + GemmCtx::split_bytes((int64_t)B * T, C) + 65536;
     // backward scratch: dlogits [R, V], d_t / du [R, E] x2, dH2_dir [R, H], dE [R, E], dC_dir [R, C], per-step grads
-    size_t bwd = (size_t)R * V * 4 + (size_t)R * E * 4 * 3 + (size_t)R * H * 4 * 2 + (size_t)R * C * 4 * 2 + (size_t)R * 3 * H * 4 * 4 +
+    size_t bwd = (size_t)R * (V + 4) * 4 + gemm_tc_scratch_bytes(std::max<int64_t>(V, 3 * H), std::max<int64_t>({(int64_t)C, (int64_t)3 * H, (int64_t)E}), std::max<int64_t>({(int64_t)R, (int64_t)B * T, (int64_t)3 * H})) +
+                 gemm_tc_scratch_bytes(std::max<int64_t>(R, (int64_t)B * T), C, std::max<int64_t>(V + 8, 3 * H)) + (size_t)R * H * 4 + (size_t)R * E * 4 * 3 + (size_t)R * H * 4 * 2 + (size_t)R * C * 4 * 2 + (size_t)R * 3 * H * 4 * 4 +
                  (size_t)B * T * C * 4 + (size_t)B * H * 4 * 4 + (size_t)B * 3 * H * 4 * 4 + 65536;
     return fwd > bwd ? fwd : bwd;
 }
@@ -642,7 +747,14 @@ extern "C" int vag_decoder_seq_bwd_f32(const vag_decoder_weights* w, const float
     const int R = B * Tt;
     const int64_t ldl = s->ld_logits;
     Arena ar(workspace, workspace_bytes);
-    float* dlogits = ar.take<float>((size_t)R * V);
+    const int64_t ldd = (V + 3) / 4 * 4;                      // dlogits pitch: rows zero-padded to a multiple of 4
+    float* dlogits = ar.take<float>((size_t)R * ldd);
+    float* hprev_all = ar.take<float>((size_t)R * H);         // [h0; h2_0 … h2_{Tt-2}]: what gru_1 saw as its previous state
+    const size_t tcs_bytes = gemm_tc_scratch_bytes(std::max<int64_t>(V, 3 * H), std::max<int64_t>({(int64_t)C, (int64_t)3 * H, (int64_t)E}),
+                                                   std::max<int64_t>({(int64_t)R, (int64_t)B * T, (int64_t)3 * H})) +
+                             gemm_tc_scratch_bytes(std::max<int64_t>(R, (int64_t)B * T), C, std::max<int64_t>(V + 8, 3 * H));
+    char* tcs = ar.take<char>(tcs_bytes);
+    TcScratchScope tc_scope(tcs, tcs ? tcs_bytes : 0);
     float* d_t = ar.take<float>((size_t)R * E);
     float* du = ar.take<float>((size_t)R * E);
     float* dh2_dir = ar.take<float>((size_t)R * H);
@@ -662,14 +774,19 @@ extern "C" int vag_decoder_seq_bwd_f32(const vag_decoder_weights* w, const float
         return VAG_ERR_WORKSPACE;
     }
     // ---- batched over all steps: vocabulary projection and read-out
+    if (ldd != V) VAG_CUDA(cudaMemsetAsync(dlogits, 0, sizeof(float) * (size_t)R * ldd, st));
     for (int t = 0; t < Tt; ++t)
-        VAG_TRY(vag_nll_bwd_f32(dlogits + (size_t)t * B * V, V, s->logits_all + (size_t)t * B * ldl, ldl, s->lse_all + (size_t)t * B,
+        VAG_TRY(vag_nll_bwd_f32(dlogits + (size_t)t * B * ldd, ldd, s->logits_all + (size_t)t * B * ldl, ldl, s->lse_all + (size_t)t * B,
                                 tgt_t + (size_t)t * B, nll_weight, dloss_rows, B, V, vs));
-    VAG_TRY(gemm_g(d_t, E, dlogits, V, 1, w->out_w, E, 1, R, E, (int)V, 0.f, st));                 // d_t = dlogits · out_w
+    {   // d_t = dlogits · out_w   (contraction over the vocabulary: rows of dlogits are padded, out_w is split transposed)
+        const int r = gemm_tc_try(d_t, E, dlogits, ldd, 1, w->out_w, E, 1, R, E, (int)V, 0.f, g_tc_scratch.base, g_tc_scratch.cap, st, true);
+        if (r < 0) return r;
+        if (r == 0) VAG_TRY(gemm_g(d_t, E, dlogits, ldd, 1, w->out_w, E, 1, R, E, (int)V, 0.f, st));
+    }
     float* d_out_w = tied ? g->emb : g->out_w;                                                       // tied: accumulate into dEmb later
     VAG_CUDA(cudaMemsetAsync(g->emb, 0, sizeof(float) * (size_t)V * E, st));
-    VAG_TRY(gemm_g(d_out_w, E, dlogits, 1, V, s->t_all, E, 1, (int)V, E, R, 0.f, st));              // dlogitsᵀ · t_all
-    VAG_TRY(vag_colsum_f32(g->out_b, dlogits, V, R, (int)V, 0, vs));
+    VAG_TRY(gemm_g(d_out_w, E, dlogits, 1, ldd, s->t_all, E, 1, (int)V, E, R, 0.f, st));            // dlogitsᵀ · t_all
+    VAG_TRY(vag_colsum_f32(g->out_b, dlogits, ldd, R, (int)V, 0, vs));
     if (out_mask) {
         tanh_dropout_bwd_kernel<<<grid_for((int64_t)R * E), 256, 0, st>>>(du, d_t, s->t_all, out_mask, (int64_t)R * E);
         VAG_LAUNCH_CHECK();
@@ -722,9 +839,10 @@ extern "C" int vag_decoder_seq_bwd_f32(const vag_decoder_weights* w, const float
     VAG_TRY(gemm_g(g->attn_h_w, H, dq_all, 1, C, s->h1_all, H, 1, C, H, R, 0.f, st));
     VAG_TRY(gemm_g(g->gru1_w_ih, E, dgi1_all, 1, 3 * H, s->e_all, E, 1, 3 * H, E, R, 0.f, st));
     VAG_TRY(vag_colsum_f32(g->gru1_b_ih, dgi1_all, 3 * H, R, 3 * H, 0, vs));
-    VAG_TRY(gemm_g(g->gru1_w_hh, H, dgh1_all, 1, 3 * H, h0, H, 1, 3 * H, H, B, 0.f, st));
+    VAG_CUDA(cudaMemcpyAsync(hprev_all, h0, sizeof(float) * (size_t)B * H, cudaMemcpyDeviceToDevice, st));
     if (Tt > 1)
-        VAG_TRY(gemm_g(g->gru1_w_hh, H, dgh1_all + (size_t)B * 3 * H, 1, 3 * H, s->h2_all, H, 1, 3 * H, H, (Tt - 1) * B, 1.f, st));
+        VAG_CUDA(cudaMemcpyAsync(hprev_all + (size_t)B * H, s->h2_all, sizeof(float) * (size_t)(Tt - 1) * B * H, cudaMemcpyDeviceToDevice, st));
+    VAG_TRY(gemm_g(g->gru1_w_hh, H, dgh1_all, 1, 3 * H, hprev_all, H, 1, 3 * H, H, R, 0.f, st));
     VAG_TRY(vag_colsum_f32(g->gru1_b_hh, dgh1_all, 3 * H, R, 3 * H, 0, vs));
     VAG_TRY(gemm_g(d_e, E, dgi1_all, 3 * H, 1, w->gru1_w_ih, E, 1, R, E, 3 * H, 1.f, st));              // de += dgi1 · W_ih1
     VAG_TRY(vag_embed_bwd_f32(g->emb, d_e, E, tok_in, R, E, V, vs));                                     // (+ dOutW already inside when tied)
@@ -769,7 +887,8 @@ static int copy2d(float* dst, int64_t ld_dst, const float* src, int64_t ld_src, 
 
 extern "C" size_t vag_encoder_train_workspace_bytes(int B, int T, int E, int H) {
     return 2 * (GemmCtx::split_bytes(3 * H, E) + GemmCtx::split_bytes(3 * H, H)) + GemmCtx::split_bytes((int64_t)T * B, E) +
-           (size_t)T * B * 3 * H * 4 * 2 + (size_t)T * B * H * 4 + (size_t)B * H * 4 * 8 + (size_t)B * 3 * H * 4 * 4 + 131072;
+           (size_t)T * B * 3 * H * 4 * 2 + (size_t)T * B * H * 4 + (size_t)B * H * 4 * 8 + (size_t)B * 3 * H * 4 * 4 + 131072 +
+           (size_t)T * B * E * 4 + gemm_tc_scratch_bytes(3 * H, std::max(E, H), (int64_t)T * B) + gemm_tc_scratch_bytes((int64_t)T * B, E, 3 * H);
 }
 
 /* saved: x [T·B, E] time-major embeddings, ids_tm int64 [T·B], gi [2][T, B, 3H], gh [2][T, B, 3H] (zero where inactive) */
@@ -845,6 +964,9 @@ extern "C" int vag_encoder_bwd_f32(const vag_encoder_weights* w, const int32_t* 
     float* carry = ar.take<float>((size_t)B * H);
     float* dh = ar.take<float>((size_t)B * H);
     float* dhp = ar.take<float>((size_t)B * H);
+    const size_t tcs_bytes = gemm_tc_scratch_bytes(3 * H, std::max(E, H), (int64_t)T * B) + gemm_tc_scratch_bytes((int64_t)T * B, E, 3 * H);
+    char* tcs = ar.take<char>(tcs_bytes);
+    TcScratchScope tc_scope(tcs, tcs ? tcs_bytes : 0);
     if (ar.overflow) {
         set_error("vag_encoder_bwd_f32: workspace too small");
         return VAG_ERR_WORKSPACE;

@@ -27,8 +27,14 @@ def gemm(A: torch.Tensor, B: torch.Tensor, trans_a: bool = False, trans_b: bool 
         out = torch.empty(M, N, dtype=torch.float32, device=A.device)
     assert out.shape == (M, N) and out.stride(1) == 1
     with on_device(A.device):
-        check(lib.vag_gemm_f32(out.data_ptr(), out.stride(0), A.data_ptr(), sam, sak, B.data_ptr(), sbk, sbn, M, N, K,
-                               _f(alpha), _f(beta), stream_ptr()))
+        if M >= 64 and N >= 64 and K >= 32:     # large enough for the tensor-core route: hand it a workspace for the operand planes
+            from .ops import workspace
+            ws = workspace(lib.vag_gemm_tc_workspace_bytes(M, N, K), A.device, slot="gemm")
+            check(lib.vag_gemm_tc_f32(out.data_ptr(), out.stride(0), A.data_ptr(), sam, sak, B.data_ptr(), sbk, sbn, M, N, K,
+                                      _f(alpha), _f(beta), ws.data_ptr(), ws.numel(), stream_ptr()))
+        else:
+            check(lib.vag_gemm_f32(out.data_ptr(), out.stride(0), A.data_ptr(), sam, sak, B.data_ptr(), sbk, sbn, M, N, K,
+                                   _f(alpha), _f(beta), stream_ptr()))
     return out
 
 
