@@ -373,15 +373,20 @@ int vag_decoder_seq_bwd_f32(const vag_decoder_weights* w, const float* h0, const
                             size_t workspace_bytes, vag_stream_t stream);
 
 /* Encoder training pair: forward that keeps what BPTT needs and the backward through both directions of the packed
- * bi-GRU.  x [T·B, E] time-major embeddings, ids_tm int64 [T·B], gi / gh [2][T, B, 3H]; gradients like the weights.
- * emb_mask (optional, [T·B, E] time-major, 0 or 1/(1-p)): the embedding dropout of Encoder.py:51-52. */
+ * bi-GRU (layers/Encoder.py:36-65 under autograd).  x [T·B, E] time-major embeddings, ids_tm int64 [T·B], gi / gh
+ * [2][T, B, 3H]; gradients like the weights.  emb_mask (optional, [T·B, E] time-major, 0 or 1/(1-p)): the embedding
+ * dropout of Encoder.py:51-52.
+ * lengths_dev: int32 [B] ON THE DEVICE (required).  Every recurrent step runs on all B rows, both directions in one
+ * launch, and rows whose sentence has ended are masked on the device, so the launch sequence depends on (B, T) only —
+ * a CUDA graph captured around the training step stays valid for any batch of that shape.  lengths_host (optional, may
+ * be NULL) is only validated (1 <= length <= T, sorted in decreasing order like pack_padded_sequence demands). */
 size_t vag_encoder_train_workspace_bytes(int B, int T, int E, int H);
-int vag_encoder_train_fwd_f32(const vag_encoder_weights* w, const int64_t* src, const int32_t* lengths_host, int B, int T,
-                              float* ctx_out, float* x, int64_t* ids_tm, float* gi, float* gh, const float* emb_mask,
-                              void* workspace, size_t workspace_bytes, vag_stream_t stream);
-int vag_encoder_bwd_f32(const vag_encoder_weights* w, const int32_t* lengths_host, int B, int T, const float* ctx,
-                        const float* dctx, const float* x, const int64_t* ids_tm, const float* gi, const float* gh,
-                        float* d_emb, float* const* d_w_ih, float* const* d_w_hh, float* const* d_b_ih,
+int vag_encoder_train_fwd_f32(const vag_encoder_weights* w, const int64_t* src, const int32_t* lengths_host,
+                              const int32_t* lengths_dev, int B, int T, float* ctx_out, float* x, int64_t* ids_tm, float* gi,
+                              float* gh, const float* emb_mask, void* workspace, size_t workspace_bytes, vag_stream_t stream);
+int vag_encoder_bwd_f32(const vag_encoder_weights* w, const int32_t* lengths_host, const int32_t* lengths_dev, int B, int T,
+                        const float* ctx, const float* dctx, const float* x, const int64_t* ids_tm, const float* gi,
+                        const float* gh, float* d_emb, float* const* d_w_ih, float* const* d_w_hh, float* const* d_b_ih,
                         float* const* d_b_hh, const float* emb_mask, void* workspace, size_t workspace_bytes,
                         vag_stream_t stream);
 

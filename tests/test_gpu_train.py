@@ -178,3 +178,55 @@ def test_training_steps_reduce_the_loss():
     losses = [train_imagine_beam(batch.src, batch.tgt, batch.im, batch.src_lengths, model, opt, crit,
                                  vag.PairwiseRankingLoss(margin=0.1), 0.99, 1.0)[0] for _ in range(10)]
     assert losses[-1] < 0.7 * losses[0], losses
+
+
+def _same_shape_batches(cfg, n, B, seed0):
+    """n batches with the SAME padded shapes but different sentence lengths / tokens (what a CUDA graph must survive)."""
+    from vag_nmt_b200 import synthetic
+    out, seed = [], seed0
+    while len(out) < n:
+        bt = synthetic.make_batch(B, cfg["src_size"], cfg["tgt_size"], cfg["im_feats_size"], seed=seed, max_len=9, min_len=2, mean=6.0, std=2.5)
+        seed += 1
+        if not out or (bt.src.shape == out[0].src.shape and bt.tgt.shape == out[0].tgt.shape and bt.src_lengths != out[0].src_lengths):
+            out.append(bt)
+    return out
+
+
+@pytest.mark.parametrize("kind", ["mm", "tm"])
+def test_graphed_step_matches_eager_step(kind):
+    """GraphedTrainStep (zero_grad → forward → backward replayed from one CUDA graph per batch shape, lengths read on the
+    device) must walk the parameters exactly where the eager step driver walks them, over batches whose lengths differ."""
+    import vag_nmt_b200 as vag
+    from vag_nmt_b200 import synthetic
+    from vag_nmt_b200.optim import ClipAdam
+    from vag_nmt_b200.train import GraphedTrainStep, train_imagine_beam, train_nmt
+    cfg = dict(synthetic.TINY)
+    build = build_mm if kind == "mm" else build_tm
+    batches = _same_shape_batches(cfg, 3, 8, 40)
+    w = torch.ones(cfg["tgt_size"])
+    w[0] = 0
+    results = []
+    for graphed in (False, True):
+        model = build(cfg, 11).cuda()
+        crit = torch.nn.NLLLoss(weight=w.cuda(), reduce=False)
+        cv = vag.PairwiseRankingLoss(margin=0.1) if kind == "mm" else None
+        opt = ClipAdam(model, lr=1e-2)
+        stepper = GraphedTrainStep(model, opt, crit, cv, clip=1.0, enabled=True)
+        losses = []
+        for it in range(6):
+            bt = batches[it % len(batches)]
+            if graphed:
+                out = stepper.step(bt.src, bt.src_lengths, bt.tgt, bt.im if kind == "mm" else None, 1.0)
+                losses.append(float(out[0]))
+            elif kind == "mm":
+                losses.append(train_imagine_beam(bt.src, bt.tgt, bt.im, bt.src_lengths, model, opt, crit, cv, 0.99, 1.0)[0])
+            else:
+                losses.append(train_nmt(bt.src, bt.tgt, bt.src_lengths, model, crit, opt, 1.0))
+        if graphed:
+            assert len(stepper._graphs) == 1          # one shape → one capture, replayed for every batch
+        results.append((losses, {k: v.detach().clone() for k, v in model.state_dict().items()}))
+    (l0, p0), (l1, p1) = results
+    for a, b in zip(l0, l1):
+        assert abs(a - b) < 1e-5 * max(1.0, abs(a)), (l0, l1)
+    for k in p0:
+        assert float((p0[k] - p1[k]).abs().max()) < 1e-5, k

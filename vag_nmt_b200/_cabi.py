@@ -115,8 +115,8 @@ SIGNATURES = {
     "vag_decoder_seq_bwd_f32": (I, [P, P, P, P, P, P, P, I, I, I, I, P, P, P, P, P, P, P, SZ, P]),
     "vag_mul_f32": (I, [P, P, I64, P]),
     "vag_encoder_train_workspace_bytes": (SZ, [I, I, I, I]),
-    "vag_encoder_train_fwd_f32": (I, [P, P, P, I, I, P, P, P, P, P, P, P, SZ, P]),
-    "vag_encoder_bwd_f32": (I, [P, P, I, I, P, P, P, P, P, P, P, P, P, P, P, P, P, SZ, P]),
+    "vag_encoder_train_fwd_f32": (I, [P, P, P, P, I, I, P, P, P, P, P, P, P, SZ, P]),
+    "vag_encoder_bwd_f32": (I, [P, P, P, I, I, P, P, P, P, P, P, P, P, P, P, P, P, P, SZ, P]),
     "vag_sumsq_f32": (I, [P, I64, P, P]),
     "vag_sumsq_multi_f32": (I, [P, I, I64, P, P]),
     "vag_clip_adam_multi_f32": (I, [P, I, I64, P, F, F, F, F, I, P]),

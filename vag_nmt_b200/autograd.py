@@ -25,6 +25,31 @@ from . import train_ops as T
 SOS_token = 2
 
 
+def _save_mode(fctx):
+    """Remember the arithmetic mode (fp32-exact split / bf16) the forward ran in.  loss.backward() executes the backward
+    Functions on autograd's device worker thread, where the caller's thread-local vag_set_gemm_mode() is not visible."""
+    fctx.gemm_mode = ops._cabi.lib().vag_get_gemm_mode()
+
+
+def _in_forward_mode(fn):
+    """Run a backward staticmethod under the mode its forward saved."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(fctx, *grads):
+        lib = ops._cabi.lib()
+        mode = getattr(fctx, "gemm_mode", None)
+        prev = lib.vag_get_gemm_mode()
+        if mode is None or mode == prev:
+            return fn(fctx, *grads)
+        lib.vag_set_gemm_mode(mode)
+        try:
+            return fn(fctx, *grads)
+        finally:
+            lib.vag_set_gemm_mode(prev)
+    return wrapper
+
+
 def _lin(x, w, b=None, flags=0, out=None):
     """y = act(x Wᵀ + b): tcgen05 split-precision kernel for eligible shapes, FP32 FFMA otherwise."""
     rows, K = x.shape
@@ -50,6 +75,7 @@ class EncoderFn(torch.autograd.Function):
 
     @staticmethod
     def forward(fctx, src, lengths, emb_mask, emb, *gru):
+        _save_mode(fctx)
         # gru = (w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r); emb_mask: [T·B, E] time-major dropout mask or None
         import ctypes as C
         from ._cabi import EncoderWeights
@@ -62,7 +88,13 @@ class EncoderFn(torch.autograd.Function):
         for d in range(2):
             w.w_ih[d], w.w_hh[d] = ops._p(gru[4 * d].detach()), ops._p(gru[4 * d + 1].detach())
             w.b_ih[d], w.b_hh[d] = ops._p(gru[4 * d + 2].detach()), ops._p(gru[4 * d + 3].detach())
-        lens = (C.c_int32 * B)(*[int(x) for x in lengths])
+        # lengths: python list (validated on the host, copied to the device) or an int32 CUDA tensor [B] (graph-captured step:
+        # the caller refreshes that buffer between replays; nothing about the launch sequence depends on its contents)
+        if torch.is_tensor(lengths):
+            lens, lens_dev = None, lengths.to(device=dev, dtype=torch.int32).contiguous()
+        else:
+            lens = (C.c_int32 * B)(*[int(x) for x in lengths])
+            lens_dev = torch.tensor([int(x) for x in lengths], dtype=torch.int32).to(dev, non_blocking=True)
         ctx = torch.empty(B, Tn, 2 * H, dtype=torch.float32, device=dev)
         x = torch.empty(Tn * B, E, dtype=torch.float32, device=dev)
         ids_tm = torch.empty(Tn * B, dtype=torch.int64, device=dev)
@@ -70,33 +102,33 @@ class EncoderFn(torch.autograd.Function):
         gh = torch.empty(2, Tn, B, 3 * H, dtype=torch.float32, device=dev)
         ws = ops.workspace(lib.vag_encoder_train_workspace_bytes(B, Tn, E, H), dev)
         with on_device(dev):
-            ops.check(lib.vag_encoder_train_fwd_f32(C.byref(w), src.data_ptr(), lens, B, Tn, ctx.data_ptr(), x.data_ptr(),
+            ops.check(lib.vag_encoder_train_fwd_f32(C.byref(w), src.data_ptr(), lens, lens_dev.data_ptr(), B, Tn, ctx.data_ptr(), x.data_ptr(),
                                                     ids_tm.data_ptr(), gi.data_ptr(), gh.data_ptr(), ops.ptr(emb_mask), ws.data_ptr(),
                                                     ws.numel(), ops.stream_ptr()))
-        fctx.save_for_backward(x, ctx, ids_tm, gi, gh, emb_mask if emb_mask is not None else ids_tm, emb, *gru)
-        fctx.meta = (B, Tn, E, H, [int(v) for v in lengths], emb_mask is not None)
+        fctx.save_for_backward(x, ctx, ids_tm, gi, gh, emb_mask if emb_mask is not None else ids_tm, lens_dev, emb, *gru)
+        fctx.meta = (B, Tn, E, H, emb_mask is not None)
         return ctx
 
     @staticmethod
+    @_in_forward_mode
     def backward(fctx, dctx):
         import ctypes as C
         from ._cabi import EncoderWeights
         lib = ops._cabi.lib()
-        x, ctx, ids_tm, gi, gh, emb_mask, emb, *gru = fctx.saved_tensors
-        B, Tn, E, H, lengths, has_mask = fctx.meta
+        x, ctx, ids_tm, gi, gh, emb_mask, lens_dev, emb, *gru = fctx.saved_tensors
+        B, Tn, E, H, has_mask = fctx.meta
         dev = emb.device
         w = EncoderWeights()
         w.E, w.H, w.vocab, w.emb = E, H, emb.shape[0], ops._p(emb.detach())
         for d in range(2):
             w.w_ih[d], w.w_hh[d] = ops._p(gru[4 * d].detach()), ops._p(gru[4 * d + 1].detach())
             w.b_ih[d], w.b_hh[d] = ops._p(gru[4 * d + 2].detach()), ops._p(gru[4 * d + 3].detach())
-        lens = (C.c_int32 * B)(*lengths)
         demb = torch.empty_like(emb)
         grads = [torch.empty_like(p) for p in gru]
         arr = lambda idx: (C.c_void_p * 2)(grads[idx].data_ptr(), grads[4 + idx].data_ptr())
         ws = ops.workspace(lib.vag_encoder_train_workspace_bytes(B, Tn, E, H), dev)
         with on_device(dev):
-            ops.check(lib.vag_encoder_bwd_f32(C.byref(w), lens, B, Tn, ctx.data_ptr(), dctx.contiguous().data_ptr(), x.data_ptr(),
+            ops.check(lib.vag_encoder_bwd_f32(C.byref(w), None, lens_dev.data_ptr(), B, Tn, ctx.data_ptr(), dctx.contiguous().data_ptr(), x.data_ptr(),
                                               ids_tm.data_ptr(), gi.data_ptr(), gh.data_ptr(), demb.data_ptr(), arr(0), arr(1), arr(2),
                                               arr(3), emb_mask.data_ptr() if has_mask else None, ws.data_ptr(), ws.numel(),
                                               ops.stream_ptr()))
@@ -131,6 +163,7 @@ class VsePoolFn(torch.autograd.Function):
 
     @staticmethod
     def forward(fctx, im, ctx, mask, method, activation, im_w, im_b, txt_w, txt_b, ctx2ctx_w, emb2ctx_w, mlp_w):
+        _save_mode(fctx)
         B, Tn, C = ctx.shape
         act = ops.LIN_TANH if activation else 0
         a_im = _lin(im, im_w, im_b, act)                               # VSE_Imagine_Enc.py:123-127
@@ -148,6 +181,7 @@ class VsePoolFn(torch.autograd.Function):
         return im_emb, txt_emb, ctx_vec
 
     @staticmethod
+    @_in_forward_mode
     def backward(fctx, d_im_emb, d_txt_emb, d_ctx_vec):
         im, ctx, mask, a_im, im_emb, iq, pk, beta, ctx_vec, a_txt, im_w, txt_w, ctx2ctx_w, emb2ctx_w, mlp_w = fctx.saved_tensors
         mode, activation, has_mlp = fctx.meta
@@ -186,6 +220,7 @@ class DecoderInitFn(torch.autograd.Function):
 
     @staticmethod
     def forward(fctx, ctx_vec, ctx, mask, split, ini_w, ini_b):
+        _save_mode(fctx)
         lib_mix = ops._cabi.lib()
         B, Tn, C = ctx.shape
         z = _empty(B, C, like=ctx)
@@ -198,6 +233,7 @@ class DecoderInitFn(torch.autograd.Function):
         return h0
 
     @staticmethod
+    @_in_forward_mode
     def backward(fctx, dh0):
         z, h0, mask, ini_w = fctx.saved_tensors
         split, has_vec, (B, Tn, C) = fctx.meta
@@ -224,6 +260,7 @@ class DecoderSeqFn(torch.autograd.Function):
 
     @staticmethod
     def forward(fctx, h0, enc, mask, tgt, weight, teacher, tied, out_mask, *params):
+        _save_mode(fctx)
         import ctypes as C
         from ._cabi import DecoderGrads, DecoderSeqSaved, DecoderWeights
         lib = ops._cabi.lib()
@@ -267,6 +304,7 @@ class DecoderSeqFn(torch.autograd.Function):
         return loss_rows
 
     @staticmethod
+    @_in_forward_mode
     def backward(fctx, dloss_rows):
         import ctypes as C
         from ._cabi import DecoderGrads, DecoderSeqSaved, DecoderWeights

@@ -24,6 +24,13 @@ __device__ __forceinline__ float4 rnd4(float4 v) {
     return v;
 }
 
+struct Rows32Problem {
+    float* y;
+    const float* x;
+    const float* w;
+    const float* bias;
+};
+
 constexpr int ROWS32_WARPS = 16;
 constexpr int ROWS32_KC = 32;   // contraction indices per warp per pass
 
@@ -32,8 +39,13 @@ constexpr int ROWS32_KC = 32;   // contraction indices per warp per pass
 // goes through a per-warp shared-memory slot, and the FMAs read it back as broadcast LDS.128.
 template <int BN, bool WK, bool RB>
 __global__ void __launch_bounds__(ROWS32_WARPS * 32, 2)
-linear_rows32_kernel(float* __restrict__ y, int64_t ldy, const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
-                     int64_t ldw, const float* __restrict__ bias, int rows, int K, int N, int flags) {
+linear_rows32_kernel(Rows32Problem p0, Rows32Problem p1, int64_t ldy, int64_t ldx, int64_t ldw, int rows, int K, int N, int flags) {
+    // blockIdx.y selects one of two independent problems of identical shape (the two directions of the encoder GRU)
+    const Rows32Problem pr = blockIdx.y == 0 ? p0 : p1;
+    float* __restrict__ y = pr.y;
+    const float* __restrict__ x = pr.x;
+    const float* __restrict__ w = pr.w;
+    const float* __restrict__ bias = pr.bias;
     __shared__ float red[ROWS32_WARPS][32][BN + 1];
     __shared__ __align__(16) float wtile[ROWS32_WARPS][BN * ROWS32_KC];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -119,13 +131,13 @@ linear_rows32_kernel(float* __restrict__ y, int64_t ldy, const float* __restrict
 }
 
 template <bool WK, bool RB>
-int launch_rows32(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, int rows,
-                  int K, int N, int flags, cudaStream_t st) {
+int launch_rows32(const Rows32Problem& p0, const Rows32Problem& p1, int nprob, int64_t ldy, int64_t ldx, int64_t ldw, int rows, int K, int N,
+                  int flags, cudaStream_t st) {
     // enough CTAs for one wave on 148 SMs: 8 columns per CTA for wide outputs, 4 otherwise
-    if (N >= 960) {
-        linear_rows32_kernel<8, WK, RB><<<ceil_div(N, 8), ROWS32_WARPS * 32, 0, st>>>(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags);
+    if (N * nprob >= 960) {
+        linear_rows32_kernel<8, WK, RB><<<dim3(ceil_div(N, 8), nprob), ROWS32_WARPS * 32, 0, st>>>(p0, p1, ldy, ldx, ldw, rows, K, N, flags);
     } else {
-        linear_rows32_kernel<4, WK, RB><<<ceil_div(N, 4), ROWS32_WARPS * 32, 0, st>>>(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags);
+        linear_rows32_kernel<4, WK, RB><<<dim3(ceil_div(N, 4), nprob), ROWS32_WARPS * 32, 0, st>>>(p0, p1, ldy, ldx, ldw, rows, K, N, flags);
     }
     VAG_LAUNCH_CHECK();
     return VAG_OK;
@@ -145,12 +157,25 @@ bool rows32_ok(const float* x, int64_t ldx, const float* w, int64_t ldw, int row
 // y[rows, N] (+)= x[rows, K] · W(c, k)  (+ bias) (tanh);  round_bf16: operands rounded to bfloat16 first (bf16 mode)
 int linear_rows32(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, int rows,
                   int K, int N, int flags, bool wk, bool round_bf16, cudaStream_t st) {
+    const Rows32Problem p{y, x, w, bias};
     if (wk) {
-        if (round_bf16) return launch_rows32<true, true>(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags, st);
-        return launch_rows32<true, false>(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags, st);
+        if (round_bf16) return launch_rows32<true, true>(p, p, 1, ldy, ldx, ldw, rows, K, N, flags, st);
+        return launch_rows32<true, false>(p, p, 1, ldy, ldx, ldw, rows, K, N, flags, st);
     }
-    if (round_bf16) return launch_rows32<false, true>(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags, st);
-    return launch_rows32<false, false>(y, ldy, x, ldx, w, ldw, bias, rows, K, N, flags, st);
+    if (round_bf16) return launch_rows32<false, true>(p, p, 1, ldy, ldx, ldw, rows, K, N, flags, st);
+    return launch_rows32<false, false>(p, p, 1, ldy, ldx, ldw, rows, K, N, flags, st);
+}
+
+// Two problems of identical shape and pitches in one launch (both directions of the bidirectional encoder GRU).
+int linear_rows32_pair(float* const y[2], int64_t ldy, const float* const x[2], int64_t ldx, const float* const w[2], int64_t ldw,
+                       const float* const bias[2], int rows, int K, int N, int flags, bool wk, bool round_bf16, cudaStream_t st) {
+    const Rows32Problem p0{y[0], x[0], w[0], bias ? bias[0] : nullptr}, p1{y[1], x[1], w[1], bias ? bias[1] : nullptr};
+    if (wk) {
+        if (round_bf16) return launch_rows32<true, true>(p0, p1, 2, ldy, ldx, ldw, rows, K, N, flags, st);
+        return launch_rows32<true, false>(p0, p1, 2, ldy, ldx, ldw, rows, K, N, flags, st);
+    }
+    if (round_bf16) return launch_rows32<false, true>(p0, p1, 2, ldy, ldx, ldw, rows, K, N, flags, st);
+    return launch_rows32<false, false>(p0, p1, 2, ldy, ldx, ldw, rows, K, N, flags, st);
 }
 
 }  // namespace vag

@@ -9,6 +9,7 @@
 #include <vector>
 
 namespace vag {
+int gemm_mode();
 bool rows32_ok(const float* x, int64_t ldx, const float* w, int64_t ldw, int rows, int K, int N, bool wk);
 int linear_rows32(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, int rows,
                   int K, int N, int flags, bool wk, bool round_bf16, cudaStream_t st);
@@ -363,7 +364,7 @@ extern "C" int vag_gemm_f32(float* C, int64_t ldc, const float* A, int64_t sam, 
         const bool wk = sbk == 1;
         const int64_t ldw = wk ? sbn : sbk;
         if (rows32_ok(A, sam, B, ldw, M, K, N, wk))
-            return linear_rows32(C, ldc, A, sam, B, ldw, nullptr, M, K, N, beta == 1.f ? VAG_LIN_ACCUMULATE : 0, wk, false, st);
+            return linear_rows32(C, ldc, A, sam, B, ldw, nullptr, M, K, N, beta == 1.f ? VAG_LIN_ACCUMULATE : 0, wk, gemm_mode() == 2, st);
     }
     const bool small_m = M <= 32;
     const int tiles = small_m ? ceil_div(N, 64) * ceil_div(M, 32) : ceil_div(N, 64) * ceil_div(M, 64);
@@ -885,23 +886,119 @@ static int copy2d(float* dst, int64_t ld_dst, const float* src, int64_t ld_src, 
 }
 }  // namespace vag
 
+namespace vag {
+int linear_rows32_pair(float* const y[2], int64_t ldy, const float* const x[2], int64_t ldx, const float* const w[2], int64_t ldw,
+                       const float* const bias[2], int rows, int K, int N, int flags, bool wk, bool round_bf16, cudaStream_t st);
+
+// One recurrent step of the packed bidirectional GRU for BOTH directions (blockIdx.y = direction; direction 0 is at time s,
+// direction 1 at time T-1-s).  Rows whose sentence is shorter than the time index are masked on the device — the launch
+// sequence does not depend on the lengths, so a captured CUDA graph of the step serves every batch of the same [B, T] shape:
+// the state of a masked row is left alone (0 before a reverse chain starts), its context stays 0 (pad_packed_sequence,
+// Encoder.py:60) and its saved hidden pre-activations are zeroed.
+__global__ void __launch_bounds__(256)
+enc_gates_fwd_kernel(float* __restrict__ h, float* __restrict__ ctx_out, const float* __restrict__ gi, float* __restrict__ gh,
+                     const int32_t* __restrict__ lengths, int B, int T, int H, int s) {
+    const int d = blockIdx.y, t = d == 0 ? s : T - 1 - s;
+    const int per_row = H >> 2;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < B * per_row; idx += gridDim.x * blockDim.x) {
+        const int row = idx / per_row, j = (idx % per_row) << 2;
+        const int64_t o3 = (((int64_t)d * T + t) * B + row) * 3 * H;
+        float* ghr = gh + o3;
+        if (lengths[row] <= t) {
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(ghr + j) = z4;
+            *reinterpret_cast<float4*>(ghr + H + j) = z4;
+            *reinterpret_cast<float4*>(ghr + 2 * H + j) = z4;
+            continue;
+        }
+        const float* gir = gi + o3;
+        float ir[4], iz[4], in_[4], hr[4], hz[4], hn[4], hp[4], out[4];
+        *reinterpret_cast<float4*>(ir) = *reinterpret_cast<const float4*>(gir + j);
+        *reinterpret_cast<float4*>(iz) = *reinterpret_cast<const float4*>(gir + H + j);
+        *reinterpret_cast<float4*>(in_) = *reinterpret_cast<const float4*>(gir + 2 * H + j);
+        *reinterpret_cast<float4*>(hr) = *reinterpret_cast<const float4*>(ghr + j);
+        *reinterpret_cast<float4*>(hz) = *reinterpret_cast<const float4*>(ghr + H + j);
+        *reinterpret_cast<float4*>(hn) = *reinterpret_cast<const float4*>(ghr + 2 * H + j);
+        float* hrow = h + ((int64_t)d * B + row) * H + j;
+        *reinterpret_cast<float4*>(hp) = *reinterpret_cast<const float4*>(hrow);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float r = sigmoidf_precise(ir[u] + hr[u]);
+            const float z = sigmoidf_precise(iz[u] + hz[u]);
+            const float n = tanhf(in_[u] + r * hn[u]);
+            out[u] = (1.0f - z) * n + z * hp[u];
+        }
+        *reinterpret_cast<float4*>(hrow) = *reinterpret_cast<float4*>(out);
+        *reinterpret_cast<float4*>(ctx_out + ((int64_t)row * T + t) * 2 * H + (int64_t)d * H + j) = *reinterpret_cast<float4*>(out);
+    }
+}
+
+// Backward of one step, both directions (direction 0 walks t = T-1 … 0, direction 1 walks t = 0 … T-1).  dh = dctx[t] + carry;
+// writes this step's dgi / dgh (zeros for masked rows), the previous state the step saw (read back from ctx: exactly 0 where
+// a chain starts), and carry = dh·z — the recurrent contraction then adds dgh·W_hh onto it.
+__global__ void __launch_bounds__(256)
+enc_gates_bwd_kernel(float* __restrict__ dgi_all, float* __restrict__ dgh_all, float* __restrict__ hprev_all, float* __restrict__ carry,
+                     const float* __restrict__ dctx, const float* __restrict__ ctx, const float* __restrict__ gi,
+                     const float* __restrict__ gh, const int32_t* __restrict__ lengths, int B, int T, int H, int s) {
+    const int d = blockIdx.y, t = d == 0 ? T - 1 - s : s, tp = d == 0 ? t - 1 : t + 1;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < B * H; idx += gridDim.x * blockDim.x) {
+        const int row = idx / H, j = idx % H;
+        const int64_t o3 = (((int64_t)d * T + t) * B + row) * 3 * H;
+        const int64_t oh = (((int64_t)d * T + t) * B + row) * H + j;
+        const float hp = (tp >= 0 && tp < T) ? ctx[((int64_t)row * T + tp) * 2 * H + (int64_t)d * H + j] : 0.f;
+        hprev_all[oh] = hp;
+        float* a = dgi_all + o3;
+        float* b = dgh_all + o3;
+        float* cr = carry + ((int64_t)d * B + row) * H + j;
+        if (lengths[row] <= t) {
+            a[j] = 0.f; a[H + j] = 0.f; a[2 * H + j] = 0.f;
+            b[j] = 0.f; b[H + j] = 0.f; b[2 * H + j] = 0.f;
+            *cr = 0.f;
+            continue;
+        }
+        const float* gir = gi + o3;
+        const float* ghr = gh + o3;
+        const float r = sigmoidf_precise(gir[j] + ghr[j]);
+        const float z = sigmoidf_precise(gir[H + j] + ghr[H + j]);
+        const float hn = ghr[2 * H + j];
+        const float n = tanhf(gir[2 * H + j] + r * hn);
+        const float g = dctx[((int64_t)row * T + t) * 2 * H + (int64_t)d * H + j] + *cr;
+        const float dn_pre = g * (1.f - z) * (1.f - n * n);
+        const float dz_pre = g * (hp - n) * z * (1.f - z);
+        const float dr_pre = dn_pre * hn * r * (1.f - r);
+        a[j] = dr_pre; a[H + j] = dz_pre; a[2 * H + j] = dn_pre;
+        b[j] = dr_pre; b[H + j] = dz_pre; b[2 * H + j] = dn_pre * r;
+        *cr = g * z;
+    }
+}
+}  // namespace vag
+
 extern "C" size_t vag_encoder_train_workspace_bytes(int B, int T, int E, int H) {
     return 2 * (GemmCtx::split_bytes(3 * H, E) + GemmCtx::split_bytes(3 * H, H)) + GemmCtx::split_bytes((int64_t)T * B, E) +
-           (size_t)T * B * 3 * H * 4 * 2 + (size_t)T * B * H * 4 + (size_t)B * H * 4 * 8 + (size_t)B * 3 * H * 4 * 4 + 131072 +
+           (size_t)T * B * 3 * H * 4 * 4 + (size_t)T * B * H * 4 * 2 + (size_t)B * H * 4 * 8 + (size_t)B * 3 * H * 4 * 4 + 131072 +
            (size_t)T * B * E * 4 + gemm_tc_scratch_bytes(3 * H, std::max(E, H), (int64_t)T * B) + gemm_tc_scratch_bytes((int64_t)T * B, E, 3 * H);
 }
 
-/* saved: x [T·B, E] time-major embeddings, ids_tm int64 [T·B], gi [2][T, B, 3H], gh [2][T, B, 3H] (zero where inactive) */
-extern "C" int vag_encoder_train_fwd_f32(const vag_encoder_weights* w, const int64_t* src, const int32_t* lengths_host, int B, int T,
-                                         float* ctx_out, float* x, int64_t* ids_tm, float* gi, float* gh, const float* emb_mask,
-                                         void* workspace, size_t workspace_bytes, vag_stream_t stream) {
-    VAG_REQUIRE(w && src && lengths_host && ctx_out && x && ids_tm && gi && gh, "vag_encoder_train_fwd_f32: null pointer");
+static int check_lengths_host(const int32_t* lengths_host, int B, int T, const char* who) {
+    if (!lengths_host) return VAG_OK;
+    for (int b = 0; b < B; ++b) {
+        VAG_REQUIRE(lengths_host[b] >= 1 && lengths_host[b] <= T, "%s: bad length", who);
+        VAG_REQUIRE(b == 0 || lengths_host[b] <= lengths_host[b - 1], "%s: lengths must be sorted in decreasing order", who);
+    }
+    return VAG_OK;
+}
+
+/* saved: x [T·B, E] time-major embeddings, ids_tm int64 [T·B], gi [2][T, B, 3H], gh [2][T, B, 3H] (zero where inactive).
+   lengths_dev int32 [B] on the device drives the masking; lengths_host (optional) is only validated. */
+extern "C" int vag_encoder_train_fwd_f32(const vag_encoder_weights* w, const int64_t* src, const int32_t* lengths_host,
+                                         const int32_t* lengths_dev, int B, int T, float* ctx_out, float* x, int64_t* ids_tm,
+                                         float* gi, float* gh, const float* emb_mask, void* workspace, size_t workspace_bytes,
+                                         vag_stream_t stream) {
+    VAG_REQUIRE(w && src && lengths_dev && ctx_out && x && ids_tm && gi && gh, "vag_encoder_train_fwd_f32: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const int E = w->E, H = w->H;
-    for (int b = 0; b < B; ++b) {
-        VAG_REQUIRE(lengths_host[b] >= 1 && lengths_host[b] <= T, "vag_encoder_train_fwd_f32: bad length");
-        VAG_REQUIRE(b == 0 || lengths_host[b] <= lengths_host[b - 1], "vag_encoder_train_fwd_f32: lengths must be sorted in decreasing order");
-    }
+    VAG_REQUIRE((H & 3) == 0, "vag_encoder_train_fwd_f32: H must be a multiple of 4");
+    VAG_TRY(check_lengths_host(lengths_host, B, T, "vag_encoder_train_fwd_f32"));
     Arena ar(workspace, workspace_bytes);
     const size_t wb = 2 * (GemmCtx::split_bytes(3 * H, E) + GemmCtx::split_bytes(3 * H, H)) + 8192;
     const size_t ab = GemmCtx::split_bytes((int64_t)T * B, E) + 8192;
@@ -920,50 +1017,48 @@ extern "C" int vag_encoder_train_fwd_f32(const vag_encoder_weights* w, const int
         if (emb_mask) VAG_TRY(vag_mul_f32(x, emb_mask, (int64_t)T * B * E, stream));   // embedding dropout, Encoder.py:51-52
     }
     VAG_CUDA(cudaMemsetAsync(ctx_out, 0, sizeof(float) * (size_t)B * T * 2 * H, st));
-    VAG_CUDA(cudaMemsetAsync(gh, 0, sizeof(float) * (size_t)2 * T * B * 3 * H, st));
     VAG_CUDA(cudaMemsetAsync(h, 0, sizeof(float) * (size_t)2 * B * H, st));
-    std::vector<int> n_act(T);
-    for (int t = 0; t < T; ++t) {
-        int n = 0;
-        while (n < B && lengths_host[n] > t) ++n;
-        n_act[t] = n;
-    }
     for (int d = 0; d < 2; ++d)
         VAG_TRY(gemm.linear(gi + (size_t)d * T * B * 3 * H, 3 * H, x, E, w->w_ih[d], E, w->b_ih[d], T * B, E, 3 * H, 0));
+    const bool pair = rows32_ok(h, H, w->w_hh[0], H, B, H, 3 * H, true) && rows32_ok(h + (size_t)B * H, H, w->w_hh[1], H, B, H, 3 * H, true);
+    const int gate_blocks = std::max(1, std::min(ceil_div(B * H / 4, 256), num_sms()));
     for (int s_ = 0; s_ < T; ++s_) {
-        for (int d = 0; d < 2; ++d) {
-            const int t = d == 0 ? s_ : T - 1 - s_;
-            const int n = n_act[t];
-            if (n == 0) continue;
-            float* hd = h + (size_t)d * B * H;
-            float* gh_t = gh + ((size_t)d * T + t) * B * 3 * H;
-            gemm.new_step();
-            VAG_TRY(gemm.linear(gh_t, 3 * H, hd, H, w->w_hh[d], H, w->b_hh[d], n, H, 3 * H, 0));
-            VAG_TRY(vag_gru_gates_f32(hd, H, ctx_out + (int64_t)t * 2 * H + d * H, (int64_t)T * 2 * H,
-                                      gi + ((size_t)d * T + t) * B * 3 * H, 3 * H, gh_t, 3 * H, hd, H, n, H, stream));
+        float* gh_t[2] = {gh + ((size_t)0 * T + s_) * B * 3 * H, gh + ((size_t)1 * T + (T - 1 - s_)) * B * 3 * H};
+        if (pair) {
+            const float* xs[2] = {h, h + (size_t)B * H};
+            const float* ws[2] = {w->w_hh[0], w->w_hh[1]};
+            const float* bs[2] = {w->b_hh[0], w->b_hh[1]};
+            VAG_TRY(linear_rows32_pair(gh_t, 3 * H, xs, H, ws, H, bs, B, H, 3 * H, 0, true, gemm_mode() == 2, st));
+        } else {
+            for (int d = 0; d < 2; ++d) {
+                gemm.new_step();
+                VAG_TRY(gemm.linear(gh_t[d], 3 * H, h + (size_t)d * B * H, H, w->w_hh[d], H, w->b_hh[d], B, H, 3 * H, 0));
+            }
         }
+        enc_gates_fwd_kernel<<<dim3(gate_blocks, 2), 256, 0, st>>>(h, ctx_out, gi, gh, lengths_dev, B, T, H, s_);
+        VAG_LAUNCH_CHECK();
     }
     return VAG_OK;
 }
 
 /* grads: d_emb [vocab, E] (zeroed here), d_w_ih[2] [3H,E], d_w_hh[2] [3H,H], d_b_ih[2], d_b_hh[2] [3H] */
-extern "C" int vag_encoder_bwd_f32(const vag_encoder_weights* w, const int32_t* lengths_host, int B, int T, const float* ctx,
-                                   const float* dctx, const float* x, const int64_t* ids_tm, const float* gi, const float* gh,
-                                   float* d_emb, float* const* d_w_ih, float* const* d_w_hh, float* const* d_b_ih,
+extern "C" int vag_encoder_bwd_f32(const vag_encoder_weights* w, const int32_t* lengths_host, const int32_t* lengths_dev, int B, int T,
+                                   const float* ctx, const float* dctx, const float* x, const int64_t* ids_tm, const float* gi,
+                                   const float* gh, float* d_emb, float* const* d_w_ih, float* const* d_w_hh, float* const* d_b_ih,
                                    float* const* d_b_hh, const float* emb_mask, void* workspace, size_t workspace_bytes,
                                    vag_stream_t stream) {
-    VAG_REQUIRE(w && lengths_host && ctx && dctx && x && ids_tm && gi && gh && d_emb, "vag_encoder_bwd_f32: null pointer");
+    VAG_REQUIRE(w && lengths_dev && ctx && dctx && x && ids_tm && gi && gh && d_emb, "vag_encoder_bwd_f32: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     vag_stream_t vs = stream;
     const int E = w->E, H = w->H;
+    VAG_TRY(check_lengths_host(lengths_host, B, T, "vag_encoder_bwd_f32"));
     Arena ar(workspace, workspace_bytes);
-    float* dgi_all = ar.take<float>((size_t)T * B * 3 * H);
-    float* dgh_all = ar.take<float>((size_t)T * B * 3 * H);
-    float* hprev_all = ar.take<float>((size_t)T * B * H);
+    const size_t per_dir3 = (size_t)T * B * 3 * H, per_dirh = (size_t)T * B * H;
+    float* dgi_all = ar.take<float>(2 * per_dir3);
+    float* dgh_all = ar.take<float>(2 * per_dir3);
+    float* hprev_all = ar.take<float>(2 * per_dirh);
     float* dx = ar.take<float>((size_t)T * B * E);
-    float* carry = ar.take<float>((size_t)B * H);
-    float* dh = ar.take<float>((size_t)B * H);
-    float* dhp = ar.take<float>((size_t)B * H);
+    float* carry = ar.take<float>((size_t)2 * B * H);
     const size_t tcs_bytes = gemm_tc_scratch_bytes(3 * H, std::max(E, H), (int64_t)T * B) + gemm_tc_scratch_bytes((int64_t)T * B, E, 3 * H);
     char* tcs = ar.take<char>(tcs_bytes);
     TcScratchScope tc_scope(tcs, tcs ? tcs_bytes : 0);
@@ -971,41 +1066,30 @@ extern "C" int vag_encoder_bwd_f32(const vag_encoder_weights* w, const int32_t* 
         set_error("vag_encoder_bwd_f32: workspace too small");
         return VAG_ERR_WORKSPACE;
     }
-    std::vector<int> n_act(T);
-    for (int t = 0; t < T; ++t) {
-        int n = 0;
-        while (n < B && lengths_host[n] > t) ++n;
-        n_act[t] = n;
-    }
-    VAG_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)T * B * E, st));
-    for (int d = 0; d < 2; ++d) {
-        VAG_CUDA(cudaMemsetAsync(dgi_all, 0, sizeof(float) * (size_t)T * B * 3 * H, st));
-        VAG_CUDA(cudaMemsetAsync(dgh_all, 0, sizeof(float) * (size_t)T * B * 3 * H, st));
-        VAG_CUDA(cudaMemsetAsync(hprev_all, 0, sizeof(float) * (size_t)T * B * H, st));
-        VAG_CUDA(cudaMemsetAsync(carry, 0, sizeof(float) * (size_t)B * H, st));
-        for (int s_ = 0; s_ < T; ++s_) {
-            const int t = d == 0 ? T - 1 - s_ : s_;           // reverse of the forward order of this direction
-            const int n = n_act[t];
-            if (n == 0) continue;
-            const int tp = d == 0 ? t - 1 : t + 1;            // where h_prev of this step was produced
-            float* hp = hprev_all + (size_t)t * B * H;
-            if (tp >= 0 && tp < T)   // rows whose chain starts here had h_prev = 0, and ctx is exactly 0 there (padding)
-                VAG_TRY(copy2d(hp, H, ctx + (int64_t)tp * 2 * H + d * H, (int64_t)T * 2 * H, n, H, st));
-            VAG_TRY(copy2d(dh, H, dctx + (int64_t)t * 2 * H + d * H, (int64_t)T * 2 * H, n, H, st));
-            VAG_TRY(vag_axpby_f32(dh, carry, 1.f, 1.f, (int64_t)n * H, vs));
-            float* dgi = dgi_all + (size_t)t * B * 3 * H;
-            float* dgh = dgh_all + (size_t)t * B * 3 * H;
-            VAG_TRY(vag_gru_gates_bwd_f32(dgi, dgh, dhp, dh, H, gi + ((size_t)d * T + t) * B * 3 * H, gh + ((size_t)d * T + t) * B * 3 * H,
-                                          hp, H, n, H, vs));
-            VAG_TRY(gemm_g(dhp, H, dgh, 3 * H, 1, w->w_hh[d], H, 1, n, H, 3 * H, 1.f, st));       // dh_prev = dh·z + dgh·W_hh
-            VAG_CUDA(cudaMemsetAsync(carry, 0, sizeof(float) * (size_t)B * H, st));
-            VAG_CUDA(cudaMemcpyAsync(carry, dhp, sizeof(float) * (size_t)n * H, cudaMemcpyDeviceToDevice, st));
+    VAG_CUDA(cudaMemsetAsync(carry, 0, sizeof(float) * (size_t)2 * B * H, st));
+    const bool pair = rows32_ok(dgh_all, 3 * H, w->w_hh[0], H, B, 3 * H, H, false) && rows32_ok(dgh_all, 3 * H, w->w_hh[1], H, B, 3 * H, H, false);
+    const int gate_blocks = std::max(1, std::min(ceil_div(B * H, 256), num_sms()));
+    for (int s_ = 0; s_ < T; ++s_) {
+        enc_gates_bwd_kernel<<<dim3(gate_blocks, 2), 256, 0, st>>>(dgi_all, dgh_all, hprev_all, carry, dctx, ctx, gi, gh, lengths_dev, B, T, H, s_);
+        VAG_LAUNCH_CHECK();
+        const int t0 = T - 1 - s_, t1 = s_;
+        const float* dgh_t[2] = {dgh_all + (size_t)t0 * B * 3 * H, dgh_all + per_dir3 + (size_t)t1 * B * 3 * H};
+        float* cr[2] = {carry, carry + (size_t)B * H};
+        if (pair) {   // carry += dgh·W_hh, both directions in one launch
+            const float* ws[2] = {w->w_hh[0], w->w_hh[1]};
+            VAG_TRY(linear_rows32_pair(cr, H, dgh_t, 3 * H, ws, H, nullptr, B, 3 * H, H, VAG_LIN_ACCUMULATE, false, gemm_mode() == 2, st));
+        } else {
+            for (int d = 0; d < 2; ++d) VAG_TRY(vag_gemm_f32(cr[d], H, dgh_t[d], 3 * H, 1, w->w_hh[d], H, 1, B, H, 3 * H, 1.f, 1.f, vs));
         }
-        VAG_TRY(gemm_g(dx, E, dgi_all, 3 * H, 1, w->w_ih[d], E, 1, T * B, E, 3 * H, 1.f, st));     // dx += dgi·W_ih
-        VAG_TRY(gemm_g(d_w_ih[d], E, dgi_all, 1, 3 * H, x, E, 1, 3 * H, E, T * B, 0.f, st));
-        VAG_TRY(gemm_g(d_w_hh[d], H, dgh_all, 1, 3 * H, hprev_all, H, 1, 3 * H, H, T * B, 0.f, st));
-        VAG_TRY(vag_colsum_f32(d_b_ih[d], dgi_all, 3 * H, T * B, 3 * H, 0, vs));
-        VAG_TRY(vag_colsum_f32(d_b_hh[d], dgh_all, 3 * H, T * B, 3 * H, 0, vs));
+    }
+    for (int d = 0; d < 2; ++d) {
+        const float* dgi_d = dgi_all + (size_t)d * per_dir3;
+        const float* dgh_d = dgh_all + (size_t)d * per_dir3;
+        VAG_TRY(gemm_g(dx, E, dgi_d, 3 * H, 1, w->w_ih[d], E, 1, T * B, E, 3 * H, d == 0 ? 0.f : 1.f, st));     // dx (+)= dgi·W_ih
+        VAG_TRY(gemm_g(d_w_ih[d], E, dgi_d, 1, 3 * H, x, E, 1, 3 * H, E, T * B, 0.f, st));
+        VAG_TRY(gemm_g(d_w_hh[d], H, dgh_d, 1, 3 * H, hprev_all + (size_t)d * per_dirh, H, 1, 3 * H, H, T * B, 0.f, st));
+        VAG_TRY(vag_colsum_f32(d_b_ih[d], dgi_d, 3 * H, T * B, 3 * H, 0, vs));
+        VAG_TRY(vag_colsum_f32(d_b_hh[d], dgh_d, 3 * H, T * B, 3 * H, 0, vs));
     }
     VAG_CUDA(cudaMemsetAsync(d_emb, 0, sizeof(float) * (size_t)w->vocab * E, st));
     if (emb_mask) VAG_TRY(vag_mul_f32(dx, emb_mask, (int64_t)T * B * E, vs));

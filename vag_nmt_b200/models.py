@@ -161,11 +161,14 @@ class _Seq2SeqBase(nn.Module):
         enc = self.encoder
         dev = self._device()
         src = src_var.to(device=dev, dtype=torch.int64).contiguous()
-        lengths = [int(x) for x in src_lengths]
-        if src.shape[1] != max(lengths):
-            raise ValueError("the padded width must equal the longest sentence (pad_packed_sequence, Encoder.py:60)")
-        if any(lengths[i] < lengths[i + 1] for i in range(len(lengths) - 1)):
-            raise RuntimeError("`lengths` array must be sorted in decreasing order (pack_padded_sequence, Encoder.py:55)")
+        if torch.is_tensor(src_lengths) and src_lengths.is_cuda:
+            lengths = src_lengths          # device-resident lengths (graph-captured step): validated by the caller on the host
+        else:
+            lengths = [int(x) for x in src_lengths]
+            if src.shape[1] != max(lengths):
+                raise ValueError("the padded width must equal the longest sentence (pad_packed_sequence, Encoder.py:60)")
+            if any(lengths[i] < lengths[i + 1] for i in range(len(lengths) - 1)):
+                raise RuntimeError("`lengths` array must be sorted in decreasing order (pack_padded_sequence, Encoder.py:55)")
         g = enc.gru
         B, Tn = src.shape
         E, H = enc.embedding.weight.shape[1], enc.hidden_size

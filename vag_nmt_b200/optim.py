@@ -91,7 +91,13 @@ class ClipAdam:
                     st = self.state[p] = (torch.zeros_like(p), torch.zeros_like(p))
                 entries.append((p.data, p.grad, st[0], st[1], float(g["weight_decay"]), float(g["lr"])))
                 max_n = max(max_n, p.numel())
-        table = T.optim_table(entries).to(dev, non_blocking=True)
+        # the descriptor table only changes when a tensor moves (graph-replayed steps keep every address fixed): cache it
+        tkey = tuple((e[0].data_ptr(), e[1].data_ptr(), e[4], e[5]) for e in entries)
+        if getattr(self, "_table_key", None) == tkey:
+            table = self._table
+        else:
+            table = T.optim_table(entries).to(dev, non_blocking=True)
+            self._table_key = tkey
         T.sumsq_multi_(self._sumsq, table, len(entries), max_n)
         T.clip_adam_multi_(table, len(entries), max_n, self._sumsq, clip if clip is not None else float("inf"), b1, b2, self.eps,
                            self.step_count)

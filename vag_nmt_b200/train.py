@@ -6,6 +6,9 @@ gradients first when torch.distributed is initialised (one process per GPU, NCCL
 """
 from __future__ import annotations
 
+import random
+from typing import Dict, Optional
+
 import torch
 
 from .losses import PairwiseRankingLoss
@@ -79,3 +82,105 @@ class DistributedPairwiseRankingLoss(PairwiseRankingLoss):
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
             return super().forward(im, s)
         return _GlobalRankLossFn.apply(im, s, float(self.margin), self.one_direction, self.group)
+
+
+# ---------------------------------------------------------------------------------------------------- CUDA-graph step
+class GraphedTrainStep:
+    """The optimisation step of train.py:36-51 with zero_grad → forward → backward replayed from a CUDA graph.
+
+    A training step at 32 sentences per GPU is ~600 short dependent launches; issued one by one the host cannot keep the
+    GPU fed.  Nothing in the launch sequence depends on the DATA of a batch — sentence lengths are read on the device
+    (vag_encoder_train_fwd_f32 masks finished rows), the teacher-forcing coin is tossed before the graph is chosen —
+    so one captured graph per batch SHAPE (B, Ts, Tt, teacher-forced?) serves every later batch of that shape.  Shapes are
+    captured lazily the first time they appear (one eager warm-up pass + the capture ≈ three steps' worth of time) and
+    share one memory pool.  Gradient all-reduce (data parallel), clipping and Adam run after the replay through
+    ``ClipAdam.step``, exactly as in the eager path.
+
+    ``step(src, lengths, tgt, im)`` takes the same arguments as ``train_imagine_beam`` (``im=None`` for the text-only
+    model) and returns device scalars (loss, loss_mt, loss_vse) — no host synchronisation.
+    """
+
+    def __init__(self, model, optimizer: ClipAdam, criterion_mt, criterion_vse=None, clip: float = CLIP, enabled: Optional[bool] = None):
+        self.model, self.optimizer = model, optimizer
+        self.criterion_mt, self.criterion_vse = criterion_mt, criterion_vse
+        self.clip = clip
+        self._graphs: Dict[tuple, dict] = {}
+        self._pool = None
+        if enabled is None:   # collectives inside a capture (the global-batch ranking loss under data parallelism) stay eager
+            import torch.distributed as dist
+            enabled = not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
+        self.enabled = enabled
+
+    # -- one forward + backward on given (static or caller) tensors
+    def _fwd_bwd(self, src, lengths, tgt, im, ratio):
+        model = self.model
+        self.optimizer.zero_grad()
+        if im is not None:
+            loss, loss_mt, loss_vse = model(src, lengths, tgt, im, ratio, criterion_mt=self.criterion_mt, criterion_vse=self.criterion_vse)
+        else:
+            loss = model(src, lengths, tgt, ratio, criterion=self.criterion_mt)
+            loss_mt, loss_vse = loss, None
+        with model.precision_scope():
+            loss.backward()
+        vse = loss_vse if torch.is_tensor(loss_vse) else torch.zeros((), device=loss.device)
+        return torch.stack([loss.detach().reshape(()), loss_mt.detach().reshape(()), vse.detach().reshape(())])
+
+    @staticmethod
+    def _check_lengths(lengths, width):
+        ls = [int(x) for x in lengths]
+        if width != max(ls):
+            raise ValueError("the padded width must equal the longest sentence (pad_packed_sequence, Encoder.py:60)")
+        if any(ls[i] < ls[i + 1] for i in range(len(ls) - 1)):
+            raise RuntimeError("`lengths` array must be sorted in decreasing order (pack_padded_sequence, Encoder.py:55)")
+        return ls
+
+    def _capture(self, key, src, ls, tgt, im, ratio):
+        from . import ops
+        dev = src.device
+        st = {"src": src.clone(), "tgt": tgt.clone(), "im": im.clone() if im is not None else None,
+              "len": torch.tensor(ls, dtype=torch.int32, device=dev)}
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):     # warm-up outside the capture: sizes the workspaces, sets kernel attributes
+            self._fwd_bwd(st["src"], st["len"], st["tgt"], st["im"], ratio)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.optimizer.zero_grad()
+        if self._pool is None:
+            self._pool = torch.cuda.graph_pool_handle()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, pool=self._pool):
+            st["out"] = self._fwd_bwd(st["src"], st["len"], st["tgt"], st["im"], ratio)
+        st["graph"] = g
+        st["grads"] = [(p, p.grad) for p in self.optimizer._all_params() if p.grad is not None]
+        st["keepalive"] = list(ops._workspaces.values())     # the graph holds raw pointers into these scratch buffers
+        self._graphs[key] = st
+        return st
+
+    def step(self, src, lengths, tgt, im=None, teacher_force_ratio: float = 1.0):
+        model = self.model
+        model.train()
+        is_teacher = random.random() < teacher_force_ratio                        # V11:136 — decided before the graph is chosen
+        ratio = 1.0 if is_teacher else 0.0
+        dev = model._device()
+        src = src.to(dev, non_blocking=True)
+        tgt = tgt.to(dev, non_blocking=True)
+        im = im.to(dev, non_blocking=True) if im is not None else None
+        if not self.enabled or getattr(model, "_dropout_masks", None):
+            out = self._fwd_bwd(src, lengths, tgt, im, ratio)
+        else:
+            ls = self._check_lengths(lengths, src.shape[1])
+            key = (tuple(src.shape), tuple(tgt.shape), is_teacher, im is not None, getattr(model, "precision", "fp32"))
+            st = self._graphs.get(key)
+            if st is None:
+                st = self._capture(key, src, ls, tgt, im, ratio)
+            st["src"].copy_(src, non_blocking=True)
+            st["tgt"].copy_(tgt, non_blocking=True)
+            if im is not None:
+                st["im"].copy_(im, non_blocking=True)
+            st["len"].copy_(torch.tensor(ls, dtype=torch.int32), non_blocking=False)
+            st["graph"].replay()
+            for p, g in st["grads"]:       # the gradients live at fixed addresses inside the graph's pool
+                p.grad = g
+            out = st["out"].clone()        # the pool is shared between shapes: hand out a private copy of the three scalars
+        self.optimizer.step(clip=self.clip)
+        return out[0], out[1], out[2]
