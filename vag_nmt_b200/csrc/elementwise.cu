@@ -164,6 +164,39 @@ nll_rows_kernel(const float* __restrict__ logits, int64_t ld, const int64_t* __r
     }
 }
 
+// All Tt·B rows of a teacher-forced pass in one launch: per-row NLL into nll_out (row = t·B + b), then nll_sum_steps_kernel
+// adds the steps of a sentence in time order (the same summation order as one launch per step).
+__global__ void __launch_bounds__(256)
+nll_rows_all_kernel(const float* __restrict__ logits, int64_t ld, const int64_t* __restrict__ tgt, const float* __restrict__ weight,
+                    int64_t V, float* __restrict__ nll_out, float* __restrict__ lse_out) {
+    __shared__ float red[33];
+    const int r = blockIdx.x;
+    const float* row = logits + (int64_t)r * ld;
+    const float lse = block_row_lse(row, V, red);
+    if (threadIdx.x == 0) {
+        int64_t t = tgt[r];
+        if (t < 0 || t >= V) t = 0;
+        const float wgt = weight ? weight[t] : 1.0f;
+        nll_out[r] = -(row[t] - lse) * wgt;
+        lse_out[r] = lse;
+    }
+}
+__global__ void nll_sum_steps_kernel(float* __restrict__ loss_rows, const float* __restrict__ nll, int B, int Tt) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float a = 0.f;
+    for (int t = 0; t < Tt; ++t) a += nll[(int64_t)t * B + b];
+    loss_rows[b] = a;
+}
+int nll_rows_all(const float* logits, int64_t ld, const int64_t* tgt, const float* weight, int B, int Tt, int64_t V, float* loss_rows,
+                 float* lse_out, float* nll_scratch, cudaStream_t st) {
+    nll_rows_all_kernel<<<B * Tt, 256, 0, st>>>(logits, ld, tgt, weight, V, nll_scratch, lse_out);
+    VAG_LAUNCH_CHECK();
+    nll_sum_steps_kernel<<<ceil_div(B, 128), 128, 0, st>>>(loss_rows, nll_scratch, B, Tt);
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
 // out = {loss, loss_mt, loss_vse};  one block, deterministic order
 __global__ void __launch_bounds__(256)
 translation_loss_kernel(const float* __restrict__ loss_rows, const int64_t* __restrict__ tgt, int B, int Tt,

@@ -46,13 +46,16 @@ linear_rows32_kernel(Rows32Problem p0, Rows32Problem p1, int64_t ldy, int64_t ld
     const float* __restrict__ x = pr.x;
     const float* __restrict__ w = pr.w;
     const float* __restrict__ bias = pr.bias;
-    __shared__ float red[ROWS32_WARPS][32][BN + 1];
-    __shared__ __align__(16) float wtile[ROWS32_WARPS][BN * ROWS32_KC];
+    // dynamic shared memory: per-warp x tile [32 rows][36] (row pitch 36 floats: conflict-free 16-byte accesses both ways),
+    // per-warp weight tile [BN·32]; the cross-warp reduction buffer [16][32][BN+1] reuses the x tiles after the main loop
+    extern __shared__ __align__(16) float smem_dyn[];
+    constexpr int XP = ROWS32_KC + 4;
+    float* xs_all = smem_dyn;
+    float* wt_all = smem_dyn + ROWS32_WARPS * 32 * XP;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int n0 = blockIdx.x * BN;
-    const bool row_ok = lane < rows;
-    const float* xr = x + (int64_t)(row_ok ? lane : 0) * ldx;
-    float* wt = wtile[wid];
+    float* xs = xs_all + wid * 32 * XP;
+    float* wt = wt_all + wid * BN * ROWS32_KC;
     float acc[BN];
 #pragma unroll
     for (int c = 0; c < BN; ++c) acc[c] = 0.f;
@@ -70,23 +73,31 @@ linear_rows32_kernel(Rows32Problem p0, Rows32Problem p1, int64_t ldy, int64_t ld
                 wv[i] = __ldg(reinterpret_cast<const float4*>(w + (int64_t)k * ldw + col));
             }
         }
-        float4 xv[ROWS32_KC / 4];
+        // x tile, coalesced: instruction i covers rows 4i..4i+3, eight lanes per row (a lane-per-row read would touch 32
+        // cache lines per instruction and is bound by the L1 tag rate)
+        float4 xl[ROWS32_KC / 4];
 #pragma unroll
-        for (int q = 0; q < ROWS32_KC / 4; ++q) {
-            const int k = k0 + 4 * q;
-            xv[q] = (row_ok && k < K) ? __ldg(reinterpret_cast<const float4*>(xr + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < ROWS32_KC / 4; ++i) {
+            const int row = 4 * i + (lane >> 3), k = k0 + 4 * (lane & 7);
+            xl[i] = (row < rows && k < K) ? __ldg(reinterpret_cast<const float4*>(x + (int64_t)row * ldx + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+#pragma unroll
+        for (int i = 0; i < ROWS32_KC / 4; ++i)
+            *reinterpret_cast<float4*>(xs + (4 * i + (lane >> 3)) * XP + 4 * (lane & 7)) = rnd4<RB>(xl[i]);
         // ---- weight tile through shared memory (same layout for both weight orientations: [piece] of float4)
 #pragma unroll
         for (int i = 0; i < BN / 4; ++i) reinterpret_cast<float4*>(wt)[i * 32 + lane] = rnd4<RB>(wv[i]);
         __syncwarp();
+        float4 xv[ROWS32_KC / 4];     // lane = row from here on
+#pragma unroll
+        for (int q = 0; q < ROWS32_KC / 4; ++q) xv[q] = *reinterpret_cast<const float4*>(xs + lane * XP + 4 * q);
         if (WK) {
 #pragma unroll
             for (int c = 0; c < BN; ++c)
 #pragma unroll
                 for (int q = 0; q < ROWS32_KC / 4; ++q) {
                     const float4 wq = reinterpret_cast<const float4*>(wt)[c * 8 + q];
-                    const float4 xq = rnd4<RB>(xv[q]);
+                    const float4 xq = xv[q];
                     acc[c] = fmaf(xq.x, wq.x, acc[c]);
                     acc[c] = fmaf(xq.y, wq.y, acc[c]);
                     acc[c] = fmaf(xq.z, wq.z, acc[c]);
@@ -95,22 +106,24 @@ linear_rows32_kernel(Rows32Problem p0, Rows32Problem p1, int64_t ldy, int64_t ld
         } else {
 #pragma unroll
             for (int q = 0; q < ROWS32_KC / 4; ++q) {
-                const float4 xq = rnd4<RB>(xv[q]);
-                const float xs[4] = {xq.x, xq.y, xq.z, xq.w};
+                const float4 xq = xv[q];
+                const float xs4[4] = {xq.x, xq.y, xq.z, xq.w};
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
                     for (int i = 0; i < BN / 4; ++i) {
                         const float4 wq = reinterpret_cast<const float4*>(wt)[i * 32 + 4 * q + kk];
-                        acc[4 * i + 0] = fmaf(xs[kk], wq.x, acc[4 * i + 0]);
-                        acc[4 * i + 1] = fmaf(xs[kk], wq.y, acc[4 * i + 1]);
-                        acc[4 * i + 2] = fmaf(xs[kk], wq.z, acc[4 * i + 2]);
-                        acc[4 * i + 3] = fmaf(xs[kk], wq.w, acc[4 * i + 3]);
+                        acc[4 * i + 0] = fmaf(xs4[kk], wq.x, acc[4 * i + 0]);
+                        acc[4 * i + 1] = fmaf(xs4[kk], wq.y, acc[4 * i + 1]);
+                        acc[4 * i + 2] = fmaf(xs4[kk], wq.z, acc[4 * i + 2]);
+                        acc[4 * i + 3] = fmaf(xs4[kk], wq.w, acc[4 * i + 3]);
                     }
             }
         }
         __syncwarp();
     }
+    __syncthreads();                                   // every warp is done with its x tile: reuse the space
+    float (*red)[32][BN + 1] = reinterpret_cast<float (*)[32][BN + 1]>(smem_dyn);
 #pragma unroll
     for (int c = 0; c < BN; ++c) red[wid][lane][c] = acc[c];
     __syncthreads();
@@ -130,17 +143,29 @@ linear_rows32_kernel(Rows32Problem p0, Rows32Problem p1, int64_t ldy, int64_t ld
     }
 }
 
+template <int BN>
+constexpr size_t rows32_smem_bytes() { return (size_t)(ROWS32_WARPS * 32 * (ROWS32_KC + 4) + ROWS32_WARPS * BN * ROWS32_KC) * sizeof(float); }
+
+template <int BN, bool WK, bool RB>
+int launch_rows32_bn(const Rows32Problem& p0, const Rows32Problem& p1, int nprob, int64_t ldy, int64_t ldx, int64_t ldw, int rows,
+                     int K, int N, int flags, cudaStream_t st) {
+    static bool attr_set = false;
+    constexpr size_t smem = rows32_smem_bytes<BN>();
+    if (!attr_set) {
+        VAG_CUDA(cudaFuncSetAttribute(linear_rows32_kernel<BN, WK, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    linear_rows32_kernel<BN, WK, RB><<<dim3(ceil_div(N, BN), nprob), ROWS32_WARPS * 32, smem, st>>>(p0, p1, ldy, ldx, ldw, rows, K, N, flags);
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
 template <bool WK, bool RB>
 int launch_rows32(const Rows32Problem& p0, const Rows32Problem& p1, int nprob, int64_t ldy, int64_t ldx, int64_t ldw, int rows, int K, int N,
                   int flags, cudaStream_t st) {
     // enough CTAs for one wave on 148 SMs: 8 columns per CTA for wide outputs, 4 otherwise
-    if (N * nprob >= 960) {
-        linear_rows32_kernel<8, WK, RB><<<dim3(ceil_div(N, 8), nprob), ROWS32_WARPS * 32, 0, st>>>(p0, p1, ldy, ldx, ldw, rows, K, N, flags);
-    } else {
-        linear_rows32_kernel<4, WK, RB><<<dim3(ceil_div(N, 4), nprob), ROWS32_WARPS * 32, 0, st>>>(p0, p1, ldy, ldx, ldw, rows, K, N, flags);
-    }
-    VAG_LAUNCH_CHECK();
-    return VAG_OK;
+    if (N * nprob >= 960) return launch_rows32_bn<8, WK, RB>(p0, p1, nprob, ldy, ldx, ldw, rows, K, N, flags, st);
+    return launch_rows32_bn<4, WK, RB>(p0, p1, nprob, ldy, ldx, ldw, rows, K, N, flags, st);
 }
 
 }  // namespace

@@ -190,11 +190,11 @@ attention_bwd_kernel(float* __restrict__ dq, int64_t ld_dq, float* __restrict__ 
 // dlogits[r, v] = g[r]·w[tgt[r]]·(softmax(logits)[r, v] − [v == tgt[r]])
 __global__ void __launch_bounds__(256)
 nll_bwd_kernel(float* __restrict__ dlogits, int64_t ldd, const float* __restrict__ logits, int64_t ld, const float* __restrict__ lse,
-               const int64_t* __restrict__ tgt, const float* __restrict__ weight, const float* __restrict__ g, int64_t V) {
+               const int64_t* __restrict__ tgt, const float* __restrict__ weight, const float* __restrict__ g, int64_t V, int g_mod) {
     const int r = blockIdx.x;
     int64_t t = tgt[r];
     if (t < 0 || t >= V) t = 0;
-    const float scale = g[r] * (weight ? weight[t] : 1.f);
+    const float scale = g[g_mod > 0 ? r % g_mod : r] * (weight ? weight[t] : 1.f);   // g_mod = B: rows are t·B + b, g is per sentence
     const float l = lse[r];
     const float* src = logits + (int64_t)r * ld;
     float* dst = dlogits + (int64_t)r * ldd;
@@ -424,7 +424,7 @@ extern "C" int vag_nll_bwd_f32(float* dlogits, int64_t ldd, const float* logits,
                                const float* weight, const float* grad_rows, int rows, int64_t V, vag_stream_t stream) {
     VAG_REQUIRE(dlogits && logits && lse && tgt && grad_rows, "vag_nll_bwd_f32: null pointer");
     if (rows == 0) return VAG_OK;
-    nll_bwd_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(dlogits, ldd, logits, ld, lse, tgt, weight, grad_rows, V);
+    nll_bwd_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(dlogits, ldd, logits, ld, lse, tgt, weight, grad_rows, V, 0);
     VAG_LAUNCH_CHECK();
     return VAG_OK;
 }
@@ -542,6 +542,8 @@ extern "C" int vag_clip_adam_multi_f32(const vag_optim_tensor* tensors_device, i
 namespace vag {
 int row_argmax(const float* logits, int64_t ld, int rows, int64_t V, int64_t* out, int64_t out_stride, int64_t* next_in,
                cudaStream_t st);
+int nll_rows_all(const float* logits, int64_t ld, const int64_t* tgt, const float* weight, int B, int Tt, int64_t V, float* loss_rows,
+                 float* lse_out, float* nll_scratch, cudaStream_t st);
 // ---- tensor-core route of the batched backward contractions (dW = dyᵀ·x over all batch·time rows, dx = dy·W) --------------
 // tc_gemm wants both operands contraction-contiguous ([M, Kc] and [N, Kc]); an operand stored the other way round goes
 // through the transposing split (tc_split_t).  Scratch for the operand planes comes from the composite's workspace.
@@ -721,17 +723,23 @@ extern "C" int vag_decoder_seq_fwd_f32(const vag_decoder_weights* w, const float
     }
     if (teacher) {   // read-out and vocabulary projection for all steps at once
         gemm.new_step();
-        VAG_TRY(gemm.linear(s->t_all, E, s->h2_all, H, w->w1_w, H, w->w1_b, R, H, E, 0));
-        VAG_TRY(gemm.linear(s->t_all, E, s->e_all, E, w->w3_w, E, w->w3_b, R, E, E, VAG_LIN_ACCUMULATE));
-        VAG_TRY(gemm.linear(s->t_all, E, s->c_all, C, w->w2_w, C, w->w2_b, R, C, E, VAG_LIN_ACCUMULATE | VAG_LIN_TANH));
+        {   // t = tanh(W1 h2 + W3 e + W2 c + b1 + b3 + b2) as ONE contraction over the concatenated [h2 | e | c] (NMT_Decoder.py:137)
+            const float* const xs[3] = {s->h2_all, s->e_all, s->c_all};
+            const int64_t ldxs[3] = {H, E, C};
+            const int Ks[3] = {H, E, C};
+            const float* const wsp[3] = {w->w1_w, w->w3_w, w->w2_w};
+            const int64_t ldws[3] = {H, E, C};
+            const float* const bsp[3] = {w->w1_b, w->w3_b, w->w2_b};
+            VAG_TRY(gemm.linear3(s->t_all, E, xs, ldxs, Ks, wsp, ldws, bsp, R, E, VAG_LIN_TANH));
+        }
         if (out_mask) VAG_TRY(vag_mul_f32(s->t_all, out_mask, (int64_t)R * E, vs));                       // output dropout
         gemm.new_step();
         VAG_TRY(gemm.linear(s->logits_all, ldl, s->t_all, E, w->out_w, E, w->out_b, R, E, (int)V, 0));
     }
-    VAG_CUDA(cudaMemsetAsync(loss_rows, 0, sizeof(float) * (size_t)B, st));
-    for (int t = 0; t < Tt; ++t)
-        VAG_TRY(vag_nll_rows_f32(s->logits_all + (size_t)t * B * ldl, ldl, tgt_t + (size_t)t * B, nll_weight, B, V, loss_rows,
-                                 s->lse_all + (size_t)t * B, vs));
+    // NLL of all Tt·B rows in one launch + a per-sentence sum over the steps in time order (V11:140-141)
+    float* nll_scratch = (float*)wr;      // the weight-plane region is free again: every contraction has been enqueued
+    VAG_REQUIRE(wr && !ar.overflow && wb >= sizeof(float) * (size_t)R, "vag_decoder_seq_fwd_f32: workspace too small for the NLL rows");
+    VAG_TRY(nll_rows_all(s->logits_all, ldl, tgt_t, nll_weight, B, Tt, V, loss_rows, s->lse_all, nll_scratch, st));
     return VAG_OK;
 }
 
@@ -776,9 +784,8 @@ extern "C" int vag_decoder_seq_bwd_f32(const vag_decoder_weights* w, const float
     }
     // ---- batched over all steps: vocabulary projection and read-out
     if (ldd != V) VAG_CUDA(cudaMemsetAsync(dlogits, 0, sizeof(float) * (size_t)R * ldd, st));
-    for (int t = 0; t < Tt; ++t)
-        VAG_TRY(vag_nll_bwd_f32(dlogits + (size_t)t * B * ldd, ldd, s->logits_all + (size_t)t * B * ldl, ldl, s->lse_all + (size_t)t * B,
-                                tgt_t + (size_t)t * B, nll_weight, dloss_rows, B, V, vs));
+    nll_bwd_kernel<<<R, 256, 0, st>>>(dlogits, ldd, s->logits_all, ldl, s->lse_all, tgt_t, nll_weight, dloss_rows, V, B);   // all steps
+    VAG_LAUNCH_CHECK();
     {   // d_t = dlogits · out_w   (contraction over the vocabulary: rows of dlogits are padded, out_w is split transposed)
         const int r = gemm_tc_try(d_t, E, dlogits, ldd, 1, w->out_w, E, 1, R, E, (int)V, 0.f, g_tc_scratch.base, g_tc_scratch.cap, st, true);
         if (r < 0) return r;
