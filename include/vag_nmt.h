@@ -406,6 +406,11 @@ typedef struct vag_optim_tensor {
     float lr;
 } vag_optim_tensor;
 int vag_sumsq_multi_f32(const vag_optim_tensor* tensors_device, int n_tensors, int64_t max_n, float* accum, vag_stream_t stream);
+/* Deterministic Σ‖g‖² (no float atomics): out[0] = the sum, overwritten.  partials: scratch of vag_sumsq_multi_partials()
+ * floats.  Bit-identical from run to run and across data-parallel replicas, so the replicas stay in lockstep. */
+size_t vag_sumsq_multi_partials(int n_tensors, int64_t max_n);
+int vag_sumsq_multi_det_f32(const vag_optim_tensor* tensors_device, int n_tensors, int64_t max_n, float* out, float* partials,
+                            size_t n_partials, vag_stream_t stream);
 int vag_clip_adam_multi_f32(const vag_optim_tensor* tensors_device, int n_tensors, int64_t max_n, const float* grad_sumsq,
                             float clip, float beta1, float beta2, float eps, int step, vag_stream_t stream);
 int vag_clip_adam_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,

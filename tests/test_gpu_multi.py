@@ -63,7 +63,18 @@ def _worker(rank, world, port, out_dir):
         scale = float(ref[n].abs().max())
         if scale > 0:
             worst = max(worst, float((p.grad - ref[n]).abs().max()) / scale)
-    torch.save(dict(decode_ok=sharded == single, n=len(sharded), worst=worst), os.path.join(out_dir, f"m{rank}.pt"))
+    # ---- replicas stay bit-identical over optimiser steps on rank-different batches (deterministic Σ‖g‖², all-reduced grads)
+    from vag_nmt_b200.train import train_imagine_beam
+    opt = ClipAdam(model, lr=1e-2)
+    cv = DistributedPairwiseRankingLoss(margin=0.1)
+    for it in range(3):
+        bt = synthetic.make_batch(4, cfg["src_size"], cfg["tgt_size"], cfg["im_feats_size"], seed=50 + 2 * it + rank, max_len=9, min_len=2, mean=5, std=2.5)
+        train_imagine_beam(bt.src, bt.tgt, bt.im, bt.src_lengths, model, opt, crit, cv, 0.99, 1.0)
+    flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    both = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(both, flat)
+    in_sync = all(torch.equal(both[0], b) for b in both)
+    torch.save(dict(decode_ok=sharded == single, n=len(sharded), worst=worst, in_sync=in_sync), os.path.join(out_dir, f"m{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -75,3 +86,4 @@ def test_two_gpu_decode_sharding_and_data_parallel_gradients(tmp_path):
         res = torch.load(tmp_path / f"m{r}.pt")
         assert res["decode_ok"] and res["n"] == 13
         assert res["worst"] < 1e-4, res["worst"]       # DP gradients == single-process gradients of the global batch
+        assert res["in_sync"]                            # replicas bit-identical after three data-parallel steps

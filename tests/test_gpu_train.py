@@ -230,3 +230,74 @@ def test_graphed_step_matches_eager_step(kind):
         assert abs(a - b) < 1e-5 * max(1.0, abs(a)), (l0, l1)
     for k in p0:
         assert float((p0[k] - p1[k]).abs().max()) < 1e-5, k
+
+
+def test_global_norm_is_deterministic_and_matches_torch():
+    """vag_sumsq_multi_det_f32: bit-identical from call to call (no float atomics) and equal to torch's norm."""
+    from vag_nmt_b200 import train_ops as T
+    g = torch.Generator().manual_seed(3)
+    shapes = [(9391, 256), (1536, 512), (1536,), (7,), (1024, 1024)]
+    ps = [torch.randn(*s, generator=g).cuda() for s in shapes]
+    gs = [torch.randn(*s, generator=g).cuda() for s in shapes]
+    entries = [(p, gr, torch.zeros_like(p), torch.zeros_like(p), 0.0, 1e-3) for p, gr in zip(ps, gs)]
+    table = T.optim_table(entries).cuda()
+    n_part = T._cabi.lib().vag_sumsq_multi_partials(len(entries), max(p.numel() for p in ps))
+    partials = torch.empty(n_part, device="cuda")
+    outs = []
+    for _ in range(5):
+        out = torch.full((1,), -1.0, device="cuda")
+        T.sumsq_multi_det_(out, table, len(entries), max(p.numel() for p in ps), partials)
+        outs.append(float(out))
+    assert len(set(outs)) == 1
+    ref = float(sum((gr.double() ** 2).sum() for gr in gs))
+    assert abs(outs[0] - ref) < 1e-5 * ref
+
+
+def test_split_graph_step_with_eager_global_ranking_loss_matches_eager_step():
+    """The data-parallel flavour of GraphedTrainStep (forward graph → eager all-gather + ranking-loss kernel → backward graph)
+    on a one-rank NCCL group: same parameter walk as the eager driver with DistributedPairwiseRankingLoss."""
+    import socket
+    import torch.distributed as dist
+    import vag_nmt_b200 as vag
+    from vag_nmt_b200 import synthetic
+    from vag_nmt_b200.optim import ClipAdam
+    from vag_nmt_b200.train import DistributedPairwiseRankingLoss, GraphedTrainStep, train_imagine_beam
+    own_group = not dist.is_initialized()
+    if own_group:
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        cfg = dict(synthetic.TINY)
+        batches = _same_shape_batches(cfg, 3, 8, 40)
+        w = torch.ones(cfg["tgt_size"])
+        w[0] = 0
+        results = []
+        for graphed in (False, True):
+            model = build_mm(cfg, 11).cuda()
+            crit = torch.nn.NLLLoss(weight=w.cuda(), reduce=False)
+            cv = DistributedPairwiseRankingLoss(margin=0.1)
+            opt = ClipAdam(model, lr=1e-2)
+            stepper = GraphedTrainStep(model, opt, crit, cv, clip=1.0, enabled=True)
+            stepper._split = True           # force the two-graph path although the world has one rank
+            losses = []
+            for it in range(6):
+                bt = batches[it % len(batches)]
+                if graphed:
+                    out = stepper.step(bt.src, bt.src_lengths, bt.tgt, bt.im, 1.0)
+                    losses.append([float(v) for v in out])
+                else:
+                    losses.append(list(train_imagine_beam(bt.src, bt.tgt, bt.im, bt.src_lengths, model, opt, crit, cv, 0.99, 1.0)))
+            if graphed:
+                assert len(stepper._graphs) == 1 and next(iter(stepper._graphs.values())).get("split")
+            results.append((losses, {k: v.detach().clone() for k, v in model.state_dict().items()}))
+        (l0, p0), (l1, p1) = results
+        for a, b in zip(l0, l1):
+            for x, y in zip(a, b):
+                assert abs(x - y) < 1e-5 * max(1.0, abs(x)), (l0, l1)
+        for k in p0:
+            assert float((p0[k] - p1[k]).abs().max()) < 1e-5, k
+    finally:
+        if own_group:
+            dist.destroy_process_group()

@@ -35,4 +35,6 @@ for graphed in (False, True):
     allc = [torch.zeros_like(chk) for _ in range(world)]; dist.all_gather(allc, chk)
     if rank == 0:
         print(f"world {world} graphed={graphed}: {float(ms):.3f} ms/step, ~{sum(toks) * (n // 8) * world / (float(ms) * n / 1e3):.0f} tok/s, loss {float(loss):.5f}, replicas in sync: {all(float(c) == float(allc[0]) for c in allc)}")
+dist.barrier(); torch.cuda.synchronize()
+if rank == 0: print("clean exit", flush=True)
 dist.destroy_process_group()

@@ -119,6 +119,8 @@ SIGNATURES = {
     "vag_encoder_bwd_f32": (I, [P, P, P, I, I, P, P, P, P, P, P, P, P, P, P, P, P, P, SZ, P]),
     "vag_sumsq_f32": (I, [P, I64, P, P]),
     "vag_sumsq_multi_f32": (I, [P, I, I64, P, P]),
+    "vag_sumsq_multi_partials": (SZ, [I, I64]),
+    "vag_sumsq_multi_det_f32": (I, [P, I, I64, P, P, SZ, P]),
     "vag_clip_adam_multi_f32": (I, [P, I, I64, P, F, F, F, F, I, P]),
     "vag_clip_adam_f32": (I, [P, P, P, P, I64, P, F, F, F, F, F, F, I, P]),
 }

@@ -330,6 +330,36 @@ __global__ void __launch_bounds__(256) sumsq_multi_kernel(const vag_optim_tensor
         if (s != 0.f) atomicAdd(out, s);
     }
 }
+// Deterministic flavour: every block stores its partial (fixed reduction tree inside the block), one block then adds the
+// partials in index order.  Float atomics would make Σ‖g‖² — hence the clip coefficient, hence every parameter — differ in
+// the last bits from run to run and, under data parallelism, from replica to replica.
+__global__ void __launch_bounds__(256) sumsq_multi_partials_kernel(const vag_optim_tensor* __restrict__ t, float* __restrict__ partials) {
+    const vag_optim_tensor e = t[blockIdx.y];
+    float a = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < e.n; i += (int64_t)gridDim.x * blockDim.x) a = fmaf(e.grad[i], e.grad[i], a);
+    a = warp_sum(a);
+    __shared__ float red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int w = 0; w < 8; ++w) s += red[w];
+        partials[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = s;
+    }
+}
+__global__ void __launch_bounds__(256) sumsq_finish_kernel(const float* __restrict__ partials, int n, float* __restrict__ out) {
+    float a = 0.f;
+    for (int i = threadIdx.x; i < n; i += 256) a += partials[i];
+    a = warp_sum(a);
+    __shared__ float red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int w = 0; w < 8; ++w) s += red[w];
+        out[0] = s;
+    }
+}
 __global__ void __launch_bounds__(256)
 clip_adam_multi_kernel(const vag_optim_tensor* __restrict__ t, const float* __restrict__ sumsq, float clip, float beta1, float beta2,
                        float eps, float bc1, float bc2_sqrt) {
@@ -515,6 +545,27 @@ extern "C" int vag_sumsq_multi_f32(const vag_optim_tensor* tensors_device, int n
     if (n_tensors == 0 || max_n == 0) return VAG_OK;
     dim3 grid((unsigned)std::min<int64_t>((max_n + 255) / 256, 128), (unsigned)n_tensors);
     sumsq_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tensors_device, accum);
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
+extern "C" size_t vag_sumsq_multi_partials(int n_tensors, int64_t max_n) {
+    return (size_t)std::min<int64_t>((max_n + 255) / 256, 128) * (size_t)std::max(n_tensors, 0);
+}
+
+extern "C" int vag_sumsq_multi_det_f32(const vag_optim_tensor* tensors_device, int n_tensors, int64_t max_n, float* out,
+                                       float* partials, size_t n_partials, vag_stream_t stream) {
+    VAG_REQUIRE(tensors_device && out && partials && n_tensors >= 0 && max_n >= 0, "vag_sumsq_multi_det_f32: bad argument");
+    VAG_REQUIRE(n_partials >= vag_sumsq_multi_partials(n_tensors, max_n), "vag_sumsq_multi_det_f32: partials buffer too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_tensors == 0 || max_n == 0) {
+        VAG_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
+        return VAG_OK;
+    }
+    dim3 grid((unsigned)std::min<int64_t>((max_n + 255) / 256, 128), (unsigned)n_tensors);
+    sumsq_multi_partials_kernel<<<grid, 256, 0, st>>>(tensors_device, partials);
+    VAG_LAUNCH_CHECK();
+    sumsq_finish_kernel<<<1, 256, 0, st>>>(partials, (int)(grid.x * grid.y), out);
     VAG_LAUNCH_CHECK();
     return VAG_OK;
 }

@@ -3,7 +3,7 @@
 Mirrors ``torch.nn.utils.clip_grad_norm_(model.parameters(), clip)`` followed by ``optim.Adam(param_groups).step()``
 with the parameter groups of nmt_multimodal_beam_DE.py:303-332 (weight decay — added to the gradient, not
 decoupled — on every parameter whose name lacks 'bias').  All arithmetic runs in TWO launches for all parameter tensors
-(vag_sumsq_multi_f32, vag_clip_adam_multi_f32 over a descriptor table); the clip coefficient is read on the device, so a
+(vag_sumsq_multi_det_f32, vag_clip_adam_multi_f32 over a descriptor table); the clip coefficient is read on the device, so a
 step never synchronises.
 """
 from __future__ import annotations
@@ -75,7 +75,6 @@ class ClipAdam:
         dev = params[0].device
         if self._sumsq is None or self._sumsq.device != dev:
             self._sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
-        self._sumsq.zero_()
         self.step_count += 1
         b1, b2 = self.betas
         # ONE descriptor table (48 B per tensor) and two launches for all tensors: Σ‖g‖², then clip + Adam
@@ -98,7 +97,10 @@ class ClipAdam:
         else:
             table = T.optim_table(entries).to(dev, non_blocking=True)
             self._table_key = tkey
-        T.sumsq_multi_(self._sumsq, table, len(entries), max_n)
+        n_part = T._cabi.lib().vag_sumsq_multi_partials(len(entries), max_n)
+        if getattr(self, "_partials", None) is None or self._partials.numel() < n_part or self._partials.device != dev:
+            self._partials = torch.empty(max(int(n_part), 1), dtype=torch.float32, device=dev)
+        T.sumsq_multi_det_(self._sumsq, table, len(entries), max_n, self._partials)   # deterministic: replicas stay bit-identical
         T.clip_adam_multi_(table, len(entries), max_n, self._sumsq, clip if clip is not None else float("inf"), b1, b2, self.eps,
                            self.step_count)
         self._table = table   # keep the descriptors alive until the kernels have run

@@ -85,6 +85,20 @@ class DistributedPairwiseRankingLoss(PairwiseRankingLoss):
 
 
 # ---------------------------------------------------------------------------------------------------- CUDA-graph step
+class _SurrogateRankLoss(torch.nn.Module):
+    """Stand-in for the ranking loss inside a captured forward: ⟨im, G_im⟩ + ⟨s, G_s⟩ with G filled in later (its gradient with
+    respect to the embeddings is G).  Remembers the embeddings it was called with — they are the inputs of the real loss."""
+
+    def __init__(self, g_im, g_s):
+        super().__init__()
+        self.g_im, self.g_s = g_im, g_s
+        self.im = self.s = None
+
+    def forward(self, im, s):
+        self.im, self.s = im.detach(), s.detach()
+        return (im * self.g_im).sum() + (s * self.g_s).sum()
+
+
 class GraphedTrainStep:
     """The optimisation step of train.py:36-51 with zero_grad → forward → backward replayed from a CUDA graph.
 
@@ -94,7 +108,8 @@ class GraphedTrainStep:
     so one captured graph per batch SHAPE (B, Ts, Tt, teacher-forced?) serves every later batch of that shape.  Shapes are
     captured lazily the first time they appear (one eager warm-up pass + the capture ≈ three steps' worth of time) and
     share one memory pool.  Gradient all-reduce (data parallel), clipping and Adam run after the replay through
-    ``ClipAdam.step``, exactly as in the eager path.
+    ``ClipAdam.step``, exactly as in the eager path.  No collective is ever captured: with the global-batch ranking loss the
+    step is two graphs (forward, backward) around the eager all-gather + ranking-loss kernel.
 
     ``step(src, lengths, tgt, im)`` takes the same arguments as ``train_imagine_beam`` (``im=None`` for the text-only
     model) and returns device scalars (loss, loss_mt, loss_vse) — no host synchronisation.
@@ -106,10 +121,13 @@ class GraphedTrainStep:
         self.clip = clip
         self._graphs: Dict[tuple, dict] = {}
         self._pool = None
-        if enabled is None:   # collectives inside a capture (the global-batch ranking loss under data parallelism) stay eager
-            import torch.distributed as dist
-            enabled = not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
-        self.enabled = enabled
+        self.enabled = True if enabled is None else enabled
+        # Data parallel with the global-batch ranking loss: its all-gather must stay OUTSIDE the graphs (ranks capture
+        # independently, and a captured collective would have to be matched launch for launch) — the step is then two graphs,
+        # forward and backward, with the eager collective + ranking-loss kernel between them (see _capture_split).
+        import torch.distributed as dist
+        self._world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        self._split = self._world > 1 and isinstance(criterion_vse, DistributedPairwiseRankingLoss)
 
     # -- one forward + backward on given (static or caller) tensors
     def _fwd_bwd(self, src, lengths, tgt, im, ratio):
@@ -142,7 +160,15 @@ class GraphedTrainStep:
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):     # warm-up outside the capture: sizes the workspaces, sets kernel attributes
-            self._fwd_bwd(st["src"], st["len"], st["tgt"], st["im"], ratio)
+            # Ranks capture independently (a shape is new on one rank and known on another), so the warm-up must not execute a
+            # collective the peers would not match: it uses the LOCAL ranking loss — its results are discarded anyway.
+            crit = self.criterion_vse
+            if isinstance(crit, DistributedPairwiseRankingLoss):
+                self.criterion_vse = PairwiseRankingLoss(crit.margin)
+            try:
+                self._fwd_bwd(st["src"], st["len"], st["tgt"], st["im"], ratio)
+            finally:
+                self.criterion_vse = crit
         torch.cuda.current_stream(dev).wait_stream(side)
         self.optimizer.zero_grad()
         if self._pool is None:
@@ -155,6 +181,67 @@ class GraphedTrainStep:
         st["keepalive"] = list(ops._workspaces.values())     # the graph holds raw pointers into these scratch buffers
         self._graphs[key] = st
         return st
+
+    def _capture_split(self, key, src, ls, tgt, im, ratio):
+        """Data-parallel flavour: graph A = zero_grad + forward with a SURROGATE ranking term ⟨im_emb, G_im⟩ + ⟨txt_emb, G_s⟩,
+        graph B = backward.  Between the replays the real global ranking loss runs eagerly (all-gather of the embeddings,
+        vag_rank_loss_f32 with gradients) and writes its local gradient rows into G_im / G_s — the surrogate's gradient with
+        respect to the embeddings is exactly G, so graph B back-propagates the true loss."""
+        from . import ops
+        model, dev = self.model, src.device
+        st = {"src": src.clone(), "tgt": tgt.clone(), "im": im.clone(), "len": torch.tensor(ls, dtype=torch.int32, device=dev), "split": True}
+        S = model.shared_embedding_size
+        st["G_im"] = torch.zeros(src.shape[0], S, dtype=torch.float32, device=dev)
+        st["G_s"] = torch.zeros_like(st["G_im"])
+        sur = _SurrogateRankLoss(st["G_im"], st["G_s"])
+        crit = self.criterion_vse
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):       # warm-up without collectives (local ranking loss; results are discarded)
+            self.criterion_vse = PairwiseRankingLoss(crit.margin)
+            try:
+                self._fwd_bwd(st["src"], st["len"], st["tgt"], st["im"], ratio)
+            finally:
+                self.criterion_vse = crit
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.optimizer.zero_grad()
+        if self._pool is None:
+            self._pool = torch.cuda.graph_pool_handle()
+        ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(ga, pool=self._pool):
+            self.optimizer.zero_grad()
+            loss, loss_mt, _ = model(st["src"], st["len"], st["tgt"], st["im"], ratio, criterion_mt=self.criterion_mt, criterion_vse=sur)
+            st["mt"] = loss_mt.detach().reshape(())
+            st["im_emb"], st["txt_emb"] = sur.im, sur.s
+        with torch.cuda.graph(gb, pool=self._pool):
+            with model.precision_scope():
+                loss.backward()
+        del loss
+        st["graph"], st["graph_b"] = ga, gb
+        st["grads"] = [(p, p.grad) for p in self.optimizer._all_params() if p.grad is not None]
+        st["keepalive"] = list(ops._workspaces.values())
+        self._graphs[key] = st
+        return st
+
+    def _global_rank_loss(self, st):
+        """Eager middle of the split step → loss_vse over the global batch; fills G_im / G_s (rows of this rank, × world so that
+        the averaging gradient all-reduce yields the single-process sum, as in _GlobalRankLossFn)."""
+        import torch.distributed as dist
+        from . import ops
+        crit = self.criterion_vse
+        world, rank = self._world, dist.get_rank(crit.group)
+        im, s = st["im_emb"], st["txt_emb"]
+        Bl = im.shape[0]
+        im_all = torch.empty(world * Bl, im.shape[1], dtype=im.dtype, device=im.device)
+        s_all = torch.empty_like(im_all)
+        dist.all_gather_into_tensor(im_all, im, group=crit.group)
+        dist.all_gather_into_tensor(s_all, s, group=crit.group)
+        loss, g_im, g_s = ops.rank_loss(im_all, s_all, float(crit.margin), crit.one_direction, want_grad=True)
+        sl = slice(rank * Bl, (rank + 1) * Bl)
+        # .data: the surrogate saved G for its backward; filling it must not trip autograd's version check at capture time
+        st["G_im"].data.copy_(g_im[sl]).mul_(float(world))
+        st["G_s"].data.copy_(g_s[sl]).mul_(float(world))
+        return loss
 
     def step(self, src, lengths, tgt, im=None, teacher_force_ratio: float = 1.0):
         model = self.model
@@ -172,15 +259,22 @@ class GraphedTrainStep:
             key = (tuple(src.shape), tuple(tgt.shape), is_teacher, im is not None, getattr(model, "precision", "fp32"))
             st = self._graphs.get(key)
             if st is None:
-                st = self._capture(key, src, ls, tgt, im, ratio)
+                split = self._split and im is not None
+                st = (self._capture_split if split else self._capture)(key, src, ls, tgt, im, ratio)
             st["src"].copy_(src, non_blocking=True)
             st["tgt"].copy_(tgt, non_blocking=True)
             if im is not None:
                 st["im"].copy_(im, non_blocking=True)
             st["len"].copy_(torch.tensor(ls, dtype=torch.int32), non_blocking=False)
             st["graph"].replay()
+            if st.get("split"):
+                vse = self._global_rank_loss(st).reshape(())
+                st["graph_b"].replay()
+                w = float(model.loss_w)
+                out = torch.stack([w * st["mt"] + (1.0 - w) * vse, st["mt"], vse])
+            else:
+                out = st["out"].clone()    # the pool is shared between shapes: hand out a private copy of the three scalars
             for p, g in st["grads"]:       # the gradients live at fixed addresses inside the graph's pool
                 p.grad = g
-            out = st["out"].clone()        # the pool is shared between shapes: hand out a private copy of the three scalars
         self.optimizer.step(clip=self.clip)
         return out[0], out[1], out[2]

@@ -166,6 +166,14 @@ def sumsq_multi_(accum: torch.Tensor, table_dev: torch.Tensor, n_tensors: int, m
         check(lib.vag_sumsq_multi_f32(table_dev.data_ptr(), int(n_tensors), int(max_n), accum.data_ptr(), stream_ptr()))
 
 
+def sumsq_multi_det_(out: torch.Tensor, table_dev: torch.Tensor, n_tensors: int, max_n: int, partials: torch.Tensor) -> None:
+    """out[0] = Σ‖g‖² over all tensors, deterministic (block partials added in index order, no atomics)."""
+    lib = _cabi.lib()
+    with on_device(out.device):
+        check(lib.vag_sumsq_multi_det_f32(table_dev.data_ptr(), int(n_tensors), int(max_n), out.data_ptr(), partials.data_ptr(),
+                                          partials.numel(), stream_ptr()))
+
+
 def clip_adam_multi_(table_dev: torch.Tensor, n_tensors: int, max_n: int, sumsq, clip, beta1, beta2, eps, step) -> None:
     lib = _cabi.lib()
     with on_device(sumsq.device):
