@@ -263,6 +263,50 @@ def measure_train(args, dev, world, rank, timed, precision="bf16"):
     return res
 
 
+def measure_text_only(args, dev, world, rank, timed, src_dev, lens):
+    """BASELINE configs[4]: the text-only baseline (NMT_Seq2Seq_Beam_V2, no visual grounding) — beam-12 decoding of the same
+    1000-sentence shard and the training step at batch 32 (bf16 mode), same timing rules as the multimodal numbers."""
+    import vag_nmt_b200 as vag
+    from vag_nmt_b200 import synthetic
+    from vag_nmt_b200.optim import ClipAdam
+    from vag_nmt_b200.train import GraphedTrainStep
+    cfg = synthetic.DE
+    torch.manual_seed(1234)
+    model = vag.NMT_Seq2Seq_Beam_V2(cfg["src_size"], cfg["tgt_size"], cfg["src_embedding_size"], cfg["tgt_embedding_size"],
+                                    cfg["hidden_size"], tied_emb=True).to(dev).eval()
+    K, L = args.beam, args.max_length
+    for _ in range(3):
+        model.decode_device(src_dev, lens, None, K, L)
+    ms = timed(lambda: model.decode_device(src_dev, lens, None, K, L), args.steps)
+    out = {"decode": {"metric": METRIC, "value": args.sentences * world * args.steps / (ms / 1e3), "unit": UNIT,
+                      "ms_per_step": ms / args.steps, "dtype": "f32"}}
+    model.precision = "bf16"
+    opt = ClipAdam(model, lr=4e-4)
+    w = torch.ones(cfg["tgt_size"], device=dev)
+    w[0] = 0
+    crit = torch.nn.NLLLoss(weight=w, reduction="none")
+    batches = [synthetic.make_batch(32, cfg["src_size"], cfg["tgt_size"], None, seed=100 + 8 * i + rank) for i in range(8)]
+    pinned = [(bt.src.pin_memory(), bt.tgt.pin_memory(), bt.src_lengths) for bt in batches]
+    tokens = [int((bt.tgt != 0).sum()) for bt in batches]
+    stepper = GraphedTrainStep(model, opt, crit, None, clip=1.0)
+    state = {"i": 0}
+
+    def step():
+        src, tgt, ls = pinned[state["i"] % len(pinned)]
+        state["i"] += 1
+        state["loss"] = stepper.step(src, ls, tgt, None, 1.0)[0]
+
+    for _ in range(len(pinned)):
+        step()
+    state["i"] = 0
+    steps = max(args.steps, 8)
+    ms = timed(step, steps)
+    tok = sum(tokens[i % len(tokens)] for i in range(steps)) * world
+    out["train"] = {"metric": "train tgt tokens/sec", "value": tok / (ms / 1e3), "unit": "tokens/s", "ms_per_step": ms / steps,
+                    "batch_per_gpu": 32, "dtype": "bf16", "loss_after": float(state["loss"])}
+    return out
+
+
 # ------------------------------------------------------------------------------------------ B200 arm
 def run_ours(args):
     import torch.distributed as dist
@@ -387,6 +431,8 @@ def run_ours(args):
                                           f"max_length {L}, oracle/vag_oracle.py (torch CPU fp32)",
                                 "token_exact_sentences": f"{agree}/{n}"}
     del model
+    torch.cuda.empty_cache()
+    line["text_only"] = measure_text_only(args, dev, world, rank, timed, src_dev, lens)   # BASELINE configs[4]
     torch.cuda.empty_cache()
     line["train"] = measure_train(args, dev, world, rank, timed, "bf16")       # BASELINE configs[1]: training step bf16
     line["train_f32"] = measure_train(args, dev, world, rank, timed, "fp32")

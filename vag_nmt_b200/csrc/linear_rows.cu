@@ -8,7 +8,7 @@
 //     shared memory, the epilogue (bias, accumulate, tanh) runs on the first BN·32 threads;
 //   * WK = true : W(c, k) = w[c·ldw + k]   (y = x·Wᵀ, the forward layout,  layers/NMT_Decoder.py:121-137)
 //     WK = false: W(c, k) = w[k·ldw + c]   (dx = dy·W, the same weight read for back-propagation through time).
-#include "common.cuh"
+#include "linear_rows.cuh"
 #include <cuda_bf16.h>
 
 namespace vag {
@@ -24,11 +24,8 @@ __device__ __forceinline__ float4 rnd4(float4 v) {
     return v;
 }
 
-struct Rows32Problem {
-    float* y;
-    const float* x;
-    const float* w;
-    const float* bias;
+struct Rows32Args {
+    Rows32Problem p[2];
 };
 
 constexpr int ROWS32_WARPS = 16;
@@ -39,13 +36,16 @@ constexpr int ROWS32_KC = 32;   // contraction indices per warp per pass
 // goes through a per-warp shared-memory slot, and the FMAs read it back as broadcast LDS.128.
 template <int BN, bool WK, bool RB>
 __global__ void __launch_bounds__(ROWS32_WARPS * 32, 2)
-linear_rows32_kernel(Rows32Problem p0, Rows32Problem p1, int64_t ldy, int64_t ldx, int64_t ldw, int rows, int K, int N, int flags) {
-    // blockIdx.y selects one of two independent problems of identical shape (the two directions of the encoder GRU)
-    const Rows32Problem pr = blockIdx.y == 0 ? p0 : p1;
+linear_rows32_kernel(const __grid_constant__ Rows32Args args, int rows, int flags) {
+    // blockIdx.y selects one of two independent problems (own N, pitches and segments); __grid_constant__ keeps the
+    // dynamically indexed descriptors in parameter space instead of a per-thread local copy
+    const Rows32Problem& pr = args.p[blockIdx.y];
+    const int N = pr.N;
+    const int n0 = blockIdx.x * BN;
+    if (n0 >= N) return;                               // the grid is sized for the wider problem
     float* __restrict__ y = pr.y;
-    const float* __restrict__ x = pr.x;
-    const float* __restrict__ w = pr.w;
     const float* __restrict__ bias = pr.bias;
+    const int64_t ldy = pr.ldy;
     // dynamic shared memory: per-warp x tile [32 rows][36] (row pitch 36 floats: conflict-free 16-byte accesses both ways),
     // per-warp weight tile [BN·32]; the cross-warp reduction buffer [16][32][BN+1] reuses the x tiles after the main loop
     extern __shared__ __align__(16) float smem_dyn[];
@@ -53,13 +53,21 @@ linear_rows32_kernel(Rows32Problem p0, Rows32Problem p1, int64_t ldy, int64_t ld
     float* xs_all = smem_dyn;
     float* wt_all = smem_dyn + ROWS32_WARPS * 32 * XP;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int n0 = blockIdx.x * BN;
     float* xs = xs_all + wid * 32 * XP;
     float* wt = wt_all + wid * BN * ROWS32_KC;
     float acc[BN];
 #pragma unroll
     for (int c = 0; c < BN; ++c) acc[c] = 0.f;
-    for (int k0 = wid * ROWS32_KC; k0 < K; k0 += ROWS32_WARPS * ROWS32_KC) {
+    // passes of 32 contraction indices, segment 0 first, dealt round-robin to the 16 warps
+    const int passes0 = (pr.seg[0].K + ROWS32_KC - 1) / ROWS32_KC;
+    const int passes = passes0 + (pr.nseg > 1 ? (pr.seg[1].K + ROWS32_KC - 1) / ROWS32_KC : 0);
+    for (int pass = wid; pass < passes; pass += ROWS32_WARPS) {
+        const Rows32Seg& sg = pr.seg[pass < passes0 ? 0 : 1];
+        const int k0 = (pass < passes0 ? pass : pass - passes0) * ROWS32_KC;
+        const float* __restrict__ x = sg.x;
+        const float* __restrict__ w = sg.w;
+        const int64_t ldx = sg.ldx, ldw = sg.ldw;
+        const int K = sg.K;
         // ---- issue every load of the pass
         float4 wv[BN / 4];
 #pragma unroll
@@ -147,25 +155,28 @@ template <int BN>
 constexpr size_t rows32_smem_bytes() { return (size_t)(ROWS32_WARPS * 32 * (ROWS32_KC + 4) + ROWS32_WARPS * BN * ROWS32_KC) * sizeof(float); }
 
 template <int BN, bool WK, bool RB>
-int launch_rows32_bn(const Rows32Problem& p0, const Rows32Problem& p1, int nprob, int64_t ldy, int64_t ldx, int64_t ldw, int rows,
-                     int K, int N, int flags, cudaStream_t st) {
+int launch_rows32_bn(const Rows32Problem& p0, const Rows32Problem& p1, int nprob, int rows, int flags, cudaStream_t st) {
     static bool attr_set = false;
     constexpr size_t smem = rows32_smem_bytes<BN>();
     if (!attr_set) {
         VAG_CUDA(cudaFuncSetAttribute(linear_rows32_kernel<BN, WK, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    linear_rows32_kernel<BN, WK, RB><<<dim3(ceil_div(N, BN), nprob), ROWS32_WARPS * 32, smem, st>>>(p0, p1, ldy, ldx, ldw, rows, K, N, flags);
+    const int nmax = nprob > 1 ? (p0.N > p1.N ? p0.N : p1.N) : p0.N;
+    Rows32Args args;
+    args.p[0] = p0;
+    args.p[1] = p1;
+    linear_rows32_kernel<BN, WK, RB><<<dim3(ceil_div(nmax, BN), nprob), ROWS32_WARPS * 32, smem, st>>>(args, rows, flags);
     VAG_LAUNCH_CHECK();
     return VAG_OK;
 }
 
 template <bool WK, bool RB>
-int launch_rows32(const Rows32Problem& p0, const Rows32Problem& p1, int nprob, int64_t ldy, int64_t ldx, int64_t ldw, int rows, int K, int N,
-                  int flags, cudaStream_t st) {
+int launch_rows32(const Rows32Problem& p0, const Rows32Problem& p1, int nprob, int rows, int flags, cudaStream_t st) {
     // enough CTAs for one wave on 148 SMs: 8 columns per CTA for wide outputs, 4 otherwise
-    if (N * nprob >= 960) return launch_rows32_bn<8, WK, RB>(p0, p1, nprob, ldy, ldx, ldw, rows, K, N, flags, st);
-    return launch_rows32_bn<4, WK, RB>(p0, p1, nprob, ldy, ldx, ldw, rows, K, N, flags, st);
+    const int ntot = p0.N + (nprob > 1 ? p1.N : 0);
+    if (ntot >= 960) return launch_rows32_bn<8, WK, RB>(p0, p1, nprob, rows, flags, st);
+    return launch_rows32_bn<4, WK, RB>(p0, p1, nprob, rows, flags, st);
 }
 
 }  // namespace
@@ -178,29 +189,29 @@ bool rows32_ok(const float* x, int64_t ldx, const float* w, int64_t ldw, int row
     if (!wk && (N & 3)) return false;
     return true;
 }
+bool rows32_problem_ok(const Rows32Problem& p, int rows, bool wk) {
+    if (p.nseg < 1 || p.nseg > 2) return false;
+    for (int i = 0; i < p.nseg; ++i)
+        if (!rows32_ok(p.seg[i].x, p.seg[i].ldx, p.seg[i].w, p.seg[i].ldw, rows, p.seg[i].K, p.N, wk)) return false;
+    return true;
+}
+
+int linear_rows32_multi(const Rows32Problem* probs, int nprob, int rows, int flags, bool wk, bool round_bf16, cudaStream_t st) {
+    const Rows32Problem& p0 = probs[0];
+    const Rows32Problem& p1 = probs[nprob > 1 ? 1 : 0];
+    if (wk) {
+        if (round_bf16) return launch_rows32<true, true>(p0, p1, nprob, rows, flags, st);
+        return launch_rows32<true, false>(p0, p1, nprob, rows, flags, st);
+    }
+    if (round_bf16) return launch_rows32<false, true>(p0, p1, nprob, rows, flags, st);
+    return launch_rows32<false, false>(p0, p1, nprob, rows, flags, st);
+}
 
 // y[rows, N] (+)= x[rows, K] · W(c, k)  (+ bias) (tanh);  round_bf16: operands rounded to bfloat16 first (bf16 mode)
 int linear_rows32(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, int rows,
                   int K, int N, int flags, bool wk, bool round_bf16, cudaStream_t st) {
-    const Rows32Problem p{y, x, w, bias};
-    if (wk) {
-        if (round_bf16) return launch_rows32<true, true>(p, p, 1, ldy, ldx, ldw, rows, K, N, flags, st);
-        return launch_rows32<true, false>(p, p, 1, ldy, ldx, ldw, rows, K, N, flags, st);
-    }
-    if (round_bf16) return launch_rows32<false, true>(p, p, 1, ldy, ldx, ldw, rows, K, N, flags, st);
-    return launch_rows32<false, false>(p, p, 1, ldy, ldx, ldw, rows, K, N, flags, st);
-}
-
-// Two problems of identical shape and pitches in one launch (both directions of the bidirectional encoder GRU).
-int linear_rows32_pair(float* const y[2], int64_t ldy, const float* const x[2], int64_t ldx, const float* const w[2], int64_t ldw,
-                       const float* const bias[2], int rows, int K, int N, int flags, bool wk, bool round_bf16, cudaStream_t st) {
-    const Rows32Problem p0{y[0], x[0], w[0], bias ? bias[0] : nullptr}, p1{y[1], x[1], w[1], bias ? bias[1] : nullptr};
-    if (wk) {
-        if (round_bf16) return launch_rows32<true, true>(p0, p1, 2, ldy, ldx, ldw, rows, K, N, flags, st);
-        return launch_rows32<true, false>(p0, p1, 2, ldy, ldx, ldw, rows, K, N, flags, st);
-    }
-    if (round_bf16) return launch_rows32<false, true>(p0, p1, 2, ldy, ldx, ldw, rows, K, N, flags, st);
-    return launch_rows32<false, false>(p0, p1, 2, ldy, ldx, ldw, rows, K, N, flags, st);
+    Rows32Problem p{y, bias, ldy, N, 1, {{x, w, ldx, ldw, K}, {nullptr, nullptr, 0, 0, 0}}};
+    return linear_rows32_multi(&p, 1, rows, flags, wk, round_bf16, st);
 }
 
 }  // namespace vag

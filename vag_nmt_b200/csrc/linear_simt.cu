@@ -6,14 +6,12 @@
 // CTA stages BK-wide slabs of both through shared memory, transposed to [k][m] so that every
 // thread reads its 2×4 A and 2×4 B values with conflict-free 128-bit loads.
 #include "common.cuh"
+#include "linear_rows.cuh"
 #include <cuda_bf16.h>
 
 namespace vag {
 
 int gemm_mode();
-bool rows32_ok(const float* x, int64_t ldx, const float* w, int64_t ldw, int rows, int K, int N, bool wk);
-int linear_rows32(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, int rows,
-                  int K, int N, int flags, bool wk, bool round_bf16, cudaStream_t st);
 
 template <int BM, int BN, int BK, int TM, int TN>
 struct SimtCfg {

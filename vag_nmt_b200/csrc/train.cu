@@ -4,15 +4,13 @@
 // Forward counterparts live in elementwise.cu / attention.cu; the Python autograd Functions in
 // vag_nmt_b200/autograd.py sequence them (back-propagation through time over the Tt decoder steps).
 #include "common.cuh"
+#include "linear_rows.cuh"
 #include <math.h>
 #include <algorithm>
 #include <vector>
 
 namespace vag {
 int gemm_mode();
-bool rows32_ok(const float* x, int64_t ldx, const float* w, int64_t ldw, int rows, int K, int N, bool wk);
-int linear_rows32(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, int rows,
-                  int K, int N, int flags, bool wk, bool round_bf16, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------ generic contraction
 // C[m, n] = alpha · Σ_k A(m, k)·B(k, n) + beta · C[m, n],   A(m,k) = A[m·sam + k·sak],  B(k,n) = B[k·sbk + n·sbn]
@@ -87,7 +85,7 @@ gemm_generic_kernel(float* __restrict__ C, int64_t ldc, const float* __restrict_
 __global__ void __launch_bounds__(256)
 gru_gates_bwd_kernel(float* __restrict__ dgi, float* __restrict__ dgh, float* __restrict__ dh_prev, const float* __restrict__ dh,
                      int64_t ld_dh, const float* __restrict__ gi, const float* __restrict__ gh, const float* __restrict__ h_prev,
-                     int64_t ld_hp, int rows, int H) {
+                     int64_t ld_hp, int rows, int H, const float* __restrict__ dh_add = nullptr) {
     const int64_t total = (int64_t)rows * H;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
         const int r_ = (int)(idx / H), j = (int)(idx % H);
@@ -98,7 +96,7 @@ gru_gates_bwd_kernel(float* __restrict__ dgi, float* __restrict__ dgh, float* __
         const float hn = ghr[2 * H + j];
         const float n = tanhf(gir[2 * H + j] + r * hn);
         const float hp = h_prev[(int64_t)r_ * ld_hp + j];
-        const float g = dh[(int64_t)r_ * ld_dh + j];
+        const float g = dh[(int64_t)r_ * ld_dh + j] + (dh_add ? dh_add[(int64_t)r_ * H + j] : 0.f);   // direct + recurrent path
         const float dn_pre = g * (1.f - z) * (1.f - n * n);
         const float dz_pre = g * (hp - n) * z * (1.f - z);
         const float dr_pre = dn_pre * hn * r * (1.f - r);
@@ -754,11 +752,16 @@ extern "C" int vag_decoder_seq_fwd_f32(const vag_decoder_weights* w, const float
         }
         VAG_TRY(gemm.linear(gh1, 3 * H, h, H, w->gru1_w_hh, H, w->gru1_b_hh, B, H, 3 * H, 0));
         VAG_TRY(vag_gru_gates_f32(h1, H, nullptr, 0, gi1, 3 * H, gh1, 3 * H, h, H, B, H, vs));
-        VAG_TRY(gemm.linear(q, C, h1, H, w->attn_h_w, H, nullptr, B, H, C, 0));
+        // the two contractions that read h1 — attention query and gru_2's hidden pre-activations — share one launch
+        const Rows32Problem h1p[2] = {{q, nullptr, C, C, 1, {{h1, w->attn_h_w, H, H, H}, {}}},
+                                      {gh2, w->gru2_b_hh, 3 * H, 3 * H, 1, {{h1, w->gru2_w_hh, H, H, H}, {}}}};
+        const bool h1_pair = rows32_problem_ok(h1p[0], B, true) && rows32_problem_ok(h1p[1], B, true);
+        if (h1_pair) VAG_TRY(linear_rows32_multi(h1p, 2, B, 0, true, gemm_mode() == 2, st));
+        else VAG_TRY(gemm.linear(q, C, h1, H, w->attn_h_w, H, nullptr, B, H, C, 0));
         VAG_TRY(vag_attention_f32(c, C, s->alpha_all + (size_t)t * B * T, q, C, s->keys, enc, w->attn_v, mask, B, 1, T, C, VAG_ATTN_MLP, vs));
         VAG_TRY(gemm.linear(x2, H, c, C, w->c2h_w, C, nullptr, B, C, H, 0));
         VAG_TRY(gemm.linear(gi2, 3 * H, x2, H, w->gru2_w_ih, H, w->gru2_b_ih, B, H, 3 * H, 0));
-        VAG_TRY(gemm.linear(gh2, 3 * H, h1, H, w->gru2_w_hh, H, w->gru2_b_hh, B, H, 3 * H, 0));
+        if (!h1_pair) VAG_TRY(gemm.linear(gh2, 3 * H, h1, H, w->gru2_w_hh, H, w->gru2_b_hh, B, H, 3 * H, 0));
         VAG_TRY(vag_gru_gates_f32(h2, H, nullptr, 0, gi2, 3 * H, gh2, 3 * H, h1, H, B, H, vs));
         h = h2;
         if (!teacher) {   // free running (V11:149-160): this step's arg-max is the next input
@@ -867,12 +870,13 @@ extern "C" int vag_decoder_seq_bwd_f32(const vag_decoder_weights* w, const float
     VAG_CUDA(cudaMemsetAsync(g->attn_v, 0, sizeof(float) * C, st));
     VAG_CUDA(cudaMemsetAsync(dh_next, 0, sizeof(float) * (size_t)B * H, st));
     for (int t = Tt - 1; t >= 0; --t) {
-        float* dh2 = dh2_dir + (size_t)t * B * H;
-        VAG_TRY(vag_axpby_f32(dh2, dh_next, 1.f, 1.f, (int64_t)B * H, vs));
+        const float* dh2 = dh2_dir + (size_t)t * B * H;     // read-out path; the recurrent path dh_next is added inside the kernel
         float* dgi2 = dgi2_all + (size_t)t * B * 3 * H;
         float* dgh2 = dgh2_all + (size_t)t * B * 3 * H;
         const float* h1 = s->h1_all + (size_t)t * B * H;
-        VAG_TRY(vag_gru_gates_bwd_f32(dgi2, dgh2, dh1, dh2, H, s->gi2_all + (size_t)t * B * 3 * H, s->gh2_all + (size_t)t * B * 3 * H, h1, H, B, H, vs));
+        gru_gates_bwd_kernel<<<grid_for((int64_t)B * H), 256, 0, st>>>(dgi2, dgh2, dh1, dh2, H, s->gi2_all + (size_t)t * B * 3 * H,
+                                                                        s->gh2_all + (size_t)t * B * 3 * H, h1, H, B, H, dh_next);
+        VAG_LAUNCH_CHECK();
         float* dx2 = dx2_all + (size_t)t * B * H;
         VAG_TRY(gemm_g(dx2, H, dgi2, 3 * H, 1, w->gru2_w_ih, H, 1, B, H, 3 * H, 0.f, st));             // dx2 = dgi2 · W_ih2
         float* dc = dc_dir + (size_t)t * B * C;
@@ -880,8 +884,15 @@ extern "C" int vag_decoder_seq_bwd_f32(const vag_decoder_weights* w, const float
         float* dq = dq_all + (size_t)t * B * C;
         VAG_TRY(vag_attention_bwd_f32(dq, C, dkeys, d_enc, g->attn_v, dc, C, s->alpha_all + (size_t)t * B * T, s->q_all + (size_t)t * B * C,
                                       C, s->keys, enc, w->attn_v, mask, B, T, C, VAG_ATTN_MLP, vs));
-        VAG_TRY(gemm_g(dh1, H, dgh2, 3 * H, 1, w->gru2_w_hh, H, 1, B, H, 3 * H, 1.f, st));              // dh1 += dgh2 · W_hh2
-        VAG_TRY(gemm_g(dh1, H, dq, C, 1, w->attn_h_w, H, 1, B, H, C, 1.f, st));                         //      + dq · W_attn_h
+        {   // dh1 += dgh2 · W_hh2 + dq · W_attn_h: one launch, two K-segments accumulating into the same output
+            const Rows32Problem dp = {dh1, nullptr, H, H, 2, {{dgh2, w->gru2_w_hh, 3 * H, H, 3 * H}, {dq, w->attn_h_w, C, H, C}}};
+            if (rows32_problem_ok(dp, B, false)) {
+                VAG_TRY(linear_rows32_multi(&dp, 1, B, VAG_LIN_ACCUMULATE, false, gemm_mode() == 2, st));
+            } else {
+                VAG_TRY(gemm_g(dh1, H, dgh2, 3 * H, 1, w->gru2_w_hh, H, 1, B, H, 3 * H, 1.f, st));
+                VAG_TRY(gemm_g(dh1, H, dq, C, 1, w->attn_h_w, H, 1, B, H, C, 1.f, st));
+            }
+        }
         const float* h_prev = t == 0 ? h0 : s->h2_all + (size_t)(t - 1) * B * H;
         float* dgi1 = dgi1_all + (size_t)t * B * 3 * H;
         float* dgh1 = dgh1_all + (size_t)t * B * 3 * H;
@@ -945,8 +956,6 @@ static int copy2d(float* dst, int64_t ld_dst, const float* src, int64_t ld_src, 
 }  // namespace vag
 
 namespace vag {
-int linear_rows32_pair(float* const y[2], int64_t ldy, const float* const x[2], int64_t ldx, const float* const w[2], int64_t ldw,
-                       const float* const bias[2], int rows, int K, int N, int flags, bool wk, bool round_bf16, cudaStream_t st);
 
 // One recurrent step of the packed bidirectional GRU for BOTH directions (blockIdx.y = direction; direction 0 is at time s,
 // direction 1 at time T-1-s).  Rows whose sentence is shorter than the time index are masked on the device — the launch
@@ -1083,10 +1092,9 @@ extern "C" int vag_encoder_train_fwd_f32(const vag_encoder_weights* w, const int
     for (int s_ = 0; s_ < T; ++s_) {
         float* gh_t[2] = {gh + ((size_t)0 * T + s_) * B * 3 * H, gh + ((size_t)1 * T + (T - 1 - s_)) * B * 3 * H};
         if (pair) {
-            const float* xs[2] = {h, h + (size_t)B * H};
-            const float* ws[2] = {w->w_hh[0], w->w_hh[1]};
-            const float* bs[2] = {w->b_hh[0], w->b_hh[1]};
-            VAG_TRY(linear_rows32_pair(gh_t, 3 * H, xs, H, ws, H, bs, B, H, 3 * H, 0, true, gemm_mode() == 2, st));
+            const Rows32Problem pp[2] = {{gh_t[0], w->b_hh[0], 3 * H, 3 * H, 1, {{h, w->w_hh[0], H, H, H}, {}}},
+                                         {gh_t[1], w->b_hh[1], 3 * H, 3 * H, 1, {{h + (size_t)B * H, w->w_hh[1], H, H, H}, {}}}};
+            VAG_TRY(linear_rows32_multi(pp, 2, B, 0, true, gemm_mode() == 2, st));
         } else {
             for (int d = 0; d < 2; ++d) {
                 gemm.new_step();
@@ -1134,8 +1142,9 @@ extern "C" int vag_encoder_bwd_f32(const vag_encoder_weights* w, const int32_t* 
         const float* dgh_t[2] = {dgh_all + (size_t)t0 * B * 3 * H, dgh_all + per_dir3 + (size_t)t1 * B * 3 * H};
         float* cr[2] = {carry, carry + (size_t)B * H};
         if (pair) {   // carry += dgh·W_hh, both directions in one launch
-            const float* ws[2] = {w->w_hh[0], w->w_hh[1]};
-            VAG_TRY(linear_rows32_pair(cr, H, dgh_t, 3 * H, ws, H, nullptr, B, 3 * H, H, VAG_LIN_ACCUMULATE, false, gemm_mode() == 2, st));
+            const Rows32Problem pp[2] = {{cr[0], nullptr, H, H, 1, {{dgh_t[0], w->w_hh[0], 3 * H, H, 3 * H}, {}}},
+                                         {cr[1], nullptr, H, H, 1, {{dgh_t[1], w->w_hh[1], 3 * H, H, 3 * H}, {}}}};
+            VAG_TRY(linear_rows32_multi(pp, 2, B, VAG_LIN_ACCUMULATE, false, gemm_mode() == 2, st));
         } else {
             for (int d = 0; d < 2; ++d) VAG_TRY(vag_gemm_f32(cr[d], H, dgh_t[d], 3 * H, 1, w->w_hh[d], H, 1, B, H, 3 * H, 1.f, 1.f, vs));
         }
