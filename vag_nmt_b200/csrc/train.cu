@@ -184,6 +184,112 @@ attention_bwd_kernel(float* __restrict__ dq, int64_t ld_dq, float* __restrict__ 
     }
 }
 
+// Same contract, shaped for latency (C a multiple of 128, 16-byte aligned rows): the kernel above walks its loops one
+// dependent global load at a time — ~30 L2 round trips in sequence per CTA.  Here every warp issues the eight 16-byte loads
+// of a context row (two rows at a time) before it touches them, dc sits in shared memory, and the score backward handles
+// eight time steps per batch of loads (masked positions have dα = 0 and simply add zero).
+template <int MODE>
+__global__ void __launch_bounds__(256)
+attention_bwd_fast_kernel(float* __restrict__ dq, int64_t ld_dq, float* __restrict__ dkeys, float* __restrict__ dctx,
+                          float* __restrict__ dv, const float* __restrict__ dc, int64_t ld_dc, const float* __restrict__ alpha,
+                          const float* __restrict__ q, int64_t ld_q, const float* __restrict__ keys, const float* __restrict__ ctx,
+                          const float* __restrict__ v, const float* __restrict__ mask, int T, int C) {
+    extern __shared__ __align__(16) float sm[];
+    float* dcs = sm;             // [C]
+    float* da = sm + C;          // [T]
+    float* red = da + T;         // [8]
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int c_lo = blockIdx.y * 256;
+    const float* key_b = keys + (int64_t)b * T * C;
+    const float* ctx_b = ctx + (int64_t)b * T * C;
+    float* dkey_b = dkeys + (int64_t)b * T * C;
+    float* dctx_b = dctx ? dctx + (int64_t)b * T * C : nullptr;
+    const float* al = alpha + (int64_t)b * T;
+    for (int c = tid * 4; c < C; c += 1024) *reinterpret_cast<float4*>(dcs + c) = *reinterpret_cast<const float4*>(dc + (int64_t)b * ld_dc + c);
+    __syncthreads();
+    const int nq = C >> 7;       // 16-byte pieces of a row per lane
+    // dα_t = dc·ctx_t (one warp per t, two rows in flight), dctx_t += α_t dc inside this CTA's 256-channel slab
+    for (int t0 = wid; t0 < T; t0 += 16) {
+        const int t1 = t0 + 8;
+        const bool live0 = mask ? mask[(int64_t)b * T + t0] != 0.f : true;
+        const bool live1 = t1 < T && (mask ? mask[(int64_t)b * T + t1] != 0.f : true);
+        float p0 = 0.f, p1 = 0.f;
+        for (int i0 = 0; i0 < nq; i0 += 4) {
+            float4 a0[4], a1[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = ((i0 + u) * 32 + lane) * 4;
+                const bool in = i0 + u < nq;
+                a0[u] = (live0 && in) ? *reinterpret_cast<const float4*>(ctx_b + (int64_t)t0 * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                a1[u] = (live1 && in) ? *reinterpret_cast<const float4*>(ctx_b + (int64_t)t1 * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (i0 + u >= nq) break;
+                const float4 g = *reinterpret_cast<const float4*>(dcs + ((i0 + u) * 32 + lane) * 4);
+                p0 += g.x * a0[u].x + g.y * a0[u].y + g.z * a0[u].z + g.w * a0[u].w;
+                p1 += g.x * a1[u].x + g.y * a1[u].y + g.z * a1[u].z + g.w * a1[u].w;
+            }
+        }
+        p0 = warp_sum(p0);
+        p1 = warp_sum(p1);
+        if (lane == 0) {
+            da[t0] = live0 ? p0 : 0.f;
+            if (t1 < T) da[t1] = live1 ? p1 : 0.f;
+        }
+    }
+    __syncthreads();
+    // softmax backward: da_t = α_t (dα_t − Σ_u α_u dα_u)
+    float part = 0.f;
+    for (int t = tid; t < T; t += 256) part += al[t] * da[t];
+    part = warp_sum(part);
+    if (lane == 0) red[wid] = part;
+    __syncthreads();
+    float dot = 0.f;
+    for (int w = 0; w < 8; ++w) dot += red[w];
+    __syncthreads();
+    for (int t = tid; t < T; t += 256) da[t] = al[t] * (da[t] - dot);
+    __syncthreads();
+    // through the score and the context: thread = channel of the slab, eight time steps per batch of loads
+    const int c = c_lo + tid;
+    if (c < C) {
+        float dqc = 0.f, dvc = 0.f;
+        const float qc = q[(int64_t)b * ld_q + c];
+        const float vc = MODE == VAG_ATTN_MLP ? v[c] : 0.f;
+        const float gdc = dcs[c];
+        for (int t0 = 0; t0 < T; t0 += 8) {
+            float k[8], dk[8], dx[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int t = min(t0 + u, T - 1);
+                k[u] = key_b[(int64_t)t * C + c];
+                dk[u] = dkey_b[(int64_t)t * C + c];
+                dx[u] = dctx_b ? dctx_b[(int64_t)t * C + c] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int t = t0 + u;
+                if (t >= T) break;
+                const float g = da[t];
+                const bool live = mask ? mask[(int64_t)b * T + t] != 0.f : true;
+                if (MODE == VAG_ATTN_MLP) {
+                    const float e = tanhf(qc + k[u]);
+                    const float dpre = g * vc * (1.f - e * e);
+                    dvc = fmaf(g, e, dvc);
+                    dqc += dpre;
+                    dkey_b[(int64_t)t * C + c] = dk[u] + dpre;
+                } else {
+                    dqc = fmaf(g, k[u], dqc);
+                    dkey_b[(int64_t)t * C + c] = dk[u] + g * qc;
+                }
+                if (dctx_b && live) dctx_b[(int64_t)t * C + c] = dx[u] + al[t] * gdc;
+            }
+        }
+        dq[(int64_t)b * ld_dq + c] = dqc;
+        if (MODE == VAG_ATTN_MLP && dv) atomicAdd(dv + c, dvc);
+    }
+}
+
 // ------------------------------------------------------------------------------------------ NLL backward
 // dlogits[r, v] = g[r]·w[tgt[r]]·(softmax(logits)[r, v] − [v == tgt[r]])
 __global__ void __launch_bounds__(256)
@@ -439,6 +545,17 @@ extern "C" int vag_attention_bwd_f32(float* dq, int64_t ld_dq, float* dkeys, flo
     VAG_REQUIRE(dq && dkeys && dc && alpha && q && keys && ctx, "vag_attention_bwd_f32: null pointer");
     VAG_REQUIRE(mode == VAG_ATTN_DOT || v, "vag_attention_bwd_f32: MLP mode needs v");
     if (B == 0) return VAG_OK;
+    cudaStream_t st_ = (cudaStream_t)stream;
+    const bool aligned = (C % 128 == 0) && (ld_dc % 4 == 0) && !(((uintptr_t)dc | (uintptr_t)ctx) & 15);
+    if (aligned && (size_t)(C + T + 8) * sizeof(float) <= 48 * 1024) {
+        const size_t smem_f = (size_t)(C + T + 8) * sizeof(float);
+        if (mode == VAG_ATTN_MLP)
+            attention_bwd_fast_kernel<VAG_ATTN_MLP><<<dim3(B, ceil_div(C, 256)), 256, smem_f, st_>>>(dq, ld_dq, dkeys, dctx, dv, dc, ld_dc, alpha, q, ld_q, keys, ctx, v, mask, T, C);
+        else
+            attention_bwd_fast_kernel<VAG_ATTN_DOT><<<dim3(B, ceil_div(C, 256)), 256, smem_f, st_>>>(dq, ld_dq, dkeys, dctx, dv, dc, ld_dc, alpha, q, ld_q, keys, ctx, v, mask, T, C);
+        VAG_LAUNCH_CHECK();
+        return VAG_OK;
+    }
     const size_t smem = (size_t)(T + 8) * sizeof(float);
     if (mode == VAG_ATTN_MLP)
         attention_bwd_kernel<VAG_ATTN_MLP><<<dim3(B, ceil_div(C, 256)), 256, smem, (cudaStream_t)stream>>>(dq, ld_dq, dkeys, dctx, dv, dc, ld_dc, alpha, q, ld_q, keys, ctx, v, mask, T, C);
