@@ -16,7 +16,7 @@ CSRC = Path(__file__).resolve().parent / "csrc"
 LIB = CSRC / "libvagnmt.so"
 OBJ_DIR = CSRC / "build"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-NVCC_FLAGS = (["-DVAG_TC_TIMERS"] if os.environ.get("VAG_TC_TIMERS") else []) + (["-DVAG_EXP_NOMATH"] if os.environ.get("VAG_EXP_NOMATH") else []) + (["-DVAG_EXP_NOLOAD"] if os.environ.get("VAG_EXP_NOLOAD") else []) + (["-DVAG_EXP_NOMATH1"] if os.environ.get("VAG_EXP_NOMATH1") else []) + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
+NVCC_FLAGS = os.environ.get("VAG_EXTRA_NVCC", "").split() + (["-DVAG_TC_TIMERS"] if os.environ.get("VAG_TC_TIMERS") else []) + (["-DVAG_EXP_NOMATH"] if os.environ.get("VAG_EXP_NOMATH") else []) + (["-DVAG_EXP_NOLOAD"] if os.environ.get("VAG_EXP_NOLOAD") else []) + (["-DVAG_EXP_NOMATH1"] if os.environ.get("VAG_EXP_NOMATH1") else []) + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 
 

@@ -10,6 +10,8 @@
 //     WK = false: W(c, k) = w[k·ldw + c]   (dx = dy·W, the same weight read for back-propagation through time).
 #include "linear_rows.cuh"
 #include <cuda_bf16.h>
+#include <stdlib.h>
+#include <string.h>
 
 namespace vag {
 
@@ -31,10 +33,25 @@ struct Rows32Args {
 constexpr int ROWS32_WARPS = 16;
 constexpr int ROWS32_KC = 32;   // contraction indices per warp per pass
 
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
 // One pass of a warp = a [BN columns] x [32 contraction indices] weight sub-tile: every lane fetches BN/4 DIFFERENT 16-byte
 // pieces of it (coalesced; together with the lane's eight x quads that is the whole pass in flight at once), the tile
 // goes through a per-warp shared-memory slot, and the FMAs read it back as broadcast LDS.128.
-template <int BN, bool WK, bool RB>
+// MMA = true: the 32 x BN x 32 product of a pass runs on the tensor cores (mma.sync m16n8k8 TF32, two row tiles x four k steps)
+// instead of the FMA loop, whose broadcast LDS.128 per 4 FMAs made shared-memory bandwidth the bound of the kernel (2.4 of 7.2 us
+// at 32 x 512 x 1536).  FP32 mode: error-compensated 3xTF32 (hi/lo split of both operands, lo·hi + hi·lo + hi·hi);
+// bf16 mode: the rounded operands are exact in TF32, one product.
+template <int BN, bool WK, bool RB, bool MMA>
 __global__ void __launch_bounds__(ROWS32_WARPS * 32, 2)
 linear_rows32_kernel(const __grid_constant__ Rows32Args args, int rows, int flags) {
     // blockIdx.y selects one of two independent problems (own N, pitches and segments); __grid_constant__ keeps the
@@ -52,12 +69,16 @@ linear_rows32_kernel(const __grid_constant__ Rows32Args args, int rows, int flag
     constexpr int XP = ROWS32_KC + 4;
     float* xs_all = smem_dyn;
     float* wt_all = smem_dyn + ROWS32_WARPS * 32 * XP;
+    constexpr int WT = BN * XP;                        // floats per warp (the [column][36] layout is the largest)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     float* xs = xs_all + wid * 32 * XP;
-    float* wt = wt_all + wid * BN * ROWS32_KC;
+    float* wt = wt_all + wid * WT;
     float acc[BN];
 #pragma unroll
     for (int c = 0; c < BN; ++c) acc[c] = 0.f;
+    // tensor-core flavour: accumulator fragments of the two 16-row tiles (m16n8k8: d0/d1 = row g, cols 2t/2t+1; d2/d3 = row g+8)
+    float dacc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    const int g = lane >> 2, t4 = lane & 3;
     // passes of 32 contraction indices, segment 0 first, dealt round-robin to the 16 warps
     const int passes0 = (pr.seg[0].K + ROWS32_KC - 1) / ROWS32_KC;
     const int passes = passes0 + (pr.nseg > 1 ? (pr.seg[1].K + ROWS32_KC - 1) / ROWS32_KC : 0);
@@ -92,10 +113,56 @@ linear_rows32_kernel(const __grid_constant__ Rows32Args args, int rows, int flag
 #pragma unroll
         for (int i = 0; i < ROWS32_KC / 4; ++i)
             *reinterpret_cast<float4*>(xs + (4 * i + (lane >> 3)) * XP + 4 * (lane & 7)) = rnd4<RB>(xl[i]);
-        // ---- weight tile through shared memory (same layout for both weight orientations: [piece] of float4)
+        // ---- weight tile through shared memory (FMA flavour: [piece] of float4 for both orientations; tensor-core flavour:
+        //      [column][36] for the k-fast orientation — pitch 36 keeps the fragment reads conflict-free — else [k][BN])
 #pragma unroll
-        for (int i = 0; i < BN / 4; ++i) reinterpret_cast<float4*>(wt)[i * 32 + lane] = rnd4<RB>(wv[i]);
+        for (int i = 0; i < BN / 4; ++i) {
+            if (MMA && WK) {
+                const int piece = i * 32 + lane;
+                *reinterpret_cast<float4*>(wt + (piece >> 3) * XP + 4 * (piece & 7)) = rnd4<RB>(wv[i]);
+            } else if (MMA) {
+                *reinterpret_cast<float4*>(wt + lane * BN + 4 * i) = rnd4<RB>(wv[i]);
+            } else {
+                reinterpret_cast<float4*>(wt)[i * 32 + lane] = rnd4<RB>(wv[i]);
+            }
+        }
         __syncwarp();
+        if (MMA) {
+#pragma unroll
+            for (int ks = 0; ks < ROWS32_KC / 8; ++ks) {
+                const int kk = ks * 8 + t4;
+                // B fragment: b0 = W(k = kk, n = g), b1 = W(k = kk + 4, n = g); columns past BN are zero
+                float bf[2] = {0.f, 0.f};
+                if (g < BN) {
+                    bf[0] = WK ? wt[g * XP + kk] : wt[kk * BN + g];
+                    bf[1] = WK ? wt[g * XP + kk + 4] : wt[(kk + 4) * BN + g];
+                }
+                uint32_t bh[2], bl[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    bh[u] = RB ? __float_as_uint(bf[u]) : to_tf32(bf[u]);
+                    if (!RB) bl[u] = to_tf32(bf[u] - __uint_as_float(bh[u]));
+                }
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    const float* xa = xs + (mt * 16 + g) * XP + kk;
+                    const float af[4] = {xa[0], xa[8 * XP], xa[4], xa[8 * XP + 4]};   // (g, t) (g+8, t) (g, t+4) (g+8, t+4)
+                    uint32_t ah[4], alo[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        ah[u] = RB ? __float_as_uint(af[u]) : to_tf32(af[u]);
+                        if (!RB) alo[u] = to_tf32(af[u] - __uint_as_float(ah[u]));
+                    }
+                    if (!RB) {
+                        mma_tf32(dacc[mt], alo, bh);
+                        mma_tf32(dacc[mt], ah, bl);
+                    }
+                    mma_tf32(dacc[mt], ah, bh);
+                }
+            }
+            __syncwarp();
+            continue;
+        }
         float4 xv[ROWS32_KC / 4];     // lane = row from here on
 #pragma unroll
         for (int q = 0; q < ROWS32_KC / 4; ++q) xv[q] = *reinterpret_cast<const float4*>(xs + lane * XP + 4 * q);
@@ -132,8 +199,18 @@ linear_rows32_kernel(const __grid_constant__ Rows32Args args, int rows, int flag
     }
     __syncthreads();                                   // every warp is done with its x tile: reuse the space
     float (*red)[32][BN + 1] = reinterpret_cast<float (*)[32][BN + 1]>(smem_dyn);
+    if (MMA) {
 #pragma unroll
-    for (int c = 0; c < BN; ++c) red[wid][lane][c] = acc[c];
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int row = mt * 16 + g + (u >> 1) * 8, c = 2 * t4 + (u & 1);
+                if (c < BN) red[wid][row][c] = dacc[mt][u];
+            }
+    } else {
+#pragma unroll
+        for (int c = 0; c < BN; ++c) red[wid][lane][c] = acc[c];
+    }
     __syncthreads();
     if (threadIdx.x < 32 * BN) {
         const int row = threadIdx.x / BN, c = threadIdx.x % BN;
@@ -152,23 +229,37 @@ linear_rows32_kernel(const __grid_constant__ Rows32Args args, int rows, int flag
 }
 
 template <int BN>
-constexpr size_t rows32_smem_bytes() { return (size_t)(ROWS32_WARPS * 32 * (ROWS32_KC + 4) + ROWS32_WARPS * BN * ROWS32_KC) * sizeof(float); }
+constexpr size_t rows32_smem_bytes() { return (size_t)(ROWS32_WARPS * 32 * (ROWS32_KC + 4) + ROWS32_WARPS * BN * (ROWS32_KC + 4)) * sizeof(float); }
 
-template <int BN, bool WK, bool RB>
-int launch_rows32_bn(const Rows32Problem& p0, const Rows32Problem& p1, int nprob, int rows, int flags, cudaStream_t st) {
+static bool rows32_use_mma() {   // VAG_ROWS32=ffma keeps the FMA inner loop (A/B runs)
+    static const bool on = [] { const char* e = getenv("VAG_ROWS32"); return !(e && strcmp(e, "ffma") == 0); }();
+    return on;
+}
+
+template <int BN, bool WK, bool RB, bool MMA>
+int launch_rows32_impl(const Rows32Problem& p0, const Rows32Problem& p1, int nprob, int rows, int flags, cudaStream_t st) {
     static bool attr_set = false;
     constexpr size_t smem = rows32_smem_bytes<BN>();
     if (!attr_set) {
-        VAG_CUDA(cudaFuncSetAttribute(linear_rows32_kernel<BN, WK, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VAG_CUDA(cudaFuncSetAttribute(linear_rows32_kernel<BN, WK, RB, MMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     const int nmax = nprob > 1 ? (p0.N > p1.N ? p0.N : p1.N) : p0.N;
     Rows32Args args;
     args.p[0] = p0;
     args.p[1] = p1;
-    linear_rows32_kernel<BN, WK, RB><<<dim3(ceil_div(nmax, BN), nprob), ROWS32_WARPS * 32, smem, st>>>(args, rows, flags);
+    linear_rows32_kernel<BN, WK, RB, MMA><<<dim3(ceil_div(nmax, BN), nprob), ROWS32_WARPS * 32, smem, st>>>(args, rows, flags);
     VAG_LAUNCH_CHECK();
     return VAG_OK;
+}
+
+template <int BN, bool WK, bool RB>
+int launch_rows32_bn(const Rows32Problem& p0, const Rows32Problem& p1, int nprob, int rows, int flags, cudaStream_t st) {
+    // bf16 mode: always the tensor-core loop (one product, no conversions).  FP32 mode pays 3 products + the hi/lo split per
+    // fragment: measured faster than the FMA loop only for the k-fast orientation with 8-column CTAs (6.1 vs 7.2 us at
+    // 32 x 512 x 1536), slower elsewhere (8.4 vs 7.5 us transposed, 6.5 vs 5.7 us with 4-column CTAs).
+    if (rows32_use_mma() && (RB || (WK && BN == 8))) return launch_rows32_impl<BN, WK, RB, true>(p0, p1, nprob, rows, flags, st);
+    return launch_rows32_impl<BN, WK, RB, false>(p0, p1, nprob, rows, flags, st);
 }
 
 template <bool WK, bool RB>
