@@ -301,3 +301,27 @@ def test_split_graph_step_with_eager_global_ranking_loss_matches_eager_step():
     finally:
         if own_group:
             dist.destroy_process_group()
+
+
+def test_graphed_step_draws_fresh_dropout_masks_on_every_replay():
+    """Dropout masks come from torch's CUDA generator INSIDE the captured step: every replay must draw new ones (Philox offsets
+    advance through the graph), the loss must stay finite and one graph must serve the shape."""
+    import vag_nmt_b200 as vag
+    from vag_nmt_b200 import synthetic
+    from vag_nmt_b200.optim import ClipAdam
+    from vag_nmt_b200.train import GraphedTrainStep
+    cfg = dict(synthetic.TINY)
+    torch.manual_seed(5)
+    model = vag.NMT_AttentionImagine_Seq2Seq_Beam_V11(
+        cfg["src_size"], cfg["tgt_size"], cfg["im_feats_size"], cfg["src_embedding_size"], cfg["tgt_embedding_size"],
+        cfg["hidden_size"], cfg["shared_embedding_size"], 0.99, dropout_emb=0.2, dropout_ctx=0.4, dropout_out=0.4, tied_emb=True).cuda()
+    bt = synthetic.make_batch(8, cfg["src_size"], cfg["tgt_size"], cfg["im_feats_size"], seed=2, max_len=8, min_len=2, mean=5, std=2)
+    w = torch.ones(cfg["tgt_size"])
+    w[0] = 0
+    crit = torch.nn.NLLLoss(weight=w.cuda(), reduce=False)
+    opt = ClipAdam(model, lr=0.0)          # frozen weights: only the masks change from step to step
+    stepper = GraphedTrainStep(model, opt, crit, vag.PairwiseRankingLoss(margin=0.1), enabled=True)
+    losses = [float(stepper.step(bt.src, bt.src_lengths, bt.tgt, bt.im, 1.0)[1]) for _ in range(5)]
+    assert len(stepper._graphs) == 1
+    assert all(torch.isfinite(torch.tensor(losses)))
+    assert len({round(v, 6) for v in losses}) >= 4, losses

@@ -133,6 +133,8 @@ class GraphedTrainStep:
     def _fwd_bwd(self, src, lengths, tgt, im, ratio):
         model = self.model
         self.optimizer.zero_grad()
+        if lengths is None:      # graph flavour: lengths = number of non-pad tokens per row, computed on the device (Encoder.py:47)
+            lengths = self._device_lengths(src)
         if im is not None:
             loss, loss_mt, loss_vse = model(src, lengths, tgt, im, ratio, criterion_mt=self.criterion_mt, criterion_vse=self.criterion_vse)
         else:
@@ -142,6 +144,10 @@ class GraphedTrainStep:
             loss.backward()
         vse = loss_vse if torch.is_tensor(loss_vse) else torch.zeros((), device=loss.device)
         return torch.stack([loss.detach().reshape(()), loss_mt.detach().reshape(()), vse.detach().reshape(())])
+
+    @staticmethod
+    def _device_lengths(src):
+        return (src != 0).sum(1, dtype=torch.int32)
 
     @staticmethod
     def _check_lengths(lengths, width):
@@ -155,8 +161,7 @@ class GraphedTrainStep:
     def _capture(self, key, src, ls, tgt, im, ratio):
         from . import ops
         dev = src.device
-        st = {"src": src.clone(), "tgt": tgt.clone(), "im": im.clone() if im is not None else None,
-              "len": torch.tensor(ls, dtype=torch.int32, device=dev)}
+        st = {"src": src.clone(), "tgt": tgt.clone(), "im": im.clone() if im is not None else None, "len": None}
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):     # warm-up outside the capture: sizes the workspaces, sets kernel attributes
@@ -189,7 +194,7 @@ class GraphedTrainStep:
         respect to the embeddings is exactly G, so graph B back-propagates the true loss."""
         from . import ops
         model, dev = self.model, src.device
-        st = {"src": src.clone(), "tgt": tgt.clone(), "im": im.clone(), "len": torch.tensor(ls, dtype=torch.int32, device=dev), "split": True}
+        st = {"src": src.clone(), "tgt": tgt.clone(), "im": im.clone(), "len": None, "split": True}
         S = model.shared_embedding_size
         st["G_im"] = torch.zeros(src.shape[0], S, dtype=torch.float32, device=dev)
         st["G_s"] = torch.zeros_like(st["G_im"])
@@ -210,7 +215,8 @@ class GraphedTrainStep:
         ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         with torch.cuda.graph(ga, pool=self._pool):
             self.optimizer.zero_grad()
-            loss, loss_mt, _ = model(st["src"], st["len"], st["tgt"], st["im"], ratio, criterion_mt=self.criterion_mt, criterion_vse=sur)
+            loss, loss_mt, _ = model(st["src"], self._device_lengths(st["src"]), st["tgt"], st["im"], ratio,
+                                     criterion_mt=self.criterion_mt, criterion_vse=sur)
             st["mt"] = loss_mt.detach().reshape(())
             st["im_emb"], st["txt_emb"] = sur.im, sur.s
         with torch.cuda.graph(gb, pool=self._pool):
@@ -249,23 +255,21 @@ class GraphedTrainStep:
         is_teacher = random.random() < teacher_force_ratio                        # V11:136 — decided before the graph is chosen
         ratio = 1.0 if is_teacher else 0.0
         dev = model._device()
-        src = src.to(dev, non_blocking=True)
-        tgt = tgt.to(dev, non_blocking=True)
-        im = im.to(dev, non_blocking=True) if im is not None else None
+        to_dev = lambda t: t.to(dev, non_blocking=True) if t is not None else None
         if not self.enabled or getattr(model, "_dropout_masks", None):
-            out = self._fwd_bwd(src, lengths, tgt, im, ratio)
+            out = self._fwd_bwd(to_dev(src), lengths, to_dev(tgt), to_dev(im), ratio)
         else:
             ls = self._check_lengths(lengths, src.shape[1])
             key = (tuple(src.shape), tuple(tgt.shape), is_teacher, im is not None, getattr(model, "precision", "fp32"))
             st = self._graphs.get(key)
             if st is None:
                 split = self._split and im is not None
-                st = (self._capture_split if split else self._capture)(key, src, ls, tgt, im, ratio)
+                st = (self._capture_split if split else self._capture)(key, to_dev(src), ls, to_dev(tgt), to_dev(im), ratio)
+            # (pinned) host or device batch → the graph's static buffers; the lengths are recomputed from src inside the graph
             st["src"].copy_(src, non_blocking=True)
             st["tgt"].copy_(tgt, non_blocking=True)
             if im is not None:
                 st["im"].copy_(im, non_blocking=True)
-            st["len"].copy_(torch.tensor(ls, dtype=torch.int32), non_blocking=False)
             st["graph"].replay()
             if st.get("split"):
                 vse = self._global_rank_loss(st).reshape(())
