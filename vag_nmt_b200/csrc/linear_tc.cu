@@ -1479,6 +1479,74 @@ int tc_split_t(const float* x, int64_t ldx, int R, int M, void* hi, void* lo, in
     return VAG_OK;
 }
 
+// Both operands of one contraction split in ONE launch (blockIdx.z = operand): out(r, c) = split(src(r, c)) for c < cols,
+// zero for cols <= c < cols_pad, where src(r, c) = src[c·ld + r] when the operand is stored contraction-major (transposed)
+// and src[r·ld + c] otherwise.  Inside a captured graph every node costs ~2 µs of dependency latency whatever it does, so the
+// backward contractions use this instead of two split launches (+ two memsets for the K padding) per contraction.
+struct SplitJob {
+    const float* src;
+    int64_t ld;
+    int rows, cols, cols_pad, transposed;
+    void* hi;
+    void* lo;
+    int64_t ldo;
+};
+struct SplitJobs {
+    SplitJob j[2];
+};
+template <int MODE>   // 0: TF32 planes (float), 1: FP16 hi/lo, 2: BF16 single plane
+__global__ void __launch_bounds__(256) split_jobs_kernel(const __grid_constant__ SplitJobs jobs) {
+    const SplitJob& jb = jobs.j[blockIdx.z];
+    const int tiles_c = (jb.cols_pad + 31) >> 5, tiles_r = (jb.rows + 31) >> 5;
+    if ((int)blockIdx.x >= tiles_c * tiles_r) return;
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int r0 = ((int)blockIdx.x / tiles_c) << 5, c0 = ((int)blockIdx.x % tiles_c) << 5;
+    if (jb.transposed) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + ty + 8 * j, r = r0 + tx;
+            tile[ty + 8 * j][tx] = (c < jb.cols && r < jb.rows) ? jb.src[(int64_t)c * jb.ld + r] : 0.f;
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int r = r0 + ty + 8 * j, c = c0 + tx;
+        if (r >= jb.rows || c >= jb.cols_pad) continue;
+        const float v = jb.transposed ? tile[tx][ty + 8 * j] : (c < jb.cols ? jb.src[(int64_t)r * jb.ld + c] : 0.f);
+        const int64_t o = (int64_t)r * jb.ldo + c;
+        if (MODE == 0) {
+            uint32_t t;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
+            const float h = __uint_as_float(t);
+            ((float*)jb.hi)[o] = h;
+            ((float*)jb.lo)[o] = v - h;
+        } else if (MODE == 1) {
+            const __half h = __float2half_rn(v);
+            ((__half*)jb.hi)[o] = h;
+            ((__half*)jb.lo)[o] = __float2half_rn((v - __half2float(h)) * 2048.0f);
+        } else {
+            ((__nv_bfloat16*)jb.hi)[o] = __float2bfloat16_rn(v);
+        }
+    }
+}
+
+// x: [M, K] logical (stored [K, M] when xt), w: [N, K] logical (stored [K, N] when wt); planes of pitch Kp (zero-padded).
+int tc_split_pair(const float* x, int64_t ldx, bool xt, int M, void* xh, void* xl, const float* w, int64_t ldw, bool wt, int N,
+                  void* wh, void* wl, int K, int Kp, cudaStream_t st) {
+    SplitJobs jobs;
+    jobs.j[0] = SplitJob{x, ldx, M, K, Kp, xt ? 1 : 0, xh, xl, (int64_t)Kp};
+    jobs.j[1] = SplitJob{w, ldw, N, K, Kp, wt ? 1 : 0, wh, wl, (int64_t)Kp};
+    const int tiles = ceil_div(Kp, 32) * ceil_div(M > N ? M : N, 32);
+    dim3 grid(tiles, 1, 2);
+    if (gemm_mode() == 2) split_jobs_kernel<2><<<grid, 256, 0, st>>>(jobs);
+    else if (use_f16_split()) split_jobs_kernel<1><<<grid, 256, 0, st>>>(jobs);
+    else split_jobs_kernel<0><<<grid, 256, 0, st>>>(jobs);
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
 // The tcgen05 contraction on pre-split operands: xh/xl [rows, K] pitch ldxs, wh/wl [N, K] pitch ldws (elements).
 // summ (optional): [rows, ceil(N / tile_w)] float4 (max, Σexp(x-max), best value, best column as int bits) per
 // (row, column tile); *summ_tile_w receives the tile width the chosen configuration uses.

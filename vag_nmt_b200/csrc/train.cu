@@ -755,24 +755,7 @@ static int gemm_tc_try(float* C, int64_t ldc, const float* A, int64_t sam, int64
     char* wl = ar.take<char>((size_t)N * Kp * esz);
     float* tmp = beta == 1.f ? ar.take<float>((size_t)M * N) : nullptr;
     if (ar.overflow) return 0;
-    if (xt) {
-        VAG_TRY(tc_split_t(A, ldx, K, M, xh, xl, Kp, Kp, st));
-    } else {
-        if (Kp != (K + 3) / 4 * 4) {
-            VAG_CUDA(cudaMemsetAsync(xh, 0, (size_t)M * Kp * esz, st));
-            VAG_CUDA(cudaMemsetAsync(xl, 0, (size_t)M * Kp * esz, st));
-        }
-        VAG_TRY(tc_split(A, ldx, M, (K + 3) / 4 * 4, xh, xl, Kp, 0, st));
-    }
-    if (wt) {
-        VAG_TRY(tc_split_t(B, ldw, K, N, wh, wl, Kp, Kp, st));
-    } else {
-        if (Kp != K) {
-            VAG_CUDA(cudaMemsetAsync(wh, 0, (size_t)N * Kp * esz, st));
-            VAG_CUDA(cudaMemsetAsync(wl, 0, (size_t)N * Kp * esz, st));
-        }
-        VAG_TRY(tc_split(B, ldw, N, K, wh, wl, Kp, 0, st));
-    }
+    VAG_TRY(tc_split_pair(A, ldx, xt, M, xh, xl, B, ldw, wt, N, wh, wl, K, Kp, st));   // both operands, one launch, K padding zeroed
     VAG_TRY(tc_gemm(tmp ? tmp : C, tmp ? N : ldc, xh, xl, Kp, wh, wl, Kp, nullptr, M, Kp, N, 0, st, nullptr, nullptr));
     if (tmp) {
         add2d_kernel<<<grid_for((int64_t)M * N / 4), 256, 0, st>>>(C, ldc, tmp, M, N);
@@ -954,7 +937,7 @@ extern "C" int vag_decoder_seq_bwd_f32(const vag_decoder_weights* w, const float
         return VAG_ERR_WORKSPACE;
     }
     // ---- batched over all steps: vocabulary projection and read-out
-    if (ldd != V) VAG_CUDA(cudaMemsetAsync(dlogits, 0, sizeof(float) * (size_t)R * ldd, st));
+    // (the pad column of dlogits is never read: the operand split, the column sum and the transposed read all stop at V)
     nll_bwd_kernel<<<R, 256, 0, st>>>(dlogits, ldd, s->logits_all, ldl, s->lse_all, tgt_t, nll_weight, dloss_rows, V, B);   // all steps
     VAG_LAUNCH_CHECK();
     {   // d_t = dlogits · out_w   (contraction over the vocabulary: rows of dlogits are padded, out_w is split transposed)
@@ -963,7 +946,7 @@ extern "C" int vag_decoder_seq_bwd_f32(const vag_decoder_weights* w, const float
         if (r == 0) VAG_TRY(gemm_g(d_t, E, dlogits, ldd, 1, w->out_w, E, 1, R, E, (int)V, 0.f, st));
     }
     float* d_out_w = tied ? g->emb : g->out_w;                                                       // tied: accumulate into dEmb later
-    VAG_CUDA(cudaMemsetAsync(g->emb, 0, sizeof(float) * (size_t)V * E, st));
+    if (!tied) VAG_CUDA(cudaMemsetAsync(g->emb, 0, sizeof(float) * (size_t)V * E, st));            // tied: the contraction below overwrites all of it
     VAG_TRY(gemm_g(d_out_w, E, dlogits, 1, ldd, s->t_all, E, 1, (int)V, E, R, 0.f, st));            // dlogitsᵀ · t_all
     VAG_TRY(vag_colsum_f32(g->out_b, dlogits, ldd, R, (int)V, 0, vs));
     if (out_mask) {
