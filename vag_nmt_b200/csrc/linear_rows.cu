@@ -26,8 +26,18 @@ __device__ __forceinline__ float4 rnd4(float4 v) {
     return v;
 }
 
+struct Rows32GruEpi {        // epilogue side of a Rows32Gru problem (the contraction side is mapped onto Rows32Problem)
+    const float* other;
+    const float* h_prev;
+    float* h_out;
+    float* out2;
+    int64_t ld_out2;
+    const int32_t* lengths;
+    int t, H, produces_gi;
+};
 struct Rows32Args {
     Rows32Problem p[2];
+    Rows32GruEpi g[2];
 };
 
 constexpr int ROWS32_WARPS = 16;
@@ -51,15 +61,17 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 // instead of the FMA loop, whose broadcast LDS.128 per 4 FMAs made shared-memory bandwidth the bound of the kernel (2.4 of 7.2 us
 // at 32 x 512 x 1536).  FP32 mode: error-compensated 3xTF32 (hi/lo split of both operands, lo·hi + hi·lo + hi·hi);
 // bf16 mode: the rounded operands are exact in TF32, one product.
-template <int BN, bool WK, bool RB, bool MMA>
+template <int BN, bool WK, bool RB, bool MMA, bool GRU = false>
 __global__ void __launch_bounds__(ROWS32_WARPS * 32, 2)
 linear_rows32_kernel(const __grid_constant__ Rows32Args args, int rows, int flags) {
     // blockIdx.y selects one of two independent problems (own N, pitches and segments); __grid_constant__ keeps the
     // dynamically indexed descriptors in parameter space instead of a per-thread local copy
     const Rows32Problem& pr = args.p[blockIdx.y];
-    const int N = pr.N;
-    const int n0 = blockIdx.x * BN;
-    if (n0 >= N) return;                               // the grid is sized for the wider problem
+    // GRU flavour: BN = 12 columns = 4 hidden units x 3 gates; tile column c is weight row (c / 4)·H + u0 + (c % 4)
+    constexpr int GU = 4;
+    const int N = pr.N;                                // GRU: 3H
+    const int n0 = GRU ? blockIdx.x * GU : blockIdx.x * BN;
+    if (n0 >= (GRU ? N / 3 : N)) return;               // the grid is sized for the wider problem
     float* __restrict__ y = pr.y;
     const float* __restrict__ bias = pr.bias;
     const int64_t ldy = pr.ldy;
@@ -77,7 +89,7 @@ linear_rows32_kernel(const __grid_constant__ Rows32Args args, int rows, int flag
 #pragma unroll
     for (int c = 0; c < BN; ++c) acc[c] = 0.f;
     // tensor-core flavour: accumulator fragments of the two 16-row tiles (m16n8k8: d0/d1 = row g, cols 2t/2t+1; d2/d3 = row g+8)
-    constexpr int NT = BN > 8 ? BN / 8 : 1;            // 8-column tiles per CTA (BN = 4 uses half of one)
+    constexpr int NT = (BN + 7) / 8;            // 8-column tiles per CTA (BN = 4 uses half of one)
     float dacc[NT][2][4];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt)
@@ -102,7 +114,8 @@ linear_rows32_kernel(const __grid_constant__ Rows32Args args, int rows, int flag
         for (int i = 0; i < BN / 4; ++i) {
             if (WK) {   // piece = (column c, quad q) of the [BN][32] tile
                 const int piece = i * 32 + lane, c = piece >> 3, q = piece & 7;
-                const int col = min(n0 + c, N - 1), k = min(k0 + 4 * q, K - 4);
+                const int col = GRU ? (c / GU) * (N / 3) + n0 + (c % GU) : min(n0 + c, N - 1);
+                const int k = min(k0 + 4 * q, K - 4);
                 wv[i] = __ldg(reinterpret_cast<const float4*>(w + (int64_t)col * ldw + k));
             } else {    // lane = contraction index, piece i = columns 4i..4i+3 of the [32][BN] tile
                 const int k = min(k0 + lane, K - 1), col = min(n0 + 4 * i, N - 4);
@@ -229,6 +242,39 @@ linear_rows32_kernel(const __grid_constant__ Rows32Args args, int rows, int flag
         for (int c = 0; c < BN; ++c) red[wid][lane][c] = acc[c];
     }
     __syncthreads();
+    if (GRU) {
+        if (threadIdx.x < 32 * GU) {
+            const Rows32GruEpi& ge = args.g[blockIdx.y];
+            const int row = threadIdx.x / GU, i = threadIdx.x % GU, u = n0 + i, H = ge.H;
+            if (row < rows) {
+                float pre[3], oth[3];
+#pragma unroll
+                for (int gt = 0; gt < 3; ++gt) {
+                    float v = 0.f;
+#pragma unroll
+                    for (int q = 0; q < ROWS32_WARPS; ++q) v += red[q][row][gt * GU + i];
+                    pre[gt] = v + (bias ? bias[gt * H + u] : 0.f);
+                    oth[gt] = ge.other[(int64_t)row * 3 * H + gt * H + u];
+                }
+                const bool live = !ge.lengths || ge.lengths[row] > ge.t;
+                const float hp = ge.h_prev[(int64_t)row * H + u];
+                float hn = hp;
+                if (live) {
+                    const float* gi = ge.produces_gi ? pre : oth;
+                    const float* gh = ge.produces_gi ? oth : pre;
+                    const float r = sigmoidf_precise(gi[0] + gh[0]);
+                    const float z = sigmoidf_precise(gi[1] + gh[1]);
+                    const float n = tanhf(gi[2] + r * gh[2]);
+                    hn = (1.0f - z) * n + z * hp;
+                    if (ge.out2) ge.out2[(int64_t)row * ge.ld_out2 + u] = hn;
+                }
+                ge.h_out[(int64_t)row * H + u] = hn;
+#pragma unroll
+                for (int gt = 0; gt < 3; ++gt) y[(int64_t)row * ldy + gt * H + u] = live ? pre[gt] : 0.f;
+            }
+        }
+        return;
+    }
     if (threadIdx.x < 32 * BN) {
         const int row = threadIdx.x / BN, c = threadIdx.x % BN;
         const int col = n0 + c;
@@ -262,7 +308,7 @@ int launch_rows32_impl(const Rows32Problem& p0, const Rows32Problem& p1, int npr
         attr_set = true;
     }
     const int nmax = nprob > 1 ? (p0.N > p1.N ? p0.N : p1.N) : p0.N;
-    Rows32Args args;
+    Rows32Args args = {};
     args.p[0] = p0;
     args.p[1] = p1;
     linear_rows32_kernel<BN, WK, RB, MMA><<<dim3(ceil_div(nmax, BN), nprob), ROWS32_WARPS * 32, smem, st>>>(args, rows, flags);
@@ -314,6 +360,38 @@ int linear_rows32_multi(const Rows32Problem* probs, int nprob, int rows, int fla
     }
     if (round_bf16) return launch_rows32<false, true>(p0, p1, nprob, rows, flags, st);
     return launch_rows32<false, false>(p0, p1, nprob, rows, flags, st);
+}
+
+bool rows32_gru_ok(const Rows32Gru& p, int rows) {
+    if (p.H < 64 || (p.H & 3) || !p.pre || !p.other || !p.h_prev || !p.h_out || p.h_out == p.h_prev || p.h_out == p.seg.x) return false;
+    return rows32_ok(p.seg.x, p.seg.ldx, p.seg.w, p.seg.ldw, rows, p.seg.K, 3 * p.H, true);
+}
+
+template <bool RB, bool MMA>
+static int launch_rows32_gru(const Rows32Args& args, int nprob, int rows, cudaStream_t st) {
+    static bool attr_set = false;
+    constexpr size_t smem = rows32_smem_bytes<12>();
+    if (!attr_set) {
+        VAG_CUDA(cudaFuncSetAttribute(linear_rows32_kernel<12, true, RB, MMA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const int H = args.g[0].H;
+    linear_rows32_kernel<12, true, RB, MMA, true><<<dim3(H / 4, nprob), ROWS32_WARPS * 32, smem, st>>>(args, rows, 0);
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
+// One GRU cell step per problem: contraction + gate epilogue in one launch (see Rows32Gru).  Problems of a launch share H.
+int linear_rows32_gru(const Rows32Gru* probs, int nprob, int rows, bool round_bf16, cudaStream_t st) {
+    Rows32Args args;
+    for (int i = 0; i < 2; ++i) {
+        const Rows32Gru& p = probs[i < nprob ? i : 0];
+        args.p[i] = Rows32Problem{p.pre, p.bias, (int64_t)3 * p.H, 3 * p.H, 1, {p.seg, Rows32Seg{nullptr, nullptr, 0, 0, 0}}};
+        args.g[i] = Rows32GruEpi{p.other, p.h_prev, p.h_out, p.out2, p.ld_out2, p.lengths, p.t, p.H, p.produces_gi};
+    }
+    const bool mma = rows32_use_mma();
+    if (round_bf16) return mma ? launch_rows32_gru<true, true>(args, nprob, rows, st) : launch_rows32_gru<true, false>(args, nprob, rows, st);
+    return mma ? launch_rows32_gru<false, true>(args, nprob, rows, st) : launch_rows32_gru<false, false>(args, nprob, rows, st);
 }
 
 // y[rows, N] (+)= x[rows, K] · W(c, k)  (+ bias) (tanh);  round_bf16: operands rounded to bfloat16 first (bf16 mode)

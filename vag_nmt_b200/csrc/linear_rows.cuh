@@ -23,6 +23,28 @@ struct Rows32Problem {
     Rows32Seg seg[2];
 };
 
+// GRU flavour (linear_rows32_gru): the contraction produces one of the two pre-activation matrices of a GRU cell,
+// pre[rows, 3H] = x · Wᵀ + bias (gate order r | z | n like torch.nn.GRU), and the epilogue finishes the cell —
+//   r = σ(gi_r + gh_r), z = σ(gi_z + gh_z), n = tanh(gi_n + r · gh_n), h' = (1 − z) · n + z · h
+// — with the other pre-activation matrix read from memory.  A CTA owns 4 hidden units = 12 columns (4 per gate), so the gate
+// kernel that used to follow the contraction (one more node of ~4 µs in the captured step) disappears.
+struct Rows32Gru {
+    float* pre;              // [rows, 3H] the pre-activations this contraction produces (kept: back-propagation reads them)
+    const float* bias;       // [3H]
+    const float* other;      // [rows, 3H] the other pre-activation matrix
+    int produces_gi;         // 1: pre = gi (input side), other = gh;  0: pre = gh, other = gi
+    const float* h_prev;     // [rows, H]
+    float* h_out;            // [rows, H]  (must not alias h_prev or x: other CTAs are still reading them)
+    float* out2;             // optional second copy of h' (the encoder's context slot), row pitch ld_out2
+    int64_t ld_out2;
+    const int32_t* lengths;  // optional [rows]: rows with lengths[row] <= t are masked (h' = h, out2 untouched, pre = 0)
+    int t;
+    int H;
+    Rows32Seg seg;           // x [rows, K] against w [3H, K] (k-fast)
+};
+bool rows32_gru_ok(const Rows32Gru& p, int rows);
+int linear_rows32_gru(const Rows32Gru* probs, int nprob, int rows, bool round_bf16, cudaStream_t st);
+
 bool rows32_ok(const float* x, int64_t ldx, const float* w, int64_t ldw, int rows, int K, int N, bool wk);
 bool rows32_problem_ok(const Rows32Problem& p, int rows, bool wk);
 int linear_rows32(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, int rows,

@@ -850,8 +850,15 @@ extern "C" int vag_decoder_seq_fwd_f32(const vag_decoder_weights* w, const float
             VAG_TRY(vag_embed_rows_f32(e_s, E, w->emb, E, tok_in + (size_t)t * B, B, V, vs));
             VAG_TRY(gemm.linear(gi1, 3 * H, e_s, E, w->gru1_w_ih, E, w->gru1_b_ih, B, E, 3 * H, 0));
         }
-        VAG_TRY(gemm.linear(gh1, 3 * H, h, H, w->gru1_w_hh, H, w->gru1_b_hh, B, H, 3 * H, 0));
-        VAG_TRY(vag_gru_gates_f32(h1, H, nullptr, 0, gi1, 3 * H, gh1, 3 * H, h, H, B, H, vs));
+        // gru_1: hidden-side contraction with the cell's gate math in its epilogue (one launch instead of two)
+        const Rows32Gru g1 = {gh1, w->gru1_b_hh, gi1, 0, h, h1, nullptr, 0, nullptr, 0, H, {h, w->gru1_w_hh, H, H, H}};
+        const bool fuse1 = rows32_gru_ok(g1, B);
+        if (fuse1) {
+            VAG_TRY(linear_rows32_gru(&g1, 1, B, gemm_mode() == 2, st));
+        } else {
+            VAG_TRY(gemm.linear(gh1, 3 * H, h, H, w->gru1_w_hh, H, w->gru1_b_hh, B, H, 3 * H, 0));
+            VAG_TRY(vag_gru_gates_f32(h1, H, nullptr, 0, gi1, 3 * H, gh1, 3 * H, h, H, B, H, vs));
+        }
         // the two contractions that read h1 — attention query and gru_2's hidden pre-activations — share one launch
         const Rows32Problem h1p[2] = {{q, nullptr, C, C, 1, {{h1, w->attn_h_w, H, H, H}, {}}},
                                       {gh2, w->gru2_b_hh, 3 * H, 3 * H, 1, {{h1, w->gru2_w_hh, H, H, H}, {}}}};
@@ -860,9 +867,15 @@ extern "C" int vag_decoder_seq_fwd_f32(const vag_decoder_weights* w, const float
         else VAG_TRY(gemm.linear(q, C, h1, H, w->attn_h_w, H, nullptr, B, H, C, 0));
         VAG_TRY(vag_attention_f32(c, C, s->alpha_all + (size_t)t * B * T, q, C, s->keys, enc, w->attn_v, mask, B, 1, T, C, VAG_ATTN_MLP, vs));
         VAG_TRY(gemm.linear(x2, H, c, C, w->c2h_w, C, nullptr, B, C, H, 0));
-        VAG_TRY(gemm.linear(gi2, 3 * H, x2, H, w->gru2_w_ih, H, w->gru2_b_ih, B, H, 3 * H, 0));
         if (!h1_pair) VAG_TRY(gemm.linear(gh2, 3 * H, h1, H, w->gru2_w_hh, H, w->gru2_b_hh, B, H, 3 * H, 0));
-        VAG_TRY(vag_gru_gates_f32(h2, H, nullptr, 0, gi2, 3 * H, gh2, 3 * H, h1, H, B, H, vs));
+        // gru_2: input-side contraction (x2 → gi2) with the gate math in its epilogue; gh2 is already there
+        const Rows32Gru g2 = {gi2, w->gru2_b_ih, gh2, 1, h1, h2, nullptr, 0, nullptr, 0, H, {x2, w->gru2_w_ih, H, H, H}};
+        if (rows32_gru_ok(g2, B)) {
+            VAG_TRY(linear_rows32_gru(&g2, 1, B, gemm_mode() == 2, st));
+        } else {
+            VAG_TRY(gemm.linear(gi2, 3 * H, x2, H, w->gru2_w_ih, H, w->gru2_b_ih, B, H, 3 * H, 0));
+            VAG_TRY(vag_gru_gates_f32(h2, H, nullptr, 0, gi2, 3 * H, gh2, 3 * H, h1, H, B, H, vs));
+        }
         h = h2;
         if (!teacher) {   // free running (V11:149-160): this step's arg-max is the next input
             float* t_s = s->t_all + (size_t)t * B * E;
@@ -1171,7 +1184,7 @@ extern "C" int vag_encoder_train_fwd_f32(const vag_encoder_weights* w, const int
     const size_t ab = GemmCtx::split_bytes((int64_t)T * B, E) + 8192;
     void* wr = ar.take<char>(wb);
     void* areg = ar.take<char>(ab);
-    float* h = ar.take<float>((size_t)2 * B * H);
+    float* h = ar.take<float>((size_t)4 * B * H);      // [parity][direction][B][H]: the fused step reads one copy and writes the other
     if (ar.overflow) {
         set_error("vag_encoder_train_fwd_f32: workspace too small");
         return VAG_ERR_WORKSPACE;
@@ -1184,9 +1197,29 @@ extern "C" int vag_encoder_train_fwd_f32(const vag_encoder_weights* w, const int
         if (emb_mask) VAG_TRY(vag_mul_f32(x, emb_mask, (int64_t)T * B * E, stream));   // embedding dropout, Encoder.py:51-52
     }
     VAG_CUDA(cudaMemsetAsync(ctx_out, 0, sizeof(float) * (size_t)B * T * 2 * H, st));
-    VAG_CUDA(cudaMemsetAsync(h, 0, sizeof(float) * (size_t)2 * B * H, st));
+    VAG_CUDA(cudaMemsetAsync(h, 0, sizeof(float) * (size_t)4 * B * H, st));
     for (int d = 0; d < 2; ++d)
         VAG_TRY(gemm.linear(gi + (size_t)d * T * B * 3 * H, 3 * H, x, E, w->w_ih[d], E, w->b_ih[d], T * B, E, 3 * H, 0));
+    {   // fused flavour: hidden-side contraction + gate math + masking of both directions in ONE launch per time step
+        float* hb[2] = {h, h + (size_t)2 * B * H};
+        Rows32Gru probe = {gh, w->b_hh[0], gi, 0, hb[0], hb[1], ctx_out, (int64_t)T * 2 * H, lengths_dev, 0, H, {hb[0], w->w_hh[0], H, H, H}};
+        if (rows32_gru_ok(probe, B)) {
+            for (int s_ = 0; s_ < T; ++s_) {
+                const float* in = hb[s_ & 1];
+                float* out = hb[(s_ + 1) & 1];
+                Rows32Gru pp[2];
+                for (int d = 0; d < 2; ++d) {
+                    const int t = d == 0 ? s_ : T - 1 - s_;
+                    const size_t o3 = ((size_t)d * T + t) * B * 3 * H;
+                    pp[d] = Rows32Gru{gh + o3, w->b_hh[d], gi + o3, 0, in + (size_t)d * B * H, out + (size_t)d * B * H,
+                                      ctx_out + (int64_t)t * 2 * H + (int64_t)d * H, (int64_t)T * 2 * H, lengths_dev, t, H,
+                                      {in + (size_t)d * B * H, w->w_hh[d], H, H, H}};
+                }
+                VAG_TRY(linear_rows32_gru(pp, 2, B, gemm_mode() == 2, st));
+            }
+            return VAG_OK;
+        }
+    }
     const bool pair = rows32_ok(h, H, w->w_hh[0], H, B, H, 3 * H, true) && rows32_ok(h + (size_t)B * H, H, w->w_hh[1], H, B, H, 3 * H, true);
     const int gate_blocks = std::max(1, std::min(ceil_div(B * H / 4, 256), num_sms()));
     for (int s_ = 0; s_ < T; ++s_) {
