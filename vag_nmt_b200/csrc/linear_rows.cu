@@ -11,6 +11,7 @@
 #include "linear_rows.cuh"
 #include <cuda_bf16.h>
 #include <stdlib.h>
+#include <type_traits>
 #include <string.h>
 
 namespace vag {
@@ -35,9 +36,29 @@ struct Rows32GruEpi {        // epilogue side of a Rows32Gru problem (the contra
     const int32_t* lengths;
     int t, H, produces_gi;
 };
+struct Rows32GruBwdEpi {     // epilogue side of a Rows32GruBwd problem
+    const float* base;
+    int64_t ld_base;
+    const float* add2;
+    int64_t ld_add2;
+    const float* gi;
+    const float* gh;
+    const float* h_prev;
+    int64_t ld_hprev;
+    float* hprev_store;
+    float* dgi;
+    float* dgh;
+    float* dh_out;
+    const int32_t* lengths;
+    int t, H;
+};
 struct Rows32Args {
     Rows32Problem p[2];
     Rows32GruEpi g[2];
+};
+struct Rows32BwdArgs {
+    Rows32Problem p[2];
+    Rows32GruBwdEpi g[2];
 };
 
 constexpr int ROWS32_WARPS = 16;
@@ -61,9 +82,10 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 // instead of the FMA loop, whose broadcast LDS.128 per 4 FMAs made shared-memory bandwidth the bound of the kernel (2.4 of 7.2 us
 // at 32 x 512 x 1536).  FP32 mode: error-compensated 3xTF32 (hi/lo split of both operands, lo·hi + hi·lo + hi·hi);
 // bf16 mode: the rounded operands are exact in TF32, one product.
-template <int BN, bool WK, bool RB, bool MMA, bool GRU = false>
+template <int BN, bool WK, bool RB, bool MMA, bool GRU = false, typename ArgsT = Rows32Args>
 __global__ void __launch_bounds__(ROWS32_WARPS * 32, 2)
-linear_rows32_kernel(const __grid_constant__ Rows32Args args, int rows, int flags) {
+linear_rows32_kernel(const __grid_constant__ ArgsT args, int rows, int flags) {
+    constexpr bool GRUB = !GRU && !WK && std::is_same<ArgsT, Rows32BwdArgs>::value;   // GRU-backward epilogue (columns = hidden units)
     // blockIdx.y selects one of two independent problems (own N, pitches and segments); __grid_constant__ keeps the
     // dynamically indexed descriptors in parameter space instead of a per-thread local copy
     const Rows32Problem& pr = args.p[blockIdx.y];
@@ -242,7 +264,7 @@ linear_rows32_kernel(const __grid_constant__ Rows32Args args, int rows, int flag
         for (int c = 0; c < BN; ++c) red[wid][lane][c] = acc[c];
     }
     __syncthreads();
-    if (GRU) {
+    if constexpr (GRU) {
         if (threadIdx.x < 32 * GU) {
             const Rows32GruEpi& ge = args.g[blockIdx.y];
             const int row = threadIdx.x / GU, i = threadIdx.x % GU, u = n0 + i, H = ge.H;
@@ -271,6 +293,42 @@ linear_rows32_kernel(const __grid_constant__ Rows32Args args, int rows, int flag
                 ge.h_out[(int64_t)row * H + u] = hn;
 #pragma unroll
                 for (int gt = 0; gt < 3; ++gt) y[(int64_t)row * ldy + gt * H + u] = live ? pre[gt] : 0.f;
+            }
+        }
+        return;
+    }
+    if constexpr (GRUB) {
+        if (threadIdx.x < 32 * BN) {
+            const auto& ge = args.g[blockIdx.y];
+            const int row = threadIdx.x / BN, c = threadIdx.x % BN, u = n0 + c, H = ge.H;
+            if (row < rows && u < N) {
+                float g = 0.f;
+#pragma unroll
+                for (int q = 0; q < ROWS32_WARPS; ++q) g += red[q][row][c];
+                if (ge.base) g += ge.base[(int64_t)row * ge.ld_base + u];
+                if (ge.add2) g += ge.add2[(int64_t)row * ge.ld_add2 + u];
+                const float hp = ge.h_prev ? ge.h_prev[(int64_t)row * ge.ld_hprev + u] : 0.f;
+                if (ge.hprev_store) ge.hprev_store[(int64_t)row * H + u] = hp;
+                float* a = ge.dgi + (int64_t)row * 3 * H;
+                float* b = ge.dgh + (int64_t)row * 3 * H;
+                if (ge.lengths && ge.lengths[row] <= ge.t) {
+                    a[u] = 0.f; a[H + u] = 0.f; a[2 * H + u] = 0.f;
+                    b[u] = 0.f; b[H + u] = 0.f; b[2 * H + u] = 0.f;
+                    ge.dh_out[(int64_t)row * H + u] = 0.f;
+                } else {
+                    const float* gir = ge.gi + (int64_t)row * 3 * H;
+                    const float* ghr = ge.gh + (int64_t)row * 3 * H;
+                    const float r = sigmoidf_precise(gir[u] + ghr[u]);
+                    const float z = sigmoidf_precise(gir[H + u] + ghr[H + u]);
+                    const float hn = ghr[2 * H + u];
+                    const float n = tanhf(gir[2 * H + u] + r * hn);
+                    const float dn_pre = g * (1.f - z) * (1.f - n * n);
+                    const float dz_pre = g * (hp - n) * z * (1.f - z);
+                    const float dr_pre = dn_pre * hn * r * (1.f - r);
+                    a[u] = dr_pre; a[H + u] = dz_pre; a[2 * H + u] = dn_pre;
+                    b[u] = dr_pre; b[H + u] = dz_pre; b[2 * H + u] = dn_pre * r;
+                    ge.dh_out[(int64_t)row * H + u] = g * z;
+                }
             }
         }
         return;
@@ -360,6 +418,43 @@ int linear_rows32_multi(const Rows32Problem* probs, int nprob, int rows, int fla
     }
     if (round_bf16) return launch_rows32<false, true>(p0, p1, nprob, rows, flags, st);
     return launch_rows32<false, false>(p0, p1, nprob, rows, flags, st);
+}
+
+bool rows32_gru_bwd_ok(const Rows32GruBwd& p, int rows) {
+    if (p.nseg < 1 || p.nseg > 2 || p.H < 64 || (p.H & 3) || !p.gi || !p.gh || !p.dgi || !p.dgh || !p.dh_out) return false;
+    for (int i = 0; i < p.nseg; ++i) {
+        if (!rows32_ok(p.seg[i].x, p.seg[i].ldx, p.seg[i].w, p.seg[i].ldw, rows, p.seg[i].K, p.H, false)) return false;
+        if (p.seg[i].x == p.dh_out) return false;
+    }
+    return true;
+}
+
+template <bool RB, bool MMA>
+static int launch_rows32_gru_bwd(const Rows32BwdArgs& args, int nprob, int rows, cudaStream_t st) {
+    static bool attr_set = false;
+    constexpr size_t smem = rows32_smem_bytes<4>();
+    if (!attr_set) {
+        VAG_CUDA(cudaFuncSetAttribute(linear_rows32_kernel<4, false, RB, MMA, false, Rows32BwdArgs>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const int H = args.g[0].H;
+    linear_rows32_kernel<4, false, RB, MMA, false, Rows32BwdArgs><<<dim3(H / 4, nprob), ROWS32_WARPS * 32, smem, st>>>(args, rows, 0);
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
+// Incoming-gradient contraction + GRU-cell backward in one launch per problem (see Rows32GruBwd).  Problems share H.
+int linear_rows32_gru_bwd(const Rows32GruBwd* probs, int nprob, int rows, bool round_bf16, cudaStream_t st) {
+    Rows32BwdArgs args = {};
+    for (int i = 0; i < 2; ++i) {
+        const Rows32GruBwd& p = probs[i < nprob ? i : 0];
+        args.p[i] = Rows32Problem{nullptr, nullptr, (int64_t)p.H, p.H, p.nseg, {p.seg[0], p.seg[1]}};
+        args.g[i] = Rows32GruBwdEpi{p.base, p.ld_base, p.add2, p.ld_add2, p.gi, p.gh, p.h_prev, p.ld_hprev, p.hprev_store,
+                                    p.dgi, p.dgh, p.dh_out, p.lengths, p.t, p.H};
+    }
+    // tensor-core inner loop only in bf16 mode for this orientation (see launch_rows32_bn)
+    if (round_bf16) return rows32_use_mma() ? launch_rows32_gru_bwd<true, true>(args, nprob, rows, st) : launch_rows32_gru_bwd<true, false>(args, nprob, rows, st);
+    return launch_rows32_gru_bwd<false, false>(args, nprob, rows, st);
 }
 
 bool rows32_gru_ok(const Rows32Gru& p, int rows) {

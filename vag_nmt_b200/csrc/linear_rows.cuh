@@ -42,6 +42,32 @@ struct Rows32Gru {
     int H;
     Rows32Seg seg;           // x [rows, K] against w [3H, K] (k-fast)
 };
+// Backward of a GRU cell fused behind the contraction that finishes its incoming gradient:
+//   g[row, u] = Σ_seg x_seg · W_seg (columns = hidden units, W read transposed)  (+ base[row, u])  (+ add2[row, u])
+//   → dgi / dgh [rows, 3H] of the cell (gate order r | z | n) and dh_out[row, u] = g · z, the part of the gradient that flows
+//   straight to the previous state.  Rows with lengths[row] <= t get zeros.  hprev_store (optional) keeps the previous state the
+//   cell saw (the encoder reads it back from its context output).
+struct Rows32GruBwd {
+    Rows32Seg seg[2];
+    int nseg;
+    const float* base;       // optional, pitch ld_base
+    int64_t ld_base;
+    const float* add2;       // optional, pitch ld_add2
+    int64_t ld_add2;
+    const float* gi;         // [rows, 3H] saved pre-activations
+    const float* gh;
+    const float* h_prev;     // optional (null: 0), pitch ld_hprev
+    int64_t ld_hprev;
+    float* hprev_store;      // optional [rows, H]
+    float* dgi;              // [rows, 3H]
+    float* dgh;
+    float* dh_out;           // [rows, H]
+    const int32_t* lengths;  // optional
+    int t;
+    int H;
+};
+bool rows32_gru_bwd_ok(const Rows32GruBwd& p, int rows);
+int linear_rows32_gru_bwd(const Rows32GruBwd* probs, int nprob, int rows, bool round_bf16, cudaStream_t st);
 bool rows32_gru_ok(const Rows32Gru& p, int rows);
 int linear_rows32_gru(const Rows32Gru* probs, int nprob, int rows, bool round_bf16, cudaStream_t st);
 

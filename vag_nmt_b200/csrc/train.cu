@@ -982,7 +982,54 @@ extern "C" int vag_decoder_seq_bwd_f32(const vag_decoder_weights* w, const float
     VAG_CUDA(cudaMemsetAsync(d_enc, 0, sizeof(float) * (size_t)B * T * C, st));
     VAG_CUDA(cudaMemsetAsync(g->attn_v, 0, sizeof(float) * C, st));
     VAG_CUDA(cudaMemsetAsync(dh_next, 0, sizeof(float) * (size_t)B * H, st));
-    for (int t = Tt - 1; t >= 0; --t) {
+    // fused flavour of the loop below: the two contractions that finish a cell's incoming gradient carry that cell's gate
+    // backward in their epilogue (dh1 → gru_1 at step t; dh_next + read-out path → gru_2 at step t-1): 5 launches per step
+    Rows32GruBwd dprobe = {};
+    dprobe.seg[0] = Rows32Seg{dgh2_all, w->gru2_w_hh, 3 * H, H, 3 * H};
+    dprobe.seg[1] = Rows32Seg{dq_all, w->attn_h_w, C, H, C};
+    dprobe.nseg = 2; dprobe.gi = s->gi1_all; dprobe.gh = s->gh1_all; dprobe.dgi = dgi1_all; dprobe.dgh = dgh1_all; dprobe.dh_out = dh_next; dprobe.H = H;
+    const bool fused_dec = rows32_gru_bwd_ok(dprobe, B);
+    if (fused_dec) {
+        const size_t last = (size_t)(Tt - 1) * B;
+        gru_gates_bwd_kernel<<<grid_for((int64_t)B * H), 256, 0, st>>>(dgi2_all + last * 3 * H, dgh2_all + last * 3 * H, dh1, dh2_dir + last * H, H,
+                                                                        s->gi2_all + last * 3 * H, s->gh2_all + last * 3 * H,
+                                                                        s->h1_all + last * H, H, B, H, dh_next);
+        VAG_LAUNCH_CHECK();
+    }
+    for (int t = Tt - 1; fused_dec && t >= 0; --t) {
+        const size_t o3 = (size_t)t * B * 3 * H, oh = (size_t)t * B * H, oc = (size_t)t * B * C;
+        float* dx2 = dx2_all + oh;
+        VAG_TRY(gemm_g(dx2, H, dgi2_all + o3, 3 * H, 1, w->gru2_w_ih, H, 1, B, H, 3 * H, 0.f, st));           // dx2 = dgi2 · W_ih2
+        float* dc = dc_dir + oc;
+        VAG_TRY(gemm_g(dc, C, dx2, H, 1, w->c2h_w, C, 1, B, C, H, 1.f, st));                                    // dc += dx2 · W_c2h
+        float* dq = dq_all + oc;
+        VAG_TRY(vag_attention_bwd_f32(dq, C, dkeys, d_enc, g->attn_v, dc, C, s->alpha_all + (size_t)t * B * T, s->q_all + oc,
+                                      C, s->keys, enc, w->attn_v, mask, B, T, C, VAG_ATTN_MLP, vs));
+        Rows32GruBwd a = {};      // g = dh1 + dgh2·W_hh2 + dq·W_attn_h → gru_1 backward at step t → dgi1, dgh1, dh_next = g·z
+        a.seg[0] = Rows32Seg{dgh2_all + o3, w->gru2_w_hh, 3 * H, H, 3 * H};
+        a.seg[1] = Rows32Seg{dq, w->attn_h_w, C, H, C};
+        a.nseg = 2;
+        a.base = dh1; a.ld_base = H;
+        a.gi = s->gi1_all + o3; a.gh = s->gh1_all + o3;
+        a.h_prev = t == 0 ? h0 : s->h2_all + (size_t)(t - 1) * B * H; a.ld_hprev = H;
+        a.dgi = dgi1_all + o3; a.dgh = dgh1_all + o3; a.dh_out = dh_next; a.H = H;
+        VAG_TRY(linear_rows32_gru_bwd(&a, 1, B, gemm_mode() == 2, st));
+        if (t > 0) {              // g = dh_next + dgh1·W_hh1 + read-out path of step t-1 → gru_2 backward at step t-1 → dgi2, dgh2, dh1 = g·z
+            const size_t p3 = (size_t)(t - 1) * B * 3 * H, ph = (size_t)(t - 1) * B * H;
+            Rows32GruBwd b2 = {};
+            b2.seg[0] = Rows32Seg{dgh1_all + o3, w->gru1_w_hh, 3 * H, H, 3 * H};
+            b2.nseg = 1;
+            b2.base = dh_next; b2.ld_base = H;
+            b2.add2 = dh2_dir + ph; b2.ld_add2 = H;
+            b2.gi = s->gi2_all + p3; b2.gh = s->gh2_all + p3;
+            b2.h_prev = s->h1_all + ph; b2.ld_hprev = H;
+            b2.dgi = dgi2_all + p3; b2.dgh = dgh2_all + p3; b2.dh_out = dh1; b2.H = H;
+            VAG_TRY(linear_rows32_gru_bwd(&b2, 1, B, gemm_mode() == 2, st));
+        } else {
+            VAG_TRY(gemm_g(dh_next, H, dgh1_all + o3, 3 * H, 1, w->gru1_w_hh, H, 1, B, H, 3 * H, 1.f, st));   // → d h0
+        }
+    }
+    for (int t = Tt - 1; !fused_dec && t >= 0; --t) {
         const float* dh2 = dh2_dir + (size_t)t * B * H;     // read-out path; the recurrent path dh_next is added inside the kernel
         float* dgi2 = dgi2_all + (size_t)t * B * 3 * H;
         float* dgh2 = dgh2_all + (size_t)t * B * 3 * H;
@@ -1268,7 +1315,40 @@ extern "C" int vag_encoder_bwd_f32(const vag_encoder_weights* w, const int32_t* 
     VAG_CUDA(cudaMemsetAsync(carry, 0, sizeof(float) * (size_t)2 * B * H, st));
     const bool pair = rows32_ok(dgh_all, 3 * H, w->w_hh[0], H, B, 3 * H, H, false) && rows32_ok(dgh_all, 3 * H, w->w_hh[1], H, B, 3 * H, H, false);
     const int gate_blocks = std::max(1, std::min(ceil_div(B * H, 256), num_sms()));
-    for (int s_ = 0; s_ < T; ++s_) {
+    // fused flavour: step 0 runs the gate backward alone; every later step is ONE launch per time step — the recurrent
+    // contraction carry + dgh(previous step)·W_hh with the gate backward of the current step in its epilogue, both directions.
+    // (The contraction after the last step would only produce the gradient of the constant zero initial state.)
+    Rows32GruBwd eprobe = {};
+    eprobe.seg[0] = Rows32Seg{dgh_all, w->w_hh[0], 3 * H, H, 3 * H};
+    eprobe.nseg = 1; eprobe.gi = gi; eprobe.gh = gh; eprobe.dgi = dgi_all; eprobe.dgh = dgh_all; eprobe.dh_out = carry; eprobe.H = H;
+    const bool fused_bwd = rows32_gru_bwd_ok(eprobe, B);
+    for (int s_ = 0; fused_bwd && s_ < T; ++s_) {
+        if (s_ == 0) {
+            enc_gates_bwd_kernel<<<dim3(gate_blocks, 2), 256, 0, st>>>(dgi_all, dgh_all, hprev_all, carry, dctx, ctx, gi, gh, lengths_dev, B, T, H, 0);
+            VAG_LAUNCH_CHECK();
+            continue;
+        }
+        Rows32GruBwd pp[2];
+        for (int d = 0; d < 2; ++d) {
+            const int t = d == 0 ? T - 1 - s_ : s_, t_before = d == 0 ? t + 1 : t - 1;      // t_before: the step handled one launch ago
+            const int tp = d == 0 ? t - 1 : t + 1;                                           // where this step's previous state was produced
+            const size_t o3 = ((size_t)d * T + t) * B * 3 * H, ob = ((size_t)d * T + t_before) * B * 3 * H;
+            Rows32GruBwd q = {};
+            q.seg[0] = Rows32Seg{dgh_all + ob, w->w_hh[d], 3 * H, H, 3 * H};
+            q.nseg = 1;
+            q.base = carry + (size_t)d * B * H; q.ld_base = H;
+            q.add2 = dctx + (int64_t)t * 2 * H + (int64_t)d * H; q.ld_add2 = (int64_t)T * 2 * H;
+            q.gi = gi + o3; q.gh = gh + o3;
+            q.h_prev = (tp >= 0 && tp < T) ? ctx + (int64_t)tp * 2 * H + (int64_t)d * H : nullptr; q.ld_hprev = (int64_t)T * 2 * H;
+            q.hprev_store = hprev_all + ((size_t)d * T + t) * B * H;
+            q.dgi = dgi_all + o3; q.dgh = dgh_all + o3;
+            q.dh_out = carry + (size_t)d * B * H;
+            q.lengths = lengths_dev; q.t = t; q.H = H;
+            pp[d] = q;
+        }
+        VAG_TRY(linear_rows32_gru_bwd(pp, 2, B, gemm_mode() == 2, st));
+    }
+    for (int s_ = 0; !fused_bwd && s_ < T; ++s_) {
         enc_gates_bwd_kernel<<<dim3(gate_blocks, 2), 256, 0, st>>>(dgi_all, dgh_all, hprev_all, carry, dctx, ctx, gi, gh, lengths_dev, B, T, H, s_);
         VAG_LAUNCH_CHECK();
         const int t0 = T - 1 - s_, t1 = s_;
