@@ -107,6 +107,25 @@ linear_rows32_kernel(const __grid_constant__ ArgsT args, int rows, int flags) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     float* xs = xs_all + wid * 32 * XP;
     float* wt = wt_all + wid * WT;
+    // GRU-backward epilogue: its operands are fetched NOW, so that their L2 round trip overlaps the main loop instead of
+    // following the cross-warp reduction
+    float pf_gi[3] = {0.f, 0.f, 0.f}, pf_gh[3] = {0.f, 0.f, 0.f}, pf_hp = 0.f, pf_add = 0.f;
+    if constexpr (GRUB) {
+        if (threadIdx.x < 32 * BN) {
+            const auto& ge = args.g[blockIdx.y];
+            const int row = threadIdx.x / BN, u = n0 + threadIdx.x % BN, H = ge.H;
+            if (row < rows && u < N) {
+#pragma unroll
+                for (int gt = 0; gt < 3; ++gt) {
+                    pf_gi[gt] = ge.gi[(int64_t)row * 3 * H + gt * H + u];
+                    pf_gh[gt] = ge.gh[(int64_t)row * 3 * H + gt * H + u];
+                }
+                pf_hp = ge.h_prev ? ge.h_prev[(int64_t)row * ge.ld_hprev + u] : 0.f;
+                if (ge.base) pf_add += ge.base[(int64_t)row * ge.ld_base + u];
+                if (ge.add2) pf_add += ge.add2[(int64_t)row * ge.ld_add2 + u];
+            }
+        }
+    }
     float acc[BN];
 #pragma unroll
     for (int c = 0; c < BN; ++c) acc[c] = 0.f;
@@ -305,9 +324,8 @@ linear_rows32_kernel(const __grid_constant__ ArgsT args, int rows, int flags) {
                 float g = 0.f;
 #pragma unroll
                 for (int q = 0; q < ROWS32_WARPS; ++q) g += red[q][row][c];
-                if (ge.base) g += ge.base[(int64_t)row * ge.ld_base + u];
-                if (ge.add2) g += ge.add2[(int64_t)row * ge.ld_add2 + u];
-                const float hp = ge.h_prev ? ge.h_prev[(int64_t)row * ge.ld_hprev + u] : 0.f;
+                g += pf_add;
+                const float hp = pf_hp;
                 if (ge.hprev_store) ge.hprev_store[(int64_t)row * H + u] = hp;
                 float* a = ge.dgi + (int64_t)row * 3 * H;
                 float* b = ge.dgh + (int64_t)row * 3 * H;
@@ -316,12 +334,10 @@ linear_rows32_kernel(const __grid_constant__ ArgsT args, int rows, int flags) {
                     b[u] = 0.f; b[H + u] = 0.f; b[2 * H + u] = 0.f;
                     ge.dh_out[(int64_t)row * H + u] = 0.f;
                 } else {
-                    const float* gir = ge.gi + (int64_t)row * 3 * H;
-                    const float* ghr = ge.gh + (int64_t)row * 3 * H;
-                    const float r = sigmoidf_precise(gir[u] + ghr[u]);
-                    const float z = sigmoidf_precise(gir[H + u] + ghr[H + u]);
-                    const float hn = ghr[2 * H + u];
-                    const float n = tanhf(gir[2 * H + u] + r * hn);
+                    const float r = sigmoidf_precise(pf_gi[0] + pf_gh[0]);
+                    const float z = sigmoidf_precise(pf_gi[1] + pf_gh[1]);
+                    const float hn = pf_gh[2];
+                    const float n = tanhf(pf_gi[2] + r * hn);
                     const float dn_pre = g * (1.f - z) * (1.f - n * n);
                     const float dz_pre = g * (hp - n) * z * (1.f - z);
                     const float dr_pre = dn_pre * hn * r * (1.f - r);
