@@ -15,7 +15,6 @@ int linear_simt(float* y, int64_t ldy, const float* x, int64_t ldx, const float*
                 int rows, int K, int N, int flags, cudaStream_t st);
 int tc_elem_bytes();
 int tc_split(const float* x, int64_t ldx, int rows, int K, void* hi, void* lo, int64_t ld_out, int64_t col_off, cudaStream_t st);
-int tc_split_t(const float* x, int64_t ldx, int R, int M, void* hi, void* lo, int64_t ld_out, int Rp, cudaStream_t st);
 int tc_split_pair(const float* x, int64_t ldx, bool xt, int M, void* xh, void* xl, const float* w, int64_t ldw, bool wt, int N,
                   void* wh, void* wl, int K, int Kp, cudaStream_t st);
 int tc_gemm(float* y, int64_t ldy, const void* xh, const void* xl, int64_t ldxs, const void* wh, const void* wl, int64_t ldws,

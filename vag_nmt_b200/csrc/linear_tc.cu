@@ -1431,54 +1431,6 @@ int tc_split(const float* x, int64_t ldx, int rows, int K, void* hi, void* lo, i
     return VAG_OK;
 }
 
-// Split of the TRANSPOSE: x is stored [R, M] (pitch ldx, any alignment); the planes are [M, ld_out] with element (m, r) =
-// split(x[r, m]) and zeros for R <= r < Rp (Rp <= ld_out: the contraction length padded to a multiple of 8).  Used by the
-// backward pass, where the contraction runs over the batch·time rows (dW = dyᵀ·x) or over a weight's output index
-// (dx = dy·W): both operands of tc_gemm must be contraction-contiguous.
-template <int MODE>   // 0: TF32 planes (float), 1: FP16 hi/lo, 2: BF16 single plane
-__global__ void __launch_bounds__(256)
-split_t_kernel(const float* __restrict__ x, int64_t ldx, int R, int M, void* __restrict__ hi_, void* __restrict__ lo_, int64_t ldo, int Rp) {
-    __shared__ float tile[32][33];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int r0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int r = r0 + ty + 8 * j, m = m0 + tx;
-        tile[ty + 8 * j][tx] = (r < R && m < M) ? x[(int64_t)r * ldx + m] : 0.f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int m = m0 + ty + 8 * j, r = r0 + tx;
-        if (m >= M || r >= Rp) continue;
-        const float v = tile[tx][ty + 8 * j];
-        const int64_t o = (int64_t)m * ldo + r;
-        if (MODE == 0) {
-            uint32_t t;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
-            const float h = __uint_as_float(t);
-            ((float*)hi_)[o] = h;
-            ((float*)lo_)[o] = v - h;
-        } else if (MODE == 1) {
-            const __half h = __float2half_rn(v);
-            ((__half*)hi_)[o] = h;
-            ((__half*)lo_)[o] = __float2half_rn((v - __half2float(h)) * 2048.0f);
-        } else {
-            ((__nv_bfloat16*)hi_)[o] = __float2bfloat16_rn(v);
-        }
-    }
-}
-
-int tc_split_t(const float* x, int64_t ldx, int R, int M, void* hi, void* lo, int64_t ld_out, int Rp, cudaStream_t st) {
-    if (M == 0 || Rp == 0) return VAG_OK;
-    dim3 grid(ceil_div(Rp, 32), ceil_div(M, 32));
-    if (gemm_mode() == 2) split_t_kernel<2><<<grid, 256, 0, st>>>(x, ldx, R, M, hi, lo, ld_out, Rp);
-    else if (use_f16_split()) split_t_kernel<1><<<grid, 256, 0, st>>>(x, ldx, R, M, hi, lo, ld_out, Rp);
-    else split_t_kernel<0><<<grid, 256, 0, st>>>(x, ldx, R, M, hi, lo, ld_out, Rp);
-    VAG_LAUNCH_CHECK();
-    return VAG_OK;
-}
-
 // Both operands of one contraction split in ONE launch (blockIdx.z = operand): out(r, c) = split(src(r, c)) for c < cols,
 // zero for cols <= c < cols_pad, where src(r, c) = src[c·ld + r] when the operand is stored contraction-major (transposed)
 // and src[r·ld + c] otherwise.  Inside a captured graph every node costs ~2 µs of dependency latency whatever it does, so the

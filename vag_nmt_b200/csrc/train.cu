@@ -712,7 +712,7 @@ int nll_rows_all(const float* logits, int64_t ld, const int64_t* tgt, const floa
                  float* lse_out, float* nll_scratch, cudaStream_t st);
 // ---- tensor-core route of the batched backward contractions (dW = dyᵀ·x over all batch·time rows, dx = dy·W) --------------
 // tc_gemm wants both operands contraction-contiguous ([M, Kc] and [N, Kc]); an operand stored the other way round goes
-// through the transposing split (tc_split_t).  Scratch for the operand planes comes from the composite's workspace.
+// through the transposing branch of the operand split (tc_split_pair).  Scratch for the operand planes comes from the composite's workspace.
 struct TcScratch {
     char* base = nullptr;
     size_t cap = 0;
