@@ -59,9 +59,33 @@ def _round_operand(t: torch.Tensor) -> torch.Tensor:
     return t.to(torch.bfloat16).to(t.dtype) if _OPERAND_ROUNDING == "bf16" else t
 
 
+class _RoundedLinearFn(torch.autograd.Function):
+    """y = r(x)·r(W)ᵀ with r = round-to-bfloat16, for the bf16-mode comparison runs.  The backward rounds the operands of ITS
+    two contractions the same way (dx = r(dy)·r(W), dW = r(dy)ᵀ·r(x)) and accumulates in the working dtype — the points at
+    which the B200 path rounds in bf16 mode ("every contraction, forward and backward, rounds its operands").  Plain autograd
+    through ``x.to(bf16).to(dtype)`` would instead round the RESULTS dx / dW, which no implementation does."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        xr, wr = _round_operand(x), _round_operand(w)
+        ctx.save_for_backward(xr, wr)
+        return xr.matmul(wr.t())
+
+    @staticmethod
+    def backward(ctx, dy):
+        xr, wr = ctx.saved_tensors
+        dyr = _round_operand(dy)
+        dx = dyr.matmul(wr)
+        dw = dyr.reshape(-1, dyr.shape[-1]).t().matmul(xr.reshape(-1, xr.shape[-1]))
+        return dx, dw
+
+
 def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor] = None) -> torch.Tensor:
     """y = x Wᵀ (+ b) — what every nn.Linear on the path computes."""
-    y = _round_operand(x).matmul(_round_operand(w).t())
+    if _OPERAND_ROUNDING == "bf16" and (x.requires_grad or w.requires_grad):
+        y = _RoundedLinearFn.apply(x, w)
+    else:
+        y = _round_operand(x).matmul(_round_operand(w).t())
     if b is not None:
         y = y + b
     return y

@@ -1,0 +1,123 @@
+"""GPU: the bf16 arithmetic mode of the TRAINING step (model.precision = "bf16", BASELINE configs[1]) — every parameter
+gradient and a 20-step loss trajectory against the oracle with bf16-rounded contraction operands.
+
+The comparison run rounds at the same points as the B200 path: the two operands of every nn.Linear / GRU-matrix contraction,
+forward (y = r(x)·r(W)ᵀ) and backward (dx = r(dy)·r(W), dW = r(dy)ᵀ·r(x)), accumulate in FP32; state, soft-max, attention,
+losses and Adam stay FP32 (oracle/vag_oracle.py:_RoundedLinearFn; reference semantics train.py:36-51, V11:82-168).
+Gradients are compared norm-wise per tensor, ‖g − g_ref‖₂ / ‖g_ref‖₂; the tolerance 1e-2 is a handful of bf16 ulps (2⁻⁸) of a
+single operand: the GPU rounds values that differ from the oracle's in their last FP32 bits, so individual bf16 roundings flip.
+"""
+import pytest
+import torch
+
+from conftest import build_mm, cpu_params
+
+pytestmark = pytest.mark.gpu
+GRAD_TOL = 1e-2
+
+
+@pytest.fixture()
+def bf16_oracle():
+    from oracle import vag_oracle as O
+    O.set_operand_rounding("bf16")
+    yield O
+    O.set_operand_rounding(None)
+
+
+def _oracle_params(model):
+    p = {k: v.clone().requires_grad_(True) for k, v in cpu_params(model).items()}
+    p["decoder.out.weight"] = p["decoder.embedding.weight"]       # tied (NMT_Decoder.py:105-106)
+    return p
+
+
+def _norm_err(g, r):
+    g, r = g.detach().cpu().double(), r.detach().double()
+    return float((g - r).norm() / r.norm().clamp(min=1e-30))
+
+
+def test_bf16_gradients_de_b32(bf16_oracle):
+    """EN→DE shapes, B = 32 (configs[1]): loss and EVERY parameter gradient of the bf16 mode."""
+    O = bf16_oracle
+    import vag_nmt_b200 as vag
+    from vag_nmt_b200 import synthetic
+    cfg = dict(synthetic.DE)
+    model = build_mm(cfg, 1234).cuda().train()
+    model.precision = "bf16"
+    batch = synthetic.make_batch(32, cfg["src_size"], cfg["tgt_size"], cfg["im_feats_size"], seed=7)
+    w = torch.ones(cfg["tgt_size"])
+    w[0] = 0
+    p = _oracle_params(model)
+    ref = O.multimodal_forward(p, batch.src, batch.src_lengths, batch.tgt, batch.im, True, w, "pairwise", 0.1)
+    ref[0].backward()
+    # the unrounded FP32 gradient, to show what the tolerance means: bf16 mode itself moves gradients by ~1e-2
+    O.set_operand_rounding(None)
+    p32 = _oracle_params(model)
+    O.multimodal_forward(p32, batch.src, batch.src_lengths, batch.tgt, batch.im, True, w, "pairwise", 0.1)[0].backward()
+    O.set_operand_rounding("bf16")
+
+    crit = torch.nn.NLLLoss(weight=w.cuda(), reduction="none")
+    out = model(batch.src, batch.src_lengths, batch.tgt, batch.im, 1.0, criterion_mt=crit, criterion_vse=vag.PairwiseRankingLoss(margin=0.1))
+    got = torch.stack([x.reshape(()) for x in out]).detach().cpu()
+    want = torch.stack([x.detach() for x in ref])
+    assert float(((got - want).abs() / want.abs()).max()) < 1e-3, (got, want)
+    with model.precision_scope():
+        out[0].backward()
+    worst, mode_shift, report = 0.0, 0.0, []
+    for name, prm in model.named_parameters():
+        assert prm.grad is not None, name
+        r = p[name].grad
+        if float(r.norm()) == 0.0:
+            assert float(prm.grad.abs().max()) < 1e-9, name
+            continue
+        e = _norm_err(prm.grad, r)
+        report.append((round(e, 5), name))
+        worst = max(worst, e)
+        mode_shift = max(mode_shift, _norm_err(p32[name].grad, r))
+        assert e < GRAD_TOL, f"{name}: ‖g − g_ref‖/‖g_ref‖ = {e:.3e}"
+    print("bf16 gradient parity, worst first:", sorted(report, reverse=True)[:6], "| bf16-vs-fp32 oracle shift", mode_shift)
+    assert worst < mode_shift + GRAD_TOL     # closer to the same-rounding oracle than a generic bf16 perturbation would require
+
+
+def test_bf16_twenty_step_loss_trajectory(bf16_oracle):
+    """20 optimisation steps (zero_grad → forward → backward → clip 1.0 → Adam, train.py:36-51) in bf16 mode against the CPU
+    run of the same-rounding oracle + torch clip_grad_norm_ + optim.Adam with the reference's parameter groups."""
+    O = bf16_oracle
+    import vag_nmt_b200 as vag
+    from vag_nmt_b200 import synthetic
+    from vag_nmt_b200.optim import ClipAdam
+    from vag_nmt_b200.train import train_imagine_beam
+    cfg = dict(synthetic.DE)
+    model = build_mm(cfg, 1234).cuda().train()
+    model.precision = "bf16"
+    batches = [synthetic.make_batch(32, cfg["src_size"], cfg["tgt_size"], cfg["im_feats_size"], seed=300 + i) for i in range(4)]
+    w = torch.ones(cfg["tgt_size"])
+    w[0] = 0
+    # CPU side
+    p = _oracle_params(model)
+    leaves = {k: v for k, v in p.items() if k != "decoder.out.weight"}
+    opt_ref = torch.optim.Adam([{"params": [v for k, v in leaves.items() if "bias" not in k], "weight_decay": 1e-5},
+                                {"params": [v for k, v in leaves.items() if "bias" in k]}], lr=4e-4)
+    ref_losses = []
+    for it in range(20):
+        bt = batches[it % 4]
+        opt_ref.zero_grad()
+        loss = O.multimodal_forward(p, bt.src, bt.src_lengths, bt.tgt, bt.im, True, w, "pairwise", 0.1)[0]
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(list(leaves.values()), 1.0)
+        opt_ref.step()
+        ref_losses.append(float(loss))
+    # B200 side
+    opt = ClipAdam(model, lr=4e-4)
+    crit = torch.nn.NLLLoss(weight=w.cuda(), reduction="none")
+    cv = vag.PairwiseRankingLoss(margin=0.1)
+    got_losses = []
+    for it in range(20):
+        bt = batches[it % 4]
+        got_losses.append(train_imagine_beam(bt.src, bt.tgt, bt.im, bt.src_lengths, model, opt, crit, cv, 0.99, 1.0)[0])
+    rel = [abs(a - b) / abs(b) for a, b in zip(got_losses, ref_losses)]
+    print("bf16 20-step trajectory: first/last loss", got_losses[0], got_losses[-1], "ref", ref_losses[0], ref_losses[-1], "max rel", max(rel))
+    assert ref_losses[-1] < ref_losses[0]                    # the run actually optimises
+    assert max(rel) < 2e-3, list(zip(got_losses, ref_losses))
+    # and the parameters after 20 steps agree norm-wise
+    for name, prm in model.named_parameters():
+        assert _norm_err(prm, leaves[name]) < 2e-3, name

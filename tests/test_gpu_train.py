@@ -82,23 +82,37 @@ def test_tiny_mlp_attention_and_text_only_gradients():
     _check_grads(tm, ref)
 
 
-def test_full_shape_gradients_fp32_oracle():
-    """EN→DE shapes, B = 8: gradients against the FP32 CPU oracle (FP64 at this size takes minutes)."""
+def test_full_shape_gradients_b32_reference_golden_and_oracle(full_de):
+    """EN→DE shapes, B = 32 (BASELINE configs[1]): losses and EVERY parameter gradient against (a) the fixture written by the
+    REAL reference's autograd in fp64 (oracle/make_golden.py:ref_train_gradients — norm and 64 probed entries per tensor) and
+    (b) full tensors from autograd through the FP32 CPU oracle on the same batch."""
     import vag_nmt_b200 as vag
     from vag_nmt_b200 import synthetic
-    cfg = dict(synthetic.DE)
-    model = build_mm(cfg, 1234).cuda().train()
-    batch = synthetic.make_batch(8, cfg["src_size"], cfg["tgt_size"], cfg["im_feats_size"], seed=9, max_len=12)
+    fix = full_de
+    cfg = fix["cfg"]
+    model = build_mm(cfg, fix["seed"]).cuda().train()
+    batch = synthetic.make_batch(fix["batch_size"], cfg["src_size"], cfg["tgt_size"], cfg["im_feats_size"], seed=fix["data_seed"])
     ref_loss, ref = _oracle_grads("mm", model, batch, True, dtype=torch.float32)
     w = torch.ones(cfg["tgt_size"])
     w[0] = 0
     crit = torch.nn.NLLLoss(weight=w.cuda(), reduce=False)
-    loss, _, _ = model(batch.src, batch.src_lengths, batch.tgt, batch.im, 1.0, criterion_mt=crit,
-                       criterion_vse=vag.PairwiseRankingLoss(margin=0.1))
-    assert abs(float(loss) - ref_loss) < 1e-4 * abs(ref_loss)
-    loss.backward()
-    worst = _check_grads(model, ref, tol=5e-3)
-    assert worst < 5e-3
+    out = model(batch.src, batch.src_lengths, batch.tgt, batch.im, 1.0, criterion_mt=crit,
+                criterion_vse=vag.PairwiseRankingLoss(margin=0.1))
+    assert abs(float(out[0]) - ref_loss) < 1e-4 * abs(ref_loss)
+    gold = fix["train_fp64"]
+    got = torch.stack([x.reshape(()) for x in out]).detach().cpu().double()
+    assert float(((got - gold["losses"]).abs() / gold["losses"].abs()).max()) < 1e-4
+    out[0].backward()
+    worst = _check_grads(model, ref, tol=2e-3)
+    assert worst < 2e-3
+    for name, prm in model.named_parameters():
+        pr = gold["grads"][name]
+        g = prm.grad.detach().cpu().double()
+        assert list(g.shape) == pr["shape"], name
+        if pr["l2"] == 0.0:
+            continue
+        assert float((g.reshape(-1)[pr["idx"]] - pr["vals"]).norm() / pr["vals"].norm()) < 2e-3, name
+        assert abs(float(g.norm()) - pr["l2"]) < 2e-3 * pr["l2"], name
 
 
 def test_training_mode_dropout_with_injected_masks():

@@ -78,6 +78,63 @@ def test_full_shapes_forward_and_beam5(full_de):
             fix["ref_fp32"]["decode_k5"]
 
 
+def test_full_fr_shapes_losses_gradients_and_beam5():
+    """EN→FR shapes (BASELINE configs[3]: V = 8748, dropout 0.2 / 0.4 / 0.4): the oracle — forward, autograd with the injected
+    dropout masks, beam 5 — against the fixture the real reference produced (oracle/make_golden.py:fr_fixture)."""
+    import vag_nmt_b200 as vag
+    from conftest import cpu_params, load_golden
+    from vag_nmt_b200 import synthetic
+    fix = load_golden("full_fr_b32.pt")
+    cfg = fix["cfg"]
+    torch.manual_seed(fix["seed"])
+    m = vag.NMT_AttentionImagine_Seq2Seq_Beam_V11(cfg["src_size"], cfg["tgt_size"], cfg["im_feats_size"], cfg["src_embedding_size"],
+                                                  cfg["tgt_embedding_size"], cfg["hidden_size"], cfg["shared_embedding_size"], 0.99,
+                                                  tied_emb=True, init_split=0.5, **fix["dropout"])
+    for k, v in m.state_dict().items():
+        s_, a = fix["param_checksums"][k]
+        assert abs(float(v.double().sum()) - s_) <= 1e-9 * max(1.0, abs(a)), k
+    b = synthetic.make_batch(fix["batch_size"], cfg["src_size"], cfg["tgt_size"], cfg["im_feats_size"], seed=fix["data_seed"])
+    B, Ts = b.src.shape
+    d = fix["dropout"]
+    masks = synthetic.dropout_masks(fix["mask_seed"], B, Ts, b.tgt.shape[1], cfg["src_embedding_size"], cfg["hidden_size"],
+                                    cfg["tgt_embedding_size"], d["dropout_emb"], d["dropout_ctx"], d["dropout_out"])
+    w = torch.ones(cfg["tgt_size"])
+    w[0] = 0
+    p = {k: v.clone().requires_grad_(True) for k, v in cpu_params(m).items()}
+    p["decoder.out.weight"] = p["decoder.embedding.weight"]
+    ref = fix["ref_fp32"]
+    with torch.no_grad():
+        _check(ref["fwd_eval"], torch.stack(O.multimodal_forward(p, b.src, b.src_lengths, b.tgt, b.im, True, w, "pairwise", 0.1)), 2e-5)
+        assert O.multimodal_beamsearch_decode(p, b.src, b.src_lengths, b.im, 5, fix["max_length"], hoist_keys=True) == ref["decode_k5"]
+    out = O.multimodal_forward(p, b.src, b.src_lengths, b.tgt, b.im, True, w, "pairwise", 0.1, dropout_masks=masks)
+    _check(ref["train"]["losses"], torch.stack([x.detach() for x in out]), 2e-5)
+    out[0].backward()
+    for name, pr in fix["ref_fp64"]["train"]["grads"].items():
+        g = p[name].grad.double()
+        assert list(g.shape) == pr["shape"]
+        if pr["l2"] > 0:
+            assert float((g.reshape(-1)[pr["idx"]] - pr["vals"]).norm() / pr["vals"].norm()) < 2e-4, name
+            assert abs(float(g.norm()) - pr["l2"]) < 2e-4 * pr["l2"], name
+
+
+def test_bf16_rounded_linear_backward_rounds_its_operands():
+    """The comparison arithmetic of the bf16 mode: forward AND backward contractions see bf16-rounded operands."""
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(7, 16, generator=g, requires_grad=True)
+    wt = torch.randn(5, 16, generator=g, requires_grad=True)
+    dy = torch.randn(7, 5, generator=g)
+    r = lambda t: t.to(torch.bfloat16).to(torch.float32)
+    O.set_operand_rounding("bf16")
+    try:
+        y = O.linear(x, wt)
+        y.backward(dy)
+    finally:
+        O.set_operand_rounding(None)
+    assert torch.equal(y.detach(), r(x.detach()) @ r(wt.detach()).t())
+    assert torch.allclose(x.grad, r(dy) @ r(wt.detach()), atol=1e-6)
+    assert torch.allclose(wt.grad, r(dy).t() @ r(x.detach()), atol=1e-6)
+
+
 def test_beam_known_answers(beam_kat):
     """SURVEY.md appendix A cases (generated by the reference's beamsearch with a table decoder)."""
     LP = torch.tensor(beam_kat["P"]).log()

@@ -27,8 +27,17 @@ def _worker(rank, world, port, out_dir):
     sents, im = synthetic.make_corpus(9, cfg["src_size"], cfg["im_feats_size"], seed=4, max_len=8, min_len=1, mean=4, std=2)
     fn = lambda src, lens, im_b, K, L: O.multimodal_beamsearch_decode(p, src, lens, im_b, K, L)
     sharded = decode_corpus_sharded(fn, sents, im, 3, 9)
+    contiguous = decode_corpus_sharded(fn, sents, im, 3, 9, balance=False)
     single = decode_corpus(fn, sents, im, 3, 9)
-    torch.save(dict(ok=sharded == single, n=len(sharded)), os.path.join(out_dir, f"r{rank}.pt"))
+    # retrieval evaluation: sharded embedding + all-gather + replicated recall == single process
+    from vag_nmt_b200.translate import embed_corpus, embed_corpus_sharded, retrieval_eval_sharded
+    efn = lambda src, lens, im_b: O.embed_sent_im(p, src, lens, im_b)
+    lim, ltxt = embed_corpus_sharded(efn, sents, im, batch_size=4)
+    lim1, ltxt1 = embed_corpus(efn, sents, im, batch_size=4)
+    recall = retrieval_eval_sharded(efn, sents, im, batch_size=4, rank_fn=O.t2i)
+    emb_ok = bool(torch.allclose(lim, lim1, atol=1e-6) and torch.allclose(ltxt, ltxt1, atol=1e-6))
+    torch.save(dict(ok=sharded == single and contiguous == single, n=len(sharded), emb_ok=emb_ok, recall=[float(x) for x in recall],
+                    recall_single=[float(x) for x in O.t2i(lim1, ltxt1)]), os.path.join(out_dir, f"r{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -41,6 +50,19 @@ def test_two_rank_sharded_decode_equals_single(tmp_path):
     for r in range(2):
         res = torch.load(tmp_path / f"r{r}.pt")
         assert res["ok"] and res["n"] == 9
+        assert res["emb_ok"] and res["recall"] == res["recall_single"]
+
+
+def test_shard_indices_balanced_and_complete():
+    from vag_nmt_b200.translate import shard_indices
+    lengths = [5, 9, 3, 9, 7, 1, 4, 8, 2, 6, 5]
+    for world in (1, 2, 3, 4, 8):
+        for balance in (True, False):
+            parts = [shard_indices(lengths, world, r, balance) for r in range(world)]
+            assert sorted(i for p in parts for i in p) == list(range(len(lengths)))      # a partition of the corpus
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+        loads = [sum(lengths[i] for i in shard_indices(lengths, world, r)) for r in range(world)]
+        assert max(loads) - min(loads) <= max(lengths)                                   # round-robin over the sorted corpus
 
 
 def _grad_worker(rank, world, port, out_dir):

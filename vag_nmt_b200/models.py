@@ -36,11 +36,6 @@ def _nll_weight(criterion, device) -> Optional[torch.Tensor]:
     return None if w is None else w.detach().to(device=device, dtype=torch.float32).contiguous()
 
 
-def _no_dropout_in_training(model) -> None:
-    """Kept for callers of older versions: training-mode dropout is implemented (see _dropout_mask)."""
-    return None
-
-
 def _dropout_mask(model, name: str, p: float, shape, device) -> Optional[torch.Tensor]:
     """Mask of nn.Dropout(p) in training mode: 0 with probability p, else 1/(1-p).  Drawn with torch's CUDA generator;
     tests inject fixed masks through ``model._dropout_masks[name]`` to compare against a reference run."""
@@ -277,7 +272,6 @@ class NMT_AttentionImagine_Seq2Seq_Beam_V11(_Seq2SeqBase):
     def _forward_train(self, src_var, src_lengths, tgt_var, im_var, teacher_force_ratio, criterion_mt, criterion_vse):
         """Same values as the inference-mode forward, recorded for autograd (hand-written backward kernels)."""
         from .autograd import DecoderInitFn, LossMixFn, VsePoolFn
-        _no_dropout_in_training(self)
         dev = self._device()
         ctx, mask = self._encode_train(src_var, src_lengths)
         vse = self.vse_imagine
@@ -381,7 +375,6 @@ class NMT_Seq2Seq_Beam_V2(_Seq2SeqBase):
         self.tgt_l = tgt_var.size()[1]
         if self._wants_grad():
             from .autograd import DecoderInitFn, LossMixFn
-            _no_dropout_in_training(self)
             ctx, mask = self._encode_train(src_var, src_lengths)
             h0 = DecoderInitFn.apply(None, ctx, mask, 0.0, self.decoderini.weight, self.decoderini.bias)
             tgt = tgt_var.to(device=dev, dtype=torch.int64).contiguous()

@@ -96,7 +96,7 @@ def save_checkpoint(path: str, model: torch.nn.Module, optimizer=None, scheduler
 
 
 def load_checkpoint(path: str, model: torch.nn.Module, optimizer=None, scheduler: Optional[ReduceLROnPlateau] = None) -> Dict:
-    blob = torch.load(path, map_location="cpu", weights_only=False)
+    blob = torch.load(path, map_location="cpu", weights_only=True)   # tensors, dicts, floats, ints only
     model.load_state_dict(blob["model"])
     if optimizer is not None and "optimizer" in blob:
         o = blob["optimizer"]

@@ -100,3 +100,23 @@ def pad_and_sort(sents: List[List[int]], im: Optional[torch.Tensor] = None):
         src[r, :len(sents[i])] = torch.tensor(sents[i])
     im_s = im[order] if im is not None else None
     return src, [int(x) for x in lens[order]], im_s, order.tolist()
+
+
+def dropout_masks(seed: int, B: int, Ts: int, Tt: int, src_emb: int, hidden: int, tgt_emb: int, p_emb: float, p_ctx: float,
+                  p_out: float) -> dict:
+    """Pre-drawn training-mode dropout masks (entries 0 or 1/(1-p)) in the layouts the drop-in injects through
+    ``model._dropout_masks``: "emb" [Ts·B, E] time-major (Encoder.py:51-52), "ctx" [B, Ts, 2H] (Encoder.py:62-63),
+    "out" [Tt·B, E] (NMT_Decoder.py:140-141).  CPU generator ⇒ the same bytes in the build container and on the GPU box."""
+    gen = torch.Generator().manual_seed(seed)
+
+    def draw(shape, p):
+        return torch.empty(shape).bernoulli_(1.0 - p, generator=gen) / (1.0 - p)
+
+    out = {}
+    if p_emb > 0:
+        out["emb"] = draw((Ts * B, src_emb), p_emb)
+    if p_ctx > 0:
+        out["ctx"] = draw((B, Ts, 2 * hidden), p_ctx)
+    if p_out > 0:
+        out["out"] = draw((Tt * B, tgt_emb), p_out)
+    return out

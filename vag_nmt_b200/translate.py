@@ -45,19 +45,101 @@ def decode_corpus(decode_fn: Callable, sents: Sequence[List[int]], im: Optional[
     return out  # type: ignore[return-value]
 
 
+def shard_indices(lengths: Sequence[int], world_size: int, rank: int, balance: bool = True) -> List[int]:
+    """Corpus positions `rank` works on.  balance=True (default): sort the corpus by length (descending, stable) and deal it
+    round-robin, so every rank gets the same mix of long and short sentences ("sort globally by length
+    then deal round-robin") — a contiguous split leaves the rank holding the longest sentences as the straggler.
+    balance=False: the contiguous ``shard_range`` slice."""
+    n = len(lengths)
+    if not balance:
+        lo, hi = shard_range(n, world_size, rank)
+        return list(range(lo, hi))
+    if world_size < 1 or not (0 <= rank < world_size):
+        raise ValueError("bad world_size / rank")
+    order = sorted(range(n), key=lambda i: -int(lengths[i]))     # sorted() is stable: equal lengths keep corpus order
+    return order[rank::world_size]
+
+
 def decode_corpus_sharded(decode_fn: Callable, sents: Sequence[List[int]], im: Optional[torch.Tensor], beam_size: int,
-                          max_length: int, batch_size: Optional[int] = None, group=None) -> List[List[int]]:
-    """Every rank decodes its ``shard_range`` slice; the full list (corpus order) is returned on every rank.
-    The only communication is one ``all_gather_object`` of the token lists after decoding."""
+                          max_length: int, batch_size: Optional[int] = None, group=None, balance: bool = True) -> List[List[int]]:
+    """Every rank decodes its ``shard_indices`` share; the full list (corpus order) is returned on every rank.
+    The only communication is one ``all_gather_object`` of (positions, token lists) after decoding."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()):
         return decode_corpus(decode_fn, sents, im, beam_size, max_length, batch_size)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    lo, hi = shard_range(len(sents), world, rank)
-    mine = decode_corpus(decode_fn, sents[lo:hi], im[lo:hi] if im is not None else None, beam_size, max_length, batch_size)
-    parts: List[Optional[List[List[int]]]] = [None] * world
-    dist.all_gather_object(parts, mine, group=group)
-    merged: List[List[int]] = []
-    for p in parts:
-        merged.extend(p)  # type: ignore[arg-type]
-    return merged
+    idx = shard_indices([len(s) for s in sents], world, rank, balance)
+    mine = decode_corpus(decode_fn, [sents[i] for i in idx], im[idx] if im is not None else None, beam_size, max_length, batch_size)
+    parts: List[Optional[tuple]] = [None] * world
+    dist.all_gather_object(parts, (idx, mine), group=group)
+    merged: List[Optional[List[int]]] = [None] * len(sents)
+    for pidx, ptoks in parts:  # type: ignore[misc]
+        for i, t in zip(pidx, ptoks):
+            merged[i] = t
+    return merged  # type: ignore[return-value]
+
+
+# ------------------------------------------------------------------ retrieval evaluation (SURVEY.md section 8e row 2)
+def embed_corpus(embed_fn: Callable, sents: Sequence[List[int]], im: torch.Tensor, batch_size: Optional[int] = None):
+    """Shared-space embeddings of a corpus in CORPUS order → (lim [n, S], ltxt [n, S]).
+
+    embed_fn(src [B, W], lengths, im [B, I]) → (im_emb [B, S], txt_emb [B, S]), i.e. ``model.embed_sent_im_test``.  Mirrors the
+    evaluation loop of nmt_multimodal_beam_DE.py:551-564: batches are length-sorted for the encoder and their rows scattered
+    back to the corpus positions (``lim[index_reorder] = test_im_vecs``)."""
+    n = len(sents)
+    lim = ltxt = None
+    step = n if not batch_size else batch_size
+    for lo in range(0, n, max(step, 1)):
+        chunk = sents[lo:lo + step]
+        src, lens, im_sorted, order = pad_and_sort(chunk, im[lo:lo + step])
+        e_im, e_txt = embed_fn(src, lens, im_sorted)
+        if lim is None:
+            lim = torch.empty(n, e_im.shape[1], dtype=e_im.dtype, device=e_im.device)
+            ltxt = torch.empty_like(lim)
+        pos = torch.as_tensor([lo + c for c in order], device=e_im.device)
+        lim[pos] = e_im
+        ltxt[pos] = e_txt
+    return lim, ltxt
+
+
+def embed_corpus_sharded(embed_fn: Callable, sents: Sequence[List[int]], im: torch.Tensor, batch_size: Optional[int] = None,
+                         group=None, balance: bool = True):
+    """Every rank embeds its ``shard_indices`` share; two ``all_gather_into_tensor`` calls of the (equal-size, padded)
+    [ceil(n/G), S] blocks put the full ``lim`` / ``ltxt`` [n, S] — corpus order — on every rank (2 MB at n = 1000)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return embed_corpus(embed_fn, sents, im, batch_size)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n = len(sents)
+    lengths = [len(s) for s in sents]
+    idx = shard_indices(lengths, world, rank, balance)
+    e_im, e_txt = embed_corpus(embed_fn, [sents[i] for i in idx], im[idx], batch_size)
+    per = -(-n // world)                                  # every rank contributes `per` rows; short shards are zero-padded
+    S = e_im.shape[1]
+
+    def gathered(local):
+        block = torch.zeros(per, S, dtype=local.dtype, device=local.device)
+        block[:local.shape[0]] = local
+        out = torch.empty(world * per, S, dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, block, group=group)
+        return out
+
+    g_im, g_txt = gathered(e_im), gathered(e_txt)
+    lim = torch.empty(n, S, dtype=e_im.dtype, device=e_im.device)
+    ltxt = torch.empty_like(lim)
+    for r in range(world):                               # every rank can recompute every rank's positions: no index exchange
+        ridx = shard_indices(lengths, world, r, balance)
+        pos = torch.as_tensor(ridx, device=lim.device)
+        lim[pos] = g_im[r * per:r * per + len(ridx)]
+        ltxt[pos] = g_txt[r * per:r * per + len(ridx)]
+    return lim, ltxt
+
+
+def retrieval_eval_sharded(embed_fn: Callable, sents: Sequence[List[int]], im: torch.Tensor, batch_size: Optional[int] = None,
+                           group=None, rank_fn: Optional[Callable] = None):
+    """Sharded embedding + REPLICATED recall computation → (r1, r5, r10, medr), identical on every rank and to the
+    single-process evaluation (nmt_multimodal_beam_DE.py:551-566 → im_retrieval_eval.t2i)."""
+    lim, ltxt = embed_corpus_sharded(embed_fn, sents, im, batch_size, group)
+    if rank_fn is None:
+        from .retrieval import t2i as rank_fn
+    return rank_fn(lim, ltxt)
