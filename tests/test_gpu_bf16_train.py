@@ -4,7 +4,7 @@ gradient and a 20-step loss trajectory against the oracle with bf16-rounded cont
 The comparison run rounds at the same points as the B200 path: the two operands of every nn.Linear / GRU-matrix contraction,
 forward (y = r(x)·r(W)ᵀ) and backward (dx = r(dy)·r(W), dW = r(dy)ᵀ·r(x)), accumulate in FP32; state, soft-max, attention,
 losses and Adam stay FP32 (oracle/vag_oracle.py:_RoundedLinearFn; reference semantics train.py:36-51, V11:82-168).
-Gradients are compared norm-wise per tensor, ‖g − g_ref‖₂ / ‖g_ref‖₂; the tolerance 1e-2 is a handful of bf16 ulps (2⁻⁸) of a
+Gradients are compared norm-wise per tensor, ‖g − g_ref‖₂ / ‖g_ref‖₂; the tolerance 6e-3 (measured worst 3.4e-3; the bf16 mode itself moves the gradients by 8e-3) is about one bf16 ulp (2⁻⁸) of a
 single operand: the GPU rounds values that differ from the oracle's in their last FP32 bits, so individual bf16 roundings flip.
 """
 import pytest
@@ -13,7 +13,7 @@ import torch
 from conftest import build_mm, cpu_params
 
 pytestmark = pytest.mark.gpu
-GRAD_TOL = 1e-2
+GRAD_TOL = 6e-3
 
 
 @pytest.fixture()
@@ -117,7 +117,11 @@ def test_bf16_twenty_step_loss_trajectory(bf16_oracle):
     rel = [abs(a - b) / abs(b) for a, b in zip(got_losses, ref_losses)]
     print("bf16 20-step trajectory: first/last loss", got_losses[0], got_losses[-1], "ref", ref_losses[0], ref_losses[-1], "max rel", max(rel))
     assert ref_losses[-1] < ref_losses[0]                    # the run actually optimises
-    assert max(rel) < 2e-3, list(zip(got_losses, ref_losses))
-    # and the parameters after 20 steps agree norm-wise
+    assert max(rel) < 1e-3, list(zip(got_losses, ref_losses))      # measured 1.8e-4
+    # and the parameters after 20 steps agree norm-wise.  Adam moves every element by up to lr = 4e-4 per step whatever the
+    # gradient's magnitude, so an element whose tiny gradient differs in the last bf16 bit can end 20·lr apart: bias vectors
+    # (initialised at ~1/sqrt(fan_in) ≈ 0.02) bound the norm-wise bar at ~1e-2, the matrices sit far below it
+    worst = max((_norm_err(prm, leaves[name]), name) for name, prm in model.named_parameters())
+    print("bf16 20-step parameters: worst ‖p − p_ref‖/‖p_ref‖", worst)
     for name, prm in model.named_parameters():
-        assert _norm_err(prm, leaves[name]) < 2e-3, name
+        assert _norm_err(prm, leaves[name]) < (1e-2 if "bias" in name else 2e-3), name

@@ -89,7 +89,7 @@ def test_fr_training_losses_and_gradients_with_injected_dropout(fr, precision):
     assert float(((got - ref["losses"]).abs() / ref["losses"].abs()).max()) < loss_tol, (got, ref["losses"])
     with model.precision_scope():
         out[0].backward()
-    tol = 2e-3 if precision == "fp32" else 3e-2       # bf16 here is against the UNROUNDED fp64 reference: the mode's own error
+    tol = 2e-4 if precision == "fp32" else 2e-2       # bf16 here is against the UNROUNDED fp64 reference: the mode's own error
     names = [n for n, _ in model.named_parameters()]
     assert sorted(names) == sorted(ref["grads"].keys())
     worst = 0.0
