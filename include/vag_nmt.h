@@ -11,8 +11,10 @@
  * Conventions
  *   - every pointer is a DEVICE pointer unless its name ends in _host;
  *   - row-major, strides (ld*) in ELEMENTS; weights keep PyTorch's [out, in] layout;
- *   - no allocation, no host synchronisation and no global state inside a call:
- *     scratch is caller-owned (…_workspace_bytes() says how much);
+ *   - no allocation and no global state inside a call: scratch is caller-owned (…_workspace_bytes() says how much), and the
+ *     arithmetic mode travels WITH the call (the `precision` field of the weight structs, the VAG_LIN_BF16 flag or a
+ *     `precision` argument) — there is no library-wide or thread-wide mode switch;
+ *   - no host synchronisation, with one opt-in exception: vag_beam_decode_f32's `host_progress` early stop;
  *   - every call enqueues on `stream` (a cudaStream_t) and returns a vag_status;
  *   - on failure vag_last_error() (thread-local) describes the reason.
  */
@@ -36,6 +38,14 @@ typedef enum {
     VAG_ERR_UNSUPPORTED = -4  /* shape outside what the kernels implement */
 } vag_status;
 
+/* Arithmetic of the contractions of one call.
+ *   VAG_PREC_FP32  FP32-exact (default): every operand is split into FP16 hi/lo planes, three tcgen05 products, FP32-level
+ *                  accuracy — the token-exact mode.  (VAG_GEMM=tf32x3 in the environment selects a TF32 hi/lo split instead:
+ *                  any FP32 range at half the rate; A/B runs only.)
+ *   VAG_PREC_BF16  north_star's bf16 mode: operands rounded to bfloat16, ONE product, FP32 accumulation; the small-shape FFMA
+ *                  kernels round their operands the same way.  State, soft-max, attention scores, losses and Adam stay FP32. */
+typedef enum { VAG_PREC_FP32 = 0, VAG_PREC_BF16 = 1 } vag_precision;
+
 const char* vag_last_error(void);
 int vag_abi_version(void);
 /* 1 when the current device is sm_100 (B200); kernels are compiled for sm_100a only. */
@@ -53,24 +63,26 @@ enum {
     VAG_LIN_TANH = 1,       /* y = tanh(...) */
     VAG_LIN_ACCUMULATE = 2, /* add the previous content of y before the activation */
     VAG_LIN_FORCE_SIMT = 4, /* (internal) never take the tensor-core path */
-    VAG_LIN_FORCE_TC = 8    /* (internal) fail with VAG_ERR_UNSUPPORTED instead of falling to SIMT FP32 */
+    VAG_LIN_FORCE_TC = 8,   /* (internal) fail with VAG_ERR_UNSUPPORTED instead of falling to SIMT FP32 */
+    VAG_LIN_BF16 = 16       /* this contraction runs in VAG_PREC_BF16 (default VAG_PREC_FP32) */
 };
 /* x [rows, in_dim] (ld ldx), w [out_dim, in_dim] (ld ldw), bias [out_dim] or NULL,
  * y [rows, out_dim] (ld ldy).  Any shape / alignment; FP32 FFMA kernel. */
 int vag_linear_f32(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw,
                    const float* bias, int rows, int in_dim, int out_dim, int flags, vag_stream_t stream);
 
-/* The same contraction on the 5th-generation tensor cores (tcgen05.mma kind::tf32, TMEM accumulators, TMA-fed):
- * every operand is split into hi = rn_tf32(v) and lo = v - hi and hi·hi + hi·lo + lo·hi is accumulated in FP32
- * (3xTF32), which keeps FP32-level accuracy so that decoded tokens stay exact.  Needs rows >= 64, out_dim >= 64,
- * in_dim >= 32 and a multiple of 4, 16-byte aligned x / w (else VAG_ERR_UNSUPPORTED).  The composites below take
- * this path automatically for eligible shapes; VAG_GEMM=simt in the environment forces the FFMA kernel. */
+/* The same contraction on the 5th-generation tensor cores (tcgen05.mma kind::f16, TMEM accumulators, TMA-fed):
+ * every operand is split into hi = rn_f16(v) and lo = rn_f16((v - hi)·2^11) and hi·hi + (hi·lo + lo·hi)·2^-11 is
+ * accumulated in FP32 (two TMEM accumulators), which keeps FP32-level accuracy so that decoded tokens stay exact; with
+ * VAG_LIN_BF16 one bfloat16 product instead.  Needs rows >= 64, out_dim >= 64, in_dim >= 32 and a multiple of 8,
+ * 16-byte aligned x / w (else VAG_ERR_UNSUPPORTED).  The composites below take this path automatically for eligible
+ * shapes; VAG_GEMM=simt in the environment forces the FFMA kernel. */
 /* Vocabulary projection of the beam loop WITHOUT an output matrix (replaces NMT_Decoder.py:143 `out` + log_softmax + the
  * topk of V11:300 for the tensor-core path): summ [ceil(out_dim / 32), rows] x 4 floats =
  *   (best logit of the 32-column slice, sum of exp(logit - best), second-best logit, best column | second column << 16)
  * in canonical order (value descending, column ascending; 0xFFFF = none).  Needs rows > 128 and a 16-bit gemm mode. */
 int vag_tc_gemm_top2_f32(float* summ, const void* x_hi, const void* x_lo, int64_t ldx, const void* w_hi, const void* w_lo,
-                         int64_t ldw, const float* bias, int rows, int in_dim, int out_dim, vag_stream_t stream);
+                         int64_t ldw, const float* bias, int rows, int in_dim, int out_dim, int precision, vag_stream_t stream);
 size_t vag_linear_tc_workspace_bytes(int rows, int in_dim, int out_dim);
 int vag_linear_tc_f32(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw,
                       const float* bias, int rows, int in_dim, int out_dim, int flags, void* workspace,
@@ -78,21 +90,16 @@ int vag_linear_tc_f32(float* y, int64_t ldy, const float* x, int64_t ldx, const 
 
 /* The two halves of vag_linear_tc_f32 for callers that keep operands split across calls (weights are split once
  * per decode; an activation read by several contractions is split once per step).
- *   vag_tc_elem_bytes(): bytes per element of a split plane (2: FP16 split, the default; 4: VAG_GEMM=tf32x3).
- *   vag_tc_split_f32 : x [rows, K] → hi / lo planes [rows, ld_out] (ld_out in elements, multiple of 8; planes 128-B aligned).
- *   vag_tc_gemm_f32  : y = act(x·Wᵀ + bias [+ y]) from split operands (tcgen05.mma, TMEM accumulators, TMA loads). */
-int vag_tc_elem_bytes(void);
-/* Arithmetic of every contraction issued by the calling thread from now on:
- *   1  FP32-exact (default): FP16 hi/lo split, 3 tensor-core products, FP32-level accuracy (token-exact decoding)
- *   0  FP32-exact, TF32 hi/lo split (any FP32 range, half the rate)
- *   2  bf16 mode: operands rounded to bfloat16, ONE product, FP32 accumulation (north_star "bf16 mode"; the FFMA
- *      fallback rounds its operands the same way)
- *  -1  back to the default / the VAG_GEMM environment variable (tf32x3 | bf16 | simt). */
-int vag_set_gemm_mode(int mode);
-int vag_get_gemm_mode(void);
+ *   vag_tc_elem_bytes(precision): bytes per element of a split plane (2; 4 under VAG_GEMM=tf32x3 in VAG_PREC_FP32).
+ *   vag_tc_split_f32 : x [rows, K] → hi / lo planes [rows, ld_out] (ld_out in elements, multiple of 8; planes 128-B aligned;
+ *                      VAG_PREC_BF16 writes the hi plane only).
+ *   vag_tc_gemm_f32  : y = act(x·Wᵀ + bias [+ y]) from split operands (tcgen05.mma, TMEM accumulators, TMA loads);
+ *                      VAG_LIN_BF16 in flags when the planes were made with VAG_PREC_BF16. */
+int vag_tc_elem_bytes(int precision);
 /* Tools only: device buffer of 32 int64 that the CTA-pair contraction fills with per-role cycle counters (NULL = off). */
 int vag_tc_set_debug(void* device_i64x32);
-int vag_tc_split_f32(const float* x, int64_t ldx, int rows, int K, void* hi, void* lo, int64_t ld_out, vag_stream_t stream);
+int vag_tc_split_f32(const float* x, int64_t ldx, int rows, int K, void* hi, void* lo, int64_t ld_out, int precision,
+                     vag_stream_t stream);
 int vag_tc_gemm_f32(float* y, int64_t ldy, const void* x_hi, const void* x_lo, int64_t ldx, const void* w_hi,
                     const void* w_lo, int64_t ldw, const float* bias, int rows, int in_dim, int out_dim, int flags,
                     vag_stream_t stream);
@@ -138,6 +145,7 @@ int vag_log_softmax_f32(float* logp, const float* logits, int rows, int V, vag_s
  * ---------------------------------------------------------------------------------- */
 typedef struct {
     int E, H;                 /* embedding size, hidden size per direction */
+    int precision;            /* vag_precision of every contraction issued on behalf of these weights */
     int64_t vocab;            /* rows of emb */
     const float* emb;         /* encoder.embedding.weight [vocab, E] */
     const float* w_ih[2];     /* encoder.gru.weight_ih_l0{,_reverse} [3H, E] */
@@ -161,6 +169,7 @@ typedef struct {
     int I, C, S;              /* image feature size, context size (2H), shared embedding size */
     int method;               /* VAG_ATTN_DOT or VAG_ATTN_MLP (imagine_attn 'dot' / 'mlp') */
     int activation;           /* activation_vse */
+    int precision;            /* vag_precision */
     const float* im_w;        /* vse_imagine.im_embedding.weight [S, I] */
     const float* im_b;        /* [S] */
     const float* txt_w;       /* vse_imagine.text_embedding.weight [S, C] */
@@ -195,6 +204,7 @@ int vag_recall_ranks_f32(const float* queries, const float* gallery, int n, int 
  * ---------------------------------------------------------------------------------- */
 typedef struct {
     int E, H, C;              /* embedding, hidden, context (2·encoder H) */
+    int precision;            /* vag_precision */
     int64_t V;                /* target vocabulary */
     const float* emb;         /* decoder.embedding.weight [V, E] */
     const float* gru1_w_ih;   /* [3H, E] */
@@ -219,7 +229,17 @@ typedef struct {
     const float* out_b;       /* [V] */
     const float* ini_w;       /* decoderini.weight [H, C]  (V11:75) */
     const float* ini_b;       /* [H] */
+    const void* prepared;     /* optional: buffer filled by vag_decoder_prepare_f32 for exactly these weights and this */
+    size_t prepared_bytes;    /* precision (NULL / 0: the decode calls derive the same data into their workspace) */
 } vag_decoder_weights;
+
+/* Decode-call invariants of a weight set, computed ONCE instead of once per vag_beam_decode_f32 call: the tensor-core operand
+ * planes of every decoder matrix, the K-concatenated read-out matrix [W1 | W3 | W2] with its summed bias, and the per-token
+ * table  Emb·W_ihᵀ + b_ih  of gru_1 ([V, 3H]: its input pre-activations depend on the token only).  7.4 GFLOP + 58 MB for
+ * EN→DE — negligible against a 1000-sentence call, dominant at the reference's eval batch of 16
+ * (nmt_multimodal_beam_DE.py:542-547).  The caller keeps `prepared` alive and re-prepares after the weights change. */
+size_t vag_decoder_prepared_bytes(int E, int H, int C, int64_t V);
+int vag_decoder_prepare_f32(const vag_decoder_weights* w, void* prepared, size_t prepared_bytes, vag_stream_t stream);
 
 /* Hoisted step-invariant half of the attention MLP: keys[b,t,:] = attn_e(ctx[b,t,:])
  * (the reference recomputes it on the K-times tiled context every step, NMT_Decoder.py:39-40,47). */
@@ -265,11 +285,24 @@ size_t vag_beam_decode_workspace_bytes(int B, int K, int T, int L, int E, int H,
  *   h0 [B, H]; ctx/keys [B, T, C]; mask [B, T]
  *   hyp_out int64 [B, L]   tokens of the best hypothesis (full row of the beam, EOS/pad included)
  *   hyp_len int32 [B]      number of tokens before the first EOS (what the reference returns)
- *   beam_out int64 [L, B, K], nll_out [B, K] (un-normalised), steps_out int32[1]: optional (NULL to skip) */
+ *   beam_out int64 [L, B, K], nll_out [B, K] (un-normalised), steps_out int32[1]: optional (NULL to skip)
+ * Early stop.  Once every hypothesis has ended (`done`), every kernel of the remaining steps returns at once, so a finished
+ * search costs launch latency only.  host_progress (optional): ONE int32 of pinned, device-mapped HOST memory
+ * (cudaHostAlloc; with unified addressing the same pointer is valid on the device).  The device stores
+ * (steps finished | done << 30) there after every step and the call — like the reference's per-step `fini_idxs` test,
+ * V11:265-269 — keeps at most 4 steps enqueued ahead of it and stops enqueueing when `done` appears.  NULL: all L steps are
+ * enqueued without touching the host (the form a CUDA graph can capture). */
 int vag_beam_decode_f32(const vag_decoder_weights* w, const float* h0, const float* keys, const float* ctx,
                         const float* mask, int B, int K, int T, int L, int avoid_double, int64_t* hyp_out,
-                        int32_t* hyp_len, int64_t* beam_out, float* nll_out, int32_t* steps_out, void* workspace,
-                        size_t workspace_bytes, vag_stream_t stream);
+                        int32_t* hyp_len, int64_t* beam_out, float* nll_out, int32_t* steps_out,
+                        volatile int32_t* host_progress, void* workspace, size_t workspace_bytes, vag_stream_t stream);
+
+/* The epilogue of the search alone (V11:315-337), for callers that drive the steps themselves (vag_decoder_step_f32 +
+ * vag_beam_select_f32): tok_hist int64 / par_hist int32 [L, B, K] = token and parent-beam index chosen at every step,
+ * nll [B, K], steps_run int32[1] ON THE DEVICE (rows >= steps_run count as 0; the last row is forced to <eos>, :315).
+ * → hyp_out int64 [B, L], hyp_len int32 [B], beam_out int64 [L, B, K] (optional, the back-traced `beam` of the reference). */
+int vag_beam_finalize_f32(const int64_t* tok_hist, const int32_t* par_hist, const float* nll, const int32_t* steps_run, int B,
+                          int K, int L, int64_t* hyp_out, int32_t* hyp_len, int64_t* beam_out, vag_stream_t stream);
 
 /* Greedy branch (beam_size == 1, V11:207-226): tokens_out int64 [B, L] = argmax at every step. */
 int vag_greedy_decode_f32(const vag_decoder_weights* w, const float* h0, const float* keys, const float* ctx,
@@ -302,7 +335,7 @@ int vag_translation_loss_f32(const float* loss_rows, const int64_t* tgt, int B, 
  * ---------------------------------------------------------------------------------- */
 /* C[m,n] = alpha·Σ_k A[m·sam + k·sak]·B[k·sbk + n·sbn] + beta·C[m,n]: dX = dY·W and dW = dYᵀ·X of every nn.Linear / GRU matrix. */
 int vag_gemm_f32(float* C, int64_t ldc, const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk,
-                 int64_t sbn, int M, int N, int K, float alpha, float beta, vag_stream_t stream);
+                 int64_t sbn, int M, int N, int K, float alpha, float beta, int precision, vag_stream_t stream);
 
 /* vag_gemm_f32 with a caller-owned workspace (vag_gemm_tc_workspace_bytes): contractions with M, N >= 64 run on the tcgen05
    path — operands are split into tensor-core planes inside the workspace, transposing those that are not contraction-
@@ -310,8 +343,8 @@ int vag_gemm_f32(float* C, int64_t ldc, const float* A, int64_t sam, int64_t sak
    weight / input gradients of every nn.Linear and nn.GRU on the path (layers/NMT_Decoder.py:121-143 under backward()). */
 size_t vag_gemm_tc_workspace_bytes(int M, int N, int K);
 int vag_gemm_tc_f32(float* C, int64_t ldc, const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk,
-                    int64_t sbn, int M, int N, int K, float alpha, float beta, void* workspace, size_t workspace_bytes,
-                    vag_stream_t stream);
+                    int64_t sbn, int M, int N, int K, float alpha, float beta, int precision, void* workspace,
+                    size_t workspace_bytes, vag_stream_t stream);
 /* GRU cell backward from the saved pre-activations: dgi, dgh [rows,3H] and dh_prev [rows,H] = dh·z (the caller adds dgh·W_hh). */
 int vag_gru_gates_bwd_f32(float* dgi, float* dgh, float* dh_prev, const float* dh, int64_t ld_dh, const float* gi,
                           const float* gh, const float* h_prev, int64_t ld_hp, int rows, int H, vag_stream_t stream);

@@ -38,6 +38,6 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     """sizeof of the ctypes mirrors == the C structs (pointer-sized fields, natural alignment)."""
     from vag_nmt_b200 import _cabi
-    assert ctypes.sizeof(_cabi.EncoderWeights) == 8 + 8 + 8 + 4 * 16
-    assert ctypes.sizeof(_cabi.VseWeights) == 24 + 7 * 8          # 5 ints padded to 24
-    assert ctypes.sizeof(_cabi.DecoderWeights) == 16 + 8 + 23 * 8  # 3 ints (+pad), int64 V, 23 pointers
+    assert ctypes.sizeof(_cabi.EncoderWeights) == 16 + 8 + 8 + 4 * 16     # E, H, precision (+pad), vocab, emb, 4 x 2 pointers
+    assert ctypes.sizeof(_cabi.VseWeights) == 24 + 7 * 8          # 6 ints
+    assert ctypes.sizeof(_cabi.DecoderWeights) == 16 + 8 + 23 * 8 + 16  # 4 ints, int64 V, 23 pointers, prepared + size

@@ -46,13 +46,11 @@ def test_bf16_mode_losses_logits_and_recall(bf16_oracle):
         # direct layer calls are outside the model's precision scope: select the bf16 arithmetic by hand.  The encoder
         # context (not a north_star quantity) is compared loosely: a recurrent state that rounds to a different bf16
         # neighbour on the two sides moves an element by 2^-9 of its value.
-        _cabi_lib().vag_set_gemm_mode(2)
-        try:
+        from vag_nmt_b200 import _cabi
+        with _cabi.precision_scope("bf16"):
             ctx, mask = model.encoder(batch.src, batch.src_lengths)
             # the step itself is fed the ORACLE's context so that the comparison isolates one decoder step
             logp, h = model.decoder(tok.cuda(), h0.cuda().unsqueeze(0), ctx_o.cuda(), ctx_mask=mask_o.cuda())
-        finally:
-            _cabi_lib().vag_set_gemm_mode(-1)
         assert float((ctx.cpu() - ctx_o).abs().max() / ctx_o.abs().max()) < 2e-3
         assert float((logp.cpu() - logp_ref).abs().max() / logp_ref.abs().max()) < 1e-3
         assert float((h.squeeze(0).cpu() - h_ref).abs().max() / h_ref.abs().max()) < 1e-3
@@ -62,16 +60,7 @@ def test_bf16_mode_losses_logits_and_recall(bf16_oracle):
         assert vag.t2i(e_im, e_txt)[:3] == O.t2i(o_im, o_txt)[:3]
         # the fp32 mode of the same model object is unaffected once the attribute is switched back
         model.precision = "fp32"
-        assert _lib_mode() == 1
-
-
-def _cabi_lib():
-    from vag_nmt_b200 import _cabi
-    return _cabi.lib()
-
-
-def _lib_mode():
-    return _cabi_lib().vag_get_gemm_mode()
+        assert _cabi.precision() == _cabi.PREC_FP32      # nothing leaks out of the scopes: the C ABI has no mode state at all
 
 
 def test_bf16_mode_is_actually_lower_precision_and_faster_path():
@@ -83,12 +72,9 @@ def test_bf16_mode_is_actually_lower_precision_and_faster_path():
     w = (torch.randn(1024, 512, generator=torch.Generator().manual_seed(2)) / math.sqrt(512)).cuda()
     ref = x.double() @ w.double().t()
     y32 = ops.linear_tc(x, w)
-    lib.vag_set_gemm_mode(2)
-    try:
+    with _cabi.precision_scope("bf16"):
         y16 = ops.linear_tc(x, w)
         ref16 = x.bfloat16().double() @ w.bfloat16().double().t()
-    finally:
-        lib.vag_set_gemm_mode(-1)
     e32 = float((y32.double() - ref).abs().max() / ref.abs().max())
     e16 = float((y16.double() - ref).abs().max() / ref.abs().max())
     e16_vs_rounded = float((y16.double() - ref16).abs().max() / ref16.abs().max())

@@ -22,7 +22,7 @@ ap.add_argument("--mode", type=int, default=-1)
 ap.add_argument("--check", type=int, default=1)
 a = ap.parse_args()
 lib = _cabi.lib()
-lib.vag_set_gemm_mode(a.mode)
+# the arithmetic mode travels with each call now (ops wrappers read _cabi.precision_scope)
 STEP = [(12000, 256, 1536), (12000, 512, 1536), (12000, 512, 1024), (12000, 1024, 512), (12000, 1792, 256), (12000, 256, 9391)]
 shapes = [(12000, 256, 9391)] if a.shapes == "vocab" else STEP + [(1000, 256, 9391), (384, 512, 1536), (12000, 1024, 1024)]
 tot = 0.0

@@ -6,8 +6,10 @@ operator raises.  The library is loaded lazily so that the package itself can be
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
+import threading
 from pathlib import Path
 from typing import Optional
 
@@ -21,24 +23,24 @@ c_i32p = C.c_void_p
 
 
 class EncoderWeights(C.Structure):
-    _fields_ = [("E", C.c_int), ("H", C.c_int), ("vocab", C.c_int64), ("emb", C.c_void_p),
+    _fields_ = [("E", C.c_int), ("H", C.c_int), ("precision", C.c_int), ("vocab", C.c_int64), ("emb", C.c_void_p),
                 ("w_ih", C.c_void_p * 2), ("w_hh", C.c_void_p * 2), ("b_ih", C.c_void_p * 2), ("b_hh", C.c_void_p * 2)]
 
 
 class VseWeights(C.Structure):
-    _fields_ = [("I", C.c_int), ("C", C.c_int), ("S", C.c_int), ("method", C.c_int), ("activation", C.c_int),
+    _fields_ = [("I", C.c_int), ("C", C.c_int), ("S", C.c_int), ("method", C.c_int), ("activation", C.c_int), ("precision", C.c_int),
                 ("im_w", C.c_void_p), ("im_b", C.c_void_p), ("txt_w", C.c_void_p), ("txt_b", C.c_void_p),
                 ("ctx2ctx_w", C.c_void_p), ("emb2ctx_w", C.c_void_p), ("mlp_w", C.c_void_p)]
 
 
 class DecoderWeights(C.Structure):
-    _fields_ = [("E", C.c_int), ("H", C.c_int), ("C", C.c_int), ("V", C.c_int64), ("emb", C.c_void_p),
+    _fields_ = [("E", C.c_int), ("H", C.c_int), ("C", C.c_int), ("precision", C.c_int), ("V", C.c_int64), ("emb", C.c_void_p),
                 ("gru1_w_ih", C.c_void_p), ("gru1_w_hh", C.c_void_p), ("gru1_b_ih", C.c_void_p), ("gru1_b_hh", C.c_void_p),
                 ("attn_h_w", C.c_void_p), ("attn_e_w", C.c_void_p), ("attn_v", C.c_void_p), ("c2h_w", C.c_void_p),
                 ("gru2_w_ih", C.c_void_p), ("gru2_w_hh", C.c_void_p), ("gru2_b_ih", C.c_void_p), ("gru2_b_hh", C.c_void_p),
                 ("w1_w", C.c_void_p), ("w1_b", C.c_void_p), ("w2_w", C.c_void_p), ("w2_b", C.c_void_p),
                 ("w3_w", C.c_void_p), ("w3_b", C.c_void_p), ("out_w", C.c_void_p), ("out_b", C.c_void_p),
-                ("ini_w", C.c_void_p), ("ini_b", C.c_void_p)]
+                ("ini_w", C.c_void_p), ("ini_b", C.c_void_p), ("prepared", C.c_void_p), ("prepared_bytes", C.c_size_t)]
 
 
 class DecoderSeqSaved(C.Structure):
@@ -78,13 +80,11 @@ SIGNATURES = {
     "vag_recall_ranks_f32": (I, [P, P, I, I, P, P, SZ, P]),
     "vag_attn_keys_workspace_bytes": (SZ, [I, I, I]),
     "vag_attn_keys_f32": (I, [P, P, I, I, P, P, SZ, P]),
-    "vag_tc_elem_bytes": (I, []),
-    "vag_set_gemm_mode": (I, [I]),
-    "vag_get_gemm_mode": (I, []),
+    "vag_tc_elem_bytes": (I, [I]),
     "vag_tc_set_debug": (I, [P]),
-    "vag_tc_split_f32": (I, [P, I64, I, I, P, P, I64, P]),
+    "vag_tc_split_f32": (I, [P, I64, I, I, P, P, I64, I, P]),
     "vag_tc_gemm_f32": (I, [P, I64, P, P, I64, P, P, I64, P, I, I, I, I, P]),
-    "vag_tc_gemm_top2_f32": (I, [P, P, P, I64, P, P, I64, P, I, I, I, P]),
+    "vag_tc_gemm_top2_f32": (I, [P, P, P, I64, P, P, I64, P, I, I, I, I, P]),
     "vag_linear_tc_workspace_bytes": (SZ, [I, I, I]),
     "vag_linear_tc_f32": (I, [P, I64, P, I64, P, I64, P, I, I, I, I, P, SZ, P]),
     "vag_decoder_init_workspace_bytes": (SZ, [I, I, I]),
@@ -93,14 +93,17 @@ SIGNATURES = {
     "vag_decoder_step_f32": (I, [P, P, P, P, P, P, I, I, I, P, P, I, P, P, SZ, P]),
     "vag_beam_select_f32": (I, [P, I64, P, P, P, P, I, I, I64, I, I, P]),
     "vag_beam_decode_workspace_bytes": (SZ, [I, I, I, I, I, I, I, I64]),
-    "vag_beam_decode_f32": (I, [P, P, P, P, P, I, I, I, I, I, P, P, P, P, P, P, SZ, P]),
+    "vag_beam_decode_f32": (I, [P, P, P, P, P, I, I, I, I, I, P, P, P, P, P, P, P, SZ, P]),
+    "vag_beam_finalize_f32": (I, [P, P, P, P, I, I, I, P, P, P, P]),
+    "vag_decoder_prepared_bytes": (SZ, [I, I, I, I64]),
+    "vag_decoder_prepare_f32": (I, [P, P, SZ, P]),
     "vag_greedy_decode_f32": (I, [P, P, P, P, P, I, I, I, P, P, SZ, P]),
     "vag_nll_rows_f32": (I, [P, I64, P, P, I, I64, P, P, P]),
     "vag_row_argmax_f32": (I, [P, I64, I, I64, P, P]),
     "vag_translation_loss_f32": (I, [P, P, I, I, P, F, P, P]),
-    "vag_gemm_f32": (I, [P, I64, P, I64, I64, P, I64, I64, I, I, I, F, F, P]),
+    "vag_gemm_f32": (I, [P, I64, P, I64, I64, P, I64, I64, I, I, I, F, F, I, P]),
     "vag_gemm_tc_workspace_bytes": (SZ, [I, I, I]),
-    "vag_gemm_tc_f32": (I, [P, I64, P, I64, I64, P, I64, I64, I, I, I, F, F, P, SZ, P]),
+    "vag_gemm_tc_f32": (I, [P, I64, P, I64, I64, P, I64, I64, I, I, I, F, F, I, P, SZ, P]),
     "vag_gru_gates_bwd_f32": (I, [P, P, P, P, I64, P, P, P, I64, I, I, P]),
     "vag_attention_bwd_f32": (I, [P, I64, P, P, P, P, I64, P, P, I64, P, P, P, P, I, I, I, I, P]),
     "vag_nll_bwd_f32": (I, [P, I64, P, I64, P, P, P, P, I, I64, P]),
@@ -126,6 +129,31 @@ SIGNATURES = {
 }
 
 _lib: Optional[C.CDLL] = None
+
+# ---- arithmetic mode.  The C ABI is stateless: every call carries its vag_precision (struct field, flag or argument).  What the
+# Python layer keeps is WHICH precision the wrappers in ops.py / train_ops.py put into the calls they make on this thread.
+PREC_FP32, PREC_BF16 = 0, 1
+LIN_BF16 = 16
+_PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, PREC_FP32: PREC_FP32, PREC_BF16: PREC_BF16}
+_tls = threading.local()
+
+
+def precision() -> int:
+    """The vag_precision the wrappers pass right now on this thread (default VAG_PREC_FP32)."""
+    return getattr(_tls, "precision", PREC_FP32)
+
+
+@contextlib.contextmanager
+def precision_scope(p):
+    """``with precision_scope("bf16"):`` — calls made inside carry VAG_PREC_BF16.  Python-side and thread-local: autograd's worker
+    thread does not inherit it, which is why the backward Functions re-enter the scope their forward ran in (autograd.py)."""
+    new = _PRECISIONS[p]
+    old = precision()
+    _tls.precision = new
+    try:
+        yield
+    finally:
+        _tls.precision = old
 
 
 class VagError(RuntimeError):

@@ -26,27 +26,19 @@ SOS_token = 2
 
 
 def _save_mode(fctx):
-    """Remember the arithmetic mode (fp32-exact split / bf16) the forward ran in.  loss.backward() executes the backward
-    Functions on autograd's device worker thread, where the caller's thread-local vag_set_gemm_mode() is not visible."""
-    fctx.gemm_mode = ops._cabi.lib().vag_get_gemm_mode()
+    """Remember the vag_precision the forward ran in.  loss.backward() executes the backward Functions on autograd's device
+    worker thread, which does not inherit the caller's (Python-side, thread-local) precision scope."""
+    fctx.precision = ops._cabi.precision()
 
 
 def _in_forward_mode(fn):
-    """Run a backward staticmethod under the mode its forward saved."""
+    """Run a backward staticmethod under the precision its forward saved."""
     import functools
 
     @functools.wraps(fn)
     def wrapper(fctx, *grads):
-        lib = ops._cabi.lib()
-        mode = getattr(fctx, "gemm_mode", None)
-        prev = lib.vag_get_gemm_mode()
-        if mode is None or mode == prev:
+        with ops._cabi.precision_scope(getattr(fctx, "precision", ops._cabi.PREC_FP32)):
             return fn(fctx, *grads)
-        lib.vag_set_gemm_mode(mode)
-        try:
-            return fn(fctx, *grads)
-        finally:
-            lib.vag_set_gemm_mode(prev)
     return wrapper
 
 
@@ -85,6 +77,7 @@ class EncoderFn(torch.autograd.Function):
         dev = emb.device
         w = EncoderWeights()
         w.E, w.H, w.vocab, w.emb = E, H, emb.shape[0], ops._p(emb.detach())
+        w.precision = ops._cabi.precision()
         for d in range(2):
             w.w_ih[d], w.w_hh[d] = ops._p(gru[4 * d].detach()), ops._p(gru[4 * d + 1].detach())
             w.b_ih[d], w.b_hh[d] = ops._p(gru[4 * d + 2].detach()), ops._p(gru[4 * d + 3].detach())
@@ -120,6 +113,7 @@ class EncoderFn(torch.autograd.Function):
         dev = emb.device
         w = EncoderWeights()
         w.E, w.H, w.vocab, w.emb = E, H, emb.shape[0], ops._p(emb.detach())
+        w.precision = ops._cabi.precision()
         for d in range(2):
             w.w_ih[d], w.w_hh[d] = ops._p(gru[4 * d].detach()), ops._p(gru[4 * d + 1].detach())
             w.b_ih[d], w.b_hh[d] = ops._p(gru[4 * d + 2].detach()), ops._p(gru[4 * d + 3].detach())
@@ -277,6 +271,7 @@ class DecoderSeqFn(torch.autograd.Function):
             tok_in[1:].copy_(tgt_t[:-1])
         w = DecoderWeights()
         w.E, w.H, w.C, w.V = E, H, Cd, V
+        w.precision = ops._cabi.precision()
         for name, p in zip(_PARAM_FIELDS, params):
             setattr(w, name, ops._p(p.detach()))
         ldl = (V + 3) // 4 * 4
@@ -314,6 +309,7 @@ class DecoderSeqFn(torch.autograd.Function):
         dev = h0.device
         w = DecoderWeights()
         w.E, w.H, w.C, w.V = E, H, Cd, V
+        w.precision = ops._cabi.precision()
         for name, p in zip(_PARAM_FIELDS, params):
             setattr(w, name, ops._p(p.detach()))
         saved = DecoderSeqSaved()

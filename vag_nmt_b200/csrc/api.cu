@@ -38,7 +38,7 @@ size_t linear_tc_scratch_bytes(int64_t rows, int64_t K, int64_t N);
 bool linear_tc_eligible(const float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw, int rows, int K, int N);
 bool tc_call_supported(const float* y, int64_t ldy, int flags);
 
-// VAG_GEMM=simt forces the FP32 FFMA path everywhere (A/B runs); default = tcgen05 3xTF32 where eligible.
+// VAG_GEMM=simt forces the FP32 FFMA path everywhere (A/B runs); default = the tcgen05 split-precision kernels where eligible.
 bool tc_enabled();
 bool tc_enabled() {
     const char* e = getenv("VAG_GEMM");
@@ -83,8 +83,9 @@ extern "C" int vag_linear_f32(float* y, int64_t ldy, const float* x, int64_t ldx
     VAG_REQUIRE(y && x && w, "vag_linear_f32: null pointer");
     VAG_REQUIRE(rows >= 0 && in_dim > 0 && out_dim > 0, "vag_linear_f32: bad shape rows=%d in=%d out=%d", rows, in_dim, out_dim);
     VAG_REQUIRE(ldx >= in_dim && ldw >= in_dim && ldy >= out_dim, "vag_linear_f32: leading dimension smaller than the row");
-    return linear_dispatch(y, ldy, x, ldx, w, ldw, bias, rows, in_dim, out_dim, flags | VAG_LIN_FORCE_SIMT, (cudaStream_t)stream,
-                           nullptr, 0);
+    ModeScope ms((flags & VAG_LIN_BF16) ? VAG_PREC_BF16 : VAG_PREC_FP32);
+    return linear_dispatch(y, ldy, x, ldx, w, ldw, bias, rows, in_dim, out_dim, (flags & ~VAG_LIN_BF16) | VAG_LIN_FORCE_SIMT,
+                           (cudaStream_t)stream, nullptr, 0);
 }
 
 namespace vag {
@@ -101,26 +102,19 @@ bool pdl_enabled() {
     return v == 1;
 }
 }
-extern "C" int vag_tc_elem_bytes(void) { return tc_elem_bytes(); }
-
-namespace vag {
-void set_gemm_mode(int m);
-int gemm_mode();
+extern "C" int vag_tc_elem_bytes(int precision) {
+    ModeScope ms(precision);
+    return tc_elem_bytes();
 }
-extern "C" int vag_set_gemm_mode(int mode) {
-    VAG_REQUIRE(mode >= -1 && mode <= 2, "vag_set_gemm_mode: mode must be -1 (environment default), 0 (tf32x3), 1 (f16x3) or 2 (bf16)");
-    set_gemm_mode(mode);
-    return VAG_OK;
-}
-extern "C" int vag_get_gemm_mode(void) { return gemm_mode(); }
 namespace vag { void set_tc_debug(long long* p); }
 extern "C" int vag_tc_set_debug(void* device_i64x32) {
     set_tc_debug(reinterpret_cast<long long*>(device_i64x32));
     return VAG_OK;
 }
 
-extern "C" int vag_tc_split_f32(const float* x, int64_t ldx, int rows, int K, void* hi, void* lo, int64_t ld_out,
+extern "C" int vag_tc_split_f32(const float* x, int64_t ldx, int rows, int K, void* hi, void* lo, int64_t ld_out, int precision,
                                 vag_stream_t stream) {
+    ModeScope ms(precision);
     VAG_REQUIRE(x && hi && lo, "vag_tc_split_f32: null pointer");
     VAG_REQUIRE(rows > 0 && K > 0 && K % 8 == 0 && ldx % 4 == 0 && ld_out >= K && ld_out % 8 == 0,
                 "vag_tc_split_f32: K and ld_out must be multiples of 8, ldx a multiple of 4");
@@ -134,7 +128,9 @@ extern "C" int vag_tc_gemm_f32(float* y, int64_t ldy, const void* x_hi, const vo
     VAG_REQUIRE(y && x_hi && x_lo && w_hi && w_lo, "vag_tc_gemm_f32: null pointer");
     VAG_REQUIRE(rows > 0 && in_dim >= 32 && in_dim % 8 == 0 && out_dim > 0 && ldx % 8 == 0 && ldw % 8 == 0 && ldy >= out_dim,
                 "vag_tc_gemm_f32: bad shape");
-    return tc_gemm(y, ldy, x_hi, x_lo, ldx, w_hi, w_lo, ldw, bias, rows, in_dim, out_dim, flags, (cudaStream_t)stream, nullptr, nullptr);
+    ModeScope ms((flags & VAG_LIN_BF16) ? VAG_PREC_BF16 : VAG_PREC_FP32);
+    return tc_gemm(y, ldy, x_hi, x_lo, ldx, w_hi, w_lo, ldw, bias, rows, in_dim, out_dim, flags & ~VAG_LIN_BF16, (cudaStream_t)stream,
+                   nullptr, nullptr);
 }
 
 namespace vag {
@@ -143,7 +139,8 @@ int tc_gemm_top2(float4* summ, const void* xh, const void* xl, int64_t ldxs, con
 }
 extern "C" int vag_tc_gemm_top2_f32(float* summ, const void* x_hi, const void* x_lo, int64_t ldx, const void* w_hi,
                                     const void* w_lo, int64_t ldw, const float* bias, int rows, int in_dim, int out_dim,
-                                    vag_stream_t stream) {
+                                    int precision, vag_stream_t stream) {
+    ModeScope ms(precision);
     VAG_REQUIRE(summ && x_hi && x_lo && w_hi && w_lo, "vag_tc_gemm_top2_f32: null pointer");
     VAG_REQUIRE(rows > 128 && in_dim >= 32 && in_dim % 8 == 0 && out_dim > 0 && out_dim < 65535 && ldx % 8 == 0 && ldw % 8 == 0,
                 "vag_tc_gemm_top2_f32: bad shape (rows > 128, in %% 8 == 0, out < 65535)");
@@ -158,6 +155,8 @@ extern "C" size_t vag_linear_tc_workspace_bytes(int rows, int in_dim, int out_di
 extern "C" int vag_linear_tc_f32(float* y, int64_t ldy, const float* x, int64_t ldx, const float* w, int64_t ldw,
                                  const float* bias, int rows, int in_dim, int out_dim, int flags, void* workspace,
                                  size_t workspace_bytes, vag_stream_t stream) {
+    ModeScope ms((flags & VAG_LIN_BF16) ? VAG_PREC_BF16 : VAG_PREC_FP32);
+    flags &= ~VAG_LIN_BF16;
     VAG_REQUIRE(y && x && w && workspace, "vag_linear_tc_f32: null pointer");
     VAG_REQUIRE(rows > 0 && in_dim > 0 && out_dim > 0, "vag_linear_tc_f32: bad shape rows=%d in=%d out=%d", rows, in_dim, out_dim);
     VAG_REQUIRE(ldx >= in_dim && ldw >= in_dim && ldy >= out_dim, "vag_linear_tc_f32: leading dimension smaller than the row");

@@ -215,8 +215,9 @@ __global__ void __launch_bounds__(256, RCAP <= 12 ? 3 : 2)
 attention_tuned_kernel(float* __restrict__ c_out, int64_t ld_c, float* __restrict__ alpha_out, const float* __restrict__ q,
                        int64_t ld_q, const float* __restrict__ keys, const float* __restrict__ ctx,
                        const float* __restrict__ v, const float* __restrict__ mask, int rows, int rows_per_sent, int T, int C,
-                       SplitDst sd) {
+                       SplitDst sd, const int* __restrict__ done) {
     pdl_trigger();   // the contraction that follows may start its prologue while this kernel drains
+    if (done && *reinterpret_cast<const volatile int*>(done)) return;   // beam search over (block-uniform)
     extern __shared__ __align__(16) float smem[];
     const int b = blockIdx.x;
     const int r_base = blockIdx.y * RCAP;
@@ -392,7 +393,7 @@ attention_tuned_kernel(float* __restrict__ c_out, int64_t ld_c, float* __restric
 template <int MODE, int RCAP, bool FULLC>
 static int launch_attention_tuned(float* c_out, int64_t ld_c, float* alpha, const float* q, int64_t ld_q, const float* keys,
                                   const float* ctx, const float* v, const float* mask, int rows, int rows_per_sent, int T, int C,
-                                  cudaStream_t st, SplitDst sd = SplitDst()) {
+                                  cudaStream_t st, SplitDst sd = SplitDst(), const int* done = nullptr) {
     const size_t smem = ((size_t)RCAP * C + C + (size_t)RCAP * T + 4 + (size_t)T * ((RCAP + 3) / 4 * 4)) * sizeof(float);
     if (smem > 227 * 1024) {
         set_error("vag_attention_f32: C=%d T=%d needs %zu B of shared memory", C, T, smem);
@@ -405,7 +406,7 @@ static int launch_attention_tuned(float* c_out, int64_t ld_c, float* alpha, cons
     }
     dim3 grid(rows / rows_per_sent, ceil_div(rows_per_sent, RCAP));
     attention_tuned_kernel<MODE, RCAP, FULLC><<<grid, 256, smem, st>>>(c_out, ld_c, alpha, q, ld_q, keys, ctx, v, mask, rows,
-                                                                 rows_per_sent, T, C, sd);
+                                                                 rows_per_sent, T, C, sd, done);
     VAG_LAUNCH_CHECK();
     return VAG_OK;
 }
@@ -413,12 +414,12 @@ static int launch_attention_tuned(float* c_out, int64_t ld_c, float* alpha, cons
 template <int MODE>
 static int dispatch_attention_tuned(float* c_out, int64_t ld_c, float* alpha, const float* q, int64_t ld_q, const float* keys,
                                     const float* ctx, const float* v, const float* mask, int rows, int rows_per_sent, int T,
-                                    int C, cudaStream_t st, SplitDst sd = SplitDst()) {
+                                    int C, cudaStream_t st, SplitDst sd = SplitDst(), const int* done = nullptr) {
 #define VAG_ATT(RC)                                                                                                        \
     do {                                                                                                                   \
         if (C % 1024 == 0)                                                                                                 \
-            return launch_attention_tuned<MODE, RC, true>(c_out, ld_c, alpha, q, ld_q, keys, ctx, v, mask, rows, rows_per_sent, T, C, st, sd); \
-        return launch_attention_tuned<MODE, RC, false>(c_out, ld_c, alpha, q, ld_q, keys, ctx, v, mask, rows, rows_per_sent, T, C, st, sd); \
+            return launch_attention_tuned<MODE, RC, true>(c_out, ld_c, alpha, q, ld_q, keys, ctx, v, mask, rows, rows_per_sent, T, C, st, sd, done); \
+        return launch_attention_tuned<MODE, RC, false>(c_out, ld_c, alpha, q, ld_q, keys, ctx, v, mask, rows, rows_per_sent, T, C, st, sd, done); \
     } while (0)
     if (rows_per_sent == 1) VAG_ATT(1);
     if (rows_per_sent <= 4) VAG_ATT(4);
@@ -431,8 +432,8 @@ static int dispatch_attention_tuned(float* c_out, int64_t ld_c, float* alpha, co
 // Decoder-step attention of the fused step: the context leaves the kernel only as tensor-core operand planes.
 // Requirements (the caller's workspace guarantees them): C % 4 == 0, 16-byte aligned q / keys / ctx, rows_per_sent <= 16.
 int attention_mlp_split(SplitDst sd, const float* q, int64_t ld_q, const float* keys, const float* ctx, const float* v,
-                        const float* mask, int rows, int rows_per_sent, int T, int C, cudaStream_t st) {
-    return dispatch_attention_tuned<VAG_ATTN_MLP>(nullptr, 0, nullptr, q, ld_q, keys, ctx, v, mask, rows, rows_per_sent, T, C, st, sd);
+                        const float* mask, int rows, int rows_per_sent, int T, int C, cudaStream_t st, const int* done) {
+    return dispatch_attention_tuned<VAG_ATTN_MLP>(nullptr, 0, nullptr, q, ld_q, keys, ctx, v, mask, rows, rows_per_sent, T, C, st, sd, done);
 }
 
 }  // namespace vag

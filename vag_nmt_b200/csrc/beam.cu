@@ -837,7 +837,8 @@ __global__ void __launch_bounds__(128)
 beam_advance_fused_kernel(float* __restrict__ h_next, const float* __restrict__ h_cur, const int32_t* __restrict__ parents,
                           const int64_t* __restrict__ tokens, int B, int K, int Kin, int H, int step, int* __restrict__ done,
                           const int* __restrict__ fin_counter, int* __restrict__ steps_run, SplitDst h_sd, SplitDst e_sd,
-                          const uint16_t* __restrict__ t_hi, const uint16_t* __restrict__ t_lo, int64_t ld_t, int E, int64_t V) {
+                          const uint16_t* __restrict__ t_hi, const uint16_t* __restrict__ t_lo, int64_t ld_t, int E, int64_t V,
+                          volatile int32_t* host_progress, int nonce) {
     pdl_trigger();   // the contraction that follows may start its prologue while this kernel drains
     if (*reinterpret_cast<volatile int*>(done)) return;
     constexpr int RPB = 4;   // rows per block: 12000 one-row blocks were launch-overhead bound
@@ -861,11 +862,23 @@ beam_advance_fused_kernel(float* __restrict__ h_next, const float* __restrict__ 
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         steps_run[0] = step + 1;
-        if (*fin_counter == B * K) *done = 1;
+        const int fin = *fin_counter == B * K;
+        if (fin) *done = 1;
+        if (host_progress) {   // mapped host memory: the host throttles / stops its launch loop on this word (vag_beam_decode_f32)
+            *host_progress = (nonce << 16) | (fin << 15) | (step + 1);
+            __threadfence_system();
+        }
     }
 }
-__global__ void beam_done_kernel(int* __restrict__ done, const int* __restrict__ fin_counter, int total) {
-    if (*fin_counter == total) *done = 1;
+__global__ void beam_done_kernel(int* __restrict__ done, const int* __restrict__ fin_counter, int total, const int* __restrict__ steps_run,
+                                 volatile int32_t* host_progress, int nonce) {
+    const int already = *done;
+    const int fin = already || *fin_counter == total;
+    if (fin) *done = 1;
+    if (host_progress) {
+        *host_progress = (nonce << 16) | (fin << 15) | (*steps_run & 0x7FFF);
+        __threadfence_system();
+    }
 }
 
 // Finalisation (V11:315-337): backtrace every final hypothesis through the parent pointers, force EOS in the
@@ -1047,19 +1060,20 @@ int beam_select_top2(const float4* summ, int slice_w, SplitDst t, const uint16_t
 }
 
 int beam_advance(float* h_next, const float* h_cur, const int32_t* parents, int B, int K, int Kin, int H, int step,
-                 int* done, int* fin_counter, int* steps_run, cudaStream_t st) {
+                 int* done, int* fin_counter, int* steps_run, cudaStream_t st, volatile int32_t* host_progress, int nonce) {
     beam_advance_kernel<<<B * K, 128, 0, st>>>(h_next, h_cur, parents, B, K, Kin, H, step, done, fin_counter, steps_run);
     VAG_LAUNCH_CHECK();
-    beam_done_kernel<<<1, 1, 0, st>>>(done, fin_counter, B * K);
+    beam_done_kernel<<<1, 1, 0, st>>>(done, fin_counter, B * K, steps_run, host_progress, nonce);
     VAG_LAUNCH_CHECK();
     return VAG_OK;
 }
 
 int beam_advance_fused(float* h_next, const float* h_cur, const int32_t* parents, const int64_t* tokens, int B, int K, int Kin,
                        int H, int step, int* done, int* fin_counter, int* steps_run, SplitDst h_sd, SplitDst e_sd,
-                       const uint16_t* t_hi, const uint16_t* t_lo, int64_t ld_t, int E, int64_t V, cudaStream_t st) {
+                       const uint16_t* t_hi, const uint16_t* t_lo, int64_t ld_t, int E, int64_t V, cudaStream_t st,
+                       volatile int32_t* host_progress, int nonce) {
     beam_advance_fused_kernel<<<(B * K + 3) / 4, 128, 0, st>>>(h_next, h_cur, parents, tokens, B, K, Kin, H, step, done, fin_counter, steps_run,
-                                                     h_sd, e_sd, t_hi, t_lo, ld_t, E, V);
+                                                     h_sd, e_sd, t_hi, t_lo, ld_t, E, V, host_progress, nonce);
     VAG_LAUNCH_CHECK();
     return VAG_OK;
 }

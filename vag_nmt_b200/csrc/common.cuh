@@ -78,6 +78,19 @@ struct ArenaSizer {
 
 int num_sms();
 
+// Arithmetic mode of the contractions issued on behalf of the C-ABI call that is executing on this thread:
+//   0 = TF32 hi/lo split (VAG_GEMM=tf32x3), 1 = FP16 hi/lo split (default of VAG_PREC_FP32), 2 = bf16 (VAG_PREC_BF16).
+// Every extern "C" entry point that contracts opens a ModeScope from ITS OWN precision argument / struct field / flag and
+// closes it on return: the mode is per call, the thread-local below is only how it reaches the kernels' launchers.
+int gemm_mode();
+struct ModeScope {
+    int prev;
+    explicit ModeScope(int precision);
+    ~ModeScope();
+    ModeScope(const ModeScope&) = delete;
+    ModeScope& operator=(const ModeScope&) = delete;
+};
+
 // Programmatic dependent launch: a kernel launched with launch_pdl() may become resident while its predecessor on the stream
 // is still draining; it must execute pdl_wait() before it touches global memory.  pdl_trigger() in the predecessor lets the
 // dependent launch as soon as every CTA of the predecessor has started.  Both are no-ops for ordinary launches.

@@ -18,7 +18,7 @@ int beam_select_summary(const float4* summ, int tile_w, const float* logits, int
                         int64_t* tokens_out, int32_t* parents_out, int B, int K, int64_t V, int step, int avoid_double,
                         const int* done, int* fin_counter, cudaStream_t st);
 int beam_advance(float* h_next, const float* h_cur, const int32_t* parents, int B, int K, int Kin, int H, int step,
-                 int* done, int* fin_counter, int* steps_run, cudaStream_t st);
+                 int* done, int* fin_counter, int* steps_run, cudaStream_t st, volatile int32_t* host_progress = nullptr, int nonce = 0);
 int beam_finalize(const int64_t* tok_hist, const int32_t* par_hist, const float* nll, const int* steps_run, int B, int K,
                   int L, int64_t* hyp_out, int32_t* hyp_len, int64_t* beam_out, cudaStream_t st);
 int row_argmax(const float* logits, int64_t ld, int rows, int64_t V, int64_t* out, int64_t out_stride, int64_t* next_in,
@@ -78,6 +78,118 @@ struct ArenaAdapter {
     template <typename T> void* take(size_t n) { return a.take<T>(n); }
 };
 
+// Operand planes of one weight matrix [rows, K] (16-bit modes: 2 bytes per element, lo unused in bf16 mode).
+struct Planes {
+    void *hi = nullptr, *lo = nullptr;
+    int64_t ld = 0;
+};
+// Decode-call invariants of a weight set (vag_decoder_prepare_f32): every decoder matrix as operand planes, the K-concatenated
+// read-out matrix [W1 | W3 | W2] with its summed bias, the per-token gru_1 table.  The layout is a pure function of
+// (E, H, C, V): the same code sizes the buffer, fills it and finds the pieces again in a later call.
+struct Prepared {
+    Planes g1i, g1h, ah, ae, c2h, g2i, g2h, ro, out, emb, ini;
+    float* b_ro = nullptr;
+    float* g1 = nullptr;   // [V, 3H] table  Emb·W_ihᵀ + b_ih  of gru_1: its input pre-activations depend on the token only
+};
+template <typename A>
+static void prepared_layout(A& a, int E, int H, int C, int64_t V, Prepared* p) {
+    auto planes = [&](Planes* d, int64_t rows, int64_t K) {
+        void* hi = a.template take<uint16_t>((size_t)rows * K);
+        void* lo = a.template take<uint16_t>((size_t)rows * K);
+        if (d) { d->hi = hi; d->lo = lo; d->ld = K; }
+    };
+    planes(p ? &p->g1i : nullptr, 3 * H, E);
+    planes(p ? &p->g1h : nullptr, 3 * H, H);
+    planes(p ? &p->ah : nullptr, C, H);
+    planes(p ? &p->ae : nullptr, C, C);
+    planes(p ? &p->c2h : nullptr, H, C);
+    planes(p ? &p->g2i : nullptr, 3 * H, H);
+    planes(p ? &p->g2h : nullptr, 3 * H, H);
+    planes(p ? &p->ro : nullptr, E, H + E + C);
+    planes(p ? &p->out : nullptr, V, E);
+    planes(p ? &p->emb : nullptr, V, E);
+    planes(p ? &p->ini : nullptr, H, C);
+    float* b_ro = (float*)a.template take<float>((size_t)E);
+    float* g1 = (float*)a.template take<float>((size_t)V * 3 * H);
+    if (p) { p->b_ro = b_ro; p->g1 = g1; }
+}
+static bool prepared_supported(const vag_decoder_weights* w, int mode) {
+    const int E = w->E, H = w->H, C = w->C;
+    if (!tc_enabled() || (mode != 1 && mode != 2) || (E % 8) || (H % 8) || (C % 8) || w->V < 64) return false;
+    const float* ws_[] = {w->gru1_w_ih, w->gru1_w_hh, w->attn_h_w, w->attn_e_w, w->c2h_w, w->gru2_w_ih, w->gru2_w_hh, w->w1_w, w->w2_w, w->w3_w,
+                          w->out_w, w->emb};
+    for (const float* q : ws_)
+        if (!q || ((uintptr_t)q & 15)) return false;
+    return true;
+}
+// Fill a prepared region (mode = the current gemm mode, 1 or 2).
+static int prepared_fill(const vag_decoder_weights* w, Prepared& pr, cudaStream_t st) {
+    const int E = w->E, H = w->H, C = w->C, Kt = H + E + C;
+    const int V = (int)w->V;
+    auto split = [&](const Planes& d, const float* src, int rows, int K, int64_t col_off = 0, int64_t ld = 0) {
+        return tc_split(src, K, rows, K, d.hi, d.lo, ld ? ld : d.ld, col_off, st);
+    };
+    VAG_TRY(split(pr.g1i, w->gru1_w_ih, 3 * H, E));
+    VAG_TRY(split(pr.g1h, w->gru1_w_hh, 3 * H, H));
+    VAG_TRY(split(pr.ah, w->attn_h_w, C, H));
+    VAG_TRY(split(pr.ae, w->attn_e_w, C, C));
+    VAG_TRY(split(pr.c2h, w->c2h_w, H, C));
+    VAG_TRY(split(pr.g2i, w->gru2_w_ih, 3 * H, H));
+    VAG_TRY(split(pr.g2h, w->gru2_w_hh, 3 * H, H));
+    VAG_TRY(split(pr.out, w->out_w, V, E));
+    if (w->emb != w->out_w) VAG_TRY(split(pr.emb, w->emb, V, E));
+    if (w->ini_w && !((uintptr_t)w->ini_w & 15)) VAG_TRY(split(pr.ini, w->ini_w, H, C));
+    VAG_TRY(split(pr.ro, w->w1_w, E, H, 0, Kt));        // read-out [W1 | W3 | W2] laid side by side along K (NMT_Decoder.py:137)
+    VAG_TRY(split(pr.ro, w->w3_w, E, E, H, Kt));
+    VAG_TRY(split(pr.ro, w->w2_w, E, C, H + E, Kt));
+    VAG_TRY(bias_sum3(pr.b_ro, w->w1_b, w->w3_b, w->w2_b, E, st));
+    // gru_1's input contraction once for EVERY token instead of once per step for every row: the same kernel on the same operand
+    // rows, so each table row is bit-identical to what the per-step contraction produces
+    if (V > 128) {
+        const Planes& em = (w->emb == w->out_w) ? pr.out : pr.emb;
+        VAG_TRY(tc_gemm(pr.g1, 3 * H, em.hi, em.lo, em.ld, pr.g1i.hi, pr.g1i.lo, pr.g1i.ld, w->gru1_b_ih, V, E, 3 * H, 0, st, nullptr, nullptr));
+    }
+    return VAG_OK;
+}
+// The prepared data of this call: the caller's buffer (w->prepared) when it is large enough, else `fallback` (a region of the
+// call's own workspace) filled now.  *have = false when the tensor-core step cannot run in this mode / for these shapes.
+static int prepared_get(const vag_decoder_weights* w, void* fallback, size_t fallback_bytes, cudaStream_t st, Prepared* pr, bool* have) {
+    *have = false;
+    const int mode = gemm_mode();
+    if (!prepared_supported(w, mode)) return VAG_OK;
+    SizerAdapter sz;
+    prepared_layout(sz, w->E, w->H, w->C, w->V, nullptr);
+    const size_t need = sz.s.total();
+    if (w->prepared && w->prepared_bytes >= need) {
+        ArenaAdapter ar(const_cast<void*>(w->prepared), w->prepared_bytes);
+        prepared_layout(ar, w->E, w->H, w->C, w->V, pr);
+        *have = !ar.a.overflow;
+        return VAG_OK;
+    }
+    if (!fallback || fallback_bytes < need) return VAG_OK;
+    ArenaAdapter ar(fallback, fallback_bytes);
+    prepared_layout(ar, w->E, w->H, w->C, w->V, pr);
+    if (ar.a.overflow) return VAG_OK;
+    VAG_TRY(prepared_fill(w, *pr, st));
+    *have = true;
+    return VAG_OK;
+}
+// Make the prepared planes visible to the generic contraction context (its weight cache is keyed by the fp32 pointer).
+static void prepared_register(GemmCtx& gemm, const vag_decoder_weights* w, const Prepared& pr) {
+    const int E = w->E, H = w->H, C = w->C;
+    gemm.preset(w->gru1_w_ih, 3 * H, E, pr.g1i.hi, pr.g1i.lo);
+    gemm.preset(w->gru1_w_hh, 3 * H, H, pr.g1h.hi, pr.g1h.lo);
+    gemm.preset(w->attn_h_w, C, H, pr.ah.hi, pr.ah.lo);
+    gemm.preset(w->attn_e_w, C, C, pr.ae.hi, pr.ae.lo);
+    gemm.preset(w->c2h_w, H, C, pr.c2h.hi, pr.c2h.lo);
+    gemm.preset(w->gru2_w_ih, 3 * H, H, pr.g2i.hi, pr.g2i.lo);
+    gemm.preset(w->gru2_w_hh, 3 * H, H, pr.g2h.hi, pr.g2h.lo);
+    gemm.preset(w->out_w, (int)w->V, E, pr.out.hi, pr.out.lo);
+    if (w->ini_w && !((uintptr_t)w->ini_w & 15)) gemm.preset(w->ini_w, H, C, pr.ini.hi, pr.ini.lo);
+    gemm.preset3(w->w1_w, E, H + E + C, pr.ro.hi, pr.ro.lo, pr.b_ro);
+}
+
+
 }  // namespace vag
 
 using namespace vag;
@@ -91,6 +203,7 @@ extern "C" size_t vag_encoder_workspace_bytes(int B, int T, int E, int H) {
 extern "C" int vag_encoder_fwd_f32(const vag_encoder_weights* w, const int64_t* src, const int32_t* lengths_host, int B, int T,
                                    float* ctx_out, float* mask_out, void* workspace, size_t workspace_bytes,
                                    vag_stream_t stream) {
+    ModeScope ms(w ? w->precision : VAG_PREC_FP32);
     VAG_REQUIRE(w && src && lengths_host && ctx_out && mask_out, "vag_encoder_fwd_f32: null pointer");
     VAG_REQUIRE(B > 0 && T > 0 && w->E > 0 && w->H > 0, "vag_encoder_fwd_f32: bad shape");
     for (int b = 0; b < B; ++b) {
@@ -160,6 +273,7 @@ extern "C" size_t vag_vse_workspace_bytes(int B, int T, int I, int C, int S) {
 extern "C" int vag_vse_pool_fwd_f32(const vag_vse_weights* w, const float* im, const float* ctx, const float* mask, int B, int T,
                                     float* im_emb, float* txt_emb, float* ctx_vec, float* beta, void* workspace,
                                     size_t workspace_bytes, vag_stream_t stream) {
+    ModeScope ms(w ? w->precision : VAG_PREC_FP32);
     VAG_REQUIRE(w && im && ctx && im_emb && txt_emb && ctx_vec, "vag_vse_pool_fwd_f32: null pointer");
     VAG_REQUIRE(B > 0 && T > 0, "vag_vse_pool_fwd_f32: bad shape");
     VAG_REQUIRE(w->method == VAG_ATTN_DOT || (w->method == VAG_ATTN_MLP && w->mlp_w), "vag_vse_pool_fwd_f32: bad attention method");
@@ -194,6 +308,7 @@ extern "C" size_t vag_attn_keys_workspace_bytes(int B, int T, int C) {
 
 extern "C" int vag_attn_keys_f32(const vag_decoder_weights* w, const float* ctx, int B, int T, float* keys, void* workspace,
                                  size_t workspace_bytes, vag_stream_t stream) {
+    ModeScope ms(w ? w->precision : VAG_PREC_FP32);
     VAG_REQUIRE(w && ctx && keys && B > 0 && T > 0, "vag_attn_keys_f32: bad argument");
     const size_t wb = GemmCtx::split_bytes(w->C, w->C) + 4096;
     Arena ar(workspace, workspace_bytes);
@@ -201,6 +316,10 @@ extern "C" int vag_attn_keys_f32(const vag_decoder_weights* w, const float* ctx,
     const size_t ab = ar.overflow || workspace_bytes < ar.off + 512 ? 0 : workspace_bytes - align_up(ar.off, 256) - 256;
     void* areg = ab ? ar.take<char>(ab) : nullptr;
     GemmCtx gemm((cudaStream_t)stream, ar.overflow ? nullptr : wr, wb, ar.overflow ? nullptr : areg, ab);
+    Prepared pr;
+    bool have_pr = false;
+    VAG_TRY(prepared_get(w, nullptr, 0, (cudaStream_t)stream, &pr, &have_pr));
+    if (have_pr) gemm.preset(w->attn_e_w, w->C, w->C, pr.ae.hi, pr.ae.lo);
     return gemm.linear(keys, w->C, ctx, w->C, w->attn_e_w, w->C, nullptr, B * T, w->C, w->C, 0);
 }
 
@@ -211,6 +330,7 @@ extern "C" size_t vag_decoder_init_workspace_bytes(int B, int C, int H) {
 extern "C" int vag_decoder_init_f32(const vag_decoder_weights* w, const float* ctx_vec, const float* ctx, const float* mask,
                                     float split, int B, int T, float* h0, void* workspace, size_t workspace_bytes,
                                     vag_stream_t stream) {
+    ModeScope ms(w ? w->precision : VAG_PREC_FP32);
     VAG_REQUIRE(w && ctx && mask && h0 && B > 0 && T > 0, "vag_decoder_init_f32: bad argument");
     VAG_REQUIRE(w->ini_w && w->ini_b, "vag_decoder_init_f32: decoderini weights missing");
     Arena ar(workspace, workspace_bytes);
@@ -224,6 +344,10 @@ extern "C" int vag_decoder_init_f32(const vag_decoder_weights* w, const float* c
     void* wr = ar.take<char>(wb);   // optional: without them the FP32 FFMA kernel runs
     void* areg = ar.take<char>(ab);
     GemmCtx gemm((cudaStream_t)stream, ar.overflow ? nullptr : wr, wb, ar.overflow ? nullptr : areg, ab);
+    Prepared pr;
+    bool have_pr = false;
+    VAG_TRY(prepared_get(w, nullptr, 0, (cudaStream_t)stream, &pr, &have_pr));
+    if (have_pr && !((uintptr_t)w->ini_w & 15)) gemm.preset(w->ini_w, w->H, w->C, pr.ini.hi, pr.ini.lo);
     return gemm.linear(h0, w->H, z, w->C, w->ini_w, w->C, w->ini_b, B, w->C, w->H, VAG_LIN_TANH);
 }
 
@@ -301,59 +425,38 @@ static int decoder_step_core(GemmCtx& gemm, const vag_decoder_weights* w, const 
 // pitch H+E+C; the embedding and the context are column windows of it (TMA takes any 16-byte aligned pitch).
 int gru_gates_split(float* h_out, int64_t ld_ho, const float* gi, int64_t ld_gi, const float* gh, int64_t ld_gh,
                     const float* h_prev, int64_t ld_hp, int rows, int H, SplitDst sd, cudaStream_t st,
-                    const int64_t* gi_rows = nullptr, int64_t gi_n_rows = 0);
+                    const int64_t* gi_rows = nullptr, int64_t gi_n_rows = 0, const int* done = nullptr);
 int embed_split_rows(SplitDst dst, const uint16_t* t_hi, const uint16_t* t_lo, int64_t ld_t, int E, const int64_t* tokens, int rows,
                      int64_t V, cudaStream_t st);
 int attention_mlp_split(SplitDst sd, const float* q, int64_t ld_q, const float* keys, const float* ctx, const float* v,
-                        const float* mask, int rows, int rows_per_sent, int T, int C, cudaStream_t st);
+                        const float* mask, int rows, int rows_per_sent, int T, int C, cudaStream_t st, const int* done = nullptr);
 int beam_select_top2(const float4* summ, int tile_w, SplitDst t, const uint16_t* w_hi, const uint16_t* w_lo, int64_t ld_w,
                      const float* bias, int E, const int64_t* prev_tokens, float* nll, int64_t* tokens_out, int32_t* parents_out,
                      int B, int K, int64_t V, int step, int avoid_double, const int* done, int* fin_counter, cudaStream_t st);
 int beam_advance_fused(float* h_next, const float* h_cur, const int32_t* parents, const int64_t* tokens, int B, int K, int Kin,
                        int H, int step, int* done, int* fin_counter, int* steps_run, SplitDst h_sd, SplitDst e_sd,
-                       const uint16_t* t_hi, const uint16_t* t_lo, int64_t ld_t, int E, int64_t V, cudaStream_t st);
+                       const uint16_t* t_hi, const uint16_t* t_lo, int64_t ld_t, int E, int64_t V, cudaStream_t st,
+                       volatile int32_t* host_progress = nullptr, int nonce = 0);
 
 struct FusedStep {
     bool ok = false;
     SplitDst hprev, h1, x2, t, cat;                 // cat = [h2 | e | c], pitch H + E + C
-    GemmCtx::Ent *w_g1i = nullptr, *w_g1h = nullptr, *w_ah = nullptr, *w_c2h = nullptr, *w_g2i = nullptr, *w_g2h = nullptr,
-                 *w_ro = nullptr, *w_out = nullptr, *w_emb = nullptr;
-    float* b_ro = nullptr;
-    float* g1 = nullptr;   // [V, 3H] table  Emb·W_ihᵀ + b_ih  of gru_1: its input pre-activations depend on the token only
+    Prepared pr;
+    const Planes* w_emb = nullptr;                  // tied: the gather reads the projection's planes
+    float* g1 = nullptr;
+    const int* done = nullptr;                      // device flag: every hypothesis has ended, later steps return at once
     SplitDst cat_e(int H) const { SplitDst d = cat; d.hi += H; if (d.lo) d.lo += H; return d; }
     SplitDst cat_c(int H, int E) const { SplitDst d = cat; d.hi += H + E; if (d.lo) d.lo += H + E; return d; }
 };
 
-static int fused_setup(GemmCtx& gemm, const vag_decoder_weights* w, const StepWs& ws, int n_rows, int rows_per_sent, float* g1,
-                       FusedStep* f) {
-    const int E = w->E, H = w->H, C = w->C, Kt = H + E + C;
-    const int64_t V = w->V;
+static int fused_setup(const vag_decoder_weights* w, const StepWs& ws, int n_rows, int rows_per_sent, const Prepared& pr, FusedStep* f) {
+    const int E = w->E, H = w->H, Kt = H + E + w->C;
     const int mode = gemm_mode();
     f->ok = false;
-    if (!gemm.tc || (mode != 1 && mode != 2) || n_rows <= 128 || rows_per_sent > 16 || V < 64) return VAG_OK;
-    if ((E % 8) || (H % 8) || (C % 8)) return VAG_OK;
-    const float* ws_[] = {w->gru1_w_ih, w->gru1_w_hh, w->attn_h_w, w->c2h_w, w->gru2_w_ih, w->gru2_w_hh, w->w1_w, w->w2_w, w->w3_w,
-                          w->out_w, w->emb};
-    for (const float* p : ws_)
-        if (!p || ((uintptr_t)p & 15)) return VAG_OK;
-    VAG_TRY(gemm.weight(&f->w_g1i, w->gru1_w_ih, E, 3 * H, E));
-    VAG_TRY(gemm.weight(&f->w_g1h, w->gru1_w_hh, H, 3 * H, H));
-    VAG_TRY(gemm.weight(&f->w_ah, w->attn_h_w, H, C, H));
-    VAG_TRY(gemm.weight(&f->w_c2h, w->c2h_w, C, H, C));
-    VAG_TRY(gemm.weight(&f->w_g2i, w->gru2_w_ih, H, 3 * H, H));
-    VAG_TRY(gemm.weight(&f->w_g2h, w->gru2_w_hh, H, 3 * H, H));
-    VAG_TRY(gemm.weight(&f->w_out, w->out_w, E, (int)V, E));
-    {
-        const float* const wts[3] = {w->w1_w, w->w3_w, w->w2_w};
-        const float* const bs[3] = {w->w1_b, w->w3_b, w->w2_b};
-        const int64_t lds[3] = {H, E, C};
-        const int Ks[3] = {H, E, C};
-        VAG_TRY(gemm.weight3(&f->w_ro, &f->b_ro, wts, lds, Ks, bs, E));
-    }
-    if (w->emb == w->out_w) f->w_emb = f->w_out;   // tied: the gather reads the projection's planes
-    else VAG_TRY(gemm.weight(&f->w_emb, w->emb, E, (int)V, E));
-    if (!f->w_g1i || !f->w_g1h || !f->w_ah || !f->w_c2h || !f->w_g2i || !f->w_g2h || !f->w_out || !f->w_ro || !f->b_ro || !f->w_emb)
-        return VAG_OK;
+    if (n_rows <= 128 || rows_per_sent > 16) return VAG_OK;
+    f->pr = pr;
+    f->w_emb = (w->emb == w->out_w) ? &f->pr.out : &f->pr.emb;
+    f->g1 = w->V > 128 ? pr.g1 : nullptr;
     // activation planes, carved once from the step's activation region (the plain path's per-step splits are not used)
     Arena ar(ws.areg, ws.abytes);
     auto planes = [&](SplitDst* d, int K) {
@@ -368,13 +471,6 @@ static int fused_setup(GemmCtx& gemm, const vag_decoder_weights* w, const StepWs
     planes(&f->t, E);
     planes(&f->cat, Kt);
     if (ar.overflow) return VAG_OK;
-    // gru_1's input contraction once per call for EVERY token instead of once per step for every row: the same kernel on
-    // the same operand rows, so each table row is bit-identical to what the per-step contraction produced
-    if (g1 && V > 128) {
-        VAG_TRY(tc_gemm(g1, 3 * H, f->w_emb->hi, f->w_emb->lo, f->w_emb->ld, f->w_g1i->hi, f->w_g1i->lo, f->w_g1i->ld, w->gru1_b_ih,
-                        (int)V, E, 3 * H, 0, gemm.st, nullptr, nullptr));
-        f->g1 = g1;
-    }
     f->ok = true;
     return VAG_OK;
 }
@@ -386,26 +482,28 @@ static int decoder_step_fused(const FusedStep& f, const vag_decoder_weights* w, 
     const int E = w->E, H = w->H, C = w->C, Kt = H + E + C;
     const int64_t V = w->V;
     const SplitDst ce = f.cat_e(H), cc = f.cat_c(H, E);
-    auto gemm = [&](float* y, int64_t ldy, const SplitDst& x, const GemmCtx::Ent* we, const float* bias, int K, int N, float4* sm,
+    const Prepared& pr = f.pr;
+    TcDoneScope ds(f.done);   // the contractions launched below return at once when *done is set
+    auto gemm = [&](float* y, int64_t ldy, const SplitDst& x, const Planes& we, const float* bias, int K, int N, float4* sm,
                     int* tw) {
-        return tc_gemm(y, ldy, x.hi, x.lo, x.ld, we->hi, we->lo, we->ld, bias, rows, K, N, 0, st, sm, tw);
+        return tc_gemm(y, ldy, x.hi, x.lo, x.ld, we.hi, we.lo, we.ld, bias, rows, K, N, 0, st, sm, tw);
     };
-    if (!f.g1) VAG_TRY(gemm(ws.gi, 3 * H, ce, f.w_g1i, w->gru1_b_ih, E, 3 * H, nullptr, nullptr));           // NMT_Decoder.py:121
-    VAG_TRY(gemm(ws.gh, 3 * H, f.hprev, f.w_g1h, w->gru1_b_hh, H, 3 * H, nullptr, nullptr));
-    if (f.g1) VAG_TRY(gru_gates_split(ws.h1, H, f.g1, 3 * H, ws.gh, 3 * H, h_prev, H, rows, H, f.h1, st, tokens, V));
-    else VAG_TRY(gru_gates_split(ws.h1, H, ws.gi, 3 * H, ws.gh, 3 * H, h_prev, H, rows, H, f.h1, st));
-    VAG_TRY(gemm(ws.q, C, f.h1, f.w_ah, nullptr, H, C, nullptr, nullptr));                                    // :47
-    VAG_TRY(attention_mlp_split(cc, ws.q, C, keys, ctx, w->attn_v, mask, rows, rows_per_sent, T, C, st));     // :124-126
-    VAG_TRY(tc_gemm_split_out(f.x2, cc.hi, cc.lo, Kt, f.w_c2h->hi, f.w_c2h->lo, f.w_c2h->ld, nullptr, rows, C, H, 0, st));   // :127
-    VAG_TRY(gemm(ws.gi, 3 * H, f.x2, f.w_g2i, w->gru2_b_ih, H, 3 * H, nullptr, nullptr));                     // :129
-    VAG_TRY(gemm(ws.gh, 3 * H, f.h1, f.w_g2h, w->gru2_b_hh, H, 3 * H, nullptr, nullptr));
-    VAG_TRY(gru_gates_split(h_out, H, ws.gi, 3 * H, ws.gh, 3 * H, ws.h1, H, rows, H, f.cat, st));
-    VAG_TRY(tc_gemm_split_out(f.t, f.cat.hi, f.cat.lo, Kt, f.w_ro->hi, f.w_ro->lo, f.w_ro->ld, f.b_ro, rows, Kt, E, VAG_LIN_TANH, st));  // :137
+    if (!f.g1) VAG_TRY(gemm(ws.gi, 3 * H, ce, pr.g1i, w->gru1_b_ih, E, 3 * H, nullptr, nullptr));           // NMT_Decoder.py:121
+    VAG_TRY(gemm(ws.gh, 3 * H, f.hprev, pr.g1h, w->gru1_b_hh, H, 3 * H, nullptr, nullptr));
+    if (f.g1) VAG_TRY(gru_gates_split(ws.h1, H, f.g1, 3 * H, ws.gh, 3 * H, h_prev, H, rows, H, f.h1, st, tokens, V, f.done));
+    else VAG_TRY(gru_gates_split(ws.h1, H, ws.gi, 3 * H, ws.gh, 3 * H, h_prev, H, rows, H, f.h1, st, nullptr, 0, f.done));
+    VAG_TRY(gemm(ws.q, C, f.h1, pr.ah, nullptr, H, C, nullptr, nullptr));                                    // :47
+    VAG_TRY(attention_mlp_split(cc, ws.q, C, keys, ctx, w->attn_v, mask, rows, rows_per_sent, T, C, st, f.done));     // :124-126
+    VAG_TRY(tc_gemm_split_out(f.x2, cc.hi, cc.lo, Kt, pr.c2h.hi, pr.c2h.lo, pr.c2h.ld, nullptr, rows, C, H, 0, st));   // :127
+    VAG_TRY(gemm(ws.gi, 3 * H, f.x2, pr.g2i, w->gru2_b_ih, H, 3 * H, nullptr, nullptr));                     // :129
+    VAG_TRY(gemm(ws.gh, 3 * H, f.h1, pr.g2h, w->gru2_b_hh, H, 3 * H, nullptr, nullptr));
+    VAG_TRY(gru_gates_split(h_out, H, ws.gi, 3 * H, ws.gh, 3 * H, ws.h1, H, rows, H, f.cat, st, nullptr, 0, f.done));
+    VAG_TRY(tc_gemm_split_out(f.t, f.cat.hi, f.cat.lo, Kt, pr.ro.hi, pr.ro.lo, pr.ro.ld, pr.b_ro, rows, Kt, E, VAG_LIN_TANH, st));  // :137
     if (!logits) {   // beam loop: only the top-2 / Σexp summaries of every 128-column tile leave the projection
         if (summ_tile_w) *summ_tile_w = 128;
-        return tc_gemm_top2(summ, f.t.hi, f.t.lo, f.t.ld, f.w_out->hi, f.w_out->lo, f.w_out->ld, w->out_b, rows, E, (int)V, st);
+        return tc_gemm_top2(summ, f.t.hi, f.t.lo, f.t.ld, pr.out.hi, pr.out.lo, pr.out.ld, w->out_b, rows, E, (int)V, st);
     }
-    return gemm(logits, ld_logits, f.t, f.w_out, w->out_b, E, (int)V, summ, summ_tile_w);                     // :143
+    return gemm(logits, ld_logits, f.t, pr.out, w->out_b, E, (int)V, summ, summ_tile_w);                     // :143
 }
 }  // namespace vag
 
@@ -419,6 +517,7 @@ extern "C" int vag_decoder_step_f32(const vag_decoder_weights* w, const int64_t*
                                     const float* ctx, const float* mask, int rows, int rows_per_sent, int T, float* h_out,
                                     float* logits_or_logp, int want_logp, float* alpha_out, void* workspace,
                                     size_t workspace_bytes, vag_stream_t stream) {
+    ModeScope ms(w ? w->precision : VAG_PREC_FP32);
     VAG_REQUIRE(w && tokens && h_prev && keys && ctx && h_out && logits_or_logp, "vag_decoder_step_f32: null pointer");
     VAG_REQUIRE(rows > 0 && rows_per_sent > 0 && rows % rows_per_sent == 0 && T > 0, "vag_decoder_step_f32: bad shape");
     VAG_REQUIRE(h_out != h_prev, "vag_decoder_step_f32: h_out must not alias h_prev");
@@ -430,6 +529,12 @@ extern "C" int vag_decoder_step_f32(const vag_decoder_weights* w, const int64_t*
         return VAG_ERR_WORKSPACE;
     }
     GemmCtx gemm((cudaStream_t)stream, ws.wreg, ws.wbytes, ws.areg, ws.abytes);
+    {
+        Prepared pr;
+        bool have_pr = false;
+        VAG_TRY(prepared_get(w, nullptr, 0, (cudaStream_t)stream, &pr, &have_pr));
+        if (have_pr) prepared_register(gemm, w, pr);
+    }
     VAG_TRY(decoder_step_core(gemm, w, ws, tokens, h_prev, keys, ctx, mask, rows, rows_per_sent, T, h_out, logits_or_logp, w->V,
                               alpha_out, (cudaStream_t)stream));
     if (want_logp) VAG_TRY(vag_log_softmax_f32(logits_or_logp, logits_or_logp, rows, (int)w->V, stream));
@@ -440,7 +545,9 @@ extern "C" int vag_decoder_step_f32(const vag_decoder_weights* w, const int64_t*
 namespace vag {
 struct BeamWs {
     StepWs step;
-    float *logits, *lse, *h_a, *h_b, *nll, *g1;
+    float *logits, *lse, *h_a, *h_b, *nll;
+    void* prep;          // the call's own copy of the decode invariants (unused when the caller passes w->prepared)
+    size_t prep_bytes;
     float4* summ;
     int64_t *tok_hist, *sos;
     int32_t* par_hist;
@@ -453,7 +560,10 @@ static void beam_layout(A& a, int B, int K, int L, int E, int H, int C, int64_t 
     step_layout(a, N, E, H, C, V, &sw);
     float* logits = (float*)a.template take<float>((size_t)N * ((V + 3) / 4 * 4));  // rows padded to 16 B
     float* lse = (float*)a.template take<float>((size_t)N);
-    float* g1 = (float*)a.template take<float>((size_t)V * 3 * H);   // per-token input pre-activations of gru_1 (fused path)
+    SizerAdapter psz;
+    prepared_layout(psz, E, H, C, V, nullptr);
+    const size_t prep_bytes = psz.s.total();
+    void* prep = a.template take<char>(prep_bytes);
     float4* summ = (float4*)a.template take<float4>((size_t)N * ((V + 31) / 32));   // per 32-column slice (top-2 kernel); the per-128 summaries need a quarter
     float* h_a = (float*)a.template take<float>((size_t)N * H);
     float* h_b = (float*)a.template take<float>((size_t)N * H);
@@ -463,7 +573,7 @@ static void beam_layout(A& a, int B, int K, int L, int E, int H, int C, int64_t 
     int32_t* par_hist = (int32_t*)a.template take<int32_t>((size_t)L * N);
     int* flags = (int*)a.template take<int>((size_t)L + 2);
     if (ws) {
-        ws->step = sw; ws->logits = logits; ws->lse = lse; ws->g1 = g1; ws->summ = summ; ws->h_a = h_a; ws->h_b = h_b; ws->nll = nll;
+        ws->step = sw; ws->logits = logits; ws->lse = lse; ws->prep = prep; ws->prep_bytes = prep_bytes; ws->summ = summ; ws->h_a = h_a; ws->h_b = h_b; ws->nll = nll;
         ws->tok_hist = tok_hist; ws->sos = sos; ws->par_hist = par_hist; ws->flags = flags;
     }
 }
@@ -476,12 +586,44 @@ extern "C" size_t vag_beam_decode_workspace_bytes(int B, int K, int T, int L, in
     return s.s.total();
 }
 
+extern "C" size_t vag_decoder_prepared_bytes(int E, int H, int C, int64_t V) {
+    SizerAdapter s;
+    prepared_layout(s, E, H, C, V, nullptr);
+    return s.s.total();
+}
+
+extern "C" int vag_decoder_prepare_f32(const vag_decoder_weights* w, void* prepared, size_t prepared_bytes, vag_stream_t stream) {
+    ModeScope ms(w ? w->precision : VAG_PREC_FP32);
+    VAG_REQUIRE(w && prepared, "vag_decoder_prepare_f32: null pointer");
+    if (!prepared_supported(w, gemm_mode())) {
+        set_error("vag_decoder_prepare_f32: needs 16-byte aligned weights, E/H/C multiples of 8, V >= 64 and a 16-bit tensor-core mode");
+        return VAG_ERR_UNSUPPORTED;
+    }
+    ArenaAdapter ar(prepared, prepared_bytes);
+    Prepared pr;
+    prepared_layout(ar, w->E, w->H, w->C, w->V, &pr);
+    if (ar.a.overflow) {
+        set_error("vag_decoder_prepare_f32: buffer %zu B too small (vag_decoder_prepared_bytes)", prepared_bytes);
+        return VAG_ERR_WORKSPACE;
+    }
+    return prepared_fill(w, pr, (cudaStream_t)stream);
+}
+
+// host_progress word: (call nonce & 0x7FFF) << 16 | done << 15 | steps finished (L < 32768)
+static inline int progress_nonce() {
+    static thread_local unsigned n = 0;
+    n = (n + 1) & 0x7FFF;
+    if (n == 0) n = 1;
+    return (int)n;
+}
+
 extern "C" int vag_beam_decode_f32(const vag_decoder_weights* w, const float* h0, const float* keys, const float* ctx,
                                    const float* mask, int B, int K, int T, int L, int avoid_double, int64_t* hyp_out,
-                                   int32_t* hyp_len, int64_t* beam_out, float* nll_out, int32_t* steps_out, void* workspace,
-                                   size_t workspace_bytes, vag_stream_t stream) {
+                                   int32_t* hyp_len, int64_t* beam_out, float* nll_out, int32_t* steps_out,
+                                   volatile int32_t* host_progress, void* workspace, size_t workspace_bytes, vag_stream_t stream) {
+    ModeScope ms(w ? w->precision : VAG_PREC_FP32);
     VAG_REQUIRE(w && h0 && keys && ctx && mask && hyp_out && hyp_len, "vag_beam_decode_f32: null pointer");
-    VAG_REQUIRE(B > 0 && K > 1 && T > 0 && L > 0, "vag_beam_decode_f32: bad shape B=%d K=%d T=%d L=%d", B, K, T, L);
+    VAG_REQUIRE(B > 0 && K > 1 && T > 0 && L > 0 && L < 32768, "vag_beam_decode_f32: bad shape B=%d K=%d T=%d L=%d", B, K, T, L);
     VAG_REQUIRE(K <= w->V, "vag_beam_decode_f32: beam larger than the vocabulary");
     cudaStream_t st = (cudaStream_t)stream;
     const int E = w->E, H = w->H, C = w->C;
@@ -502,9 +644,40 @@ extern "C" int vag_beam_decode_f32(const vag_decoder_weights* w, const float* h0
     VAG_LAUNCH_CHECK();
     const int64_t ldl = (V + 3) / 4 * 4;
     GemmCtx gemm(st, ws.step.wreg, ws.step.wbytes, ws.step.areg, ws.step.abytes);
+    Prepared pr;
+    bool have_pr = false;
+    VAG_TRY(prepared_get(w, ws.prep, ws.prep_bytes, st, &pr, &have_pr));
     FusedStep fused;
-    VAG_TRY(fused_setup(gemm, w, ws.step, N, K, ws.g1, &fused));
+    if (have_pr) {
+        prepared_register(gemm, w, pr);
+        VAG_TRY(fused_setup(w, ws.step, N, K, pr, &fused));
+        fused.done = done;
+    }
+    const int nonce = host_progress ? progress_nonce() : 0;
+    constexpr int kLookahead = 4;     // steps the host may enqueue ahead of the device when it polls host_progress
     for (int di = 0; di < L; ++di) {
+        if (host_progress && di > kLookahead) {
+            // The reference tests `n_fini == B·K` on the host after EVERY step (V11:265-269).  Here the device publishes its
+            // progress in mapped host memory and the host only stays kLookahead steps ahead: when `done` appears it stops
+            // enqueueing, so a search that ends after s steps costs s (+ at most kLookahead returned-at-once) steps, not L.
+            bool stop = false;
+            for (unsigned spin = 0;; ++spin) {
+                const int v = *host_progress;
+                const bool mine = ((v >> 16) & 0x7FFF) == nonce;
+                if (mine && (v & 0x8000)) { stop = true; break; }
+                if (mine && (v & 0x7FFF) >= di - kLookahead) break;
+                if ((spin & 0x3FF) == 0x3FF) {   // every ~1000 polls: has the stream died or drained without progress?
+                    const cudaError_t q = cudaStreamQuery(st);
+                    if (q != cudaErrorNotReady) {
+                        if (q != cudaSuccess) { set_error("vag_beam_decode_f32: stream error while polling: %s", cudaGetErrorString(q)); return VAG_ERR_CUDA; }
+                        const int v2 = *host_progress;   // drained: the last store is visible now
+                        if (((v2 >> 16) & 0x7FFF) == nonce && (v2 & 0x8000)) stop = true;
+                        break;
+                    }
+                }
+            }
+            if (stop) break;
+        }
         const int rows = di == 0 ? B : N;
         const int rps = di == 0 ? 1 : K;
         const int64_t* tokens = di == 0 ? ws.sos : ws.tok_hist + (size_t)(di - 1) * N;
@@ -520,8 +693,8 @@ extern "C" int vag_beam_decode_f32(const vag_decoder_weights* w, const float* h0
             VAG_TRY(decoder_step_fused(fused, w, ws.step, tokens, h_prev, keys, ctx, mask, rows, rps, T, ws.h_b, no_logits ? nullptr : ws.logits,
                                        ldl, st, V >= 512 ? ws.summ : nullptr, &tile_w));
             if (no_logits) {
-                VAG_TRY(beam_select_top2(ws.summ, 32, fused.t, (const uint16_t*)fused.w_out->hi, (const uint16_t*)fused.w_out->lo,
-                                         fused.w_out->ld, w->out_b, E, di == 0 ? nullptr : tokens, ws.nll, ws.tok_hist + (size_t)di * N,
+                VAG_TRY(beam_select_top2(ws.summ, 32, fused.t, (const uint16_t*)pr.out.hi, (const uint16_t*)pr.out.lo,
+                                         pr.out.ld, w->out_b, E, di == 0 ? nullptr : tokens, ws.nll, ws.tok_hist + (size_t)di * N,
                                          ws.par_hist + (size_t)di * N, B, K, V, di, avoid_double, done, fin + di, st));
                 tile_w = -1;   // selection done
             }
@@ -542,9 +715,10 @@ extern "C" int vag_beam_decode_f32(const vag_decoder_weights* w, const float* h0
         if (fused.ok)
             VAG_TRY(beam_advance_fused(ws.h_a, ws.h_b, ws.par_hist + (size_t)di * N, ws.tok_hist + (size_t)di * N, B, K, rps, H, di, done,
                                        fin + di, steps_run, fused.hprev, fused.cat_e(H), (const uint16_t*)fused.w_emb->hi,
-                                       (const uint16_t*)fused.w_emb->lo, fused.w_emb->ld, E, V, st));
+                                       (const uint16_t*)fused.w_emb->lo, fused.w_emb->ld, E, V, st, host_progress, nonce));
         else
-            VAG_TRY(beam_advance(ws.h_a, ws.h_b, ws.par_hist + (size_t)di * N, B, K, rps, H, di, done, fin + di, steps_run, st));
+            VAG_TRY(beam_advance(ws.h_a, ws.h_b, ws.par_hist + (size_t)di * N, B, K, rps, H, di, done, fin + di, steps_run, st,
+                                 host_progress, nonce));
     }
     VAG_TRY(beam_finalize(ws.tok_hist, ws.par_hist, ws.nll, steps_run, B, K, L, hyp_out, hyp_len, beam_out, st));
     if (nll_out) VAG_CUDA(cudaMemcpyAsync(nll_out, ws.nll, sizeof(float) * (size_t)N, cudaMemcpyDeviceToDevice, st));
@@ -552,9 +726,20 @@ extern "C" int vag_beam_decode_f32(const vag_decoder_weights* w, const float* h0
     return VAG_OK;
 }
 
+/* The epilogue of the search alone (V11:315-337) for callers that drive the steps themselves with vag_decoder_step_f32 +
+ * vag_beam_select_f32: tok_hist / par_hist [L, B, K] (token and parent-beam index chosen at every step), nll [B, K],
+ * steps_run[1] on the device (rows >= steps_run count as 0, the last row is forced to <eos>). */
+extern "C" int vag_beam_finalize_f32(const int64_t* tok_hist, const int32_t* par_hist, const float* nll, const int32_t* steps_run, int B,
+                                     int K, int L, int64_t* hyp_out, int32_t* hyp_len, int64_t* beam_out, vag_stream_t stream) {
+    VAG_REQUIRE(tok_hist && par_hist && nll && steps_run && hyp_out && hyp_len, "vag_beam_finalize_f32: null pointer");
+    VAG_REQUIRE(B > 0 && K > 0 && K <= 32 && L > 0, "vag_beam_finalize_f32: bad shape");
+    return beam_finalize(tok_hist, par_hist, nll, (const int*)steps_run, B, K, L, hyp_out, hyp_len, beam_out, (cudaStream_t)stream);
+}
+
 extern "C" int vag_greedy_decode_f32(const vag_decoder_weights* w, const float* h0, const float* keys, const float* ctx,
                                      const float* mask, int B, int T, int L, int64_t* tokens_out, void* workspace,
                                      size_t workspace_bytes, vag_stream_t stream) {
+    ModeScope ms(w ? w->precision : VAG_PREC_FP32);
     VAG_REQUIRE(w && h0 && keys && ctx && mask && tokens_out, "vag_greedy_decode_f32: null pointer");
     VAG_REQUIRE(B > 0 && T > 0 && L > 0, "vag_greedy_decode_f32: bad shape");
     cudaStream_t st = (cudaStream_t)stream;
@@ -572,6 +757,12 @@ extern "C" int vag_greedy_decode_f32(const vag_decoder_weights* w, const float* 
     float* h_nxt = ws.h_b;
     const int64_t ldl = (w->V + 3) / 4 * 4;
     GemmCtx gemm(st, ws.step.wreg, ws.step.wbytes, ws.step.areg, ws.step.abytes);
+    {
+        Prepared pr;
+        bool have_pr = false;
+        VAG_TRY(prepared_get(w, nullptr, 0, st, &pr, &have_pr));   // only the caller's buffer: greedy has no table to build
+        if (have_pr) prepared_register(gemm, w, pr);
+    }
     for (int di = 0; di < L; ++di) {
         VAG_TRY(decoder_step_core(gemm, w, ws.step, ws.sos, h_cur, keys, ctx, mask, B, 1, T, h_nxt, ws.logits, ldl, nullptr, st));
         VAG_TRY(row_argmax(ws.logits, ldl, B, w->V, tokens_out + di, L, ws.sos, st));

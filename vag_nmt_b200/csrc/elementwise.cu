@@ -13,8 +13,9 @@ __global__ void __launch_bounds__(256)
 gru_gates_kernel(float* h_out, int64_t ld_ho, float* h_out2, int64_t ld_ho2,
                  const float* __restrict__ gi, int64_t ld_gi, const float* __restrict__ gh, int64_t ld_gh,
                  const float* h_prev /* may alias h_out */, int64_t ld_hp, int rows, int H, SplitDst sd,
-                 const int64_t* __restrict__ gi_rows = nullptr, int64_t gi_n_rows = 0) {
+                 const int64_t* __restrict__ gi_rows = nullptr, int64_t gi_n_rows = 0, const int* __restrict__ done = nullptr) {
     pdl_trigger();   // the contraction that follows may start its prologue while this kernel drains
+    if (done && *reinterpret_cast<const volatile int*>(done)) return;   // beam search over: the state is never read again
     constexpr int W = VEC ? 4 : 1;
     const int per_row = H / W;
     const int64_t total = (int64_t)rows * per_row;
@@ -244,11 +245,11 @@ int row_lse(float* lse_out, const float* logits, int64_t ld, int rows, int64_t V
 // aligned pointers — guaranteed by the caller's workspace layout).
 int gru_gates_split(float* h_out, int64_t ld_ho, const float* gi, int64_t ld_gi, const float* gh, int64_t ld_gh,
                     const float* h_prev, int64_t ld_hp, int rows, int H, SplitDst sd, cudaStream_t st, const int64_t* gi_rows,
-                    int64_t gi_n_rows) {
+                    int64_t gi_n_rows, const int* done) {
     if (rows == 0) return VAG_OK;
     const int64_t total = (int64_t)rows * (H / 4);
     const int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)num_sms() * 16);
-    gru_gates_kernel<true><<<blocks, 256, 0, st>>>(h_out, ld_ho, nullptr, 0, gi, ld_gi, gh, ld_gh, h_prev, ld_hp, rows, H, sd, gi_rows, gi_n_rows);
+    gru_gates_kernel<true><<<blocks, 256, 0, st>>>(h_out, ld_ho, nullptr, 0, gi, ld_gi, gh, ld_gh, h_prev, ld_hp, rows, H, sd, gi_rows, gi_n_rows, done);
     VAG_LAUNCH_CHECK();
     return VAG_OK;
 }

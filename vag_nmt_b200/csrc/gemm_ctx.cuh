@@ -26,6 +26,13 @@ int tc_gemm_top2(float4* summ, const void* xh, const void* xl, int64_t ldxs, con
 int tc_gemm_split_out(SplitDst out, const void* xh, const void* xl, int64_t ldxs, const void* wh, const void* wl, int64_t ldws,
                       const float* bias, int rows, int K, int N, int flags, cudaStream_t st);
 bool tc_call_supported(const float* y, int64_t ldy, int flags);
+// While alive, every tcgen05 contraction launched from this thread receives `done` (device flag, may be null): its CTAs return
+// right after their prologue when *done != 0 (beam search: every hypothesis has ended, the remaining steps are dead).
+struct TcDoneScope {
+    const int* prev;
+    explicit TcDoneScope(const int* done);
+    ~TcDoneScope();
+};
 int bias_sum3(float* out, const float* a, const float* b, const float* c, int n, cudaStream_t st);
 
 struct GemmCtx {
@@ -81,6 +88,16 @@ struct GemmCtx {
         return &tab[n++];
     }
 
+    // Planes that already exist (vag_decoder_prepare_f32): later lookups of `w` hit them and no split is launched.
+    void preset(const float* w, int N, int K, void* hi, void* lo) {
+        if (nw < 32 && !lookup(wc, nw, w, N, K)) wc[nw++] = Ent{w, N, K, hi, lo, K};
+    }
+    void preset3(const float* w0, int N, int Kt, void* hi, void* lo, float* bsum) {
+        if (nw + 1 < 32 && !lookup(wc, nw, w0, N, Kt)) {
+            wc[nw++] = Ent{w0, N, Kt, hi, lo, Kt};
+            wc[nw++] = Ent{(const void*)((uintptr_t)w0 + 1), N, Kt, bsum, nullptr, 0};
+        }
+    }
     // Split planes of a weight matrix, made once per composite call (nullptr: cache full / no region → FFMA path).
     int weight(Ent** out, const float* w, int64_t ldw, int N, int K) {
         Ent* we = lookup(wc, nw, w, N, K);

@@ -1,4 +1,5 @@
-// Tensor-core contraction for the FP32-exact mode:  y = act(x · Wᵀ + bias [+ y])  with 3xTF32 error compensation.
+// Tensor-core contraction:  y = act(x · Wᵀ + bias [+ y])  in the FP32-exact mode (error-compensated hi/lo operand split, three
+// products — FP16 planes by default, TF32 planes under VAG_GEMM=tf32x3) or in the bf16 mode (one product).
 //
 // tcgen05 has no FP32-input MMA, and plain TF32 (10-bit mantissa) flips beams (hard part 1).
 // Every operand is therefore split once into hi = rn_tf32(v) and lo = v - hi (exact in FP32) and the product is
@@ -17,6 +18,7 @@
 //   warps 2-5  epilogue: tcgen05.ld (32 lanes x 32 columns) → bias / accumulate / tanh → global stores
 #include "common.cuh"
 #include "split.cuh"
+#include "gemm_ctx.cuh"
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
@@ -701,7 +703,7 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
                    const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
                    const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_yh,
                    const __grid_constant__ CUtensorMap map_yl, const float* __restrict__ bias, int rows, int K, int N,
-                   int flags, float4* __restrict__ summ, long long* __restrict__ dbg) {
+                   int flags, float4* __restrict__ summ, long long* __restrict__ dbg, const int* __restrict__ done) {
     constexpr bool F16 = MODE != 0;
     constexpr bool SPLIT = MODE != 2;
     constexpr int BMP = 256, BM = 128, BN = 128, ELT = F16 ? 2 : 4, BK = Q_ROWB / ELT, UK = 32 / ELT;
@@ -751,8 +753,12 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
     const uint32_t tmem_base = *tmem_slot;
     pdl_trigger();   // the next kernel on the stream may start its own prologue as SMs drain
     pdl_wait();      // everything above touched no global memory; from here on the predecessor's results are needed
+    // beam search: every hypothesis has ended — the flag was set by an EARLIER kernel of the stream, so all threads of all CTAs
+    // read the same value and skip their role loops together (barriers untouched, TMEM released below)
+    const bool dead = done && *reinterpret_cast<const volatile int*>(done) != 0;
 
-    if (warp == 0) {
+    if (dead) {
+    } else if (warp == 0) {
         if (lane == 0) {
             uint32_t g = 0;
             long long t_wait = 0, t_begin = VAG_TCLK();
@@ -1002,7 +1008,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(576, 1)
 vocab_top2_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                        const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
                        const float* __restrict__ bias, int rows, int K, int N, float4* __restrict__ summ,
-                       long long* __restrict__ dbg) {
+                       long long* __restrict__ dbg, const int* __restrict__ done) {
     constexpr bool F16 = MODE != 0;
     constexpr bool SPLIT = MODE != 2;
     constexpr int BMP = 256, BM = 128, BN = 128, ELT = F16 ? 2 : 4, BK = Q_ROWB / ELT, UK = 32 / ELT;
@@ -1060,8 +1066,10 @@ vocab_top2_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_
     const uint32_t tmem_base = *tmem_slot;
     pdl_trigger();   // the next kernel on the stream may start its own prologue as SMs drain
     pdl_wait();      // everything above touched no global memory; from here on the predecessor's results are needed
+    const bool dead = done && *reinterpret_cast<const volatile int*>(done) != 0;   // see linear_pair_kernel
 
-    if (warp == 0) {
+    if (dead) {
+    } else if (warp == 0) {
         if (lane == 0) {
             uint32_t g = 0, nb = 0;
             int cur_tn = -1;
@@ -1392,12 +1400,16 @@ static int launch_tc(const CUtensorMap& xh, const CUtensorMap& xl, const CUtenso
 }
 
 // VAG_GEMM=tf32x3 selects the TF32 split (any FP32 range); default is the FP16 split (2x the tensor rate).
-// 0 = TF32 split, 1 = FP16 split (default), 2 = BF16 single product.  vag_set_gemm_mode() (thread-local) wins over VAG_GEMM.
+// 0 = TF32 split, 1 = FP16 split (default), 2 = BF16 single product.  Set per C-ABI call by ModeScope (common.cuh).
 static thread_local int g_mode_override = -1;
 static long long* g_tc_dbg = nullptr;   // optional device buffer [32] for the pair kernel's role timers (tools only)
+static thread_local const int* g_tc_done = nullptr;   // TcDoneScope (gemm_ctx.cuh)
+TcDoneScope::TcDoneScope(const int* done) : prev(g_tc_done) { g_tc_done = done; }
+TcDoneScope::~TcDoneScope() { g_tc_done = prev; }
 void set_tc_debug(long long* p) { g_tc_dbg = p; }
 long long* tc_debug() { return g_tc_dbg; }
-void set_gemm_mode(int m) { g_mode_override = m; }
+ModeScope::ModeScope(int precision) : prev(g_mode_override) { g_mode_override = precision == VAG_PREC_BF16 ? 2 : -1; }
+ModeScope::~ModeScope() { g_mode_override = prev; }
 int gemm_mode() {
     if (g_mode_override >= 0) return g_mode_override;
     const char* e = getenv("VAG_GEMM");
@@ -1525,10 +1537,10 @@ int tc_gemm_split_out(SplitDst out, const void* xh, const void* xl, int64_t ldxs
     static bool attr_set[3] = {false, false, false};
     if (mode == 1) {
         if (!attr_set[1]) { VAG_CUDA(cudaFuncSetAttribute(linear_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES)); attr_set[1] = true; }
-        VAG_CUDA(launch_pdl(linear_pair_kernel<1>, dim3(grid), dim3(320), Q_SMEM_BYTES, st, mxh, mxl, mwh, mwl, myh, myh, myl, bias, rows, K, N, flags | VAG_LIN_SPLIT_OUT, (float4*)nullptr, g_tc_dbg));
+        VAG_CUDA(launch_pdl(linear_pair_kernel<1>, dim3(grid), dim3(320), Q_SMEM_BYTES, st, mxh, mxl, mwh, mwl, myh, myh, myl, bias, rows, K, N, flags | VAG_LIN_SPLIT_OUT, (float4*)nullptr, g_tc_dbg, g_tc_done));
     } else {
         if (!attr_set[2]) { VAG_CUDA(cudaFuncSetAttribute(linear_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES)); attr_set[2] = true; }
-        VAG_CUDA(launch_pdl(linear_pair_kernel<2>, dim3(grid), dim3(320), Q_SMEM_BYTES, st, mxh, mxl, mwh, mwl, myh, myh, myl, bias, rows, K, N, flags | VAG_LIN_SPLIT_OUT, (float4*)nullptr, g_tc_dbg));
+        VAG_CUDA(launch_pdl(linear_pair_kernel<2>, dim3(grid), dim3(320), Q_SMEM_BYTES, st, mxh, mxl, mwh, mwl, myh, myh, myl, bias, rows, K, N, flags | VAG_LIN_SPLIT_OUT, (float4*)nullptr, g_tc_dbg, g_tc_done));
     }
     VAG_LAUNCH_CHECK();
     return VAG_OK;
@@ -1555,10 +1567,10 @@ int tc_gemm_top2(float4* summ, const void* xh, const void* xl, int64_t ldxs, con
     static bool attr_set[3] = {false, false, false};
     if (mode == 1) {
         if (!attr_set[1]) { VAG_CUDA(cudaFuncSetAttribute(vocab_top2_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, V_SMEM_BYTES)); attr_set[1] = true; }
-        VAG_CUDA(launch_pdl(vocab_top2_pair_kernel<1>, dim3(grid), dim3(576), V_SMEM_BYTES, st, mxh, mxl, mwh, mwl, bias, rows, K, N, summ, g_tc_dbg));
+        VAG_CUDA(launch_pdl(vocab_top2_pair_kernel<1>, dim3(grid), dim3(576), V_SMEM_BYTES, st, mxh, mxl, mwh, mwl, bias, rows, K, N, summ, g_tc_dbg, g_tc_done));
     } else {
         if (!attr_set[2]) { VAG_CUDA(cudaFuncSetAttribute(vocab_top2_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, V_SMEM_BYTES)); attr_set[2] = true; }
-        VAG_CUDA(launch_pdl(vocab_top2_pair_kernel<2>, dim3(grid), dim3(576), V_SMEM_BYTES, st, mxh, mxl, mwh, mwl, bias, rows, K, N, summ, g_tc_dbg));
+        VAG_CUDA(launch_pdl(vocab_top2_pair_kernel<2>, dim3(grid), dim3(576), V_SMEM_BYTES, st, mxh, mxl, mwh, mwl, bias, rows, K, N, summ, g_tc_dbg, g_tc_done));
     }
     VAG_LAUNCH_CHECK();
     return VAG_OK;
@@ -1591,7 +1603,7 @@ int tc_gemm(float* y, int64_t ldy, const void* xh, const void* xl, int64_t ldxs,
             VAG_CUDA(cudaFuncSetAttribute(linear_pair_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES));    \
             attr_set[M] = true;                                                                                                 \
         }                                                                                                                       \
-        VAG_CUDA(launch_pdl(linear_pair_kernel<M>, dim3(grid), dim3(320), Q_SMEM_BYTES, st, mxh, mxl, mwh, mwl, my, my, my, bias, rows, K, N, flags & ~VAG_LIN_SPLIT_OUT, summ, g_tc_dbg));          \
+        VAG_CUDA(launch_pdl(linear_pair_kernel<M>, dim3(grid), dim3(320), Q_SMEM_BYTES, st, mxh, mxl, mwh, mwl, my, my, my, bias, rows, K, N, flags & ~VAG_LIN_SPLIT_OUT, summ, g_tc_dbg, g_tc_done));          \
     } while (0)
         if (mode == 0) VAG_PAIR(0);
         else if (mode == 1) VAG_PAIR(1);

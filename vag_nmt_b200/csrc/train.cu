@@ -487,8 +487,18 @@ clip_adam_multi_kernel(const vag_optim_tensor* __restrict__ t, const float* __re
 
 using namespace vag;
 
+namespace vag {
+int gemm_f32(float* C, int64_t ldc, const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn, int M, int N,
+             int K, float alpha, float beta, vag_stream_t stream);
+}
 extern "C" int vag_gemm_f32(float* C, int64_t ldc, const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk,
-                            int64_t sbn, int M, int N, int K, float alpha, float beta, vag_stream_t stream) {
+                            int64_t sbn, int M, int N, int K, float alpha, float beta, int precision, vag_stream_t stream) {
+    ModeScope ms(precision);
+    return gemm_f32(C, ldc, A, sam, sak, B, sbk, sbn, M, N, K, alpha, beta, stream);
+}
+// the arithmetic mode is the enclosing C-ABI call's (ModeScope)
+int vag::gemm_f32(float* C, int64_t ldc, const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn, int M,
+                  int N, int K, float alpha, float beta, vag_stream_t stream) {
     VAG_REQUIRE(C && A && B, "vag_gemm_f32: null pointer");
     VAG_REQUIRE(M >= 0 && N >= 0 && K >= 0 && ldc >= N, "vag_gemm_f32: bad shape");
     if (M == 0 || N == 0) return VAG_OK;
@@ -767,7 +777,7 @@ static int gemm_g(float* C, int64_t ldc, const float* A, int64_t sam, int64_t sa
                   int N, int K, float beta, cudaStream_t st) {
     const int r = gemm_tc_try(C, ldc, A, sam, sak, B, sbk, sbn, M, N, K, beta, g_tc_scratch.base, g_tc_scratch.cap, st);
     if (r != 0) return r < 0 ? r : VAG_OK;
-    return vag_gemm_f32(C, ldc, A, sam, sak, B, sbk, sbn, M, N, K, 1.0f, beta, (vag_stream_t)st);
+    return gemm_f32(C, ldc, A, sam, sak, B, sbk, sbn, M, N, K, 1.0f, beta, (vag_stream_t)st);
 }
 // scratch the tensor-core route may need for one contraction of the given logical shape
 static size_t gemm_tc_scratch_bytes(int64_t M, int64_t N, int64_t K) {
@@ -781,8 +791,9 @@ extern "C" size_t vag_gemm_tc_workspace_bytes(int M, int N, int K) { return gemm
 /* vag_gemm_f32 with a caller-owned workspace: large contractions run on the tcgen05 path (operands are split, and
    transposed where they are not contraction-contiguous, into the workspace); everything else takes the FFMA kernels. */
 extern "C" int vag_gemm_tc_f32(float* C, int64_t ldc, const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk,
-                               int64_t sbn, int M, int N, int K, float alpha, float beta, void* workspace, size_t workspace_bytes,
-                               vag_stream_t stream) {
+                               int64_t sbn, int M, int N, int K, float alpha, float beta, int precision, void* workspace,
+                               size_t workspace_bytes, vag_stream_t stream) {
+    ModeScope ms(precision);
     VAG_REQUIRE(C && A && B, "vag_gemm_tc_f32: null pointer");
     VAG_REQUIRE(M >= 0 && N >= 0 && K >= 0 && ldc >= N, "vag_gemm_tc_f32: bad shape");
     if (M == 0 || N == 0) return VAG_OK;
@@ -790,7 +801,7 @@ extern "C" int vag_gemm_tc_f32(float* C, int64_t ldc, const float* A, int64_t sa
         const int r = gemm_tc_try(C, ldc, A, sam, sak, B, sbk, sbn, M, N, K, beta, (char*)workspace, workspace_bytes, (cudaStream_t)stream);
         if (r != 0) return r < 0 ? r : VAG_OK;
     }
-    return vag_gemm_f32(C, ldc, A, sam, sak, B, sbk, sbn, M, N, K, alpha, beta, stream);
+    return gemm_f32(C, ldc, A, sam, sak, B, sbk, sbn, M, N, K, alpha, beta, stream);
 }
 
 extern "C" size_t vag_decoder_seq_workspace_bytes(int B, int T, int Tt, int E, int H, int C, int64_t V) {
@@ -810,6 +821,7 @@ extern "C" int vag_decoder_seq_fwd_f32(const vag_decoder_weights* w, const float
                                        int64_t* tok_in, const int64_t* tgt_t, const float* nll_weight, int B, int T, int Tt,
                                        int teacher, const vag_decoder_seq_saved* s, const float* out_mask, float* loss_rows,
                                        void* workspace, size_t workspace_bytes, vag_stream_t stream) {
+    ModeScope ms(w ? w->precision : VAG_PREC_FP32);
     VAG_REQUIRE(w && h0 && enc && mask && tok_in && tgt_t && s && loss_rows, "vag_decoder_seq_fwd_f32: null pointer");
     VAG_REQUIRE(B > 0 && T > 0 && Tt > 0, "vag_decoder_seq_fwd_f32: bad shape");
     cudaStream_t st = (cudaStream_t)stream;
@@ -915,6 +927,7 @@ extern "C" int vag_decoder_seq_bwd_f32(const vag_decoder_weights* w, const float
                                        int tied, const vag_decoder_seq_saved* s, const float* out_mask, const float* dloss_rows,
                                        const vag_decoder_grads* g, float* d_h0, float* d_enc, void* workspace,
                                        size_t workspace_bytes, vag_stream_t stream) {
+    ModeScope ms(w ? w->precision : VAG_PREC_FP32);
     VAG_REQUIRE(w && h0 && enc && mask && tok_in && tgt_t && s && dloss_rows && g && d_h0 && d_enc, "vag_decoder_seq_bwd_f32: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     vag_stream_t vs = stream;
@@ -1221,6 +1234,7 @@ extern "C" int vag_encoder_train_fwd_f32(const vag_encoder_weights* w, const int
                                          const int32_t* lengths_dev, int B, int T, float* ctx_out, float* x, int64_t* ids_tm,
                                          float* gi, float* gh, const float* emb_mask, void* workspace, size_t workspace_bytes,
                                          vag_stream_t stream) {
+    ModeScope ms(w ? w->precision : VAG_PREC_FP32);
     VAG_REQUIRE(w && src && lengths_dev && ctx_out && x && ids_tm && gi && gh, "vag_encoder_train_fwd_f32: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const int E = w->E, H = w->H;
@@ -1293,6 +1307,7 @@ extern "C" int vag_encoder_bwd_f32(const vag_encoder_weights* w, const int32_t* 
                                    const float* gh, float* d_emb, float* const* d_w_ih, float* const* d_w_hh, float* const* d_b_ih,
                                    float* const* d_b_hh, const float* emb_mask, void* workspace, size_t workspace_bytes,
                                    vag_stream_t stream) {
+    ModeScope ms(w ? w->precision : VAG_PREC_FP32);
     VAG_REQUIRE(w && lengths_dev && ctx && dctx && x && ids_tm && gi && gh && d_emb, "vag_encoder_bwd_f32: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     vag_stream_t vs = stream;
@@ -1359,7 +1374,7 @@ extern "C" int vag_encoder_bwd_f32(const vag_encoder_weights* w, const int32_t* 
                                          {cr[1], nullptr, H, H, 1, {{dgh_t[1], w->w_hh[1], 3 * H, H, 3 * H}, {}}}};
             VAG_TRY(linear_rows32_multi(pp, 2, B, VAG_LIN_ACCUMULATE, false, gemm_mode() == 2, st));
         } else {
-            for (int d = 0; d < 2; ++d) VAG_TRY(vag_gemm_f32(cr[d], H, dgh_t[d], 3 * H, 1, w->w_hh[d], H, 1, B, H, 3 * H, 1.f, 1.f, vs));
+            for (int d = 0; d < 2; ++d) VAG_TRY(gemm_f32(cr[d], H, dgh_t[d], 3 * H, 1, w->w_hh[d], H, 1, B, H, 3 * H, 1.f, 1.f, vs));
         }
     }
     for (int d = 0; d < 2; ++d) {

@@ -48,21 +48,15 @@ def _dropout_mask(model, name: str, p: float, shape, device) -> Optional[torch.T
 
 
 def _with_precision(fn):
-    """Run a public model method under the model's arithmetic mode (model.precision = "fp32" | "bf16")."""
+    """Run a public model method under the model's arithmetic mode (model.precision = "fp32" | "bf16"): every C-ABI call the
+    method makes carries that vag_precision (the C library itself has no mode switch)."""
     import functools
 
     @functools.wraps(fn)
     def wrapper(self, *args, **kwargs):
-        mode = {"fp32": -1, "bf16": 2}[getattr(self, "precision", "fp32")]
-        if mode == -1:
-            return fn(self, *args, **kwargs)
         from . import _cabi
-        lib = _cabi.lib()
-        lib.vag_set_gemm_mode(mode)
-        try:
+        with _cabi.precision_scope(getattr(self, "precision", "fp32")):
             return fn(self, *args, **kwargs)
-        finally:
-            lib.vag_set_gemm_mode(-1)
     return wrapper
 
 
@@ -76,23 +70,9 @@ class _Seq2SeqBase(nn.Module):
     precision = "fp32"
 
     def precision_scope(self):
-        """Context manager: run the enclosed calls (e.g. ``loss.backward()``) under the model's arithmetic mode."""
-        import contextlib
-
-        @contextlib.contextmanager
-        def scope():
-            mode = {"fp32": -1, "bf16": 2}[getattr(self, "precision", "fp32")]
-            if mode == -1:
-                yield
-                return
-            from . import _cabi
-            lib = _cabi.lib()
-            lib.vag_set_gemm_mode(mode)
-            try:
-                yield
-            finally:
-                lib.vag_set_gemm_mode(-1)
-        return scope()
+        """Context manager: run the enclosed calls under the model's arithmetic mode."""
+        from . import _cabi
+        return _cabi.precision_scope(getattr(self, "precision", "fp32"))
 
     def _reset_like_reference(self):
         # V11:77-80 / V2:53-56: kaiming-normal on EVERY ≥2-D non-bias parameter (embeddings and GRU matrices too)
@@ -240,7 +220,7 @@ class NMT_AttentionImagine_Seq2Seq_Beam_V11(_Seq2SeqBase):
         dev = self._device()
         ctx, mask = self._encode(src_var, src_lengths)                                   # V11:111 / :193
         im_emb, txt_emb, ctx_vec, _ = self.vse_imagine.pool_sentence_major(im_var.to(dev), ctx, mask)  # :114 / :196
-        w = ops.decoder_weights(self.decoder, self.decoderini)
+        w = ops.decoder_weights(self.decoder, self.decoderini, prepare=not self.training)
         h0 = ops.decoder_init(w, ctx_vec, ctx, mask, self.init_split)                    # :118 / :201
         keys = ops.attn_keys(w, ctx)
         return w, ctx, mask, keys, h0, im_emb, txt_emb
@@ -363,7 +343,7 @@ class NMT_Seq2Seq_Beam_V2(_Seq2SeqBase):
     def _prepare(self, src_var, src_lengths):
         self._device()
         ctx, mask = self._encode(src_var, src_lengths)
-        w = ops.decoder_weights(self.decoder, self.decoderini)
+        w = ops.decoder_weights(self.decoder, self.decoderini, prepare=not self.training)
         h0 = ops.decoder_init(w, None, ctx, mask, 0.0)                                   # V2:85,142
         keys = ops.attn_keys(w, ctx)
         return w, ctx, mask, keys, h0

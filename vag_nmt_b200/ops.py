@@ -14,7 +14,12 @@ from . import _cabi
 from ._cabi import DecoderWeights, EncoderWeights, VseWeights, check, on_device, ptr, stream_ptr
 
 ATTN_MLP, ATTN_DOT = 0, 1
-LIN_TANH, LIN_ACCUMULATE, LIN_FORCE_SIMT, LIN_FORCE_TC = 1, 2, 4, 8
+LIN_TANH, LIN_ACCUMULATE, LIN_FORCE_SIMT, LIN_FORCE_TC, LIN_BF16 = 1, 2, 4, 8, 16
+
+
+def _pflag() -> int:
+    """VAG_LIN_BF16 when the current precision scope is bf16"""
+    return LIN_BF16 if _cabi.precision() == _cabi.PREC_BF16 else 0
 
 _workspaces = {}
 
@@ -64,13 +69,13 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     with on_device(x.device):
         check(lib.vag_linear_f32(out2.data_ptr(), out2.stride(0) if rows > 1 else out_dim, x2.data_ptr(),
                                  x2.stride(0) if rows > 1 else in_dim, w.data_ptr(), w.stride(0), ptr(bias), rows, in_dim,
-                                 out_dim, flags, stream_ptr()))
+                                 out_dim, flags | _pflag(), stream_ptr()))
     return out2.reshape(*lead, out_dim)
 
 
 def linear_tc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, flags: int = 0,
               out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Same contract as ``linear`` on the tcgen05 3xTF32 kernel (raises VagError for ineligible shapes)."""
+    """Same contract as ``linear`` on the tcgen05 split-precision kernel (raises VagError for ineligible shapes)."""
     _chk_f32(x, w, bias, out)
     lib = _cabi.lib()
     assert x.dim() == 2 and x.stride(1) == 1 and w.stride(1) == 1
@@ -82,7 +87,7 @@ def linear_tc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = N
     ws = workspace(lib.vag_linear_tc_workspace_bytes(rows, in_dim, out_dim), x.device, slot="gemm")
     with on_device(x.device):
         check(lib.vag_linear_tc_f32(out.data_ptr(), out.stride(0), x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0),
-                                    ptr(bias), rows, in_dim, out_dim, flags, ws.data_ptr(), ws.numel(), stream_ptr()))
+                                    ptr(bias), rows, in_dim, out_dim, flags | _pflag(), ws.data_ptr(), ws.numel(), stream_ptr()))
     return out
 
 
@@ -92,11 +97,11 @@ def tc_split(x: torch.Tensor):
     lib = _cabi.lib()
     assert x.dim() == 2 and x.stride(1) == 1
     rows, K = x.shape
-    esz = lib.vag_tc_elem_bytes()
+    esz = lib.vag_tc_elem_bytes(_cabi.precision())
     hi = torch.empty(rows * K * esz, dtype=torch.uint8, device=x.device)
     lo = torch.empty_like(hi)
     with on_device(x.device):
-        check(lib.vag_tc_split_f32(x.data_ptr(), x.stride(0), rows, K, hi.data_ptr(), lo.data_ptr(), K, stream_ptr()))
+        check(lib.vag_tc_split_f32(x.data_ptr(), x.stride(0), rows, K, hi.data_ptr(), lo.data_ptr(), K, _cabi.precision(), stream_ptr()))
     return hi, lo
 
 
@@ -109,7 +114,7 @@ def tc_gemm(xs, ws, rows: int, in_dim: int, out_dim: int, bias: Optional[torch.T
         out = torch.empty(rows, out_dim, dtype=torch.float32, device=dev)
     with on_device(dev):
         check(lib.vag_tc_gemm_f32(out.data_ptr(), out.stride(0), xs[0].data_ptr(), xs[1].data_ptr(), in_dim, ws[0].data_ptr(),
-                                  ws[1].data_ptr(), in_dim, ptr(bias), rows, in_dim, out_dim, flags, stream_ptr()))
+                                  ws[1].data_ptr(), in_dim, ptr(bias), rows, in_dim, out_dim, flags | _pflag(), stream_ptr()))
     return out
 
 
@@ -120,7 +125,7 @@ def tc_gemm_top2(xs, ws, rows: int, in_dim: int, out_dim: int, bias: Optional[to
     summ = torch.empty((out_dim + 31) // 32, rows, 4, dtype=torch.float32, device=dev)
     with on_device(dev):
         check(lib.vag_tc_gemm_top2_f32(summ.data_ptr(), xs[0].data_ptr(), xs[1].data_ptr(), in_dim, ws[0].data_ptr(), ws[1].data_ptr(),
-                                       in_dim, ptr(bias), rows, in_dim, out_dim, stream_ptr()))
+                                       in_dim, ptr(bias), rows, in_dim, out_dim, _cabi.precision(), stream_ptr()))
     return summ
 
 
@@ -216,6 +221,7 @@ def encoder_weights(enc) -> EncoderWeights:
     g = enc.gru
     w = EncoderWeights()
     w.E, w.H, w.vocab = enc.embedding.weight.shape[1], g.hidden_size, enc.embedding.weight.shape[0]
+    w.precision = _cabi.precision()
     w.emb = _p(enc.embedding.weight)
     for d, sfx in enumerate(("", "_reverse")):
         w.w_ih[d] = _p(getattr(g, "weight_ih_l0" + sfx))
@@ -230,6 +236,7 @@ def vse_weights(vse) -> VseWeights:
     w.I, w.C, w.S = vse.im_size, vse.hidden_size, vse.shared_embedding_size
     w.method = ATTN_DOT if vse.attn_type == "dot" else ATTN_MLP
     w.activation = 1 if vse.activation_vse else 0
+    w.precision = _cabi.precision()
     w.im_w, w.im_b = _p(vse.im_embedding.weight), _p(vse.im_embedding.bias)
     w.txt_w, w.txt_b = _p(vse.text_embedding.weight), _p(vse.text_embedding.bias)
     w.ctx2ctx_w = _p(vse.imagine_attn.ctx2ctx.weight)
@@ -238,9 +245,35 @@ def vse_weights(vse) -> VseWeights:
     return w
 
 
-def decoder_weights(dec, decoderini=None) -> DecoderWeights:
+_prepared = {}        # (id(decoder module), precision) → (key, buffer): decode-call invariants of a weight set
+_weights_epoch = 0
+
+
+def invalidate_prepared() -> None:
+    """Parameters were updated through raw pointers (ClipAdam's fused kernel does not bump tensor versions): drop every cached
+    ``vag_decoder_prepare_f32`` buffer."""
+    global _weights_epoch
+    _weights_epoch += 1
+    _prepared.clear()
+
+
+def _decoder_params(dec, decoderini):
+    ps = [dec.embedding.weight, dec.gru_1.weight_ih_l0, dec.gru_1.weight_hh_l0, dec.gru_1.bias_ih_l0, dec.gru_1.bias_hh_l0,
+          dec.attn.attn_h.weight, dec.attn.attn_e.weight, dec.attn.v, dec.context2hid.weight, dec.gru_2.weight_ih_l0,
+          dec.gru_2.weight_hh_l0, dec.gru_2.bias_ih_l0, dec.gru_2.bias_hh_l0, dec.W1.weight, dec.W1.bias, dec.W2.weight, dec.W2.bias,
+          dec.W3.weight, dec.W3.bias, dec.out.weight, dec.out.bias]
+    if decoderini is not None:
+        ps += [decoderini.weight, decoderini.bias]
+    return ps
+
+
+def decoder_weights(dec, decoderini=None, prepare: bool = False) -> DecoderWeights:
+    """The weight struct of one call.  prepare=True attaches the decode-call invariants (operand planes of every matrix, the
+    per-token gru_1 table; vag_decoder_prepare_f32), computed once per (weights, precision) and cached until a parameter
+    changes — what makes decoding in the reference's eval batches of 16 (nmt_multimodal_beam_DE.py:542-547) affordable."""
     w = DecoderWeights()
     w.E, w.H, w.C, w.V = dec.embedding_size, dec.hidden_size, dec.context_size, dec.embedding.weight.shape[0]
+    w.precision = _cabi.precision()
     w.emb = _p(dec.embedding.weight)
     w.gru1_w_ih, w.gru1_w_hh = _p(dec.gru_1.weight_ih_l0), _p(dec.gru_1.weight_hh_l0)
     w.gru1_b_ih, w.gru1_b_hh = _p(dec.gru_1.bias_ih_l0), _p(dec.gru_1.bias_hh_l0)
@@ -254,6 +287,25 @@ def decoder_weights(dec, decoderini=None) -> DecoderWeights:
     w.out_w, w.out_b = _p(dec.out.weight), _p(dec.out.bias)
     if decoderini is not None:
         w.ini_w, w.ini_b = _p(decoderini.weight), _p(decoderini.bias)
+    if prepare and w.E % 8 == 0 and w.H % 8 == 0 and w.C % 8 == 0 and w.V >= 64:
+        params = _decoder_params(dec, decoderini)
+        key = (tuple((t.data_ptr(), t._version) for t in params), _weights_epoch)
+        slot = (id(dec), w.precision)
+        hit = _prepared.get(slot)
+        if hit is None or hit[0] != key:
+            lib = _cabi.lib()
+            dev = dec.embedding.weight.device
+            buf = torch.empty(lib.vag_decoder_prepared_bytes(w.E, w.H, w.C, w.V), dtype=torch.uint8, device=dev)
+            with on_device(dev):
+                status = lib.vag_decoder_prepare_f32(C.byref(w), buf.data_ptr(), buf.numel(), stream_ptr())
+            if status == -4:          # VAG_ERR_UNSUPPORTED (VAG_GEMM=simt / tf32x3, unaligned weights): decode without it
+                buf = None
+            else:
+                check(status)
+            hit = _prepared[slot] = (key, buf)
+        if hit[1] is not None:
+            w.prepared, w.prepared_bytes = hit[1].data_ptr(), hit[1].numel()
+            w._keepalive = hit[1]
     return w
 
 
@@ -359,9 +411,25 @@ def beam_select(logp: torch.Tensor, prev_tokens: Optional[torch.Tensor], nll: to
     return tokens, parents
 
 
+_progress_words = {}
+
+
+def _host_progress(dev: torch.device) -> Optional[torch.Tensor]:
+    """One pinned (device-mapped) int32 per device for vag_beam_decode_f32's early stop; None while a CUDA graph is being
+    captured (a captured call must not poll the host)."""
+    if torch.cuda.is_current_stream_capturing():
+        return None
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    t = _progress_words.get(key)
+    if t is None:
+        t = _progress_words[key] = torch.zeros(1, dtype=torch.int32).pin_memory()
+    return t
+
+
 def beam_decode(w: DecoderWeights, h0: torch.Tensor, keys: torch.Tensor, ctx: torch.Tensor, mask: torch.Tensor, K: int,
-                L: int, avoid_double: bool = True, debug: bool = False):
-    """→ hyp [B, L] int64, hyp_len [B] int32 (+ beam [L,B,K], nll [B,K], steps [1] when debug)"""
+                L: int, avoid_double: bool = True, debug: bool = False, early_stop: bool = True):
+    """→ hyp [B, L] int64, hyp_len [B] int32 (+ beam [L,B,K], nll [B,K], steps [1] when debug).  early_stop: the host follows
+    the device's progress word and stops launching steps once every hypothesis has ended (V11:265-269)."""
     lib = _cabi.lib()
     dev = ctx.device
     B, T, Cd = ctx.shape
@@ -372,10 +440,11 @@ def beam_decode(w: DecoderWeights, h0: torch.Tensor, keys: torch.Tensor, ctx: to
     steps = torch.empty(1, dtype=torch.int32, device=dev) if debug else None
     nbytes = lib.vag_beam_decode_workspace_bytes(B, K, T, L, w.E, w.H, w.C, w.V)
     ws = workspace(nbytes, dev)
+    prog = _host_progress(dev) if early_stop else None
     with on_device(dev):
         check(lib.vag_beam_decode_f32(C.byref(w), h0.data_ptr(), keys.data_ptr(), ctx.data_ptr(), mask.data_ptr(), B, K, T,
                                       L, 1 if avoid_double else 0, hyp.data_ptr(), hyp_len.data_ptr(), ptr(beam), ptr(nll),
-                                      ptr(steps), ws.data_ptr(), ws.numel(), stream_ptr()))
+                                      ptr(steps), ptr(prog), ws.data_ptr(), ws.numel(), stream_ptr()))
     if debug:
         return hyp, hyp_len, beam, nll, steps
     return hyp, hyp_len

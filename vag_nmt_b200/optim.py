@@ -107,4 +107,6 @@ class ClipAdam:
         T.clip_adam_multi_(table, len(entries), max_n, self._sumsq, clip if clip is not None else float("inf"), b1, b2, self.eps,
                            self.step_count)
         self._table = table   # keep the descriptors alive until the kernels have run
+        from . import ops
+        ops.invalidate_prepared()   # the update went through raw pointers: cached decode invariants are stale
         return self._sumsq

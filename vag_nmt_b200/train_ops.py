@@ -31,10 +31,10 @@ def gemm(A: torch.Tensor, B: torch.Tensor, trans_a: bool = False, trans_b: bool 
             from .ops import workspace
             ws = workspace(lib.vag_gemm_tc_workspace_bytes(M, N, K), A.device, slot="gemm")
             check(lib.vag_gemm_tc_f32(out.data_ptr(), out.stride(0), A.data_ptr(), sam, sak, B.data_ptr(), sbk, sbn, M, N, K,
-                                      _f(alpha), _f(beta), ws.data_ptr(), ws.numel(), stream_ptr()))
+                                      _f(alpha), _f(beta), _cabi.precision(), ws.data_ptr(), ws.numel(), stream_ptr()))
         else:
             check(lib.vag_gemm_f32(out.data_ptr(), out.stride(0), A.data_ptr(), sam, sak, B.data_ptr(), sbk, sbn, M, N, K,
-                                   _f(alpha), _f(beta), stream_ptr()))
+                                   _f(alpha), _f(beta), _cabi.precision(), stream_ptr()))
     return out
 
 
