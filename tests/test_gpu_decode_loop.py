@@ -1,0 +1,149 @@
+"""GPU: the decode loop's control — early stop that saves time, cached decode invariants, CUDA-graph replay of small batches,
+the reference's eval batching — all token-exact against the one-batch decode and the CPU oracle.
+
+Reference behaviour: V11.beamsearch breaks out of its loop once every hypothesis has ended (V11:265-269) and the drivers decode
+in eval batches of 16 with a per-batch length sort (nmt_multimodal_beam_DE.py:542-547, preprocessing.py:234-306).
+"""
+import os
+import time
+
+import pytest
+import torch
+
+from conftest import build_mm, cpu_params
+
+pytestmark = pytest.mark.gpu
+
+
+def _eos_clock(model, mean_len=15.0):
+    """Random-init models never emit <eos>; synthetic.install_eos_clock rewires one hidden unit into a clock so that
+    hypotheses end after ≈ mean_len tokens like a trained model's."""
+    from vag_nmt_b200 import ops, synthetic
+    synthetic.install_eos_clock(model, mean_len)
+    ops.invalidate_prepared()
+    return model
+
+
+def test_early_stop_tokens_steps_and_time():
+    from oracle import vag_oracle as O
+    from vag_nmt_b200 import ops, synthetic
+    cfg = dict(synthetic.DE)
+    model = _eos_clock(build_mm(cfg, 1234).cuda().eval())
+    b = synthetic.make_batch(160, cfg["src_size"], cfg["tgt_size"], cfg["im_feats_size"], seed=31)
+    L = 80
+    w, ctx, mask, keys, h0, _, _ = model._prepare(b.src, b.src_lengths, b.im)
+    outs = {}
+    for early in (True, False):
+        hyp, hyp_len, beam, nll, steps = ops.beam_decode(w, h0, keys, ctx, mask, 12, L, debug=True, early_stop=early)
+        outs[early] = (hyp.cpu(), hyp_len.cpu(), int(steps))
+    assert torch.equal(outs[True][0], outs[False][0]) and torch.equal(outs[True][1], outs[False][1])
+    s = outs[True][2]
+    assert s == outs[False][2] and 10 <= s < L // 2, s           # the search really ended early (≈ 16 of 80 steps)
+    # token-exact against the oracle, which breaks out of its loop like the reference
+    got = model.beamsearch_decode(b.src[:24], b.src_lengths[:24], b.im[:24], beam_size=12, max_length=L)
+    with torch.no_grad():
+        want = O.multimodal_beamsearch_decode(cpu_params(model), b.src[:24], b.src_lengths[:24], b.im[:24], 12, L)
+    assert got == want
+
+    def timed(fn, n=5):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / n
+    t_poll = timed(lambda: ops.beam_decode(w, h0, keys, ctx, mask, 12, L, early_stop=True))
+    t_flag = timed(lambda: ops.beam_decode(w, h0, keys, ctx, mask, 12, L, early_stop=False))
+    # the same search forced through all L steps (no clock) for scale
+    full = build_mm(cfg, 1234).cuda().eval()
+    wf, ctxf, maskf, keysf, h0f, _, _ = full._prepare(b.src, b.src_lengths, b.im)
+    t_full = timed(lambda: ops.beam_decode(wf, h0f, keysf, ctxf, maskf, 12, L, early_stop=True))
+    print(f"early stop after {s}/{L} steps: polled {t_poll * 1e3:.2f} ms, flag-only {t_flag * 1e3:.2f} ms, full search {t_full * 1e3:.2f} ms")
+    assert t_poll < 0.5 * t_full and t_flag < 0.6 * t_full      # time follows steps_run, not max_length
+
+
+def test_reference_batching_graph_replay_and_prepared_cache(monkeypatch):
+    """1-batch decode == eval batches of 16 (graph-replayed) == eager batches of 16, and the cached invariants follow the weights."""
+    from oracle import vag_oracle as O
+    from vag_nmt_b200 import ops, synthetic
+    from vag_nmt_b200.translate import decode_corpus
+    cfg = dict(synthetic.DE)
+    model = build_mm(cfg, 1234).cuda().eval()
+    sents, im = synthetic.make_corpus(70, cfg["src_size"], cfg["im_feats_size"], seed=17)
+    fn = lambda s, l, i, K, L: model.beamsearch_decode(s, l, i, beam_size=K, max_length=L)
+    one = decode_corpus(fn, sents, im, 12, 16)
+    ref16 = decode_corpus(fn, sents, im, 12, 16, batch_size=16)          # graphs captured
+    again = decode_corpus(fn, sents, im, 12, 16, batch_size=16)          # graphs replayed
+    monkeypatch.setenv("VAG_DECODE_GRAPH", "0")
+    eager16 = decode_corpus(fn, sents, im, 12, 16, batch_size=16)
+    monkeypatch.delenv("VAG_DECODE_GRAPH")
+    assert one == ref16 == again == eager16
+    assert len(model._decode_graphs) >= 1
+    with torch.no_grad():
+        src, lens, im_s, order = synthetic.pad_and_sort(sents[:16], im[:16])
+        want = O.multimodal_beamsearch_decode(cpu_params(model), src, lens, im_s, 12, 16)
+    assert [one[c] for c in order] == want
+    # weights change (in place, version bump) → the invariants are rebuilt, stale graphs dropped
+    with torch.no_grad():
+        model.decoder.gru_2.weight_hh_l0.mul_(1.5)
+        model.decoder.out.bias[7] += 3.0
+    changed = decode_corpus(fn, sents[:16], im[:16], 12, 16, batch_size=16)
+    fresh = build_mm(cfg, 1234)
+    fresh.load_state_dict({k: v.detach().cpu() for k, v in model.state_dict().items()})
+    fresh = fresh.cuda().eval()
+    assert changed == decode_corpus(lambda s, l, i, K, L: fresh.beamsearch_decode(s, l, i, beam_size=K, max_length=L), sents[:16], im[:16], 12, 16)
+    assert changed != one[:16]
+    # … and through the raw-pointer optimiser update (no version bump: ClipAdam invalidates explicitly)
+    from vag_nmt_b200.optim import ClipAdam
+    from vag_nmt_b200.train import train_imagine_beam
+    import vag_nmt_b200 as vag
+    bt = synthetic.make_batch(8, cfg["src_size"], cfg["tgt_size"], cfg["im_feats_size"], seed=3)
+    wgt = torch.ones(cfg["tgt_size"], device="cuda")
+    wgt[0] = 0
+    before = model.beamsearch_decode(bt.src, bt.src_lengths, bt.im, beam_size=12, max_length=10)
+    train_imagine_beam(bt.src, bt.tgt, bt.im, bt.src_lengths, model, ClipAdam(model, lr=5e-2), torch.nn.NLLLoss(weight=wgt, reduction="none"),
+                       vag.PairwiseRankingLoss(margin=0.1), 0.99, 1.0)
+    model.eval()
+    after = model.beamsearch_decode(bt.src, bt.src_lengths, bt.im, beam_size=12, max_length=10)
+    with torch.no_grad():
+        want = O.multimodal_beamsearch_decode(cpu_params(model), bt.src, bt.src_lengths, bt.im, 12, 10)
+    assert after == want and after != before
+
+
+def test_beam_finalize_entry_point_matches_fused_loop():
+    """vag_beam_finalize_f32 on the histories of a debug decode reproduces that decode's hypotheses (V11:315-337)."""
+    import ctypes as C
+    from vag_nmt_b200 import _cabi, ops, synthetic
+    cfg = dict(synthetic.TINY)
+    model = build_mm(cfg, 5).cuda().eval()
+    b = synthetic.make_batch(7, cfg["src_size"], cfg["tgt_size"], cfg["im_feats_size"], seed=3, max_len=9, min_len=2, mean=5.0, std=2.5)
+    w, ctx, mask, keys, h0, _, _ = model._prepare(b.src, b.src_lengths, b.im)
+    K, L = 4, 11
+    hyp, hyp_len, beam, nll, steps = ops.beam_decode(w, h0, keys, ctx, mask, K, L, debug=True)
+    # rebuild (token, parent) histories from the back-traced beam is not possible in general; drive the selection by hand instead
+    B = ctx.shape[0]
+    tok_hist = torch.zeros(L, B, K, dtype=torch.int64, device="cuda")
+    par_hist = torch.zeros(L, B, K, dtype=torch.int32, device="cuda")
+    score = torch.zeros(B, K, device="cuda")
+    h = h0
+    tokens = torch.full((B,), 2, dtype=torch.int64, device="cuda")
+    for di in range(L):
+        rps = 1 if di == 0 else K
+        logp, h_new, _ = ops.decoder_step(w, tokens, h, keys, ctx, mask, rps, want_logp=True)
+        t, par = ops.beam_select(logp, None if di == 0 else tok_hist[di - 1], score, B, K, di)
+        tok_hist[di], par_hist[di] = t, par
+        idx = (torch.arange(B, device="cuda").unsqueeze(1) * rps + (par.long() if di > 0 else torch.zeros_like(par).long())).reshape(-1)
+        h = h_new[idx]
+        tokens = t.reshape(-1)
+    lib = _cabi.lib()
+    hyp2 = torch.empty(B, L, dtype=torch.int64, device="cuda")
+    len2 = torch.empty(B, dtype=torch.int32, device="cuda")
+    steps_dev = torch.tensor([L], dtype=torch.int32, device="cuda")
+    _cabi.check(lib.vag_beam_finalize_f32(tok_hist.data_ptr(), par_hist.data_ptr(), score.data_ptr(), steps_dev.data_ptr(), B, K, L,
+                                          hyp2.data_ptr(), len2.data_ptr(), None, _cabi.stream_ptr()))
+    assert int(steps) == L        # this tiny random model never finishes early
+    assert torch.equal(len2, hyp_len)
+    for r in range(B):
+        n = int(len2[r])
+        assert torch.equal(hyp2[r, :n], hyp[r, :n])

@@ -103,10 +103,53 @@ class _Seq2SeqBase(nn.Module):
                     cut.append(t)
                 out.append(cut)
             return out
-        hyp, hyp_len = ops.beam_decode(w, h0, keys, ctx, mask, beam_size, tgt_l)  # V11:229 → 233-337
+        hyp, hyp_len = self._beam_decode(w, h0, keys, ctx, mask, beam_size, tgt_l)  # V11:229 → 233-337
         rows = hyp.cpu().numpy()             # one device→host copy; numpy row slices convert ~2x faster than a whole-tensor tolist()
         lens = hyp_len.cpu().tolist()
         return [rows[b, :lens[b]].tolist() for b in range(B)]
+
+    # Small batches (the reference decodes in eval batches of 16, nmt_multimodal_beam_DE.py:542-547): 12 launches of a few µs per
+    # step are bound by launch latency, so the whole L-step loop of one (B, T, K, L) shape is captured in a CUDA graph once
+    # and replayed.  A captured loop cannot poll the host; its early stop is the kernels' own `done` test.
+    _GRAPH_ROWS_MAX = 2048
+    _GRAPH_CACHE_MAX = 48
+
+    def _beam_decode(self, w, h0, keys, ctx, mask, K, L):
+        import os
+        B, T, _ = ctx.shape
+        if B * K > self._GRAPH_ROWS_MAX or not w.prepared or os.environ.get("VAG_DECODE_GRAPH", "1") == "0" \
+                or torch.cuda.is_current_stream_capturing():
+            return ops.beam_decode(w, h0, keys, ctx, mask, K, L)
+        from collections import OrderedDict
+        cache = self.__dict__.setdefault("_decode_graphs", OrderedDict())
+        key = (B, T, K, L, w.precision, w.prepared, ops._weights_epoch)
+        st = cache.get(key)
+        if st is None:
+            for k in [k for k in cache if k[-1] != ops._weights_epoch]:     # graphs of an older weight set hold stale pointers
+                del cache[k]
+            while len(cache) >= self._GRAPH_CACHE_MAX:
+                cache.popitem(last=False)
+            dev = ctx.device
+            st = {"h0": h0.clone(), "keys": keys.clone(), "ctx": ctx.clone(), "mask": mask.clone()}
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):      # warm-up outside the capture: sizes the workspace, sets kernel attributes
+                ops.beam_decode(w, st["h0"], st["keys"], st["ctx"], st["mask"], K, L, early_stop=False)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                st["hyp"], st["hyp_len"] = ops.beam_decode(w, st["h0"], st["keys"], st["ctx"], st["mask"], K, L, early_stop=False)
+            st["graph"] = g
+            st["keepalive"] = (list(ops._workspaces.values()), getattr(w, "_keepalive", None))   # raw pointers inside the graph
+            cache[key] = st
+        else:
+            cache.move_to_end(key)
+        st["h0"].copy_(h0)
+        st["keys"].copy_(keys)
+        st["ctx"].copy_(ctx)
+        st["mask"].copy_(mask)
+        st["graph"].replay()
+        return st["hyp"], st["hyp_len"]      # static buffers: consume (or clone) before the next decode of this shape
 
     @_with_precision
     def decode_device(self, src_var, src_lengths, im_var=None, beam_size=12, max_length=80):
@@ -118,7 +161,8 @@ class _Seq2SeqBase(nn.Module):
             w, ctx, mask, keys, h0 = self._prepare(src_var, src_lengths)
         if beam_size == 1:
             return ops.greedy_decode(w, h0, keys, ctx, mask, max_length), None
-        return ops.beam_decode(w, h0, keys, ctx, mask, beam_size, max_length)
+        hyp, hyp_len = self._beam_decode(w, h0, keys, ctx, mask, beam_size, max_length)
+        return hyp.clone(), hyp_len.clone()
 
     # -- training path (autograd through hand-written backward kernels) ------------------------------------
     def _wants_grad(self) -> bool:

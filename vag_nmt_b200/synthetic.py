@@ -120,3 +120,40 @@ def dropout_masks(seed: int, B: int, Ts: int, Tt: int, src_emb: int, hidden: int
     if p_out > 0:
         out["out"] = draw((Tt * B, tgt_emb), p_out)
     return out
+
+
+def install_eos_clock(model, mean_len: float = 15.0, gain: float = 8.0, slope: float = 3.0) -> None:
+    """Make a RANDOM-INIT model end its hypotheses after ≈ mean_len tokens, the way a trained Multi30K model does (targets average
+    ≈ 14 tokens) — random-init weights never emit <eos>, so without this every decode runs max_length
+    steps and the early stop (V11:265-269) cannot be measured.  One hidden unit j = H-1 of the decoder is rewired into a clock:
+      h0_j = -0.9 (decoderini row j), gru_1 passes it through (z_j ≈ 1), gru_2 leaks it towards 1 (h' = ε + (1-ε)·h),
+      read-out channel d = E-1 is tanh(slope·h_j) and only <eos> (id 3) reads that channel with weight `gain`.
+    The <eos> logit so rises by ≈ gain·slope·ε per step and overtakes the random logits of the other tokens around step mean_len.
+    Everything else keeps its random initialisation; the oracle sees the same state_dict, so parity checks still apply."""
+    import math
+    dec = model.decoder
+    H, E = dec.hidden_size, dec.embedding_size
+    j, d = H - 1, E - 1
+    # crossing level of the clock: <eos> wins once gain·tanh(slope·h) ≈ 1.3 (measured transition of the random logits)
+    h_cross = math.atanh(min(1.3 / gain, 0.99)) / slope
+    eps = 1.0 - ((1.0 - h_cross) / 1.9) ** (1.0 / mean_len)
+    with torch.no_grad():
+        model.decoderini.weight[j].zero_()
+        model.decoderini.bias[j] = math.atanh(-0.9)
+        for gru, z_bias, n_bias in ((dec.gru_1, 20.0, 0.0), (dec.gru_2, math.log((1.0 - eps) / eps), 4.0)):
+            for base in (0, H, 2 * H):                         # rows r_j, z_j, n_j see no input and no state
+                gru.weight_ih_l0[base + j].zero_()
+                gru.weight_hh_l0[base + j].zero_()
+                gru.bias_ih_l0[base + j] = 0.0
+                gru.bias_hh_l0[base + j] = 0.0
+            gru.bias_ih_l0[H + j] = z_bias                     # z_j = σ(z_bias)
+            gru.bias_ih_l0[2 * H + j] = n_bias                 # n_j = tanh(n_bias)
+        for lin in (dec.W1, dec.W2, dec.W3):                   # read-out channel d = tanh(slope·h2_j)
+            lin.weight[d].zero_()
+            lin.bias[d] = 0.0
+        dec.W1.weight[d, j] = slope
+        dec.embedding.weight[:, d] = 0.0                       # tied with out.weight: only <eos> reads channel d
+        dec.embedding.weight[3, d] = gain
+        if dec.out.weight.data_ptr() != dec.embedding.weight.data_ptr():
+            dec.out.weight[:, d] = 0.0
+            dec.out.weight[3, d] = gain
