@@ -23,20 +23,30 @@ def test_bucket_sampler_reproduces_reference_schedules():
                 assert len({case["lengths"][i] for i in b}) == 1
 
 
-def test_bucket_sampler_rank_sharding_covers_every_batch_with_equal_step_counts():
+def test_bucket_sampler_data_parallel_equal_slices_of_global_batches():
+    """Data-parallel mode: every rank runs the same number of steps with the SAME local batch size at every step (what the
+    global-batch ranking loss and the averaging gradient all-reduce need), one target length per global batch, no sample twice,
+    and at most world-1 samples of each bucket dropped per epoch."""
     from vag_nmt_b200.data import BucketBatchSampler
     lengths = [int(x) for x in np.random.RandomState(5).randint(4, 20, size=333)]
-    world = 4
-    per_rank = []
-    for r in range(world):
-        np.random.seed(9)
-        per_rank.append([tuple(int(i) for i in b) for b in BucketBatchSampler(lengths, 16, world_size=world, rank=r)])
-    np.random.seed(9)
-    full = [tuple(int(i) for i in b) for b in BucketBatchSampler(lengths, 16)]
-    assert len({len(p) for p in per_rank}) == 1
-    seen = set(b for p in per_rank for b in p)
-    assert seen == set(full)
-    assert sum(len(p) for p in per_rank) - len(full) < world      # only the wrap-around padding is duplicated
+    world, bs = 4, 16
+    per_rank = [[[int(i) for i in b] for b in BucketBatchSampler(lengths, bs, world_size=world, rank=r, seed=9)] for r in range(world)]
+    assert len({len(p) for p in per_rank}) == 1 and len(per_rank[0]) == len(BucketBatchSampler(lengths, bs, world_size=world, rank=0, seed=9))
+    for step in range(len(per_rank[0])):
+        sizes = {len(per_rank[r][step]) for r in range(world)}
+        assert len(sizes) == 1 and 1 <= next(iter(sizes)) <= bs               # equal local batch on every rank
+        assert len({lengths[i] for r in range(world) for i in per_rank[r][step]}) == 1
+    seen = [i for p in per_rank for b in p for i in b]
+    assert len(seen) == len(set(seen))
+    n_buckets = len(set(lengths))
+    n_batches = sum(-(-lengths.count(n) // (bs * world)) for n in set(lengths))
+    assert len(lengths) - len(seen) <= (world - 1) * n_batches and n_buckets > 0
+    # the private RandomState advances per epoch and never touches the global numpy RNG the reference sampler uses
+    np.random.seed(1)
+    before = np.random.get_state()[1].copy()
+    s0 = BucketBatchSampler(lengths, bs, world_size=world, rank=0, seed=9)
+    e1, e2 = [list(map(int, b)) for b in s0], [list(map(int, b)) for b in s0]
+    assert e1 != e2 and (np.random.get_state()[1] == before).all()
 
 
 def test_train_generator_pads_sorts_and_keeps_rows_together():

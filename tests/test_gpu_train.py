@@ -339,3 +339,44 @@ def test_graphed_step_draws_fresh_dropout_masks_on_every_replay():
     assert len(stepper._graphs) == 1
     assert all(torch.isfinite(torch.tensor(losses)))
     assert len({round(v, 6) for v in losses}) >= 4, losses
+
+
+def test_flat_gradient_buffer_shared_by_all_graphs_and_lru_eviction():
+    """ClipAdam keeps ONE persistent flat gradient buffer: the backward kernels write into it (no autograd copy), every captured
+    graph of GraphedTrainStep uses the same addresses (nothing per graph but activations), the graph cache evicts least-recently
+    used shapes, and an evicted shape is captured again with identical results."""
+    import vag_nmt_b200 as vag
+    from vag_nmt_b200 import synthetic
+    from vag_nmt_b200.optim import ClipAdam
+    from vag_nmt_b200.train import GraphedTrainStep, train_imagine_beam
+    cfg = dict(synthetic.TINY)
+    w = torch.ones(cfg["tgt_size"], device="cuda")
+    w[0] = 0
+    crit = torch.nn.NLLLoss(weight=w, reduction="none")
+    cv = vag.PairwiseRankingLoss(margin=0.1)
+    mk = lambda seed, n: synthetic.make_batch(n, cfg["src_size"], cfg["tgt_size"], cfg["im_feats_size"], seed=seed, max_len=9, min_len=2,
+                                              mean=5.0, std=2.5)
+    batches = [mk(41, 6), mk(42, 5), mk(43, 4), mk(41, 6)]       # three shapes, the first one again at the end
+    results = {}
+    for mode in ("eager", "graph"):
+        model = build_mm(cfg, 77).cuda()
+        opt = ClipAdam(model, lr=1e-2)
+        stepper = GraphedTrainStep(model, opt, crit, cv, clip=1.0, enabled=(mode == "graph"), max_graphs=2)
+        losses = []
+        for bt in batches:
+            if mode == "eager":
+                losses.append(train_imagine_beam(bt.src, bt.tgt, bt.im, bt.src_lengths, model, opt, crit, cv, 0.99, 1.0)[0])
+            else:
+                losses.append(float(stepper.step(bt.src, bt.src_lengths, bt.tgt, bt.im, 1.0)[0]))
+            assert opt.grads_in_place, "a gradient was produced outside the flat buffer and had to be copied"
+        base, size = opt._flat.data_ptr(), opt._flat.numel() * 4
+        for p in model.parameters():
+            assert base <= p.grad.data_ptr() < base + size
+        if mode == "graph":
+            assert len(stepper._graphs) == 2                      # LRU: three shapes seen, two kept
+            ptrs = [[g.data_ptr() for _, g in st["grads"]] for st in stepper._graphs.values()]
+            assert ptrs[0] == ptrs[1]                             # both graphs write the same gradient addresses
+        results[mode] = (losses, torch.cat([p.detach().reshape(-1) for p in model.parameters()]).cpu())
+    for a, b in zip(results["eager"][0], results["graph"][0]):
+        assert abs(a - b) < 1e-5 * abs(a)
+    assert float((results["eager"][1] - results["graph"][1]).abs().max()) < 1e-5

@@ -52,6 +52,27 @@ def _lin(x, w, b=None, flags=0, out=None):
     return ops.linear(x, w, b, flags, out)
 
 
+# Where parameter gradients are written.  By default every backward allocates its outputs; an optimiser that keeps ONE persistent
+# flat gradient buffer (optim.ClipAdam) installs a sink mapping a parameter to its slice of that buffer, so that the backward
+# kernels write the gradients in place: no torch.cat before the data-parallel all-reduce, no copy back after it, and every captured
+# CUDA graph of the step writes to the same addresses instead of pinning a private 64 MB gradient set in its pool.
+_grad_sink = None
+
+
+def set_grad_sink(fn) -> None:
+    global _grad_sink
+    _grad_sink = fn
+
+
+def _gbuf(p: torch.Tensor) -> torch.Tensor:
+    """Uninitialised buffer for the gradient of parameter `p` (the backward kernels overwrite every element)."""
+    if _grad_sink is not None:
+        v = _grad_sink(p)
+        if v is not None:
+            return v
+    return torch.empty_like(p)
+
+
 def _zeros(*shape, like):
     return torch.zeros(*shape, dtype=torch.float32, device=like.device)
 
@@ -117,8 +138,8 @@ class EncoderFn(torch.autograd.Function):
         for d in range(2):
             w.w_ih[d], w.w_hh[d] = ops._p(gru[4 * d].detach()), ops._p(gru[4 * d + 1].detach())
             w.b_ih[d], w.b_hh[d] = ops._p(gru[4 * d + 2].detach()), ops._p(gru[4 * d + 3].detach())
-        demb = torch.empty_like(emb)
-        grads = [torch.empty_like(p) for p in gru]
+        demb = _gbuf(emb)
+        grads = [_gbuf(p) for p in gru]
         arr = lambda idx: (C.c_void_p * 2)(grads[idx].data_ptr(), grads[4 + idx].data_ptr())
         ws = ops.workspace(lib.vag_encoder_train_workspace_bytes(B, Tn, E, H), dev)
         with on_device(dev):
@@ -172,6 +193,7 @@ class VsePoolFn(torch.autograd.Function):
         fctx.save_for_backward(im, ctx, mask, a_im, im_emb, iq, pk, beta, ctx_vec, a_txt, im_w, txt_w, ctx2ctx_w, emb2ctx_w,
                                mlp_w if mlp_w is not None else im_b)
         fctx.meta = (mode, activation, mlp_w is not None)
+        fctx.bias_refs = (im_b, txt_b)      # only their identity is needed (gradient sink lookup)
         return im_emb, txt_emb, ctx_vec
 
     @staticmethod
@@ -184,8 +206,8 @@ class VsePoolFn(torch.autograd.Function):
         du_t = T.l2norm_bwd(d_txt_emb, a_txt)
         if activation:
             du_t = T.tanh_bwd(du_t, a_txt)
-        d_txt_w = T.gemm(du_t, ctx_vec, trans_a=True)
-        d_txt_b = T.colsum(du_t)
+        d_txt_w = T.gemm(du_t, ctx_vec, trans_a=True, out=_gbuf(txt_w))
+        d_txt_b = T.colsum(du_t, out=_gbuf(fctx.bias_refs[1]))
         dcv = d_ctx_vec.contiguous().clone()
         T.gemm(du_t, txt_w, out=dcv, beta=1.0)
         # pooling attention
@@ -194,16 +216,16 @@ class VsePoolFn(torch.autograd.Function):
         dv = _zeros(C, like=ctx) if has_mlp else None
         d_iq = T.attention_bwd(dcv, beta, iq, pk, ctx, mlp_w.reshape(-1) if has_mlp else None, mask, dpk, dctx, dv, mode)
         T.gemm(dpk.view(B * Tn, C), ctx2ctx_w, out=dctx.view(B * Tn, C), beta=1.0)
-        d_ctx2ctx = T.gemm(dpk.view(B * Tn, C), ctx.view(B * Tn, C), trans_a=True)
-        d_emb2ctx = T.gemm(d_iq, im_emb, trans_a=True)
+        d_ctx2ctx = T.gemm(dpk.view(B * Tn, C), ctx.view(B * Tn, C), trans_a=True, out=_gbuf(ctx2ctx_w))
+        d_emb2ctx = T.gemm(d_iq, im_emb, trans_a=True, out=_gbuf(emb2ctx_w))
         # image branch
         d_ie = d_im_emb.contiguous().clone()
         T.gemm(d_iq, emb2ctx_w, out=d_ie, beta=1.0)
         du_i = T.l2norm_bwd(d_ie, a_im)
         if activation:
             du_i = T.tanh_bwd(du_i, a_im)
-        d_im_w = T.gemm(du_i, im, trans_a=True)
-        d_im_b = T.colsum(du_i)
+        d_im_w = T.gemm(du_i, im, trans_a=True, out=_gbuf(im_w))
+        d_im_b = T.colsum(du_i, out=_gbuf(fctx.bias_refs[0]))
         d_mlp = dv.view(1, C) if has_mlp else None
         return None, dctx, None, None, None, d_im_w, d_im_b, d_txt_w, d_txt_b, d_ctx2ctx, d_emb2ctx, d_mlp
 
@@ -224,6 +246,7 @@ class DecoderInitFn(torch.autograd.Function):
         h0 = _lin(z, ini_w, ini_b, ops.LIN_TANH)
         fctx.save_for_backward(z, h0, mask, ini_w)
         fctx.meta = (float(split), ctx_vec is not None, (B, Tn, C))
+        fctx.bias_ref = ini_b
         return h0
 
     @staticmethod
@@ -232,8 +255,8 @@ class DecoderInitFn(torch.autograd.Function):
         z, h0, mask, ini_w = fctx.saved_tensors
         split, has_vec, (B, Tn, C) = fctx.meta
         du = T.tanh_bwd(dh0, h0)
-        d_w = T.gemm(du, z, trans_a=True)
-        d_b = T.colsum(du)
+        d_w = T.gemm(du, z, trans_a=True, out=_gbuf(ini_w))
+        d_b = T.colsum(du, out=_gbuf(fctx.bias_ref))
         dz = T.gemm(du, ini_w)
         dctx = _zeros(B, Tn, C, like=z)
         dvec = T.init_mix_bwd(dz, mask, split, dctx, has_vec)
@@ -316,7 +339,7 @@ class DecoderSeqFn(torch.autograd.Function):
         saved.ld_logits = ldl
         for k, o in offs.items():
             setattr(saved, k, store.data_ptr() + 4 * o)
-        grads = [torch.empty_like(p) for p in params]
+        grads = [_gbuf(p) if not (tied and i == 19) else torch.empty(0, device=p.device) for i, p in enumerate(params)]
         g = DecoderGrads()
         for name, t in zip(_PARAM_FIELDS, grads):
             setattr(g, name, t.data_ptr())

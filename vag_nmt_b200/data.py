@@ -4,9 +4,9 @@
   training batch has a single target length and the teacher-forced loop carries no padding.  Same constructor, same
   ``__iter__`` / ``__len__`` contract and the same numpy-RNG call sequence (one permutation per bucket in insertion
   order, then one permutation of the bucket schedule), hence the same batches as the reference under the same
-  ``np.random.seed``.  Extension for one-process-per-GPU data parallelism: ``world_size`` / ``rank`` deal the epoch's
-  batch schedule round-robin, padded by wrap-around so every rank runs the same number of steps (the gradient all-reduce
-  needs that).
+  ``np.random.seed``.  Extension for one-process-per-GPU data parallelism: ``world_size`` / ``rank`` cut every GLOBAL batch
+  (``batch_size · world_size`` samples of one bucket) into equal per-rank slices, so all ranks run the same number of steps with
+  the same local batch size (the ranking-loss all-gather and the gradient all-reduce need that).
 * ``data_generator_tl_mtv`` / ``data_generator_mtv`` — the batch builders of preprocessing.py:308-384 / :234-306: pad with
   0, sort the batch by source length (descending, reference tie order), reorder targets and image rows alike.  Batches are
   built in pinned host memory and copied asynchronously to the device.
@@ -23,9 +23,19 @@ PAD_token = 0
 
 
 class BucketBatchSampler:
-    """samplers/bucket.py:10-103.  ``lengths[i]`` is the target length of sample i."""
+    """samplers/bucket.py:10-103.  ``lengths[i]`` is the target length of sample i.
 
-    def __init__(self, lengths: Sequence[int], batch_size: int, max_len: Optional[int] = None, world_size: int = 1, rank: int = 0):
+    Data-parallel extension (``world_size`` > 1, one process per GPU): ``batch_size`` stays the PER-RANK batch.  The epoch's schedule
+    is drawn over GLOBAL batches of ``batch_size · world_size`` samples of one bucket and every global batch is cut into
+    ``world_size`` equal contiguous slices — every rank runs the same number of steps with the SAME local batch size, which the
+    global-batch ranking loss (all-gather of [B_local, S] blocks) and the averaging gradient all-reduce both require.  A bucket's
+    remainder that does not divide by ``world_size`` loses its last ``n mod world_size`` samples for that epoch (a remainder smaller
+    than ``world_size`` is skipped by every rank).  All ranks must draw the same schedule: pass the same ``seed`` everywhere
+    (a private ``RandomState`` advanced once per epoch); without a seed the global numpy RNG is used like the reference does, which
+    is only correct when every rank seeded it identically."""
+
+    def __init__(self, lengths: Sequence[int], batch_size: int, max_len: Optional[int] = None, world_size: int = 1, rank: int = 0,
+                 seed: Optional[int] = None):
         if batch_size < 1:
             raise ValueError("batch_size must be positive")
         if not (0 <= rank < world_size):
@@ -33,6 +43,7 @@ class BucketBatchSampler:
         self.batch_size = int(batch_size)
         self.max_len = 10000 if max_len is None else max_len
         self.world_size, self.rank = int(world_size), int(rank)
+        self._rng = np.random.RandomState(seed) if seed is not None else None
         members = {}                                   # length -> sample indices, in first-seen order (dict keeps insertion order)
         for idx, n in enumerate(lengths):
             n = int(n)
@@ -40,19 +51,25 @@ class BucketBatchSampler:
                 members.setdefault(n, []).append(idx)
         self.buckets = {n: np.asarray(ix) for n, ix in members.items()}
         self.bucket_names = list(self.buckets)
+        self._draw = self.batch_size * self.world_size  # samples per (global) batch
         schedule: List[int] = []                        # one entry per batch: the bucket it is drawn from
         for n, ix in self.buckets.items():
-            schedule.extend([n] * math.ceil(ix.size / self.batch_size))
+            schedule.extend([n] * math.ceil(ix.size / self._draw))
         self.bucket_idxs = np.asarray(schedule)
-        self.n_batches = len(schedule)
+        if self.world_size == 1:
+            self.n_batches = len(schedule)
+        else:   # global batches that still hold at least one sample per rank
+            self.n_batches = sum(1 for n, ix in self.buckets.items() for k in range(math.ceil(ix.size / self._draw))
+                                 if min(self._draw, ix.size - k * self._draw) >= self.world_size)
 
     def _epoch(self) -> List[np.ndarray]:
-        views = {n: np.random.permutation(len(ix)) for n, ix in self.buckets.items()}     # bucket.py:80-83
+        rng = self._rng if self._rng is not None else np.random
+        views = {n: rng.permutation(len(ix)) for n, ix in self.buckets.items()}     # bucket.py:80-83
         cursor = dict.fromkeys(self.buckets, 0)
         out = []
-        for n in np.random.permutation(self.bucket_idxs):                                   # bucket.py:87
+        for n in rng.permutation(self.bucket_idxs):                                   # bucket.py:87
             n = int(n)
-            pick = views[n][cursor[n]: cursor[n] + self.batch_size]
+            pick = views[n][cursor[n]: cursor[n] + self._draw]
             cursor[n] += len(pick)
             out.append(self.buckets[n][pick])
         return out
@@ -62,12 +79,14 @@ class BucketBatchSampler:
         if self.world_size == 1:
             yield from batches
             return
-        steps = math.ceil(len(batches) / self.world_size)
-        for s in range(steps):
-            yield batches[(s * self.world_size + self.rank) % len(batches)]
+        for g in batches:
+            per = len(g) // self.world_size
+            if per == 0:
+                continue
+            yield g[self.rank * per:(self.rank + 1) * per]
 
     def __len__(self) -> int:
-        return self.n_batches if self.world_size == 1 else math.ceil(self.n_batches / self.world_size)
+        return self.n_batches
 
 
 def _pad(rows: List[List[int]], width: int) -> torch.Tensor:
@@ -90,9 +109,9 @@ def _sort_desc(lengths: List[int]) -> List[int]:
     return [int(i) for i in reversed(np.argsort(lengths))]
 
 
-def data_generator_tl_mtv(data_pairs, data_im, batch_size: int, device=None, world_size: int = 1, rank: int = 0):
+def data_generator_tl_mtv(data_pairs, data_im, batch_size: int, device=None, world_size: int = 1, rank: int = 0, seed: Optional[int] = None):
     """preprocessing.py:308-384 → (batch_x [B,Lx], batch_y [B,Ly], batch_im [B,I] float32, x_lengths desc, y_lengths)."""
-    sampler = BucketBatchSampler([len(p[1]) for p in data_pairs], batch_size, world_size=world_size, rank=rank)
+    sampler = BucketBatchSampler([len(p[1]) for p in data_pairs], batch_size, world_size=world_size, rank=rank, seed=seed)
     for bidx in sampler:
         xs = [list(data_pairs[i][0]) for i in bidx]
         ys = [list(data_pairs[i][1]) for i in bidx]

@@ -22,24 +22,33 @@ def named_param_groups(model: torch.nn.Module, weight_decay: float = 1e-5) -> Li
             {"params": [p for n, p in named if "bias" in n], "weight_decay": 0.0}]
 
 
-def allreduce_gradients(params: Iterable[torch.nn.Parameter], group=None) -> None:
-    """Average the gradients over the data-parallel ranks with ONE NCCL all-reduce of a flat bucket."""
+def allreduce_gradients(params: Iterable[torch.nn.Parameter], group=None, flat: Optional[torch.Tensor] = None) -> None:
+    """Average the gradients over the data-parallel ranks with ONE NCCL all-reduce.  `flat`: the persistent flat buffer the
+    gradients are views of (ClipAdam keeps one) — reduced in place, no gather / scatter passes.  Without it the gradients are
+    concatenated into a temporary bucket and copied back."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    world = dist.get_world_size(group)
+
+    def reduce_(t):
+        if dist.get_backend(group) == "nccl":
+            dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group)   # NCCL averages inside the collective: no extra pass over 64 MB
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            t.mul_(1.0 / world)
+
+    if flat is not None:
+        reduce_(flat)
         return
     grads = [p.grad for p in params if p.grad is not None]
     if not grads:
         return
-    world = dist.get_world_size(group)
-    flat = torch.cat([g.reshape(-1) for g in grads])              # one launch
-    if dist.get_backend(group) == "nccl":
-        dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)  # NCCL averages inside the collective: no extra pass over 64 MB
-    else:
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        flat.mul_(1.0 / world)
+    bucket = torch.cat([g.reshape(-1) for g in grads])             # one launch
+    reduce_(bucket)
     views, off = [], 0
     for g in grads:
-        views.append(flat[off:off + g.numel()].view_as(g))
+        views.append(bucket[off:off + g.numel()].view_as(g))
         off += g.numel()
     torch._foreach_copy_(grads, views)                            # multi-tensor copy back: a couple of launches, not one per tensor
 
@@ -60,11 +69,43 @@ class ClipAdam:
         self.state = {}
         self.step_count = 0
         self._sumsq: Optional[torch.Tensor] = None
+        self._flat: Optional[torch.Tensor] = None     # ONE persistent gradient buffer; every p.grad is a view of it
+        self._offsets = {}                            # param data_ptr → (element offset, numel)
+
+    # -- persistent flat gradient buffer ------------------------------------------------------------------------------------
+    def _ensure_flat(self) -> bool:
+        params = self._all_params()
+        if not params or not params[0].is_cuda:
+            return False
+        key = tuple(p.data_ptr() for p in params)
+        if self._flat is not None and self._flat_key == key:
+            return True
+        off, offsets = 0, {}
+        for p in params:
+            if p.data_ptr() in offsets:               # a tensor registered twice (tied weights): one slice
+                continue
+            offsets[p.data_ptr()] = (off, p.numel())
+            off += (p.numel() + 3) // 4 * 4           # 16-byte aligned slices (vector loads in the optimiser kernels)
+        self._flat = torch.zeros(off, dtype=torch.float32, device=params[0].device)
+        self._offsets, self._flat_key = offsets, key
+        self._table_key = None
+        return True
+
+    def _grad_view(self, p: torch.Tensor) -> Optional[torch.Tensor]:
+        """A FRESH view of p's slice (autograd adopts an incoming gradient as p.grad without a copy only when nothing else holds
+        the tensor object)."""
+        hit = self._offsets.get(p.data_ptr())
+        if hit is None or self._flat is None:
+            return None
+        return self._flat[hit[0]:hit[0] + hit[1]].view(p.shape)
 
     def zero_grad(self) -> None:
         for g in self.param_groups:
             for p in g["params"]:
                 p.grad = None
+        if self._ensure_flat():
+            from . import autograd
+            autograd.set_grad_sink(self._grad_view)   # the backward kernels of the next pass write straight into the flat buffer
 
     def _all_params(self):
         return [p for g in self.param_groups for p in g["params"]]
@@ -74,7 +115,22 @@ class ClipAdam:
         """→ device scalar Σ‖g‖² BEFORE clipping (sqrt of it is what clip_grad_norm_ returns)."""
         clip = self.clip if clip is None else clip
         params = [p for p in self._all_params() if p.grad is not None]
-        allreduce_gradients(params, self.group)       # data parallel: clip must see the GLOBAL gradient
+        flat = None
+        if self._ensure_flat():
+            # gradients that did not land in the flat buffer (a backward outside autograd.py's Functions, an accumulated or cloned
+            # gradient) are moved there now; the common case finds every p.grad already in place
+            base, in_place = self._flat.data_ptr(), True
+            for p in params:
+                off, n = self._offsets[p.data_ptr()]
+                if p.grad.data_ptr() != base + 4 * off or not p.grad.is_contiguous():
+                    view = self._grad_view(p)
+                    view.copy_(p.grad)
+                    p.grad = view
+                    in_place = False
+            self.grads_in_place = in_place            # diagnostic (tests / bench)
+            if len(params) == len({p.data_ptr() for p in self._all_params()}):
+                flat = self._flat                     # every parameter has a gradient: reduce the whole buffer in place
+        allreduce_gradients(params, self.group, flat)  # data parallel: clip must see the GLOBAL gradient
         dev = params[0].device
         if self._sumsq is None or self._sumsq.device != dev:
             self._sumsq = torch.zeros(1, dtype=torch.float32, device=dev)

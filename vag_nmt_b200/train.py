@@ -43,6 +43,25 @@ def train_imagine_beam(input_variable, target_variable, im_variable, input_lengt
     return loss.item(), loss_mt.item(), loss_vse.item() if torch.is_tensor(loss_vse) else loss_vse
 
 
+_checked_sizes = {}
+
+
+def _check_equal_local_batch(Bl: int, group) -> None:
+    """The all-gather below sizes its output as world·B_local and the averaging gradient all-reduce weights every rank equally:
+    both are only right when all ranks hold the same number of sentences (data.BucketBatchSampler's data-parallel mode guarantees
+    it).  Checked with one small collective the first time each local size is seen, then cached."""
+    import torch.distributed as dist
+    key = (id(group), Bl)
+    if key in _checked_sizes:
+        return
+    sizes = [None] * dist.get_world_size(group)
+    dist.all_gather_object(sizes, Bl, group=group)
+    if len(set(sizes)) != 1:
+        raise RuntimeError(f"data-parallel ranks hold different local batch sizes {sizes}: the global-batch ranking loss and the "
+                           "averaging gradient all-reduce need equal slices (use data.BucketBatchSampler(world_size=…, seed=…))")
+    _checked_sizes[key] = True
+
+
 class _GlobalRankLossFn(torch.autograd.Function):
     """Ranking loss over the GLOBAL batch under data parallelism: all-gather the local
     [B_local, S] embeddings, evaluate the full [B, B] hinge on every rank, keep the gradient rows of the local slice.
@@ -54,6 +73,7 @@ class _GlobalRankLossFn(torch.autograd.Function):
         from . import ops
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         Bl = im.shape[0]
+        _check_equal_local_batch(Bl, group)
         im_all = torch.empty(world * Bl, im.shape[1], dtype=im.dtype, device=im.device)
         s_all = torch.empty_like(im_all)
         dist.all_gather_into_tensor(im_all, im.detach().contiguous(), group=group)
@@ -115,11 +135,18 @@ class GraphedTrainStep:
     model) and returns device scalars (loss, loss_mt, loss_vse) — no host synchronisation.
     """
 
-    def __init__(self, model, optimizer: ClipAdam, criterion_mt, criterion_vse=None, clip: float = CLIP, enabled: Optional[bool] = None):
+    def __init__(self, model, optimizer: ClipAdam, criterion_mt, criterion_vse=None, clip: float = CLIP, enabled: Optional[bool] = None,
+                 max_graphs: int = 64):
+        from collections import OrderedDict
         self.model, self.optimizer = model, optimizer
         self.criterion_mt, self.criterion_vse = criterion_mt, criterion_vse
         self.clip = clip
-        self._graphs: Dict[tuple, dict] = {}
+        # One graph per batch shape, least-recently-used eviction beyond `max_graphs` (Multi30K's bucketed batches produce a few
+        # hundred (Ts, Tt) pairs; an evicted shape is simply captured again).  The gradients are NOT part of a graph's private
+        # memory: ClipAdam owns one persistent flat gradient buffer and the backward kernels write into it (autograd.set_grad_sink),
+        # so every graph shares the same 64 MB and only the step's activations live in the graphs' pool.
+        self.max_graphs = int(max_graphs)
+        self._graphs: "OrderedDict[tuple, dict]" = OrderedDict()
         self._pool = None
         self.enabled = True if enabled is None else enabled
         # Data parallel with the global-batch ranking loss: its all-gather must stay OUTSIDE the graphs (ranks capture
@@ -238,6 +265,7 @@ class GraphedTrainStep:
         world, rank = self._world, dist.get_rank(crit.group)
         im, s = st["im_emb"], st["txt_emb"]
         Bl = im.shape[0]
+        _check_equal_local_batch(Bl, crit.group)
         im_all = torch.empty(world * Bl, im.shape[1], dtype=im.dtype, device=im.device)
         s_all = torch.empty_like(im_all)
         dist.all_gather_into_tensor(im_all, im, group=crit.group)
@@ -263,8 +291,12 @@ class GraphedTrainStep:
             key = (tuple(src.shape), tuple(tgt.shape), is_teacher, im is not None, getattr(model, "precision", "fp32"))
             st = self._graphs.get(key)
             if st is None:
+                while len(self._graphs) >= self.max_graphs:
+                    self._graphs.popitem(last=False)          # least recently used shape; its memory returns to the shared pool
                 split = self._split and im is not None
                 st = (self._capture_split if split else self._capture)(key, to_dev(src), ls, to_dev(tgt), to_dev(im), ratio)
+            else:
+                self._graphs.move_to_end(key)
             # (pinned) host or device batch → the graph's static buffers; the lengths are recomputed from src inside the graph
             st["src"].copy_(src, non_blocking=True)
             st["tgt"].copy_(tgt, non_blocking=True)
