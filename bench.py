@@ -3,17 +3,24 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-One "step" = one pass of the hot path over one batch of synthetic input: every rank decodes ITS OWN 1000-sentence
-shard (weak scaling, no data-path collective — sentences are independent) with
-``model.beamsearch_decode`` at beam 12, max_length 80 (the reference's MAX_LENGTH), EN→DE shapes, FP32
+One "step" = one pass of the hot path over the SAME 1000 synthetic sentences: they are sorted by length and dealt round-robin to the
+N ranks (1000/N sentences per GPU — STRONG scaling, no data-path collective: sentences are independent), every
+rank decodes its share with ``model.beamsearch_decode`` at beam 12, max_length 80 (the reference's MAX_LENGTH), EN→DE shapes, FP32
 token-exact mode.  Prints ONE JSON line on rank 0 (contract in the task statement):
 
-  value     decoded sentences/s, inputs resident in HBM, CUDA-event timed, max over ranks
-  e2e       same metric through the public API with HOST (pinned) inputs and host token lists out
-  roofline  the dominant kernel (vocabulary-projection contraction) timed alone with CUDA events
-  cpu_baseline  the CPU oracle (a port of the reference's algorithm, reference batching 16) on a bounded sample
+  value          decoded sentences/s of the whole job, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e            same through the public API with HOST (pinned) inputs, host token lists out, and (N > 1) the all_gather_object of
+                 the translations that puts the full corpus on every rank
+  roofline       the dominant kernel (vocabulary-projection contraction) timed alone with CUDA events; roofline_bf16 the same launch
+                 in the bf16 mode against the UNDIVIDED measured peak; whole_step the job's algorithmic TFLOP/s in both modes
+  cpu_baseline   the CPU oracle (a port of the reference's algorithm, reference batching 16) on a bounded sample
+  decode_ref_batching   the same corpus in the reference's eval batches of 16 (nmt_multimodal_beam_DE.py:542-547), host inputs
+  decode_eos_clock      the same decode when hypotheses END after ≈ 15 tokens (synthetic.install_eos_clock): the early stop at work
+  reference_eager_b200  the reference's algorithm (oracle port) run with CUDA tensors through torch eager ops on this GPU
+  weak_scaling   (N > 1) every rank decoding its own 1000 sentences — labelled as such; dp_parity (N > 1) data-parallel correctness
+  train / train_f32 / train_fr / text_only   the second headline metric (training target tokens/s) and the other configs
 
-``--impl reference`` times that CPU port alone (rank 0 only), each step = one reference batch of 16 sentences.
+``--impl reference`` times the CPU port alone (rank 0 only), each step = one reference batch of 16 sentences.
 """
 from __future__ import annotations
 
@@ -175,12 +182,14 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, per_step):
+def workload_config(args, per_step, world=1):
     return {"workload": "VAG-NMT EN->DE beam-12 decoding of a 1000-sentence test-set shape (BASELINE configs[2])",
             "model": "NMT_AttentionImagine_Seq2Seq_Beam_V11 E256 H512 S512 I2048 V9391 random-init (seed 1234)",
-            "sentences_per_rank_per_step": per_step, "beam": args.beam, "max_length": args.max_length,
-            "src_len": "clip(round(N(14,4.5)),4,40)", "parallelism": f"dp{args.gpus} (sentence-sharded, no collective)",
-            "l2": "one bench step = 80 decoder steps over 12000 rows; the activations + summaries + weights each decoder step touches (~0.5 GB) exceed the 126 MB L2; no explicit flush"}
+            "sentences_per_step": per_step, "sentences_per_rank_per_step": -(-per_step // world), "beam": args.beam,
+            "max_length": args.max_length, "src_len": "clip(round(N(14,4.5)),4,40)",
+            "parallelism": f"dp{world}: the same {per_step} sentences sorted by length and dealt round-robin to the ranks, no data-path collective",
+            "l2": f"one bench step = {args.max_length} decoder steps over {-(-per_step // world) * args.beam} rows per GPU; the weights + activations + summaries a decoder "
+                  "step touches exceed the 126 MB L2 at 1-2 GPUs (0.5 GB at 12000 rows) and every step streams the 58 MB gru_1 table + 42 MB of weight planes; no explicit flush"}
 
 
 # ------------------------------------------------------------------------------------------ training step (second metric)
@@ -210,10 +219,21 @@ def oracle_train_step_time(model_cpu, batches, threads, lr=4e-4):
     return toks / sum(times), len(times)
 
 
+def train_flops(model_cfg, B, Ts, Tt):
+    """Algorithmic FLOPs of one optimisation step: 3 x the forward contractions."""
+    E, H, C, S, I, V = 256, 512, 1024, 512, 2048, model_cfg["tgt_size"]
+    p_step = 3 * H * E + 3 * H * H + C * H + H * C + 2 * 3 * H * H + E * H + E * C + E * E + V * E
+    fwd = 2.0 * B * Tt * p_step + 4.0 * B * Tt * Ts * C + 2.0 * B * Ts * 2 * ((E + H) * 3 * H) + 2.0 * B * Ts * C * C * 2 \
+        + 2.0 * B * (I * S + S * C + C * S) + 2.0 * B * B * S
+    return 3.0 * fwd
+
+
 def measure_train(args, dev, world, rank, timed, precision="bf16", french=False):
-    """BASELINE configs[1]/[3] shape: EN->DE multimodal training step, batch 32 per GPU, teacher forced, dropout 0
-    (parity configuration), gradients all-reduced over ranks.  precision "bf16": every tensor-core / FFMA contraction of the
-    forward AND backward pass rounds its operands to bfloat16 and accumulates in FP32; state, soft-max, losses, Adam FP32."""
+    """BASELINE configs[1]/[3] shape: EN->DE (or EN->FR) multimodal training step, batch 32 per GPU, teacher forced, gradients
+    all-reduced over ranks.  precision "bf16": every tensor-core / FFMA contraction of the forward AND backward pass rounds its
+    operands to bfloat16 and accumulates in FP32; state, soft-max, losses, Adam FP32.  Under data parallelism every rank draws its
+    own sentences but all ranks share the step's TARGET length, as data.BucketBatchSampler's data-parallel mode hands them out
+    (one bucket per global batch)."""
     import vag_nmt_b200 as vag
     from vag_nmt_b200 import synthetic
     from vag_nmt_b200.optim import ClipAdam
@@ -234,14 +254,24 @@ def measure_train(args, dev, world, rank, timed, precision="bf16", french=False)
     crit_mt = torch.nn.NLLLoss(weight=w, reduction="none")
     crit_vse = DistributedPairwiseRankingLoss(margin=0.1)
     B = 32
-    batches = [synthetic.make_batch(B, cfg["src_size"], cfg["tgt_size"], cfg["im_feats_size"], seed=100 + 8 * i + rank) for i in range(8)]
+    batches = []
+    for i in range(8):
+        bt = synthetic.make_batch(B, cfg["src_size"], cfg["tgt_size"], cfg["im_feats_size"], seed=100 + 8 * i + rank)
+        if world > 1:   # the global batch comes from ONE target-length bucket: every rank uses rank 0's target length for step i
+            ref = synthetic.make_batch(B, cfg["src_size"], cfg["tgt_size"], cfg["im_feats_size"], seed=100 + 8 * i)
+            Tt = ref.tgt.shape[1]
+            g = torch.Generator().manual_seed(1000 + 8 * i + rank)
+            lt = torch.full((B,), Tt, dtype=torch.long)
+            bt.tgt = synthetic._sentences(lt, cfg["tgt_size"], g)
+        batches.append(bt)
     pinned = [(bt.src.pin_memory(), bt.tgt.pin_memory(), bt.im.pin_memory(), bt.src_lengths) for bt in batches]
     tokens = [int((bt.tgt != 0).sum()) for bt in batches]
+    flops = [train_flops(cfg, B, bt.src.shape[1], bt.tgt.shape[1]) for bt in batches]
     state = {"i": 0, "loss": None}
 
     # the step driver of train.py:36-51 with zero_grad/forward/backward replayed from one CUDA graph per batch shape
-    # (single process; under data parallelism the collectives keep the step eager)
     stepper = GraphedTrainStep(model, opt, crit_mt, crit_vse, clip=1.0)
+    host_loss = torch.zeros(3, dtype=torch.float32).pin_memory()
 
     def step():
         src, tgt, im, lens = pinned[state["i"] % len(pinned)]
@@ -249,15 +279,34 @@ def measure_train(args, dev, world, rank, timed, precision="bf16", french=False)
         out = stepper.step(src, lens, tgt, im, 1.0)       # pinned host batch → device copies inside the step
         state["loss"] = out[0]
 
+    def step_e2e():      # ... plus the device→host read of the step's losses the reference does with .item() (train.py:51)
+        step()
+        host_loss.copy_(torch.stack([x.reshape(()) for x in stepper.last_out]), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
     for _ in range(len(pinned)):      # one pass over the batch shapes: every shape's graph is captured before the timed region
         step()
     state["i"] = 0
     steps = max(args.steps, 8)
     ms = timed(step, steps)
     final_loss = float(state["loss"])
+    state["i"] = 0
+    ms_e2e = timed(step_e2e, steps)
     tok = sum(tokens[i % len(tokens)] for i in range(steps)) * world
+    fl = sum(flops[i % len(flops)] for i in range(steps)) * world
+    pk = peaks()
+    peak = pk["bf16_sustained"] if precision == "bf16" else pk["bf16_sustained"] / 3.0
+    achieved = fl / (ms / 1e3) / 1e12 / world
     res = {"metric": "train tgt tokens/sec", "value": tok / (ms / 1e3), "unit": "tokens/s", "ms_per_step": ms / steps, "steps": steps,
            "batch_per_gpu": B, "global_batch": B * world, "dtype": "bf16" if precision == "bf16" else "f32", "loss_after": final_loss,
+           "e2e": {"value": tok / (ms_e2e / 1e3), "unit": "tokens/s", "ms_per_step": ms_e2e / steps,
+                   "h2d_bytes_per_step": int(sum(p[0].numel() * 8 + p[1].numel() * 8 + p[2].numel() * 4 for p in pinned) / len(pinned)),
+                   "d2h_bytes_per_step": 12, "note": "pinned host batch in, the three losses read back (synchronised) every step"},
+           "roofline": {"bound": "tensor", "kernel": "whole optimisation step (forward + BPTT + clip + Adam, ~330 launches): latency-bound, see DESIGN.md section 5",
+                        "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                        "peak_note": f"{pk['src']} bf16 sustained {pk['bf16_sustained']} TF/s" + ("" if precision == "bf16" else " ÷ 3 (three FP16 products per MAC)")
+                                     + "; algorithmic FLOPs = 3 x forward contractions (SURVEY 8d), per GPU"},
+           "grads_in_place": bool(getattr(opt, "grads_in_place", False)),
            "note": ("EN->FR multimodal, teacher forcing 1.0, dropout emb 0.2 / ctx 0.4 / out 0.4 (masks drawn on the device inside the step), "
                     "pairwise ranking loss over the global batch, clip 1.0 + Adam(lr 1e-3, wd 1e-5 on non-bias); " if french else
                     "EN->DE multimodal, teacher forcing 1.0, dropout 0, pairwise ranking loss over the global batch, "
@@ -269,6 +318,56 @@ def measure_train(args, dev, world, rank, timed, precision="bf16", french=False)
         v, n = oracle_train_step_time(cpu_model, batches[:4], threads)
         res["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": threads, "kind": "port",
                                "sample": f"{n} optimisation steps, batch {B}, oracle forward + torch autograd + clip + Adam on CPU fp32"}
+    return res
+
+
+def dp_parity(dev, world, rank):
+    """Data-parallel correctness, asserted BEFORE any timing under torchrun (EN->DE shapes, 8 sentences per rank):
+    (i) the all-reduced gradient of the global batch split over the ranks equals the gradient one process computes on the whole
+        global batch (global-batch ranking loss included), worst  max|Δ| / max|g|  over all parameters;
+    (ii) after three optimisation steps on rank-different batches the replicas are bit-identical (torch.equal)."""
+    import torch.distributed as dist
+    import vag_nmt_b200 as vag
+    from vag_nmt_b200 import synthetic
+    from vag_nmt_b200.optim import ClipAdam, allreduce_gradients
+    from vag_nmt_b200.train import DistributedPairwiseRankingLoss, train_imagine_beam
+    cfg = synthetic.DE
+    model = build_cpu_params().to(dev).train()
+    Bl = 8
+    batch = synthetic.make_batch(Bl * world, cfg["src_size"], cfg["tgt_size"], cfg["im_feats_size"], seed=5)
+    w = torch.ones(cfg["tgt_size"], device=dev)
+    w[0] = 0
+    crit = torch.nn.NLLLoss(weight=w, reduction="none")
+    loss, _, _ = model(batch.src, batch.src_lengths, batch.tgt, batch.im, 1.0, criterion_mt=crit, criterion_vse=vag.PairwiseRankingLoss(margin=0.1))
+    loss.backward()
+    ref = {n: p.grad.clone() for n, p in model.named_parameters()}
+    for p_ in model.parameters():
+        p_.grad = None
+    sl = slice(rank * Bl, (rank + 1) * Bl)
+    lens = batch.src_lengths[sl]
+    loss_l, _, _ = model(batch.src[sl][:, :max(lens)], lens, batch.tgt[sl], batch.im[sl], 1.0, criterion_mt=crit,
+                         criterion_vse=DistributedPairwiseRankingLoss(margin=0.1))
+    loss_l.backward()
+    allreduce_gradients(list(model.parameters()))
+    worst = 0.0
+    for n, p_ in model.named_parameters():
+        scale = float(ref[n].abs().max())
+        if scale > 0:
+            worst = max(worst, float((p_.grad - ref[n]).abs().max()) / scale)
+    worst_t = torch.tensor([worst], device=dev)
+    dist.all_reduce(worst_t, op=dist.ReduceOp.MAX)
+    opt = ClipAdam(model, lr=1e-2)
+    cv = DistributedPairwiseRankingLoss(margin=0.1)
+    for it in range(3):
+        bt = synthetic.make_batch(Bl, cfg["src_size"], cfg["tgt_size"], cfg["im_feats_size"], seed=50 + world * it + rank)
+        train_imagine_beam(bt.src, bt.tgt, bt.im, bt.src_lengths, model, opt, crit, cv, 0.99, 1.0)
+    flat = torch.cat([p_.detach().reshape(-1) for p_ in model.parameters()])
+    allp = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(allp, flat)
+    in_sync = all(torch.equal(allp[0], t) for t in allp)
+    res = {"grad_vs_single_process_worst_rel": float(worst_t), "grad_ok": bool(float(worst_t) < 1e-4), "replicas_bit_identical_after_3_steps": bool(in_sync),
+           "global_batch": Bl * world, "grads_in_place": bool(getattr(opt, "grads_in_place", False))}
+    assert res["grad_ok"] and res["replicas_bit_identical_after_3_steps"], res
     return res
 
 
@@ -317,6 +416,37 @@ def measure_text_only(args, dev, world, rank, timed, src_dev, lens):
 
 
 # ------------------------------------------------------------------------------------------ B200 arm
+def reference_eager_on_gpu(params_cpu, sents, im, K, L, dev):
+    """The reference's algorithm (the oracle port: per-step attn_e recomputation, K-times tiled context, log-softmax + topk over
+    [B, K·V], a host test per step — V11:233-337) executed with CUDA tensors through torch's eager operators, eval batches of 16,
+    TF32 off.  NOT this repository's product path: the "existing implementation on a B200" bar of SURVEY.md section 8d."""
+    from oracle import vag_oracle as O
+    from vag_nmt_b200 import synthetic
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        p = {k: v.to(dev) for k, v in params_cpu.items()}
+        out = [None] * len(sents)
+
+        def run():
+            for i in range(0, len(sents), REF_BATCH):
+                src, lens, im_s, order = synthetic.pad_and_sort(sents[i:i + REF_BATCH], im[i:i + REF_BATCH])     # host, like the reference
+                with torch.no_grad(), torch.device(dev):     # the oracle's own tensors (beams, masks, indices) are created on the GPU
+                    toks = O.multimodal_beamsearch_decode(p, src.to(dev), lens, im_s.to(dev), K, L, hoist_keys=False)
+                for r, c in enumerate(order):
+                    out[i + c] = toks[r]
+        run()                                   # warm-up (cuBLAS handles, allocator)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        run()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    return len(sents) / dt, out
+
+
 def run_ours(args):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -330,13 +460,9 @@ def run_ours(args):
 
     import vag_nmt_b200 as vag
     from vag_nmt_b200 import _cabi, ops, synthetic
+    from vag_nmt_b200.translate import decode_corpus, shard_indices
     lib = _cabi.lib()
     cfg = synthetic.DE
-    model = build_cpu_params().to(dev)
-    sents, im = synthetic.make_corpus(args.sentences, cfg["src_size"], cfg["im_feats_size"], seed=7 + rank)
-    src, lens, im_s, order = synthetic.pad_and_sort(sents, im)
-    src_pin, im_pin = src.pin_memory(), im_s.pin_memory()
-    src_dev, im_dev = src.to(dev), im_s.to(dev)
     K, L = args.beam, args.max_length
 
     def barrier():
@@ -357,6 +483,16 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
+    parity = dp_parity(dev, world, rank) if world > 1 else None      # asserts; nothing is timed before the replicas are proven equal
+
+    model = build_cpu_params().to(dev)
+    # ---- the SAME corpus on every rank; rank r decodes every world-th sentence of the length-sorted corpus (strong scaling)
+    sents, im = synthetic.make_corpus(args.sentences, cfg["src_size"], cfg["im_feats_size"], seed=7)
+    idx = shard_indices([len(x) for x in sents], world, rank)
+    src, lens, im_s, order = synthetic.pad_and_sort([sents[i] for i in idx], im[idx])
+    src_pin, im_pin = src.pin_memory(), im_s.pin_memory()
+    src_dev, im_dev = src.to(dev), im_s.to(dev)
+
     def step_device():
         model.decode_device(src_dev, lens, im_dev, K, L)
 
@@ -365,7 +501,16 @@ def run_ours(args):
     def step_e2e():
         s = src_pin.to(dev, non_blocking=True)
         i = im_pin.to(dev, non_blocking=True)
-        result["tokens"] = model.beamsearch_decode(s, lens, i, beam_size=K, max_length=L)
+        mine = model.beamsearch_decode(s, lens, i, beam_size=K, max_length=L)
+        if world > 1:      # the translations of the whole corpus on every rank, corpus order (translate.decode_corpus_sharded)
+            parts = [None] * world
+            dist.all_gather_object(parts, ([idx[c] for c in order], mine))
+            merged = [None] * args.sentences
+            for pidx, ptoks in parts:
+                for j, t in zip(pidx, ptoks):
+                    merged[j] = t
+            result["corpus"] = merged
+        result["tokens"] = mine
 
     for _ in range(max(args.warmup, 3)):
         step_device()
@@ -385,47 +530,96 @@ def run_ours(args):
     ms_bf16 = timed(step_device, args.steps)
     model.precision = "fp32"
 
-    total_sent = args.sentences * world
+    total_sent = args.sentences
     value = total_sent * args.steps / (ms / 1e3)
     e2e = total_sent * args.steps / (ms_e2e / 1e3)
+    value_bf16 = total_sent * args.steps / (ms_bf16 / 1e3)
 
-    # ---- roofline of the dominant kernel: the vocabulary projection of one decoder step, [B*K, E] x [E, V] reduced in its
-    #      epilogue to per-slice top-2 / soft-max summaries (vocab_top2_pair_kernel — tcgen05 cta_group::2, FP16-split
-    #      operands, exactly the launch the beam loop makes), timed alone with CUDA events on the launching stream.
+    # ---- roofline of the dominant kernel: the vocabulary projection of one decoder step, [rows, E] x [E, V] reduced in its
+    #      epilogue to per-slice top-2 / soft-max summaries (vocab_top2_pair_kernel — tcgen05 cta_group::2, split operands, exactly
+    #      the launch the beam loop makes for this rank's rows), timed alone with CUDA events on the launching stream.
     pk = peaks()
-    N = args.sentences * K
+    N = len(idx) * K
     E, V = cfg["tgt_embedding_size"], cfg["tgt_size"]
     x = torch.tanh(torch.randn(N, E, device=dev))
     wgt, bias = model.decoder.out.weight.detach(), model.decoder.out.bias.detach()
-    xs, wsplit = ops.tc_split(x), ops.tc_split(wgt)
-    for _ in range(3):
-        ops.tc_gemm_top2(xs, wsplit, N, E, V, bias)
-    reps = 20
-    ms_k = timed(lambda: ops.tc_gemm_top2(xs, wsplit, N, E, V, bias), reps) / reps
-    flops = 2.0 * N * E * V
-    achieved = flops / (ms_k / 1e3) / 1e12
-    peak_tf = pk["bf16"] / 3.0
     traffic = None
     tpath = ROOT / "profiles" / "dominant_kernel_traffic.json"
-    if tpath.exists():
+    if tpath.exists() and world == 1:
         traffic = json.loads(tpath.read_text()).get("dram_bytes_per_launch")
-    roofline = {"bound": "tensor", "kernel": "vocab_top2_pair_kernel (vag_tc_gemm_top2_f32) vocabulary projection + top-2/soft-max "
-                                             "summaries, rows=%d K=%d N=%d" % (N, E, V),
-                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
-                "peak_note": f"{pk['src']} bf16 burst {pk['bf16']} TF/s ÷ 3: FP32-exact mode issues 3 FP16 tensor products "
-                             "(hi·hi, hi·lo, lo·hi) per algorithmic MAC; algorithmic FLOPs = 2·rows·K·N",
-                "ms_per_launch": ms_k, "flops_per_launch": flops}
+    roof = {}
+    for mode in ("fp32", "bf16"):
+        with _cabi.precision_scope(mode):
+            xs, wsplit = ops.tc_split(x), ops.tc_split(wgt)
+            for _ in range(3):
+                ops.tc_gemm_top2(xs, wsplit, N, E, V, bias)
+            reps = 20
+            ms_k = timed(lambda: ops.tc_gemm_top2(xs, wsplit, N, E, V, bias), reps) / reps
+        flops = 2.0 * N * E * V
+        achieved = flops / (ms_k / 1e3) / 1e12
+        peak_tf = pk["bf16"] / 3.0 if mode == "fp32" else pk["bf16"]
+        roof[mode] = {"bound": "tensor", "kernel": "vocab_top2_pair_kernel (vag_tc_gemm_top2_f32) vocabulary projection + top-2/soft-max "
+                                                   "summaries, rows=%d K=%d N=%d, %s" % (N, E, V, "FP16 hi/lo split, 3 products" if mode == "fp32" else "bf16, 1 product"),
+                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                      "traffic": traffic if mode == "fp32" else None,
+                      "peak_note": (f"{pk['src']} bf16 burst {pk['bf16']} TF/s ÷ 3: FP32-exact mode issues 3 FP16 tensor products (hi·hi, hi·lo, lo·hi) per "
+                                    "algorithmic MAC" if mode == "fp32" else f"{pk['src']} bf16 burst {pk['bf16']} TF/s, undivided") + "; algorithmic FLOPs = 2·rows·K·N",
+                      "ms_per_launch": ms_k, "flops_per_launch": flops}
+    gf_sent = 2.0 * (1 + (L - 1) * K) * P_STEP_DE / 1e9
+    tf_fp32, tf_bf16 = value * gf_sent / 1e3 / world, value_bf16 * gf_sent / 1e3 / world
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload_config(args, per_step=args.sentences),
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(src_pin.numel() * 8 + im_pin.numel() * 4),
-                    "d2h_bytes_per_step": int(args.sentences * (L * 8 + 4)), "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-            "decode_bf16": {"value": total_sent * args.steps / (ms_bf16 / 1e3), "unit": UNIT, "ms_per_step": ms_bf16 / args.steps,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args, per_step=args.sentences, world=world),
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(src_pin.numel() * 8 + im_pin.numel() * 4) * world,
+                    "d2h_bytes_per_step": int(args.sentences * (L * 8 + 4)), "ms_per_step": ms_e2e / args.steps,
+                    "note": "pinned host inputs → model.beamsearch_decode → host token lists" + (" → all_gather_object of the translations (full corpus on every rank)" if world > 1 else "")},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof["fp32"], "roofline_bf16": roof["bf16"],
+            "decode_bf16": {"value": value_bf16, "unit": UNIT, "ms_per_step": ms_bf16 / args.steps,
                             "note": "same workload with model.precision = 'bf16' (bfloat16 operands, one tensor product, FP32 accumulation)"},
-            "algorithmic": {"gflop_per_sentence": 2.0 * (1 + (L - 1) * K) * P_STEP_DE / 1e9,
-                            "achieved_tflops_whole_job": value * 2.0 * (1 + (L - 1) * K) * P_STEP_DE / 1e12 / world}}
+            "whole_step": {"gflop_per_sentence": gf_sent,
+                           "fp32": {"achieved_tflops_per_gpu": tf_fp32, "frac_of_split_peak": tf_fp32 / (pk["bf16"] / 3.0)},
+                           "bf16": {"achieved_tflops_per_gpu": tf_bf16, "frac_of_burst_peak": tf_bf16 / pk["bf16"],
+                                    "frac_of_sustained_peak": tf_bf16 / pk["bf16_sustained"]},
+                           "note": "whole decode job (encoder, pooling, 80 decoder steps, selection, back-trace): algorithmic decoder-step FLOPs / wall time"}}
+    if parity is not None:
+        line["dp_parity"] = parity
+
+    if world > 1:
+        # weak scaling for comparison with round 1, labelled as such: every rank decodes ITS OWN args.sentences sentences
+        ws_sents, ws_im = synthetic.make_corpus(args.sentences, cfg["src_size"], cfg["im_feats_size"], seed=7 + rank)
+        w_src, w_lens, w_im, _ = synthetic.pad_and_sort(ws_sents, ws_im)
+        w_src, w_im = w_src.to(dev), w_im.to(dev)
+        model.decode_device(w_src, w_lens, w_im, K, L)
+        ms_w = timed(lambda: model.decode_device(w_src, w_lens, w_im, K, L), max(2, args.steps // 2))
+        line["weak_scaling"] = {"value": args.sentences * world * max(2, args.steps // 2) / (ms_w / 1e3), "unit": UNIT,
+                                "sentences_per_rank": args.sentences, "note": "WEAK scaling: per-GPU work fixed, no collective — not the configs[2] workload"}
+
+    if rank == 0 and world == 1:
+        # ---- the reference's own batching: eval batches of 16, per-batch length sort, host tensors in, token lists out
+        fn = lambda s_, l_, i_, K_, L_: model.beamsearch_decode(s_, l_, i_, beam_size=K_, max_length=L_)
+        ref16 = decode_corpus(fn, sents, im, K, L, batch_size=REF_BATCH)          # captures one graph per (B, T) shape
+        ms_ref = timed(lambda: decode_corpus(fn, sents, im, K, L, batch_size=REF_BATCH), 2) / 2
+        one = decode_corpus(fn, sents, im, K, L)
+        line["decode_ref_batching"] = {"value": args.sentences / (ms_ref / 1e3), "unit": UNIT, "batch": REF_BATCH, "ms_per_batch": ms_ref / -(-args.sentences // REF_BATCH),
+                                       "graphs": len(getattr(model, "_decode_graphs", {})), "same_tokens_as_one_batch": sum(int(a == b) for a, b in zip(ref16, one)),
+                                       "note": "reference eval batching (nmt_multimodal_beam_DE.py:542-547): 63 calls of beamsearch_decode with host inputs; "
+                                               "decode invariants cached across calls, the 80-step loop of each (B, T) shape replayed from a CUDA graph"}
+        # ---- hypotheses that END (≈ 15 tokens): the early stop
+        clock = build_cpu_params().to(dev)
+        synthetic.install_eos_clock(clock, 15.0)
+        ops.invalidate_prepared()
+        w_, ctx_, mask_, keys_, h0_, _, _ = clock._prepare(src_dev, lens, im_dev)
+        steps_run = int(ops.beam_decode(w_, h0_, keys_, ctx_, mask_, K, L, debug=True)[4])
+        for _ in range(2):
+            clock.decode_device(src_dev, lens, im_dev, K, L)
+        ms_c = timed(lambda: clock.decode_device(src_dev, lens, im_dev, K, L), args.steps)
+        line["decode_eos_clock"] = {"value": args.sentences * args.steps / (ms_c / 1e3), "unit": UNIT, "ms_per_step": ms_c / args.steps,
+                                    "steps_run": steps_run, "max_length": L,
+                                    "note": "same workload with synthetic.install_eos_clock (hypotheses end after ≈ 15 tokens like a trained Multi30K model's): "
+                                            "the host follows the device's progress word and stops launching steps (V11:265-269)"}
+        del clock
+        ops.invalidate_prepared()
 
     if rank == 0 and world == 1 and args.cpu_sample > 0:
         threads = os.cpu_count() or 1
@@ -433,16 +627,25 @@ def run_ours(args):
         n = args.cpu_sample
         dt, cpu_tokens = oracle_decode_time(params, sents[:n], im[:n], K, L, REF_BATCH, threads)
         # the sample doubles as a parity spot check: the CPU port must produce the tokens the GPU produced
-        inv = {c: r for r, c in enumerate(order)}
-        agree = sum(int(cpu_tokens[i] == result["tokens"][inv[i]]) for i in range(n))
+        pos = {idx[c]: r for r, c in enumerate(order)}
+        agree = sum(int(cpu_tokens[i] == result["tokens"][pos[i]]) for i in range(n))
         line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"first {n} sentences of the shard in reference eval batches of {REF_BATCH}, beam {K}, "
+                                "sample": f"first {n} sentences of the corpus in reference eval batches of {REF_BATCH}, beam {K}, "
                                           f"max_length {L}, oracle/vag_oracle.py (torch CPU fp32)",
                                 "token_exact_sentences": f"{agree}/{n}"}
+        try:
+            v_gpu, gpu_tokens = reference_eager_on_gpu(params, sents[:64], im[:64], K, L, dev)
+            line["reference_eager_b200"] = {"value": v_gpu, "unit": UNIT, "kind": "port", "sample": "first 64 sentences, eval batches of 16, beam 12, max_length 80",
+                                            "same_tokens_as_cpu": sum(int(a == b) for a, b in zip(gpu_tokens[:n], cpu_tokens)),
+                                            "note": "the reference's algorithm (oracle port) with CUDA tensors through torch eager operators on this B200, TF32 off — "
+                                                    "the 'existing implementation' bar of SURVEY 8d; not this repository's product path"}
+        except Exception as exc:
+            line["reference_eager_b200"] = {"error": f"{type(exc).__name__}: {exc}"}
     del model
     torch.cuda.empty_cache()
-    line["text_only"] = measure_text_only(args, dev, world, rank, timed, src_dev, lens)   # BASELINE configs[4]
-    torch.cuda.empty_cache()
+    if world == 1:
+        line["text_only"] = measure_text_only(args, dev, world, rank, timed, src_dev, lens)   # BASELINE configs[4]
+        torch.cuda.empty_cache()
     line["train"] = measure_train(args, dev, world, rank, timed, "bf16")       # BASELINE configs[1]: training step bf16
     line["train_f32"] = measure_train(args, dev, world, rank, timed, "fp32")
     try:

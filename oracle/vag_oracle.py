@@ -404,7 +404,7 @@ def beamsearch(step_fn, n_vocab: int, B: int, h0: torch.Tensor, beam_size: int, 
     lens = (beam.transpose(0, 2) > 3).sum(-1).t().to(nll.dtype).clamp(min=1)  # :318
     nll_norm = nll / lens  # :321
     best = topk_canonical(nll_norm, 1)[1].squeeze(1)  # :322
-    hyps = beam[:, torch.arange(B), best].numpy().T  # :324
+    hyps = beam[:, torch.arange(B), best].cpu().numpy().T  # :324 (.cpu(): a no-op here; lets the same code run on CUDA tensors for bench.py's reference-eager datum)
     final = []
     for b in range(B):
         cur_list = []

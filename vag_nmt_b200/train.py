@@ -313,4 +313,5 @@ class GraphedTrainStep:
             for p, g in st["grads"]:       # the gradients live at fixed addresses inside the graph's pool
                 p.grad = g
         self.optimizer.step(clip=self.clip)
+        self.last_out = (out[0], out[1], out[2])
         return out[0], out[1], out[2]
