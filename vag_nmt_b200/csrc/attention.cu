@@ -202,6 +202,66 @@ __device__ __forceinline__ float sum4_v_over_one_plus_exp2(const float4& v, floa
     return num * r;
 }
 
+// Factored form for the beam loop: exp(2(q + k)) = exp(2q)·exp(2k).  exp(2k) depends on (sentence, position, channel) only and is
+// computed ONCE per decode call (attn_exp_keys), exp(2q) once per (row, channel) when a CTA stages its q rows — the inner loop
+// over (row, position, channel) then needs no exponential at all:  Σ_{i<4} v_i / (1 + Eq_i·Ek_i)  costs ONE SFU operation (the
+// shared reciprocal) per four elements instead of five, i.e. 0.25 instead of 1.25 MUFU per element, and the kernel moves from the
+// SFU roof (16 lanes per SM) to the FMA pipe (128 lanes).  Both exponentials are the PRECISE expf (≤ 2 ulp), so the product
+// carries ≤ 3e-7 relative error — an absolute error ≤ 1.5e-7 in tanh, the same as the single-exponential formula above.
+// Each 1 + Eq·Ek is clamped to 2^30 (beyond that 1/(1+E) < 1e-9, below half an ulp of the O(1) sum) so that the product of four
+// stays finite.  Valid while |q|, |k| ≤ 40 (both exponentials finite and normal); a CTA that sees anything larger takes the
+// single-exponential path — checked per sentence for k (attn_exp_keys) and per CTA for q.
+constexpr float kFactoredMaxAbs = 40.0f;
+// exp(2x) = 2^(x·2·log2e) with the rounding of the product compensated: u_hi = rn(x·c_hi), the exact residual of that product
+// plus x·c_lo goes into a first-order correction, so the result carries only ex2.approx's own error (≤ 2 ulp) instead of an
+// argument error that grows with |x| — six instructions against ~35 for the range-checked expf.
+__device__ __forceinline__ float exp2x_comp(float x) {
+    constexpr float c_hi = 2.88539004f;                 // rn(2·log2(e))
+    constexpr float c_lo = 4.05197e-08f;                // 2·log2(e) − c_hi
+    const float u = x * c_hi;
+    const float err = fmaf(x, c_lo, fmaf(x, c_hi, -u));
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(u));
+    return fmaf(e, err * 0.693147182f, e);
+}
+__device__ __forceinline__ float sum4_v_over_one_plus_prod(const float4& v, const float4& eq, const float4& ek) {
+    const float a0 = fminf(fmaf(eq.x, ek.x, 1.0f), 1073741824.0f), a1 = fminf(fmaf(eq.y, ek.y, 1.0f), 1073741824.0f);
+    const float a2 = fminf(fmaf(eq.z, ek.z, 1.0f), 1073741824.0f), a3 = fminf(fmaf(eq.w, ek.w, 1.0f), 1073741824.0f);
+    const float p01 = a0 * a1, p23 = a2 * a3;
+    const float n01 = fmaf(v.x, a1, v.y * a0), n23 = fmaf(v.z, a3, v.w * a2);
+    const float num = fmaf(n01, p23, n23 * p01);
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p01 * p23));
+    return num * r;
+}
+
+// ekeys = exp(2·keys) (precise), kflag[b] = 1 when sentence b holds a key outside ±kFactoredMaxAbs.  One block per (sentence, chunk).
+__global__ void __launch_bounds__(256)
+attn_exp_keys_kernel(float* __restrict__ ekeys, int* __restrict__ kflag, const float* __restrict__ keys, int TC) {
+    const int b = blockIdx.y;
+    const float4* src = reinterpret_cast<const float4*>(keys + (int64_t)b * TC);
+    float4* dst = reinterpret_cast<float4*>(ekeys + (int64_t)b * TC);
+    bool bad = false;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < TC / 4; i += gridDim.x * blockDim.x) {
+        const float4 k = src[i];
+        bad |= !(fabsf(k.x) <= kFactoredMaxAbs) | !(fabsf(k.y) <= kFactoredMaxAbs) | !(fabsf(k.z) <= kFactoredMaxAbs) | !(fabsf(k.w) <= kFactoredMaxAbs);
+        dst[i] = make_float4(expf(2.0f * k.x), expf(2.0f * k.y), expf(2.0f * k.z), expf(2.0f * k.w));
+    }
+    if (__syncthreads_or(bad) && threadIdx.x == 0) kflag[b] = 1;
+}
+int attn_exp_keys(float* ekeys, int* kflag, const float* keys, int B, int T, int C, cudaStream_t st) {
+    if ((C & 3) || B <= 0) {
+        set_error("attn_exp_keys: C must be a multiple of 4");
+        return VAG_ERR_UNSUPPORTED;
+    }
+    VAG_CUDA(cudaMemsetAsync(kflag, 0, sizeof(int) * (size_t)B, st));
+    const int TC = T * C;
+    dim3 grid(ceil_div(TC / 4, 256 * 4) > 0 ? ceil_div(TC / 4, 256 * 4) : 1, B);
+    attn_exp_keys_kernel<<<grid, 256, 0, st>>>(ekeys, kflag, keys, TC);
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Tuned variant for C % 4 == 0 (every real configuration): rows-per-CTA is a template parameter so that the
 // accumulator arrays are exactly as large as the beam, a warp loads a whole key row (up to 1024 channels) with
@@ -215,7 +275,7 @@ __global__ void __launch_bounds__(256, RCAP <= 12 ? 3 : 2)
 attention_tuned_kernel(float* __restrict__ c_out, int64_t ld_c, float* __restrict__ alpha_out, const float* __restrict__ q,
                        int64_t ld_q, const float* __restrict__ keys, const float* __restrict__ ctx,
                        const float* __restrict__ v, const float* __restrict__ mask, int rows, int rows_per_sent, int T, int C,
-                       SplitDst sd, const int* __restrict__ done) {
+                       SplitDst sd, const int* __restrict__ done, const float* __restrict__ ekeys, const int* __restrict__ kflag) {
     pdl_trigger();   // the contraction that follows may start its prologue while this kernel drains
     if (done && *reinterpret_cast<const volatile int*>(done)) return;   // beam search over (block-uniform)
     extern __shared__ __align__(16) float smem[];
@@ -235,12 +295,41 @@ attention_tuned_kernel(float* __restrict__ c_out, int64_t ld_c, float* __restric
     const float* ctx_b = ctx + (int64_t)b * T * C;
     const float* mask_b = mask ? mask + (int64_t)b * T : nullptr;
 
-    for (int i = tid * 4; i < R * C; i += 1024) {
-        const int r = i / C, c = i - r * C;
-        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row0 + r < rows) val = *reinterpret_cast<const float4*>(q + (int64_t)(row0 + r) * ld_q + c);
-        if (MODE == VAG_ATTN_MLP) { val.x *= kTwoLog2e; val.y *= kTwoLog2e; val.z *= kTwoLog2e; val.w *= kTwoLog2e; }
-        *reinterpret_cast<float4*>(q_s + r * C + c) = val;
+    // Stage the q rows.  Factored exponentials (see sum4_v_over_one_plus_prod) are usable when the sentence's keys and this CTA's q
+    // rows are in range: the rows are staged as exp(2q) in ONE pass that also checks the range; only a CTA that fails the check
+    // (never with real models) stages them again in the single-exponential form.  All RCAP rows are staged — rows the CTA does
+    // not own hold zeros (their scores are never read) — so that the score loop carries no per-row guard.
+    bool fast = false;
+    {
+        const bool try_fast = MODE == VAG_ATTN_MLP && ekeys != nullptr;
+        bool bad = try_fast && kflag[b] != 0;
+        for (int i = tid * 4; i < RCAP * C; i += 1024) {
+            const int r = i / C, c = i - r * C;
+            float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < R && row0 + r < rows) {
+                val = *reinterpret_cast<const float4*>(q + (int64_t)(row0 + r) * ld_q + c);
+                if (try_fast) {
+                    bad |= !(fabsf(val.x) <= kFactoredMaxAbs) | !(fabsf(val.y) <= kFactoredMaxAbs) | !(fabsf(val.z) <= kFactoredMaxAbs) | !(fabsf(val.w) <= kFactoredMaxAbs);
+                    val.x = exp2x_comp(val.x); val.y = exp2x_comp(val.y); val.z = exp2x_comp(val.z); val.w = exp2x_comp(val.w);
+                } else if (MODE == VAG_ATTN_MLP) {
+                    val.x *= kTwoLog2e; val.y *= kTwoLog2e; val.z *= kTwoLog2e; val.w *= kTwoLog2e;
+                }
+            }
+            *reinterpret_cast<float4*>(q_s + r * C + c) = val;
+        }
+        if (try_fast) {
+            fast = !__syncthreads_or(bad);
+            if (!fast) {
+                for (int i = tid * 4; i < R * C; i += 1024) {
+                    const int r = i / C, c = i - r * C;
+                    if (row0 + r < rows) {
+                        float4 val = *reinterpret_cast<const float4*>(q + (int64_t)(row0 + r) * ld_q + c);
+                        val.x *= kTwoLog2e; val.y *= kTwoLog2e; val.z *= kTwoLog2e; val.w *= kTwoLog2e;
+                        *reinterpret_cast<float4*>(q_s + r * C + c) = val;
+                    }
+                }
+            }
+        }
     }
     // MLP mode: Σ_c v_c·tanh(x_c) = Σ_c v_c − 2·Σ_c v_c / (1 + exp(2 x_c)); the first sum is a per-CTA constant
     __shared__ float vsum_s[8];
@@ -278,6 +367,43 @@ attention_tuned_kernel(float* __restrict__ c_out, int64_t ld_c, float* __restric
     __syncthreads();
     const int n_live = n_live_s;
     const int n_groups = (R + RG - 1) / RG;
+    if (MODE == VAG_ATTN_MLP && fast) {
+        const float* ekey_b = ekeys + (int64_t)b * T * C;
+        for (int item = wid; item < n_live * n_groups; item += NW) {
+            const int t = live_t[item / n_groups];
+            const int r_lo = (item % n_groups) * RG;
+            float part[RG];
+#pragma unroll
+            for (int g = 0; g < RG; ++g) part[g] = 0.f;
+            const float* kr = ekey_b + (int64_t)t * C;
+            for (int cb = 0; cb < C; cb += 1024) {
+                float4 kv[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = cb + j * 128 + lane * 4;
+                    kv[j] = (FULLC || c < C) ? *reinterpret_cast<const float4*>(kr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = cb + j * 128 + lane * 4;
+                    if (FULLC || c < C) {
+                        const float4 vv = *reinterpret_cast<const float4*>(v_s + c);
+#pragma unroll
+                        for (int g = 0; g < RG; ++g)   // r_lo + g < RCAP always (RG·n_groups covers RCAP rows at most): no guard
+                            part[g] += sum4_v_over_one_plus_prod(vv, *reinterpret_cast<const float4*>(q_s + min(r_lo + g, RCAP - 1) * C + c), kv[j]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < RG; ++g) {
+                const int r = r_lo + g;
+                if (r < R) {
+                    const float sum = warp_sum(part[g]);
+                    if (lane == 0) sc_s[r * T + t] = fmaf(-2.0f, sum, vsum);
+                }
+            }
+        }
+    } else
     for (int item = wid; item < n_live * n_groups; item += NW) {
         const int t = live_t[item / n_groups];
         const int r_lo = (item % n_groups) * RG;
@@ -350,27 +476,28 @@ attention_tuned_kernel(float* __restrict__ c_out, int64_t ld_c, float* __restric
     }
     __syncthreads();
 
-    // ---- phase 3: context, each thread owns 4 channels and keeps 4 positions in flight
+    // ---- phase 3: context, each thread owns 4 channels and keeps 4 LIVE positions in flight (α is exactly 0 at masked positions:
+    //      they are never loaded and cost no arithmetic)
     for (int c = tid * 4; c < C; c += 1024) {
         float4 acc[RCAP];
 #pragma unroll
         for (int r = 0; r < RCAP; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int t0 = 0; t0 < T; t0 += 4) {
+        for (int i0 = 0; i0 < n_live; i0 += 4) {
             float4 x[4];
+            int tt[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int t = t0 + u;
-                const bool on = t < T && !(mask_b && mask_b[t] == 0.f);  // α is exactly 0 at masked positions
-                x[u] = on ? *reinterpret_cast<const float4*>(ctx_b + (int64_t)t * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const bool on = i0 + u < n_live;
+                tt[u] = live_t[on ? i0 + u : 0];
+                x[u] = on ? *reinterpret_cast<const float4*>(ctx_b + (int64_t)tt[u] * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int t = t0 + u;
-                if (t < T) {
+                if (i0 + u < n_live) {
                     float al[RPAD];
 #pragma unroll
-                    for (int r4 = 0; r4 < RPAD / 4; ++r4)   // rows ≥ R hold zeros (cleared below): no per-row guard in the FMA loop
-                        *reinterpret_cast<float4*>(al + 4 * r4) = *reinterpret_cast<const float4*>(al_s + t * RPAD + 4 * r4);
+                    for (int r4 = 0; r4 < RPAD / 4; ++r4)   // rows ≥ R hold zeros: no per-row guard in the FMA loop
+                        *reinterpret_cast<float4*>(al + 4 * r4) = *reinterpret_cast<const float4*>(al_s + tt[u] * RPAD + 4 * r4);
 #pragma unroll
                     for (int r = 0; r < RCAP; ++r) {
                         acc[r].x = fmaf(al[r], x[u].x, acc[r].x);
@@ -393,7 +520,8 @@ attention_tuned_kernel(float* __restrict__ c_out, int64_t ld_c, float* __restric
 template <int MODE, int RCAP, bool FULLC>
 static int launch_attention_tuned(float* c_out, int64_t ld_c, float* alpha, const float* q, int64_t ld_q, const float* keys,
                                   const float* ctx, const float* v, const float* mask, int rows, int rows_per_sent, int T, int C,
-                                  cudaStream_t st, SplitDst sd = SplitDst(), const int* done = nullptr) {
+                                  cudaStream_t st, SplitDst sd = SplitDst(), const int* done = nullptr, const float* ekeys = nullptr,
+                                  const int* kflag = nullptr) {
     const size_t smem = ((size_t)RCAP * C + C + (size_t)RCAP * T + 4 + (size_t)T * ((RCAP + 3) / 4 * 4)) * sizeof(float);
     if (smem > 227 * 1024) {
         set_error("vag_attention_f32: C=%d T=%d needs %zu B of shared memory", C, T, smem);
@@ -406,7 +534,7 @@ static int launch_attention_tuned(float* c_out, int64_t ld_c, float* alpha, cons
     }
     dim3 grid(rows / rows_per_sent, ceil_div(rows_per_sent, RCAP));
     attention_tuned_kernel<MODE, RCAP, FULLC><<<grid, 256, smem, st>>>(c_out, ld_c, alpha, q, ld_q, keys, ctx, v, mask, rows,
-                                                                 rows_per_sent, T, C, sd, done);
+                                                                 rows_per_sent, T, C, sd, done, ekeys, kflag);
     VAG_LAUNCH_CHECK();
     return VAG_OK;
 }
@@ -414,12 +542,13 @@ static int launch_attention_tuned(float* c_out, int64_t ld_c, float* alpha, cons
 template <int MODE>
 static int dispatch_attention_tuned(float* c_out, int64_t ld_c, float* alpha, const float* q, int64_t ld_q, const float* keys,
                                     const float* ctx, const float* v, const float* mask, int rows, int rows_per_sent, int T,
-                                    int C, cudaStream_t st, SplitDst sd = SplitDst(), const int* done = nullptr) {
+                                    int C, cudaStream_t st, SplitDst sd = SplitDst(), const int* done = nullptr,
+                                    const float* ekeys = nullptr, const int* kflag = nullptr) {
 #define VAG_ATT(RC)                                                                                                        \
     do {                                                                                                                   \
         if (C % 1024 == 0)                                                                                                 \
-            return launch_attention_tuned<MODE, RC, true>(c_out, ld_c, alpha, q, ld_q, keys, ctx, v, mask, rows, rows_per_sent, T, C, st, sd, done); \
-        return launch_attention_tuned<MODE, RC, false>(c_out, ld_c, alpha, q, ld_q, keys, ctx, v, mask, rows, rows_per_sent, T, C, st, sd, done); \
+            return launch_attention_tuned<MODE, RC, true>(c_out, ld_c, alpha, q, ld_q, keys, ctx, v, mask, rows, rows_per_sent, T, C, st, sd, done, ekeys, kflag); \
+        return launch_attention_tuned<MODE, RC, false>(c_out, ld_c, alpha, q, ld_q, keys, ctx, v, mask, rows, rows_per_sent, T, C, st, sd, done, ekeys, kflag); \
     } while (0)
     if (rows_per_sent == 1) VAG_ATT(1);
     if (rows_per_sent <= 4) VAG_ATT(4);
@@ -432,8 +561,10 @@ static int dispatch_attention_tuned(float* c_out, int64_t ld_c, float* alpha, co
 // Decoder-step attention of the fused step: the context leaves the kernel only as tensor-core operand planes.
 // Requirements (the caller's workspace guarantees them): C % 4 == 0, 16-byte aligned q / keys / ctx, rows_per_sent <= 16.
 int attention_mlp_split(SplitDst sd, const float* q, int64_t ld_q, const float* keys, const float* ctx, const float* v,
-                        const float* mask, int rows, int rows_per_sent, int T, int C, cudaStream_t st, const int* done) {
-    return dispatch_attention_tuned<VAG_ATTN_MLP>(nullptr, 0, nullptr, q, ld_q, keys, ctx, v, mask, rows, rows_per_sent, T, C, st, sd, done);
+                        const float* mask, int rows, int rows_per_sent, int T, int C, cudaStream_t st, const int* done, const float* ekeys,
+                        const int* kflag) {
+    return dispatch_attention_tuned<VAG_ATTN_MLP>(nullptr, 0, nullptr, q, ld_q, keys, ctx, v, mask, rows, rows_per_sent, T, C, st, sd, done, ekeys,
+                                                  kflag);
 }
 
 }  // namespace vag

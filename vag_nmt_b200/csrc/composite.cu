@@ -429,7 +429,9 @@ int gru_gates_split(float* h_out, int64_t ld_ho, const float* gi, int64_t ld_gi,
 int embed_split_rows(SplitDst dst, const uint16_t* t_hi, const uint16_t* t_lo, int64_t ld_t, int E, const int64_t* tokens, int rows,
                      int64_t V, cudaStream_t st);
 int attention_mlp_split(SplitDst sd, const float* q, int64_t ld_q, const float* keys, const float* ctx, const float* v,
-                        const float* mask, int rows, int rows_per_sent, int T, int C, cudaStream_t st, const int* done = nullptr);
+                        const float* mask, int rows, int rows_per_sent, int T, int C, cudaStream_t st, const int* done = nullptr,
+                        const float* ekeys = nullptr, const int* kflag = nullptr);
+int attn_exp_keys(float* ekeys, int* kflag, const float* keys, int B, int T, int C, cudaStream_t st);
 int beam_select_top2(const float4* summ, int tile_w, SplitDst t, const uint16_t* w_hi, const uint16_t* w_lo, int64_t ld_w,
                      const float* bias, int E, const int64_t* prev_tokens, float* nll, int64_t* tokens_out, int32_t* parents_out,
                      int B, int K, int64_t V, int step, int avoid_double, const int* done, int* fin_counter, cudaStream_t st);
@@ -445,6 +447,8 @@ struct FusedStep {
     const Planes* w_emb = nullptr;                  // tied: the gather reads the projection's planes
     float* g1 = nullptr;
     const int* done = nullptr;                      // device flag: every hypothesis has ended, later steps return at once
+    const float* ekeys = nullptr;                   // exp(2·keys) [B, T, C] and its per-sentence range flags (attention.cu, factored form)
+    const int* kflag = nullptr;
     SplitDst cat_e(int H) const { SplitDst d = cat; d.hi += H; if (d.lo) d.lo += H; return d; }
     SplitDst cat_c(int H, int E) const { SplitDst d = cat; d.hi += H + E; if (d.lo) d.lo += H + E; return d; }
 };
@@ -493,7 +497,7 @@ static int decoder_step_fused(const FusedStep& f, const vag_decoder_weights* w, 
     if (f.g1) VAG_TRY(gru_gates_split(ws.h1, H, f.g1, 3 * H, ws.gh, 3 * H, h_prev, H, rows, H, f.h1, st, tokens, V, f.done));
     else VAG_TRY(gru_gates_split(ws.h1, H, ws.gi, 3 * H, ws.gh, 3 * H, h_prev, H, rows, H, f.h1, st, nullptr, 0, f.done));
     VAG_TRY(gemm(ws.q, C, f.h1, pr.ah, nullptr, H, C, nullptr, nullptr));                                    // :47
-    VAG_TRY(attention_mlp_split(cc, ws.q, C, keys, ctx, w->attn_v, mask, rows, rows_per_sent, T, C, st, f.done));     // :124-126
+    VAG_TRY(attention_mlp_split(cc, ws.q, C, keys, ctx, w->attn_v, mask, rows, rows_per_sent, T, C, st, f.done, f.ekeys, f.kflag));     // :124-126
     VAG_TRY(tc_gemm_split_out(f.x2, cc.hi, cc.lo, Kt, pr.c2h.hi, pr.c2h.lo, pr.c2h.ld, nullptr, rows, C, H, 0, st));   // :127
     VAG_TRY(gemm(ws.gi, 3 * H, f.x2, pr.g2i, w->gru2_b_ih, H, 3 * H, nullptr, nullptr));                     // :129
     VAG_TRY(gemm(ws.gh, 3 * H, f.h1, pr.g2h, w->gru2_b_hh, H, 3 * H, nullptr, nullptr));
@@ -552,9 +556,11 @@ struct BeamWs {
     int64_t *tok_hist, *sos;
     int32_t* par_hist;
     int* flags;  // [0] done, [1] steps_run, [2..2+L) per-step EOS counters
+    float* ekeys;
+    int* kflag;
 };
 template <typename A>
-static void beam_layout(A& a, int B, int K, int L, int E, int H, int C, int64_t V, BeamWs* ws) {
+static void beam_layout(A& a, int B, int K, int T, int L, int E, int H, int C, int64_t V, BeamWs* ws) {
     const int N = B * K;
     StepWs sw;
     step_layout(a, N, E, H, C, V, &sw);
@@ -572,7 +578,10 @@ static void beam_layout(A& a, int B, int K, int L, int E, int H, int C, int64_t 
     int64_t* sos = (int64_t*)a.template take<int64_t>((size_t)B);
     int32_t* par_hist = (int32_t*)a.template take<int32_t>((size_t)L * N);
     int* flags = (int*)a.template take<int>((size_t)L + 2);
+    float* ekeys = (float*)a.template take<float>((size_t)B * T * C);   // exp(2·keys) for the factored attention scores
+    int* kflag = (int*)a.template take<int>((size_t)B);
     if (ws) {
+        ws->ekeys = ekeys; ws->kflag = kflag;
         ws->step = sw; ws->logits = logits; ws->lse = lse; ws->prep = prep; ws->prep_bytes = prep_bytes; ws->summ = summ; ws->h_a = h_a; ws->h_b = h_b; ws->nll = nll;
         ws->tok_hist = tok_hist; ws->sos = sos; ws->par_hist = par_hist; ws->flags = flags;
     }
@@ -581,8 +590,7 @@ static void beam_layout(A& a, int B, int K, int L, int E, int H, int C, int64_t 
 
 extern "C" size_t vag_beam_decode_workspace_bytes(int B, int K, int T, int L, int E, int H, int C, int64_t V) {
     SizerAdapter s;
-    beam_layout(s, B, K, L, E, H, C, V, nullptr);
-    (void)T;
+    beam_layout(s, B, K, T, L, E, H, C, V, nullptr);
     return s.s.total();
 }
 
@@ -631,7 +639,7 @@ extern "C" int vag_beam_decode_f32(const vag_decoder_weights* w, const float* h0
     const int N = B * K;
     ArenaAdapter ar(workspace, workspace_bytes);
     BeamWs ws;
-    beam_layout(ar, B, K, L, E, H, C, V, &ws);
+    beam_layout(ar, B, K, T, L, E, H, C, V, &ws);
     if (ar.a.overflow) {
         set_error("vag_beam_decode_f32: workspace %zu B too small", workspace_bytes);
         return VAG_ERR_WORKSPACE;
@@ -652,6 +660,11 @@ extern "C" int vag_beam_decode_f32(const vag_decoder_weights* w, const float* h0
         prepared_register(gemm, w, pr);
         VAG_TRY(fused_setup(w, ws.step, N, K, pr, &fused));
         fused.done = done;
+        if (fused.ok && (C % 4 == 0) && !getenv("VAG_ATTN_SINGLE_EXP")) {   // factored attention scores: exp(2·keys) once per call
+            VAG_TRY(attn_exp_keys(ws.ekeys, ws.kflag, keys, B, T, C, st));
+            fused.ekeys = ws.ekeys;
+            fused.kflag = ws.kflag;
+        }
     }
     const int nonce = host_progress ? progress_nonce() : 0;
     constexpr int kLookahead = 4;     // steps the host may enqueue ahead of the device when it polls host_progress
@@ -745,7 +758,7 @@ extern "C" int vag_greedy_decode_f32(const vag_decoder_weights* w, const float* 
     cudaStream_t st = (cudaStream_t)stream;
     ArenaAdapter ar(workspace, workspace_bytes);
     BeamWs ws;
-    beam_layout(ar, B, 1, L, w->E, w->H, w->C, w->V, &ws);
+    beam_layout(ar, B, 1, T, L, w->E, w->H, w->C, w->V, &ws);
     if (ar.a.overflow) {
         set_error("vag_greedy_decode_f32: workspace %zu B too small (use vag_beam_decode_workspace_bytes with K=1)", workspace_bytes);
         return VAG_ERR_WORKSPACE;
