@@ -402,6 +402,11 @@ def main():
         compare(r64, o64, "fp64")
         fix["ref_fp32"], fix["ref_fp64"] = r32, r64
         torch.save(fix, GOLD / f"tiny_{attn}.pt")
+        if attn == "dot":
+            # whole-module pickles the way the reference's driver writes its checkpoints (nmt_multimodal_beam_DE.py:491-519):
+            # the fixtures of vag_nmt_b200.checkpoint_compat (the fp64 cast above is undone first: same weights as params_mm / params_tm)
+            torch.save(mm.float(), GOLD / "ref_module_tiny_mm.pt")
+            torch.save(tm.float(), GOLD / "ref_module_tiny_tm.pt")
 
     if "--only-tiny" in sys.argv:
         return

@@ -215,3 +215,22 @@ def test_fused_step_selection_variants_token_exact(env, monkeypatch, full_de):
     with torch.no_grad():
         want = O.multimodal_beamsearch_decode(cpu_params(mm), big.src, big.src_lengths, big.im, 12, 12)
     assert got == want
+
+
+def test_reference_whole_module_checkpoint_decodes_like_the_reference(tiny_dot):
+    """A torch.save(model) file written by the real reference (nmt_multimodal_beam_DE.py:491-519 format), loaded through
+    checkpoint_compat with the reference package absent, reproduces the reference's tokens and losses."""
+    import vag_nmt_b200 as vag
+    from conftest import GOLD
+    from vag_nmt_b200.checkpoint_compat import load_reference_module
+    fix = tiny_dot
+    b, ref, ref64 = fix["batch"], fix["ref_fp32"], fix["ref_fp64"]
+    mm = load_reference_module(GOLD / "ref_module_tiny_mm.pt", "cuda")
+    tm = load_reference_module(GOLD / "ref_module_tiny_tm.pt", "cuda")
+    for K in fix["beams"]:
+        assert mm.beamsearch_decode(b["src"], b["src_lengths"], b["im"], beam_size=K, max_length=fix["max_length"]) == ref[f"decode_k{K}"]
+        assert tm.beamsearch_decode(b["src"], b["src_lengths"], beam_size=K, max_length=fix["max_length"]) == ref[f"decode_text_k{K}"]
+    out = mm(b["src"], b["src_lengths"], b["tgt"], b["im"], 1.0, criterion_mt=_crit(fix["cfg"]["tgt_size"], "cuda"),
+             criterion_vse=vag.PairwiseRankingLoss(margin=0.1))
+    got = torch.stack([x.reshape(()) for x in out]).cpu().double()
+    assert float(((got - ref64["fwd_tf"]).abs() / ref64["fwd_tf"].abs()).max()) < TOL

@@ -8,7 +8,7 @@ from pathlib import Path
 import pytest
 import torch
 
-from conftest import build_mm, build_tm
+from conftest import GOLD, build_mm, build_tm
 
 ROOT = Path(__file__).resolve().parent.parent
 
@@ -116,3 +116,36 @@ def test_product_never_imports_the_oracle():
         assert "vag_oracle" not in src and "oracle." not in src.replace("CPU oracle.", ""), f
     for f in (ROOT / "vag_nmt_b200" / "csrc").glob("*.cu*"):
         assert "oracle" not in f.read_text(), f
+
+
+def test_reference_whole_module_checkpoints_load_without_the_reference(tiny_dot, tmp_path):
+    """torch.save(model) files written by the REAL reference (oracle/make_golden.py; the format of nmt_multimodal_beam_DE.py:491-519)
+    load into the drop-in classes with the reference package absent: same state_dict, same hyper-parameters."""
+    import pickle
+    import sys
+    from vag_nmt_b200.checkpoint_compat import load_reference_module, load_reference_stub
+    assert not any(m == "machine_translation_vision" or m.startswith("machine_translation_vision.") for m in sys.modules)
+    import vag_nmt_b200 as vag
+    mm = load_reference_module(GOLD / "ref_module_tiny_mm.pt")
+    tm = load_reference_module(GOLD / "ref_module_tiny_tm.pt")
+    assert isinstance(mm, vag.NMT_AttentionImagine_Seq2Seq_Beam_V11) and isinstance(tm, vag.NMT_Seq2Seq_Beam_V2)
+    for model, want in ((mm, tiny_dot["params_mm"]), (tm, tiny_dot["params_tm"])):
+        sd = model.state_dict()
+        assert list(sd.keys()) == list(want.keys())
+        for k in want:
+            assert torch.equal(sd[k], want[k]), k
+    cfg = tiny_dot["cfg"]
+    assert (mm.hidden_size, mm.shared_embedding_size, mm.tgt_size, mm.loss_w, mm.init_split, mm.tied_emb) == \
+        (cfg["hidden_size"], cfg["shared_embedding_size"], cfg["tgt_size"], 0.99, 0.5, True)
+    assert mm.decoder.out.weight is mm.decoder.embedding.weight            # the tie survives the conversion
+    stub = load_reference_stub(GOLD / "ref_module_tiny_mm.pt")
+    assert stub._ref_class.endswith("NMT_AttentionImagine_Seq2Seq_Beam_V11.NMT_AttentionImagine_Seq2Seq_Beam_V11")
+    # the resolver is an allow-list: a pickle naming anything else is refused
+    evil = tmp_path / "evil.pt"
+    class Boom:
+        def __reduce__(self):
+            import os
+            return (os.system, ("true",))
+    torch.save({"x": Boom()}, evil)
+    with pytest.raises(pickle.UnpicklingError):
+        load_reference_stub(evil)
