@@ -212,27 +212,14 @@ __device__ __forceinline__ float sum4_v_over_one_plus_exp2(const float4& v, floa
 // stays finite.  Valid while |q|, |k| ≤ 40 (both exponentials finite and normal); a CTA that sees anything larger takes the
 // single-exponential path — checked per sentence for k (attn_exp_keys) and per CTA for q.
 constexpr float kFactoredMaxAbs = 40.0f;
-// exp(2x) = 2^(x·2·log2e) with the rounding of the product compensated: u_hi = rn(x·c_hi), the exact residual of that product
-// plus x·c_lo goes into a first-order correction, so the result carries only ex2.approx's own error (≤ 2 ulp) instead of an
-// argument error that grows with |x| — six instructions against ~35 for the range-checked expf.
-__device__ __forceinline__ float exp2x_comp(float x) {
-    constexpr float c_hi = 2.88539004f;                 // rn(2·log2(e))
-    constexpr float c_lo = 4.05197e-08f;                // 2·log2(e) − c_hi
-    const float u = x * c_hi;
-    const float err = fmaf(x, c_lo, fmaf(x, c_hi, -u));
-    float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(u));
-    return fmaf(e, err * 0.693147182f, e);
-}
+
 __device__ __forceinline__ float sum4_v_over_one_plus_prod(const float4& v, const float4& eq, const float4& ek) {
     const float a0 = fminf(fmaf(eq.x, ek.x, 1.0f), 1073741824.0f), a1 = fminf(fmaf(eq.y, ek.y, 1.0f), 1073741824.0f);
     const float a2 = fminf(fmaf(eq.z, ek.z, 1.0f), 1073741824.0f), a3 = fminf(fmaf(eq.w, ek.w, 1.0f), 1073741824.0f);
     const float p01 = a0 * a1, p23 = a2 * a3;
     const float n01 = fmaf(v.x, a1, v.y * a0), n23 = fmaf(v.z, a3, v.w * a2);
     const float num = fmaf(n01, p23, n23 * p01);
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p01 * p23));
-    return num * r;
+    return num * rcp_approx(p01 * p23);
 }
 
 // ekeys = exp(2·keys) (precise), kflag[b] = 1 when sentence b holds a key outside ±kFactoredMaxAbs.  One block per (sentence, chunk).

@@ -123,5 +123,22 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 __device__ __forceinline__ float sigmoidf_precise(float x) { return 1.0f / (1.0f + expf(-x)); }
+// exp(2x) = 2^(x·2·log2e) with the rounding of the product compensated: u = rn(x·c_hi), the exact residual of that product plus
+// x·c_lo goes into a first-order correction, so the result carries only ex2.approx's own error (≤ 2 ulp) instead of an argument
+// error that grows with |x| — six instructions against ~35 for the range-checked expf.  Overflows to +inf / underflows to 0 cleanly.
+__device__ __forceinline__ float exp2x_comp(float x) {
+    constexpr float c_hi = 2.88539004f;                 // rn(2·log2(e))
+    constexpr float c_lo = 4.05197e-08f;                // 2·log2(e) − c_hi
+    const float u = x * c_hi;
+    const float err = fmaf(x, c_lo, fmaf(x, c_hi, -u));
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(u));
+    return fmaf(e, err * 0.693147182f, e);
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 
 }  // namespace vag

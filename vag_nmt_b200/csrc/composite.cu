@@ -88,6 +88,10 @@ struct Planes {
 // (E, H, C, V): the same code sizes the buffer, fills it and finds the pieces again in a later call.
 struct Prepared {
     Planes g1i, g1h, ah, ae, c2h, g2i, g2h, ro, out, emb, ini;
+    Planes g1h_p, g2i_p, g2h_p;   // row-permuted copies for the GRU-fused contraction (gru_pair.cuh)
+    float* gb1 = nullptr;         // [4][H] unit-major biases of gru_1 (input side in the per-token table) and gru_2
+    float* gb2 = nullptr;
+    float* scratch = nullptr;     // [3H, max(E, H)] fp32 staging of a permuted matrix
     float* b_ro = nullptr;
     float* g1 = nullptr;   // [V, 3H] table  Emb·W_ihᵀ + b_ih  of gru_1: its input pre-activations depend on the token only
 };
@@ -109,9 +113,15 @@ static void prepared_layout(A& a, int E, int H, int C, int64_t V, Prepared* p) {
     planes(p ? &p->out : nullptr, V, E);
     planes(p ? &p->emb : nullptr, V, E);
     planes(p ? &p->ini : nullptr, H, C);
+    planes(p ? &p->g1h_p : nullptr, 3 * H, H);
+    planes(p ? &p->g2i_p : nullptr, 3 * H, H);
+    planes(p ? &p->g2h_p : nullptr, 3 * H, H);
+    float* gb1 = (float*)a.template take<float>((size_t)4 * H);
+    float* gb2 = (float*)a.template take<float>((size_t)4 * H);
+    float* scratch = (float*)a.template take<float>((size_t)3 * H * (E > H ? E : H));
     float* b_ro = (float*)a.template take<float>((size_t)E);
     float* g1 = (float*)a.template take<float>((size_t)V * 3 * H);
-    if (p) { p->b_ro = b_ro; p->g1 = g1; }
+    if (p) { p->b_ro = b_ro; p->g1 = g1; p->gb1 = gb1; p->gb2 = gb2; p->scratch = scratch; }
 }
 static bool prepared_supported(const vag_decoder_weights* w, int mode) {
     const int E = w->E, H = w->H, C = w->C;
@@ -143,6 +153,13 @@ static int prepared_fill(const vag_decoder_weights* w, Prepared& pr, cudaStream_
     VAG_TRY(split(pr.ro, w->w3_w, E, E, H, Kt));
     VAG_TRY(split(pr.ro, w->w2_w, E, C, H + E, Kt));
     VAG_TRY(bias_sum3(pr.b_ro, w->w1_b, w->w3_b, w->w2_b, E, st));
+    if (H % 32 == 0) {   // GRU-fused contraction: permuted matrices + unit-major biases
+        VAG_TRY(tc_gru_prepare_weight(pr.g1h_p.hi, pr.g1h_p.lo, w->gru1_w_hh, H, H, true, pr.scratch, st));
+        VAG_TRY(tc_gru_prepare_weight(pr.g2i_p.hi, pr.g2i_p.lo, w->gru2_w_ih, H, H, false, pr.scratch, st));
+        VAG_TRY(tc_gru_prepare_weight(pr.g2h_p.hi, pr.g2h_p.lo, w->gru2_w_hh, H, H, true, pr.scratch, st));
+        VAG_TRY(tc_gru_prepare_bias(pr.gb1, nullptr, w->gru1_b_hh, H, false, st));
+        VAG_TRY(tc_gru_prepare_bias(pr.gb2, w->gru2_b_ih, w->gru2_b_hh, H, true, st));
+    }
     // gru_1's input contraction once for EVERY token instead of once per step for every row: the same kernel on the same operand
     // rows, so each table row is bit-identical to what the per-step contraction produces
     if (V > 128) {
@@ -449,6 +466,7 @@ struct FusedStep {
     const int* done = nullptr;                      // device flag: every hypothesis has ended, later steps return at once
     const float* ekeys = nullptr;                   // exp(2·keys) [B, T, C] and its per-sentence range flags (attention.cu, factored form)
     const int* kflag = nullptr;
+    bool gru_fused = false;                         // the two GRU cells run as gru_pair_kernel (contractions + gates in one launch)
     SplitDst cat_e(int H) const { SplitDst d = cat; d.hi += H; if (d.lo) d.lo += H; return d; }
     SplitDst cat_c(int H, int E) const { SplitDst d = cat; d.hi += H + E; if (d.lo) d.lo += H + E; return d; }
 };
@@ -476,6 +494,7 @@ static int fused_setup(const vag_decoder_weights* w, const StepWs& ws, int n_row
     planes(&f->cat, Kt);
     if (ar.overflow) return VAG_OK;
     f->ok = true;
+    f->gru_fused = tc_gru_supported(n_rows, H, H, H) && !getenv("VAG_GRU_UNFUSED");
     return VAG_OK;
 }
 
@@ -492,16 +511,36 @@ static int decoder_step_fused(const FusedStep& f, const vag_decoder_weights* w, 
                     int* tw) {
         return tc_gemm(y, ldy, x.hi, x.lo, x.ld, we.hi, we.lo, we.ld, bias, rows, K, N, 0, st, sm, tw);
     };
-    if (!f.g1) VAG_TRY(gemm(ws.gi, 3 * H, ce, pr.g1i, w->gru1_b_ih, E, 3 * H, nullptr, nullptr));           // NMT_Decoder.py:121
-    VAG_TRY(gemm(ws.gh, 3 * H, f.hprev, pr.g1h, w->gru1_b_hh, H, 3 * H, nullptr, nullptr));
-    if (f.g1) VAG_TRY(gru_gates_split(ws.h1, H, f.g1, 3 * H, ws.gh, 3 * H, h_prev, H, rows, H, f.h1, st, tokens, V, f.done));
-    else VAG_TRY(gru_gates_split(ws.h1, H, ws.gi, 3 * H, ws.gh, 3 * H, h_prev, H, rows, H, f.h1, st, nullptr, 0, f.done));
+    const bool fused_cells = f.gru_fused && rows > 128;
+    if (fused_cells && f.g1) {   // gru_1: hidden contraction + per-token input pre-activations + gates in one launch  (NMT_Decoder.py:121)
+        GruCall g;
+        g.hh = f.hprev.hi; g.hl = f.hprev.lo; g.ldh = f.hprev.ld; g.Kh = H;
+        g.whh_h = pr.g1h_p.hi; g.whh_l = pr.g1h_p.lo;
+        g.bias4 = pr.gb1; g.g1 = f.g1; g.tokens = tokens; g.V = V;
+        g.h_prev = h_prev; g.h_out = ws.h1; g.out = f.h1; g.rows = rows; g.H = H;
+        VAG_TRY(tc_gru(g, st));
+    } else {
+        if (!f.g1) VAG_TRY(gemm(ws.gi, 3 * H, ce, pr.g1i, w->gru1_b_ih, E, 3 * H, nullptr, nullptr));
+        VAG_TRY(gemm(ws.gh, 3 * H, f.hprev, pr.g1h, w->gru1_b_hh, H, 3 * H, nullptr, nullptr));
+        if (f.g1) VAG_TRY(gru_gates_split(ws.h1, H, f.g1, 3 * H, ws.gh, 3 * H, h_prev, H, rows, H, f.h1, st, tokens, V, f.done));
+        else VAG_TRY(gru_gates_split(ws.h1, H, ws.gi, 3 * H, ws.gh, 3 * H, h_prev, H, rows, H, f.h1, st, nullptr, 0, f.done));
+    }
     VAG_TRY(gemm(ws.q, C, f.h1, pr.ah, nullptr, H, C, nullptr, nullptr));                                    // :47
     VAG_TRY(attention_mlp_split(cc, ws.q, C, keys, ctx, w->attn_v, mask, rows, rows_per_sent, T, C, st, f.done, f.ekeys, f.kflag));     // :124-126
     VAG_TRY(tc_gemm_split_out(f.x2, cc.hi, cc.lo, Kt, pr.c2h.hi, pr.c2h.lo, pr.c2h.ld, nullptr, rows, C, H, 0, st));   // :127
-    VAG_TRY(gemm(ws.gi, 3 * H, f.x2, pr.g2i, w->gru2_b_ih, H, 3 * H, nullptr, nullptr));                     // :129
-    VAG_TRY(gemm(ws.gh, 3 * H, f.h1, pr.g2h, w->gru2_b_hh, H, 3 * H, nullptr, nullptr));
-    VAG_TRY(gru_gates_split(h_out, H, ws.gi, 3 * H, ws.gh, 3 * H, ws.h1, H, rows, H, f.cat, st, nullptr, 0, f.done));
+    if (fused_cells) {           // gru_2: both contractions + gates in one launch                                     (:129)
+        GruCall g;
+        g.xh = f.x2.hi; g.xl = f.x2.lo; g.ldx = f.x2.ld; g.Kx = H;
+        g.hh = f.h1.hi; g.hl = f.h1.lo; g.ldh = f.h1.ld; g.Kh = H;
+        g.wih_h = pr.g2i_p.hi; g.wih_l = pr.g2i_p.lo; g.whh_h = pr.g2h_p.hi; g.whh_l = pr.g2h_p.lo;
+        g.bias4 = pr.gb2;
+        g.h_prev = ws.h1; g.h_out = h_out; g.out = f.cat; g.rows = rows; g.H = H;
+        VAG_TRY(tc_gru(g, st));
+    } else {
+        VAG_TRY(gemm(ws.gi, 3 * H, f.x2, pr.g2i, w->gru2_b_ih, H, 3 * H, nullptr, nullptr));
+        VAG_TRY(gemm(ws.gh, 3 * H, f.h1, pr.g2h, w->gru2_b_hh, H, 3 * H, nullptr, nullptr));
+        VAG_TRY(gru_gates_split(h_out, H, ws.gi, 3 * H, ws.gh, 3 * H, ws.h1, H, rows, H, f.cat, st, nullptr, 0, f.done));
+    }
     VAG_TRY(tc_gemm_split_out(f.t, f.cat.hi, f.cat.lo, Kt, pr.ro.hi, pr.ro.lo, pr.ro.ld, pr.b_ro, rows, Kt, E, VAG_LIN_TANH, st));  // :137
     if (!logits) {   // beam loop: only the top-2 / Σexp summaries of every 128-column tile leave the projection
         if (summ_tile_w) *summ_tile_w = 128;

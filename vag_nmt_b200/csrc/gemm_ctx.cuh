@@ -35,6 +35,31 @@ struct TcDoneScope {
 };
 int bias_sum3(float* out, const float* a, const float* b, const float* c, int n, cudaStream_t st);
 
+// GRU cell fused into its contractions (gru_pair.cuh): h' = GRU(x, h_prev) from operand planes of x (phase X; absent when the
+// input pre-activations come from a per-token table g1) and of h_prev (phase H) against PERMUTED weight planes
+// (tc_gru_prepare_weight); writes h' as fp32 and as operand planes.
+struct GruCall {
+    const void *xh = nullptr, *xl = nullptr;   // x planes [rows, Kx], pitch ldx
+    int64_t ldx = 0;
+    int Kx = 0;
+    const void *hh = nullptr, *hl = nullptr;   // h_prev planes [rows, Kh], pitch ldh
+    int64_t ldh = 0;
+    int Kh = 0;
+    const void *wih_h = nullptr, *wih_l = nullptr, *whh_h = nullptr, *whh_l = nullptr;   // permuted weight planes [3H, K]
+    const float* bias4 = nullptr;              // [4][H] b_r, b_z, b_in, b_hn (tc_gru_prepare_bias)
+    const float* g1 = nullptr;                 // [V, 3H] per-token input pre-activations (Kx == 0)
+    const int64_t* tokens = nullptr;
+    int64_t V = 0;
+    const float* h_prev = nullptr;             // [rows, H] fp32
+    float* h_out = nullptr;                    // [rows, H] fp32 (must not alias h_prev)
+    SplitDst out;                              // operand planes of h'
+    int rows = 0, H = 0;
+};
+bool tc_gru_supported(int rows, int H, int Kx, int Kh);
+int tc_gru(const GruCall& c, cudaStream_t st);
+int tc_gru_prepare_weight(void* hi, void* lo, const float* w, int H, int K, bool hidden, float* scratch, cudaStream_t st);
+int tc_gru_prepare_bias(float* out4h, const float* b_ih, const float* b_hh, int H, bool with_ih, cudaStream_t st);
+
 struct GemmCtx {
     struct Ent {
         const void* src;

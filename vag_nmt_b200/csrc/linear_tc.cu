@@ -1293,6 +1293,8 @@ vocab_top2_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_
     }
 }
 
+#include "gru_pair.cuh"
+
 // ------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1572,6 +1574,61 @@ int tc_gemm_top2(float4* summ, const void* xh, const void* xl, int64_t ldxs, con
         if (!attr_set[2]) { VAG_CUDA(cudaFuncSetAttribute(vocab_top2_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, V_SMEM_BYTES)); attr_set[2] = true; }
         VAG_CUDA(launch_pdl(vocab_top2_pair_kernel<2>, dim3(grid), dim3(576), V_SMEM_BYTES, st, mxh, mxl, mwh, mwl, bias, rows, K, N, summ, g_tc_dbg, g_tc_done));
     }
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
+// GRU cell fused into its contractions (gru_pair.cuh).  16-bit modes, rows > 128, H % 32 == 0, K % 8 == 0.
+bool tc_gru_supported(int rows, int H, int Kx, int Kh) {
+    const int mode = gemm_mode();
+    return (mode == 1 || mode == 2) && rows > 128 && H % 32 == 0 && Kh >= 32 && Kh % 8 == 0 && (Kx == 0 || (Kx >= 32 && Kx % 8 == 0));
+}
+int tc_gru(const GruCall& c, cudaStream_t st) {
+    const int mode = gemm_mode();
+    if (!tc_gru_supported(c.rows, c.H, c.Kx, c.Kh) || !c.out.hi || (c.out.ld & 7) || (reinterpret_cast<uintptr_t>(c.out.hi) & 15) ||
+        (mode == 1 && (!c.out.lo || (reinterpret_cast<uintptr_t>(c.out.lo) & 15))) || (c.Kx == 0) != (c.g1 != nullptr)) {
+        set_error("tc_gru: unsupported shape / mode / output planes");
+        return VAG_ERR_UNSUPPORTED;
+    }
+    CUtensorMap mxh, mxl, mhh, mhl, mwih, mwil, mwhh, mwhl;
+    VAG_TRY(make_map(&mhh, c.hh, c.rows, c.Kh, c.ldh, 128, true, Q_ROWB));
+    VAG_TRY(make_map(&mhl, mode == 2 ? c.hh : c.hl, c.rows, c.Kh, c.ldh, 128, true, Q_ROWB));
+    VAG_TRY(make_map(&mwhh, c.whh_h, 3 * c.H, c.Kh, c.Kh, 48, true, Q_ROWB));
+    VAG_TRY(make_map(&mwhl, mode == 2 ? c.whh_h : c.whh_l, 3 * c.H, c.Kh, c.Kh, 48, true, Q_ROWB));
+    if (c.Kx) {
+        VAG_TRY(make_map(&mxh, c.xh, c.rows, c.Kx, c.ldx, 128, true, Q_ROWB));
+        VAG_TRY(make_map(&mxl, mode == 2 ? c.xh : c.xl, c.rows, c.Kx, c.ldx, 128, true, Q_ROWB));
+        VAG_TRY(make_map(&mwih, c.wih_h, 3 * c.H, c.Kx, c.Kx, 48, true, Q_ROWB));
+        VAG_TRY(make_map(&mwil, mode == 2 ? c.wih_h : c.wih_l, 3 * c.H, c.Kx, c.Kx, 48, true, Q_ROWB));
+    } else {
+        mxh = mhh; mxl = mhl; mwih = mwhh; mwil = mwhl;   // never dereferenced (no phase X)
+    }
+    GruArgs a;
+    a.bias = c.bias4; a.g1 = c.g1; a.tokens = c.tokens; a.V = c.V; a.h_prev = c.h_prev; a.h_out = c.h_out;
+    a.out_hi = c.out.hi; a.out_lo = c.out.lo; a.out_ld = c.out.ld; a.rows = c.rows; a.Kx = c.Kx; a.Kh = c.Kh; a.H = c.H; a.done = g_tc_done;
+    const int n_tiles = (c.H / 32) * ceil_div(c.rows, 256);
+    const int max_pairs = num_sms() / 2;
+    const int grid = 2 * (n_tiles < max_pairs ? n_tiles : max_pairs);
+    static bool attr_set[3] = {false, false, false};
+    if (mode == 1) {
+        if (!attr_set[1]) { VAG_CUDA(cudaFuncSetAttribute(gru_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES)); attr_set[1] = true; }
+        VAG_CUDA(launch_pdl(gru_pair_kernel<1>, dim3(grid), dim3(320), G_SMEM_BYTES, st, mxh, mxl, mhh, mhl, mwih, mwil, mwhh, mwhl, a));
+    } else {
+        if (!attr_set[2]) { VAG_CUDA(cudaFuncSetAttribute(gru_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES)); attr_set[2] = true; }
+        VAG_CUDA(launch_pdl(gru_pair_kernel<2>, dim3(grid), dim3(320), G_SMEM_BYTES, st, mxh, mxl, mhh, mhl, mwih, mwil, mwhh, mwhl, a));
+    }
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+// Permuted operand planes of one GRU matrix w [3H, K] (hidden: the hidden-state matrix' tile order) and the unit-major biases.
+int tc_gru_prepare_weight(void* hi, void* lo, const float* w, int H, int K, bool hidden, float* scratch, cudaStream_t st) {
+    if (H % 32) { set_error("tc_gru_prepare_weight: H must be a multiple of 32"); return VAG_ERR_UNSUPPORTED; }
+    gru_permute_rows_kernel<<<3 * H, 256, 0, st>>>(scratch, w, H, K, hidden ? 1 : 0);
+    VAG_LAUNCH_CHECK();
+    return tc_split(scratch, K, 3 * H, K, hi, lo, K, 0, st);
+}
+int tc_gru_prepare_bias(float* out4h, const float* b_ih, const float* b_hh, int H, bool with_ih, cudaStream_t st) {
+    gru_bias_kernel<<<ceil_div(H, 128), 128, 0, st>>>(out4h, b_ih, b_hh, H, with_ih ? 1 : 0);
     VAG_LAUNCH_CHECK();
     return VAG_OK;
 }
