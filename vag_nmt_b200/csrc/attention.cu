@@ -538,7 +538,15 @@ static int dispatch_attention_tuned(float* c_out, int64_t ld_c, float* alpha, co
         return launch_attention_tuned<MODE, RC, false>(c_out, ld_c, alpha, q, ld_q, keys, ctx, v, mask, rows, rows_per_sent, T, C, st, sd, done, ekeys, kflag); \
     } while (0)
     if (rows_per_sent == 1) VAG_ATT(1);
-    if (rows_per_sent <= 4) VAG_ATT(4);
+    // One CTA per sentence re-reads nothing, but with few sentences (the reference's eval batch of 16; 125 sentences per GPU when
+    // a 1000-sentence test set is sharded over 8 GPUs) it leaves most SMs idle and a single CTA's latency IS the kernel's
+    // duration: split a sentence's rows over several CTAs (each re-reads the sentence's keys / context from L2) until the grid
+    // holds about three CTAs per SM.
+    const int B = rows / rows_per_sent, slots = 3 * num_sms();
+    if (rows_per_sent <= 4 || B * ceil_div(rows_per_sent, 8) <= slots) {
+        if (rows_per_sent > 4 && B * ceil_div(rows_per_sent, 4) > slots) VAG_ATT(8);
+        VAG_ATT(4);
+    }
     if (rows_per_sent <= 8) VAG_ATT(8);
     if (rows_per_sent <= 12) VAG_ATT(12);
     VAG_ATT(16);

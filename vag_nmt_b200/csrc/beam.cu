@@ -530,8 +530,11 @@ struct SelCand {
     int tok2;      // ... and its column (0xFFFF: the slice has no second; -2: not loaded, read the summary again)
 };
 
-template <int KMAX>
-__global__ void __launch_bounds__(kSel2Threads)
+// NT = threads per sentence: 128 when there are enough sentences to fill the GPU (7 CTAs per SM), 512 for small batches (the
+// reference's eval batch of 16; a test set sharded over 8 GPUs), where the kernel's duration is ONE CTA's latency and that latency
+// is the summary scan (294 x K float4 loads per sentence, four in flight per thread): more workers per row shorten it fourfold.
+template <int KMAX, int NT>
+__global__ void __launch_bounds__(NT)
 beam_select_top2_kernel(const float4* __restrict__ summ /*[n_slices][n_rows]*/, int n_slices, int slice_w, int n_rows,
                         const uint16_t* __restrict__ t_hi, const uint16_t* __restrict__ t_lo, int64_t ld_t,
                         const uint16_t* __restrict__ w_hi, const uint16_t* __restrict__ w_lo, int64_t ld_w,
@@ -542,7 +545,7 @@ beam_select_top2_kernel(const float4* __restrict__ summ /*[n_slices][n_rows]*/, 
     if (done && *done) return;
     extern __shared__ float dyn[];
     const int b = blockIdx.x;
-    constexpr int NT = kSel2Threads, NW = NT / 32;
+    constexpr int NW = NT / 32;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int Kin = step == 0 ? 1 : K;
     const int n_sl = Kin * n_slices;                     // entry idx = slice·Kin + k (k fastest: coalesced summary reads)
@@ -1039,22 +1042,29 @@ int beam_select_top2(const float4* summ, int slice_w, SplitDst t, const uint16_t
     // VAG_SELECT_RECOMPUTE=1 (tests): never use a slice's stored runner-up, always recompute — exercises the rare path
     const char* fe = getenv("VAG_SELECT_RECOMPUTE");
     const int force = fe ? (fe[0] == '1' ? 1 : (fe[0] == '2' ? 2 : 0)) : 0;   // 2: timing experiments only (never recompute)
-#define VAG_SEL2(KM)                                                                                                          \
+    const bool wide = B <= 2 * num_sms();                                     // few sentences: 512 threads each (see the kernel)
+#define VAG_SEL2_NT(KM, NT_)                                                                                                  \
     do {                                                                                                                      \
         static size_t configured = 0;                                                                                         \
         if (smem > 48 * 1024 && smem > configured) {                                                                          \
-            VAG_CUDA(cudaFuncSetAttribute(beam_select_top2_kernel<KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            VAG_CUDA(cudaFuncSetAttribute(beam_select_top2_kernel<KM, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             configured = smem;                                                                                                \
         }                                                                                                                     \
-        beam_select_top2_kernel<KM><<<B, kSel2Threads, smem, st>>>(summ, n_slices, slice_w, B * Kin, t.hi, t.lo, t.ld, w_hi, w_lo, ld_w, bias, E, \
+        beam_select_top2_kernel<KM, NT_><<<B, NT_, smem, st>>>(summ, n_slices, slice_w, B * Kin, t.hi, t.lo, t.ld, w_hi, w_lo, ld_w, bias, E, \
                                                           t.mode, prev_tokens, nll, tokens_out, parents_out, K, (int)V, step,  \
                                                           avoid_double, done, fin_counter, force, tc_debug());                 \
+    } while (0)
+#define VAG_SEL2(KM)                                                                                                          \
+    do {                                                                                                                      \
+        if (wide) VAG_SEL2_NT(KM, 512);                                                                                       \
+        else VAG_SEL2_NT(KM, kSel2Threads);                                                                                   \
     } while (0)
     if (K <= 4) VAG_SEL2(4);
     else if (K <= 8) VAG_SEL2(8);
     else if (K <= 12) VAG_SEL2(12);
     else VAG_SEL2(16);
 #undef VAG_SEL2
+#undef VAG_SEL2_NT
     VAG_LAUNCH_CHECK();
     return VAG_OK;
 }
