@@ -392,7 +392,13 @@ typedef struct {              /* gradient outputs, same shapes as the weights (o
 } vag_decoder_grads;
 
 size_t vag_decoder_seq_workspace_bytes(int B, int T, int Tt, int E, int H, int C, int64_t V);
-/* tok_in int64 [Tt, B]: row 0 = <sos>; teacher != 0: rows 1.. hold tgt[:, :-1] (caller fills); else the kernel's own
+/* vag_decoder_seq_bwd_f32 `phases` — a mask, 15 = everything in one call:
+ *   1  head: d logits, d read-out (all steps at once)            2  the recurrent part + the path back into the encoder context
+ *   4  weight gradients of the vocabulary projection / read-out (need 1)      8  all other weight gradients (need 2)
+ * All phases of one backward pass share one workspace, untouched in between.  Nothing downstream of the decoder reads a weight
+ * gradient before the optimiser, so 4 and 8 may run on a second stream (they use private operand-plane scratch when called
+ * without 1 / 2): 4 beside the latency-bound recurrent part, 8 beside the encoder's back-propagation.
+ * tok_in int64 [Tt, B]: row 0 = <sos>; teacher != 0: rows 1.. hold tgt[:, :-1] (caller fills); else the kernel's own
  * arg-max feedback is written there.  tgt_t int64 [Tt, B].  loss_rows [B] = Σ_t NLL (nn.NLLLoss(weight, reduce=False)).
  * out_mask (optional, [Tt·B, E], values 0 or 1/(1-p)): the output dropout of NMT_Decoder.py:140-141 with a caller-drawn mask. */
 int vag_decoder_seq_fwd_f32(const vag_decoder_weights* w, const float* h0, const float* enc, const float* mask,
@@ -402,7 +408,7 @@ int vag_decoder_seq_fwd_f32(const vag_decoder_weights* w, const float* h0, const
 int vag_decoder_seq_bwd_f32(const vag_decoder_weights* w, const float* h0, const float* enc, const float* mask,
                             const int64_t* tok_in, const int64_t* tgt_t, const float* nll_weight, int B, int T, int Tt,
                             int tied, const vag_decoder_seq_saved* s, const float* out_mask, const float* dloss_rows,
-                            const vag_decoder_grads* g, float* d_h0, float* d_enc, void* workspace,
+                            const vag_decoder_grads* g, float* d_h0, float* d_enc, int phases, void* workspace,
                             size_t workspace_bytes, vag_stream_t stream);
 
 /* Encoder training pair: forward that keeps what BPTT needs and the backward through both directions of the packed

@@ -115,7 +115,7 @@ SIGNATURES = {
     "vag_init_mix_bwd_f32": (I, [P, P, P, P, F, I, I, I, P]),
     "vag_decoder_seq_workspace_bytes": (SZ, [I, I, I, I, I, I, I64]),
     "vag_decoder_seq_fwd_f32": (I, [P, P, P, P, P, P, P, I, I, I, I, P, P, P, P, SZ, P]),
-    "vag_decoder_seq_bwd_f32": (I, [P, P, P, P, P, P, P, I, I, I, I, P, P, P, P, P, P, P, SZ, P]),
+    "vag_decoder_seq_bwd_f32": (I, [P, P, P, P, P, P, P, I, I, I, I, P, P, P, P, P, P, I, P, SZ, P]),
     "vag_mul_f32": (I, [P, P, I64, P]),
     "vag_encoder_train_workspace_bytes": (SZ, [I, I, I, I]),
     "vag_encoder_train_fwd_f32": (I, [P, P, P, P, I, I, P, P, P, P, P, P, P, SZ, P]),

@@ -73,6 +73,37 @@ def _gbuf(p: torch.Tensor) -> torch.Tensor:
     return torch.empty_like(p)
 
 
+_side_streams = {}
+_pending_join = {}
+
+
+def _overlap_weight_gradients() -> bool:
+    import os
+    return os.environ.get("VAG_TRAIN_OVERLAP", "1") != "0"
+
+
+def _side_stream(dev: torch.device):
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    st = _side_streams.get(key)
+    if st is None:
+        st = _side_streams[key] = torch.cuda.Stream(device=dev)
+    return st
+
+
+def _join_after_backward(dev: torch.device, side) -> None:
+    """Make the stream the backward pass runs on wait for `side` when the pass ends (once per pass)."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if _pending_join.get(key):
+        return
+    _pending_join[key] = True
+
+    def join():
+        _pending_join[key] = False
+        torch.cuda.current_stream(dev).wait_stream(side)
+
+    torch.autograd.Variable._execution_engine.queue_callback(join)
+
+
 def _zeros(*shape, like):
     return torch.zeros(*shape, dtype=torch.float32, device=like.device)
 
@@ -345,13 +376,40 @@ class DecoderSeqFn(torch.autograd.Function):
             setattr(g, name, t.data_ptr())
         d_h0 = torch.empty_like(h0)
         d_enc = torch.empty_like(enc)
-        ws = ops.workspace(lib.vag_decoder_seq_workspace_bytes(B, Tn, Tt, E, H, Cd, V), dev)
-        with on_device(dev):
-            ops.check(lib.vag_decoder_seq_bwd_f32(C.byref(w), h0.data_ptr(), enc.data_ptr(), mask.data_ptr(), tok_in.data_ptr(),
-                                                  tgt_t.data_ptr(), weight.data_ptr() if has_weight else None, B, Tn, Tt,
-                                                  1 if tied else 0, C.byref(saved), out_mask.data_ptr() if has_out_mask else None,
-                                                  dloss_rows.contiguous().data_ptr(), C.byref(g),
-                                                  d_h0.data_ptr(), d_enc.data_ptr(), ws.data_ptr(), ws.numel(), ops.stream_ptr()))
+        # its own scratch slot: the weight-gradient phase may still be reading it while later backward Functions use the main one
+        ws = ops.workspace(lib.vag_decoder_seq_workspace_bytes(B, Tn, Tt, E, H, Cd, V), dev, slot="dec_bwd")
+        dl = dloss_rows.contiguous()
+
+        def run(phases):
+            with on_device(dev):
+                ops.check(lib.vag_decoder_seq_bwd_f32(C.byref(w), h0.data_ptr(), enc.data_ptr(), mask.data_ptr(), tok_in.data_ptr(),
+                                                      tgt_t.data_ptr(), weight.data_ptr() if has_weight else None, B, Tn, Tt,
+                                                      1 if tied else 0, C.byref(saved), out_mask.data_ptr() if has_out_mask else None,
+                                                      dl.data_ptr(), C.byref(g), d_h0.data_ptr(), d_enc.data_ptr(), phases,
+                                                      ws.data_ptr(), ws.numel(), ops.stream_ptr()))
+
+        # (only for a fresh pass: with gradients being ACCUMULATED autograd adds into p.grad on this stream right after this node)
+        if not _overlap_weight_gradients() or any(getattr(p, "grad", None) is not None for p in params):
+            run(15)
+        else:
+            # Everything d_h0 / d_enc depend on runs on this stream; the time-batched weight-gradient contractions — ~0.4 ms of
+            # tensor-core work nothing downstream reads before the optimiser — run on a second stream: the vocabulary / read-out
+            # ones beside the decoder's own latency-bound recurrent part, the rest beside the back-propagation of the encoder /
+            # pooling that autograd runs next.  The streams re-join when the backward pass ends (engine callback), i.e. before
+            # anybody can look at a gradient; inside a CUDA-graph capture the forks and the join become parallel graph branches.
+            main = torch.cuda.current_stream(dev)
+            side = _side_stream(dev)
+            run(1)                          # head: d logits, d read-out
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                run(4)                      # vocabulary / read-out weight gradients, beside the recurrent part
+            run(2)                          # recurrent part → d_h0, d_enc
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                run(8)                      # remaining weight gradients, beside whatever autograd runs next
+            for t in (store, tok_in, h0, enc, tgt_t, dl):     # freed when this node is done, read by the side stream until the join
+                t.record_stream(side)
+            _join_after_backward(dev, side)
         if tied:
             grads[19] = None          # out.weight IS the embedding: its gradient was accumulated into grads[0]
         return (d_h0, d_enc, None, None, None, None, None, None, *grads)

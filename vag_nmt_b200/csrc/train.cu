@@ -814,6 +814,9 @@ extern "C" size_t vag_decoder_seq_workspace_bytes(int B, int T, int Tt, int E, i
     size_t bwd = (size_t)R * (V + 4) * 4 + gemm_tc_scratch_bytes(std::max<int64_t>(V, 3 * H), std::max<int64_t>({(int64_t)C, (int64_t)3 * H, (int64_t)E}), std::max<int64_t>({(int64_t)R, (int64_t)B * T, (int64_t)3 * H})) +
                  gemm_tc_scratch_bytes(std::max<int64_t>(R, (int64_t)B * T), C, std::max<int64_t>(V + 8, 3 * H)) + (size_t)R * H * 4 + (size_t)R * E * 4 * 3 + (size_t)R * H * 4 * 2 + (size_t)R * C * 4 * 2 + (size_t)R * 3 * H * 4 * 4 +
                  (size_t)B * T * C * 4 + (size_t)B * H * 4 * 4 + (size_t)B * 3 * H * 4 * 4 + 65536;
+    // … and a second operand-plane scratch for the weight-gradient phases, which may run on another stream than the recurrent part
+    bwd += gemm_tc_scratch_bytes(std::max<int64_t>(V, 3 * H), std::max<int64_t>({(int64_t)C, (int64_t)3 * H, (int64_t)E}), std::max<int64_t>({(int64_t)R, (int64_t)B * T, (int64_t)3 * H})) +
+           gemm_tc_scratch_bytes(std::max<int64_t>(R, (int64_t)B * T), C, std::max<int64_t>(V + 8, 3 * H)) + 4096;
     return fwd > bwd ? fwd : bwd;
 }
 
@@ -925,10 +928,12 @@ extern "C" int vag_decoder_seq_fwd_f32(const vag_decoder_weights* w, const float
 extern "C" int vag_decoder_seq_bwd_f32(const vag_decoder_weights* w, const float* h0, const float* enc, const float* mask,
                                        const int64_t* tok_in, const int64_t* tgt_t, const float* nll_weight, int B, int T, int Tt,
                                        int tied, const vag_decoder_seq_saved* s, const float* out_mask, const float* dloss_rows,
-                                       const vag_decoder_grads* g, float* d_h0, float* d_enc, void* workspace,
+                                       const vag_decoder_grads* g, float* d_h0, float* d_enc, int phases, void* workspace,
                                        size_t workspace_bytes, vag_stream_t stream) {
     ModeScope ms(w ? w->precision : VAG_PREC_FP32);
     VAG_REQUIRE(w && h0 && enc && mask && tok_in && tgt_t && s && dloss_rows && g && d_h0 && d_enc, "vag_decoder_seq_bwd_f32: null pointer");
+    VAG_REQUIRE(phases >= 1 && phases <= 15, "vag_decoder_seq_bwd_f32: phases is a mask of 1 (head) | 2 (recurrent part) | 4 (read-out weight gradients) | 8 (other weight gradients)");
+    const bool do_head = phases & 1, do_rec = phases & 2, do_wg_ro = phases & 4, do_wg = phases & 8;
     cudaStream_t st = (cudaStream_t)stream;
     vag_stream_t vs = stream;
     const int E = w->E, H = w->H, C = w->C;
@@ -943,7 +948,10 @@ extern "C" int vag_decoder_seq_bwd_f32(const vag_decoder_weights* w, const float
                                                    std::max<int64_t>({(int64_t)R, (int64_t)B * T, (int64_t)3 * H})) +
                              gemm_tc_scratch_bytes(std::max<int64_t>(R, (int64_t)B * T), C, std::max<int64_t>(V + 8, 3 * H));
     char* tcs = ar.take<char>(tcs_bytes);
-    TcScratchScope tc_scope(tcs, tcs ? tcs_bytes : 0);
+    char* tcs_wg = ar.take<char>(tcs_bytes);
+    // the weight-gradient phases, called on their own, may overlap the recurrent part on another stream: private operand planes
+    const bool wg_only = !(phases & 3);
+    TcScratchScope tc_scope(wg_only ? tcs_wg : tcs, (wg_only ? tcs_wg : tcs) ? tcs_bytes : 0);
     float* d_t = ar.take<float>((size_t)R * E);
     float* du = ar.take<float>((size_t)R * E);
     float* dh2_dir = ar.take<float>((size_t)R * H);
@@ -962,6 +970,7 @@ extern "C" int vag_decoder_seq_bwd_f32(const vag_decoder_weights* w, const float
         set_error("vag_decoder_seq_bwd_f32: workspace %zu B too small", workspace_bytes);
         return VAG_ERR_WORKSPACE;
     }
+    if (do_head) {
     // ---- batched over all steps: vocabulary projection and read-out
     // (the pad column of dlogits is never read: the operand split, the column sum and the transposed read all stop at V)
     nll_bwd_kernel<<<R, 256, 0, st>>>(dlogits, ldd, s->logits_all, ldl, s->lse_all, tgt_t, nll_weight, dloss_rows, V, B);   // all steps
@@ -971,10 +980,6 @@ extern "C" int vag_decoder_seq_bwd_f32(const vag_decoder_weights* w, const float
         if (r < 0) return r;
         if (r == 0) VAG_TRY(gemm_g(d_t, E, dlogits, ldd, 1, w->out_w, E, 1, R, E, (int)V, 0.f, st));
     }
-    float* d_out_w = tied ? g->emb : g->out_w;                                                       // tied: accumulate into dEmb later
-    if (!tied) VAG_CUDA(cudaMemsetAsync(g->emb, 0, sizeof(float) * (size_t)V * E, st));            // tied: the contraction below overwrites all of it
-    VAG_TRY(gemm_g(d_out_w, E, dlogits, 1, ldd, s->t_all, E, 1, (int)V, E, R, 0.f, st));            // dlogitsᵀ · t_all
-    VAG_TRY(vag_colsum_f32(g->out_b, dlogits, ldd, R, (int)V, 0, vs));
     if (out_mask) {
         tanh_dropout_bwd_kernel<<<grid_for((int64_t)R * E), 256, 0, st>>>(du, d_t, s->t_all, out_mask, (int64_t)R * E);
         VAG_LAUNCH_CHECK();
@@ -984,12 +989,8 @@ extern "C" int vag_decoder_seq_bwd_f32(const vag_decoder_weights* w, const float
     VAG_TRY(gemm_g(dh2_dir, H, du, E, 1, w->w1_w, H, 1, R, H, E, 0.f, st));
     VAG_TRY(gemm_g(d_e, E, du, E, 1, w->w3_w, E, 1, R, E, E, 0.f, st));
     VAG_TRY(gemm_g(dc_dir, C, du, E, 1, w->w2_w, C, 1, R, C, E, 0.f, st));
-    VAG_TRY(gemm_g(g->w1_w, H, du, 1, E, s->h2_all, H, 1, E, H, R, 0.f, st));
-    VAG_TRY(gemm_g(g->w3_w, E, du, 1, E, s->e_all, E, 1, E, E, R, 0.f, st));
-    VAG_TRY(gemm_g(g->w2_w, C, du, 1, E, s->c_all, C, 1, E, C, R, 0.f, st));
-    VAG_TRY(vag_colsum_f32(g->w1_b, du, E, R, E, 0, vs));
-    VAG_CUDA(cudaMemcpyAsync(g->w2_b, g->w1_b, sizeof(float) * E, cudaMemcpyDeviceToDevice, st));
-    VAG_CUDA(cudaMemcpyAsync(g->w3_b, g->w1_b, sizeof(float) * E, cudaMemcpyDeviceToDevice, st));
+    }
+    if (do_rec) {
     // ---- recurrent part, reverse time
     VAG_CUDA(cudaMemsetAsync(dkeys, 0, sizeof(float) * (size_t)B * T * C, st));
     VAG_CUDA(cudaMemsetAsync(d_enc, 0, sizeof(float) * (size_t)B * T * C, st));
@@ -1073,6 +1074,25 @@ extern "C" int vag_decoder_seq_bwd_f32(const vag_decoder_weights* w, const float
         VAG_TRY(gemm_g(dh_next, H, dgh1, 3 * H, 1, w->gru1_w_hh, H, 1, B, H, 3 * H, 1.f, st));          // dh_prev = dh1·z + dgh1 · W_hh1
     }
     VAG_CUDA(cudaMemcpyAsync(d_h0, dh_next, sizeof(float) * (size_t)B * H, cudaMemcpyDeviceToDevice, st));
+    // ---- hoisted keys: the path back into the encoder context
+    VAG_TRY(gemm_g(d_enc, C, dkeys, C, 1, w->attn_e_w, C, 1, B * T, C, C, 1.f, st));
+    }
+    if (do_wg_ro) {
+    // Weight gradients: contractions over all Tt·B rows of what the recurrent part left in the workspace.  Nothing downstream of
+    // the decoder reads them before the optimiser, so a caller may run this phase on a second stream while the encoder's
+    // back-propagation proceeds (autograd.DecoderSeqFn).
+    float* d_out_w = tied ? g->emb : g->out_w;                                                       // tied: accumulate into dEmb later
+    if (!tied) VAG_CUDA(cudaMemsetAsync(g->emb, 0, sizeof(float) * (size_t)V * E, st));            // tied: the contraction below overwrites all of it
+    VAG_TRY(gemm_g(d_out_w, E, dlogits, 1, ldd, s->t_all, E, 1, (int)V, E, R, 0.f, st));            // dlogitsᵀ · t_all
+    VAG_TRY(vag_colsum_f32(g->out_b, dlogits, ldd, R, (int)V, 0, vs));
+    VAG_TRY(gemm_g(g->w1_w, H, du, 1, E, s->h2_all, H, 1, E, H, R, 0.f, st));
+    VAG_TRY(gemm_g(g->w3_w, E, du, 1, E, s->e_all, E, 1, E, E, R, 0.f, st));
+    VAG_TRY(gemm_g(g->w2_w, C, du, 1, E, s->c_all, C, 1, E, C, R, 0.f, st));
+    VAG_TRY(vag_colsum_f32(g->w1_b, du, E, R, E, 0, vs));
+    VAG_CUDA(cudaMemcpyAsync(g->w2_b, g->w1_b, sizeof(float) * E, cudaMemcpyDeviceToDevice, st));
+    VAG_CUDA(cudaMemcpyAsync(g->w3_b, g->w1_b, sizeof(float) * E, cudaMemcpyDeviceToDevice, st));
+    }
+    if (do_wg) {
     // ---- weight gradients, batched over steps
     VAG_TRY(gemm_g(g->gru2_w_ih, H, dgi2_all, 1, 3 * H, s->x2_all, H, 1, 3 * H, H, R, 0.f, st));
     VAG_TRY(vag_colsum_f32(g->gru2_b_ih, dgi2_all, 3 * H, R, 3 * H, 0, vs));
@@ -1089,9 +1109,9 @@ extern "C" int vag_decoder_seq_bwd_f32(const vag_decoder_weights* w, const float
     VAG_TRY(vag_colsum_f32(g->gru1_b_hh, dgh1_all, 3 * H, R, 3 * H, 0, vs));
     VAG_TRY(gemm_g(d_e, E, dgi1_all, 3 * H, 1, w->gru1_w_ih, E, 1, R, E, 3 * H, 1.f, st));              // de += dgi1 · W_ih1
     VAG_TRY(vag_embed_bwd_f32(g->emb, d_e, E, tok_in, R, E, V, vs));                                     // (+ dOutW already inside when tied)
-    // ---- hoisted keys: dW_attn_e and the path back into the encoder context
+    // ---- hoisted keys: dW_attn_e
     VAG_TRY(gemm_g(g->attn_e_w, C, dkeys, 1, C, enc, C, 1, C, C, B * T, 0.f, st));
-    VAG_TRY(gemm_g(d_enc, C, dkeys, C, 1, w->attn_e_w, C, 1, B * T, C, C, 1.f, st));
+    }
     return VAG_OK;
 }
 
