@@ -209,9 +209,25 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
                 if (id < 0 || id >= args.V) id = 0;
                 g1_row = args.g1 + id * 3 * (int64_t)H;
             }
+            // Operands that do not depend on the accumulators — this row's previous state and, for gru_1, its token's table row —
+            // are requested for BOTH unit passes before the wait for the tile's MMAs, so their L2 latency (every lane reads its own
+            // row: 32 lines per load instruction) overlaps the tensor work.  (Measured: no change in the kernel's duration — the
+            // kernel is bound by L2 → shared-memory operand traffic, 44 KB per K block and CTA for 12 MMAs of N = 96, not by this
+            // epilogue; kept because it costs nothing.)
+            const int ub = tn * UNITS + uh * 16;          // first of this warp's 16 units
+            float hp[16], tr[16], tz[16], tq[16];
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                *reinterpret_cast<float4*>(hp + 4 * q4) = *reinterpret_cast<const float4*>(hp_row + ub + 4 * q4);
+                if (table) {
+                    *reinterpret_cast<float4*>(tr + 4 * q4) = *reinterpret_cast<const float4*>(g1_row + ub + 4 * q4);
+                    *reinterpret_cast<float4*>(tz + 4 * q4) = *reinterpret_cast<const float4*>(g1_row + H + ub + 4 * q4);
+                    *reinterpret_cast<float4*>(tq + 4 * q4) = *reinterpret_cast<const float4*>(g1_row + 2 * H + ub + 4 * q4);
+                }
+            }
             mbar_wait(&tfull_bar[a], (it >> 1) & 1);
             tcgen05_fence_after();
-#pragma unroll 1
+#pragma unroll
             for (int p = 0; p < 2; ++p) {
                 const int uc = uh * 16 + p * 8;            // first unit of this pass inside the tile
                 const int u0 = tn * UNITS + uc;            // … and in the layer
@@ -227,21 +243,13 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
                     if (!table) VAG_TMEM_LD8(ci, taddr + 128u + C_GIN);
                     VAG_TMEM_LD8(chn, taddr + 128u + C_GHN);
                 }
-                // operands that do not depend on the accumulators travel while the TMEM loads complete
-                float hp[8], br[8], bz[8], bi[8], bh[8], tr[8], tz[8], tn_[8];
-                *reinterpret_cast<float4*>(hp) = *reinterpret_cast<const float4*>(hp_row + u0);
-                *reinterpret_cast<float4*>(hp + 4) = *reinterpret_cast<const float4*>(hp_row + u0 + 4);
+                float br[8], bz[8], bi[8], bh[8];          // biases: the same addresses for every lane (one L1 line per load)
 #pragma unroll
                 for (int q4 = 0; q4 < 2; ++q4) {
                     *reinterpret_cast<float4*>(br + 4 * q4) = __ldg(reinterpret_cast<const float4*>(args.bias + u0 + 4 * q4));
                     *reinterpret_cast<float4*>(bz + 4 * q4) = __ldg(reinterpret_cast<const float4*>(args.bias + H + u0 + 4 * q4));
                     *reinterpret_cast<float4*>(bi + 4 * q4) = __ldg(reinterpret_cast<const float4*>(args.bias + 2 * H + u0 + 4 * q4));
                     *reinterpret_cast<float4*>(bh + 4 * q4) = __ldg(reinterpret_cast<const float4*>(args.bias + 3 * H + u0 + 4 * q4));
-                    if (table) {
-                        *reinterpret_cast<float4*>(tr + 4 * q4) = *reinterpret_cast<const float4*>(g1_row + u0 + 4 * q4);
-                        *reinterpret_cast<float4*>(tz + 4 * q4) = *reinterpret_cast<const float4*>(g1_row + H + u0 + 4 * q4);
-                        *reinterpret_cast<float4*>(tn_ + 4 * q4) = *reinterpret_cast<const float4*>(g1_row + 2 * H + u0 + 4 * q4);
-                    }
                 }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (p == 1) {   // all TMEM reads of this warp for this tile are complete: re-zero gh_n, hand the buffer back
@@ -265,14 +273,14 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
                     sz += bz[u];
                     gh += bh[u];
                     gi += bi[u];
-                    if (table) { sr += tr[u]; sz += tz[u]; gi = tn_[u]; }
+                    if (table) { sr += tr[8 * p + u]; sz += tz[8 * p + u]; gi = tq[8 * p + u]; }
                     // σ(x) = 1 / (1 + e^-x) and tanh(y) = 1 − 2 / (1 + e^2y) from the compensated exponential (≤ 2 ulp) and the
                     // hardware reciprocal: absolute error ≤ 2e-7, FP32 rounding level of the gate values they feed — at a tenth of
                     // the instructions of expf / tanhf, which would make this epilogue the kernel's critical path
                     const float r = rcp_approx(1.0f + exp2x_comp(-0.5f * sr));
                     const float z = rcp_approx(1.0f + exp2x_comp(-0.5f * sz));
                     const float n = fmaf(-2.0f, rcp_approx(1.0f + exp2x_comp(fmaf(r, gh, gi))), 1.0f);
-                    out[u] = fmaf(z, hp[u] - n, n);       // (1 − z)·n + z·h_prev
+                    out[u] = fmaf(z, hp[8 * p + u] - n, n);       // (1 − z)·n + z·h_prev
                 }
                 if (live) {
                     float* ho = args.h_out + (int64_t)row * H + u0;
