@@ -456,6 +456,30 @@ int vag_clip_adam_f32(float* param, const float* grad, float* exp_avg, float* ex
                       const float* grad_sumsq, float clip, float lr, float beta1, float beta2, float eps,
                       float weight_decay, int step, vag_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * Data-parallel gradient exchange over NVLink peer memory (one process per GPU on one node).  Replaces the NCCL all-reduce +
+ * the norm pass of the step driver (train.py:36-51 under the commented nn.DataParallel of nmt_multimodal_beam_DE.py:277-282).
+ * Every rank keeps its flat gradient buffer at the START of a peer-visible arena:
+ *   vag_p2p_alloc (cudaMalloc + CUDA IPC handle; the one allocating entry point of this ABI) → exchange the 64-byte handles by any
+ *   host channel → vag_p2p_open on every peer's handle → vag_dp_comm{world, rank, peers[]} (own arena at peers[rank]).
+ * vag_dp_allreduce_f32 (call number `step` = 0, 1, 2 … — the same on all ranks — on every rank, once per optimisation step):
+ *   barrier · reduce-scatter (rank r averages slice r over all ranks, fixed summation order) + Σ avg² block partials ·
+ *   barrier · all-gather of the averaged slices + the norm (fixed order) · barrier.
+ * Afterwards every rank's buffer holds the same bits (the average) and sumsq_out[0] the same Σ‖g‖² — what the replicated
+ * vag_clip_adam_multi_f32 needs to keep the replicas bit-identical.  n_floats: a multiple of 4; the arena must hold
+ * vag_dp_arena_bytes(n_floats).  A rank that never arrives makes the others trap after a bounded wait.
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+    int world, rank;
+    void* peers[16];          /* arena base pointer of every rank as mapped INTO THIS process (vag_p2p_open; own at [rank]) */
+} vag_dp_comm;
+int vag_p2p_alloc(size_t bytes, void** dev_ptr, unsigned char* handle_out_64);
+int vag_p2p_free(void* dev_ptr);
+int vag_p2p_open(const unsigned char* handle_64, void** dev_ptr);
+int vag_p2p_close(void* dev_ptr);
+size_t vag_dp_arena_bytes(int64_t n_floats);
+int vag_dp_allreduce_f32(const vag_dp_comm* c, int64_t n_floats, int step, float* sumsq_out, vag_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,6 +24,7 @@ def _worker(rank, world, port, out_dir):
     sys.path.insert(0, str(ROOT / "tests"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    os.environ["VAG_DP_P2P"] = "1"          # exercise the peer-memory gradient exchange (opt-in; NCCL is the default)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     import vag_nmt_b200 as vag
@@ -74,7 +75,30 @@ def _worker(rank, world, port, out_dir):
     both = [torch.empty_like(flat) for _ in range(world)]
     dist.all_gather(both, flat)
     in_sync = all(torch.equal(both[0], b) for b in both)
-    torch.save(dict(decode_ok=sharded == single, n=len(sharded), worst=worst, in_sync=in_sync), os.path.join(out_dir, f"m{rank}.pt"))
+    # ---- the peer-memory gradient exchange (csrc/p2p.cu) against NCCL on the same numbers
+    from vag_nmt_b200.optim import PeerGradientExchange
+    n = 4 * 25_003                                    # not a multiple of the slice size: ragged last slice
+    ex = PeerGradientExchange(n, torch.device("cuda", rank))
+    g = torch.Generator().manual_seed(100 + rank)
+    vals = torch.randn(n, generator=g).cuda()
+    p2p_ok = True
+    for it in range(3):                               # three calls: the barrier sequence numbers advance
+        ex.flat[:n].copy_(vals * (it + 1))
+        ss = torch.zeros(1, device="cuda")
+        ex.allreduce(ss)
+        want = vals * (it + 1)
+        dist.all_reduce(want, op=dist.ReduceOp.AVG)       # NCCL on the same inputs
+        c1 = bool(torch.allclose(ex.flat[:n], want, rtol=1e-6, atol=1e-6))
+        c2 = bool(abs(float(ss) - float((want.double() ** 2).sum())) < 1e-4 * float((want.double() ** 2).sum()))
+        both_g = [torch.empty(n + 1, device="cuda") for _ in range(world)]
+        dist.all_gather(both_g, torch.cat([ex.flat[:n], ss]))
+        c3 = all(torch.equal(both_g[0], t) for t in both_g)           # bit-identical gradient AND norm on every rank
+        if not (c1 and c2 and c3):
+            print(f"rank {rank} it {it}: avg {c1} (max err {float((ex.flat[:n] - want).abs().max())}) norm {c2} ({float(ss)} vs {float((want.double() ** 2).sum())}) identical {c3}", flush=True)
+        p2p_ok &= c1 and c2 and c3
+    p2p_used = getattr(opt, "_peer", None) is not None
+    torch.save(dict(decode_ok=sharded == single, n=len(sharded), worst=worst, in_sync=in_sync, p2p_ok=p2p_ok, p2p_used=p2p_used),
+               os.path.join(out_dir, f"m{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -87,3 +111,4 @@ def test_two_gpu_decode_sharding_and_data_parallel_gradients(tmp_path):
         assert res["decode_ok"] and res["n"] == 13
         assert res["worst"] < 1e-4, res["worst"]       # DP gradients == single-process gradients of the global batch
         assert res["in_sync"]                            # replicas bit-identical after three data-parallel steps
+        assert res["p2p_used"] and res["p2p_ok"]         # … through the peer-memory exchange, which matches NCCL's average

@@ -43,6 +43,10 @@ class DecoderWeights(C.Structure):
                 ("ini_w", C.c_void_p), ("ini_b", C.c_void_p), ("prepared", C.c_void_p), ("prepared_bytes", C.c_size_t)]
 
 
+class DpComm(C.Structure):
+    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("peers", C.c_void_p * 16)]
+
+
 class DecoderSeqSaved(C.Structure):
     _fields_ = [("ld_logits", C.c_int64)] + [(n, C.c_void_p) for n in (
         "keys", "e_all", "gi1_all", "gh1_all", "h1_all", "q_all", "alpha_all", "c_all", "x2_all", "gi2_all", "gh2_all", "h2_all",
@@ -126,6 +130,12 @@ SIGNATURES = {
     "vag_sumsq_multi_det_f32": (I, [P, I, I64, P, P, SZ, P]),
     "vag_clip_adam_multi_f32": (I, [P, I, I64, P, F, F, F, F, I, P]),
     "vag_clip_adam_f32": (I, [P, P, P, P, I64, P, F, F, F, F, F, F, I, P]),
+    "vag_p2p_alloc": (I, [SZ, P, P]),
+    "vag_p2p_free": (I, [P]),
+    "vag_p2p_open": (I, [P, P]),
+    "vag_p2p_close": (I, [P]),
+    "vag_dp_arena_bytes": (SZ, [I64]),
+    "vag_dp_allreduce_f32": (I, [P, I64, I, P, P]),
 }
 
 _lib: Optional[C.CDLL] = None
