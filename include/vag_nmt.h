@@ -186,6 +186,27 @@ int vag_vse_pool_fwd_f32(const vag_vse_weights* w, const float* im, const float*
                          float* im_emb, float* txt_emb, float* ctx_vec, float* beta, void* workspace,
                          size_t workspace_bytes, vag_stream_t stream);
 
+/* Training pair of the pooling: the forward that keeps what back-propagation needs, and the whole backward chain in one call
+ * (what loss.backward() does through VSE_Imagine_Enc.forward, layers/VSE_Imagine_Enc.py:110-152, and ImagineAttn, :29-79).
+ *   saved: a_im [B, S] = act(im_embedding(im)) before l2norm, iq [B, C] = emb2ctx(im_emb), pk [B, T, C] = ctx2ctx(ctx),
+ *          a_txt [B, S] = act(text_embedding(ctx_vec)) before l2norm — caller-owned, filled by the forward.
+ *   backward: d_im_emb / d_txt_emb / d_ctx_vec may be NULL (no gradient arrives there);  g: gradients like the weights (mlp_w only
+ *   for the mlp attention), overwritten;  d_ctx [B, T, C] overwritten with the gradient w.r.t. the encoder context. */
+typedef struct {
+    float *a_im, *iq, *pk, *a_txt;
+} vag_vse_saved;
+typedef struct {
+    float *im_w, *im_b, *txt_w, *txt_b, *ctx2ctx_w, *emb2ctx_w, *mlp_w;
+} vag_vse_grads;
+int vag_vse_pool_train_fwd_f32(const vag_vse_weights* w, const float* im, const float* ctx, const float* mask, int B, int T,
+                               float* im_emb, float* txt_emb, float* ctx_vec, float* beta, const vag_vse_saved* saved,
+                               void* workspace, size_t workspace_bytes, vag_stream_t stream);
+size_t vag_vse_pool_bwd_workspace_bytes(int B, int T, int I, int C, int S);
+int vag_vse_pool_bwd_f32(const vag_vse_weights* w, const float* im, const float* ctx, const float* mask, int B, int T,
+                         const vag_vse_saved* saved, const float* im_emb, const float* beta, const float* ctx_vec,
+                         const float* d_im_emb, const float* d_txt_emb, const float* d_ctx_vec, const vag_vse_grads* g,
+                         float* d_ctx, void* workspace, size_t workspace_bytes, vag_stream_t stream);
+
 /* Bidirectional hinge ranking loss, SUM over pairs (losses/PairwiseRankingLoss.py:9-24); with
  * one_direction != 0 only cost_s (losses/ImageRetrievalRankingLoss.py:9-21).
  * im [B, S], s [B, S] → loss_out[1]; grad_im/grad_s ([B, S], may both be NULL) receive dLoss/d·. */

@@ -40,6 +40,12 @@ def _worker(rank, world, port, out_dir):
     fn = lambda s, l, i, K, L: model.beamsearch_decode(s, l, i, beam_size=K, max_length=L)
     sharded = decode_corpus_sharded(fn, sents, im, 4, 10)
     single = decode_corpus(fn, sents, im, 4, 10)
+    # ---- retrieval evaluation: sharded embedding + all-gather + replicated recall == single GPU
+    from vag_nmt_b200.translate import embed_corpus, retrieval_eval_sharded
+    efn = lambda s, l, i: model.embed_sent_im_test(s, l, i)
+    recall_sharded = retrieval_eval_sharded(efn, sents, im, batch_size=4)
+    lim1, ltxt1 = embed_corpus(efn, sents, im, batch_size=4)
+    recall_single = vag.t2i(lim1, ltxt1)
     # ---- training: global batch 8 split 4 + 4 must give the single-process gradients
     batch = synthetic.make_batch(8, cfg["src_size"], cfg["tgt_size"], cfg["im_feats_size"], seed=5, max_len=9, min_len=2, mean=5, std=2.5)
     w = torch.ones(cfg["tgt_size"], device="cuda")
@@ -97,7 +103,8 @@ def _worker(rank, world, port, out_dir):
             print(f"rank {rank} it {it}: avg {c1} (max err {float((ex.flat[:n] - want).abs().max())}) norm {c2} ({float(ss)} vs {float((want.double() ** 2).sum())}) identical {c3}", flush=True)
         p2p_ok &= c1 and c2 and c3
     p2p_used = getattr(opt, "_peer", None) is not None
-    torch.save(dict(decode_ok=sharded == single, n=len(sharded), worst=worst, in_sync=in_sync, p2p_ok=p2p_ok, p2p_used=p2p_used),
+    torch.save(dict(decode_ok=sharded == single, n=len(sharded), worst=worst, in_sync=in_sync, p2p_ok=p2p_ok, p2p_used=p2p_used,
+                    recall_ok=tuple(recall_sharded) == tuple(recall_single)),
                os.path.join(out_dir, f"m{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
@@ -109,6 +116,7 @@ def test_two_gpu_decode_sharding_and_data_parallel_gradients(tmp_path):
     for r in range(2):
         res = torch.load(tmp_path / f"m{r}.pt")
         assert res["decode_ok"] and res["n"] == 13
+        assert res["recall_ok"]                          # sharded retrieval evaluation == single-GPU r@1/5/10, median rank
         assert res["worst"] < 1e-4, res["worst"]       # DP gradients == single-process gradients of the global batch
         assert res["in_sync"]                            # replicas bit-identical after three data-parallel steps
         assert res["p2p_used"] and res["p2p_ok"]         # … through the peer-memory exchange, which matches NCCL's average

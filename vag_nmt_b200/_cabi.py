@@ -43,6 +43,14 @@ class DecoderWeights(C.Structure):
                 ("ini_w", C.c_void_p), ("ini_b", C.c_void_p), ("prepared", C.c_void_p), ("prepared_bytes", C.c_size_t)]
 
 
+class VseSaved(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("a_im", "iq", "pk", "a_txt")]
+
+
+class VseGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("im_w", "im_b", "txt_w", "txt_b", "ctx2ctx_w", "emb2ctx_w", "mlp_w")]
+
+
 class DpComm(C.Structure):
     _fields_ = [("world", C.c_int), ("rank", C.c_int), ("peers", C.c_void_p * 16)]
 
@@ -78,6 +86,9 @@ SIGNATURES = {
     "vag_encoder_fwd_f32": (I, [P, P, P, I, I, P, P, P, SZ, P]),
     "vag_vse_workspace_bytes": (SZ, [I, I, I, I, I]),
     "vag_vse_pool_fwd_f32": (I, [P, P, P, P, I, I, P, P, P, P, P, SZ, P]),
+    "vag_vse_pool_train_fwd_f32": (I, [P, P, P, P, I, I, P, P, P, P, P, P, SZ, P]),
+    "vag_vse_pool_bwd_workspace_bytes": (SZ, [I, I, I, I, I]),
+    "vag_vse_pool_bwd_f32": (I, [P, P, P, P, I, I, P, P, P, P, P, P, P, P, P, P, SZ, P]),
     "vag_rank_loss_workspace_bytes": (SZ, [I, I]),
     "vag_rank_loss_f32": (I, [P, P, I, I, F, I, P, P, P, P, SZ, P]),
     "vag_recall_ranks_workspace_bytes": (SZ, [I, I]),

@@ -205,60 +205,74 @@ class MaskMulFn(torch.autograd.Function):
 
 # ---------------------------------------------------------------------------------------------------- VSE pooling
 class VsePoolFn(torch.autograd.Function):
-    """(im [B,I], ctx [B,T,C], mask [B,T]) → im_emb [B,S], txt_emb [B,S], ctx_vec [B,C]."""
+    """(im [B,I], ctx [B,T,C], mask [B,T]) → im_emb [B,S], txt_emb [B,S], ctx_vec [B,C].
+    Forward (with saved activations) and backward are ONE C call each: vag_vse_pool_train_fwd_f32 / vag_vse_pool_bwd_f32."""
+
+    @staticmethod
+    def _weights(method, activation, im_w, im_b, txt_w, txt_b, ctx2ctx_w, emb2ctx_w, mlp_w):
+        from ._cabi import VseWeights
+        w = VseWeights()
+        w.I, w.C, w.S = im_w.shape[1], ctx2ctx_w.shape[0], im_w.shape[0]
+        w.method = ops.ATTN_DOT if method == "dot" else ops.ATTN_MLP
+        w.activation = 1 if activation else 0
+        w.precision = ops._cabi.precision()
+        w.im_w, w.im_b, w.txt_w, w.txt_b = ops._p(im_w.detach()), ops._p(im_b.detach()), ops._p(txt_w.detach()), ops._p(txt_b.detach())
+        w.ctx2ctx_w, w.emb2ctx_w = ops._p(ctx2ctx_w.detach()), ops._p(emb2ctx_w.detach())
+        w.mlp_w = ops._p(mlp_w.detach().reshape(-1)) if mlp_w is not None else None
+        return w
 
     @staticmethod
     def forward(fctx, im, ctx, mask, method, activation, im_w, im_b, txt_w, txt_b, ctx2ctx_w, emb2ctx_w, mlp_w):
         _save_mode(fctx)
-        B, Tn, C = ctx.shape
-        act = ops.LIN_TANH if activation else 0
-        a_im = _lin(im, im_w, im_b, act)                               # VSE_Imagine_Enc.py:123-127
-        im_emb = ops.l2norm_rows_(a_im.clone())                        # :132
-        iq = _lin(im_emb, emb2ctx_w)                                   # :58
-        pk = _lin(ctx.view(B * Tn, C), ctx2ctx_w).view(B, Tn, C)       # :57
-        mode = ops.ATTN_DOT if method == "dot" else ops.ATTN_MLP
-        v = mlp_w.reshape(-1) if mode == ops.ATTN_MLP else None
-        ctx_vec, beta = ops.attention(iq, pk, ctx, v, mask, 1, mode)   # :135-137
-        a_txt = _lin(ctx_vec, txt_w, txt_b, act)                       # :138-140
-        txt_emb = ops.l2norm_rows_(a_txt.clone())                      # :145
-        fctx.save_for_backward(im, ctx, mask, a_im, im_emb, iq, pk, beta, ctx_vec, a_txt, im_w, txt_w, ctx2ctx_w, emb2ctx_w,
+        import ctypes as C
+        from ._cabi import VseSaved
+        lib = ops._cabi.lib()
+        B, Tn, Cd = ctx.shape
+        S, dev = im_w.shape[0], ctx.device
+        im, ctx, mask = im.contiguous(), ctx.contiguous(), mask.contiguous()
+        w = VsePoolFn._weights(method, activation, im_w, im_b, txt_w, txt_b, ctx2ctx_w, emb2ctx_w, mlp_w)
+        im_emb, txt_emb = _empty(B, S, like=ctx), _empty(B, S, like=ctx)
+        ctx_vec, beta = _empty(B, Cd, like=ctx), _empty(B, Tn, like=ctx)
+        a_im, a_txt, iq, pk = _empty(B, S, like=ctx), _empty(B, S, like=ctx), _empty(B, Cd, like=ctx), _empty(B, Tn, Cd, like=ctx)
+        sv = VseSaved()
+        sv.a_im, sv.iq, sv.pk, sv.a_txt = a_im.data_ptr(), iq.data_ptr(), pk.data_ptr(), a_txt.data_ptr()
+        ws = ops.workspace(lib.vag_vse_workspace_bytes(B, Tn, w.I, w.C, w.S), dev)
+        with on_device(dev):
+            ops.check(lib.vag_vse_pool_train_fwd_f32(C.byref(w), im.data_ptr(), ctx.data_ptr(), mask.data_ptr(), B, Tn, im_emb.data_ptr(),
+                                                     txt_emb.data_ptr(), ctx_vec.data_ptr(), beta.data_ptr(), C.byref(sv), ws.data_ptr(),
+                                                     ws.numel(), ops.stream_ptr()))
+        fctx.save_for_backward(im, ctx, mask, a_im, im_emb, iq, pk, beta, ctx_vec, a_txt, im_w, im_b, txt_w, txt_b, ctx2ctx_w, emb2ctx_w,
                                mlp_w if mlp_w is not None else im_b)
-        fctx.meta = (mode, activation, mlp_w is not None)
-        fctx.bias_refs = (im_b, txt_b)      # only their identity is needed (gradient sink lookup)
+        fctx.meta = (method, activation, mlp_w is not None)
         return im_emb, txt_emb, ctx_vec
 
     @staticmethod
     @_in_forward_mode
     def backward(fctx, d_im_emb, d_txt_emb, d_ctx_vec):
-        im, ctx, mask, a_im, im_emb, iq, pk, beta, ctx_vec, a_txt, im_w, txt_w, ctx2ctx_w, emb2ctx_w, mlp_w = fctx.saved_tensors
-        mode, activation, has_mlp = fctx.meta
-        B, Tn, C = ctx.shape
-        # text branch
-        du_t = T.l2norm_bwd(d_txt_emb, a_txt)
-        if activation:
-            du_t = T.tanh_bwd(du_t, a_txt)
-        d_txt_w = T.gemm(du_t, ctx_vec, trans_a=True, out=_gbuf(txt_w))
-        d_txt_b = T.colsum(du_t, out=_gbuf(fctx.bias_refs[1]))
-        dcv = d_ctx_vec.contiguous().clone()
-        T.gemm(du_t, txt_w, out=dcv, beta=1.0)
-        # pooling attention
-        dctx = _zeros(B, Tn, C, like=ctx)
-        dpk = _zeros(B, Tn, C, like=ctx)
-        dv = _zeros(C, like=ctx) if has_mlp else None
-        d_iq = T.attention_bwd(dcv, beta, iq, pk, ctx, mlp_w.reshape(-1) if has_mlp else None, mask, dpk, dctx, dv, mode)
-        T.gemm(dpk.view(B * Tn, C), ctx2ctx_w, out=dctx.view(B * Tn, C), beta=1.0)
-        d_ctx2ctx = T.gemm(dpk.view(B * Tn, C), ctx.view(B * Tn, C), trans_a=True, out=_gbuf(ctx2ctx_w))
-        d_emb2ctx = T.gemm(d_iq, im_emb, trans_a=True, out=_gbuf(emb2ctx_w))
-        # image branch
-        d_ie = d_im_emb.contiguous().clone()
-        T.gemm(d_iq, emb2ctx_w, out=d_ie, beta=1.0)
-        du_i = T.l2norm_bwd(d_ie, a_im)
-        if activation:
-            du_i = T.tanh_bwd(du_i, a_im)
-        d_im_w = T.gemm(du_i, im, trans_a=True, out=_gbuf(im_w))
-        d_im_b = T.colsum(du_i, out=_gbuf(fctx.bias_refs[0]))
-        d_mlp = dv.view(1, C) if has_mlp else None
-        return None, dctx, None, None, None, d_im_w, d_im_b, d_txt_w, d_txt_b, d_ctx2ctx, d_emb2ctx, d_mlp
+        import ctypes as C
+        from ._cabi import VseGrads, VseSaved
+        lib = ops._cabi.lib()
+        (im, ctx, mask, a_im, im_emb, iq, pk, beta, ctx_vec, a_txt, im_w, im_b, txt_w, txt_b, ctx2ctx_w, emb2ctx_w, mlp_w) = fctx.saved_tensors
+        method, activation, has_mlp = fctx.meta
+        B, Tn, Cd = ctx.shape
+        dev = ctx.device
+        w = VsePoolFn._weights(method, activation, im_w, im_b, txt_w, txt_b, ctx2ctx_w, emb2ctx_w, mlp_w if has_mlp else None)
+        sv = VseSaved()
+        sv.a_im, sv.iq, sv.pk, sv.a_txt = a_im.data_ptr(), iq.data_ptr(), pk.data_ptr(), a_txt.data_ptr()
+        grads = [_gbuf(t) for t in (im_w, im_b, txt_w, txt_b, ctx2ctx_w, emb2ctx_w)]
+        d_mlp = _gbuf(mlp_w) if has_mlp else None
+        g = VseGrads()
+        g.im_w, g.im_b, g.txt_w, g.txt_b, g.ctx2ctx_w, g.emb2ctx_w = [t.data_ptr() for t in grads]
+        g.mlp_w = d_mlp.data_ptr() if has_mlp else None
+        dctx = _empty(B, Tn, Cd, like=ctx)
+        cont = lambda t: None if t is None else t.contiguous()
+        d_im_emb, d_txt_emb, d_ctx_vec = cont(d_im_emb), cont(d_txt_emb), cont(d_ctx_vec)
+        ws = ops.workspace(lib.vag_vse_pool_bwd_workspace_bytes(B, Tn, w.I, w.C, w.S), dev)
+        with on_device(dev):
+            ops.check(lib.vag_vse_pool_bwd_f32(C.byref(w), im.data_ptr(), ctx.data_ptr(), mask.data_ptr(), B, Tn, C.byref(sv), im_emb.data_ptr(),
+                                               beta.data_ptr(), ctx_vec.data_ptr(), ops.ptr(d_im_emb), ops.ptr(d_txt_emb), ops.ptr(d_ctx_vec),
+                                               C.byref(g), dctx.data_ptr(), ws.data_ptr(), ws.numel(), ops.stream_ptr()))
+        return (None, dctx, None, None, None, *grads, d_mlp)
 
 
 # ---------------------------------------------------------------------------------------------------- decoder init

@@ -287,13 +287,14 @@ extern "C" size_t vag_vse_workspace_bytes(int B, int T, int I, int C, int S) {
     return s.total();
 }
 
-extern "C" int vag_vse_pool_fwd_f32(const vag_vse_weights* w, const float* im, const float* ctx, const float* mask, int B, int T,
-                                    float* im_emb, float* txt_emb, float* ctx_vec, float* beta, void* workspace,
-                                    size_t workspace_bytes, vag_stream_t stream) {
-    ModeScope ms(w ? w->precision : VAG_PREC_FP32);
-    VAG_REQUIRE(w && im && ctx && im_emb && txt_emb && ctx_vec, "vag_vse_pool_fwd_f32: null pointer");
-    VAG_REQUIRE(B > 0 && T > 0, "vag_vse_pool_fwd_f32: bad shape");
-    VAG_REQUIRE(w->method == VAG_ATTN_DOT || (w->method == VAG_ATTN_MLP && w->mlp_w), "vag_vse_pool_fwd_f32: bad attention method");
+namespace vag {
+// Shared body of the inference forward and the training forward (which keeps what the backward needs: `sv`).
+static int vse_pool_core(const vag_vse_weights* w, const float* im, const float* ctx, const float* mask, int B, int T, float* im_emb,
+                         float* txt_emb, float* ctx_vec, float* beta, const vag_vse_saved* sv, void* workspace, size_t workspace_bytes,
+                         vag_stream_t stream, const char* who) {
+    VAG_REQUIRE(w && im && ctx && im_emb && txt_emb && ctx_vec, "%s: null pointer", who);
+    VAG_REQUIRE(B > 0 && T > 0, "%s: bad shape", who);
+    VAG_REQUIRE(w->method == VAG_ATTN_DOT || (w->method == VAG_ATTN_MLP && w->mlp_w), "%s: bad attention method", who);
     const int I = w->I, C = w->C, S = w->S;
     cudaStream_t st = (cudaStream_t)stream;
     Arena ar(workspace, workspace_bytes);
@@ -303,19 +304,44 @@ extern "C" int vag_vse_pool_fwd_f32(const vag_vse_weights* w, const float* im, c
     void* wr = ar.take<char>(wb);
     void* areg = ar.take<char>(ab);
     if (ar.overflow) {
-        set_error("vag_vse_pool_fwd_f32: workspace %zu B too small", workspace_bytes);
+        set_error("%s: workspace %zu B too small", who, workspace_bytes);
         return VAG_ERR_WORKSPACE;
     }
+    if (sv) {   // training: the projected keys / query are outputs, not scratch
+        VAG_REQUIRE(sv->a_im && sv->iq && sv->pk && sv->a_txt, "%s: saved-activation pointers missing", who);
+        pk = sv->pk;
+        iq = sv->iq;
+    }
+    float* a_im = sv ? sv->a_im : im_emb;
+    float* a_txt = sv ? sv->a_txt : txt_emb;
     GemmCtx gemm(st, wr, wb, areg, ab);
     const int act = w->activation ? VAG_LIN_TANH : 0;
-    VAG_TRY(gemm.linear(im_emb, S, im, I, w->im_w, I, w->im_b, B, I, S, act));            // VSE_Imagine_Enc.py:123-127
+    VAG_TRY(gemm.linear(a_im, S, im, I, w->im_w, I, w->im_b, B, I, S, act));              // VSE_Imagine_Enc.py:123-127
+    if (sv) VAG_CUDA(cudaMemcpyAsync(im_emb, a_im, sizeof(float) * (size_t)B * S, cudaMemcpyDeviceToDevice, st));
     VAG_TRY(vag_l2norm_rows_f32(im_emb, S, B, S, stream));                                        // :132
     VAG_TRY(gemm.linear(iq, C, im_emb, S, w->emb2ctx_w, S, nullptr, B, S, C, 0));         // :58
     VAG_TRY(gemm.linear(pk, C, ctx, C, w->ctx2ctx_w, C, nullptr, B * T, C, C, 0));        // :57
     VAG_TRY(vag_attention_f32(ctx_vec, C, beta, iq, C, pk, ctx, w->mlp_w, mask, B, 1, T, C, w->method, stream));  // :135-137
-    VAG_TRY(gemm.linear(txt_emb, S, ctx_vec, C, w->txt_w, C, w->txt_b, B, C, S, act));    // :138-140
+    VAG_TRY(gemm.linear(a_txt, S, ctx_vec, C, w->txt_w, C, w->txt_b, B, C, S, act));      // :138-140
+    if (sv) VAG_CUDA(cudaMemcpyAsync(txt_emb, a_txt, sizeof(float) * (size_t)B * S, cudaMemcpyDeviceToDevice, st));
     VAG_TRY(vag_l2norm_rows_f32(txt_emb, S, B, S, stream));                                       // :145
     return VAG_OK;
+}
+}  // namespace vag
+
+extern "C" int vag_vse_pool_fwd_f32(const vag_vse_weights* w, const float* im, const float* ctx, const float* mask, int B, int T,
+                                    float* im_emb, float* txt_emb, float* ctx_vec, float* beta, void* workspace,
+                                    size_t workspace_bytes, vag_stream_t stream) {
+    ModeScope ms(w ? w->precision : VAG_PREC_FP32);
+    return vse_pool_core(w, im, ctx, mask, B, T, im_emb, txt_emb, ctx_vec, beta, nullptr, workspace, workspace_bytes, stream, "vag_vse_pool_fwd_f32");
+}
+
+extern "C" int vag_vse_pool_train_fwd_f32(const vag_vse_weights* w, const float* im, const float* ctx, const float* mask, int B, int T,
+                                          float* im_emb, float* txt_emb, float* ctx_vec, float* beta, const vag_vse_saved* saved,
+                                          void* workspace, size_t workspace_bytes, vag_stream_t stream) {
+    ModeScope ms(w ? w->precision : VAG_PREC_FP32);
+    VAG_REQUIRE(saved && beta, "vag_vse_pool_train_fwd_f32: saved activations and beta are required");
+    return vse_pool_core(w, im, ctx, mask, B, T, im_emb, txt_emb, ctx_vec, beta, saved, workspace, workspace_bytes, stream, "vag_vse_pool_train_fwd_f32");
 }
 
 // ------------------------------------------------------------------ decoder

@@ -804,6 +804,73 @@ extern "C" int vag_gemm_tc_f32(float* C, int64_t ldc, const float* A, int64_t sa
     return gemm_f32(C, ldc, A, sam, sak, B, sbk, sbn, M, N, K, alpha, beta, stream);
 }
 
+// ----------------------------------------------------------------------------------------------------------
+// Backward of the visual-attention pooling (VSE_Imagine_Enc.forward / ImagineAttn, layers/VSE_Imagine_Enc.py:29-152 under
+// autograd): one call for the whole chain  l2norm ← tanh ← text_embedding ← Σβ·ctx ← softmax(score) ← ctx2ctx / emb2ctx ←
+// l2norm ← tanh ← im_embedding.
+// ----------------------------------------------------------------------------------------------------------
+extern "C" size_t vag_vse_pool_bwd_workspace_bytes(int B, int T, int I, int C, int S) {
+    const int64_t BT = (int64_t)B * T;
+    return (size_t)B * S * 4 * 3 + (size_t)B * C * 4 * 2 + (size_t)BT * C * 4 + 16 * 256 +
+           gemm_tc_scratch_bytes(std::max<int64_t>(BT, S), std::max<int64_t>(C, S), std::max<int64_t>({(int64_t)C, (int64_t)I, BT})) + 65536;
+}
+
+extern "C" int vag_vse_pool_bwd_f32(const vag_vse_weights* w, const float* im, const float* ctx, const float* mask, int B, int T,
+                                    const vag_vse_saved* sv, const float* im_emb, const float* beta, const float* ctx_vec,
+                                    const float* d_im_emb, const float* d_txt_emb, const float* d_ctx_vec, const vag_vse_grads* g,
+                                    float* d_ctx, void* workspace, size_t workspace_bytes, vag_stream_t stream) {
+    ModeScope ms(w ? w->precision : VAG_PREC_FP32);
+    VAG_REQUIRE(w && im && ctx && sv && im_emb && beta && ctx_vec && g && d_ctx, "vag_vse_pool_bwd_f32: null pointer");
+    VAG_REQUIRE(sv->a_im && sv->iq && sv->pk && sv->a_txt, "vag_vse_pool_bwd_f32: saved-activation pointers missing");
+    VAG_REQUIRE(g->im_w && g->im_b && g->txt_w && g->txt_b && g->ctx2ctx_w && g->emb2ctx_w, "vag_vse_pool_bwd_f32: gradient pointers missing");
+    VAG_REQUIRE(w->method == VAG_ATTN_DOT || (w->mlp_w && g->mlp_w), "vag_vse_pool_bwd_f32: the mlp attention needs its weight and gradient pointer");
+    const int I = w->I, C = w->C, S = w->S, BT = B * T;
+    cudaStream_t st = (cudaStream_t)stream;
+    vag_stream_t vs = stream;
+    Arena ar(workspace, workspace_bytes);
+    float* du_t = ar.take<float>((size_t)B * S);
+    float* du_i = ar.take<float>((size_t)B * S);
+    float* d_ie = ar.take<float>((size_t)B * S);
+    float* dcv = ar.take<float>((size_t)B * C);
+    float* d_iq = ar.take<float>((size_t)B * C);
+    float* dpk = ar.take<float>((size_t)BT * C);
+    const size_t tcs_bytes = gemm_tc_scratch_bytes(std::max<int64_t>(BT, S), std::max<int64_t>(C, S), std::max<int64_t>({(int64_t)C, (int64_t)I, (int64_t)BT}));
+    char* tcs = ar.take<char>(tcs_bytes);
+    if (ar.overflow) {
+        set_error("vag_vse_pool_bwd_f32: workspace %zu B too small", workspace_bytes);
+        return VAG_ERR_WORKSPACE;
+    }
+    TcScratchScope tc_scope(tcs, tcs_bytes);
+    const bool mlp = w->method == VAG_ATTN_MLP;
+    // ---- text branch: txt_emb = l2norm(a_txt), a_txt = act(text_embedding(ctx_vec))
+    if (d_txt_emb) VAG_TRY(vag_l2norm_bwd_f32(du_t, d_txt_emb, sv->a_txt, B, S, vs));
+    else VAG_CUDA(cudaMemsetAsync(du_t, 0, sizeof(float) * (size_t)B * S, st));
+    if (w->activation) VAG_TRY(vag_tanh_bwd_f32(du_t, du_t, sv->a_txt, (int64_t)B * S, vs));
+    VAG_TRY(gemm_g(g->txt_w, C, du_t, 1, S, ctx_vec, C, 1, S, C, B, 0.f, st));                 // du_tᵀ · ctx_vec
+    VAG_TRY(vag_colsum_f32(g->txt_b, du_t, S, B, S, 0, vs));
+    if (d_ctx_vec) VAG_CUDA(cudaMemcpyAsync(dcv, d_ctx_vec, sizeof(float) * (size_t)B * C, cudaMemcpyDeviceToDevice, st));
+    else VAG_CUDA(cudaMemsetAsync(dcv, 0, sizeof(float) * (size_t)B * C, st));
+    VAG_TRY(gemm_g(dcv, C, du_t, S, 1, w->txt_w, C, 1, B, C, S, 1.f, st));                      // dcv += du_t · W_txt
+    // ---- pooling attention
+    VAG_CUDA(cudaMemsetAsync(d_ctx, 0, sizeof(float) * (size_t)BT * C, st));
+    VAG_CUDA(cudaMemsetAsync(dpk, 0, sizeof(float) * (size_t)BT * C, st));
+    if (mlp) VAG_CUDA(cudaMemsetAsync(g->mlp_w, 0, sizeof(float) * (size_t)C, st));
+    VAG_TRY(vag_attention_bwd_f32(d_iq, C, dpk, d_ctx, mlp ? g->mlp_w : nullptr, dcv, C, beta, sv->iq, C, sv->pk, ctx, w->mlp_w, mask, B, T, C,
+                                  w->method, vs));
+    VAG_TRY(gemm_g(d_ctx, C, dpk, C, 1, w->ctx2ctx_w, C, 1, BT, C, C, 1.f, st));                // d_ctx += dpk · W_ctx2ctx
+    VAG_TRY(gemm_g(g->ctx2ctx_w, C, dpk, 1, C, ctx, C, 1, C, C, BT, 0.f, st));                  // dpkᵀ · ctx
+    VAG_TRY(gemm_g(g->emb2ctx_w, S, d_iq, 1, C, im_emb, S, 1, C, S, B, 0.f, st));               // d_iqᵀ · im_emb
+    // ---- image branch: im_emb = l2norm(a_im), a_im = act(im_embedding(im))
+    if (d_im_emb) VAG_CUDA(cudaMemcpyAsync(d_ie, d_im_emb, sizeof(float) * (size_t)B * S, cudaMemcpyDeviceToDevice, st));
+    else VAG_CUDA(cudaMemsetAsync(d_ie, 0, sizeof(float) * (size_t)B * S, st));
+    VAG_TRY(gemm_g(d_ie, S, d_iq, C, 1, w->emb2ctx_w, S, 1, B, S, C, 1.f, st));                 // d_ie += d_iq · W_emb2ctx
+    VAG_TRY(vag_l2norm_bwd_f32(du_i, d_ie, sv->a_im, B, S, vs));
+    if (w->activation) VAG_TRY(vag_tanh_bwd_f32(du_i, du_i, sv->a_im, (int64_t)B * S, vs));
+    VAG_TRY(gemm_g(g->im_w, I, du_i, 1, S, im, I, 1, S, I, B, 0.f, st));                        // du_iᵀ · im
+    VAG_TRY(vag_colsum_f32(g->im_b, du_i, S, B, S, 0, vs));
+    return VAG_OK;
+}
+
 extern "C" size_t vag_decoder_seq_workspace_bytes(int B, int T, int Tt, int E, int H, int C, int64_t V) {
     const int64_t R = (int64_t)B * Tt;
     size_t fwd = GemmCtx::split_bytes(3 * H, E) + 3 * GemmCtx::split_bytes(3 * H, H) + GemmCtx::split_bytes(C, H) +
