@@ -348,6 +348,14 @@ int vag_row_argmax_f32(const float* logits, int64_t ld, int rows, int64_t V, int
  * loss_vse is a device scalar or NULL (text-only model: loss = loss_mt).  out[3] = {loss, loss_mt, loss_vse}. */
 int vag_translation_loss_f32(const float* loss_rows, const int64_t* tgt, int B, int Tt, const float* loss_vse,
                              float loss_w, float* out, vag_stream_t stream);
+/* Its backward in one launch (what autograd derives from V11:164-166): given g[3] = d/d{loss, loss_mt, loss_vse},
+ *   g_rows[b] = (g[0]·w + g[1]) / (B · #non-pad_b)   with w = loss_w (has_vse) or 1,   g_vse[0] = g[0]·(1-loss_w) + g[2]. */
+int vag_translation_loss_bwd_f32(const float* g, const int64_t* tgt, int B, int Tt, float loss_w, int has_vse,
+                                 float* g_rows, float* g_vse, vag_stream_t stream);
+
+/* Source padding mask and sentence lengths, one launch (models/Encoder.py:47 `src_mask = (input_var != 0)`; the lengths are
+ * what prepare_batch hands to pack_padded_sequence, Encoder.py:55).  Either output may be NULL. */
+int vag_src_mask_lengths(const int64_t* src, int B, int T, float* mask, int32_t* lengths, vag_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Backward pieces of the training step (train.py:36-51: forward, loss.backward(), clip_grad_norm_, Adam.step()).

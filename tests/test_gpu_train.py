@@ -380,3 +380,36 @@ def test_flat_gradient_buffer_shared_by_all_graphs_and_lru_eviction():
     for a, b in zip(results["eager"][0], results["graph"][0]):
         assert abs(a - b) < 1e-5 * abs(a)
     assert float((results["eager"][1] - results["graph"][1]).abs().max()) < 1e-5
+
+
+def test_loss_mix_backward_and_mask_lengths_kernels():
+    """vag_translation_loss_bwd_f32 against autograd of the same formula, vag_src_mask_lengths against (src != 0) — exact."""
+    from vag_nmt_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    B, Tt, Ts = 37, 19, 23
+    tgt = torch.randint(1, 50, (B, Tt), generator=g)
+    src = torch.randint(1, 50, (B, Ts), generator=g)
+    for b in range(B):
+        tgt[b, 1 + b % (Tt - 1):] = 0
+        src[b, 1 + (b * 7) % Ts:] = 0
+    rows = torch.rand(B, generator=g).double().requires_grad_(True)
+    vse = torch.rand(1, generator=g).double().requires_grad_(True)
+    gvec = torch.tensor([0.7, -0.3, 0.2], dtype=torch.float64)
+    for has_vse in (True, False):
+        w = 0.99
+        cnt = (tgt != 0).sum(1).double()
+        mt = (rows / cnt).mean()
+        out = torch.stack([w * mt + (1 - w) * vse[0], mt, vse[0]]) if has_vse else torch.stack([mt, mt, 0 * mt])
+        rows.grad = vse.grad = None
+        out.backward(gvec)
+        g_rows, g_vse = ops.translation_loss_bwd(gvec.float().cuda(), tgt.cuda(), w, has_vse)
+        assert torch.allclose(g_rows.cpu().double(), rows.grad, rtol=1e-6, atol=1e-9)
+        if has_vse:
+            assert torch.allclose(g_vse.cpu().double(), vse.grad, rtol=1e-6)
+        else:
+            assert g_vse is None
+    mask, lens = ops.src_mask_lengths(src.cuda())
+    assert torch.equal(mask.cpu(), (src != 0).float())
+    assert torch.equal(lens.cpu(), (src != 0).sum(1, dtype=torch.int32))
+    mask2, none = ops.src_mask_lengths(src.cuda(), want_lengths=False)
+    assert none is None and torch.equal(mask2, mask)

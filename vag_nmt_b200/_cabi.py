@@ -116,6 +116,8 @@ SIGNATURES = {
     "vag_nll_rows_f32": (I, [P, I64, P, P, I, I64, P, P, P]),
     "vag_row_argmax_f32": (I, [P, I64, I, I64, P, P]),
     "vag_translation_loss_f32": (I, [P, P, I, I, P, F, P, P]),
+    "vag_translation_loss_bwd_f32": (I, [P, P, I, I, F, I, P, P, P]),
+    "vag_src_mask_lengths": (I, [P, I, I, P, P, P]),
     "vag_gemm_f32": (I, [P, I64, P, I64, I64, P, I64, I64, I, I, I, F, F, I, P]),
     "vag_gemm_tc_workspace_bytes": (SZ, [I, I, I]),
     "vag_gemm_tc_f32": (I, [P, I64, P, I64, I64, P, I64, I64, I, I, I, F, F, I, P, SZ, P]),

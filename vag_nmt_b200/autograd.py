@@ -444,11 +444,6 @@ class LossMixFn(torch.autograd.Function):
     def backward(fctx, g):
         (tgt,) = fctx.saved_tensors
         loss_w, has_vse = fctx.meta
-        B = tgt.shape[0]
         # d loss_rows[b] = (g_loss·w + g_mt) / (B · count_b);   d loss_vse = g_loss·(1-w) + g_vse
-        counts = (tgt != 0).sum(-1).to(torch.float32)
-        g = g.to(torch.float32)
-        w_eff = loss_w if has_vse else 1.0
-        g_rows = (g[0] * w_eff + g[1]) / (B * counts)
-        g_vse = (g[0] * (1.0 - loss_w) + g[2]).reshape(1) if has_vse else None
+        g_rows, g_vse = ops.translation_loss_bwd(g.to(torch.float32).contiguous(), tgt, loss_w, has_vse)
         return g_rows, None, g_vse, None

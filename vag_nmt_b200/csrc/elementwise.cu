@@ -223,6 +223,34 @@ translation_loss_kernel(const float* __restrict__ loss_rows, const int64_t* __re
     }
 }
 
+// Backward of the mix above, one launch:  d loss_rows[b] = (g_loss·w + g_mt) / (B·count_b),  d loss_vse = g_loss·(1-w) + g_vse.
+__global__ void __launch_bounds__(256)
+translation_loss_bwd_kernel(const float* __restrict__ g, const int64_t* __restrict__ tgt, int B, int Tt, float loss_w,
+                            int has_vse, float* __restrict__ g_rows, float* __restrict__ g_vse) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const float g0 = g[0], g1 = g[1], g2 = g[2];
+    if (b == 0 && g_vse) g_vse[0] = g0 * (1.0f - loss_w) + g2;
+    if (b >= B) return;
+    float cnt = 0.f;
+    for (int t = 0; t < Tt; ++t) cnt += (tgt[(int64_t)b * Tt + t] != 0) ? 1.f : 0.f;
+    g_rows[b] = (g0 * (has_vse ? loss_w : 1.0f) + g1) / ((float)B * cnt);
+}
+
+// mask[b,t] = (src[b,t] != 0), lengths[b] = number of non-pad tokens  (Encoder.py:47); one warp per sentence
+__global__ void __launch_bounds__(256)
+src_mask_lengths_kernel(const int64_t* __restrict__ src, int B, int T, float* __restrict__ mask, int32_t* __restrict__ lengths) {
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= B) return;
+    int n = 0;
+    for (int t = lane; t < T; t += 32) {
+        const bool live = src[(int64_t)b * T + t] != 0;
+        if (mask) mask[(int64_t)b * T + t] = live ? 1.f : 0.f;
+        n += live ? 1 : 0;
+    }
+    n = __reduce_add_sync(0xffffffffu, n);
+    if (lane == 0 && lengths) lengths[b] = n;
+}
+
 __global__ void bias_sum3_kernel(float* __restrict__ out, const float* __restrict__ a, const float* __restrict__ b,
                                  const float* __restrict__ c, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -337,6 +365,25 @@ extern "C" int vag_nll_rows_f32(const float* logits, int64_t ld, const int64_t* 
     VAG_REQUIRE(rows >= 0 && V > 0 && ld >= V, "vag_nll_rows_f32: bad shape");
     if (rows == 0) return VAG_OK;
     nll_rows_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(logits, ld, tgt, weight, V, loss_rows, lse_out);
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
+extern "C" int vag_translation_loss_bwd_f32(const float* g, const int64_t* tgt, int B, int Tt, float loss_w, int has_vse,
+                                            float* g_rows, float* g_vse, vag_stream_t stream) {
+    VAG_REQUIRE(g && tgt && g_rows, "vag_translation_loss_bwd_f32: null pointer");
+    VAG_REQUIRE(B > 0 && Tt > 0, "vag_translation_loss_bwd_f32: bad shape");
+    VAG_REQUIRE(!has_vse || g_vse, "vag_translation_loss_bwd_f32: g_vse is required when the ranking term is mixed in");
+    translation_loss_bwd_kernel<<<ceil_div(B, 256), 256, 0, (cudaStream_t)stream>>>(g, tgt, B, Tt, loss_w, has_vse, g_rows,
+                                                                                    has_vse ? g_vse : nullptr);
+    VAG_LAUNCH_CHECK();
+    return VAG_OK;
+}
+
+extern "C" int vag_src_mask_lengths(const int64_t* src, int B, int T, float* mask, int32_t* lengths, vag_stream_t stream) {
+    VAG_REQUIRE(src && (mask || lengths), "vag_src_mask_lengths: null pointer");
+    VAG_REQUIRE(B > 0 && T > 0, "vag_src_mask_lengths: bad shape");
+    src_mask_lengths_kernel<<<ceil_div(B, 8), 256, 0, (cudaStream_t)stream>>>(src, B, T, mask, lengths);
     VAG_LAUNCH_CHECK();
     return VAG_OK;
 }

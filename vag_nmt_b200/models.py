@@ -180,8 +180,12 @@ class _Seq2SeqBase(nn.Module):
         enc = self.encoder
         dev = self._device()
         src = src_var.to(device=dev, dtype=torch.int64).contiguous()
-        if torch.is_tensor(src_lengths) and src_lengths.is_cuda:
-            lengths = src_lengths          # device-resident lengths (graph-captured step): validated by the caller on the host
+        mask = None
+        if src_lengths is None:
+            # graph-captured step: the caller validated the lengths on the host; the device recomputes them from the padding
+            mask, lengths = ops.src_mask_lengths(src)
+        elif torch.is_tensor(src_lengths) and src_lengths.is_cuda:
+            lengths = src_lengths
         else:
             lengths = [int(x) for x in src_lengths]
             if src.shape[1] != max(lengths):
@@ -199,7 +203,8 @@ class _Seq2SeqBase(nn.Module):
         if ctx_mask is not None:
             from .autograd import MaskMulFn
             ctx = MaskMulFn.apply(ctx, ctx_mask)
-        mask = (src != 0).to(torch.float32)                          # Encoder.py:47
+        if mask is None:
+            mask, _ = ops.src_mask_lengths(src, want_lengths=False)   # Encoder.py:47
         return ctx, mask
 
     def _decoder_loss_train(self, h0, ctx, mask, tgt, teacher_force_ratio, weight):
@@ -312,7 +317,9 @@ class NMT_AttentionImagine_Seq2Seq_Beam_V11(_Seq2SeqBase):
         vse_in = loss_vse.reshape(1) if loss_vse is not None else None
         out = LossMixFn.apply(loss_rows, tgt, vse_in, float(self.loss_w))
         if loss_vse is None:
+            self._loss_vec = None
             return self.loss_w * out[1], out[1], 0
+        self._loss_vec = (out, 0)       # GraphedTrainStep seeds backward on the whole vector (no select/stack kernels)
         return out[0], out[1], out[2]
 
     @_with_precision
@@ -403,7 +410,9 @@ class NMT_Seq2Seq_Beam_V2(_Seq2SeqBase):
             h0 = DecoderInitFn.apply(None, ctx, mask, 0.0, self.decoderini.weight, self.decoderini.bias)
             tgt = tgt_var.to(device=dev, dtype=torch.int64).contiguous()
             loss_rows = self._decoder_loss_train(h0, ctx, mask, tgt, teacher_force_ratio, _nll_weight(criterion, dev))
-            return LossMixFn.apply(loss_rows, tgt, None, 1.0)[1]
+            out = LossMixFn.apply(loss_rows, tgt, None, 1.0)
+            self._loss_vec = (out, 1)
+            return out[1]
         w, ctx, mask, keys, h0 = self._prepare(src_var, src_lengths)
         tgt = tgt_var.to(device=dev, dtype=torch.int64).contiguous()
         weight = _nll_weight(criterion, dev)

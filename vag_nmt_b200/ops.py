@@ -505,6 +505,30 @@ def row_argmax(logits: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def translation_loss_bwd(g: torch.Tensor, tgt: torch.Tensor, loss_w: float, has_vse: bool):
+    """g [3] = d/d(loss, loss_mt, loss_vse) → (g_rows [B], g_vse [1] | None), one launch"""
+    _chk_f32(g)
+    lib = _cabi.lib()
+    B, Tt = tgt.shape
+    g_rows = torch.empty(B, dtype=torch.float32, device=g.device)
+    g_vse = torch.empty(1, dtype=torch.float32, device=g.device) if has_vse else None
+    with on_device(g.device):
+        check(lib.vag_translation_loss_bwd_f32(g.data_ptr(), tgt.data_ptr(), B, Tt, float(loss_w), int(has_vse),
+                                               g_rows.data_ptr(), ptr(g_vse), stream_ptr()))
+    return g_rows, g_vse
+
+
+def src_mask_lengths(src: torch.Tensor, want_lengths: bool = True):
+    """src int64 [B,T] → (mask fp32 [B,T] = (src != 0), lengths int32 [B] | None), one launch (Encoder.py:47)"""
+    lib = _cabi.lib()
+    B, T = src.shape
+    mask = torch.empty(B, T, dtype=torch.float32, device=src.device)
+    lengths = torch.empty(B, dtype=torch.int32, device=src.device) if want_lengths else None
+    with on_device(src.device):
+        check(lib.vag_src_mask_lengths(src.data_ptr(), B, T, mask.data_ptr(), ptr(lengths), stream_ptr()))
+    return mask, lengths
+
+
 def translation_loss(loss_rows: torch.Tensor, tgt: torch.Tensor, loss_vse: Optional[torch.Tensor], loss_w: float) -> torch.Tensor:
     """→ fp32 [3] = (loss, loss_mt, loss_vse)"""
     _chk_f32(loss_rows, loss_vse)

@@ -148,6 +148,7 @@ class GraphedTrainStep:
         self.max_graphs = int(max_graphs)
         self._graphs: "OrderedDict[tuple, dict]" = OrderedDict()
         self._pool = None
+        self._seeds = {}
         self.enabled = True if enabled is None else enabled
         # Data parallel with the global-batch ranking loss: its all-gather must stay OUTSIDE the graphs (ranks capture
         # independently, and a captured collective would have to be matched launch for launch) — the step is then two graphs,
@@ -160,17 +161,33 @@ class GraphedTrainStep:
     def _fwd_bwd(self, src, lengths, tgt, im, ratio):
         model = self.model
         self.optimizer.zero_grad()
-        if lengths is None:      # graph flavour: lengths = number of non-pad tokens per row, computed on the device (Encoder.py:47)
-            lengths = self._device_lengths(src)
+        # lengths None = graph flavour: the model recomputes them on the device from the padding (vag_src_mask_lengths)
+        model._loss_vec = None
         if im is not None:
             loss, loss_mt, loss_vse = model(src, lengths, tgt, im, ratio, criterion_mt=self.criterion_mt, criterion_vse=self.criterion_vse)
         else:
             loss = model(src, lengths, tgt, ratio, criterion=self.criterion_mt)
             loss_mt, loss_vse = loss, None
+        vec = getattr(model, "_loss_vec", None)
+        model._loss_vec = None
         with model.precision_scope():
+            if vec is not None:
+                # the three losses come out of one kernel as one [3] tensor: seed the backward on it directly with a constant
+                # one-hot instead of loss.backward() (which would add a select-backward, a fill and a stack to every step)
+                out, which = vec
+                torch.autograd.backward([out], [self._seed(out.device, which)])
+                return out.detach()          # text-only: the kernel already wrote (loss_mt, loss_mt, 0)
             loss.backward()
         vse = loss_vse if torch.is_tensor(loss_vse) else torch.zeros((), device=loss.device)
         return torch.stack([loss.detach().reshape(()), loss_mt.detach().reshape(()), vse.detach().reshape(())])
+
+    def _seed(self, dev, which):
+        key = (str(dev), which)
+        if key not in self._seeds:      # created once per device, outside any capture (the first call is the warm-up)
+            e = torch.zeros(3, dtype=torch.float32, device=dev)
+            e[which] = 1.0
+            self._seeds[key] = e
+        return self._seeds[key]
 
     @staticmethod
     def _device_lengths(src):
@@ -242,14 +259,15 @@ class GraphedTrainStep:
         ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         with torch.cuda.graph(ga, pool=self._pool):
             self.optimizer.zero_grad()
-            loss, loss_mt, _ = model(st["src"], self._device_lengths(st["src"]), st["tgt"], st["im"], ratio,
+            loss, loss_mt, _ = model(st["src"], None, st["tgt"], st["im"], ratio,
                                      criterion_mt=self.criterion_mt, criterion_vse=sur)
             st["mt"] = loss_mt.detach().reshape(())
             st["im_emb"], st["txt_emb"] = sur.im, sur.s
+            vec, model._loss_vec = model._loss_vec, None
         with torch.cuda.graph(gb, pool=self._pool):
             with model.precision_scope():
-                loss.backward()
-        del loss
+                torch.autograd.backward([vec[0]], [self._seed(dev, vec[1])])
+        del loss, vec
         st["graph"], st["graph_b"] = ga, gb
         st["grads"] = [(p, p.grad) for p in self.optimizer._all_params() if p.grad is not None]
         st["keepalive"] = list(ops._workspaces.values())
