@@ -120,3 +120,57 @@ def test_two_gpu_decode_sharding_and_data_parallel_gradients(tmp_path):
         assert res["worst"] < 1e-4, res["worst"]       # DP gradients == single-process gradients of the global batch
         assert res["in_sync"]                            # replicas bit-identical after three data-parallel steps
         assert res["p2p_used"] and res["p2p_ok"]         # … through the peer-memory exchange, which matches NCCL's average
+
+
+def _overlap_worker(rank, world, port, out_dir):
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ.pop("VAG_DP_P2P", None)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from conftest import build_mm
+    from vag_nmt_b200 import synthetic
+    from vag_nmt_b200.optim import ClipAdam
+    from vag_nmt_b200.train import DistributedPairwiseRankingLoss, GraphedTrainStep
+    cfg = dict(synthetic.TINY)
+    w = torch.ones(cfg["tgt_size"], device="cuda")
+    w[0] = 0
+    crit = torch.nn.NLLLoss(weight=w, reduction="none")
+    finals, losses, used = [], [], []
+    for overlap in (True, False):
+        model = build_mm(cfg, 7).cuda()
+        opt = ClipAdam(model, lr=1e-2)
+        stepper = GraphedTrainStep(model, opt, crit, DistributedPairwiseRankingLoss(margin=0.1))
+        stepper._overlap = overlap
+        ls = []
+        for it in range(4):      # two shapes, each replayed once after its capture
+            bt = synthetic.make_batch(4, cfg["src_size"], cfg["tgt_size"], cfg["im_feats_size"], seed=70 + 2 * (it % 2) + rank,
+                                      max_len=9, min_len=2, mean=5, std=2.5)
+            out = stepper.step(bt.src, bt.src_lengths, bt.tgt, bt.im, 1.0)
+            ls.append([float(x) for x in out])
+        used.append(any(st.get("graph_b2") is not None for st in stepper._graphs.values()))
+        finals.append(torch.cat([p.detach().reshape(-1) for p in model.parameters()]))
+        losses.append(ls)
+    both = [torch.empty_like(finals[0]) for _ in range(world)]
+    dist.all_gather(both, finals[0])
+    torch.save(dict(used=used, in_sync=all(torch.equal(both[0], b) for b in both),
+                    diff=float((finals[0] - finals[1]).abs().max()), scale=float(finals[1].abs().max()),
+                    losses=losses), os.path.join(out_dir, f"o{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_graphed_step_overlaps_the_decoder_bucket_exchange(tmp_path):
+    """The data-parallel graphed step cuts the backward behind the decoder and all-reduces the decoder's gradients while the
+    encoder back-propagates: same parameters as the un-overlapped step (one all-reduce after the whole backward)."""
+    mp.spawn(_overlap_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        res = torch.load(tmp_path / f"o{r}.pt")
+        assert res["used"] == [True, False]
+        assert res["in_sync"]
+        assert res["diff"] <= 1e-6 * res["scale"], res
+        for a, b in zip(*res["losses"]):
+            assert a == pytest.approx(b, rel=1e-6, abs=1e-7)

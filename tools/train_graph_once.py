@@ -24,3 +24,14 @@ for _ in range(4):
     loss = stepper.step(bt.src, bt.src_lengths, bt.tgt, bt.im, 1.0)[0]
 torch.cuda.synchronize()
 print("Ts", bt.src.shape[1], "Tt", bt.tgt.shape[1], "loss", float(loss))
+if "time" in sys.argv:      # replay timing (CUDA events, 3 x 40 steps, best): python tools/train_graph_once.py bf16 time
+    best = 1e9
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(40):
+            stepper.step(bt.src, bt.src_lengths, bt.tgt, bt.im, 1.0)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / 40)
+    print(f"ms_per_step {best:.4f}  PDL_MASK={os.environ.get('VAG_PDL_MASK', 'default')}")

@@ -96,10 +96,15 @@ int tc_gemm(float* y, int64_t ldy, const void* xh, const void* xl, int64_t ldxs,
 }
 
 namespace vag {
-bool pdl_enabled() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("VAG_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
-    return v == 1;
+bool pdl_enabled(int family) {
+    static int mask = -1;
+    if (mask < 0) {
+        const char* e = getenv("VAG_PDL_MASK");
+        mask = e ? atoi(e) : (PDL_TC | PDL_SMALL);
+        const char* off = getenv("VAG_PDL");
+        if (off && off[0] == '0') mask = 0;
+    }
+    return (mask & family) != 0;
 }
 }
 extern "C" int vag_tc_elem_bytes(int precision) {

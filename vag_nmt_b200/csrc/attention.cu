@@ -264,6 +264,7 @@ attention_tuned_kernel(float* __restrict__ c_out, int64_t ld_c, float* __restric
                        const float* __restrict__ v, const float* __restrict__ mask, int rows, int rows_per_sent, int T, int C,
                        SplitDst sd, const int* __restrict__ done, const float* __restrict__ ekeys, const int* __restrict__ kflag) {
     pdl_trigger();   // the contraction that follows may start its prologue while this kernel drains
+    pdl_wait();      // launched programmatically itself: the query projection before it must have landed
     if (done && *reinterpret_cast<const volatile int*>(done)) return;   // beam search over (block-uniform)
     extern __shared__ __align__(16) float smem[];
     const int b = blockIdx.x;
@@ -520,8 +521,8 @@ static int launch_attention_tuned(float* c_out, int64_t ld_c, float* alpha, cons
         configured = smem;
     }
     dim3 grid(rows / rows_per_sent, ceil_div(rows_per_sent, RCAP));
-    attention_tuned_kernel<MODE, RCAP, FULLC><<<grid, 256, smem, st>>>(c_out, ld_c, alpha, q, ld_q, keys, ctx, v, mask, rows,
-                                                                 rows_per_sent, T, C, sd, done, ekeys, kflag);
+    VAG_CUDA(launch_pdl(PDL_ATTN, attention_tuned_kernel<MODE, RCAP, FULLC>, grid, dim3(256), smem, st, c_out, ld_c, alpha, q, ld_q, keys, ctx, v,
+                        mask, rows, rows_per_sent, T, C, sd, done, ekeys, kflag));
     VAG_LAUNCH_CHECK();
     return VAG_OK;
 }

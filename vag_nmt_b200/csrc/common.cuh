@@ -96,9 +96,14 @@ struct ModeScope {
 // dependent launch as soon as every CTA of the predecessor has started.  Both are no-ops for ordinary launches.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-bool pdl_enabled();   // VAG_PDL=0 switches it off (A/B runs)
+// Kernel families for A/B runs: VAG_PDL_MASK is a bit mask of the families that launch programmatically.  Default TC | SMALL,
+// from the graph-replayed training step (batch 32, bf16): none 2.144 ms, TC 2.127, TC+SMALL 2.052, TC+SMALL+ATTN 2.066,
+// TC+SMALL+ROWS32 2.151 (early or late trigger alike: the recurrent 32-row kernels lose ~1 us per launch when launched
+// programmatically, so they stay ordinary launches).
+enum { PDL_TC = 1, PDL_ROWS32 = 2, PDL_ATTN = 4, PDL_SMALL = 8 };
+bool pdl_enabled(int family);
 template <typename... KArgs, typename... Args>
-static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+static inline cudaError_t launch_pdl(int family, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
@@ -106,7 +111,7 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled(family) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);

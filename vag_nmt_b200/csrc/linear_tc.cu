@@ -77,6 +77,8 @@ split_f16_kernel(const float* __restrict__ x, int64_t ldx, int rows, int K, __ha
 // BF16 mode (north_star "bf16 mode": bf16 operands, FP32 accumulation): one plane, no error compensation.
 __global__ void __launch_bounds__(256)
 round_bf16_kernel(const float* __restrict__ x, int64_t ldx, int rows, int K, __nv_bfloat16* __restrict__ hi, int64_t ldo) {
+    pdl_trigger();
+    pdl_wait();
     const int kq = K >> 2;
     const int64_t total = (int64_t)rows * kq;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -1436,7 +1438,7 @@ int tc_split(const float* x, int64_t ldx, int rows, int K, void* hi, void* lo, i
     if (tot == 0) return VAG_OK;
     const int g = (int)std::min<int64_t>(ceil_div64(tot, 256), (int64_t)num_sms() * 8);
     if (gemm_mode() == 2)
-        round_bf16_kernel<<<g, 256, 0, st>>>(x, ldx, rows, K, (__nv_bfloat16*)hi + col_off, ld_out);
+        VAG_CUDA(launch_pdl(PDL_SMALL, round_bf16_kernel, dim3(g), dim3(256), 0, st, x, ldx, rows, K, (__nv_bfloat16*)hi + col_off, ld_out));
     else if (use_f16_split())
         split_f16_kernel<<<g, 256, 0, st>>>(x, ldx, rows, K, (__half*)hi + col_off, (__half*)lo + col_off, ld_out);
     else
@@ -1462,6 +1464,8 @@ struct SplitJobs {
 };
 template <int MODE>   // 0: TF32 planes (float), 1: FP16 hi/lo, 2: BF16 single plane
 __global__ void __launch_bounds__(256) split_jobs_kernel(const __grid_constant__ SplitJobs jobs) {
+    pdl_trigger();
+    pdl_wait();
     const SplitJob& jb = jobs.j[blockIdx.z];
     const int tiles_c = (jb.cols_pad + 31) >> 5, tiles_r = (jb.rows + 31) >> 5;
     if ((int)blockIdx.x >= tiles_c * tiles_r) return;
@@ -1506,9 +1510,9 @@ int tc_split_pair(const float* x, int64_t ldx, bool xt, int M, void* xh, void* x
     jobs.j[1] = SplitJob{w, ldw, N, K, Kp, wt ? 1 : 0, wh, wl, (int64_t)Kp};
     const int tiles = ceil_div(Kp, 32) * ceil_div(M > N ? M : N, 32);
     dim3 grid(tiles, 1, 2);
-    if (gemm_mode() == 2) split_jobs_kernel<2><<<grid, 256, 0, st>>>(jobs);
-    else if (use_f16_split()) split_jobs_kernel<1><<<grid, 256, 0, st>>>(jobs);
-    else split_jobs_kernel<0><<<grid, 256, 0, st>>>(jobs);
+    if (gemm_mode() == 2) VAG_CUDA(launch_pdl(PDL_SMALL, split_jobs_kernel<2>, dim3(grid), dim3(256), 0, st, jobs));
+    else if (use_f16_split()) VAG_CUDA(launch_pdl(PDL_SMALL, split_jobs_kernel<1>, dim3(grid), dim3(256), 0, st, jobs));
+    else VAG_CUDA(launch_pdl(PDL_SMALL, split_jobs_kernel<0>, dim3(grid), dim3(256), 0, st, jobs));
     VAG_LAUNCH_CHECK();
     return VAG_OK;
 }
@@ -1539,10 +1543,10 @@ int tc_gemm_split_out(SplitDst out, const void* xh, const void* xl, int64_t ldxs
     static bool attr_set[3] = {false, false, false};
     if (mode == 1) {
         if (!attr_set[1]) { VAG_CUDA(cudaFuncSetAttribute(linear_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES)); attr_set[1] = true; }
-        VAG_CUDA(launch_pdl(linear_pair_kernel<1>, dim3(grid), dim3(320), Q_SMEM_BYTES, st, mxh, mxl, mwh, mwl, myh, myh, myl, bias, rows, K, N, flags | VAG_LIN_SPLIT_OUT, (float4*)nullptr, g_tc_dbg, g_tc_done));
+        VAG_CUDA(launch_pdl(PDL_TC, linear_pair_kernel<1>, dim3(grid), dim3(320), Q_SMEM_BYTES, st, mxh, mxl, mwh, mwl, myh, myh, myl, bias, rows, K, N, flags | VAG_LIN_SPLIT_OUT, (float4*)nullptr, g_tc_dbg, g_tc_done));
     } else {
         if (!attr_set[2]) { VAG_CUDA(cudaFuncSetAttribute(linear_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES)); attr_set[2] = true; }
-        VAG_CUDA(launch_pdl(linear_pair_kernel<2>, dim3(grid), dim3(320), Q_SMEM_BYTES, st, mxh, mxl, mwh, mwl, myh, myh, myl, bias, rows, K, N, flags | VAG_LIN_SPLIT_OUT, (float4*)nullptr, g_tc_dbg, g_tc_done));
+        VAG_CUDA(launch_pdl(PDL_TC, linear_pair_kernel<2>, dim3(grid), dim3(320), Q_SMEM_BYTES, st, mxh, mxl, mwh, mwl, myh, myh, myl, bias, rows, K, N, flags | VAG_LIN_SPLIT_OUT, (float4*)nullptr, g_tc_dbg, g_tc_done));
     }
     VAG_LAUNCH_CHECK();
     return VAG_OK;
@@ -1569,10 +1573,10 @@ int tc_gemm_top2(float4* summ, const void* xh, const void* xl, int64_t ldxs, con
     static bool attr_set[3] = {false, false, false};
     if (mode == 1) {
         if (!attr_set[1]) { VAG_CUDA(cudaFuncSetAttribute(vocab_top2_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, V_SMEM_BYTES)); attr_set[1] = true; }
-        VAG_CUDA(launch_pdl(vocab_top2_pair_kernel<1>, dim3(grid), dim3(576), V_SMEM_BYTES, st, mxh, mxl, mwh, mwl, bias, rows, K, N, summ, g_tc_dbg, g_tc_done));
+        VAG_CUDA(launch_pdl(PDL_TC, vocab_top2_pair_kernel<1>, dim3(grid), dim3(576), V_SMEM_BYTES, st, mxh, mxl, mwh, mwl, bias, rows, K, N, summ, g_tc_dbg, g_tc_done));
     } else {
         if (!attr_set[2]) { VAG_CUDA(cudaFuncSetAttribute(vocab_top2_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, V_SMEM_BYTES)); attr_set[2] = true; }
-        VAG_CUDA(launch_pdl(vocab_top2_pair_kernel<2>, dim3(grid), dim3(576), V_SMEM_BYTES, st, mxh, mxl, mwh, mwl, bias, rows, K, N, summ, g_tc_dbg, g_tc_done));
+        VAG_CUDA(launch_pdl(PDL_TC, vocab_top2_pair_kernel<2>, dim3(grid), dim3(576), V_SMEM_BYTES, st, mxh, mxl, mwh, mwl, bias, rows, K, N, summ, g_tc_dbg, g_tc_done));
     }
     VAG_LAUNCH_CHECK();
     return VAG_OK;
@@ -1612,10 +1616,10 @@ int tc_gru(const GruCall& c, cudaStream_t st) {
     static bool attr_set[3] = {false, false, false};
     if (mode == 1) {
         if (!attr_set[1]) { VAG_CUDA(cudaFuncSetAttribute(gru_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES)); attr_set[1] = true; }
-        VAG_CUDA(launch_pdl(gru_pair_kernel<1>, dim3(grid), dim3(320), G_SMEM_BYTES, st, mxh, mxl, mhh, mhl, mwih, mwil, mwhh, mwhl, a));
+        VAG_CUDA(launch_pdl(PDL_TC, gru_pair_kernel<1>, dim3(grid), dim3(320), G_SMEM_BYTES, st, mxh, mxl, mhh, mhl, mwih, mwil, mwhh, mwhl, a));
     } else {
         if (!attr_set[2]) { VAG_CUDA(cudaFuncSetAttribute(gru_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES)); attr_set[2] = true; }
-        VAG_CUDA(launch_pdl(gru_pair_kernel<2>, dim3(grid), dim3(320), G_SMEM_BYTES, st, mxh, mxl, mhh, mhl, mwih, mwil, mwhh, mwhl, a));
+        VAG_CUDA(launch_pdl(PDL_TC, gru_pair_kernel<2>, dim3(grid), dim3(320), G_SMEM_BYTES, st, mxh, mxl, mhh, mhl, mwih, mwil, mwhh, mwhl, a));
     }
     VAG_LAUNCH_CHECK();
     return VAG_OK;
@@ -1660,7 +1664,7 @@ int tc_gemm(float* y, int64_t ldy, const void* xh, const void* xl, int64_t ldxs,
             VAG_CUDA(cudaFuncSetAttribute(linear_pair_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES));    \
             attr_set[M] = true;                                                                                                 \
         }                                                                                                                       \
-        VAG_CUDA(launch_pdl(linear_pair_kernel<M>, dim3(grid), dim3(320), Q_SMEM_BYTES, st, mxh, mxl, mwh, mwl, my, my, my, bias, rows, K, N, flags & ~VAG_LIN_SPLIT_OUT, summ, g_tc_dbg, g_tc_done));          \
+        VAG_CUDA(launch_pdl(PDL_TC, linear_pair_kernel<M>, dim3(grid), dim3(320), Q_SMEM_BYTES, st, mxh, mxl, mwh, mwl, my, my, my, bias, rows, K, N, flags & ~VAG_LIN_SPLIT_OUT, summ, g_tc_dbg, g_tc_done));          \
     } while (0)
         if (mode == 0) VAG_PAIR(0);
         else if (mode == 1) VAG_PAIR(1);

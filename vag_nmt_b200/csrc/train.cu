@@ -86,6 +86,8 @@ __global__ void __launch_bounds__(256)
 gru_gates_bwd_kernel(float* __restrict__ dgi, float* __restrict__ dgh, float* __restrict__ dh_prev, const float* __restrict__ dh,
                      int64_t ld_dh, const float* __restrict__ gi, const float* __restrict__ gh, const float* __restrict__ h_prev,
                      int64_t ld_hp, int rows, int H, const float* __restrict__ dh_add = nullptr) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t total = (int64_t)rows * H;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
         const int r_ = (int)(idx / H), j = (int)(idx % H);
@@ -194,6 +196,8 @@ attention_bwd_fast_kernel(float* __restrict__ dq, int64_t ld_dq, float* __restri
                           float* __restrict__ dv, const float* __restrict__ dc, int64_t ld_dc, const float* __restrict__ alpha,
                           const float* __restrict__ q, int64_t ld_q, const float* __restrict__ keys, const float* __restrict__ ctx,
                           const float* __restrict__ v, const float* __restrict__ mask, int T, int C) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) float sm[];
     float* dcs = sm;             // [C]
     float* da = sm + C;          // [T]
@@ -295,6 +299,8 @@ attention_bwd_fast_kernel(float* __restrict__ dq, int64_t ld_dq, float* __restri
 __global__ void __launch_bounds__(256)
 nll_bwd_kernel(float* __restrict__ dlogits, int64_t ldd, const float* __restrict__ logits, int64_t ld, const float* __restrict__ lse,
                const int64_t* __restrict__ tgt, const float* __restrict__ weight, const float* __restrict__ g, int64_t V, int g_mod) {
+    pdl_trigger();
+    pdl_wait();
     const int r = blockIdx.x;
     int64_t t = tgt[r];
     if (t < 0 || t >= V) t = 0;
@@ -307,6 +313,8 @@ nll_bwd_kernel(float* __restrict__ dlogits, int64_t ldd, const float* __restrict
 
 // ------------------------------------------------------------------------------------------ small element-wise / reductions
 __global__ void tanh_bwd_kernel(float* __restrict__ dx, const float* __restrict__ dy, const float* __restrict__ y, int64_t n) {
+    pdl_trigger();
+    pdl_wait();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         dx[i] = dy[i] * (1.f - y[i] * y[i]);
 }
@@ -317,6 +325,8 @@ __global__ void mul_kernel(float* __restrict__ y, const float* __restrict__ m, i
 // y = tanh(u)·m was stored; dx = dy·m·(1 − tanh(u)²) with tanh(u) = y/m where the unit was kept, 0 gradient elsewhere
 __global__ void tanh_dropout_bwd_kernel(float* __restrict__ dx, const float* __restrict__ dy, const float* __restrict__ y,
                                         const float* __restrict__ m, int64_t n) {
+    pdl_trigger();
+    pdl_wait();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const float mi = m[i];
         const float th = mi != 0.f ? y[i] / mi : 0.f;
@@ -329,6 +339,8 @@ __global__ void axpby_kernel(float* __restrict__ y, const float* __restrict__ x,
 }
 // out[c] (+)= Σ_r x[r, c]
 __global__ void __launch_bounds__(256) colsum_kernel(float* __restrict__ out, const float* __restrict__ x, int64_t ldx, int rows, int cols, int accumulate) {
+    pdl_trigger();
+    pdl_wait();
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     const int part = threadIdx.x >> 5;
     __shared__ float sm[8][33];
@@ -346,6 +358,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(float* __restrict__ out, co
 // table_grad[ids[r], :] += g[r, :]
 __global__ void embed_bwd_kernel(float* __restrict__ table_grad, const float* __restrict__ g, int64_t ldg, const int64_t* __restrict__ ids,
                                  int rows, int dim, int64_t table_rows) {
+    pdl_trigger();
+    pdl_wait();
     const int row = blockIdx.x;
     int64_t id = ids[row];
     if (id < 0 || id >= table_rows) return;
@@ -353,6 +367,8 @@ __global__ void embed_bwd_kernel(float* __restrict__ table_grad, const float* __
 }
 // y = x / max(‖x‖, eps) per row;  dx = (dy − y (y·dy)) / max(‖x‖, eps)      (one warp per row)
 __global__ void l2norm_bwd_kernel(float* __restrict__ dx, const float* __restrict__ dy, const float* __restrict__ x, int rows, int dim) {
+    pdl_trigger();
+    pdl_wait();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -544,7 +560,7 @@ extern "C" int vag_gru_gates_bwd_f32(float* dgi, float* dgh, float* dh_prev, con
                                      const float* gh, const float* h_prev, int64_t ld_hp, int rows, int H, vag_stream_t stream) {
     VAG_REQUIRE(dgi && dgh && dh_prev && dh && gi && gh && h_prev, "vag_gru_gates_bwd_f32: null pointer");
     if (rows == 0) return VAG_OK;
-    gru_gates_bwd_kernel<<<grid_for((int64_t)rows * H), 256, 0, (cudaStream_t)stream>>>(dgi, dgh, dh_prev, dh, ld_dh, gi, gh, h_prev, ld_hp, rows, H);
+    VAG_CUDA(launch_pdl(PDL_SMALL, gru_gates_bwd_kernel, dim3(grid_for((int64_t)rows * H)), dim3(256), 0, (cudaStream_t)stream, dgi, dgh, dh_prev, dh, ld_dh, gi, gh, h_prev, ld_hp, rows, H, nullptr));
     VAG_LAUNCH_CHECK();
     return VAG_OK;
 }
@@ -560,9 +576,9 @@ extern "C" int vag_attention_bwd_f32(float* dq, int64_t ld_dq, float* dkeys, flo
     if (aligned && (size_t)(C + T + 8) * sizeof(float) <= 48 * 1024) {
         const size_t smem_f = (size_t)(C + T + 8) * sizeof(float);
         if (mode == VAG_ATTN_MLP)
-            attention_bwd_fast_kernel<VAG_ATTN_MLP><<<dim3(B, ceil_div(C, 256)), 256, smem_f, st_>>>(dq, ld_dq, dkeys, dctx, dv, dc, ld_dc, alpha, q, ld_q, keys, ctx, v, mask, T, C);
+            VAG_CUDA(launch_pdl(PDL_ATTN, attention_bwd_fast_kernel<VAG_ATTN_MLP>, dim3(B, ceil_div(C, 256)), dim3(256), smem_f, st_, dq, ld_dq, dkeys, dctx, dv, dc, ld_dc, alpha, q, ld_q, keys, ctx, v, mask, T, C));
         else
-            attention_bwd_fast_kernel<VAG_ATTN_DOT><<<dim3(B, ceil_div(C, 256)), 256, smem_f, st_>>>(dq, ld_dq, dkeys, dctx, dv, dc, ld_dc, alpha, q, ld_q, keys, ctx, v, mask, T, C);
+            VAG_CUDA(launch_pdl(PDL_ATTN, attention_bwd_fast_kernel<VAG_ATTN_DOT>, dim3(B, ceil_div(C, 256)), dim3(256), smem_f, st_, dq, ld_dq, dkeys, dctx, dv, dc, ld_dc, alpha, q, ld_q, keys, ctx, v, mask, T, C));
         VAG_LAUNCH_CHECK();
         return VAG_OK;
     }
@@ -579,7 +595,7 @@ extern "C" int vag_nll_bwd_f32(float* dlogits, int64_t ldd, const float* logits,
                                const float* weight, const float* grad_rows, int rows, int64_t V, vag_stream_t stream) {
     VAG_REQUIRE(dlogits && logits && lse && tgt && grad_rows, "vag_nll_bwd_f32: null pointer");
     if (rows == 0) return VAG_OK;
-    nll_bwd_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(dlogits, ldd, logits, ld, lse, tgt, weight, grad_rows, V, 0);
+    VAG_CUDA(launch_pdl(PDL_SMALL, nll_bwd_kernel, dim3(rows), dim3(256), 0, (cudaStream_t)stream, dlogits, ldd, logits, ld, lse, tgt, weight, grad_rows, V, 0));
     VAG_LAUNCH_CHECK();
     return VAG_OK;
 }
@@ -587,7 +603,7 @@ extern "C" int vag_nll_bwd_f32(float* dlogits, int64_t ldd, const float* logits,
 extern "C" int vag_tanh_bwd_f32(float* dx, const float* dy, const float* y, int64_t n, vag_stream_t stream) {
     VAG_REQUIRE(dx && dy && y, "vag_tanh_bwd_f32: null pointer");
     if (n == 0) return VAG_OK;
-    tanh_bwd_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(dx, dy, y, n);
+    VAG_CUDA(launch_pdl(PDL_SMALL, tanh_bwd_kernel, dim3(grid_for(n)), dim3(256), 0, (cudaStream_t)stream, dx, dy, y, n));
     VAG_LAUNCH_CHECK();
     return VAG_OK;
 }
@@ -611,7 +627,7 @@ extern "C" int vag_mul_f32(float* y, const float* m, int64_t n, vag_stream_t str
 extern "C" int vag_colsum_f32(float* out, const float* x, int64_t ldx, int rows, int cols, int accumulate, vag_stream_t stream) {
     VAG_REQUIRE(out && x, "vag_colsum_f32: null pointer");
     if (cols == 0) return VAG_OK;
-    colsum_kernel<<<ceil_div(cols, 32), 256, 0, (cudaStream_t)stream>>>(out, x, ldx, rows, cols, accumulate);
+    VAG_CUDA(launch_pdl(PDL_SMALL, colsum_kernel, dim3(ceil_div(cols, 32)), dim3(256), 0, (cudaStream_t)stream, out, x, ldx, rows, cols, accumulate));
     VAG_LAUNCH_CHECK();
     return VAG_OK;
 }
@@ -620,7 +636,7 @@ extern "C" int vag_embed_bwd_f32(float* table_grad, const float* g, int64_t ldg,
                                  int64_t table_rows, vag_stream_t stream) {
     VAG_REQUIRE(table_grad && g && ids, "vag_embed_bwd_f32: null pointer");
     if (rows == 0) return VAG_OK;
-    embed_bwd_kernel<<<rows, 128, 0, (cudaStream_t)stream>>>(table_grad, g, ldg, ids, rows, dim, table_rows);
+    VAG_CUDA(launch_pdl(PDL_SMALL, embed_bwd_kernel, dim3(rows), dim3(128), 0, (cudaStream_t)stream, table_grad, g, ldg, ids, rows, dim, table_rows));
     VAG_LAUNCH_CHECK();
     return VAG_OK;
 }
@@ -628,7 +644,7 @@ extern "C" int vag_embed_bwd_f32(float* table_grad, const float* g, int64_t ldg,
 extern "C" int vag_l2norm_bwd_f32(float* dx, const float* dy, const float* x, int rows, int dim, vag_stream_t stream) {
     VAG_REQUIRE(dx && dy && x, "vag_l2norm_bwd_f32: null pointer");
     if (rows == 0) return VAG_OK;
-    l2norm_bwd_kernel<<<ceil_div(rows, 4), 128, 0, (cudaStream_t)stream>>>(dx, dy, x, rows, dim);
+    VAG_CUDA(launch_pdl(PDL_SMALL, l2norm_bwd_kernel, dim3(ceil_div(rows, 4)), dim3(128), 0, (cudaStream_t)stream, dx, dy, x, rows, dim));
     VAG_LAUNCH_CHECK();
     return VAG_OK;
 }
@@ -734,6 +750,8 @@ struct TcScratchScope {
     ~TcScratchScope() { g_tc_scratch = prev; }
 };
 __global__ void add2d_kernel(float* __restrict__ C, int64_t ldc, const float* __restrict__ T, int M, int N) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t total = (int64_t)M * (N >> 2);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int m = (int)(i / (N >> 2)), n = (int)(i % (N >> 2)) * 4;
@@ -768,7 +786,7 @@ static int gemm_tc_try(float* C, int64_t ldc, const float* A, int64_t sam, int64
     VAG_TRY(tc_split_pair(A, ldx, xt, M, xh, xl, B, ldw, wt, N, wh, wl, K, Kp, st));   // both operands, one launch, K padding zeroed
     VAG_TRY(tc_gemm(tmp ? tmp : C, tmp ? N : ldc, xh, xl, Kp, wh, wl, Kp, nullptr, M, Kp, N, 0, st, nullptr, nullptr));
     if (tmp) {
-        add2d_kernel<<<grid_for((int64_t)M * N / 4), 256, 0, st>>>(C, ldc, tmp, M, N);
+        VAG_CUDA(launch_pdl(PDL_SMALL, add2d_kernel, dim3(grid_for((int64_t)M * N / 4)), dim3(256), 0, st, C, ldc, tmp, M, N));
         VAG_LAUNCH_CHECK();
     }
     return 1;
@@ -1040,7 +1058,7 @@ extern "C" int vag_decoder_seq_bwd_f32(const vag_decoder_weights* w, const float
     if (do_head) {
     // ---- batched over all steps: vocabulary projection and read-out
     // (the pad column of dlogits is never read: the operand split, the column sum and the transposed read all stop at V)
-    nll_bwd_kernel<<<R, 256, 0, st>>>(dlogits, ldd, s->logits_all, ldl, s->lse_all, tgt_t, nll_weight, dloss_rows, V, B);   // all steps
+    VAG_CUDA(launch_pdl(PDL_SMALL, nll_bwd_kernel, dim3(R), dim3(256), 0, st, dlogits, ldd, s->logits_all, ldl, s->lse_all, tgt_t, nll_weight, dloss_rows, V, B));   // all steps
     VAG_LAUNCH_CHECK();
     {   // d_t = dlogits · out_w   (contraction over the vocabulary: rows of dlogits are padded, out_w is split transposed)
         const int r = gemm_tc_try(d_t, E, dlogits, ldd, 1, w->out_w, E, 1, R, E, (int)V, 0.f, g_tc_scratch.base, g_tc_scratch.cap, st, true);
@@ -1048,7 +1066,7 @@ extern "C" int vag_decoder_seq_bwd_f32(const vag_decoder_weights* w, const float
         if (r == 0) VAG_TRY(gemm_g(d_t, E, dlogits, ldd, 1, w->out_w, E, 1, R, E, (int)V, 0.f, st));
     }
     if (out_mask) {
-        tanh_dropout_bwd_kernel<<<grid_for((int64_t)R * E), 256, 0, st>>>(du, d_t, s->t_all, out_mask, (int64_t)R * E);
+        VAG_CUDA(launch_pdl(PDL_SMALL, tanh_dropout_bwd_kernel, dim3(grid_for((int64_t)R * E)), dim3(256), 0, st, du, d_t, s->t_all, out_mask, (int64_t)R * E));
         VAG_LAUNCH_CHECK();
     } else {
         VAG_TRY(vag_tanh_bwd_f32(du, d_t, s->t_all, (int64_t)R * E, vs));
@@ -1072,9 +1090,9 @@ extern "C" int vag_decoder_seq_bwd_f32(const vag_decoder_weights* w, const float
     const bool fused_dec = rows32_gru_bwd_ok(dprobe, B);
     if (fused_dec) {
         const size_t last = (size_t)(Tt - 1) * B;
-        gru_gates_bwd_kernel<<<grid_for((int64_t)B * H), 256, 0, st>>>(dgi2_all + last * 3 * H, dgh2_all + last * 3 * H, dh1, dh2_dir + last * H, H,
+        VAG_CUDA(launch_pdl(PDL_SMALL, gru_gates_bwd_kernel, dim3(grid_for((int64_t)B * H)), dim3(256), 0, st, dgi2_all + last * 3 * H, dgh2_all + last * 3 * H, dh1, dh2_dir + last * H, H,
                                                                         s->gi2_all + last * 3 * H, s->gh2_all + last * 3 * H,
-                                                                        s->h1_all + last * H, H, B, H, dh_next);
+                                                                        s->h1_all + last * H, H, B, H, dh_next));
         VAG_LAUNCH_CHECK();
     }
     for (int t = Tt - 1; fused_dec && t >= 0; --t) {
@@ -1115,8 +1133,8 @@ extern "C" int vag_decoder_seq_bwd_f32(const vag_decoder_weights* w, const float
         float* dgi2 = dgi2_all + (size_t)t * B * 3 * H;
         float* dgh2 = dgh2_all + (size_t)t * B * 3 * H;
         const float* h1 = s->h1_all + (size_t)t * B * H;
-        gru_gates_bwd_kernel<<<grid_for((int64_t)B * H), 256, 0, st>>>(dgi2, dgh2, dh1, dh2, H, s->gi2_all + (size_t)t * B * 3 * H,
-                                                                        s->gh2_all + (size_t)t * B * 3 * H, h1, H, B, H, dh_next);
+        VAG_CUDA(launch_pdl(PDL_SMALL, gru_gates_bwd_kernel, dim3(grid_for((int64_t)B * H)), dim3(256), 0, st, dgi2, dgh2, dh1, dh2, H, s->gi2_all + (size_t)t * B * 3 * H,
+                                                                        s->gh2_all + (size_t)t * B * 3 * H, h1, H, B, H, dh_next));
         VAG_LAUNCH_CHECK();
         float* dx2 = dx2_all + (size_t)t * B * H;
         VAG_TRY(gemm_g(dx2, H, dgi2, 3 * H, 1, w->gru2_w_ih, H, 1, B, H, 3 * H, 0.f, st));             // dx2 = dgi2 · W_ih2
@@ -1225,6 +1243,8 @@ namespace vag {
 __global__ void __launch_bounds__(256)
 enc_gates_fwd_kernel(float* __restrict__ h, float* __restrict__ ctx_out, const float* __restrict__ gi, float* __restrict__ gh,
                      const int32_t* __restrict__ lengths, int B, int T, int H, int s) {
+    pdl_trigger();
+    pdl_wait();
     const int d = blockIdx.y, t = d == 0 ? s : T - 1 - s;
     const int per_row = H >> 2;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < B * per_row; idx += gridDim.x * blockDim.x) {
@@ -1267,6 +1287,8 @@ __global__ void __launch_bounds__(256)
 enc_gates_bwd_kernel(float* __restrict__ dgi_all, float* __restrict__ dgh_all, float* __restrict__ hprev_all, float* __restrict__ carry,
                      const float* __restrict__ dctx, const float* __restrict__ ctx, const float* __restrict__ gi,
                      const float* __restrict__ gh, const int32_t* __restrict__ lengths, int B, int T, int H, int s) {
+    pdl_trigger();
+    pdl_wait();
     const int d = blockIdx.y, t = d == 0 ? T - 1 - s : s, tp = d == 0 ? t - 1 : t + 1;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < B * H; idx += gridDim.x * blockDim.x) {
         const int row = idx / H, j = idx % H;
@@ -1382,7 +1404,7 @@ extern "C" int vag_encoder_train_fwd_f32(const vag_encoder_weights* w, const int
                 VAG_TRY(gemm.linear(gh_t[d], 3 * H, h + (size_t)d * B * H, H, w->w_hh[d], H, w->b_hh[d], B, H, 3 * H, 0));
             }
         }
-        enc_gates_fwd_kernel<<<dim3(gate_blocks, 2), 256, 0, st>>>(h, ctx_out, gi, gh, lengths_dev, B, T, H, s_);
+        VAG_CUDA(launch_pdl(PDL_SMALL, enc_gates_fwd_kernel, dim3(gate_blocks, 2), dim3(256), 0, st, h, ctx_out, gi, gh, lengths_dev, B, T, H, s_));
         VAG_LAUNCH_CHECK();
     }
     return VAG_OK;
@@ -1426,7 +1448,7 @@ extern "C" int vag_encoder_bwd_f32(const vag_encoder_weights* w, const int32_t* 
     const bool fused_bwd = rows32_gru_bwd_ok(eprobe, B);
     for (int s_ = 0; fused_bwd && s_ < T; ++s_) {
         if (s_ == 0) {
-            enc_gates_bwd_kernel<<<dim3(gate_blocks, 2), 256, 0, st>>>(dgi_all, dgh_all, hprev_all, carry, dctx, ctx, gi, gh, lengths_dev, B, T, H, 0);
+            VAG_CUDA(launch_pdl(PDL_SMALL, enc_gates_bwd_kernel, dim3(gate_blocks, 2), dim3(256), 0, st, dgi_all, dgh_all, hprev_all, carry, dctx, ctx, gi, gh, lengths_dev, B, T, H, 0));
             VAG_LAUNCH_CHECK();
             continue;
         }
@@ -1451,7 +1473,7 @@ extern "C" int vag_encoder_bwd_f32(const vag_encoder_weights* w, const int32_t* 
         VAG_TRY(linear_rows32_gru_bwd(pp, 2, B, gemm_mode() == 2, st));
     }
     for (int s_ = 0; !fused_bwd && s_ < T; ++s_) {
-        enc_gates_bwd_kernel<<<dim3(gate_blocks, 2), 256, 0, st>>>(dgi_all, dgh_all, hprev_all, carry, dctx, ctx, gi, gh, lengths_dev, B, T, H, s_);
+        VAG_CUDA(launch_pdl(PDL_SMALL, enc_gates_bwd_kernel, dim3(gate_blocks, 2), dim3(256), 0, st, dgi_all, dgh_all, hprev_all, carry, dctx, ctx, gi, gh, lengths_dev, B, T, H, s_));
         VAG_LAUNCH_CHECK();
         const int t0 = T - 1 - s_, t1 = s_;
         const float* dgh_t[2] = {dgh_all + (size_t)t0 * B * 3 * H, dgh_all + per_dir3 + (size_t)t1 * B * 3 * H};

@@ -313,8 +313,16 @@ class NMT_AttentionImagine_Seq2Seq_Beam_V11(_Seq2SeqBase):
         h0 = DecoderInitFn.apply(ctx_vec, ctx, mask, float(self.init_split), self.decoderini.weight, self.decoderini.bias)
         tgt = tgt_var.to(device=dev, dtype=torch.int64).contiguous()
         weight = _nll_weight(criterion_mt, dev)
-        loss_rows = self._decoder_loss_train(h0, ctx, mask, tgt, teacher_force_ratio, weight)
         vse_in = loss_vse.reshape(1) if loss_vse is not None else None
+        self._boundary = None
+        if getattr(self, "_bwd_split", False) and vse_in is not None:
+            # Data-parallel step (train.GraphedTrainStep): the backward runs in two pieces — decoder first, so that the
+            # all-reduce of the decoder's gradients overlaps with the encoder's back-propagation through time.  The cut is made of
+            # detached leaves; piece 2 starts from (roots, the leaves' gradients).
+            roots = [ctx, h0, vse_in]
+            ctx, h0, vse_in = (t.detach().requires_grad_() for t in roots)
+            self._boundary = (roots, [ctx, h0, vse_in])
+        loss_rows = self._decoder_loss_train(h0, ctx, mask, tgt, teacher_force_ratio, weight)
         out = LossMixFn.apply(loss_rows, tgt, vse_in, float(self.loss_w))
         if loss_vse is None:
             self._loss_vec = None

@@ -182,9 +182,40 @@ class ClipAdam:
     def _all_params(self):
         return [p for g in self.param_groups for p in g["params"]]
 
+    # -- bucketed exchange: the caller reduces slices of the flat buffer as soon as their gradients are final -------------------
+    def flat_span(self, params) -> Optional[Tuple[int, int]]:
+        """→ element range [lo, hi) of the LONGEST run of consecutive flat-buffer slices that all belong to `params` (None without
+        a flat buffer, or with the peer-memory exchange, which reduces the whole arena in one kernel)."""
+        if not self._ensure_flat() or getattr(self, "_peer", None) is not None:
+            return None
+        want = {p.data_ptr() for p in params}
+        best, run = None, None
+        for ptr, (off, n) in sorted(self._offsets.items(), key=lambda kv: kv[1][0]):
+            end = off + (n + 3) // 4 * 4
+            if ptr in want:
+                run = (run[0], end) if run is not None else (off, end)
+                if best is None or run[1] - run[0] > best[1] - best[0]:
+                    best = run
+            else:
+                run = None
+        return best
+
+    def allreduce_range_async(self, lo: int, hi: int):
+        """Average flat[lo:hi] over the data-parallel ranks; → the c10d work handle (the collective runs on the process group's own
+        stream, ordered after what the current stream has enqueued so far: kernels launched afterwards overlap with it)."""
+        import torch.distributed as dist
+        view = self._flat[lo:hi]
+        if dist.get_backend(self.group) == "nccl":
+            return [dist.all_reduce(view, op=dist.ReduceOp.AVG, group=self.group, async_op=True)]
+        w = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        w.wait()
+        view.mul_(1.0 / dist.get_world_size(self.group))
+        return []
+
     @torch.no_grad()
-    def step(self, clip: Optional[float] = None) -> torch.Tensor:
-        """→ device scalar Σ‖g‖² BEFORE clipping (sqrt of it is what clip_grad_norm_ returns)."""
+    def step(self, clip: Optional[float] = None, pre_reduced: bool = False) -> torch.Tensor:
+        """→ device scalar Σ‖g‖² BEFORE clipping (sqrt of it is what clip_grad_norm_ returns).  pre_reduced: the caller has already
+        averaged the whole flat buffer over the ranks (allreduce_range_async, overlapped with the backward)."""
         clip = self.clip if clip is None else clip
         params = [p for p in self._all_params() if p.grad is not None]
         flat = None
@@ -206,7 +237,10 @@ class ClipAdam:
         if self._sumsq is None or self._sumsq.device != dev:
             self._sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
         peer_done = False
-        if flat is not None and getattr(self, "_peer", None) is not None:
+        if pre_reduced:
+            if flat is None or not self.grads_in_place:
+                raise RuntimeError("pre_reduced=True needs every gradient in place in the flat buffer")
+        elif flat is not None and getattr(self, "_peer", None) is not None:
             self._peer.allreduce(self._sumsq)          # averaged gradients in place + Σ‖g‖², bit-identical on every rank
             peer_done = True
         else:
