@@ -1,7 +1,7 @@
 """GPU parity of every C-ABI operator against the CPU oracle (oracle/vag_oracle.py) on seeded inputs.
 
-Floating-point tolerance (stated per test): the kernels compute in FP32 (SIMT FFMA or error-compensated 3xTF32
-with FP32 accumulation) while the oracle is evaluated in FP64 here, so the bound is a few FP32 ulps of the
+Floating-point tolerance (stated per test): the kernels compute in FP32 (SIMT FFMA, or three error-compensated tensor-core products of
+FP16 hi/lo operand planes with FP32 accumulation) while the oracle is evaluated in FP64 here, so the bound is a few FP32 ulps of the
 largest magnitude: 2e-5 relative to max|ref| for single contractions, 1e-4 for chained operators.
 Integer outputs (tokens, parents, ranks) must be bit-exact.
 """

@@ -1,6 +1,7 @@
-"""GPU: the tcgen05 3xTF32 contraction against an FP64 reference.
+"""GPU: the tcgen05 error-compensated contraction (FP16 hi/lo operand planes, three products, FP32 accumulation in TMEM)
+against an FP64 reference.
 
-Bar: max |y - ref| / max|ref| < 3e-6 — two orders of magnitude tighter than a plain TF32 product (~1e-3) could
+Bar: max |y - ref| / max|ref| < 3e-6 — two orders of magnitude tighter than a single FP16 / TF32 product (~1e-3) could
 meet, i.e. the error-compensated split is doing its job — and within 4x of what the FP32 FFMA kernel achieves."""
 import math
 
