@@ -5,6 +5,7 @@
 // vag_nmt_b200/autograd.py sequence them (back-propagation through time over the Tt decoder steps).
 #include "common.cuh"
 #include "linear_rows.cuh"
+#include "enc_seq.cuh"
 #include <math.h>
 #include <algorithm>
 #include <vector>
@@ -1325,7 +1326,8 @@ enc_gates_bwd_kernel(float* __restrict__ dgi_all, float* __restrict__ dgh_all, f
 extern "C" size_t vag_encoder_train_workspace_bytes(int B, int T, int E, int H) {
     return 2 * (GemmCtx::split_bytes(3 * H, E) + GemmCtx::split_bytes(3 * H, H)) + GemmCtx::split_bytes((int64_t)T * B, E) +
            (size_t)T * B * 3 * H * 4 * 4 + (size_t)T * B * H * 4 * 2 + (size_t)B * H * 4 * 8 + (size_t)B * 3 * H * 4 * 4 + 131072 +
-           (size_t)T * B * E * 4 + gemm_tc_scratch_bytes(3 * H, std::max(E, H), (int64_t)T * B) + gemm_tc_scratch_bytes((int64_t)T * B, E, 3 * H);
+           (size_t)T * B * E * 4 + gemm_tc_scratch_bytes(3 * H, std::max(E, H), (int64_t)T * B) + gemm_tc_scratch_bytes((int64_t)T * B, E, 3 * H) +
+           enc_seq_scratch_bytes(H) + 1024;
 }
 
 static int check_lengths_host(const int32_t* lengths_host, int B, int T, const char* who) {
@@ -1370,6 +1372,16 @@ extern "C" int vag_encoder_train_fwd_f32(const vag_encoder_weights* w, const int
     VAG_CUDA(cudaMemsetAsync(h, 0, sizeof(float) * (size_t)4 * B * H, st));
     for (int d = 0; d < 2; ++d)
         VAG_TRY(gemm.linear(gi + (size_t)d * T * B * 3 * H, 3 * H, x, E, w->w_ih[d], E, w->b_ih[d], T * B, E, 3 * H, 0));
+    if (enc_seq_fwd_ok(B, T, H)) {   // persistent flavour: ONE launch for the whole time loop of both directions (enc_seq.cu)
+        const size_t sb = enc_seq_scratch_bytes(H);
+        void* scratch = ar.take<char>(sb);
+        if (ar.overflow) {
+            set_error("vag_encoder_train_fwd_f32: workspace too small");
+            return VAG_ERR_WORKSPACE;
+        }
+        EncSeqFwd a = {{w->w_hh[0], w->w_hh[1]}, {w->b_hh[0], w->b_hh[1]}, gi, gh, ctx_out, lengths_dev, B, T, H, nullptr, nullptr, 0};
+        return enc_seq_fwd(a, scratch, sb, gemm_mode() == 2, st);
+    }
     {   // fused flavour: hidden-side contraction + gate math + masking of both directions in ONE launch per time step
         float* hb[2] = {h, h + (size_t)2 * B * H};
         Rows32Gru probe = {gh, w->b_hh[0], gi, 0, hb[0], hb[1], ctx_out, (int64_t)T * 2 * H, lengths_dev, 0, H, {hb[0], w->w_hh[0], H, H, H}};
@@ -1431,6 +1443,8 @@ extern "C" int vag_encoder_bwd_f32(const vag_encoder_weights* w, const int32_t* 
     float* carry = ar.take<float>((size_t)2 * B * H);
     const size_t tcs_bytes = gemm_tc_scratch_bytes(3 * H, std::max(E, H), (int64_t)T * B) + gemm_tc_scratch_bytes((int64_t)T * B, E, 3 * H);
     char* tcs = ar.take<char>(tcs_bytes);
+    const size_t es_bytes = enc_seq_scratch_bytes(H);
+    void* es_scratch = ar.take<char>(es_bytes);
     TcScratchScope tc_scope(tcs, tcs ? tcs_bytes : 0);
     if (ar.overflow) {
         set_error("vag_encoder_bwd_f32: workspace too small");
@@ -1446,7 +1460,12 @@ extern "C" int vag_encoder_bwd_f32(const vag_encoder_weights* w, const int32_t* 
     eprobe.seg[0] = Rows32Seg{dgh_all, w->w_hh[0], 3 * H, H, 3 * H};
     eprobe.nseg = 1; eprobe.gi = gi; eprobe.gh = gh; eprobe.dgi = dgi_all; eprobe.dgh = dgh_all; eprobe.dh_out = carry; eprobe.H = H;
     const bool fused_bwd = rows32_gru_bwd_ok(eprobe, B);
-    for (int s_ = 0; fused_bwd && s_ < T; ++s_) {
+    const bool persistent = enc_seq_bwd_ok(B, T, H);
+    if (persistent) {   // ONE launch for the whole back-propagation through time of both directions (enc_seq.cu)
+        EncSeqBwd a = {{w->w_hh[0], w->w_hh[1]}, gi, gh, ctx, dctx, dgi_all, dgh_all, hprev_all, lengths_dev, B, T, H, nullptr, nullptr, 0, 0};
+        VAG_TRY(enc_seq_bwd(a, es_scratch, es_bytes, gemm_mode() == 2, st));
+    }
+    for (int s_ = 0; !persistent && fused_bwd && s_ < T; ++s_) {
         if (s_ == 0) {
             VAG_CUDA(launch_pdl(PDL_SMALL, enc_gates_bwd_kernel, dim3(gate_blocks, 2), dim3(256), 0, st, dgi_all, dgh_all, hprev_all, carry, dctx, ctx, gi, gh, lengths_dev, B, T, H, 0));
             VAG_LAUNCH_CHECK();
@@ -1472,7 +1491,7 @@ extern "C" int vag_encoder_bwd_f32(const vag_encoder_weights* w, const int32_t* 
         }
         VAG_TRY(linear_rows32_gru_bwd(pp, 2, B, gemm_mode() == 2, st));
     }
-    for (int s_ = 0; !fused_bwd && s_ < T; ++s_) {
+    for (int s_ = 0; !persistent && !fused_bwd && s_ < T; ++s_) {
         VAG_CUDA(launch_pdl(PDL_SMALL, enc_gates_bwd_kernel, dim3(gate_blocks, 2), dim3(256), 0, st, dgi_all, dgh_all, hprev_all, carry, dctx, ctx, gi, gh, lengths_dev, B, T, H, s_));
         VAG_LAUNCH_CHECK();
         const int t0 = T - 1 - s_, t1 = s_;
