@@ -413,3 +413,25 @@ def test_loss_mix_backward_and_mask_lengths_kernels():
     assert torch.equal(lens.cpu(), (src != 0).sum(1, dtype=torch.int32))
     mask2, none = ops.src_mask_lengths(src.cuda(), want_lengths=False)
     assert none is None and torch.equal(mask2, mask)
+
+
+@pytest.mark.parametrize("hidden,batch_size", [(24, 3), (40, 7), (72, 32)])
+def test_persistent_encoder_loops_odd_widths_and_ragged_batches(hidden, batch_size):
+    """csrc/enc_seq.cu (one launch for the whole bidirectional GRU time loop, forward and BPTT) at widths where the warps' contraction
+    ranges do not tile H evenly (72: the last working warp holds one k-step, 24 / 40: most warps idle), with fewer than 32 rows and
+    ragged lengths — loss and every gradient against the fp64 oracle."""
+    import vag_nmt_b200 as vag
+    from vag_nmt_b200 import synthetic
+    cfg = dict(synthetic.TINY, hidden_size=hidden, shared_embedding_size=16)
+    model = build_mm(cfg, 33).cuda().train()
+    batch = synthetic.make_batch(batch_size, cfg["src_size"], cfg["tgt_size"], cfg["im_feats_size"], seed=9, max_len=11, min_len=1,
+                                 mean=5.0, std=3.0, common_tgt_len=False)
+    ref_loss, ref = _oracle_grads("mm", model, batch, True)
+    w = torch.ones(cfg["tgt_size"])
+    w[0] = 0
+    crit = torch.nn.NLLLoss(weight=w.cuda(), reduce=False)
+    loss, _, _ = model(batch.src, batch.src_lengths, batch.tgt, batch.im, 1.0, criterion_mt=crit,
+                       criterion_vse=vag.PairwiseRankingLoss(margin=0.1))
+    assert abs(float(loss) - ref_loss) < 1e-4 * abs(ref_loss)
+    loss.backward()
+    _check_grads(model, ref)

@@ -27,9 +27,13 @@ namespace vag {
 namespace {
 
 constexpr int ES_UNITS = 8;           // hidden units per CTA
-constexpr int ES_FWD_WARPS = 8;       // forward: K = H dealt to 8 warps
+#ifndef ES_FWD_WARPS_N
+#define ES_FWD_WARPS_N 8
+#endif
+constexpr int ES_FWD_WARPS = ES_FWD_WARPS_N;   // forward: K = H dealt to the warps
 constexpr int ES_BWD_WARPS = 16;      // backward: K = 3H dealt to 16 warps
-constexpr int ES_FWD_MAXLD = 20;      // forward: float4 loads per lane and step (4 rows per warp, <= 160 float4 per row)
+constexpr int ES_FWD_RPW = 32 / ES_FWD_WARPS;  // forward: rows of the state tile each warp copies
+constexpr int ES_FWD_MAXLD = 5 * ES_FWD_RPW;   // forward: float4 loads per lane and step (<= 160 float4 per row)
 constexpr int ES_BWD_MAXLD = 14;      // backward: float4 loads per lane and chunk (2 rows per warp, <= 224 float4 per row)
 constexpr int ES_MAX_CTAS = 128;      // flags per direction
 
@@ -118,7 +122,7 @@ __global__ void __launch_bounds__(ES_FWD_WARPS * 32, 1) enc_seq_fwd_kernel(const
     for (int n = tid; n < 24; n += blockDim.x) *reinterpret_cast<float4*>(ws + n * P + H) = make_float4(0.f, 0.f, 0.f, 0.f);
     // epilogue thread = (row, unit)
     const int erow = tid >> 3, eu = tid & 7;
-    const bool ework = erow < B;
+    const bool ework = tid < 256 && erow < B;
     float bias[3] = {0.f, 0.f, 0.f};
     int len = 0;
     if (ework) {
@@ -157,18 +161,18 @@ __global__ void __launch_bounds__(ES_FWD_WARPS * 32, 1) enc_seq_fwd_kernel(const
         if (s > 0) {                                        // step 0 starts from the zero state: nothing to wait for or to contract
             es_wait(flags, n_cta, s, &gave_up);
             ES_T(0);
-            // the whole [32][P] state of this direction: warp w copies rows 4w … 4w+3, every load issued before the first store
+            // the whole [32][P] state of this direction, ES_FWD_RPW rows per warp, every load issued before the first store
             float4 v[ES_FWD_MAXLD];
 #pragma unroll
             for (int i = 0; i < ES_FWD_MAXLD; ++i) {
-                const int r = i / (ES_FWD_MAXLD / 4), q = (i % (ES_FWD_MAXLD / 4)) * 32 + lane;
-                if (q < qrow) v[i] = __ldcg(reinterpret_cast<const float4*>(x_in + (wid * 4 + r) * P) + q);
+                const int r = i / 5, q = (i % 5) * 32 + lane;
+                if (q < qrow) v[i] = __ldcg(reinterpret_cast<const float4*>(x_in + (wid * ES_FWD_RPW + r) * P) + q);
             }
             ES_T(5);
 #pragma unroll
             for (int i = 0; i < ES_FWD_MAXLD; ++i) {
-                const int r = i / (ES_FWD_MAXLD / 4), q = (i % (ES_FWD_MAXLD / 4)) * 32 + lane;
-                if (q < qrow) reinterpret_cast<float4*>(xs + (wid * 4 + r) * P)[q] = v[i];
+                const int r = i / 5, q = (i % 5) * 32 + lane;
+                if (q < qrow) reinterpret_cast<float4*>(xs + (wid * ES_FWD_RPW + r) * P)[q] = v[i];
             }
             __syncthreads();
             ES_T(6);
@@ -441,7 +445,7 @@ size_t enc_seq_scratch_bytes(int H) {      // flags + the larger (backward) exch
 }
 bool enc_seq_fwd_ok(int B, int T, int H) {
     // every row of the exchange buffer must fit the per-lane load budget
-    return es_common_ok(B, T, H) && (H + 4) / 4 <= 32 * (ES_FWD_MAXLD / 4) && es_fwd_smem(H) <= 200 * 1024;
+    return es_common_ok(B, T, H) && (H + 4) / 4 <= 32 * 5 && es_fwd_smem(H) <= 200 * 1024;
 }
 bool enc_seq_bwd_ok(int B, int T, int H) {
     const int nc = es_bwd_chunks(H), cw = 3 * H / nc;
