@@ -147,3 +147,36 @@ def test_beam_finalize_entry_point_matches_fused_loop():
     for r in range(B):
         n = int(len2[r])
         assert torch.equal(hyp2[r, :n], hyp[r, :n])
+
+
+def test_pipelined_eval_batches_and_in_call_lanes_give_the_sequential_tokens(monkeypatch):
+    """Several eval batches in flight on separate streams (translate.decode_corpus_pipelined), and one call cut into lanes
+    (VAG_DECODE_LANES): private scratch buffers and graphs per lane, tokens of the plain sequential decode; text-only model too."""
+    from vag_nmt_b200 import synthetic
+    from vag_nmt_b200.translate import decode_corpus, decode_corpus_pipelined
+    from conftest import build_tm
+    cfg = dict(synthetic.DE)
+    model = build_mm(cfg, 1234).cuda().eval()
+    sents, im = synthetic.make_corpus(90, cfg["src_size"], cfg["im_feats_size"], seed=23)
+    fn = lambda s, l, i, K, L: model.beamsearch_decode(s, l, i, beam_size=K, max_length=L)
+    seq = decode_corpus(fn, sents, im, 12, 14, batch_size=16)
+    for lanes in (1, 3, 8):
+        assert decode_corpus_pipelined(model, sents, im, 12, 14, 16, lanes=lanes) == seq
+    assert decode_corpus_pipelined(model, sents, im, 12, 14, 16, lanes=3) == seq       # second pass: graphs replayed per lane
+    assert decode_corpus_pipelined(model, sents, im, 1, 14, 16, lanes=2) == decode_corpus(fn, sents, im, 1, 14, batch_size=16)  # greedy
+    # one call cut into 3 lanes == the same three sub-batches decoded one after the other (a DIFFERENT batch composition may break
+    # a near-tie of these random-weight models differently — sentence 11 of this corpus does between B = 90 and B <= 45 — which is
+    # why the comparison keeps the composition fixed)
+    src, lens, im_s, order = synthetic.pad_and_sort(sents, im)
+    want = []
+    for lo in range(0, 90, 30):
+        want += model.beamsearch_decode(src[lo:lo + 30, :lens[lo]], lens[lo:lo + 30], im_s[lo:lo + 30], beam_size=12, max_length=14)
+    monkeypatch.setenv("VAG_DECODE_LANES", "3")
+    assert model._lane_plan(90, 12) == [(0, 30), (30, 60), (60, 90)]
+    assert model.beamsearch_decode(src, lens, im_s, beam_size=12, max_length=14) == want
+    hyp, hyp_len = model.decode_device(src, lens, im_s, 12, 14)
+    assert model._hyp_lists(hyp, hyp_len) == want
+    monkeypatch.delenv("VAG_DECODE_LANES")
+    tm = build_tm(cfg, 77).cuda().eval()
+    fn_t = lambda s, l, i, K, L: tm.beamsearch_decode(s, l, beam_size=K, max_length=L)
+    assert decode_corpus_pipelined(tm, sents, None, 12, 14, 16, lanes=4) == decode_corpus(fn_t, sents, None, 12, 14, batch_size=16)

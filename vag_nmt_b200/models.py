@@ -104,15 +104,19 @@ class _Seq2SeqBase(nn.Module):
                 out.append(cut)
             return out
         hyp, hyp_len = self._beam_decode(w, h0, keys, ctx, mask, beam_size, tgt_l)  # V11:229 → 233-337
+        return self._hyp_lists(hyp, hyp_len)
+
+    @staticmethod
+    def _hyp_lists(hyp, hyp_len) -> List[List[int]]:
         rows = hyp.cpu().numpy()             # one device→host copy; numpy row slices convert ~2x faster than a whole-tensor tolist()
         lens = hyp_len.cpu().tolist()
-        return [rows[b, :lens[b]].tolist() for b in range(B)]
+        return [rows[b, :lens[b]].tolist() for b in range(rows.shape[0])]
 
     # Small batches (the reference decodes in eval batches of 16, nmt_multimodal_beam_DE.py:542-547): 12 launches of a few µs per
     # step are bound by launch latency, so the whole L-step loop of one (B, T, K, L) shape is captured in a CUDA graph once
     # and replayed.  A captured loop cannot poll the host; its early stop is the kernels' own `done` test.
     _GRAPH_ROWS_MAX = 2048
-    _GRAPH_CACHE_MAX = 48
+    _GRAPH_CACHE_MAX = 192
 
     def _beam_decode(self, w, h0, keys, ctx, mask, K, L):
         import os
@@ -122,7 +126,7 @@ class _Seq2SeqBase(nn.Module):
             return ops.beam_decode(w, h0, keys, ctx, mask, K, L)
         from collections import OrderedDict
         cache = self.__dict__.setdefault("_decode_graphs", OrderedDict())
-        key = (B, T, K, L, w.precision, w.prepared, ops._weights_epoch)
+        key = (ops._lane, B, T, K, L, w.precision, w.prepared, ops._weights_epoch)
         st = cache.get(key)
         if st is None:
             for k in [k for k in cache if k[-1] != ops._weights_epoch]:     # graphs of an older weight set hold stale pointers
@@ -151,10 +155,59 @@ class _Seq2SeqBase(nn.Module):
         st["graph"].replay()
         return st["hyp"], st["hyp_len"]      # static buffers: consume (or clone) before the next decode of this shape
 
+    # Decode lanes (opt-in, VAG_DECODE_LANES=n): one call's batch cut into n independent sub-batches (sentences do not interact),
+    # each decoded by its own CUDA graph on its own stream with private scratch buffers (ops.lane).  Measured on one B200
+    # (tools/decode_lanes_bench.py), tokens identical, but SLOWER for every batch a call would be cut from — 125 sentences 14.7 →
+    # 18.5 ms with 2 lanes, 250: 22.0 → 23.1, 500: 29.8 → 36.3 — because the persistent contraction kernels of each lane claim all
+    # SMs and the lanes' steps serialise.  The same machinery pays where the batches are small by definition: the reference's eval
+    # batches of 16 with several batches in flight (translate.decode_corpus_pipelined: 1.46 k → 3.5 k sentences/s).
+    def _lane_plan(self, B: int, K: int):
+        import os
+        env = os.environ.get("VAG_DECODE_LANES", "1")
+        if K <= 1 or self.training or torch.cuda.is_current_stream_capturing() or ops._lane or not env.isdigit() or int(env) < 2:
+            return None
+        n = min(int(env), 8, B)
+        if n < 2 or -(-B // n) * K > self._GRAPH_ROWS_MAX:
+            return None
+        per = -(-B // n)
+        return [(lo, min(B, lo + per)) for lo in range(0, B, per)]
+
+    def _lane_streams(self, n: int, dev):
+        pool = self.__dict__.setdefault("_lane_stream_pool", [])
+        while len(pool) < n:
+            pool.append(torch.cuda.Stream(device=dev))
+        return pool[:n]
+
+    def _decode_lanes(self, plan, src_var, src_lengths, im_var, beam_size, max_length):
+        dev = self._device()
+        cur = torch.cuda.current_stream(dev)
+        src = src_var.to(device=dev, dtype=torch.int64)
+        im = im_var.to(dev) if im_var is not None else None
+        lens = [int(x) for x in src_lengths]
+        ops.decoder_weights(self.decoder, self.decoderini, prepare=True)    # the shared invariants, once, on the caller's stream
+        streams = self._lane_streams(len(plan), dev)
+        outs = []
+        for i, (lo, hi) in enumerate(plan):
+            streams[i].wait_stream(cur)
+            with torch.cuda.stream(streams[i]), ops.lane(f"lane{i}:"):
+                sub = src[lo:hi, :lens[lo]].contiguous()                    # rows are sorted by length: lens[lo] is the slice's width
+                outs.append(self._decode_device_one(sub, lens[lo:hi], im[lo:hi] if im is not None else None, beam_size, max_length))
+        for st in streams:
+            cur.wait_stream(st)
+        if beam_size == 1:
+            return torch.cat([o[0] for o in outs]), None
+        return torch.cat([o[0] for o in outs]), torch.cat([o[1] for o in outs])
+
     @_with_precision
     def decode_device(self, src_var, src_lengths, im_var=None, beam_size=12, max_length=80):
         """Device-resident beam search: same work as ``beamsearch_decode`` but returns CUDA tensors
         (hyp int64 [B, L], hyp_len int32 [B]) without the final device→host copy / list building."""
+        plan = self._lane_plan(len(src_lengths), beam_size)
+        if plan is not None:
+            return self._decode_lanes(plan, src_var, src_lengths, im_var, beam_size, max_length)
+        return self._decode_device_one(src_var, src_lengths, im_var, beam_size, max_length)
+
+    def _decode_device_one(self, src_var, src_lengths, im_var, beam_size, max_length):
         if isinstance(self, NMT_AttentionImagine_Seq2Seq_Beam_V11):
             w, ctx, mask, keys, h0, _, _ = self._prepare(src_var, src_lengths, im_var)
         else:
@@ -336,6 +389,11 @@ class NMT_AttentionImagine_Seq2Seq_Beam_V11(_Seq2SeqBase):
         tgt_l = max_length if tgt_var is None else tgt_var.size()[1]
         self.tgt_l = tgt_l
         self.beam_size = beam_size
+        plan = self._lane_plan(len(src_lengths), beam_size)
+        if plan is not None:
+            hyp, hyp_len = self._decode_lanes(plan, src_var, src_lengths, im_var, beam_size, tgt_l)
+            self.final_sample = self._hyp_lists(hyp, hyp_len)
+            return self.final_sample
         w, ctx, mask, keys, h0, _, _ = self._prepare(src_var, src_lengths, im_var)
         self.final_sample = self._decode_tokens(w, h0, keys, ctx, mask, beam_size, tgt_l)
         return self.final_sample
@@ -433,6 +491,11 @@ class NMT_Seq2Seq_Beam_V2(_Seq2SeqBase):
         tgt_l = max_length if tgt_var is None else tgt_var.size()[1]
         self.tgt_l = tgt_l
         self.beam_size = beam_size
+        plan = self._lane_plan(len(src_lengths), beam_size)
+        if plan is not None:
+            hyp, hyp_len = self._decode_lanes(plan, src_var, src_lengths, None, beam_size, tgt_l)
+            self.final_sample = self._hyp_lists(hyp, hyp_len)
+            return self.final_sample
         w, ctx, mask, keys, h0 = self._prepare(src_var, src_lengths)
         self.final_sample = self._decode_tokens(w, h0, keys, ctx, mask, beam_size, tgt_l)
         return self.final_sample

@@ -24,9 +24,30 @@ def _pflag() -> int:
 _workspaces = {}
 
 
+_lane = ""     # prefix of every workspace slot while a decode lane is active (see lane())
+
+
+class lane:
+    """Context manager: the calls inside use PRIVATE scratch buffers (workspace slots prefixed with `name`), so that several
+    decodes can be in flight on different CUDA streams at once (models._decode_lanes, translate.decode_corpus_pipelined)."""
+
+    def __init__(self, name: str):
+        self.name, self.prev = name, ""
+
+    def __enter__(self):
+        global _lane
+        self.prev, _lane = _lane, self.name
+        return self
+
+    def __exit__(self, *exc):
+        global _lane
+        _lane = self.prev
+        return False
+
+
 def workspace(nbytes: int, device: torch.device, slot: str = "main") -> torch.Tensor:
-    """Grow-only scratch buffer per (device, slot); the C side never allocates."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(), slot)
+    """Grow-only scratch buffer per (device, lane + slot); the C side never allocates."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), _lane + slot)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
@@ -419,7 +440,7 @@ def _host_progress(dev: torch.device) -> Optional[torch.Tensor]:
     captured (a captured call must not poll the host)."""
     if torch.cuda.is_current_stream_capturing():
         return None
-    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), _lane)
     t = _progress_words.get(key)
     if t is None:
         t = _progress_words[key] = torch.zeros(1, dtype=torch.int32).pin_memory()

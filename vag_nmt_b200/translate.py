@@ -45,6 +45,65 @@ def decode_corpus(decode_fn: Callable, sents: Sequence[List[int]], im: Optional[
     return out  # type: ignore[return-value]
 
 
+def decode_corpus_pipelined(model, sents: Sequence[List[int]], im: Optional[torch.Tensor], beam_size: int, max_length: int,
+                            batch_size: int, lanes: int = 4) -> List[List[int]]:
+    """``decode_corpus`` in eval batches (the reference's loop, nmt_multimodal_beam_DE.py:542-547) with up to `lanes` batches in
+    flight: batch i runs on CUDA stream i mod lanes with private scratch buffers (``ops.lane``) and its own captured graphs,
+    and its tokens are fetched only when the lane is needed again.  A batch of 16 sentences occupies a small part of the GPU
+    in every launch and its 80 steps are one dependent chain, so consecutive batches overlap almost perfectly; the tokens
+    are those of the sequential loop (batches are independent)."""
+    from collections import deque
+    from . import ops
+    n = len(sents)
+    out: List[Optional[List[int]]] = [None] * n
+    dev = model._device()
+    text_only = im is None
+    lanes = max(1, int(lanes))
+    streams = model._lane_streams(lanes, dev)
+    cur = torch.cuda.current_stream(dev)
+    with model.precision_scope():
+        ops.decoder_weights(model.decoder, model.decoderini, prepare=not model.training)   # shared invariants, on the caller's stream
+    pending = deque()
+
+    def collect():
+        lo, order, hyp, hyp_len, ev = pending.popleft()
+        ev.synchronize()
+        if hyp_len is None:
+            hyps = [_cut_eos(r) for r in hyp.cpu().tolist()]
+        else:
+            hyps = model._hyp_lists(hyp, hyp_len)
+        for r, c in enumerate(order):
+            out[lo + c] = [int(t) for t in hyps[r]]
+
+    for i, lo in enumerate(range(0, n, max(batch_size, 1))):
+        chunk = sents[lo:lo + batch_size]
+        src, lens, im_sorted, order = pad_and_sort(chunk, None if text_only else im[lo:lo + batch_size])
+        k = i % lanes
+        if len(pending) >= lanes:
+            collect()
+        streams[k].wait_stream(cur)
+        with torch.cuda.stream(streams[k]), ops.lane(f"pipe{k}:"), model.precision_scope():
+            hyp, hyp_len = model._decode_device_one(src, lens, None if text_only else im_sorted, beam_size, max_length)
+            ev = torch.cuda.Event()
+            ev.record(streams[k])
+        pending.append((lo, order, hyp, hyp_len, ev))
+    while pending:
+        collect()
+    for st in streams:
+        cur.wait_stream(st)
+    return out  # type: ignore[return-value]
+
+
+def _cut_eos(row: List[int]) -> List[int]:
+    from .models import EOS_token
+    cut = []
+    for t in row:
+        if t == EOS_token:
+            break
+        cut.append(t)
+    return cut
+
+
 def shard_indices(lengths: Sequence[int], world_size: int, rank: int, balance: bool = True) -> List[int]:
     """Corpus positions `rank` works on.  balance=True (default): sort the corpus by length (descending, stable) and deal it
     round-robin, so every rank gets the same mix of long and short sentences ("sort globally by length
