@@ -435,3 +435,31 @@ def test_persistent_encoder_loops_odd_widths_and_ragged_batches(hidden, batch_si
     assert abs(float(loss) - ref_loss) < 1e-4 * abs(ref_loss)
     loss.backward()
     _check_grads(model, ref)
+
+
+def test_persistent_decoder_forward_loop_opt_in(monkeypatch):
+    """csrc/dec_seq.cu (VAG_DEC_SEQ=1: one launch for the teacher-forced decoder time loop — five exchange phases per step around
+    the attention) writes what the per-step kernels write: loss and every gradient against the fp64 oracle, FP32 and bf16 modes
+    against each other's tolerance."""
+    import vag_nmt_b200 as vag
+    from vag_nmt_b200 import synthetic
+    cfg = dict(synthetic.TINY, hidden_size=128, shared_embedding_size=32, src_embedding_size=16, tgt_embedding_size=16)
+    model = build_mm(cfg, 41).cuda().train()
+    batch = synthetic.make_batch(9, cfg["src_size"], cfg["tgt_size"], cfg["im_feats_size"], seed=11, max_len=12, min_len=2,
+                                 mean=6.0, std=3.0, common_tgt_len=False)
+    ref_loss, ref = _oracle_grads("mm", model, batch, True)
+    w = torch.ones(cfg["tgt_size"])
+    w[0] = 0
+    crit = torch.nn.NLLLoss(weight=w.cuda(), reduce=False)
+    losses = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("VAG_DEC_SEQ", flag)
+        for p in model.parameters():
+            p.grad = None
+        loss, _, _ = model(batch.src, batch.src_lengths, batch.tgt, batch.im, 1.0, criterion_mt=crit,
+                           criterion_vse=vag.PairwiseRankingLoss(margin=0.1))
+        assert abs(float(loss) - ref_loss) < 1e-4 * abs(ref_loss)
+        loss.backward()
+        _check_grads(model, ref)
+        losses[flag] = float(loss)
+    assert abs(losses["0"] - losses["1"]) < 2e-6 * abs(ref_loss)

@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "linear_rows.cuh"
 #include "enc_seq.cuh"
+#include "dec_seq.cuh"
 #include <math.h>
 #include <algorithm>
 #include <vector>
@@ -896,6 +897,7 @@ extern "C" size_t vag_decoder_seq_workspace_bytes(int B, int T, int Tt, int E, i
                  GemmCtx::split_bytes(H, C) + GemmCtx::split_bytes(E, H) + GemmCtx::split_bytes(E, E) + GemmCtx::split_bytes(E, C) +
                  GemmCtx::split_bytes(V, E) + GemmCtx::split_bytes(C, C) + 65536;
     fwd += GemmCtx::split_bytes(R, E) * 2 + GemmCtx::split_bytes(R, H) + GemmCtx::split_bytes(R, C) + GemmCtx::split_bytes((int64_t)B * T, C) + 65536;
+    fwd += dec_seq_scratch_bytes(H, C) + 4096;     // flags + exchange buffers of the persistent time loop
     // backward scratch: dlogits [R, V], d_t / du [R, E] x2, dH2_dir [R, H], dE [R, E], dC_dir [R, C], per-step grads
     size_t bwd = (size_t)R * (V + 4) * 4 + gemm_tc_scratch_bytes(std::max<int64_t>(V, 3 * H), std::max<int64_t>({(int64_t)C, (int64_t)3 * H, (int64_t)E}), std::max<int64_t>({(int64_t)R, (int64_t)B * T, (int64_t)3 * H})) +
                  gemm_tc_scratch_bytes(std::max<int64_t>(R, (int64_t)B * T), C, std::max<int64_t>(V + 8, 3 * H)) + (size_t)R * H * 4 + (size_t)R * E * 4 * 3 + (size_t)R * H * 4 * 2 + (size_t)R * C * 4 * 2 + (size_t)R * 3 * H * 4 * 4 +
@@ -923,6 +925,9 @@ extern "C" int vag_decoder_seq_fwd_f32(const vag_decoder_weights* w, const float
                       GemmCtx::split_bytes(H, C) + GemmCtx::split_bytes(E, H) + GemmCtx::split_bytes(E, E) + GemmCtx::split_bytes(E, C) +
                       GemmCtx::split_bytes(V, E) + GemmCtx::split_bytes(C, C) + 32768;
     void* wr = ar.take<char>(wb);
+    const bool persistent = teacher && dec_seq_fwd_ok(B, T, Tt, H, C);     // ONE launch for the whole time loop (dec_seq.cu)
+    const size_t ds_bytes = persistent ? dec_seq_scratch_bytes(H, C) : 0;
+    void* ds_scratch = persistent ? ar.take<char>(ds_bytes) : nullptr;
     const size_t ab = ar.overflow ? 0 : (workspace_bytes > align_up(ar.off, 256) + 1024 ? workspace_bytes - align_up(ar.off, 256) - 512 : 0);
     void* areg = ab ? ar.take<char>(ab) : nullptr;
     GemmCtx gemm(st, ar.overflow ? nullptr : wr, wb, ar.overflow ? nullptr : areg, ab);
@@ -934,8 +939,19 @@ extern "C" int vag_decoder_seq_fwd_f32(const vag_decoder_weights* w, const float
         VAG_TRY(vag_embed_rows_f32(s->e_all, E, w->emb, E, tok_in, R, V, vs));
         VAG_TRY(gemm.linear(s->gi1_all, 3 * H, s->e_all, E, w->gru1_w_ih, E, w->gru1_b_ih, R, E, 3 * H, 0));
     }
+    if (persistent) {
+        if (ar.overflow) {
+            set_error("vag_decoder_seq_fwd_f32: workspace too small");
+            return VAG_ERR_WORKSPACE;
+        }
+        DecSeqFwd a = {w->gru1_w_hh, w->gru1_b_hh, w->attn_h_w, w->attn_v, w->c2h_w, w->gru2_w_ih, w->gru2_w_hh, w->gru2_b_ih, w->gru2_b_hh,
+                       h0, s->keys, enc, mask, s->gi1_all,
+                       s->gh1_all, s->h1_all, s->q_all, s->alpha_all, s->c_all, s->x2_all, s->gi2_all, s->gh2_all, s->h2_all,
+                       B, T, Tt, H, C, nullptr, nullptr, 0};
+        VAG_TRY(dec_seq_fwd(a, ds_scratch, ds_bytes, gemm_mode() == 2, st));
+    }
     const float* h = h0;
-    for (int t = 0; t < Tt; ++t) {
+    for (int t = 0; !persistent && t < Tt; ++t) {
         gemm.new_step();
         float* e_s = s->e_all + (size_t)t * B * E;
         float* gi1 = s->gi1_all + (size_t)t * B * 3 * H;
