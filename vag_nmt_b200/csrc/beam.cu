@@ -533,7 +533,7 @@ struct SelCand {
 // NT = threads per sentence: 128 when there are enough sentences to fill the GPU (7 CTAs per SM), 512 for small batches (the
 // reference's eval batch of 16; a test set sharded over 8 GPUs), where the kernel's duration is ONE CTA's latency and that latency
 // is the summary scan (294 x K float4 loads per sentence, four in flight per thread): more workers per row shorten it fourfold.
-template <int KMAX, int NT>
+template <int KMAX, int NT, int UNR>
 __global__ void __launch_bounds__(NT)
 beam_select_top2_kernel(const float4* __restrict__ summ /*[n_slices][n_rows]*/, int n_slices, int slice_w, int n_rows,
                         const uint16_t* __restrict__ t_hi, const uint16_t* __restrict__ t_lo, int64_t ld_t,
@@ -542,7 +542,9 @@ beam_select_top2_kernel(const float4* __restrict__ summ /*[n_slices][n_rows]*/, 
                         float* __restrict__ nll, int64_t* __restrict__ tokens_out, int32_t* __restrict__ parents_out, int K,
                         int V, int step, int avoid_double, const int* __restrict__ done, int* __restrict__ fin_counter,
                         int force_recompute, long long* __restrict__ dbg) {
-    if (done && *done) return;
+    pdl_trigger();   // the reorder kernel that follows may become resident while this one drains
+    pdl_wait();      // launched programmatically itself (PDL_BEAM): the vocabulary summaries must have landed
+    if (done && *reinterpret_cast<const volatile int*>(done)) return;
     extern __shared__ float dyn[];
     const int b = blockIdx.x;
     constexpr int NW = NT / 32;
@@ -561,12 +563,12 @@ beam_select_top2_kernel(const float4* __restrict__ summ /*[n_slices][n_rows]*/, 
     __shared__ float nll_s[KMAX], lse_s[KMAX];
     __shared__ int cur_s[KMAX];
     __shared__ float part_m[NT], part_s[NT];
-    __shared__ float red_a[NW];
-    __shared__ int red_i[NW], red_t[NW];
-    __shared__ int win_sl;
+    __shared__ float red_a[2][NW], rc_a[NW];
+    __shared__ int red_k[2][NW], rc_i[NW];
     __shared__ int win_par[KMAX], win_tok[KMAX];
     __shared__ float win_v[KMAX];
-    __shared__ int req_flag, req_idx;                    // pending block-wide recomputation of one slice
+    __shared__ int req_flag[2], req_idx, req_tid;        // pending block-wide recomputation of one slice (flag per iteration parity)
+    __shared__ int n_eos_s;
     constexpr float kL2e = 1.4426950408889634f;
     const int64_t row0 = (int64_t)b * Kin;
 
@@ -574,7 +576,7 @@ beam_select_top2_kernel(const float4* __restrict__ summ /*[n_slices][n_rows]*/, 
         nll_s[tid] = step == 0 ? 0.f : nll[(int64_t)b * K + tid];
         cur_s[tid] = step == 0 ? -1 : (int)prev_tokens[(int64_t)b * K + tid];
     }
-    if (tid == 0) req_flag = 0;
+    if (tid == 0) { req_flag[0] = req_flag[1] = 0; n_eos_s = 0; }
     __syncthreads();
 
     // ---- the thread's sorted list of its three best entries (sc = RAW logit until the log-sum-exps are known)
@@ -604,32 +606,61 @@ beam_select_top2_kernel(const float4* __restrict__ summ /*[n_slices][n_rows]*/, 
                 insert(c);
             }
         } else {
+            // Straight-line scan (round 2: the branchy version — early-out insert with three struct shuffles, two-way soft-max update
+            // — ran every path for nearly every entry because SOME lane of the warp took it): the list is three (raw logit, token,
+            // entry) triples updated with selects, the soft-max partial is one FMA whose operands are selected (bit-identical to
+            // the two-branch form), and the full candidates are built once after the loop.
             const float4* sp = summ + row0 + my_k;
-            for (int sl0 = my_j; sl0 < n_slices; sl0 += 4 * J) {
-                float4 e[4];
+            float lv0 = -INFINITY, lv1 = -INFINITY, lv2 = -INFINITY;
+            int lt0 = 0x7fffffff, lt1 = 0x7fffffff, lt2 = 0x7fffffff, li0 = 0, li1 = 0, li2 = 0;
+            for (int sl0 = my_j; sl0 < n_slices; sl0 += UNR * J) {
+                float4 e[UNR];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {            // four independent loads in flight
+                for (int u = 0; u < UNR; ++u) {          // UNR independent loads in flight
                     const int sl = sl0 + u * J;
                     e[u] = sl < n_slices ? sp[(int64_t)sl * n_rows] : make_float4(-INFINITY, 0.f, -INFINITY, __int_as_float((int)0xFFFFFFFFu));
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < UNR; ++u) {
                     const int sl = sl0 + u * J;
                     if (sl >= n_slices) break;
                     const int idx = sl * Kin + my_k;
-                    if (e[u].x > pm) { ps = ps * exp2f((pm - e[u].x) * kL2e) + e[u].y; pm = e[u].x; }
-                    else if (e[u].x != -INFINITY) ps += e[u].y * exp2f((e[u].x - pm) * kL2e);
+                    {   // soft-max partial: ps·2^(pm − x) + y when x is a new maximum, else ps + y·2^(x − pm) — one FMA either way
+                        const bool up = e[u].x > pm;
+                        const float ex = exp2f((up ? pm - e[u].x : e[u].x - pm) * kL2e);
+                        const float upd = fmaf(up ? ps : e[u].y, ex, up ? e[u].y : ps);
+                        ps = (up || e[u].x != -INFINITY) ? upd : ps;
+                        pm = up ? e[u].x : pm;
+                    }
                     const int bits = __float_as_int(e[u].w), i1 = bits & 0xFFFF, i2 = (bits >> 16) & 0xFFFF;
-                    SelCand c;
-                    c.idx = idx; c.sc2 = -INFINITY; c.tok2 = 0xFFFF; c.depth = 2; c.sc = -INFINITY;
-                    int tok = 0x7fffffff;
-                    if (i1 != 0xFFFF && i1 != my_skip) { c.sc = e[u].x; tok = i1; c.depth = 0; c.tok2 = i2; c.sc2 = e[u].z; }
-                    else if (i1 != 0xFFFF && i2 != 0xFFFF) { c.sc = e[u].z; tok = i2; c.depth = 1; }   // i1 == skip ⇒ i2 != skip
-                    sl_v[idx] = c.sc;
-                    sl_i[idx] = tok == 0x7fffffff ? tok : (tok | (c.depth << 16));
-                    if (tok != 0x7fffffff) { c.flat = my_k * V + tok; insert(c); }
+                    const bool first = i1 != 0xFFFF && i1 != my_skip;                  // the slice's best may be chosen
+                    const bool second = !first && i1 != 0xFFFF && i2 != 0xFFFF;          // i1 == skip ⇒ i2 != skip
+                    const float cv = first ? e[u].x : (second ? e[u].z : -INFINITY);
+                    const int ct = first ? i1 : (second ? i2 : 0x7fffffff);
+                    sl_v[idx] = cv;
+                    sl_i[idx] = first ? i1 : (second ? (i2 | (1 << 16)) : 0x7fffffff);
+                    // keep the best three (logit descending, token ascending): an empty candidate (−inf, INT_MAX) beats nothing
+                    const bool b0 = cand_better(cv, ct, lv0, lt0), b1 = cand_better(cv, ct, lv1, lt1), b2 = cand_better(cv, ct, lv2, lt2);
+                    lv2 = b1 ? lv1 : (b2 ? cv : lv2); lt2 = b1 ? lt1 : (b2 ? ct : lt2); li2 = b1 ? li1 : (b2 ? idx : li2);
+                    lv1 = b0 ? lv0 : (b1 ? cv : lv1); lt1 = b0 ? lt0 : (b1 ? ct : lt1); li1 = b0 ? li0 : (b1 ? idx : li1);
+                    lv0 = b0 ? cv : lv0;              lt0 = b0 ? ct : lt0;              li0 = b0 ? idx : li0;
                 }
             }
+            // full candidates of the three survivors: depth from the entry just written, the slice's runner-up (depth 0 only) from
+            // the summary again (three independent loads, L2-resident)
+            auto build = [&](SelCand& L, float v, int t, int idx) {
+                if (t == 0x7fffffff) return;
+                L.sc = v; L.flat = my_k * V + t; L.idx = idx; L.depth = (sl_i[idx] >> 16) & 0xF; L.sc2 = -INFINITY; L.tok2 = 0xFFFF;
+                if (L.depth == 0) {
+                    const float4 e2 = sp[(int64_t)(idx / Kin) * n_rows];
+                    L.sc2 = e2.z;
+                    L.tok2 = (__float_as_int(e2.w) >> 16) & 0xFFFF;
+                }
+                ++n_l;
+            };
+            build(L0, lv0, lt0, li0);
+            build(L1, lv1, lt1, li1);
+            build(L2, lv2, lt2, li2);
         }
     }
     part_m[tid] = pm;
@@ -687,20 +718,29 @@ beam_select_top2_kernel(const float4* __restrict__ summ /*[n_slices][n_rows]*/, 
     };
     __syncthreads();
 
-    int n_eos = 0;
+    // K rounds of a block arg-max over the list heads.  A head travels as (score, flat << 9 | holder's thread): the flat index
+    // sits in the high bits, so the packed word orders ties exactly like the flat index alone, and the holder — which IS the
+    // owner of the winner's slice — is known without the two integer divisions every thread used to execute per round.  Every
+    // thread finishes the cross-warp step itself (double-buffered partials), so a round has ONE block barrier and no
+    // single-thread section: the owner records the winner and advances its slice while the others already reduce the next round.
+    int it = 0;
     for (int round = 0; round < K;) {
         float bv = L0.sc;
-        int bi = L0.flat, bs = L0.idx;
+        int bk = L0.flat == 0x7fffffff ? 0x7fffffff : ((L0.flat << 9) | tid);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            const int os = __shfl_xor_sync(0xffffffffu, bs, o);
-            if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; bs = os; }
+            const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+            if (cand_better(ov, ok, bv, bk)) { bv = ov; bk = ok; }
         }
-        if (lane == 0) { red_a[wid] = bv; red_i[wid] = bi; red_t[wid] = bs; }
+        const int pb = it & 1;
+        ++it;
+        if (lane == 0) { red_a[pb][wid] = bv; red_k[pb][wid] = bk; }
         __syncthreads();
-        if (req_flag) {
+        // The flag is double-buffered like the partials: this iteration reads word pb, an owner that asks for a recomputation
+        // writes word pb ^ 1 (read after the NEXT barrier) — with one barrier per round a single word would be written by a fast
+        // owner while slower warps still test it.
+        if (req_flag[pb]) {
             // block-uniform: the previous winner's slice needs a third (or later) candidate.  The CTA recomputes the slice's
             // logits from the operand planes with the tensor core's own three products (hi·hi + (lo·hi + hi·lo)·2^-11);
             // warp = every NW-th column, lane = 8 consecutive k; columns already taken are excluded.
@@ -746,61 +786,64 @@ beam_select_top2_kernel(const float4* __restrict__ summ /*[n_slices][n_rows]*/, 
                     if (cand_better(x, c, nv, ni)) { nv = x; ni = c; }
                 }
             }
-            __syncthreads();                              // red_* of the aborted arg-max are no longer needed
-            if (lane == 0) { red_a[wid] = nv; red_i[wid] = ni; }
+            if (lane == 0) { rc_a[wid] = nv; rc_i[wid] = ni; }
             __syncthreads();
-            if (((sl % J) * Kin + k) == tid) {            // the owner installs the recomputed candidate
-                nv = red_a[0]; ni = red_i[0];
+            if (tid == req_tid) {                         // the owner installs the recomputed candidate
+                nv = rc_a[0]; ni = rc_i[0];
                 for (int w = 1; w < NW; ++w)
-                    if (cand_better(red_a[w], red_i[w], nv, ni)) { nv = red_a[w]; ni = red_i[w]; }
+                    if (cand_better(rc_a[w], rc_i[w], nv, ni)) { nv = rc_a[w]; ni = rc_i[w]; }
                 apply_next(idx, k, ni == 0x7fffffff ? -INFINITY : score_of(k, nv), ni, 2);
-                req_flag = 0;
+                req_flag[pb] = 0;
             }
             __syncthreads();
             continue;                                     // redo the arg-max of this round with the owner's updated list
         }
-        if (tid == 0) {
-            float fv = red_a[0];
-            int fi = red_i[0], fs = red_t[0];
-            for (int w = 1; w < NW; ++w)
-                if (cand_better(red_a[w], red_i[w], fv, fi)) { fv = red_a[w]; fi = red_i[w]; fs = red_t[w]; }
-            const int par = fi / V, tok = fi - par * V;
-            win_sl = fs;
-            win_par[round] = par;
+        // cross-warp step, by every warp: lane l takes partial l mod NW, log2(NW) butterfly levels leave the winner in all lanes
+        float fv = red_a[pb][lane & (NW - 1)];
+        int fk = red_k[pb][lane & (NW - 1)];
+#pragma unroll
+        for (int o = NW / 2; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, fv, o);
+            const int ok = __shfl_xor_sync(0xffffffffu, fk, o);
+            if (cand_better(ov, ok, fv, fk)) { fv = ov; fk = ok; }
+        }
+        const bool none = fk == 0x7fffffff;               // no candidate left (needs V <= K + 1: excluded by the launcher)
+        if (tid == (none ? 0 : (fk & 511))) {             // the holder of the winning head = the owner of its slice
+            const int k = my_k, idx = L0.idx;
+            const int tok = none ? 0 : L0.flat - k * V;
+            win_par[round] = none ? 0 : k;
             win_tok[round] = tok;
             win_v[round] = fv;
-            n_eos += (tok == kEOS);
-        }
-        __syncthreads();
-        ++round;
-        const int w_idx = win_sl, w_sl = w_idx / Kin, w_k = w_idx - w_sl * Kin;
-        if (round < K && ((w_sl % J) * Kin + w_k) == tid) {   // owner: next candidate of the winner's slice
-            const int idx = w_idx, sl = w_sl, k = w_k;
-            const int cur = cur_s[k];
-            const int skip = (avoid_double && step > 0) ? cur : -1;
-            bool recompute = false;
-            float nsc = -INFINITY;
-            int nt = 0x7fffffff;
-            if (!(step > 0 && cur == kEOS)) {
-                if (L0.depth == 0 && force_recompute != 1) {
-                    int tok2 = L0.tok2;
-                    float sc2 = L0.sc2;
-                    if (tok2 == -2) {                     // list entry rebuilt by a rescan: fetch the slice's second again
-                        const float4 e = summ[(int64_t)sl * n_rows + row0 + k];
-                        tok2 = (__float_as_int(e.w) >> 16) & 0xFFFF;
-                        sc2 = tok2 == 0xFFFF ? -INFINITY : score_of(k, e.z);
+            if (tok == kEOS) atomicAdd(&n_eos_s, 1);
+            if (round + 1 < K && !none) {                 // next candidate of the winner's slice
+                const int sl = idx / Kin;
+                const int cur = cur_s[k];
+                const int skip = (avoid_double && step > 0) ? cur : -1;
+                bool recompute = false;
+                float nsc = -INFINITY;
+                int nt = 0x7fffffff;
+                if (!(step > 0 && cur == kEOS)) {
+                    if (L0.depth == 0 && force_recompute != 1) {
+                        int tok2 = L0.tok2;
+                        float sc2 = L0.sc2;
+                        if (tok2 == -2) {                 // list entry rebuilt by a rescan: fetch the slice's second again
+                            const float4 e = summ[(int64_t)sl * n_rows + row0 + k];
+                            tok2 = (__float_as_int(e.w) >> 16) & 0xFFFF;
+                            sc2 = tok2 == 0xFFFF ? -INFINITY : score_of(k, e.z);
+                        }
+                        if (tok2 == 0xFFFF) { /* single-column slice: exhausted */ }
+                        else if (tok2 != skip) { nsc = sc2; nt = tok2; }
+                        else recompute = true;
+                    } else {
+                        recompute = true;
                     }
-                    if (tok2 == 0xFFFF) { /* single-column slice: exhausted */ }
-                    else if (tok2 != skip) { nsc = sc2; nt = tok2; }
-                    else recompute = true;
-                } else {
-                    recompute = true;
                 }
+                if (dbg) { atomicAdd((unsigned long long*)dbg + 20, (unsigned long long)recompute); atomicAdd((unsigned long long*)dbg + 21, 1ull); }
+                if (recompute) { req_idx = idx; req_tid = tid; req_flag[pb ^ 1] = 1; }   // seen by everybody after the next barrier
+                else apply_next(idx, k, nsc, nt, 1);
             }
-            if (dbg) { atomicAdd((unsigned long long*)dbg + 20, (unsigned long long)recompute); atomicAdd((unsigned long long*)dbg + 21, 1ull); }
-            if (recompute) { req_idx = idx; req_flag = 1; }   // seen by everybody after the next round's first barrier
-            else apply_next(idx, k, nsc, nt, 1);
         }
+        ++round;
     }
     __syncthreads();
     if (tid < K) {
@@ -808,7 +851,7 @@ beam_select_top2_kernel(const float4* __restrict__ summ /*[n_slices][n_rows]*/, 
         tokens_out[(int64_t)b * K + tid] = win_tok[tid];
         parents_out[(int64_t)b * K + tid] = win_par[tid];
     }
-    if (tid == 0 && fin_counter) atomicAdd(fin_counter, n_eos);
+    if (tid == 0 && fin_counter) atomicAdd(fin_counter, n_eos_s);
 }
 
 // Row gather by parent + early-stop bookkeeping.
@@ -843,6 +886,7 @@ beam_advance_fused_kernel(float* __restrict__ h_next, const float* __restrict__ 
                           const uint16_t* __restrict__ t_hi, const uint16_t* __restrict__ t_lo, int64_t ld_t, int E, int64_t V,
                           volatile int32_t* host_progress, int nonce) {
     pdl_trigger();   // the contraction that follows may start its prologue while this kernel drains
+    pdl_wait();      // launched programmatically itself (PDL_BEAM): the selection's parents / tokens must have landed
     if (*reinterpret_cast<volatile int*>(done)) return;
     constexpr int RPB = 4;   // rows per block: 12000 one-row blocks were launch-overhead bound
     for (int n = blockIdx.x * RPB; n < min((int)(blockIdx.x + 1) * RPB, B * K); ++n) {   // new row
@@ -1042,22 +1086,29 @@ int beam_select_top2(const float4* summ, int slice_w, SplitDst t, const uint16_t
     // VAG_SELECT_RECOMPUTE=1 (tests): never use a slice's stored runner-up, always recompute — exercises the rare path
     const char* fe = getenv("VAG_SELECT_RECOMPUTE");
     const int force = fe ? (fe[0] == '1' ? 1 : (fe[0] == '2' ? 2 : 0)) : 0;   // 2: timing experiments only (never recompute)
-    const bool wide = B <= 2 * num_sms();                                     // few sentences: 512 threads each (see the kernel)
-#define VAG_SEL2_NT(KM, NT_)                                                                                                  \
+    // threads per sentence / summary loads in flight: VAG_SELECT_NT = 128 | 256 | 512, VAG_SELECT_UNR = 4 | 8 override the choice (A/B runs)
+    static const int env_nt = getenv("VAG_SELECT_NT") ? atoi(getenv("VAG_SELECT_NT")) : 0;
+    static const int env_unr = getenv("VAG_SELECT_UNR") ? atoi(getenv("VAG_SELECT_UNR")) : 0;
+    const int nt = env_nt ? env_nt : (B <= 2 * num_sms() ? 512 : kSel2Threads);   // few sentences: 512 threads each (see the kernel)
+    const int unr = env_unr ? env_unr : 4;
+#define VAG_SEL2_NT(KM, NT_, UNR_)                                                                                            \
     do {                                                                                                                      \
         static size_t configured = 0;                                                                                         \
         if (smem > 48 * 1024 && smem > configured) {                                                                          \
-            VAG_CUDA(cudaFuncSetAttribute(beam_select_top2_kernel<KM, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            VAG_CUDA(cudaFuncSetAttribute(beam_select_top2_kernel<KM, NT_, UNR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             configured = smem;                                                                                                \
         }                                                                                                                     \
-        beam_select_top2_kernel<KM, NT_><<<B, NT_, smem, st>>>(summ, n_slices, slice_w, B * Kin, t.hi, t.lo, t.ld, w_hi, w_lo, ld_w, bias, E, \
-                                                          t.mode, prev_tokens, nll, tokens_out, parents_out, K, (int)V, step,  \
-                                                          avoid_double, done, fin_counter, force, tc_debug());                 \
+        VAG_CUDA(launch_pdl(PDL_BEAM, beam_select_top2_kernel<KM, NT_, UNR_>, dim3(B), dim3(NT_), smem, st, summ, n_slices, slice_w, B * Kin, \
+                            (const uint16_t*)t.hi, (const uint16_t*)t.lo, (int64_t)t.ld, w_hi, w_lo, ld_w, bias, E, (int)t.mode, prev_tokens, nll, tokens_out, \
+                            parents_out, K, (int)V, step, avoid_double, done, fin_counter, force, tc_debug()));                \
     } while (0)
 #define VAG_SEL2(KM)                                                                                                          \
     do {                                                                                                                      \
-        if (wide) VAG_SEL2_NT(KM, 512);                                                                                       \
-        else VAG_SEL2_NT(KM, kSel2Threads);                                                                                   \
+        if (nt >= 512) VAG_SEL2_NT(KM, 512, 4);                                                                               \
+        else if (nt >= 256 && unr >= 8) VAG_SEL2_NT(KM, 256, 8);                                                              \
+        else if (nt >= 256) VAG_SEL2_NT(KM, 256, 4);                                                                          \
+        else if (unr >= 8) VAG_SEL2_NT(KM, 128, 8);                                                                           \
+        else VAG_SEL2_NT(KM, 128, 4);                                                                                         \
     } while (0)
     if (K <= 4) VAG_SEL2(4);
     else if (K <= 8) VAG_SEL2(8);
@@ -1082,8 +1133,8 @@ int beam_advance_fused(float* h_next, const float* h_cur, const int32_t* parents
                        int H, int step, int* done, int* fin_counter, int* steps_run, SplitDst h_sd, SplitDst e_sd,
                        const uint16_t* t_hi, const uint16_t* t_lo, int64_t ld_t, int E, int64_t V, cudaStream_t st,
                        volatile int32_t* host_progress, int nonce) {
-    beam_advance_fused_kernel<<<(B * K + 3) / 4, 128, 0, st>>>(h_next, h_cur, parents, tokens, B, K, Kin, H, step, done, fin_counter, steps_run,
-                                                     h_sd, e_sd, t_hi, t_lo, ld_t, E, V, host_progress, nonce);
+    VAG_CUDA(launch_pdl(PDL_BEAM, beam_advance_fused_kernel, dim3((B * K + 3) / 4), dim3(128), 0, st, h_next, h_cur, parents, tokens, B, K, Kin, H,
+                        step, done, (const int*)fin_counter, steps_run, h_sd, e_sd, t_hi, t_lo, ld_t, E, V, host_progress, nonce));
     VAG_LAUNCH_CHECK();
     return VAG_OK;
 }

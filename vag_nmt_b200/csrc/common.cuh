@@ -100,7 +100,7 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 // from the graph-replayed training step (batch 32, bf16): none 2.144 ms, TC 2.127, TC+SMALL 2.052, TC+SMALL+ATTN 2.066,
 // TC+SMALL+ROWS32 2.151 (early or late trigger alike: the recurrent 32-row kernels lose ~1 us per launch when launched
 // programmatically, so they stay ordinary launches).
-enum { PDL_TC = 1, PDL_ROWS32 = 2, PDL_ATTN = 4, PDL_SMALL = 8 };
+enum { PDL_TC = 1, PDL_ROWS32 = 2, PDL_ATTN = 4, PDL_SMALL = 8, PDL_BEAM = 16 /* selection + reorder kernels of the decode loop */ };
 bool pdl_enabled(int family);
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(int family, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {

@@ -33,6 +33,26 @@ constexpr int G_SMEM_BYTES = G_STAGES_SPLIT * (2 * G_A_BYTES + 2 * G_B_BYTES) + 
                  : "r"(addr)                                                                                                    \
                  : "memory")
 
+// 256-bit global accesses (sm_100: LDG / STG .256).  The epilogue's accesses are one row per lane — 32 cache lines per warp
+// instruction whatever its width, and the LSU pays per line — so moving a lane's 64 contiguous bytes with two instructions
+// instead of four halves the epilogue's LSU time.  Addresses must be 32-byte aligned.
+__device__ __forceinline__ void ldg256(float* d, const float* p) {
+    asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3]), "=f"(d[4]), "=f"(d[5]), "=f"(d[6]), "=f"(d[7]) : "l"(p));
+}
+__device__ __forceinline__ void ldg256_nc(float* d, const float* p) {
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3]), "=f"(d[4]), "=f"(d[5]), "=f"(d[6]), "=f"(d[7]) : "l"(p));
+}
+__device__ __forceinline__ void stg256(float* p, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+__device__ __forceinline__ void stg256_b32(void* p, const uint32_t* v) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+
 struct GruArgs {
     const float* bias;        // [4][H]: b_r, b_z, b_in, b_hn (unit-major; made by gru_bias_kernel)
     const float* g1;          // optional per-token table [V, 3H] (gate-major r | z | n, b_ih included): replaces phase X
@@ -45,6 +65,7 @@ struct GruArgs {
     int64_t out_ld;
     int rows, Kx, Kh, H;
     const int* done;
+    int wide;                 // every row base above is 32-byte aligned: 256-bit epilogue accesses (set by the launcher)
 };
 
 template <int MODE>
@@ -216,15 +237,29 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
             // epilogue; kept because it costs nothing.)
             const int ub = tn * UNITS + uh * 16;          // first of this warp's 16 units
             float hp[16], tr[16], tz[16], tq[16];
+            const bool wide = args.wide != 0;             // kernel-uniform
+            if (wide) {
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-                *reinterpret_cast<float4*>(hp + 4 * q4) = *reinterpret_cast<const float4*>(hp_row + ub + 4 * q4);
-                if (table) {
-                    *reinterpret_cast<float4*>(tr + 4 * q4) = *reinterpret_cast<const float4*>(g1_row + ub + 4 * q4);
-                    *reinterpret_cast<float4*>(tz + 4 * q4) = *reinterpret_cast<const float4*>(g1_row + H + ub + 4 * q4);
-                    *reinterpret_cast<float4*>(tq + 4 * q4) = *reinterpret_cast<const float4*>(g1_row + 2 * H + ub + 4 * q4);
+                for (int q8 = 0; q8 < 2; ++q8) {
+                    ldg256(hp + 8 * q8, hp_row + ub + 8 * q8);
+                    if (table) {
+                        ldg256_nc(tr + 8 * q8, g1_row + ub + 8 * q8);
+                        ldg256_nc(tz + 8 * q8, g1_row + H + ub + 8 * q8);
+                        ldg256_nc(tq + 8 * q8, g1_row + 2 * H + ub + 8 * q8);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    *reinterpret_cast<float4*>(hp + 4 * q4) = *reinterpret_cast<const float4*>(hp_row + ub + 4 * q4);
+                    if (table) {
+                        *reinterpret_cast<float4*>(tr + 4 * q4) = *reinterpret_cast<const float4*>(g1_row + ub + 4 * q4);
+                        *reinterpret_cast<float4*>(tz + 4 * q4) = *reinterpret_cast<const float4*>(g1_row + H + ub + 4 * q4);
+                        *reinterpret_cast<float4*>(tq + 4 * q4) = *reinterpret_cast<const float4*>(g1_row + 2 * H + ub + 4 * q4);
+                    }
                 }
             }
+            uint32_t keep_h[4], keep_l[4];                // operand planes of pass 0, stored together with pass 1's (wide mode)
             mbar_wait(&tfull_bar[a], (it >> 1) & 1);
             tcgen05_fence_after();
 #pragma unroll
@@ -282,19 +317,33 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
                     const float n = fmaf(-2.0f, rcp_approx(1.0f + exp2x_comp(fmaf(r, gh, gi))), 1.0f);
                     out[u] = fmaf(z, hp[8 * p + u] - n, n);       // (1 − z)·n + z·h_prev
                 }
-                if (live) {
+                uint32_t hw[4], lw[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    uint16_t h0, l0, h1, l1;
+                    split_one(MODE, out[2 * u], h0, l0);
+                    split_one(MODE, out[2 * u + 1], h1, l1);
+                    hw[u] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                    lw[u] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                }
+                if (live && wide) {
+                    stg256(args.h_out + (int64_t)row * H + u0, out);
+                    if (p == 0) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) { keep_h[u] = hw[u]; keep_l[u] = lw[u]; }
+                    } else {                               // 16 units = 32 bytes per plane
+                        const int64_t po = (int64_t)row * args.out_ld + u0 - 8;
+                        const uint32_t h8[8] = {keep_h[0], keep_h[1], keep_h[2], keep_h[3], hw[0], hw[1], hw[2], hw[3]};
+                        stg256_b32(args.out_hi + po, h8);
+                        if (SPLIT) {
+                            const uint32_t l8[8] = {keep_l[0], keep_l[1], keep_l[2], keep_l[3], lw[0], lw[1], lw[2], lw[3]};
+                            stg256_b32(args.out_lo + po, l8);
+                        }
+                    }
+                } else if (live) {
                     float* ho = args.h_out + (int64_t)row * H + u0;
                     *reinterpret_cast<float4*>(ho) = *reinterpret_cast<float4*>(out);
                     *reinterpret_cast<float4*>(ho + 4) = *reinterpret_cast<float4*>(out + 4);
-                    uint32_t hw[4], lw[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        uint16_t h0, l0, h1, l1;
-                        split_one(MODE, out[2 * u], h0, l0);
-                        split_one(MODE, out[2 * u + 1], h1, l1);
-                        hw[u] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-                        lw[u] = (uint32_t)l0 | ((uint32_t)l1 << 16);
-                    }
                     const int64_t po = (int64_t)row * args.out_ld + u0;
                     *reinterpret_cast<uint4*>(args.out_hi + po) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
                     if (SPLIT) *reinterpret_cast<uint4*>(args.out_lo + po) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
