@@ -25,7 +25,8 @@
 constexpr int G_A_BYTES = 128 * Q_ROWB;                 // 128 activation rows x 128 B
 constexpr int G_B_BYTES = 48 * Q_ROWB;                  // 48 weight rows x 128 B
 constexpr int G_STAGES_SPLIT = 4;                       // 4 x 44 KB (hi + lo planes); bf16 mode: 8 x 22 KB
-constexpr int G_SMEM_BYTES = G_STAGES_SPLIT * (2 * G_A_BYTES + 2 * G_B_BYTES) + 256 /*barriers*/ + 1024 /*align*/;
+constexpr int G_BIAS_MAX_H = 1024;                      // biases of the whole layer staged in shared memory: 4 x H floats
+constexpr int G_SMEM_BYTES = G_STAGES_SPLIT * (2 * G_A_BYTES + 2 * G_B_BYTES) + 256 /*barriers*/ + 4 * G_BIAS_MAX_H * 4 /*biases*/ + 1024 /*align*/;
 
 #define VAG_TMEM_LD8(v, addr)                                                                                                   \
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"                                \
@@ -68,8 +69,10 @@ struct GruArgs {
     int wide;                 // every row base above is 32-byte aligned: 256-bit epilogue accesses (set by the launcher)
 };
 
-template <int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
+// NEW = epilogue warps per CTA: 8 (each warp finishes 16 units of its 32 rows in two passes) or 16 (8 units, one pass).  The
+// epilogue of a tile is a chain of latencies (token → table row → accumulator → gate math); twice the warps halve it.
+template <int MODE, int NEW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * NEW, 1)
 gru_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                 const __grid_constant__ CUtensorMap map_hh, const __grid_constant__ CUtensorMap map_hl,
                 const __grid_constant__ CUtensorMap map_wih, const __grid_constant__ CUtensorMap map_wil,
@@ -90,6 +93,7 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
     uint64_t* tfull_bar = empty_bar + NST;    // [2]
     uint64_t* tempty_bar = tfull_bar + 2;     // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* bias_s = reinterpret_cast<float*>(smem + G_STAGES_SPLIT * (2 * G_A_BYTES + 2 * G_B_BYTES) + 256);   // [4][H]: the whole layer's biases
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -112,13 +116,23 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wih) : "memory");
         }
         for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], rank == 0 ? 9 : 8); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], rank == 0 ? NEW + 1 : NEW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
+    // the layer's biases (weights: independent of the predecessor kernel) go to shared memory once; the epilogue used to fetch
+    // them per tile and pass with same-address global loads whose L2 round trip sat between the TMEM loads and the gate math
+    // (only when a CTA works through several tiles: for a small batch the 8 KB copy and its barrier cost more than they save —
+    // measured +2.5 us per decoder step at 1500 rows)
+    const bool stage_bias = n_tiles > 2 * n_pairs;
+    if (stage_bias) {
+        for (int i = threadIdx.x; i < 4 * args.H; i += blockDim.x) bias_s[i] = args.bias[i];
+        __syncthreads();
+    }
+    const float* bias_src = stage_bias ? bias_s : args.bias;   // generic pointer: shared or global
     tcgen05_fence_before();
     cluster_sync_all();
     tcgen05_fence_after();
@@ -199,18 +213,23 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
             }
         }
     } else {
-        // ---- epilogue warps 2..9: TMEM lane group lg = warp % 4 (rows), unit half uh (16 of the tile's 32 hidden units)
+        // ---- epilogue warps 2..: TMEM lane group lg = warp % 4 (rows), unit group uh (UPW of the tile's 32 hidden units)
+        constexpr int UPW = 128 / NEW;                // units per warp: 16 (8 warps) or 8 (16 warps)
+        constexpr int NP = UPW / 8;                   // passes of 8 units
         const int ew = warp - 2, lg = warp & 3, uh = ew >> 2;
         const bool table = args.g1 != nullptr;
         constexpr uint32_t C_GIN = 0, C_R = 32, C_Z = 64, C_GHN = 96;   // accumulator columns of a buffer (cross accumulator: + 128)
         const uint32_t lane_base = tmem_base + ((uint32_t)(lg * 32) << 16);
-        // zero this warp's 16 gh_n columns (main and cross) of accumulator buffer a
+        // zero this warp's UPW gh_n columns (main and cross) of accumulator buffer a
         auto zero_ghn = [&](uint32_t a) {
             const uint32_t z = 0u;
-            const uint32_t t0 = lane_base + a * 256 + C_GHN + (uint32_t)(uh * 16);
-            asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(t0), "r"(z) : "memory");
-            if (SPLIT)
-                asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(t0 + 128u), "r"(z) : "memory");
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                const uint32_t t0 = lane_base + a * 256 + C_GHN + (uint32_t)(uh * UPW + q * 8);
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(t0), "r"(z) : "memory");
+                if (SPLIT)
+                    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(t0 + 128u), "r"(z) : "memory");
+            }
         };
         // completion 0 of both tempty barriers: the buffers start with gh_n = 0
         if (nkb_x) { zero_ghn(0); zero_ghn(1); asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -218,6 +237,12 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         if (lane == 0) { mbar_arrive(&tempty_bar[0]); mbar_arrive(&tempty_bar[1]); }
         __syncwarp();
         uint32_t it = 0;
+        // the token of a row is the head of the epilogue's dependency chain (token → table row → loads): fetched one tile ahead
+        auto token_of = [&](int tile) -> int64_t {
+            const int r = (tile / tiles_n) * BMP + (int)rank * BM + lg * 32 + lane;
+            return (table && tile < n_tiles && r < rows) ? args.tokens[r] : 0;
+        };
+        int64_t id_next = token_of(pair);
         for (int tile = pair; tile < n_tiles; tile += n_pairs, ++it) {
             const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
             const int row = tm * BMP + (int)rank * BM + lg * 32 + lane;
@@ -226,21 +251,19 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
             const float* hp_row = args.h_prev + (int64_t)(live ? row : 0) * H;
             const float* g1_row = nullptr;
             if (table) {
-                int64_t id = live ? args.tokens[row] : 0;
+                int64_t id = id_next;
                 if (id < 0 || id >= args.V) id = 0;
                 g1_row = args.g1 + id * 3 * (int64_t)H;
             }
             // Operands that do not depend on the accumulators — this row's previous state and, for gru_1, its token's table row —
-            // are requested for BOTH unit passes before the wait for the tile's MMAs, so their L2 latency (every lane reads its own
-            // row: 32 lines per load instruction) overlaps the tensor work.  (Measured: no change in the kernel's duration — the
-            // kernel is bound by L2 → shared-memory operand traffic, 44 KB per K block and CTA for 12 MMAs of N = 96, not by this
-            // epilogue; kept because it costs nothing.)
-            const int ub = tn * UNITS + uh * 16;          // first of this warp's 16 units
-            float hp[16], tr[16], tz[16], tq[16];
+            // are requested for all unit passes before the wait for the tile's MMAs, so their L2 latency (every lane reads its own
+            // row: 32 lines per load instruction) overlaps the tensor work.
+            const int ub = tn * UNITS + uh * UPW;         // first of this warp's units
+            float hp[UPW], tr[UPW], tz[UPW], tq[UPW];
             const bool wide = args.wide != 0;             // kernel-uniform
             if (wide) {
 #pragma unroll
-                for (int q8 = 0; q8 < 2; ++q8) {
+                for (int q8 = 0; q8 < NP; ++q8) {
                     ldg256(hp + 8 * q8, hp_row + ub + 8 * q8);
                     if (table) {
                         ldg256_nc(tr + 8 * q8, g1_row + ub + 8 * q8);
@@ -250,7 +273,7 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
                 }
             } else {
 #pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
+                for (int q4 = 0; q4 < 2 * NP; ++q4) {
                     *reinterpret_cast<float4*>(hp + 4 * q4) = *reinterpret_cast<const float4*>(hp_row + ub + 4 * q4);
                     if (table) {
                         *reinterpret_cast<float4*>(tr + 4 * q4) = *reinterpret_cast<const float4*>(g1_row + ub + 4 * q4);
@@ -259,12 +282,13 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
                     }
                 }
             }
-            uint32_t keep_h[4], keep_l[4];                // operand planes of pass 0, stored together with pass 1's (wide mode)
+            id_next = token_of(tile + n_pairs);
+            uint32_t keep_h[4], keep_l[4];                // operand planes of pass 0, stored together with pass 1's (wide mode, two passes)
             mbar_wait(&tfull_bar[a], (it >> 1) & 1);
             tcgen05_fence_after();
 #pragma unroll
-            for (int p = 0; p < 2; ++p) {
-                const int uc = uh * 16 + p * 8;            // first unit of this pass inside the tile
+            for (int p = 0; p < NP; ++p) {
+                const int uc = uh * UPW + p * 8;           // first unit of this pass inside the tile
                 const int u0 = tn * UNITS + uc;            // … and in the layer
                 uint32_t mr[8], mz[8], mi[8], mh[8], cr[8], cz[8], ci[8], chn[8];
                 const uint32_t taddr = lane_base + a * 256 + (uint32_t)uc;
@@ -278,16 +302,16 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
                     if (!table) VAG_TMEM_LD8(ci, taddr + 128u + C_GIN);
                     VAG_TMEM_LD8(chn, taddr + 128u + C_GHN);
                 }
-                float br[8], bz[8], bi[8], bh[8];          // biases: the same addresses for every lane (one L1 line per load)
+                float br[8], bz[8], bi[8], bh[8];          // biases: the same address for every lane (shared-memory broadcast / one L1 line)
 #pragma unroll
                 for (int q4 = 0; q4 < 2; ++q4) {
-                    *reinterpret_cast<float4*>(br + 4 * q4) = __ldg(reinterpret_cast<const float4*>(args.bias + u0 + 4 * q4));
-                    *reinterpret_cast<float4*>(bz + 4 * q4) = __ldg(reinterpret_cast<const float4*>(args.bias + H + u0 + 4 * q4));
-                    *reinterpret_cast<float4*>(bi + 4 * q4) = __ldg(reinterpret_cast<const float4*>(args.bias + 2 * H + u0 + 4 * q4));
-                    *reinterpret_cast<float4*>(bh + 4 * q4) = __ldg(reinterpret_cast<const float4*>(args.bias + 3 * H + u0 + 4 * q4));
+                    *reinterpret_cast<float4*>(br + 4 * q4) = *reinterpret_cast<const float4*>(bias_src + u0 + 4 * q4);
+                    *reinterpret_cast<float4*>(bz + 4 * q4) = *reinterpret_cast<const float4*>(bias_src + H + u0 + 4 * q4);
+                    *reinterpret_cast<float4*>(bi + 4 * q4) = *reinterpret_cast<const float4*>(bias_src + 2 * H + u0 + 4 * q4);
+                    *reinterpret_cast<float4*>(bh + 4 * q4) = *reinterpret_cast<const float4*>(bias_src + 3 * H + u0 + 4 * q4);
                 }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (p == 1) {   // all TMEM reads of this warp for this tile are complete: re-zero gh_n, hand the buffer back
+                if (p == NP - 1) {   // all TMEM reads of this warp for this tile are complete: re-zero gh_n, hand the buffer back
                     if (nkb_x) { zero_ghn(a); asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
                     tcgen05_fence_before();
                     if (lane == 0) mbar_arrive(&tempty_bar[a]);
@@ -326,7 +350,7 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
                     hw[u] = (uint32_t)h0 | ((uint32_t)h1 << 16);
                     lw[u] = (uint32_t)l0 | ((uint32_t)l1 << 16);
                 }
-                if (live && wide) {
+                if (live && wide && NP == 2) {
                     stg256(args.h_out + (int64_t)row * H + u0, out);
                     if (p == 0) {
 #pragma unroll
@@ -342,8 +366,11 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
                     }
                 } else if (live) {
                     float* ho = args.h_out + (int64_t)row * H + u0;
-                    *reinterpret_cast<float4*>(ho) = *reinterpret_cast<float4*>(out);
-                    *reinterpret_cast<float4*>(ho + 4) = *reinterpret_cast<float4*>(out + 4);
+                    if (wide) stg256(ho, out);
+                    else {
+                        *reinterpret_cast<float4*>(ho) = *reinterpret_cast<float4*>(out);
+                        *reinterpret_cast<float4*>(ho + 4) = *reinterpret_cast<float4*>(out + 4);
+                    }
                     const int64_t po = (int64_t)row * args.out_ld + u0;
                     *reinterpret_cast<uint4*>(args.out_hi + po) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
                     if (SPLIT) *reinterpret_cast<uint4*>(args.out_lo + po) = make_uint4(lw[0], lw[1], lw[2], lw[3]);

@@ -1585,7 +1585,7 @@ int tc_gemm_top2(float4* summ, const void* xh, const void* xl, int64_t ldxs, con
 // GRU cell fused into its contractions (gru_pair.cuh).  16-bit modes, rows > 128, H % 32 == 0, K % 8 == 0.
 bool tc_gru_supported(int rows, int H, int Kx, int Kh) {
     const int mode = gemm_mode();
-    return (mode == 1 || mode == 2) && rows > 128 && H % 32 == 0 && Kh >= 32 && Kh % 8 == 0 && (Kx == 0 || (Kx >= 32 && Kx % 8 == 0));
+    return (mode == 1 || mode == 2) && rows > 128 && H % 32 == 0 && H <= G_BIAS_MAX_H && Kh >= 32 && Kh % 8 == 0 && (Kx == 0 || (Kx >= 32 && Kx % 8 == 0));
 }
 int tc_gru(const GruCall& c, cudaStream_t st) {
     const int mode = gemm_mode();
@@ -1617,14 +1617,18 @@ int tc_gru(const GruCall& c, cudaStream_t st) {
     const int n_tiles = (c.H / 32) * ceil_div(c.rows, 256);
     const int max_pairs = num_sms() / 2;
     const int grid = 2 * (n_tiles < max_pairs ? n_tiles : max_pairs);
-    static bool attr_set[3] = {false, false, false};
-    if (mode == 1) {
-        if (!attr_set[1]) { VAG_CUDA(cudaFuncSetAttribute(gru_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES)); attr_set[1] = true; }
-        VAG_CUDA(launch_pdl(PDL_TC, gru_pair_kernel<1>, dim3(grid), dim3(320), G_SMEM_BYTES, st, mxh, mxl, mhh, mhl, mwih, mwil, mwhh, mwhl, a));
-    } else {
-        if (!attr_set[2]) { VAG_CUDA(cudaFuncSetAttribute(gru_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES)); attr_set[2] = true; }
-        VAG_CUDA(launch_pdl(PDL_TC, gru_pair_kernel<2>, dim3(grid), dim3(320), G_SMEM_BYTES, st, mxh, mxl, mhh, mhl, mwih, mwil, mwhh, mwhl, a));
-    }
+    // 8 epilogue warps (two passes of 8 units each) is the default; VAG_GRU_EW=16 selects sixteen single-pass warps — measured
+    // SLOWER (1000 sentences: 52.9 vs 48.4 ms): 96 registers per thread at 576 threads spill the accumulator fragments
+    static const bool ew8 = !(getenv("VAG_GRU_EW") && atoi(getenv("VAG_GRU_EW")) == 16);
+#define VAG_GRU_LAUNCH(MODE_, NEW_)                                                                                            \
+    do {                                                                                                                       \
+        static bool attr_set = false;                                                                                          \
+        if (!attr_set) { VAG_CUDA(cudaFuncSetAttribute(gru_pair_kernel<MODE_, NEW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES)); attr_set = true; } \
+        VAG_CUDA(launch_pdl(PDL_TC, gru_pair_kernel<MODE_, NEW_>, dim3(grid), dim3(64 + 32 * NEW_), G_SMEM_BYTES, st, mxh, mxl, mhh, mhl, mwih, mwil, mwhh, mwhl, a)); \
+    } while (0)
+    if (mode == 1) { if (ew8) VAG_GRU_LAUNCH(1, 8); else VAG_GRU_LAUNCH(1, 16); }
+    else { if (ew8) VAG_GRU_LAUNCH(2, 8); else VAG_GRU_LAUNCH(2, 16); }
+#undef VAG_GRU_LAUNCH
     VAG_LAUNCH_CHECK();
     return VAG_OK;
 }
