@@ -530,6 +530,25 @@ struct SelCand {
     int tok2;      // ... and its column (0xFFFF: the slice has no second; -2: not loaded, read the summary again)
 };
 
+// Optional tail of the selection kernel: the work of beam_advance_fused_kernel for the CTA's own sentence — state rows gathered
+// by parent (fp32 + operand planes), operand planes of the chosen tokens' embeddings — and, by the LAST CTA to finish (ticket
+// counter), the stop test and the host progress word.  One launch less per decoder step; the copies (≈ 100 MB per step at 12 000
+// rows) overlap the latency-bound pops of the other sentences on the SM.
+struct SelAdvance {
+    float* h_next = nullptr;          // nullptr: disabled (the caller launches beam_advance_fused itself)
+    const float* h_cur = nullptr;
+    int H = 0, E = 0;
+    SplitDst h_sd, e_sd;
+    const uint16_t* emb_hi = nullptr;
+    const uint16_t* emb_lo = nullptr;
+    int64_t ld_emb = 0;
+    int* done = nullptr;
+    int* steps_run = nullptr;
+    int* ticket = nullptr;            // zeroed per decode call, one word per step
+    volatile int32_t* host_progress = nullptr;
+    int nonce = 0;
+};
+
 // NT = threads per sentence: 128 when there are enough sentences to fill the GPU (7 CTAs per SM), 512 for small batches (the
 // reference's eval batch of 16; a test set sharded over 8 GPUs), where the kernel's duration is ONE CTA's latency and that latency
 // is the summary scan (294 x K float4 loads per sentence, four in flight per thread): more workers per row shorten it fourfold.
@@ -541,8 +560,8 @@ beam_select_top2_kernel(const float4* __restrict__ summ /*[n_slices][n_rows]*/, 
                         const float* __restrict__ bias, int E, int mode, const int64_t* __restrict__ prev_tokens,
                         float* __restrict__ nll, int64_t* __restrict__ tokens_out, int32_t* __restrict__ parents_out, int K,
                         int V, int step, int avoid_double, const int* __restrict__ done, int* __restrict__ fin_counter,
-                        int force_recompute, long long* __restrict__ dbg) {
-    pdl_trigger();   // the reorder kernel that follows may become resident while this one drains
+                        int force_recompute, long long* __restrict__ dbg, const SelAdvance adv) {
+    pdl_trigger();   // the kernel that follows may become resident while this one drains
     pdl_wait();      // launched programmatically itself (PDL_BEAM): the vocabulary summaries must have landed
     if (done && *reinterpret_cast<const volatile int*>(done)) return;
     extern __shared__ float dyn[];
@@ -851,6 +870,52 @@ beam_select_top2_kernel(const float4* __restrict__ summ /*[n_slices][n_rows]*/, 
         tokens_out[(int64_t)b * K + tid] = win_tok[tid];
         parents_out[(int64_t)b * K + tid] = win_par[tid];
     }
+    if (adv.h_next) {
+        // ---- the sentence's share of the reorder (see SelAdvance): new row n = b·K + k takes the state of row b·Kin + parent
+        const int H4 = adv.H >> 2, E8 = adv.E >> 3;
+        for (int k0 = 0; k0 < K; k0 += 4) {               // four rows' loads in flight per thread
+            for (int c = tid; c < H4; c += NT) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (k0 + u < K) v[u] = reinterpret_cast<const float4*>(adv.h_cur + (row0 + (Kin == 1 ? 0 : win_par[k0 + u])) * adv.H)[c];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (k0 + u < K) {
+                        const int64_t n = (int64_t)b * K + k0 + u;
+                        reinterpret_cast<float4*>(adv.h_next + n * adv.H)[c] = v[u];
+                        split_store4(adv.h_sd, n, c * 4, v[u]);
+                    }
+            }
+        }
+        if (adv.e_sd.hi) {
+            for (int i = tid; i < K * E8; i += NT) {
+                const int k = i / E8, c = i - k * E8;
+                int64_t id = win_tok[k];
+                if (id < 0 || id >= V) id = 0;
+                const int64_t n = (int64_t)b * K + k;
+                *reinterpret_cast<uint4*>(adv.e_sd.hi + n * adv.e_sd.ld + c * 8) = *reinterpret_cast<const uint4*>(adv.emb_hi + id * adv.ld_emb + c * 8);
+                if (adv.e_sd.mode != 2)
+                    *reinterpret_cast<uint4*>(adv.e_sd.lo + n * adv.e_sd.ld + c * 8) = *reinterpret_cast<const uint4*>(adv.emb_lo + id * adv.ld_emb + c * 8);
+            }
+        }
+        if (tid == 0) {
+            // stop test (V11:265-269) by the last CTA to get here: every CTA adds its <eos> count BEFORE it takes a ticket
+            atomicAdd(fin_counter, n_eos_s);
+            __threadfence();
+            if (atomicAdd(adv.ticket, 1) == (int)gridDim.x - 1) {
+                __threadfence();
+                const int fin = atomicAdd(fin_counter, 0) == (int)gridDim.x * K;
+                adv.steps_run[0] = step + 1;
+                if (fin) *adv.done = 1;
+                if (adv.host_progress) {   // mapped host memory: the host throttles / stops its launch loop on this word
+                    *adv.host_progress = (adv.nonce << 16) | (fin << 15) | (step + 1);
+                    __threadfence_system();
+                }
+            }
+        }
+        return;
+    }
     if (tid == 0 && fin_counter) atomicAdd(fin_counter, n_eos_s);
 }
 
@@ -1071,7 +1136,9 @@ long long* tc_debug();
 // summ: [ceil(V / slice_w)][n_rows] (tc_gemm_top2), n_rows = B (step 0) or B·K
 int beam_select_top2(const float4* summ, int slice_w, SplitDst t, const uint16_t* w_hi, const uint16_t* w_lo, int64_t ld_w,
                      const float* bias, int E, const int64_t* prev_tokens, float* nll, int64_t* tokens_out, int32_t* parents_out,
-                     int B, int K, int64_t V, int step, int avoid_double, const int* done, int* fin_counter, cudaStream_t st) {
+                     int B, int K, int64_t V, int step, int avoid_double, const int* done, int* fin_counter, cudaStream_t st,
+                     const SelAdvance* adv_in) {
+    const SelAdvance adv = adv_in ? *adv_in : SelAdvance();
     if (K > kMaxBeam || (int64_t)K * V >= 0x7fffffff || V <= K + 1 || V >= 0xFFFF || (E % 8)) {
         set_error("beam_select_top2: unsupported K=%d V=%lld E=%d", K, (long long)V, E);
         return VAG_ERR_UNSUPPORTED;
@@ -1100,7 +1167,7 @@ int beam_select_top2(const float4* summ, int slice_w, SplitDst t, const uint16_t
         }                                                                                                                     \
         VAG_CUDA(launch_pdl(PDL_BEAM, beam_select_top2_kernel<KM, NT_, UNR_>, dim3(B), dim3(NT_), smem, st, summ, n_slices, slice_w, B * Kin, \
                             (const uint16_t*)t.hi, (const uint16_t*)t.lo, (int64_t)t.ld, w_hi, w_lo, ld_w, bias, E, (int)t.mode, prev_tokens, nll, tokens_out, \
-                            parents_out, K, (int)V, step, avoid_double, done, fin_counter, force, tc_debug()));                \
+                            parents_out, K, (int)V, step, avoid_double, done, fin_counter, force, tc_debug(), adv));           \
     } while (0)
 #define VAG_SEL2(KM)                                                                                                          \
     do {                                                                                                                      \

@@ -475,9 +475,24 @@ int attention_mlp_split(SplitDst sd, const float* q, int64_t ld_q, const float* 
                         const float* mask, int rows, int rows_per_sent, int T, int C, cudaStream_t st, const int* done = nullptr,
                         const float* ekeys = nullptr, const int* kflag = nullptr);
 int attn_exp_keys(float* ekeys, int* kflag, const float* keys, int B, int T, int C, cudaStream_t st);
+struct SelAdvance {   // mirrors beam.cu (tail of the selection kernel that replaces beam_advance_fused)
+    float* h_next = nullptr;
+    const float* h_cur = nullptr;
+    int H = 0, E = 0;
+    SplitDst h_sd, e_sd;
+    const uint16_t* emb_hi = nullptr;
+    const uint16_t* emb_lo = nullptr;
+    int64_t ld_emb = 0;
+    int* done = nullptr;
+    int* steps_run = nullptr;
+    int* ticket = nullptr;
+    volatile int32_t* host_progress = nullptr;
+    int nonce = 0;
+};
 int beam_select_top2(const float4* summ, int tile_w, SplitDst t, const uint16_t* w_hi, const uint16_t* w_lo, int64_t ld_w,
                      const float* bias, int E, const int64_t* prev_tokens, float* nll, int64_t* tokens_out, int32_t* parents_out,
-                     int B, int K, int64_t V, int step, int avoid_double, const int* done, int* fin_counter, cudaStream_t st);
+                     int B, int K, int64_t V, int step, int avoid_double, const int* done, int* fin_counter, cudaStream_t st,
+                     const SelAdvance* adv = nullptr);
 int beam_advance_fused(float* h_next, const float* h_cur, const int32_t* parents, const int64_t* tokens, int B, int K, int Kin,
                        int H, int step, int* done, int* fin_counter, int* steps_run, SplitDst h_sd, SplitDst e_sd,
                        const uint16_t* t_hi, const uint16_t* t_lo, int64_t ld_t, int E, int64_t V, cudaStream_t st,
@@ -620,7 +635,7 @@ struct BeamWs {
     float4* summ;
     int64_t *tok_hist, *sos;
     int32_t* par_hist;
-    int* flags;  // [0] done, [1] steps_run, [2..2+L) per-step EOS counters
+    int* flags;  // [0] done, [1] steps_run, [2..2+L) per-step EOS counters, [2+L..2+2L) per-step CTA tickets (fused reorder)
     float* ekeys;
     int* kflag;
 };
@@ -642,7 +657,7 @@ static void beam_layout(A& a, int B, int K, int T, int L, int E, int H, int C, i
     int64_t* tok_hist = (int64_t*)a.template take<int64_t>((size_t)L * N);
     int64_t* sos = (int64_t*)a.template take<int64_t>((size_t)B);
     int32_t* par_hist = (int32_t*)a.template take<int32_t>((size_t)L * N);
-    int* flags = (int*)a.template take<int>((size_t)L + 2);
+    int* flags = (int*)a.template take<int>(2 * (size_t)L + 2);
     float* ekeys = (float*)a.template take<float>((size_t)B * T * C);   // exp(2·keys) for the factored attention scores
     int* kflag = (int*)a.template take<int>((size_t)B);
     if (ws) {
@@ -712,7 +727,7 @@ extern "C" int vag_beam_decode_f32(const vag_decoder_weights* w, const float* h0
     int* done = ws.flags;
     int* steps_run = ws.flags + 1;
     int* fin = ws.flags + 2;
-    VAG_CUDA(cudaMemsetAsync(ws.flags, 0, sizeof(int) * (size_t)(L + 2), st));
+    VAG_CUDA(cudaMemsetAsync(ws.flags, 0, sizeof(int) * (2 * (size_t)L + 2), st));
     fill_i64_kernel<<<ceil_div(B, 256), 256, 0, st>>>(ws.sos, 2 /*SOS*/, B);
     VAG_LAUNCH_CHECK();
     const int64_t ldl = (V + 3) / 4 * 4;
@@ -732,6 +747,10 @@ extern "C" int vag_beam_decode_f32(const vag_decoder_weights* w, const float* h0
         }
     }
     const int nonce = host_progress ? progress_nonce() : 0;
+    // VAG_SEL_ADVANCE=1: the reorder runs as the tail of the selection kernel (one launch less per step).  Opt-in: token-identical
+    // but measured SLOWER than the separate bandwidth-shaped launch in every regime (1000 sentences bf16 34.86 vs 34.32 ms, FP32
+    // 49.2 vs 48.9; 16 sentences 9.85 vs 9.76 ms) — a sentence's 84 KB of copies serialise behind its own pops.
+    static const bool sel_advance = getenv("VAG_SEL_ADVANCE") && getenv("VAG_SEL_ADVANCE")[0] == '1';
     constexpr int kLookahead = 4;     // steps the host may enqueue ahead of the device when it polls host_progress
     for (int di = 0; di < L; ++di) {
         if (host_progress && di > kLookahead) {
@@ -771,10 +790,17 @@ extern "C" int vag_beam_decode_f32(const vag_decoder_weights* w, const float* h0
             VAG_TRY(decoder_step_fused(fused, w, ws.step, tokens, h_prev, keys, ctx, mask, rows, rps, T, ws.h_b, no_logits ? nullptr : ws.logits,
                                        ldl, st, V >= 512 ? ws.summ : nullptr, &tile_w));
             if (no_logits) {
+                // the reorder (state rows by parent, embedding planes, stop test) runs as the tail of the selection kernel
+                SelAdvance adv;
+                if (sel_advance && (H % 4) == 0 && (E % 8) == 0) {
+                    adv.h_next = ws.h_a; adv.h_cur = ws.h_b; adv.H = H; adv.E = E; adv.h_sd = fused.hprev; adv.e_sd = fused.cat_e(H);
+                    adv.emb_hi = (const uint16_t*)fused.w_emb->hi; adv.emb_lo = (const uint16_t*)fused.w_emb->lo; adv.ld_emb = fused.w_emb->ld;
+                    adv.done = done; adv.steps_run = steps_run; adv.ticket = fin + L + di; adv.host_progress = host_progress; adv.nonce = nonce;
+                }
                 VAG_TRY(beam_select_top2(ws.summ, 32, fused.t, (const uint16_t*)pr.out.hi, (const uint16_t*)pr.out.lo,
                                          pr.out.ld, w->out_b, E, di == 0 ? nullptr : tokens, ws.nll, ws.tok_hist + (size_t)di * N,
-                                         ws.par_hist + (size_t)di * N, B, K, V, di, avoid_double, done, fin + di, st));
-                tile_w = -1;   // selection done
+                                         ws.par_hist + (size_t)di * N, B, K, V, di, avoid_double, done, fin + di, st, &adv));
+                tile_w = adv.h_next ? -2 : -1;   // selection done (-2: and the reorder with it)
             }
         } else
         VAG_TRY(decoder_step_core(gemm, w, ws.step, tokens, h_prev, keys, ctx, mask, rows, rps, T, ws.h_b, ws.logits, ldl, nullptr, st,
@@ -790,7 +816,8 @@ extern "C" int vag_beam_decode_f32(const vag_decoder_weights* w, const float* h0
             VAG_TRY(beam_select(ws.logits, ldl, ws.lse, di == 0 ? nullptr : tokens, ws.nll, ws.tok_hist + (size_t)di * N,
                                 ws.par_hist + (size_t)di * N, B, K, V, di, avoid_double, done, fin + di, st));
         }
-        if (fused.ok)
+        if (tile_w == -2) {
+        } else if (fused.ok)
             VAG_TRY(beam_advance_fused(ws.h_a, ws.h_b, ws.par_hist + (size_t)di * N, ws.tok_hist + (size_t)di * N, B, K, rps, H, di, done,
                                        fin + di, steps_run, fused.hprev, fused.cat_e(H), (const uint16_t*)fused.w_emb->hi,
                                        (const uint16_t*)fused.w_emb->lo, fused.w_emb->ld, E, V, st, host_progress, nonce));
