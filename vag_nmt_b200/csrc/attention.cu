@@ -307,8 +307,12 @@ attention_tuned_kernel(float* __restrict__ c_out, int64_t ld_c, float* __restric
         const float kmax = try_fast ? __int_as_float(kflag[b]) : INFINITY;   // +inf: a key out of range (attn_exp_keys)
         bool bad = try_fast && !(kmax <= kFactoredMaxAbs);
         float qmax = 0.f;
+        int sr = (tid * 4) / C, scol = tid * 4 - sr * C;     // (row, channel) of element i, advanced without a division per pass
+        const int adv_r = 1024 / C, adv_c = 1024 - adv_r * C;
         for (int i = tid * 4; i < RCAP * C; i += 1024) {
-            const int r = i / C, c = i - r * C;
+            const int r = sr, c = scol;
+            sr += adv_r; scol += adv_c;
+            if (scol >= C) { scol -= C; ++sr; }
             float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
             if (r < R && row0 + r < rows) {
                 val = *reinterpret_cast<const float4*>(q + (int64_t)(row0 + r) * ld_q + c);
@@ -377,9 +381,14 @@ attention_tuned_kernel(float* __restrict__ c_out, int64_t ld_c, float* __restric
         const float* ekey_b = ekeys + (int64_t)b * T * C;
         auto score_loop = [&](auto clamp_tag) {
             constexpr bool CLAMP = decltype(clamp_tag)::value;
+            // item = (live position, row group), dealt round-robin; the pair is advanced incrementally (no division per item)
+            const int step_t = NW / n_groups, step_g = NW - step_t * n_groups;
+            int it_t = wid / n_groups, it_g = wid - it_t * n_groups;
             for (int item = wid; item < n_live * n_groups; item += NW) {
-                const int t = live_t[item / n_groups];
-                const int r_lo = (item % n_groups) * RG;
+                const int t = live_t[it_t];
+                const int r_lo = it_g * RG;
+                it_t += step_t; it_g += step_g;
+                if (it_g >= n_groups) { it_g -= n_groups; ++it_t; }
                 float part[RG];
 #pragma unroll
                 for (int g = 0; g < RG; ++g) part[g] = 0.f;
@@ -402,12 +411,23 @@ attention_tuned_kernel(float* __restrict__ c_out, int64_t ld_c, float* __restric
                         }
                     }
                 }
+                if (RG == 2) {
+                    // two reductions in five shuffles: the halves of the warp swap the sum they do not keep, then both butterflies
+                    // run in the same four instructions (the same additions in the same order as two separate warp sums)
+                    const bool lo = lane < 16;
+                    float keep = (lo ? part[0] : part[RG - 1]) + __shfl_xor_sync(0xffffffffu, lo ? part[RG - 1] : part[0], 16);
 #pragma unroll
-                for (int g = 0; g < RG; ++g) {
-                    const int r = r_lo + g;
-                    if (r < R) {
-                        const float sum = warp_sum(part[g]);
-                        if (lane == 0) sc_s[r * T + t] = fmaf(-2.0f, sum, vsum);
+                    for (int o = 8; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+                    const int r = r_lo + (lo ? 0 : 1);
+                    if ((lane & 15) == 0 && r < R) sc_s[r * T + t] = fmaf(-2.0f, keep, vsum);
+                } else {
+#pragma unroll
+                    for (int g = 0; g < RG; ++g) {
+                        const int r = r_lo + g;
+                        if (r < R) {
+                            const float sum = warp_sum(part[g]);
+                            if (lane == 0) sc_s[r * T + t] = fmaf(-2.0f, sum, vsum);
+                        }
                     }
                 }
             }
