@@ -49,6 +49,14 @@ struct EncoderWs {
     float *x, *gi[2], *gh[2], *h[2];
     void *wreg, *areg;
     size_t wbytes, abytes;
+    // GRU cell fused into its hidden contraction (gru_pair_kernel, > 128 active rows): permuted W_hh planes and unit-major
+    // biases per direction, a second state buffer (the fused kernel must not write the rows other tiles still read) and the
+    // operand planes of both state buffers
+    void *whp[2], *wlp[2];
+    float* bias4[2];
+    float* h_alt[2];
+    void *php[2][2], *plp[2][2];
+    float* permute_scratch;
 };
 template <typename A>
 static void encoder_layout(A& a, int B, int T, int E, int H, EncoderWs* ws) {
@@ -63,9 +71,27 @@ static void encoder_layout(A& a, int B, int T, int E, int H, EncoderWs* ws) {
     const size_t ab = max_sz(GemmCtx::split_bytes((int64_t)T * B, E), GemmCtx::split_bytes(B, H)) + 4096;
     void* wr = a.template take<char>(wb);
     void* ar = a.template take<char>(ab);
+    void *whp[2], *wlp[2], *php[2][2], *plp[2][2];
+    float *bias4[2], *h_alt[2];
+    for (int d = 0; d < 2; ++d) {
+        whp[d] = a.template take<uint16_t>((size_t)3 * H * H);
+        wlp[d] = a.template take<uint16_t>((size_t)3 * H * H);
+        bias4[d] = (float*)a.template take<float>((size_t)4 * H);
+        h_alt[d] = (float*)a.template take<float>((size_t)B * H);
+        for (int q = 0; q < 2; ++q) {
+            php[d][q] = a.template take<uint16_t>((size_t)B * H);
+            plp[d][q] = a.template take<uint16_t>((size_t)B * H);
+        }
+    }
+    float* permute_scratch = (float*)a.template take<float>((size_t)3 * H * H);
     if (ws) {
         ws->x = x; ws->gi[0] = gi0; ws->gi[1] = gi1; ws->gh[0] = gh0; ws->gh[1] = gh1; ws->h[0] = h0; ws->h[1] = h1;
         ws->wreg = wr; ws->wbytes = wb; ws->areg = ar; ws->abytes = ab;
+        for (int d = 0; d < 2; ++d) {
+            ws->whp[d] = whp[d]; ws->wlp[d] = wlp[d]; ws->bias4[d] = bias4[d]; ws->h_alt[d] = h_alt[d];
+            for (int q = 0; q < 2; ++q) { ws->php[d][q] = php[d][q]; ws->plp[d][q] = plp[d][q]; }
+        }
+        ws->permute_scratch = permute_scratch;
     }
 }
 struct SizerAdapter {
@@ -256,16 +282,57 @@ extern "C" int vag_encoder_fwd_f32(const vag_encoder_weights* w, const int64_t* 
         VAG_TRY(gemm.linear(ws.gi[d], 3 * H, ws.x, E, w->w_ih[d], E, w->b_ih[d], T * B, E, 3 * H, 0));
         VAG_CUDA(cudaMemsetAsync(ws.h[d], 0, (size_t)B * H * sizeof(float), st));
     }
+    // Steps with more than 128 active rows run the whole cell in ONE launch (gru_pair_kernel: hidden contraction + gates on the TMEM
+    // drain, the input pre-activations gi[t] gathered like the decoder's per-token table with table row = sentence, h' written
+    // into the state buffer, its operand planes and the context slab) instead of contraction + operand split + gate kernel.  The
+    // fused kernel ping-pongs between two state buffers; rows beyond the active prefix are never written, so a sentence that
+    // starts later (backward direction) finds zeros in both.  Smaller steps keep the three-kernel path on the current buffer.
+    static const bool enc_fused_off = getenv("VAG_ENC_FUSED") && getenv("VAG_ENC_FUSED")[0] == '0';
+    const int mode = gemm_mode();
+    bool fused_ok = !enc_fused_off && (mode == 1 || mode == 2) && tc_gru_supported(n_act[0], H, 0, H) && (H % 16) == 0 &&
+                    ((reinterpret_cast<uintptr_t>(ctx_out) & 15) == 0);
+    float* hbuf[2][2] = {{ws.h[0], ws.h_alt[0]}, {ws.h[1], ws.h_alt[1]}};
+    int cur[2] = {0, 0};
+    bool planes_valid[2] = {false, false};
+    if (fused_ok) {
+        for (int d = 0; d < 2; ++d) {
+            VAG_TRY(tc_gru_prepare_weight(ws.whp[d], ws.wlp[d], w->w_hh[d], H, H, true, ws.permute_scratch, st));
+            VAG_TRY(tc_gru_prepare_bias(ws.bias4[d], nullptr, w->b_hh[d], H, false, st));
+            VAG_CUDA(cudaMemsetAsync(ws.h_alt[d], 0, (size_t)B * H * sizeof(float), st));
+        }
+    }
     // the two directions are independent chains; interleave them so neighbouring launches can overlap their tails
     for (int s = 0; s < T; ++s) {
         for (int d = 0; d < 2; ++d) {
             const int t = d == 0 ? s : T - 1 - s;
             const int n = n_act[t];
             if (n == 0) continue;
+            float* hc = hbuf[d][cur[d]];
+            if (fused_ok && tc_gru_supported(n, H, 0, H)) {
+                float* hn = hbuf[d][cur[d] ^ 1];
+                if (!planes_valid[d]) {   // first fused step of this direction (or after three-kernel steps): planes of ALL rows of the current state
+                    VAG_TRY(tc_split(hc, H, B, H, ws.php[d][cur[d]], ws.plp[d][cur[d]], H, 0, st));
+                    VAG_CUDA(cudaMemsetAsync(ws.php[d][cur[d] ^ 1], 0, (size_t)B * H * 2, st));
+                    VAG_CUDA(cudaMemsetAsync(ws.plp[d][cur[d] ^ 1], 0, (size_t)B * H * 2, st));
+                    planes_valid[d] = true;
+                }
+                GruCall g;
+                g.hh = ws.php[d][cur[d]]; g.hl = ws.plp[d][cur[d]]; g.ldh = H; g.Kh = H;
+                g.whh_h = ws.whp[d]; g.whh_l = ws.wlp[d];
+                g.bias4 = ws.bias4[d]; g.g1 = ws.gi[d] + (int64_t)t * B * 3 * H; g.tokens = nullptr; g.V = B;
+                g.h_prev = hc; g.h_out = hn;
+                g.out.hi = (uint16_t*)ws.php[d][cur[d] ^ 1]; g.out.lo = (uint16_t*)ws.plp[d][cur[d] ^ 1]; g.out.ld = H; g.out.mode = mode;
+                g.rows = n; g.H = H;
+                g.y2 = ctx_out + (int64_t)t * 2 * H + d * H; g.ld_y2 = (int64_t)T * 2 * H;
+                VAG_TRY(tc_gru(g, st));
+                cur[d] ^= 1;
+                continue;
+            }
+            planes_valid[d] = false;
             gemm.new_step();  // h changed: its split is stale
-            VAG_TRY(gemm.linear(ws.gh[d], 3 * H, ws.h[d], H, w->w_hh[d], H, w->b_hh[d], n, H, 3 * H, 0));
-            VAG_TRY(vag_gru_gates_f32(ws.h[d], H, ctx_out + (int64_t)t * 2 * H + d * H, (int64_t)T * 2 * H,
-                                      ws.gi[d] + (int64_t)t * B * 3 * H, 3 * H, ws.gh[d], 3 * H, ws.h[d], H, n, H, stream));
+            VAG_TRY(gemm.linear(ws.gh[d], 3 * H, hc, H, w->w_hh[d], H, w->b_hh[d], n, H, 3 * H, 0));
+            VAG_TRY(vag_gru_gates_f32(hc, H, ctx_out + (int64_t)t * 2 * H + d * H, (int64_t)T * 2 * H,
+                                      ws.gi[d] + (int64_t)t * B * 3 * H, 3 * H, ws.gh[d], 3 * H, hc, H, n, H, stream));
         }
     }
     return VAG_OK;

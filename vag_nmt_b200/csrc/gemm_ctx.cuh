@@ -48,12 +48,14 @@ struct GruCall {
     const void *wih_h = nullptr, *wih_l = nullptr, *whh_h = nullptr, *whh_l = nullptr;   // permuted weight planes [3H, K]
     const float* bias4 = nullptr;              // [4][H] b_r, b_z, b_in, b_hn (tc_gru_prepare_bias)
     const float* g1 = nullptr;                 // [V, 3H] per-token input pre-activations (Kx == 0)
-    const int64_t* tokens = nullptr;
+    const int64_t* tokens = nullptr;           // nullptr with g1: table row = row index
     int64_t V = 0;
     const float* h_prev = nullptr;             // [rows, H] fp32
     float* h_out = nullptr;                    // [rows, H] fp32 (must not alias h_prev)
     SplitDst out;                              // operand planes of h'
     int rows = 0, H = 0;
+    float* y2 = nullptr;                       // optional second fp32 copy of h' (the encoder's context slab), row pitch ld_y2
+    int64_t ld_y2 = 0;
 };
 bool tc_gru_supported(int rows, int H, int Kx, int Kh);
 int tc_gru(const GruCall& c, cudaStream_t st);

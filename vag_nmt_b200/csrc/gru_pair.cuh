@@ -57,7 +57,7 @@ __device__ __forceinline__ void stg256_b32(void* p, const uint32_t* v) {
 struct GruArgs {
     const float* bias;        // [4][H]: b_r, b_z, b_in, b_hn (unit-major; made by gru_bias_kernel)
     const float* g1;          // optional per-token table [V, 3H] (gate-major r | z | n, b_ih included): replaces phase X
-    const int64_t* tokens;    // [rows] row → table row (out of range → 0, like the embedding)
+    const int64_t* tokens;    // [rows] row → table row (out of range → 0, like the embedding); nullptr: table row = row
     int64_t V;
     const float* h_prev;      // [rows, H] fp32
     float* h_out;             // [rows, H] fp32
@@ -66,6 +66,8 @@ struct GruArgs {
     int64_t out_ld;
     int rows, Kx, Kh, H;
     const int* done;
+    float* y2;                // optional second fp32 copy of h' (row pitch ld_y2): the encoder's context slab
+    int64_t ld_y2;
     int wide;                 // every row base above is 32-byte aligned: 256-bit epilogue accesses (set by the launcher)
 };
 
@@ -240,7 +242,7 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         // the token of a row is the head of the epilogue's dependency chain (token → table row → loads): fetched one tile ahead
         auto token_of = [&](int tile) -> int64_t {
             const int r = (tile / tiles_n) * BMP + (int)rank * BM + lg * 32 + lane;
-            return (table && tile < n_tiles && r < rows) ? args.tokens[r] : 0;
+            return (table && tile < n_tiles && r < rows) ? (args.tokens ? args.tokens[r] : (int64_t)r) : 0;
         };
         int64_t id_next = token_of(pair);
         for (int tile = pair; tile < n_tiles; tile += n_pairs, ++it) {
@@ -349,6 +351,14 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
                     split_one(MODE, out[2 * u + 1], h1, l1);
                     hw[u] = (uint32_t)h0 | ((uint32_t)h1 << 16);
                     lw[u] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                }
+                if (live && args.y2) {
+                    float* y2 = args.y2 + (int64_t)row * args.ld_y2 + u0;
+                    if (wide) stg256(y2, out);
+                    else {
+                        *reinterpret_cast<float4*>(y2) = *reinterpret_cast<float4*>(out);
+                        *reinterpret_cast<float4*>(y2 + 4) = *reinterpret_cast<float4*>(out + 4);
+                    }
                 }
                 if (live && wide && NP == 2) {
                     stg256(args.h_out + (int64_t)row * H + u0, out);

@@ -1590,7 +1590,8 @@ bool tc_gru_supported(int rows, int H, int Kx, int Kh) {
 int tc_gru(const GruCall& c, cudaStream_t st) {
     const int mode = gemm_mode();
     if (!tc_gru_supported(c.rows, c.H, c.Kx, c.Kh) || !c.out.hi || (c.out.ld & 7) || (reinterpret_cast<uintptr_t>(c.out.hi) & 15) ||
-        (mode == 1 && (!c.out.lo || (reinterpret_cast<uintptr_t>(c.out.lo) & 15))) || (c.Kx == 0) != (c.g1 != nullptr)) {
+        (mode == 1 && (!c.out.lo || (reinterpret_cast<uintptr_t>(c.out.lo) & 15))) || (c.Kx == 0) != (c.g1 != nullptr) ||
+        (c.y2 && ((reinterpret_cast<uintptr_t>(c.y2) & 15) || (c.ld_y2 & 3)))) {
         set_error("tc_gru: unsupported shape / mode / output planes");
         return VAG_ERR_UNSUPPORTED;
     }
@@ -1609,11 +1610,12 @@ int tc_gru(const GruCall& c, cudaStream_t st) {
     }
     GruArgs a;
     a.bias = c.bias4; a.g1 = c.g1; a.tokens = c.tokens; a.V = c.V; a.h_prev = c.h_prev; a.h_out = c.h_out;
-    a.out_hi = c.out.hi; a.out_lo = c.out.lo; a.out_ld = c.out.ld; a.rows = c.rows; a.Kx = c.Kx; a.Kh = c.Kh; a.H = c.H; a.done = g_tc_done;
+    a.out_hi = c.out.hi; a.out_lo = c.out.lo; a.out_ld = c.out.ld; a.rows = c.rows; a.Kx = c.Kx; a.Kh = c.Kh; a.H = c.H; a.done = g_tc_done; a.y2 = c.y2; a.ld_y2 = c.ld_y2;
     static const bool wide_off = getenv("VAG_GRU_WIDE") && getenv("VAG_GRU_WIDE")[0] == '0';   // A/B runs: 128-bit epilogue accesses
     const uintptr_t al = reinterpret_cast<uintptr_t>(c.h_prev) | reinterpret_cast<uintptr_t>(c.h_out) | reinterpret_cast<uintptr_t>(c.g1) |
-                         reinterpret_cast<uintptr_t>(c.out.hi) | (mode == 1 ? reinterpret_cast<uintptr_t>(c.out.lo) : 0);
-    a.wide = (!wide_off && (al & 31) == 0 && (c.out.ld & 15) == 0) ? 1 : 0;
+                         reinterpret_cast<uintptr_t>(c.out.hi) | (mode == 1 ? reinterpret_cast<uintptr_t>(c.out.lo) : 0) |
+                         reinterpret_cast<uintptr_t>(c.y2);
+    a.wide = (!wide_off && (al & 31) == 0 && (c.out.ld & 15) == 0 && (c.ld_y2 & 7) == 0) ? 1 : 0;
     const int n_tiles = (c.H / 32) * ceil_div(c.rows, 256);
     const int max_pairs = num_sms() / 2;
     const int grid = 2 * (n_tiles < max_pairs ? n_tiles : max_pairs);
