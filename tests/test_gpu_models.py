@@ -180,10 +180,10 @@ def test_fresh_seeds_against_oracle():
                 O.multimodal_beamsearch_decode(p, src, lens, im_s, K, 15)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_encoder_fused_cell_path_ragged_batch(precision):
-    """More than 128 active rows: the encoder runs a GRU step as ONE launch (cell fused into the hidden contraction, two state
-    buffers); the ragged batch crosses the 128-row boundary in both directions (forward: fused steps, then the three-kernel
+@pytest.mark.parametrize("precision,n_sent", [("fp32", 300), ("bf16", 300), ("fp32", 100)])
+def test_encoder_fused_cell_path_ragged_batch(precision, n_sent):
+    """More than 32 active rows: the encoder runs a GRU step as ONE launch (cell fused into the hidden contraction, two state
+    buffers); the ragged batch crosses the 32-row boundary in both directions (forward: fused steps, then the three-kernel
     steps on the current buffer; backward: the reverse, with sentences joining at their last token on a zero state).
     Against the CPU oracle of Encoder.py:36-65: values, exact zeros at the padded positions, mask."""
     from oracle import vag_oracle as O
@@ -192,9 +192,9 @@ def test_encoder_fused_cell_path_ragged_batch(precision):
     from vag_nmt_b200 import _cabi
     mm = build_mm(cfg, 3).cuda()
     p = cpu_params(mm)
-    lens = sorted([2 + (7 * i) % 23 for i in range(300)], reverse=True)       # 300 sentences, 2..24 tokens: 300 rows active at t = 0,
-    g = torch.Generator().manual_seed(5)                                      # fewer than 128 from t = 14 on
-    src = torch.zeros(300, lens[0], dtype=torch.int64)
+    lens = sorted([2 + (7 * i) % 23 for i in range(n_sent)], reverse=True)    # 2..24 tokens: every row active at t = 0, fewer than
+    g = torch.Generator().manual_seed(5)                                      # 128 / 32 rows towards the end (three-kernel steps)
+    src = torch.zeros(n_sent, lens[0], dtype=torch.int64)
     for b, n in enumerate(lens):
         src[b, :n] = torch.randint(4, cfg["src_size"], (n,), generator=g)
     with _cabi.precision_scope(precision):
@@ -208,7 +208,7 @@ def test_encoder_fused_cell_path_ragged_batch(precision):
     assert torch.equal(mask.cpu(), want_mask)
     got = ctx.cpu()
     assert rel_err(got, want) < (2e-5 if precision == "fp32" else 2e-3)
-    for b in (0, 57, 150, 299):
+    for b in (0, 57, n_sent // 2, n_sent - 1):
         assert got[lens[b]:, b].abs().sum().item() == 0.0                     # pad_packed_sequence: exact zeros
 
 

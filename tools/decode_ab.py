@@ -35,7 +35,7 @@ def worker(n, L, prec, reps):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize()
             e0.record()
-            hyp, hyp_len = ops.beam_decode(w, h0, keys, ctx, mask, 12, L, early_stop=False)
+            hyp, hyp_len = ops.beam_decode(w, h0, keys, ctx, mask, 12, L, early_stop=os.environ.get("AB_EARLY_STOP") == "1")
             e1.record()
             torch.cuda.synchronize()
             if i >= 2:

@@ -1582,10 +1582,12 @@ int tc_gemm_top2(float4* summ, const void* xh, const void* xl, int64_t ldxs, con
     return VAG_OK;
 }
 
-// GRU cell fused into its contractions (gru_pair.cuh).  16-bit modes, rows > 128, H % 32 == 0, K % 8 == 0.
+// GRU cell fused into its contractions (gru_pair.cuh).  16-bit modes, rows > 32 (up to 32 rows the latency-shaped linear_rows32
+// kernels are faster; between 33 and 128 rows the peer CTA of a pair works on zero-filled rows, still one launch instead of
+// three), H % 32 == 0, K % 8 == 0.
 bool tc_gru_supported(int rows, int H, int Kx, int Kh) {
     const int mode = gemm_mode();
-    return (mode == 1 || mode == 2) && rows > 128 && H % 32 == 0 && H <= G_BIAS_MAX_H && Kh >= 32 && Kh % 8 == 0 && (Kx == 0 || (Kx >= 32 && Kx % 8 == 0));
+    return (mode == 1 || mode == 2) && rows > 32 && H % 32 == 0 && H <= G_BIAS_MAX_H && Kh >= 32 && Kh % 8 == 0 && (Kx == 0 || (Kx >= 32 && Kx % 8 == 0));
 }
 int tc_gru(const GruCall& c, cudaStream_t st) {
     const int mode = gemm_mode();
