@@ -87,3 +87,33 @@ def test_vocab_top2_summaries_match_fp64(rows, K, N):
     m = summ[..., 0].max(1).values
     lse = m + torch.log((summ[..., 1] * torch.exp(summ[..., 0] - m[:, None])).sum(1))
     assert float((lse.double() - torch.logsumexp(ref, 1)).abs().max()) < tol
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_vocab_top2_summaries_tie_order_is_canonical(precision):
+    """Exact ties: small-integer operands make every logit an exactly representable integer whatever the accumulation order, so
+    most 32-column slices hold several equal maxima.  The summary must name the best two in CANONICAL order — value descending,
+    column ascending — i.e. the first two entries of a stable descending sort.  (The first epilogue of this kernel broke a tie for
+    the runner-up by insertion history: correct values, but the higher of two equal columns when the slice's best came later in the
+    same insertion chain; found with a CPU cross-check against a brute-force top-2.)"""
+    from vag_nmt_b200 import _cabi, ops
+    rows, K, N = 700, 64, 1000                                   # ragged last slice: 1000 = 31 x 32 + 8
+    g = torch.Generator(device="cuda").manual_seed(17)
+    x = torch.randint(-2, 3, (rows, K), device="cuda", generator=g).float()
+    w = torch.randint(-1, 2, (N, K), device="cuda", generator=g).float()
+    b = torch.randint(-3, 4, (N,), device="cuda", generator=g).float()
+    with _cabi.precision_scope(precision):
+        summ = ops.tc_gemm_top2(ops.tc_split(x), ops.tc_split(w), rows, K, N, b).permute(1, 0, 2).contiguous()   # [rows, slices, 4]
+    ref = x @ w.t() + b                                           # exact integers
+    slices = (N + 31) // 32
+    pad = torch.full((rows, slices * 32 - N), -float("inf"), device="cuda")
+    rt = torch.cat([ref, pad], 1).view(rows, slices, 32)
+    order = torch.sort(rt, dim=2, descending=True, stable=True)   # equal values keep ascending column order
+    base = (torch.arange(slices, device="cuda") * 32).view(1, slices)
+    bits = summ[..., 3].contiguous().view(torch.int32)
+    i1, i2 = (bits & 0xFFFF).long(), ((bits >> 16) & 0xFFFF).long()
+    assert torch.equal(summ[..., 0], order.values[..., 0]) and torch.equal(summ[..., 2], order.values[..., 1])
+    assert torch.equal(i1, order.indices[..., 0] + base)
+    assert torch.equal(i2, order.indices[..., 1] + base)
+    ties = (order.values[..., 0] == order.values[..., 1]).float().mean().item()
+    assert ties > 0.05, ties                                      # the case really is about ties (one slice in ten)

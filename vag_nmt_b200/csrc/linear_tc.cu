@@ -1235,38 +1235,60 @@ vocab_top2_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_
 #pragma unroll
                     for (int j = 0; j < 32; ++j) x[j] = j < n_valid ? x[j] : -INFINITY;
                 }
-                // best two of the chunk: four independent insertion chains (j mod 4) merged at the end; compares are strict,
-                // so inside a chain the lower column wins ties; the merges order equal values by column explicitly
-                float c1[4], c2[4];
-                int k1[4], k2[4];
+                // Best two of the chunk in canonical order (value descending, column ascending), two levels — the flat version (four
+                // insertion chains of 8 ALU-pipe instructions per element + three merges, ~300 per chunk) made the ALU pipe the limit of
+                // this kernel in bf16 mode (63 % busy at the FP32 mode's tensor-bound pace):
+                //   level 1: best (value, column) of each 8-column group            — 3 instructions per element, strict >: lowest column wins
+                //   level 2: best of the four group winners                        — the chunk's best
+                //   runner-up = best of { the other three group winners, the best of the winner's group WITHOUT the winner } — only the
+                //   winner's group is scanned a second time (selected out of the register array with three predicated moves per element)
+                float gb[4];
+                int gi[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { c1[u] = -INFINITY; c2[u] = -INFINITY; k1[u] = 0xFFFF; k2[u] = 0xFFFF; }
+                for (int g = 0; g < 4; ++g) {
+                    float bv = x[8 * g];
+                    int bi = 8 * g;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {   // values through min/max (no predicates), columns through two selects each
-                    const int u = j & 3;
-                    const float xv = x[j];
-                    const bool g1 = xv > c1[u];
-                    const float loser = fminf(c1[u], xv);          // the one of (old best, new) that is not the new best
-                    const int kl = g1 ? k1[u] : j;
-                    c1[u] = fmaxf(c1[u], xv);
-                    k1[u] = g1 ? j : k1[u];
-                    const bool g2 = loser > c2[u];
-                    c2[u] = fmaxf(c2[u], loser);
-                    k2[u] = g2 ? kl : k2[u];
+                    for (int t = 1; t < 8; ++t) {
+                        const float xv = x[8 * g + t];
+                        const bool gt = xv > bv;
+                        bv = fmaxf(bv, xv);
+                        bi = gt ? 8 * g + t : bi;
+                    }
+                    gb[g] = bv;
+                    gi[g] = bi;
                 }
-                auto better = [](float av, int ai, float bv, int bi) { return av > bv || (av == bv && ai < bi); };
-                auto merge2 = [&](float& p1, int& i1, float& p2, int& i2, float q1, int j1_, float q2, int j2_) {
-                    const bool qf = better(q1, j1_, p1, i1);
-                    const float r1 = qf ? q1 : p1; const int ri1 = qf ? j1_ : i1;
-                    const float s1 = qf ? p1 : p2; const int si1 = qf ? i1 : i2;     // runner-up candidates: the loser's head ...
-                    const float s2 = qf ? q2 : q1; const int si2 = qf ? j2_ : j1_;   // ... and the winner's next
-                    const bool sf = better(s2, si2, s1, si1);
-                    p1 = r1; i1 = ri1;
-                    p2 = sf ? s2 : s1; i2 = sf ? si2 : si1;
-                };
-                merge2(c1[0], k1[0], c2[0], k2[0], c1[1], k1[1], c2[1], k2[1]);
-                merge2(c1[2], k1[2], c2[2], k2[2], c1[3], k1[3], c2[3], k2[3]);
-                merge2(c1[0], k1[0], c2[0], k2[0], c1[2], k1[2], c2[2], k2[2]);
+                float c1v = gb[0];
+                int k1v = gi[0];
+#pragma unroll
+                for (int g = 1; g < 4; ++g) {
+                    const bool gt = gb[g] > c1v;
+                    c1v = fmaxf(c1v, gb[g]);
+                    k1v = gt ? gi[g] : k1v;
+                }
+                const int wg = k1v >> 3, wt = k1v & 7;                    // the winner's group and its place in it
+                float sv = -INFINITY;
+                int st_ = 0;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const float xs = wg == 0 ? x[t] : (wg == 1 ? x[8 + t] : (wg == 2 ? x[16 + t] : x[24 + t]));
+                    const float xv = t == wt ? -INFINITY : xs;
+                    const bool gt = xv > sv;
+                    sv = fmaxf(sv, xv);
+                    st_ = gt ? t : st_;
+                }
+                float c2v = -INFINITY;
+                int k2v = 0xFFFF;                                         // stays "none" when nothing but -inf is left (single-column chunk)
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {                             // candidates in ascending column order: strict > keeps the lowest column
+                    const float cv = g == wg ? sv : gb[g];
+                    const int ci = g == wg ? 8 * g + st_ : gi[g];
+                    const bool gt = cv > c2v;
+                    c2v = fmaxf(c2v, cv);
+                    k2v = gt ? ci : k2v;
+                }
+                float c1[1] = {c1v}, c2[1] = {c2v};
+                int k1[1] = {c1v == -INFINITY ? 0xFFFF : k1v}, k2[1] = {k2v};
                 const float m2 = c1[0] * kL2e;
                 float ps[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
