@@ -1269,9 +1269,14 @@ vocab_top2_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_
                 const int wg = k1v >> 3, wt = k1v & 7;                    // the winner's group and its place in it
                 float sv = -INFINITY;
                 int st_ = 0;
+                // the winner's group out of the register array: bit selects with two lane masks (one LOP3 each) — written as a
+                // conditional expression the compiler emitted a four-way divergent branch here (ncu: 18 % of the kernel's
+                // instructions, 31 % of its stall samples)
+                const uint32_t gm1 = (wg & 1) ? 0xFFFFFFFFu : 0u, gm2 = (wg & 2) ? 0xFFFFFFFFu : 0u;
+                auto bitsel = [](uint32_t m, float a, float b) { return __uint_as_float((__float_as_uint(a) & m) | (__float_as_uint(b) & ~m)); };
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
-                    const float xs = wg == 0 ? x[t] : (wg == 1 ? x[8 + t] : (wg == 2 ? x[16 + t] : x[24 + t]));
+                    const float xs = bitsel(gm2, bitsel(gm1, x[24 + t], x[16 + t]), bitsel(gm1, x[8 + t], x[t]));
                     const float xv = t == wt ? -INFINITY : xs;
                     const bool gt = xv > sv;
                     sv = fmaxf(sv, xv);
