@@ -180,3 +180,45 @@ def test_pipelined_eval_batches_and_in_call_lanes_give_the_sequential_tokens(mon
     tm = build_tm(cfg, 77).cuda().eval()
     fn_t = lambda s, l, i, K, L: tm.beamsearch_decode(s, l, beam_size=K, max_length=L)
     assert decode_corpus_pipelined(tm, sents, None, 12, 14, 16, lanes=4) == decode_corpus(fn_t, sents, None, 12, 14, batch_size=16)
+
+
+_SWITCH_SCRIPT = r"""
+import json, sys, torch
+sys.path.insert(0, {root!r})
+sys.path.insert(0, {tests!r})
+from conftest import build_mm
+from vag_nmt_b200 import synthetic
+cfg = dict(synthetic.DE)
+model = build_mm(cfg, 1234).cuda().eval()
+sents, im = synthetic.make_corpus(160, cfg["src_size"], cfg["im_feats_size"], seed=31)
+src, lens, im_s, _ = synthetic.pad_and_sort(sents, im)
+out = model.beamsearch_decode(src, lens, im_s, beam_size=12, max_length=10)
+out2 = model.beamsearch_decode(src, lens, im_s, beam_size=12, max_length=10)     # second call: graph replay where a switch enables it
+assert out == out2
+print("TOKENS" + json.dumps(out))
+"""
+
+
+def test_opt_in_kernel_variants_keep_the_tokens():
+    """The variants that are kept behind switches read once per process — the reorder as the tail of the selection kernel
+    (VAG_SEL_ADVANCE=1), sixteen single-pass epilogue warps in the fused GRU kernel (VAG_GRU_EW=16), whole-loop graph replay for
+    large batches (VAG_DECODE_GRAPH_ROWS), the three-kernel encoder steps (VAG_ENC_FUSED=0), 128-bit GRU epilogue accesses
+    (VAG_GRU_WIDE=0) — must translate exactly like the default build: one fresh process with all of them set, 160 sentences x beam 12
+    (1920 rows: the tensor-core step with every fused kernel), against this process's default decode."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+    from vag_nmt_b200 import synthetic
+    cfg = dict(synthetic.DE)
+    model = build_mm(cfg, 1234).cuda().eval()
+    sents, im = synthetic.make_corpus(160, cfg["src_size"], cfg["im_feats_size"], seed=31)
+    src, lens, im_s, _ = synthetic.pad_and_sort(sents, im)
+    want = model.beamsearch_decode(src, lens, im_s, beam_size=12, max_length=10)
+    root = Path(__file__).resolve().parent.parent
+    env = dict(os.environ, VAG_SEL_ADVANCE="1", VAG_GRU_EW="16", VAG_DECODE_GRAPH_ROWS="100000", VAG_ENC_FUSED="0", VAG_GRU_WIDE="0")
+    res = subprocess.run([sys.executable, "-c", _SWITCH_SCRIPT.format(root=str(root), tests=str(root / "tests"))], env=env,
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = [ln for ln in res.stdout.splitlines() if ln.startswith("TOKENS")][-1]
+    assert json.loads(line[len("TOKENS"):]) == want
