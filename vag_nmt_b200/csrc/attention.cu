@@ -266,7 +266,8 @@ int attn_exp_keys(float* ekeys, int* kflag, const float* keys, int B, int T, int
 // Tuned variant for C % 4 == 0 (every real configuration): rows-per-CTA is a template parameter so that the
 // accumulator arrays are exactly as large as the beam, a warp loads a whole key row (up to 1024 channels) with
 // independent 128-bit loads BEFORE the SFU-heavy row loop (memory-level parallelism), and the context phase
-// streams ctx with four positions in flight.  MLP-mode cost is 1.25 SFU ops per (row, position, channel).
+// streams ctx with four positions in flight.  MLP-mode cost is 1.25 SFU ops per (row, position, channel) in the single-exponential
+// form, 0.25 in the factored form the beam loop uses (exp(2·keys) precomputed per call, exp(2q) per staged row).
 // ---------------------------------------------------------------------------------------------------------
 // FULLC: C is a multiple of 1024, so the per-chunk bounds checks (and the branches that fence the SFU chains apart)
 // disappear from the inner loops.

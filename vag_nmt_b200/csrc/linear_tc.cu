@@ -999,8 +999,8 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
 //     (best logit, Σ exp(logit − best), second-best logit, best column | second column << 16)       [canonical order]
 // written to summ[slice][row] (slice = 32-column chunk of the vocabulary, row fastest ⇒ coalesced 512-byte stores).
 // beam_select_top2_kernel picks the K winners from these 294 x 16 B per row instead of 9391 x 4 B of logits.
-// Why 16 warps: with K = 256 the three-product main loop lasts only ≈ 3 k cycles per tile, and the reduction (≈ 17
-// instructions per element, serial insertion chains) is latency-bound with two warps per scheduler; four per scheduler
+// Why 16 warps: with K = 256 the three-product main loop lasts only ≈ 3 k cycles per tile, and the reduction (≈ 12
+// instructions per element: two-level top-2 + Σexp) is latency-bound with two warps per scheduler; four per scheduler
 // hide it.  No staging tiles ⇒ room for a fourth pipeline stage.
 constexpr int V_STAGES = 4;
 constexpr int V_SMEM_BYTES = V_STAGES * Q_STAGE_BYTES + 2048 /*bias per warp*/ + 256 /*barriers*/ + 1024;   // stationary mode: 64 KB resident weights + 4 x 32 KB
