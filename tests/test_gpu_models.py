@@ -212,6 +212,22 @@ def test_encoder_fused_cell_path_ragged_batch(precision, n_sent):
         assert got[lens[b]:, b].abs().sum().item() == 0.0                     # pad_packed_sequence: exact zeros
 
 
+def test_decode_160_sentences_token_exact_vs_oracle():
+    """1920 rows at full Multi30K shapes: the encoder's fused-cell steps (more than 32 active rows), the tensor-core decoder step with
+    every fused kernel, 6-row attention CTAs, the summary-based selection — token for token against the CPU oracle (beam 12, 10
+    steps), multimodal and text-only."""
+    from oracle import vag_oracle as O
+    from vag_nmt_b200 import synthetic
+    cfg = dict(synthetic.DE)
+    sents, im = synthetic.make_corpus(160, cfg["src_size"], cfg["im_feats_size"], seed=41)
+    src, lens, im_s, _ = synthetic.pad_and_sort(sents, im)
+    mm = build_mm(cfg, 77).cuda().eval()
+    assert mm.beamsearch_decode(src, lens, im_s, beam_size=12, max_length=10) == \
+        O.multimodal_beamsearch_decode(cpu_params(mm), src, lens, im_s, 12, 10)
+    tm = build_tm(cfg, 78).cuda().eval()
+    assert tm.beamsearch_decode(src, lens, beam_size=12, max_length=10) == O.text_beamsearch_decode(cpu_params(tm), src, lens, 12, 10)
+
+
 def test_error_behaviour():
     import vag_nmt_b200 as vag
     from vag_nmt_b200 import synthetic
