@@ -318,6 +318,17 @@ int vag_beam_decode_f32(const vag_decoder_weights* w, const float* h0, const flo
                         int32_t* hyp_len, int64_t* beam_out, float* nll_out, int32_t* steps_out,
                         volatile int32_t* host_progress, void* workspace, size_t workspace_bytes, vag_stream_t stream);
 
+/* Steps [step_begin, step_end) of the same search (V11:255-313), on the state a previous range left in `workspace` (same buffer, same
+ * shape arguments): step_begin == 0 initialises it, step_end >= L appends the epilogue and writes the outputs
+ * (step_begin == step_end == L: the epilogue alone).  done_host (optional): one int32 of PINNED host memory that receives the `done`
+ * flag as it stands after the range, asynchronously and in stream order.  No host polling inside the call, so every range can be
+ * captured in a CUDA graph: a caller replays chunk graphs one ahead of an event and stops launching once `done` has arrived — the
+ * reference's per-step `fini_idxs` test (V11:265-269) at chunk granularity. */
+int vag_beam_decode_steps_f32(const vag_decoder_weights* w, const float* h0, const float* keys, const float* ctx,
+                              const float* mask, int B, int K, int T, int L, int avoid_double, int step_begin, int step_end,
+                              int64_t* hyp_out, int32_t* hyp_len, int64_t* beam_out, float* nll_out, int32_t* steps_out,
+                              int32_t* done_host, void* workspace, size_t workspace_bytes, vag_stream_t stream);
+
 /* The epilogue of the search alone (V11:315-337), for callers that drive the steps themselves (vag_decoder_step_f32 +
  * vag_beam_select_f32): tok_hist int64 / par_hist int32 [L, B, K] = token and parent-beam index chosen at every step,
  * nll [B, K], steps_run int32[1] ON THE DEVICE (rows >= steps_run count as 0; the last row is forced to <eos>, :315).

@@ -1,5 +1,5 @@
-"""Stream-enqueued (polled) decode loop against whole-loop CUDA-graph replay at several batch sizes:
-python tools/graph_rows_ab.py [fp32|bf16] 125 250 500 1000"""
+"""Stream-enqueued (polled) decode loop against CUDA-graph replay (chunks of steps, VAG_DECODE_CHUNK; 0 = the whole loop as one
+graph) at several batch sizes:  python tools/graph_rows_ab.py [fp32|bf16] 125 250 500 1000"""
 import sys
 from pathlib import Path
 

@@ -109,6 +109,7 @@ SIGNATURES = {
     "vag_beam_select_f32": (I, [P, I64, P, P, P, P, I, I, I64, I, I, P]),
     "vag_beam_decode_workspace_bytes": (SZ, [I, I, I, I, I, I, I, I64]),
     "vag_beam_decode_f32": (I, [P, P, P, P, P, I, I, I, I, I, P, P, P, P, P, P, P, SZ, P]),
+    "vag_beam_decode_steps_f32": (I, [P, P, P, P, P, I, I, I, I, I, I, I, P, P, P, P, P, P, P, SZ, P]),
     "vag_beam_finalize_f32": (I, [P, P, P, P, I, I, I, P, P, P, P]),
     "vag_decoder_prepared_bytes": (SZ, [I, I, I, I64]),
     "vag_decoder_prepare_f32": (I, [P, P, SZ, P]),

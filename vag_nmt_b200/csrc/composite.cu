@@ -772,10 +772,14 @@ static inline int progress_nonce() {
     return (int)n;
 }
 
-extern "C" int vag_beam_decode_f32(const vag_decoder_weights* w, const float* h0, const float* keys, const float* ctx,
-                                   const float* mask, int B, int K, int T, int L, int avoid_double, int64_t* hyp_out,
-                                   int32_t* hyp_len, int64_t* beam_out, float* nll_out, int32_t* steps_out,
-                                   volatile int32_t* host_progress, void* workspace, size_t workspace_bytes, vag_stream_t stream) {
+// Steps [step_begin, step_end) of the search on the state the workspace holds; step_begin == 0 initialises that state, step_end >= L
+// appends the epilogue.  vag_beam_decode_f32 is the range [0, L); vag_beam_decode_steps_f32 exposes the ranges so that a caller can
+// capture the loop as a few CUDA graphs (one per chunk of steps) and look at `done` between chunks.
+static int beam_decode_range(const vag_decoder_weights* w, const float* h0, const float* keys, const float* ctx,
+                             const float* mask, int B, int K, int T, int L, int avoid_double, int step_begin, int step_end,
+                             int64_t* hyp_out, int32_t* hyp_len, int64_t* beam_out, float* nll_out, int32_t* steps_out,
+                             volatile int32_t* host_progress, int32_t* done_host, void* workspace, size_t workspace_bytes,
+                             vag_stream_t stream) {
     ModeScope ms(w ? w->precision : VAG_PREC_FP32);
     VAG_REQUIRE(w && h0 && keys && ctx && mask && hyp_out && hyp_len, "vag_beam_decode_f32: null pointer");
     VAG_REQUIRE(B > 0 && K > 1 && T > 0 && L > 0 && L < 32768, "vag_beam_decode_f32: bad shape B=%d K=%d T=%d L=%d", B, K, T, L);
@@ -794,9 +798,12 @@ extern "C" int vag_beam_decode_f32(const vag_decoder_weights* w, const float* h0
     int* done = ws.flags;
     int* steps_run = ws.flags + 1;
     int* fin = ws.flags + 2;
-    VAG_CUDA(cudaMemsetAsync(ws.flags, 0, sizeof(int) * (2 * (size_t)L + 2), st));
-    fill_i64_kernel<<<ceil_div(B, 256), 256, 0, st>>>(ws.sos, 2 /*SOS*/, B);
-    VAG_LAUNCH_CHECK();
+    const bool first = step_begin == 0, last = step_end >= L;
+    if (first) {
+        VAG_CUDA(cudaMemsetAsync(ws.flags, 0, sizeof(int) * (2 * (size_t)L + 2), st));
+        fill_i64_kernel<<<ceil_div(B, 256), 256, 0, st>>>(ws.sos, 2 /*SOS*/, B);
+        VAG_LAUNCH_CHECK();
+    }
     const int64_t ldl = (V + 3) / 4 * 4;
     GemmCtx gemm(st, ws.step.wreg, ws.step.wbytes, ws.step.areg, ws.step.abytes);
     Prepared pr;
@@ -808,7 +815,7 @@ extern "C" int vag_beam_decode_f32(const vag_decoder_weights* w, const float* h0
         VAG_TRY(fused_setup(w, ws.step, N, K, pr, &fused));
         fused.done = done;
         if (fused.ok && (C % 4 == 0) && !getenv("VAG_ATTN_SINGLE_EXP")) {   // factored attention scores: exp(2·keys) once per call
-            VAG_TRY(attn_exp_keys(ws.ekeys, ws.kflag, keys, B, T, C, st));
+            if (first) VAG_TRY(attn_exp_keys(ws.ekeys, ws.kflag, keys, B, T, C, st));
             fused.ekeys = ws.ekeys;
             fused.kflag = ws.kflag;
         }
@@ -819,7 +826,7 @@ extern "C" int vag_beam_decode_f32(const vag_decoder_weights* w, const float* h0
     // 49.2 vs 48.9; 16 sentences 9.85 vs 9.76 ms) — a sentence's 84 KB of copies serialise behind its own pops.
     static const bool sel_advance = getenv("VAG_SEL_ADVANCE") && getenv("VAG_SEL_ADVANCE")[0] == '1';
     constexpr int kLookahead = 4;     // steps the host may enqueue ahead of the device when it polls host_progress
-    for (int di = 0; di < L; ++di) {
+    for (int di = step_begin; di < (last ? L : step_end); ++di) {
         if (host_progress && di > kLookahead) {
             // The reference tests `n_fini == B·K` on the host after EVERY step (V11:265-269).  Here the device publishes its
             // progress in mapped host memory and the host only stays kLookahead steps ahead: when `done` appears it stops
@@ -892,10 +899,35 @@ extern "C" int vag_beam_decode_f32(const vag_decoder_weights* w, const float* h0
             VAG_TRY(beam_advance(ws.h_a, ws.h_b, ws.par_hist + (size_t)di * N, B, K, rps, H, di, done, fin + di, steps_run, st,
                                  host_progress, nonce));
     }
+    if (done_host) VAG_CUDA(cudaMemcpyAsync(done_host, done, sizeof(int), cudaMemcpyDeviceToHost, st));   // pinned host word: `done` after this range
+    if (!last) return VAG_OK;
     VAG_TRY(beam_finalize(ws.tok_hist, ws.par_hist, ws.nll, steps_run, B, K, L, hyp_out, hyp_len, beam_out, st));
     if (nll_out) VAG_CUDA(cudaMemcpyAsync(nll_out, ws.nll, sizeof(float) * (size_t)N, cudaMemcpyDeviceToDevice, st));
     if (steps_out) VAG_CUDA(cudaMemcpyAsync(steps_out, steps_run, sizeof(int), cudaMemcpyDeviceToDevice, st));
     return VAG_OK;
+}
+
+extern "C" int vag_beam_decode_f32(const vag_decoder_weights* w, const float* h0, const float* keys, const float* ctx,
+                                   const float* mask, int B, int K, int T, int L, int avoid_double, int64_t* hyp_out,
+                                   int32_t* hyp_len, int64_t* beam_out, float* nll_out, int32_t* steps_out,
+                                   volatile int32_t* host_progress, void* workspace, size_t workspace_bytes, vag_stream_t stream) {
+    return beam_decode_range(w, h0, keys, ctx, mask, B, K, T, L, avoid_double, 0, L, hyp_out, hyp_len, beam_out, nll_out, steps_out,
+                             host_progress, nullptr, workspace, workspace_bytes, stream);
+}
+
+/* Steps [step_begin, step_end) of the same search, on the state a previous range left in `workspace` (same buffer, same shape
+ * arguments): step_begin == 0 initialises it, step_end >= L appends the epilogue and writes the outputs (step_begin == step_end == L:
+ * the epilogue alone).  done_host (optional): one int32 of PINNED host memory that receives the `done` flag as it stands after the
+ * range — asynchronously, in stream order.  No host polling inside: every range can be captured in a CUDA graph, and a caller that
+ * replays chunk graphs one ahead of an event can stop launching once `done` arrives (V11:265-269). */
+extern "C" int vag_beam_decode_steps_f32(const vag_decoder_weights* w, const float* h0, const float* keys, const float* ctx,
+                                         const float* mask, int B, int K, int T, int L, int avoid_double, int step_begin, int step_end,
+                                         int64_t* hyp_out, int32_t* hyp_len, int64_t* beam_out, float* nll_out, int32_t* steps_out,
+                                         int32_t* done_host, void* workspace, size_t workspace_bytes, vag_stream_t stream) {
+    VAG_REQUIRE(step_begin >= 0 && step_begin <= step_end && step_begin <= L, "vag_beam_decode_steps_f32: bad step range [%d, %d) of %d",
+                step_begin, step_end, L);
+    return beam_decode_range(w, h0, keys, ctx, mask, B, K, T, L, avoid_double, step_begin, step_end, hyp_out, hyp_len, beam_out, nll_out,
+                             steps_out, nullptr, done_host, workspace, workspace_bytes, stream);
 }
 
 /* The epilogue of the search alone (V11:315-337) for callers that drive the steps themselves with vag_decoder_step_f32 +

@@ -112,29 +112,49 @@ class _Seq2SeqBase(nn.Module):
         lens = hyp_len.cpu().tolist()
         return [rows[b, :lens[b]].tolist() for b in range(rows.shape[0])]
 
-    # Small batches (the reference decodes in eval batches of 16, nmt_multimodal_beam_DE.py:542-547): 12 launches of a few µs per
-    # step are bound by launch latency, so the whole L-step loop of one (B, T, K, L) shape is captured in a CUDA graph once
-    # and replayed.  A captured loop cannot poll the host; its early stop is the kernels' own `done` test.
-    _GRAPH_ROWS_MAX = 2048
+    # The L-step loop of one (B, T, K, L) shape is captured in CUDA graphs once and replayed: a replayed loop loses ≈ 10 µs less per
+    # step between its dependent launches than an enqueued one (tools/graph_rows_ab.py: 125 / 250 / 1000 sentences 13.6 → 12.5,
+    # 18.3 → 17.5, 47.5 → 47.0 ms), and at the reference's eval batch of 16 (nmt_multimodal_beam_DE.py:542-547) the host could not even
+    # enqueue 12 launches per step fast enough.  A captured loop cannot poll the host, so it is captured in CHUNKS of
+    # `_GRAPH_CHUNK` steps (vag_beam_decode_steps_f32): every chunk ends with an asynchronous copy of the device's `done` flag into
+    # pinned host memory, the host replays chunk c + 1, waits for the event behind chunk c − 1 and stops replaying when that chunk
+    # reported `done` — the reference's per-step test (V11:265-269) at chunk granularity, at most two chunks of returned-at-once
+    # kernels after the search has ended.  Inside a decode lane (several batches in flight from one host thread) the whole loop stays
+    # ONE graph: waiting for a lane's events would serialise the lanes.  Above `_GRAPH_ROWS_MAX` rows (VAG_DECODE_GRAPH_ROWS) the
+    # loop is enqueued from one C call that follows the device's progress word (ops.beam_decode).
+    _GRAPH_ROWS_MAX = 16384
     _GRAPH_CACHE_MAX = 192
+    _GRAPH_BIG_MAX = 4           # graphs of more than 2048 rows hold hundreds of MB of private scratch each: keep few
+    _GRAPH_CHUNK = 8
 
     def _beam_decode(self, w, h0, keys, ctx, mask, K, L):
         import os
         B, T, _ = ctx.shape
-        # VAG_DECODE_GRAPH_ROWS raises the row limit: at 12 000 rows replaying the whole loop is 1-3 % faster than enqueueing it
-        # (FP32 47.7 -> 47.2 ms, bf16 33.05 -> 32.16 ms: fewer gaps between dependent launches), but a captured loop launches all L
-        # steps — with a trained model, whose search ends after a third of them, the polled launch loop wins; hence opt-in.
         rows_max = int(os.environ.get("VAG_DECODE_GRAPH_ROWS", self._GRAPH_ROWS_MAX))
         if B * K > rows_max or not w.prepared or os.environ.get("VAG_DECODE_GRAPH", "1") == "0" \
                 or torch.cuda.is_current_stream_capturing():
             return ops.beam_decode(w, h0, keys, ctx, mask, K, L)
         from collections import OrderedDict
         cache = self.__dict__.setdefault("_decode_graphs", OrderedDict())
-        key = (ops._lane, B, T, K, L, w.precision, w.prepared, ops._weights_epoch)
+        # chunk length: a chunk boundary costs ≈ 20 µs (flag copy, event, graph-to-graph launch), a returned-at-once step ≈ 20 µs too
+        chunk = 0 if ops._lane else int(os.environ.get("VAG_DECODE_CHUNK", self._GRAPH_CHUNK * (1 if B * K > 2048 else 2)))
+        key = (ops._lane, B, T, K, L, w.precision, w.prepared, chunk, ops._weights_epoch)
         st = cache.get(key)
+        if st is None and B * K > 2048:
+            # a large shape is captured when it comes back: capturing costs two extra decodes, which a one-off call (a whole test
+            # set in one batch) would never recover, while the enqueued loop is only ≈ 1-4 % slower than the replayed one there
+            seen = self.__dict__.setdefault("_decode_seen", set())
+            if key not in seen:
+                if len(seen) > 4096:
+                    seen.clear()
+                seen.add(key)
+                return ops.beam_decode(w, h0, keys, ctx, mask, K, L)
         if st is None:
             for k in [k for k in cache if k[-1] != ops._weights_epoch]:     # graphs of an older weight set hold stale pointers
                 del cache[k]
+            big = [k for k in cache if k[1] * k[3] > 2048]
+            while B * K > 2048 and len(big) >= self._GRAPH_BIG_MAX:
+                del cache[big.pop(0)]
             while len(cache) >= self._GRAPH_CACHE_MAX:
                 cache.popitem(last=False)
             dev = ctx.device
@@ -144,10 +164,26 @@ class _Seq2SeqBase(nn.Module):
             with torch.cuda.stream(side):      # warm-up outside the capture: sizes the workspace, sets kernel attributes
                 ops.beam_decode(w, st["h0"], st["keys"], st["ctx"], st["mask"], K, L, early_stop=False)
             torch.cuda.current_stream(dev).wait_stream(side)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                st["hyp"], st["hyp_len"] = ops.beam_decode(w, st["h0"], st["keys"], st["ctx"], st["mask"], K, L, early_stop=False)
-            st["graph"] = g
+            if chunk <= 0 or chunk >= L:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    st["hyp"], st["hyp_len"] = ops.beam_decode(w, st["h0"], st["keys"], st["ctx"], st["mask"], K, L, early_stop=False)
+                st["graph"] = g
+            else:
+                st["hyp"] = torch.empty(B, L, dtype=torch.int64, device=dev)
+                st["hyp_len"] = torch.empty(B, dtype=torch.int32, device=dev)
+                bounds = list(range(0, L, chunk)) + [L]
+                st["done_host"] = torch.zeros(len(bounds), dtype=torch.int32).pin_memory()
+                st["chunks"] = []
+                pool = None
+                for c in range(len(bounds)):        # the last "chunk" is the epilogue alone: [L, L)
+                    lo, hi = bounds[c], (bounds[c + 1] if c + 1 < len(bounds) else L)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, pool=pool):
+                        ops.beam_decode_steps(w, st["h0"], st["keys"], st["ctx"], st["mask"], K, L, lo, hi, st["hyp"], st["hyp_len"],
+                                              st["done_host"][c:c + 1] if hi < L or lo < L else None)
+                    pool = pool or g.pool()
+                    st["chunks"].append(g)
             st["keepalive"] = (list(ops._workspaces.values()), getattr(w, "_keepalive", None))   # raw pointers inside the graph
             cache[key] = st
         else:
@@ -156,7 +192,20 @@ class _Seq2SeqBase(nn.Module):
         st["keys"].copy_(keys)
         st["ctx"].copy_(ctx)
         st["mask"].copy_(mask)
-        st["graph"].replay()
+        if "graph" in st:
+            st["graph"].replay()
+        else:
+            graphs, flags, events = st["chunks"], st["done_host"], []
+            for c in range(len(graphs) - 1):
+                if c >= 2:
+                    events[c - 2].synchronize()        # chunk c − 1 is queued behind it: the device stays busy while the host looks
+                    if int(flags[c - 2]) != 0:
+                        break
+                graphs[c].replay()
+                ev = torch.cuda.Event()
+                ev.record()
+                events.append(ev)
+            graphs[-1].replay()                        # epilogue: back-trace, best hypothesis per sentence
         return st["hyp"], st["hyp_len"]      # static buffers: consume (or clone) before the next decode of this shape
 
     # Decode lanes (opt-in, VAG_DECODE_LANES=n): one call's batch cut into n independent sub-batches (sentences do not interact),
@@ -171,7 +220,7 @@ class _Seq2SeqBase(nn.Module):
         if K <= 1 or self.training or torch.cuda.is_current_stream_capturing() or ops._lane or not env.isdigit() or int(env) < 2:
             return None
         n = min(int(env), 8, B)
-        if n < 2 or -(-B // n) * K > self._GRAPH_ROWS_MAX:
+        if n < 2 or -(-B // n) * K > 2048:      # lanes only pay for batches that leave most of the GPU idle
             return None
         per = -(-B // n)
         return [(lo, min(B, lo + per)) for lo in range(0, B, per)]

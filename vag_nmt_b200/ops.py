@@ -471,6 +471,23 @@ def beam_decode(w: DecoderWeights, h0: torch.Tensor, keys: torch.Tensor, ctx: to
     return hyp, hyp_len
 
 
+def beam_decode_steps(w: DecoderWeights, h0: torch.Tensor, keys: torch.Tensor, ctx: torch.Tensor, mask: torch.Tensor, K: int, L: int,
+                      step_begin: int, step_end: int, hyp: torch.Tensor, hyp_len: torch.Tensor, done_host: Optional[torch.Tensor] = None,
+                      avoid_double: bool = True) -> None:
+    """Steps [step_begin, step_end) of the search ``beam_decode`` runs in one call, on the state the lane's workspace holds
+    (vag_beam_decode_steps_f32): 0 initialises, step_end >= L appends the epilogue and fills hyp [B, L] / hyp_len [B].  done_host:
+    one pinned int32 that receives the `done` flag after the range, in stream order.  Capturable in a CUDA graph."""
+    lib = _cabi.lib()
+    dev = ctx.device
+    B, T, _ = ctx.shape
+    nbytes = lib.vag_beam_decode_workspace_bytes(B, K, T, L, w.E, w.H, w.C, w.V)
+    ws = workspace(nbytes, dev)
+    with on_device(dev):
+        check(lib.vag_beam_decode_steps_f32(C.byref(w), h0.data_ptr(), keys.data_ptr(), ctx.data_ptr(), mask.data_ptr(), B, K, T, L,
+                                            1 if avoid_double else 0, step_begin, step_end, hyp.data_ptr(), hyp_len.data_ptr(), None, None,
+                                            None, ptr(done_host), ws.data_ptr(), ws.numel(), stream_ptr()))
+
+
 def greedy_decode(w: DecoderWeights, h0: torch.Tensor, keys: torch.Tensor, ctx: torch.Tensor, mask: torch.Tensor,
                   L: int) -> torch.Tensor:
     lib = _cabi.lib()
