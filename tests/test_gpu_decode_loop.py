@@ -61,6 +61,14 @@ def test_early_stop_tokens_steps_and_time():
     t_full = timed(lambda: ops.beam_decode(wf, h0f, keysf, ctxf, maskf, 12, L, early_stop=True))
     print(f"early stop after {s}/{L} steps: polled {t_poll * 1e3:.2f} ms, flag-only {t_flag * 1e3:.2f} ms, full search {t_full * 1e3:.2f} ms")
     assert t_poll < 0.5 * t_full and t_flag < 0.6 * t_full      # time follows steps_run, not max_length
+    # the model's own path replays the loop from CUDA graphs in chunks of steps and stops replaying once a chunk reports `done`
+    hyp_g, len_g = model.decode_device(b.src, b.src_lengths, b.im, 12, L)
+    assert torch.equal(hyp_g.cpu(), outs[True][0]) and torch.equal(len_g.cpu(), outs[True][1])
+    assert any("chunks" in st for st in model._decode_graphs.values())
+    t_chunks = timed(lambda: model.decode_device(b.src, b.src_lengths, b.im, 12, L))
+    t_full_g = timed(lambda: full.decode_device(b.src, b.src_lengths, b.im, 12, L))
+    print(f"graph chunks: {t_chunks * 1e3:.2f} ms with the clock, {t_full_g * 1e3:.2f} ms for the full search")
+    assert t_chunks < 0.6 * t_full_g
 
 
 def test_reference_batching_graph_replay_and_prepared_cache(monkeypatch):
