@@ -125,6 +125,7 @@ def test_bf16_twenty_step_loss_trajectory(bf16_oracle):
     print("bf16 20-step parameters: worst ‖p − p_ref‖/‖p_ref‖", worst)
     # The B200 side is not bit-reproducible from run to run (float atomics in the embedding / bias reductions): over ten runs of this
     # test the loss deviation ranged 4e-5 … 1.7e-4 and the worst parameter (always `vse_imagine.im_embedding.bias`) 4.0e-3 … 6.0e-3;
-    # one run in about twenty of the whole suite tripped the former bars (1e-2 / 2e-3), which sat within a factor two of that spread.
+    # one full-suite run of about twenty failed in this test (message not kept; eight repeats of the file then passed).  The former
+    # bars (1e-2 / 2e-3) sat within a factor two of the typical value of an error that Adam amplifies chaotically — hence 2e-2 / 5e-3.
     for name, prm in model.named_parameters():
         assert _norm_err(prm, leaves[name]) < (2e-2 if "bias" in name else 5e-3), name
