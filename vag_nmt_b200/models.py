@@ -195,17 +195,19 @@ class _Seq2SeqBase(nn.Module):
         if "graph" in st:
             st["graph"].replay()
         else:
-            graphs, flags, events = st["chunks"], st["done_host"], []
+            graphs, flags, events, stopped = st["chunks"], st["done_host"], [], False
             for c in range(len(graphs) - 1):
                 if c >= 2:
                     events[c - 2].synchronize()        # chunk c − 1 is queued behind it: the device stays busy while the host looks
                     if int(flags[c - 2]) != 0:
+                        stopped = True
                         break
                 graphs[c].replay()
                 ev = torch.cuda.Event()
                 ev.record()
                 events.append(ev)
-            graphs[-1].replay()                        # epilogue: back-trace, best hypothesis per sentence
+            if stopped:
+                graphs[-1].replay()                    # the epilogue alone (the chunk that reaches step L carries its own)
         return st["hyp"], st["hyp_len"]      # static buffers: consume (or clone) before the next decode of this shape
 
     # Decode lanes (opt-in, VAG_DECODE_LANES=n): one call's batch cut into n independent sub-batches (sentences do not interact),
