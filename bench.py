@@ -601,7 +601,7 @@ def run_ours(args):
         ws_sents, ws_im = synthetic.make_corpus(args.sentences, cfg["src_size"], cfg["im_feats_size"], seed=7 + rank)
         w_src, w_lens, w_im, _ = synthetic.pad_and_sort(ws_sents, ws_im)
         w_src, w_im = w_src.to(dev), w_im.to(dev)
-        for _ in range(3):      # a large shape is captured into graphs on its second occurrence: keep that out of the timed region
+        for _ in range(3):      # a large shape is captured into graphs when it is decoded twice in a row: keep that out of the timed region
             model.decode_device(w_src, w_lens, w_im, K, L)
         ms_w = timed(lambda: model.decode_device(w_src, w_lens, w_im, K, L), max(2, args.steps // 2))
         line["weak_scaling"] = {"value": args.sentences * world * max(2, args.steps // 2) / (ms_w / 1e3), "unit": UNIT,

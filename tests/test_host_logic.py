@@ -149,3 +149,18 @@ def test_reference_whole_module_checkpoints_load_without_the_reference(tiny_dot,
     torch.save({"x": Boom()}, evil)
     with pytest.raises(pickle.UnpicklingError):
         load_reference_stub(evil)
+
+
+def test_large_decode_shapes_are_captured_only_when_they_repeat_back_to_back():
+    """models._capture_large_now: the graph capture of a > 2048-row decode shape waits for the same shape twice in a row (one-off
+    calls and callers cycling through many large shapes keep the enqueued loop)."""
+    from conftest import build_mm
+    from vag_nmt_b200 import synthetic
+    m = build_mm(dict(synthetic.TINY), 1)
+    a, b = ("", 1000, 30, 12, 80, "fp32", True, 8, 0), ("", 1000, 31, 12, 80, "fp32", True, 8, 0)
+    assert m._capture_large_now(a) is False          # first sight: enqueue
+    assert m._capture_large_now(a) is True           # came straight back: capture
+    assert m._capture_large_now(b) is False
+    assert m._capture_large_now(a) is False          # alternating shapes never capture
+    assert m._capture_large_now(b) is False
+    assert m._capture_large_now(b) is True

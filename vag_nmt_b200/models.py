@@ -127,6 +127,15 @@ class _Seq2SeqBase(nn.Module):
     _GRAPH_BIG_MAX = 4           # graphs of more than 2048 rows hold hundreds of MB of private scratch each: keep few
     _GRAPH_CHUNK = 8
 
+    def _capture_large_now(self, key) -> bool:
+        """A shape of more than 2048 rows is captured into graphs only when the large decode just before it had the SAME shape.
+        Capturing costs two extra decodes and hundreds of MB of static inputs: a one-off call (a whole test set in one batch) would
+        never recover them, and a caller that cycles through more distinct large shapes than `_GRAPH_BIG_MAX` would capture, evict
+        and capture again on every call — both keep the enqueued loop, which is only ≈ 1-4 % slower than the replayed one there."""
+        last = self.__dict__.get("_decode_last_large")
+        self.__dict__["_decode_last_large"] = key
+        return last == key
+
     def _beam_decode(self, w, h0, keys, ctx, mask, K, L):
         import os
         B, T, _ = ctx.shape
@@ -140,15 +149,8 @@ class _Seq2SeqBase(nn.Module):
         chunk = 0 if ops._lane else int(os.environ.get("VAG_DECODE_CHUNK", self._GRAPH_CHUNK * (1 if B * K > 2048 else 2)))
         key = (ops._lane, B, T, K, L, w.precision, w.prepared, chunk, ops._weights_epoch)
         st = cache.get(key)
-        if st is None and B * K > 2048:
-            # a large shape is captured when it comes back: capturing costs two extra decodes, which a one-off call (a whole test
-            # set in one batch) would never recover, while the enqueued loop is only ≈ 1-4 % slower than the replayed one there
-            seen = self.__dict__.setdefault("_decode_seen", set())
-            if key not in seen:
-                if len(seen) > 4096:
-                    seen.clear()
-                seen.add(key)
-                return ops.beam_decode(w, h0, keys, ctx, mask, K, L)
+        if st is None and B * K > 2048 and not self._capture_large_now(key):
+            return ops.beam_decode(w, h0, keys, ctx, mask, K, L)
         if st is None:
             for k in [k for k in cache if k[-1] != ops._weights_epoch]:     # graphs of an older weight set hold stale pointers
                 del cache[k]
