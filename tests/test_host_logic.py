@@ -164,3 +164,20 @@ def test_large_decode_shapes_are_captured_only_when_they_repeat_back_to_back():
     assert m._capture_large_now(a) is False          # alternating shapes never capture
     assert m._capture_large_now(b) is False
     assert m._capture_large_now(b) is True
+
+
+def test_top2_epilogue_algorithm_is_canonical_on_ties(tmp_path):
+    """tools/top2_crosscheck.cpp restates the per-chunk top-2 of the vocabulary kernel's epilogue (csrc/linear_tc.cu) and checks it
+    against a brute-force canonical top-2 on random chunks full of exact ties; the insertion chains it replaced fail the same check
+    (the defect this harness found).  The kernel itself is pinned on the GPU by tests/test_gpu_tc.py."""
+    import shutil
+    import subprocess
+    from pathlib import Path
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    src = Path(__file__).resolve().parent.parent / "tools" / "top2_crosscheck.cpp"
+    exe = tmp_path / "top2_crosscheck"
+    subprocess.run(["g++", "-O2", "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe), "1000000"], capture_output=True, text=True, check=True).stdout.split()
+    assert out[0] == "new_vs_ref" and int(out[1]) == 0
+    assert out[2] == "old_vs_ref" and int(out[3]) > 0
